@@ -139,7 +139,12 @@ def make_contig(rng: np.random.Generator, name: str, length: int, n_reads: int, 
     starts = np.concatenate([[0], starts[starts < length]])
     blk_ps = (starts + 1 + rng.integers(0, 1000, size=starts.shape[0])).astype(np.int32)
     ps = blk_ps[np.searchsorted(starts, pos, side="right") - 1]
-    tagged = rng.random(n_reads) < tagged_frac
+    # ~10 % of phase blocks are "untaggable" (no het SNPs nearby): SVs there have no
+    # haplotagged support read at all (class 0 in sv_phasing_fn.py:194)
+    blk_dead = rng.random(starts.shape[0]) < 0.1
+    p_tag = np.where(blk_dead[np.searchsorted(starts, pos, side="right") - 1], 0.02,
+                     min(1.0, tagged_frac / 0.902))
+    tagged = rng.random(n_reads) < p_tag
     hp = rng.integers(1, 3, size=n_reads).astype(np.uint8)
     pc = np.minimum(rng.exponential(1500.0, size=n_reads), 20000.0).astype(np.int32)
     pc[rng.random(n_reads) < 0.01] = 0
@@ -180,8 +185,13 @@ def make_contig(rng: np.random.Generator, name: str, length: int, n_reads: int, 
     sv_len = np.where(sv_type == 0, -sv_abs, sv_abs).astype(np.int32)
     sv_len[sv_type == 4] = 0                      # BND: no SVLEN field
     sv_gt = rng.choice(len(GTS), size=n_svs, p=[0.55, 0.3, 0.1, 0.05]).astype(np.int8)
-    sv_refread = np.where(rng.random(n_svs) < 0.3, 0, rng.integers(0, 41, size=n_svs)).astype(np.int32)
-    het = rng.random(n_svs) < 0.7
+    het = rng.random(n_svs) < 0.6
+    # het SVs see about as many reference reads as support reads, hom SVs few or none
+    ref_het = (k * rng.uniform(0.4, 1.6, size=n_svs)).astype(np.int64)
+    ref_hom = np.where(rng.random(n_svs) < 0.6, 0, rng.integers(0, 4, size=n_svs))
+    sv_refread = np.where(het, ref_het, ref_hom)
+    noisy = rng.random(n_svs) < 0.15
+    sv_refread = np.where(noisy, rng.integers(0, 41, size=n_svs), sv_refread).astype(np.int32)
     pref = rng.integers(1, 3, size=n_svs)
     centre = np.searchsorted(pos, sv_pos)
     sup_lists = []
@@ -196,7 +206,7 @@ def make_contig(rng: np.random.Generator, name: str, length: int, n_reads: int, 
             pick = cand
         else:
             if het[i]:
-                w = np.where(tagged[cand], np.where(hp[cand] == pref[i], 0.9, 0.1), 0.5)
+                w = np.where(tagged[cand], np.where(hp[cand] == pref[i], 0.97, 0.03), 0.5)
             else:
                 w = np.full(cand.shape[0], 0.5)
             keyv = rng.random(cand.shape[0]) ** (1.0 / w)
@@ -230,8 +240,11 @@ def make_contig(rng: np.random.Generator, name: str, length: int, n_reads: int, 
 
 def make_sample(seed: int = 0, *, contigs=None, n_reads: int = 70_000, n_svs: int = 2_500,
                 dense: bool = False, chr_prefix: bool = False, empty_oneps_contig: str | None = "auto",
-                shuffle_vcf: bool = False, id_base: int = 0, **kw) -> SynthSample:
-    """Reads and SVs are spread over `contigs` proportionally to GRCh37 length."""
+                shuffle_vcf: bool = False, id_base: int = 0, bp_per_read: float | None = None,
+                **kw) -> SynthSample:
+    """Reads and SVs are spread over `contigs` proportionally to GRCh37 length.  With
+    `bp_per_read` the contigs are shrunk to keep that read density (small test cases
+    then look like 30x data: ~700 bp between read starts)."""
     rng = np.random.default_rng(seed)
     contigs = list(contigs) if contigs is not None else ["21"]
     total = float(sum(GRCH37.get(c, 50_000_000) for c in contigs))
@@ -243,6 +256,8 @@ def make_sample(seed: int = 0, *, contigs=None, n_reads: int = 70_000, n_svs: in
         length = GRCH37.get(c, 50_000_000)
         nr = int(round(n_reads * length / total))
         ns = int(round(n_svs * length / total))
+        if bp_per_read is not None:
+            length = max(int(nr * bp_per_read), 20_000)
         sc = make_contig(rng, c, length, nr, ns, base, dense=dense,
                          empty_oneps=(c == empty_oneps_contig), shuffle_vcf=shuffle_vcf, **kw)
         out.append(sc)

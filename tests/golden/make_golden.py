@@ -177,12 +177,12 @@ def main():
     dump("kat_phase_info.json.gz", kat_cases(ref))
 
     mk = synth.make_sample
-    e2e_case(ref, sp, "cutesv_3ctg", mk(1, contigs=["1", "21", "X"], n_reads=3000, n_svs=260, block_mean=2e6), "cutesv")
+    e2e_case(ref, sp, "cutesv_3ctg", mk(1, contigs=["1", "21", "X"], n_reads=3000, n_svs=260, bp_per_read=700, block_mean=1.5e5), "cutesv")
     e2e_case(ref, sp, "sniffles_chr", mk(2, contigs=["2", "22"], n_reads=2500, n_svs=200, chr_prefix=True,
-                                        block_mean=2e6), "sniffles")
+                                        bp_per_read=700, block_mean=1.5e5), "sniffles")
     e2e_case(ref, sp, "svim_shuffled", mk(3, contigs=["5", "10", "Y"], n_reads=2500, n_svs=220, shuffle_vcf=True,
-                                         block_mean=3e6), "svim", svlen_thres=40, suppread_thres=3)
-    e2e_case(ref, sp, "dense", mk(4, contigs=["20", "21"], n_reads=6000, n_svs=60, dense=True, block_mean=1e6,
+                                         bp_per_read=700, block_mean=1e5), "svim", svlen_thres=40, suppread_thres=3)
+    e2e_case(ref, sp, "dense", mk(4, contigs=["20", "21"], n_reads=6000, n_svs=60, dense=True, bp_per_read=350, block_mean=3e5,
                                  empty_oneps_contig=None), "cutesv")
 
     # chrom ordering ('10' < 'chr1' as strings), duplicate QNAME last-wins, tie on (chrom,pos)
@@ -202,7 +202,7 @@ def main():
         with open(p, "w") as f:
             f.writelines(out)
 
-    e2e_case(ref, sp, "mixed_prefix", mk(5, contigs=["1", "10"], n_reads=2000, n_svs=150, block_mean=3e6,
+    e2e_case(ref, sp, "mixed_prefix", mk(5, contigs=["1", "10"], n_reads=2000, n_svs=150, bp_per_read=700, block_mean=1e5,
                                         empty_oneps_contig=None), "cutesv", mutate=mixed_prefix)
 
 
