@@ -1,0 +1,472 @@
+// C-ABI of the sv_phasing hot path (include/duet_b200.h): handle, staging, launches, results.
+// The library owns the stream, the join table and every scratch array; callers pass plain
+// column pointers.  No CPU fallback exists: every entry point needs a CUDA device.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "phase_kernels.cuh"
+
+using namespace duet;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+enum { EV_H2D0, EV_H2D1, EV_X0, EV_K0, EV_K1, EV_K2, EV_K3, EV_K4, EV_K5, EV_K6, EV_D2H0, EV_D2H1, EV_COUNT };
+
+}  // namespace
+
+struct duet_handle {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_COUNT] = {};
+    duet_thresholds thr;
+    bool thr_dirty = true;
+    std::string err;
+    int64_t launches = 0;
+    bool staged = false, executed = false, per_kernel = false, have_h2d = false, have_d2h = false;
+
+    PhaseArgs a;                    // device view
+    std::vector<long long> h_read_off, h_sv_off;
+    long long n_slots = 0;
+    size_t oneps_smem = 0, order_smem = 0;
+
+    // staged input copies (HOST mode)
+    DevBuf in_read_key, in_read_key_hi, in_read_hp, in_read_ps, in_read_pc;
+    DevBuf in_sv_pos, in_sv_svlen, in_sv_svread, in_sv_refread, in_sv_flags, in_sv_group;
+    DevBuf in_csr_off, in_csr_key, in_csr_key_hi;
+    // descriptors, table, scratch, outputs
+    DevBuf d_read_off, d_sv_off, d_tab_off, d_tab_mask;
+    DevBuf d_table;                 // [tab_key | tab_row] cleared with one memset
+    DevBuf d_tab_hi, d_csr_slot, d_join_row, d_n_hit, d_cand, d_oneps, d_oneps_n, d_sort;
+    DevBuf d_gt, d_cls, d_ps, d_hap1, d_hap2, d_hap0, d_allhap, d_t1, d_t2, d_feat, d_order, d_n_emit;
+    DevBuf d_counts, d_status;
+};
+
+namespace {
+
+int fail(duet_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CU(h, call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(h, DUET_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+int stage(duet_handle *h, DevBuf &buf, const void *src, size_t bytes, int mem, const void **dev_view) {
+    if (src == nullptr) { *dev_view = nullptr; return DUET_OK; }
+    if (mem == DUET_MEM_DEVICE) { *dev_view = src; return DUET_OK; }
+    CU(h, buf.reserve(bytes ? bytes : 1));
+    if (bytes) CU(h, cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    *dev_view = buf.p;
+    return DUET_OK;
+}
+
+long long pow2_at_least(long long n) {
+    long long p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+int duet_abi_version(void) { return DUET_ABI_VERSION; }
+
+void duet_default_thresholds(duet_thresholds *t) {
+    if (!t) return;
+    std::memset(t, 0, sizeof(*t));
+    t->svlen_thres = 50;
+    t->suppread_thres = 2;
+    t->pc_max = 8100;
+    t->c0_sv_num_min = 4;
+    t->c2_sv_num_min = 3;
+    t->c2_hap0_min = 6;
+    t->c1_ref_num_max = 10;
+    t->c2_sv_ratio_min = 0.72;
+    t->c2_avgsc_diff_max = 1369.50;
+    t->c1_one_ratio_lo = 0.24;
+    t->c1_one_ratio_hi = 0.9;
+    t->c1_hapread_ratio = 0.75;
+    t->c1_avgsc_diff_max = 2400;
+    t->c1_two_ratio_a = 0.3;
+    t->c1_two_ratio_b = 0.45;
+    t->c1_two_ratio_c = 0.75;
+    t->c1_totsc_ratio_max = 9.72;
+}
+
+int duet_create(int device_id, duet_handle **out) {
+    if (!out) return fail(nullptr, DUET_ERR_INVALID, "duet_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, DUET_ERR_NO_DEVICE,
+                    std::string("duet_create: no CUDA device (") + cudaGetErrorString(e) +
+                        "); this library has no CPU path");
+    if (device_id < 0 || device_id >= n) return fail(nullptr, DUET_ERR_INVALID, "duet_create: bad device id");
+    duet_handle *h = new duet_handle();
+    h->device = device_id;
+    duet_default_thresholds(&h->thr);
+    std::memset(&h->a, 0, sizeof(h->a));
+    if (cudaSetDevice(device_id) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        std::string msg = std::string("duet_create: ") + cudaGetErrorString(cudaGetLastError());
+        delete h;
+        return fail(nullptr, DUET_ERR_CUDA, msg);
+    }
+    h->stream = h->own_stream;
+    for (auto &ev : h->ev) cudaEventCreate(&ev);
+    cudaFuncSetAttribute(k_oneps, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         kOnepsSmemMaxElems * (int)sizeof(long long));
+    cudaFuncSetAttribute(k_order, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         kOrderSmemMaxElems * (int)sizeof(u128));
+    if (cudaGetLastError() != cudaSuccess) {
+        delete h;
+        return fail(nullptr, DUET_ERR_CUDA, "duet_create: kernel image not loadable on this device (built for sm_100a)");
+    }
+    *out = h;
+    return DUET_OK;
+}
+
+void duet_destroy(duet_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf *bufs[] = {&h->in_read_key, &h->in_read_key_hi, &h->in_read_hp, &h->in_read_ps, &h->in_read_pc,
+                      &h->in_sv_pos, &h->in_sv_svlen, &h->in_sv_svread, &h->in_sv_refread, &h->in_sv_flags,
+                      &h->in_sv_group, &h->in_csr_off, &h->in_csr_key, &h->in_csr_key_hi, &h->d_read_off,
+                      &h->d_sv_off, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_tab_hi, &h->d_csr_slot,
+                      &h->d_join_row, &h->d_n_hit, &h->d_cand, &h->d_oneps, &h->d_oneps_n, &h->d_sort, &h->d_gt,
+                      &h->d_cls, &h->d_ps, &h->d_hap1, &h->d_hap2, &h->d_hap0, &h->d_allhap, &h->d_t1, &h->d_t2,
+                      &h->d_feat, &h->d_order, &h->d_n_emit, &h->d_counts, &h->d_status};
+    for (DevBuf *b : bufs) b->release();
+    for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+const char *duet_last_error(const duet_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int duet_set_thresholds(duet_handle *h, const duet_thresholds *t) {
+    if (!h || !t) return fail(h, DUET_ERR_INVALID, "duet_set_thresholds: NULL argument");
+    h->thr = *t;
+    h->thr_dirty = true;
+    return DUET_OK;
+}
+
+int duet_set_stream(duet_handle *h, void *cuda_stream) {
+    if (!h) return DUET_ERR_INVALID;
+    h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    return DUET_OK;
+}
+
+int duet_host_alloc(void **ptr, int64_t bytes) {
+    if (!ptr || bytes < 0) return DUET_ERR_INVALID;
+    *ptr = nullptr;
+    cudaError_t e = cudaHostAlloc(ptr, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("duet_host_alloc: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? DUET_ERR_NO_DEVICE : DUET_ERR_CUDA;
+    }
+    return DUET_OK;
+}
+
+int duet_host_free(void *ptr) {
+    if (!ptr) return DUET_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? DUET_OK : DUET_ERR_CUDA;
+}
+
+int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
+    if (!h || !in) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: NULL argument");
+    h->staged = h->executed = false;
+    const int ns = in->n_shards;
+    const long long R = in->n_reads, S = in->n_svs, J = in->n_joins;
+    if (ns < 1 || R < 0 || S < 0 || J < 0 || R >= (1ll << 31) || S >= (1ll << 31) || J >= (1ll << 30))
+        return fail(h, DUET_ERR_INVALID, "duet_phase_upload: sizes out of range");
+    if (!in->read_off || !in->sv_off || !in->csr_off)
+        return fail(h, DUET_ERR_INVALID, "duet_phase_upload: offset arrays are required");
+    if ((R && (!in->read_key || !in->read_hp || !in->read_ps || !in->read_pc)) ||
+        (S && (!in->sv_pos || !in->sv_svlen || !in->sv_svread || !in->sv_refread || !in->sv_flags)) ||
+        (J && !in->csr_key))
+        return fail(h, DUET_ERR_INVALID, "duet_phase_upload: a required column is NULL");
+    if ((in->read_key_hi == nullptr) != (in->csr_key_hi == nullptr) && R && J)
+        return fail(h, DUET_ERR_INVALID, "duet_phase_upload: read_key_hi and csr_key_hi must both be given or both NULL");
+    if (in->read_off[0] != 0 || in->sv_off[0] != 0 || in->read_off[ns] != R || in->sv_off[ns] != S)
+        return fail(h, DUET_ERR_INVALID, "duet_phase_upload: shard offsets do not span the columns");
+    for (int s = 0; s < ns; ++s)
+        if (in->read_off[s] > in->read_off[s + 1] || in->sv_off[s] > in->sv_off[s + 1])
+            return fail(h, DUET_ERR_INVALID, "duet_phase_upload: shard offsets are not monotone");
+    CU(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    CU(h, cudaEventRecord(h->ev[EV_H2D0], st));
+
+    // CSR offsets at shard boundaries size the per-shard slot ranges
+    std::vector<long long> csr_host;
+    const long long *csr = reinterpret_cast<const long long *>(in->csr_off);
+    if (in->mem == DUET_MEM_DEVICE) {
+        csr_host.resize(S + 1);
+        CU(h, cudaMemcpyAsync(csr_host.data(), in->csr_off, (S + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CU(h, cudaStreamSynchronize(st));
+        csr = csr_host.data();
+    }
+    if (csr[0] != 0 || csr[S] != J) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: csr_off does not span csr_key");
+    std::vector<int> tab_off(ns), tab_mask(ns);
+    long long slots = 0, max_sv = 0;
+    for (int s = 0; s < ns; ++s) {
+        const long long nj = csr[in->sv_off[s + 1]] - csr[in->sv_off[s]];
+        if (nj < 0) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: csr_off is not monotone");
+        const long long cap = pow2_at_least(std::max<long long>(2 * nj, 32));
+        tab_off[s] = (int)slots;
+        tab_mask[s] = (int)(cap - 1);
+        slots += cap;
+        max_sv = std::max<long long>(max_sv, in->sv_off[s + 1] - in->sv_off[s]);
+        if (slots >= (1ll << 31)) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: join table too large");
+    }
+    h->n_slots = slots;
+    h->h_read_off.assign(in->read_off, in->read_off + ns + 1);
+    h->h_sv_off.assign(in->sv_off, in->sv_off + ns + 1);
+
+    PhaseArgs &a = h->a;
+    std::memset(&a, 0, sizeof(a));
+    a.n_shards = ns; a.n_reads = (int)R; a.n_svs = (int)S; a.n_joins = (int)J;
+    const int mem = in->mem;
+    int rc;
+#define STAGE(buf, field, T, count)                                                                  \
+    if ((rc = stage(h, h->buf, in->field, sizeof(T) * (size_t)(count), mem,                          \
+                    reinterpret_cast<const void **>(&a.field))) != DUET_OK) return rc;
+    STAGE(in_read_key, read_key, uint64_t, R)
+    STAGE(in_read_key_hi, read_key_hi, uint64_t, R)
+    STAGE(in_read_hp, read_hp, uint8_t, R)
+    STAGE(in_read_ps, read_ps, int32_t, R)
+    STAGE(in_read_pc, read_pc, int32_t, R)
+    STAGE(in_sv_pos, sv_pos, int32_t, S)
+    STAGE(in_sv_svlen, sv_svlen, int32_t, S)
+    STAGE(in_sv_svread, sv_svread, int32_t, S)
+    STAGE(in_sv_refread, sv_refread, int32_t, S)
+    STAGE(in_sv_flags, sv_flags, uint8_t, S)
+    STAGE(in_sv_group, sv_group, int32_t, S)
+    STAGE(in_csr_off, csr_off, int64_t, S + 1)
+    STAGE(in_csr_key, csr_key, uint64_t, J)
+    STAGE(in_csr_key_hi, csr_key_hi, uint64_t, J)
+#undef STAGE
+    // descriptors are host arrays in both modes
+    const void *dv;
+    if ((rc = stage(h, h->d_read_off, h->h_read_off.data(), sizeof(long long) * (ns + 1), DUET_MEM_HOST, &dv))) return rc;
+    a.read_off = static_cast<const long long *>(dv);
+    if ((rc = stage(h, h->d_sv_off, h->h_sv_off.data(), sizeof(long long) * (ns + 1), DUET_MEM_HOST, &dv))) return rc;
+    a.sv_off = static_cast<const long long *>(dv);
+    if ((rc = stage(h, h->d_tab_off, tab_off.data(), sizeof(int) * ns, DUET_MEM_HOST, &dv))) return rc;
+    a.tab_off = static_cast<const int *>(dv);
+    if ((rc = stage(h, h->d_tab_mask, tab_mask.data(), sizeof(int) * ns, DUET_MEM_HOST, &dv))) return rc;
+    a.tab_mask = static_cast<const int *>(dv);
+    CU(h, cudaEventRecord(h->ev[EV_H2D1], st));
+    h->have_h2d = true;
+
+    const size_t S1 = (size_t)std::max<long long>(S, 1), J1 = (size_t)std::max<long long>(J, 1);
+    CU(h, h->d_table.reserve((size_t)slots * 12));
+    a.tab_key = h->d_table.as<unsigned long long>();
+    a.tab_row = reinterpret_cast<int *>(a.tab_key + slots);
+    CU(h, h->d_tab_hi.reserve((size_t)slots * 8));       a.tab_hi = h->d_tab_hi.as<unsigned long long>();
+    CU(h, h->d_csr_slot.reserve(J1 * 4));                a.csr_slot = h->d_csr_slot.as<int>();
+    CU(h, h->d_join_row.reserve(J1 * 4));                a.join_row = h->d_join_row.as<int>();
+    CU(h, h->d_n_hit.reserve(S1 * 4));                   a.n_hit = h->d_n_hit.as<int>();
+    CU(h, h->d_cand.reserve(S1 * 8));                    a.cand = h->d_cand.as<long long>();
+    CU(h, h->d_oneps.reserve(S1 * 4));                   a.oneps = h->d_oneps.as<int>();
+    CU(h, h->d_oneps_n.reserve((size_t)ns * 4));         a.oneps_n = h->d_oneps_n.as<int>();
+    const long long pad = pow2_at_least(std::max<long long>(max_sv, 1));
+    a.oneps_smem_elems = (int)std::min<long long>(pad, kOnepsSmemMaxElems);
+    a.order_smem_elems = (int)std::min<long long>(pad, kOrderSmemMaxElems);
+    h->oneps_smem = (size_t)a.oneps_smem_elems * sizeof(long long);
+    h->order_smem = (size_t)a.order_smem_elems * sizeof(u128);
+    if (pad > a.order_smem_elems) { CU(h, h->d_sort.reserve(S1 * 32)); a.sort_scratch = h->d_sort.as<long long>(); }
+    CU(h, h->d_gt.reserve(S1));                          a.gt = h->d_gt.as<uint8_t>();
+    CU(h, h->d_cls.reserve(S1));                         a.cls = h->d_cls.as<uint8_t>();
+    CU(h, h->d_ps.reserve(S1 * 4));                      a.ps = h->d_ps.as<int>();
+    CU(h, h->d_hap1.reserve(S1 * 4));                    a.hap1 = h->d_hap1.as<int>();
+    CU(h, h->d_hap2.reserve(S1 * 4));                    a.hap2 = h->d_hap2.as<int>();
+    CU(h, h->d_hap0.reserve(S1 * 4));                    a.hap0 = h->d_hap0.as<int>();
+    CU(h, h->d_allhap.reserve(S1 * 4));                  a.allhap = h->d_allhap.as<int>();
+    CU(h, h->d_t1.reserve(S1 * 8));                      a.totsc1 = h->d_t1.as<long long>();
+    CU(h, h->d_t2.reserve(S1 * 8));                      a.totsc2 = h->d_t2.as<long long>();
+    CU(h, h->d_feat.reserve(S1 * 8 * DUET_N_FEATURES));  a.features = h->d_feat.as<double>();
+    CU(h, h->d_order.reserve(S1 * 4));                   a.order = h->d_order.as<int>();
+    CU(h, h->d_n_emit.reserve((size_t)ns * 4));          a.n_emit = h->d_n_emit.as<int>();
+    CU(h, h->d_counts.reserve((size_t)ns * 8 * DUET_N_COUNTERS)); a.shard_counts = h->d_counts.as<long long>();
+    CU(h, h->d_status.reserve(sizeof(DevStatus)));       a.status = h->d_status.as<DevStatus>();
+    h->staged = true;
+    return DUET_OK;
+}
+
+int duet_phase_execute(duet_handle *h, int per_kernel) {
+    if (!h) return DUET_ERR_INVALID;
+    if (!h->staged) return fail(h, DUET_ERR_STATE, "duet_phase_execute: nothing staged (call duet_phase_upload)");
+    CU(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    if (h->thr_dirty) {
+        CU(h, cudaMemcpyToSymbolAsync(c_thr, &h->thr, sizeof(h->thr), 0, cudaMemcpyHostToDevice, st));
+        h->thr_dirty = false;
+    }
+    const PhaseArgs &a = h->a;
+    h->per_kernel = per_kernel != 0;
+    auto mark = [&](int ev) { if (h->per_kernel) cudaEventRecord(h->ev[ev], st); };
+    CU(h, cudaEventRecord(h->ev[EV_X0], st));
+    // every slot EMPTY (all ones) and every row -1 (all ones): one memset; S-sized features
+    // are fully rewritten only for predicted SVs, so zero them with the status word
+    CU(h, cudaMemsetAsync(h->d_table.p, 0xFF, (size_t)h->n_slots * 12, st));
+    CU(h, cudaMemsetAsync(h->d_status.p, 0, sizeof(DevStatus), st));
+    CU(h, cudaMemsetAsync(h->d_feat.p, 0, (size_t)std::max(a.n_svs, 1) * 8 * DUET_N_FEATURES, st));
+    mark(EV_K0);
+    const int sv_blocks = (a.n_svs + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (a.n_svs) {
+        k_build<<<sv_blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+        ++h->launches;
+    }
+    mark(EV_K1);
+    if (a.n_reads && a.n_joins) {
+        const int per_block = kProbeThreads * kProbePerThread;
+        k_probe<<<(a.n_reads + per_block - 1) / per_block, kProbeThreads, 0, st>>>(a);
+        ++h->launches;
+    }
+    mark(EV_K2);
+    if (a.n_svs) {
+        k_reduce<<<sv_blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+        ++h->launches;
+    }
+    mark(EV_K3);
+    k_oneps<<<a.n_shards, kSortThreads, h->oneps_smem, st>>>(a);
+    ++h->launches;
+    mark(EV_K4);
+    if (a.n_svs) {
+        k_predict<<<sv_blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+        ++h->launches;
+    }
+    mark(EV_K5);
+    k_order<<<a.n_shards, kSortThreads, h->order_smem, st>>>(a);
+    ++h->launches;
+    CU(h, cudaEventRecord(h->ev[EV_K6], st));
+    CU(h, cudaGetLastError());
+    h->executed = true;
+    return DUET_OK;
+}
+
+int duet_sync(duet_handle *h) {
+    if (!h) return DUET_ERR_INVALID;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return DUET_OK;
+}
+
+int duet_phase_download(duet_handle *h, duet_phase_output *out) {
+    if (!h || !out) return fail(h, DUET_ERR_INVALID, "duet_phase_download: NULL argument");
+    if (!h->executed) return fail(h, DUET_ERR_STATE, "duet_phase_download: nothing executed");
+    CU(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const PhaseArgs &a = h->a;
+    const size_t S = (size_t)a.n_svs, J = (size_t)a.n_joins;
+    DevStatus status;
+    CU(h, cudaEventRecord(h->ev[EV_D2H0], st));
+    CU(h, cudaMemcpyAsync(&status, a.status, sizeof(status), cudaMemcpyDeviceToHost, st));
+#define PULL(dst, src, bytes)                                                                        \
+    if ((dst) != nullptr && (bytes) != 0) CU(h, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, st));
+    PULL(out->gt, a.gt, S)
+    PULL(out->ps, a.ps, S * 4)
+    PULL(out->cls, a.cls, S)
+    PULL(out->hap1, a.hap1, S * 4)
+    PULL(out->hap2, a.hap2, S * 4)
+    PULL(out->hap0, a.hap0, S * 4)
+    PULL(out->allhap, a.allhap, S * 4)
+    PULL(out->totsc1, a.totsc1, S * 8)
+    PULL(out->totsc2, a.totsc2, S * 8)
+    PULL(out->features, a.features, S * 8 * DUET_N_FEATURES)
+    PULL(out->join_row, a.join_row, J * 4)
+    PULL(out->shard_counts, a.shard_counts, (size_t)a.n_shards * 8 * DUET_N_COUNTERS)
+    std::vector<int> n_emit(a.n_shards), order_raw;
+    CU(h, cudaMemcpyAsync(n_emit.data(), a.n_emit, sizeof(int) * a.n_shards, cudaMemcpyDeviceToHost, st));
+    if (out->order && S) {
+        order_raw.resize(S);
+        CU(h, cudaMemcpyAsync(order_raw.data(), a.order, S * 4, cudaMemcpyDeviceToHost, st));
+    }
+#undef PULL
+    CU(h, cudaEventRecord(h->ev[EV_D2H1], st));
+    CU(h, cudaStreamSynchronize(st));
+    h->have_d2h = true;
+    if (status.code != 0) {
+        char buf[160];
+        const char *what = status.code == DUET_ERR_HASH_COLLISION ? "64-bit read-name key collision"
+                         : status.code == DUET_ERR_BAD_HP ? "HP outside {1,2} in a multi-phase-set SV"
+                         : status.code == DUET_ERR_ZERO_DIVISION ? "svread + refread == 0 (or empty read list)"
+                         : "device error";
+        std::snprintf(buf, sizeof(buf), "%s (sv=%d detail=%lld)", what, status.sv, status.detail);
+        return fail(h, status.code, buf);
+    }
+    // shard regions of `order` -> one compact list
+    long long total = 0;
+    for (int s = 0; s < a.n_shards; ++s) {
+        if (out->order && S)
+            std::memcpy(out->order + total, order_raw.data() + h->h_sv_off[s], sizeof(int) * (size_t)n_emit[s]);
+        total += n_emit[s];
+    }
+    out->n_emitted = total;
+    return DUET_OK;
+}
+
+int duet_phase_run(duet_handle *h, const duet_phase_input *in, duet_phase_output *out) {
+    int rc = duet_phase_upload(h, in);
+    if (rc == DUET_OK) rc = duet_phase_execute(h, 0);
+    if (rc == DUET_OK) rc = duet_phase_download(h, out);
+    return rc;
+}
+
+int duet_get_timings(duet_handle *h, duet_timings *t) {
+    if (!h || !t) return DUET_ERR_INVALID;
+    std::memset(t, 0, sizeof(*t));
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (h->have_h2d) cudaEventElapsedTime(&t->h2d_ms, h->ev[EV_H2D0], h->ev[EV_H2D1]);
+    if (h->executed) {
+        cudaEventElapsedTime(&t->device_ms, h->ev[EV_X0], h->ev[EV_K6]);
+        if (h->per_kernel) {
+            const int seq[] = {EV_X0, EV_K0, EV_K1, EV_K2, EV_K3, EV_K4, EV_K5, EV_K6};
+            for (int i = 0; i < 7; ++i) cudaEventElapsedTime(&t->kernel_ms[i], h->ev[seq[i]], h->ev[seq[i + 1]]);
+        }
+    }
+    if (h->have_d2h) cudaEventElapsedTime(&t->d2h_ms, h->ev[EV_D2H0], h->ev[EV_D2H1]);
+    cudaGetLastError();
+    return DUET_OK;
+}
+
+int64_t duet_launch_count(const duet_handle *h) { return h ? h->launches : 0; }
+
+}  // extern "C"

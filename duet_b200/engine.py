@@ -1,0 +1,206 @@
+"""Host driver of the device path: one `PhaseEngine` per GPU wraps one C-ABI handle
+(include/duet_b200.h).  All compute happens in libduet_b200.so; nothing here falls back
+to the CPU -- without the library or a GPU the constructor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import DuetError
+from .columnar import PhaseBatch
+
+GT_TEXT = {1: "1|0", 2: "0|1", 3: "1|1"}   # sv_phasing_fn.py:217-222
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+@dataclass
+class PhaseResult:
+    gt: np.ndarray          # uint8 [S]
+    ps: np.ndarray          # int32 [S]
+    cls: np.ndarray         # uint8 [S]
+    hap1: np.ndarray
+    hap2: np.ndarray
+    hap0: np.ndarray
+    allhap: np.ndarray
+    totsc1: np.ndarray
+    totsc2: np.ndarray
+    features: np.ndarray    # float64 [6, S]
+    join_row: np.ndarray    # int32 [J]
+    order: np.ndarray       # int32 [n_emitted]
+    shard_counts: np.ndarray  # int64 [n_shards, 8]
+
+    def feature(self, name: str) -> np.ndarray:
+        return self.features[_lib.FEATURE_NAMES.index(name)]
+
+    def rows(self, batch: PhaseBatch, sample: int | None = None) -> list[dict]:
+        """The reference's return value (sv_phasing_fn.py:213-229): one dict per phased SV,
+        stably sorted by (chrom, pos).  The device order already is the reference's append order
+        sorted per shard, so the final sort only has to interleave shards."""
+        out = []
+        shard_of = np.searchsorted(batch.sv_off, self.order, side="right") - 1
+        for i, s in zip(self.order.tolist(), shard_of.tolist()):
+            if sample is not None and batch.shard_sample[s] != sample:
+                continue
+            svtype = batch.sv_type[i]
+            ln = int(batch.sv_svlen[i])
+            out.append({"ps": int(self.ps[i]), "hp": GT_TEXT[int(self.gt[i])], "chrom": batch.sv_chrom[i],
+                        "pos": int(batch.sv_pos[i]), "svlen": ln if svtype in ("INS", "DUP") else -ln,
+                        "svtype": svtype, "ref": batch.sv_ref[i], "alt": batch.sv_alt[i]})
+        out.sort(key=lambda d: (d["chrom"], d["pos"]))
+        return out
+
+
+class PhaseEngine:
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.duet_create(int(device), C.byref(h))
+        if rc != _lib.DUET_OK:
+            raise DuetError(rc, self.lib.duet_last_error(None).decode())
+        self.h = h
+        self.device = device
+        self._batch = None
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.duet_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != _lib.DUET_OK:
+            raise DuetError(rc, self.lib.duet_last_error(self.h).decode())
+
+    # -- configuration ----------------------------------------------------------------------
+    def thresholds(self) -> _lib.Thresholds:
+        t = _lib.Thresholds()
+        self.lib.duet_default_thresholds(C.byref(t))
+        return t
+
+    def set_thresholds(self, svlen_thres: int = 50, suppread_thres: int = 2, **overrides):
+        t = self.thresholds()
+        t.svlen_thres, t.suppread_thres = int(svlen_thres), int(suppread_thres)
+        for k, v in overrides.items():
+            setattr(t, k, v)
+        self._check(self.lib.duet_set_thresholds(self.h, C.byref(t)))
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self.lib.duet_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
+
+    # -- data path --------------------------------------------------------------------------
+    def upload(self, batch: PhaseBatch):
+        """Host columns -> device (copies; pinned arrays copy at PCIe speed)."""
+        inp = _lib.PhaseInput()
+        inp.mem = _lib.MEM_HOST
+        inp.n_shards, inp.n_reads, inp.n_svs, inp.n_joins = batch.n_shards, batch.n_reads, batch.n_svs, batch.n_joins
+        for name in ("read_off", "sv_off", "read_key", "read_key_hi", "read_hp", "read_ps", "read_pc", "sv_pos",
+                     "sv_svlen", "sv_svread", "sv_refread", "sv_flags", "sv_group", "csr_off", "csr_key",
+                     "csr_key_hi"):
+            arr = getattr(batch, name)
+            if arr is not None and not arr.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"{name} must be C-contiguous")
+            setattr(inp, name, _ptr(arr))
+        self._batch = batch
+        self._check(self.lib.duet_phase_upload(self.h, C.byref(inp)))
+
+    def upload_device(self, batch: PhaseBatch, dev_ptrs: dict, keep=None):
+        """Columns already resident in HBM (e.g. torch tensors): `dev_ptrs` maps column name ->
+        device address; the offset descriptors still come from `batch` (host)."""
+        inp = _lib.PhaseInput()
+        inp.mem = _lib.MEM_DEVICE
+        inp.n_shards, inp.n_reads, inp.n_svs, inp.n_joins = batch.n_shards, batch.n_reads, batch.n_svs, batch.n_joins
+        inp.read_off, inp.sv_off = _ptr(batch.read_off), _ptr(batch.sv_off)
+        for name, p in dev_ptrs.items():
+            setattr(inp, name, p)
+        self._batch = batch
+        self._keep = keep
+        self._check(self.lib.duet_phase_upload(self.h, C.byref(inp)))
+
+    def execute(self, per_kernel: bool = False):
+        self._check(self.lib.duet_phase_execute(self.h, 1 if per_kernel else 0))
+
+    def sync(self):
+        self._check(self.lib.duet_sync(self.h))
+
+    def download(self, *, join: bool = True, buffers: dict | None = None) -> PhaseResult:
+        b = self._batch
+        S, J, ns = b.n_svs, b.n_joins, b.n_shards
+        mk = (lambda name, shape, dt: buffers[name]) if buffers else (lambda name, shape, dt: np.empty(shape, dt))
+        arr = {
+            "gt": mk("gt", S, np.uint8), "ps": mk("ps", S, np.int32), "cls": mk("cls", S, np.uint8),
+            "hap1": mk("hap1", S, np.int32), "hap2": mk("hap2", S, np.int32), "hap0": mk("hap0", S, np.int32),
+            "allhap": mk("allhap", S, np.int32), "totsc1": mk("totsc1", S, np.int64),
+            "totsc2": mk("totsc2", S, np.int64), "features": mk("features", (_lib.N_FEATURES, S), np.float64),
+            "join_row": mk("join_row", J, np.int32) if join else None,
+            "order": mk("order", S, np.int32), "shard_counts": mk("shard_counts", (ns, _lib.N_COUNTERS), np.int64),
+        }
+        out = _lib.PhaseOutput()
+        for k, v in arr.items():
+            setattr(out, k, _ptr(v))
+        self._check(self.lib.duet_phase_download(self.h, C.byref(out)))
+        n = int(out.n_emitted)
+        if arr["join_row"] is None:
+            arr["join_row"] = np.zeros(0, np.int32)
+        arr["order"] = arr["order"][:n]
+        return PhaseResult(**arr)
+
+    def run(self, batch: PhaseBatch, *, join: bool = True) -> PhaseResult:
+        self.upload(batch)
+        self.execute()
+        return self.download(join=join)
+
+    def timings(self) -> dict:
+        t = _lib.Timings()
+        self._check(self.lib.duet_get_timings(self.h, C.byref(t)))
+        return {"h2d_ms": t.h2d_ms, "device_ms": t.device_ms, "d2h_ms": t.d2h_ms,
+                "kernel_ms": dict(zip(_lib.KERNEL_NAMES, list(t.kernel_ms)))}
+
+    def launch_count(self) -> int:
+        return int(self.lib.duet_launch_count(self.h))
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array over page-locked memory from duet_host_alloc; freed when the last view dies."""
+    lib = _lib.load()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    p = C.c_void_p()
+    rc = lib.duet_host_alloc(C.byref(p), n * dtype.itemsize)
+    if rc != _lib.DUET_OK:
+        raise DuetError(rc, lib.duet_last_error(None).decode())
+    buf = (C.c_uint8 * max(n * dtype.itemsize, 1)).from_address(p.value)
+    weakref.finalize(buf, lib.duet_host_free, C.c_void_p(p.value))
+    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+
+_COLUMNS = ("read_off", "sv_off", "read_key", "read_key_hi", "read_hp", "read_ps", "read_pc", "sv_pos", "sv_svlen",
+            "sv_svread", "sv_refread", "sv_flags", "sv_group", "csr_off", "csr_key", "csr_key_hi")
+
+
+def pin_batch(batch: PhaseBatch) -> PhaseBatch:
+    """Copy every column into page-locked memory (what a decoder writing into duet_host_alloc'd
+    buffers produces directly)."""
+    import dataclasses
+    new = {}
+    for name in _COLUMNS:
+        arr = getattr(batch, name)
+        if arr is None:
+            continue
+        dst = pinned_empty(arr.shape, arr.dtype)
+        dst[...] = arr
+        new[name] = dst
+    return dataclasses.replace(batch, **new)

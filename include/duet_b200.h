@@ -1,0 +1,183 @@
+/*
+ * duet_b200 -- C ABI of the B200-native sv_phasing hot path.
+ *
+ * The reference (yekaizhou/duet) has no FFI of its own; its seam for this path is the
+ * Python call
+ *     duet.sv_phasing_fn.generate_phased_callset(vcf_path, sam_home, svlen_thres,
+ *                                                suppread_thres, thread, include_all_ctgs)
+ * (src/duet/sv_phasing_fn.py:185), reached from src/duet/sv_phasing.py:17.  A maintainer
+ * binds this library with ctypes (INTEGRATION.md shows the stub); the entry points below
+ * are what that binding calls after the host has decoded the haplotagged alignments and
+ * the SV VCF into columns.  Plain pointers and sizes only: no Python, torch or C++ types.
+ *
+ * Units follow the reference's domain:
+ *   shard   one (sample, contig) pair -- every dict / set / loop of the reference is per
+ *           contig (sv_phasing_fn.py:15-18,195-212), so shards never exchange data
+ *   read    one haplotagged alignment row kept by read_hap_bam (sv_phasing_fn.py:28-29)
+ *   SV      one VCF record kept by parse_vcf for a contig (read_file.py:30)
+ *   join    one support-read name of one SV (an RNAMES / READS entry, read_file.py:48-55)
+ *
+ * All functions return DUET_OK (0) or a DUET_ERR_* code; duet_last_error() gives the text.
+ * There is no CPU fallback: without a usable CUDA device duet_create() fails.
+ * One host thread per handle; handles on different GPUs are independent.
+ */
+#ifndef DUET_B200_H
+#define DUET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DUET_ABI_VERSION 1
+
+enum {
+    DUET_OK = 0,
+    DUET_ERR_INVALID = 1,        /* bad argument / inconsistent offsets                       */
+    DUET_ERR_CUDA = 2,           /* a CUDA call failed (text in duet_last_error)              */
+    DUET_ERR_NO_DEVICE = 3,      /* no CUDA device: the product path refuses to run           */
+    DUET_ERR_HASH_COLLISION = 4, /* two different names share a 64-bit key (hi words differ)  */
+    DUET_ERR_BAD_HP = 5,         /* HP not in {1,2} inside a multi-phase-set SV: the reference
+                                    raises KeyError there (sv_phasing_fn.py:96)               */
+    DUET_ERR_ZERO_DIVISION = 6,  /* svread + refread == 0 (sv_phasing_fn.py:123)              */
+    DUET_ERR_STATE = 7           /* call order violated (execute before upload, ...)          */
+};
+
+enum { DUET_MEM_HOST = 0, DUET_MEM_DEVICE = 1 };
+
+/* sv_flags bits */
+enum { DUET_SV_GT_MISSING = 1 };   /* GT == "./." (sv_phasing_fn.py:190) */
+
+/* value of `cls` for SVs removed by the svlen / support / GT filter (sv_phasing_fn.py:189-190) */
+#define DUET_CLS_FILTERED 255
+
+/* The literals of sv_phasing_fn.py:76,146-177, kept together so they live in __constant__
+ * memory.  duet_default_thresholds() fills in the reference's values. */
+typedef struct duet_thresholds {
+    int32_t svlen_thres;        /* -s, default 50  (utils.py)                          */
+    int32_t suppread_thres;     /* -r, default 2                                        */
+    int32_t pc_max;             /* 8100   :76,88,201                                    */
+    int32_t c0_sv_num_min;      /* 4      :146                                          */
+    int32_t c2_sv_num_min;      /* 3      :151                                          */
+    int32_t c2_hap0_min;        /* 6      :154                                          */
+    int32_t c1_ref_num_max;     /* 10     :172                                          */
+    int32_t _pad;
+    double c2_sv_ratio_min;     /* 0.72   :149                                          */
+    double c2_avgsc_diff_max;   /* 1369.5 :150                                          */
+    double c1_one_ratio_lo;     /* 0.24   :160                                          */
+    double c1_one_ratio_hi;     /* 0.9    :162                                          */
+    double c1_hapread_ratio;    /* 0.75   :163,166                                      */
+    double c1_avgsc_diff_max;   /* 2400   :163,166                                      */
+    double c1_two_ratio_a;      /* 0.3    :169                                          */
+    double c1_two_ratio_b;      /* 0.45   :171                                          */
+    double c1_two_ratio_c;      /* 0.75   :176                                          */
+    double c1_totsc_ratio_max;  /* 9.72   :177                                          */
+} duet_thresholds;
+
+/* Columnar input of one call: any number of shards, laid out back to back.
+ *
+ * Reads of shard s are rows [read_off[s], read_off[s+1]) IN FILE ORDER (a later row with the
+ * same name overrides an earlier one, sv_phasing_fn.py:29).  SVs of shard s are
+ * [sv_off[s], sv_off[s+1]) in VCF order; the support reads of SV i are CSR entries
+ * [csr_off[i], csr_off[i+1]) in RNAMES order.
+ *
+ * read_off / sv_off are ALWAYS host pointers (tiny descriptors).  Every other array lives
+ * where `mem` says: DUET_MEM_HOST (pageable or pinned; duet_phase_upload copies it) or
+ * DUET_MEM_DEVICE (used in place, must stay valid and unchanged until the next upload).
+ * `*_key_hi` may both be NULL: then 64-bit key equality is trusted (no collision check).
+ * `sv_group` may be NULL (= all zero).
+ */
+typedef struct duet_phase_input {
+    int32_t mem;                 /* DUET_MEM_HOST | DUET_MEM_DEVICE                              */
+    int32_t n_shards;
+    int64_t n_reads;             /* R < 2^31                                                     */
+    int64_t n_svs;               /* S < 2^31                                                     */
+    int64_t n_joins;             /* J < 2^30                                                     */
+    const int64_t *read_off;     /* [n_shards+1] host                                            */
+    const int64_t *sv_off;       /* [n_shards+1] host                                            */
+    const uint64_t *read_key;    /* [R] low 64 bits of the name hash, never 0xFFFF...F           */
+    const uint64_t *read_key_hi; /* [R] or NULL                                                  */
+    const uint8_t *read_hp;      /* [R] HP tag                                                   */
+    const int32_t *read_ps;      /* [R] PS tag                                                   */
+    const int32_t *read_pc;      /* [R] PC tag                                                   */
+    const int32_t *sv_pos;       /* [S]                                                          */
+    const int32_t *sv_svlen;     /* [S] |SVLEN| (sv_phasing_fn.py:62)                            */
+    const int32_t *sv_svread;    /* [S] SUPPORT / RE / SR value (read_file.py:40-47)             */
+    const int32_t *sv_refread;   /* [S] column [15] of parse_vcf (read_file.py:56-76)            */
+    const uint8_t *sv_flags;     /* [S] DUET_SV_* bits                                           */
+    const int32_t *sv_group;     /* [S] or NULL: rank of the SV's CHROM string inside its shard  */
+    const int64_t *csr_off;      /* [S+1]                                                        */
+    const uint64_t *csr_key;     /* [J]                                                          */
+    const uint64_t *csr_key_hi;  /* [J] or NULL                                                  */
+} duet_phase_input;
+
+#define DUET_N_FEATURES 6        /* hapread_ratio, sv_ratio, hap1_avgsc, hap2_avgsc, totsc_ratio,
+                                    hap_avgsc_diff (sv_phasing_fn.py:112-132)                    */
+#define DUET_N_COUNTERS 8        /* per shard: n_sv, n_kept, n_emitted, n_1|0, n_0|1, n_1|1,
+                                    n_joins, n_hits                                              */
+
+/* Caller-allocated HOST arrays filled by duet_phase_download.  Any pointer may be NULL
+ * (that output is skipped).  Values of SVs with cls == DUET_CLS_FILTERED are unspecified
+ * except gt == 0. */
+typedef struct duet_phase_output {
+    uint8_t *gt;           /* [S] 0 dropped, 1 "1|0", 2 "0|1", 3 "1|1" (sv_phasing_fn.py:213-222)    */
+    int32_t *ps;           /* [S] phase set written for the SV (f['ps'])                             */
+    uint8_t *cls;          /* [S] number of distinct PS among joined reads, capped at 2 (:192-194)   */
+    int32_t *hap1, *hap2, *hap0, *allhap;   /* [S] each                                              */
+    int64_t *totsc1, *totsc2;               /* [S] each                                              */
+    double *features;      /* [DUET_N_FEATURES][S] planes                                            */
+    int32_t *join_row;     /* [J] row (into the read columns) each support read joined to, -1 = miss */
+    int32_t *order;        /* [S] first n_emitted: SV indices, shard by shard, each shard sorted by
+                              (group, pos, class, VCF order) = the reference's stable order (:206-229) */
+    int64_t *shard_counts; /* [n_shards][DUET_N_COUNTERS]                                            */
+    int64_t n_emitted;     /* out                                                                    */
+} duet_phase_output;
+
+typedef struct duet_timings {
+    float h2d_ms;          /* upload: host -> device copies                       */
+    float device_ms;       /* all kernels of one execute                          */
+    float d2h_ms;          /* download                                            */
+    float kernel_ms[8];    /* init, build, probe, reduce, oneps, predict, order, - */
+} duet_timings;
+
+typedef struct duet_handle duet_handle;
+
+int duet_abi_version(void);
+void duet_default_thresholds(duet_thresholds *t);
+
+int duet_create(int device_id, duet_handle **out);
+void duet_destroy(duet_handle *h);
+const char *duet_last_error(const duet_handle *h);   /* h may be NULL: error of the last failed duet_create */
+
+int duet_set_thresholds(duet_handle *h, const duet_thresholds *t);
+
+/* Use this stream (a cudaStream_t / CUstream, e.g. torch's current stream) for all work of the
+ * handle; NULL = the handle's own non-blocking stream (default). */
+int duet_set_stream(duet_handle *h, void *cuda_stream);
+
+/* Stage the columns on the device (copy for HOST, alias for DEVICE) and size the join table. */
+int duet_phase_upload(duet_handle *h, const duet_phase_input *in);
+/* Launch the whole path on the staged columns (asynchronous; may be called repeatedly).
+ * `per_kernel` != 0 records an event after every kernel (for duet_get_timings). */
+int duet_phase_execute(duet_handle *h, int per_kernel);
+/* Wait for the device, turn device-side error flags into a status, copy results out. */
+int duet_phase_download(duet_handle *h, duet_phase_output *out);
+/* upload + execute + download. */
+int duet_phase_run(duet_handle *h, const duet_phase_input *in, duet_phase_output *out);
+
+/* Page-locked host memory for the columns (so uploads run at full PCIe speed and decoders can
+ * write straight into it).  Usable without a handle; fails with DUET_ERR_NO_DEVICE on a box
+ * without a GPU. */
+int duet_host_alloc(void **ptr, int64_t bytes);
+int duet_host_free(void *ptr);
+
+int duet_sync(duet_handle *h);
+int duet_get_timings(duet_handle *h, duet_timings *t);
+/* Number of kernels this library launched on the handle since creation (bench "gpu_launches"). */
+int64_t duet_launch_count(const duet_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DUET_B200_H */

@@ -87,7 +87,7 @@ def haplotag_tables(sam_home: str, thread: int, include_all_ctgs: bool) -> list[
 
 class SvRecord:
     __slots__ = ("fields", "chrom", "pos", "ref", "alt", "svlen", "svtype", "svread",
-                 "names", "gt", "refread", "altread", "reads")
+                 "names", "gt", "refread", "altread", "reads", "index")
 
     def __init__(self, fields):
         self.fields = fields
@@ -96,6 +96,7 @@ class SvRecord:
         self.ref = fields[3]
         self.alt = fields[4]
         self.reads = None
+        self.index = -1       # position in contig-major order (set by join_support_reads)
 
 
 def _first_with(info: list[str], needles) -> str | None:
@@ -185,6 +186,7 @@ def join_support_reads(per_contig: list[list[SvRecord]], tables: list[dict]) -> 
                 joined.append((nm,) if tag is None else (nm, tag[0], tag[1], tag[2]))
             r.reads = joined
             r.svlen = abs(r.svlen)
+            r.index = len(flat)
             flat.append(r)
     return flat
 

@@ -1,0 +1,222 @@
+"""Parity of the CUDA path (through the C-ABI) against the oracle port and the golden
+fixtures recorded from the unmodified reference.  Bit-exact: genotype, PS, class, counts,
+score sums, join rows, AND the fp64 features (same IEEE operations in the same order)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from duet_b200 import _lib, synth
+from duet_b200.columnar import from_synth
+from duet_b200.engine import DuetError, PhaseEngine, pin_batch
+from oracle import synth_adapter
+from util_batches import BatchBuilder, assert_matches_trace, kat_class, kat_shard
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    eng = PhaseEngine(0)
+    yield eng
+    eng.close()
+
+
+def run_and_compare(engine, sample, svlen=50, supp=2, **kw):
+    batch = from_synth(sample, **kw)
+    engine.set_thresholds(svlen, supp)
+    res = engine.run(batch)
+    trace = []
+    rows, flat = synth_adapter.phase_sample(sample, svlen, supp, trace)
+    assert_matches_trace(res, batch, trace, flat)
+    assert res.rows(batch) == rows
+    # counters: n_sv, n_kept, n_emitted, genotype split, joins, hits
+    c = res.shard_counts.sum(axis=0)
+    assert c[0] == batch.n_svs and c[2] == len(rows) == res.order.shape[0]
+    assert c[3] == sum(r["hp"] == "1|0" for r in rows) and c[4] == sum(r["hp"] == "0|1" for r in rows)
+    assert c[5] == sum(r["hp"] == "1|1" for r in rows)
+    assert c[6] == batch.n_joins and c[7] == int((res.join_row >= 0).sum())
+    return batch, res, rows
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_multi_contig_small(engine, seed):
+    s = synth.make_sample(seed, contigs=["1", "2", "7", "21", "X", "Y"], n_reads=12000, n_svs=900,
+                          bp_per_read=700, block_mean=1.2e5, shuffle_vcf=(seed % 2 == 1),
+                          chr_prefix=(seed >= 2))
+    _, _, rows = run_and_compare(engine, s)
+    assert len(rows) > 100
+    assert {r["hp"] for r in rows} == {"1|0", "0|1", "1|1"}
+
+
+def test_thresholds_change_result(engine):
+    s = synth.make_sample(5, contigs=["3", "4"], n_reads=6000, n_svs=500, bp_per_read=700, block_mean=1e5)
+    _, _, rows_a = run_and_compare(engine, s, 50, 2)
+    _, _, rows_b = run_and_compare(engine, s, 500, 12)
+    assert 0 < len(rows_b) < len(rows_a)
+
+
+def test_dense_support_lists(engine):
+    s = synth.make_sample(6, contigs=["20", "21"], n_reads=30000, n_svs=300, dense=True, bp_per_read=350,
+                          block_mean=3e5, empty_oneps_contig=None)
+    batch, res, _ = run_and_compare(engine, s)
+    assert np.diff(batch.csr_off).max() > 500
+
+
+def test_c1_shape_chr21(engine):
+    """BASELINE.json configs[0]: chr21 demo shape (70 k reads, 2.5 k SVs)."""
+    batch, res, rows = run_and_compare(engine, synth.config_c1(0))
+    assert batch.n_svs == 2500 and len(rows) > 800
+
+
+def test_without_hi_words(engine):
+    s = synth.make_sample(8, contigs=["1", "2"], n_reads=4000, n_svs=300, bp_per_read=700, block_mean=1e5)
+    run_and_compare(engine, s, with_hi=False)
+
+
+def test_pinned_input_same_result(engine):
+    s = synth.make_sample(9, contigs=["1", "2"], n_reads=4000, n_svs=300, bp_per_read=700, block_mean=1e5)
+    batch = from_synth(s)
+    engine.set_thresholds(50, 2)
+    a = engine.run(batch)
+    b = engine.run(pin_batch(batch))
+    for k in ("gt", "ps", "cls", "hap1", "hap2", "join_row", "order"):
+        assert np.array_equal(getattr(a, k), getattr(b, k))
+    # execute is repeatable on staged columns (the bench loop relies on it)
+    engine.execute(); engine.execute()
+    c = engine.download()
+    assert np.array_equal(a.gt, c.gt) and np.array_equal(a.ps, c.ps) and np.array_equal(a.order, c.order)
+
+
+def test_golden_kat_on_device(engine):
+    """Every known-answer case recorded from the reference's get_phase_info / predict_hp whose
+    class is reachable through the pipeline, run as one shard each in ONE device call."""
+    cases = [c for c in load_golden("kat_phase_info.json.gz") if "raises" not in c and kat_class(c) == c["ps_num"]]
+    assert len(cases) > 900
+    bb = BatchBuilder()
+    for k, c in enumerate(cases):
+        kat_shard(bb, c, f"k{k}")
+    batch = bb.build()
+    engine.set_thresholds(0, 0)
+    res = engine.run(batch)
+    outcomes = set()
+    for k, c in enumerate(cases):
+        i = int(batch.sv_off[k])
+        assert res.cls[i] == c["ps_num"]
+        assert res.gt[i] == c["pred"], (c, res.gt[i])
+        assert res.ps[i] == c["ps"], (c, res.ps[i])
+        f = c["features"]
+        assert (res.hap1[i], res.hap2[i], res.hap0[i], res.allhap[i]) == (f["hap1"], f["hap2"], f["hap0"], f["allhap"])
+        assert (res.totsc1[i], res.totsc2[i]) == (f["hap1_totsc"], f["hap2_totsc"])
+        for name in _lib.FEATURE_NAMES:
+            assert float(res.feature(name)[i]) == float(f[name]), (name, c)
+        outcomes.add((c["ps_num"], c["pred"]))
+    assert outcomes >= {(0, 0), (0, 3), (1, 0), (1, 1), (1, 2), (1, 3), (2, 0), (2, 3)}
+
+
+def test_golden_kat_errors(engine):
+    """KeyError (:96) and ZeroDivisionError (:123) of the reference surface as status codes."""
+    want = {"KeyError": _lib.ERR_BAD_HP, "ZeroDivisionError": _lib.ERR_ZERO_DIVISION}
+    cases = [c for c in load_golden("kat_phase_info.json.gz") if "raises" in c]
+    assert {c["raises"] for c in cases} == set(want)
+    engine.set_thresholds(0, 0)
+    for k, c in enumerate(cases):
+        bb = BatchBuilder()
+        if c["raises"] == "KeyError":      # force class 2 with an extra phase set
+            c = dict(c, reads=c["reads"] + [["x", 1, 4242, 0]])
+        kat_shard(bb, c, f"e{k}")
+        with pytest.raises(DuetError) as ei:
+            engine.run(bb.build())
+        assert ei.value.code == want[c["raises"]]
+
+
+def test_last_row_wins_and_duplicate_names(engine):
+    """duplicate QNAME -> the LAST row's tag (:29); a name listed twice counts twice (:46-48);
+    the same name in another contig's BAM is a different read."""
+    bb = BatchBuilder()
+    bb.shard([("dup", 1, 500, 100), ("q2", 1, 500, 7), ("dup", 2, 500, 300), ("solo", 1, 500, 1)],
+             [dict(pos=10, svread=5, refread=0, names=["dup", "q2", "dup", "ghost"]),
+              dict(pos=20, svread=5, refread=0, names=["solo"])], contig="1")
+    bb.shard([("dup", 1, 900, 11)], [dict(pos=10, svread=5, refread=0, names=["dup", "q2"])], contig="2")
+    batch = bb.build()
+    engine.set_thresholds(0, 0)
+    res = engine.run(batch)
+    assert res.join_row.tolist() == [2, 1, 2, -1, 3, 4, -1]
+    assert (res.hap1[0], res.hap2[0], res.totsc1[0], res.totsc2[0]) == (1, 2, 7, 600)
+    assert res.feature("hapread_ratio")[0] == 3 / 4
+    assert res.ps[2] == 900 and res.hap1[2] == 1
+
+
+def test_empty_oneps_contig_and_empty_shards(engine):
+    bb = BatchBuilder()
+    bb.shard([], [], contig="1")                                            # nothing at all
+    bb.shard([("a", 1, 100, 9000)], [dict(pos=5, svread=9, refread=0, names=["a", "b"])], contig="2")  # pc>8100 only
+    bb.shard([("c", 1, 100, 5)], [], contig="3")                            # reads but no SVs
+    bb.shard([], [dict(pos=5, svread=9, refread=0, names=["zz"])], contig="4")   # SVs but no reads
+    bb.shard([("d", 2, 300, 5)], [dict(pos=5, svread=9, refread=0, names=["d"])], contig="5")
+    batch = bb.build()
+    engine.set_thresholds(0, 0)
+    res = engine.run(batch)
+    assert res.gt.tolist() == [0, 0, 3]
+    assert res.order.tolist() == [2]
+    assert res.shard_counts[:, 2].tolist() == [0, 0, 0, 0, 1]
+
+
+def test_tie_order_and_filters(engine):
+    """Rows tying on (chrom, pos) come out class 0 first, then class 1, then class 2, VCF order
+    inside a class (:206-229); svlen / support / GT filters (:189-190)."""
+    reads = [("a", 1, 100, 5), ("b", 2, 100, 5), ("c", 1, 200, 5), ("h", 1, 200, 0)]
+    svs = [dict(pos=700, svread=9, refread=0, names=["a", "c"]),            # class 2
+           dict(pos=700, svread=9, refread=0, names=["a", "b"]),            # class 1
+           dict(pos=700, svread=9, refread=0, names=["nope"]),              # class 0
+           dict(pos=700, svread=9, refread=0, names=["a"]),                 # class 1 (later in VCF)
+           dict(pos=600, svread=9, refread=0, names=["h"]),                 # pins 200 into the one-PS set
+           dict(pos=1, svread=9, refread=0, names=["a"], svlen=10),         # svlen filter
+           dict(pos=1, svread=1, refread=0, names=["a"]),                   # support filter
+           dict(pos=1, svread=9, refread=0, names=["a"], gt_missing=True)]  # GT ./.
+    batch = BatchBuilder().shard(reads, svs).build()
+    engine.set_thresholds(50, 2)
+    res = engine.run(batch)
+    assert res.cls.tolist() == [2, 1, 0, 1, 1, 255, 255, 255]
+    assert res.order.tolist() == [4, 2, 1, 3, 0]
+
+
+def test_more_than_32_phase_sets_in_one_sv(engine):
+    """The shared-memory distinct-PS list holds 32 entries; beyond that the exact slow path runs."""
+    rng = np.random.default_rng(0)
+    pss = list(range(1000, 1000 + 45 * 10, 10))
+    reads, names = [], []
+    for k in range(400):
+        ps = int(rng.choice(pss)) if k >= 45 else pss[k]
+        reads.append((f"r{k}", int(rng.integers(1, 3)), ps, int(rng.integers(0, 9000))))
+        names.append(f"r{k}")
+    helpers, hsv = [], []
+    for k, ps in enumerate(pss[3:]):
+        helpers.append((f"h{k}", 1, ps, 0))
+        hsv.append(dict(pos=1, svread=2, refread=5, names=[f"h{k}"]))
+    bb = BatchBuilder().shard(reads + helpers, [dict(pos=1234, svread=40, refread=3, names=names)] + hsv)
+    batch = bb.build()
+    engine.set_thresholds(0, 0)
+    res = engine.run(batch)
+    from oracle import ref_port
+    joined = [(n, h, p, c) for (n, h, p, c) in reads]
+    pred, ps, f = ref_port.predict(joined, 1234, 40, 3, 2, set(pss[3:]))
+    assert (res.gt[0], res.ps[0], res.hap1[0], res.hap2[0], res.hap0[0], res.allhap[0]) == \
+           (pred, ps, f["hap1"], f["hap2"], f["hap0"], f["allhap"])
+    assert (res.totsc1[0], res.totsc2[0]) == (f["hap1_totsc"], f["hap2_totsc"])
+
+
+def test_hash_collision_is_reported(engine):
+    bb = BatchBuilder().shard([("a", 1, 100, 5), ("b", 1, 100, 5)],
+                              [dict(pos=5, svread=9, refread=0, names=["a", "b"])])
+    batch = bb.build()
+    batch.read_key[1] = batch.read_key[0]          # 'b' now collides with 'a' on the 64-bit key only
+    engine.set_thresholds(0, 0)
+    with pytest.raises(DuetError) as ei:
+        engine.run(batch)
+    assert ei.value.code == _lib.ERR_HASH_COLLISION
+
+
+def test_big_shard_uses_global_sort_scratch(engine):
+    """One shard with more SVs than the shared-memory sort tiles hold (16384 / 8192)."""
+    s = synth.make_sample(12, contigs=["1"], n_reads=60000, n_svs=20000, bp_per_read=700, block_mean=2e5)
+    run_and_compare(engine, s)
