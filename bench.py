@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the sv_phasing hot path (BASELINE.json metric: SVs phased/sec & support-read
+joins/sec at 1/2/4/8 B200 vs the host-CPU reference).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c4|c1] [--impl reference]
+
+One "step" = one pass of the whole device path (join table build -> read stream/probe ->
+per-SV reductions -> one-PS sets -> decision tree -> emission order) over one synthetic WGS
+sample.  N>1: one process per GPU (torchrun), rank r owns sample r of an N-sample cohort --
+shards are (sample, contig) pairs and never exchange data, so scaling is weak and no
+collective sits on the data path; per-shard counters are all-gathered once after the timed
+region (latency reported as gather_ms).
+
+Timing: CUDA events on the stream the kernels are launched on, one event pair per step, L2
+flushed (512 MiB memset, outside the event pair) between steps; max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "SVs phased/sec (support-read joins/sec in joins_per_sec)"
+WORKLOADS = {
+    "c1": "C1 chr21 demo shape (70k ONT reads, 2.5k SVs)",
+    "c2": "C2 synthetic GRCh37 WGS 30x ONT (4.5M reads, 25k cuteSV SVs)",
+    "c4": "C4 synthetic WGS 60x ONT dense support lists (9M reads, 30k SVs)",
+}
+CPU_SAMPLE_CONTIGS = ["17", "18", "19", "20", "21", "22"]      # 12.3 % of GRCh37: bounded CPU sample
+
+
+def make_sample(workload: str, seed: int):
+    from duet_b200 import synth
+    return {"c1": synth.config_c1, "c2": synth.config_c2, "c4": synth.config_c4}[workload](seed)
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks (pynvml, sampled while the timed loops run)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._active = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
+
+    def _loop(self):
+        while not self._stop.is_set():
+            if self.nv is not None and self._active.is_set():
+                try:
+                    self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.dev, self.nv.NVML_CLOCK_SM))
+                    bits = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
+                    for b, name in self.REASONS.items():
+                        if bits & b and name != "gpu_idle":
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        self._active.set()
+        return self
+
+    def __exit__(self, *a):
+        self._active.clear()
+
+    def summary(self):
+        self._stop.set()
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU legs (the oracle port; the only place bench.py executes oracle/)
+# ----------------------------------------------------------------------------------------------
+class CpuPort:
+    """Post-decode reference compute on ONE host core: QNAME dict build from already-split rows,
+    the support-read join, classification, one-PS sets, predict_hp over every kept SV and the final
+    sort -- the same span the device path covers.  Bounded sample = contigs 17-22 of the workload."""
+
+    def __init__(self, workload: str, seed: int):
+        from duet_b200 import synth
+        from oracle import ref_port, synth_adapter
+        self.ref_port = ref_port
+        full = make_sample(workload, seed)
+        keep = [c for c in full.contigs if c.name in CPU_SAMPLE_CONTIGS] or full.contigs
+        sub = synth.SynthSample(keep, chr_prefix=full.chr_prefix, seed=seed)
+        self.names, tables, self.per_contig = synth_adapter.tables_and_records(sub)   # untimed: text -> fields
+        self.rows_in = [list(t.items()) for t in tables]
+        self.n_svs, self.n_joins, self.n_reads = sub.n_svs, sub.n_joins, sub.n_tagged
+        self.sample = (f"contigs {','.join(c.name for c in keep)} of {workload} seed {seed}: {sub.n_tagged} tagged "
+                       f"reads, {sub.n_svs} SVs, {sub.n_joins} joins; post-decode compute (dict build + join + "
+                       f"classify + predict + sort) on 1 core")
+
+    def step(self) -> float:
+        t0 = time.perf_counter()
+        tables = []
+        for items in self.rows_in:                 # dict insert per kept alignment row (:26-29)
+            d = {}
+            for nm, tag in items:
+                d[nm] = tag
+            tables.append(d)
+        flat = self.ref_port.join_support_reads(self.per_contig, tables)
+        self.rows = self.ref_port.phase_records(flat, self.names, 50, 2)
+        return time.perf_counter() - t0
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cpu = CpuPort(args.workload, 0)
+    times = [cpu.step() for _ in range(args.warmup + args.steps)][args.warmup:]
+    sec = float(np.mean(times))
+    val = cpu.n_svs / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "SV/s", "joins_per_sec": cpu.n_joins / sec,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/f64 (CPython)",
+        "data": "synthetic", "config": {"workload": WORKLOADS[args.workload], "sample": cpu.sample},
+        "cpu_baseline": {"value": val, "unit": "SV/s", "cores": 1, "kind": "port", "sample": cpu.sample},
+        "e2e": {"value": val, "unit": "SV/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from duet_b200.columnar import from_synth
+    from duet_b200.engine import PhaseEngine, pin_batch
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    t0 = time.perf_counter()
+    sample = make_sample(args.workload, seed=rank)
+    batch = pin_batch(from_synth(sample, with_text=False))
+    gen_s = time.perf_counter() - t0
+
+    eng = PhaseEngine(local)
+    stream = torch.cuda.Stream(device=local)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_thresholds(50, 2)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+    clocks = ClockSampler(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_steps(n, per_kernel=False):
+        """n steps on staged columns; returns per-step device ms (events on the launch stream)."""
+        evs = []
+        with torch.cuda.stream(stream):
+            for _ in range(n):
+                flush.zero_()                               # evict the previous step from L2
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                eng.execute(per_kernel)
+                b.record(stream)
+                evs.append((a, b))
+                if per_kernel:
+                    stream.synchronize()
+                    kt = eng.timings()["kernel_ms"]
+                    for k, v in kt.items():
+                        ksum[k] = ksum.get(k, 0.0) + v
+        stream.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    ksum: dict = {}
+    # ---- device-resident throughput ("value") ----
+    eng.upload(batch)
+    eng.sync()
+    timed_steps(args.warmup)
+    launches0 = eng.launch_count()
+    barrier()
+    with clocks:
+        step_ms = timed_steps(args.steps)
+    barrier()
+    launches = eng.launch_count() - launches0
+    res = eng.download()
+    total_ms = float(np.sum(step_ms))
+
+    # ---- per-kernel durations for the roofline (same loop, one event after each kernel) ----
+    ksum.clear()
+    timed_steps(args.steps, per_kernel=True)
+    kernel_ms = {k: v / args.steps for k, v in ksum.items()}
+
+    # ---- end to end through the public API: pinned host columns -> results on the host ----
+    for _ in range(args.warmup):
+        eng.run(batch)
+    barrier()
+    with clocks:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r2 = eng.run(batch)
+        e2e_s = time.perf_counter() - t0
+    barrier()
+    tm = eng.timings()
+    assert np.array_equal(r2.gt, res.gt) and np.array_equal(r2.ps, res.ps)
+    d2h_bytes = sum(getattr(r2, k).nbytes for k in ("gt", "ps", "cls", "hap1", "hap2", "hap0", "allhap", "totsc1",
+                                                    "totsc2", "features", "join_row", "shard_counts")) + 4 * batch.n_svs
+
+    # ---- cross-rank: max time, summed units; counters gathered once (not on the data path) ----
+    n_svs, n_joins = batch.n_svs, batch.n_joins
+    gather_ms = None
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = float(t[0]), float(t[1])
+        u = torch.tensor([n_svs, n_joins], dtype=torch.int64, device=f"cuda:{local}")
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+        n_svs, n_joins = int(u[0]), int(u[1])
+        counts = torch.from_numpy(res.shard_counts.sum(axis=0)).to(f"cuda:{local}")
+        out = [torch.empty_like(counts) for _ in range(world)]
+        dist.all_gather(out, counts)                        # warm
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        dist.all_gather(out, counts)
+        b.record()
+        torch.cuda.synchronize()
+        gather_ms = a.elapsed_time(b)
+        all_counts = torch.stack(out).sum(0).tolist()
+    else:
+        all_counts = res.shard_counts.sum(axis=0).tolist()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        ms = total_ms / args.steps
+        alg = batch.algorithmic_bytes()
+        dom = max(kernel_ms, key=kernel_ms.get)
+        # algorithmic bytes of each kernel of THIS design
+        kbytes = {"init": 0, "build": 24 * batch.n_joins, "probe": 8 * batch.n_reads,
+                  "reduce": 4 * batch.n_joins + 64 * batch.n_svs, "oneps": 12 * batch.n_svs,
+                  "predict": 64 * batch.n_svs, "order": 16 * batch.n_svs}
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(args.workload, {}).get(dom)
+        except Exception:
+            pass
+        ach = kbytes[dom] / (kernel_ms[dom] * 1e-3) / 1e9 if kernel_ms[dom] > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": n_svs / (ms * 1e-3), "unit": "SV/s",
+            "joins_per_sec": n_joins / (ms * 1e-3), "reads_per_sec": batch.n_reads * world / (ms * 1e-3),
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/i32/f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload] + (f" x {world} samples (one per GPU)" if world > 1 else ""),
+                       "reads_tagged_per_gpu": batch.n_reads, "svs_per_gpu": batch.n_svs,
+                       "joins_per_gpu": batch.n_joins, "shards_per_gpu": batch.n_shards,
+                       "parallelism": f"shard=(sample,contig); {world} GPU(s), no data-path collective",
+                       "l2": "flushed between steps (512 MiB memset outside the event pair)",
+                       "thresholds": "svlen>=50, support>=2 (reference defaults)"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": n_svs / (e2e_s / args.steps), "unit": "SV/s", "ms_per_step": e2e_s / args.steps * 1e3,
+                    "h2d_bytes_per_step": batch.input_bytes(), "d2h_bytes_per_step": int(d2h_bytes),
+                    "last_step": {k: tm[k] for k in ("h2d_ms", "device_ms", "d2h_ms")}},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": traffic, "peak_kind": peak_kind,
+                         "algorithmic_bytes": kbytes[dom], "kernel_ms": kernel_ms[dom]},
+            "kernel_ms": kernel_ms,
+            "path_roofline": {"algorithmic_bytes_8d": alg["total"], "device_ms": ms,
+                              "achieved": alg["total"] / (ms * 1e-3) / 1e9, "frac": alg["total"] / (ms * 1e-3) / 1e9 / peak,
+                              "note": "SURVEY.md 8(d): 33 B/tagged read + 24 B/join + 64 B/SV over the whole device path"},
+            "counters": dict(zip(("n_sv", "n_kept", "n_emitted", "n_1|0", "n_0|1", "n_1|1", "n_joins", "n_hits"),
+                                 [int(x) for x in all_counts])),
+            "gather_ms": gather_ms, "synth_seconds": gen_s,
+        }
+        if not args.no_cpu_baseline:
+            cpu = CpuPort(args.workload, 0)
+            sec = min(cpu.step() for _ in range(3))
+            line["cpu_baseline"] = {"value": cpu.n_svs / sec, "unit": "SV/s", "cores": 1, "kind": "port",
+                                    "joins_per_sec": cpu.n_joins / sec, "seconds": sec,
+                                    "host_cores_available": os.cpu_count(), "sample": cpu.sample + ", best of 3"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
