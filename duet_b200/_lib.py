@@ -53,8 +53,9 @@ SYMBOLS = (
     "duet_abi_version", "duet_default_thresholds", "duet_create", "duet_destroy", "duet_last_error",
     "duet_set_thresholds", "duet_set_stream", "duet_phase_upload", "duet_phase_execute",
     "duet_phase_download", "duet_phase_run", "duet_host_alloc", "duet_host_free", "duet_sync",
-    "duet_get_timings", "duet_launch_count",
+    "duet_get_timings", "duet_launch_count", "duet_hash_names", "duet_decode_sam_text", "duet_count_lines",
 )
+DECODE_ERR_INDEX, DECODE_ERR_VALUE, DECODE_ERR_ASCII, DECODE_ERR_RANGE, DECODE_ERR_CAPACITY = 20, 21, 22, 23, 24
 
 _lib = None
 
@@ -98,5 +99,11 @@ def load() -> C.CDLL:
     lib.duet_get_timings.argtypes = [H, C.POINTER(Timings)]
     lib.duet_launch_count.argtypes = [H]
     lib.duet_launch_count.restype = C.c_int64
+    lib.duet_hash_names.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.duet_hash_names.restype = None
+    lib.duet_decode_sam_text.argtypes = [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 5 + \
+                                       [C.POINTER(C.c_int64)] * 3
+    lib.duet_count_lines.argtypes = [C.c_void_p, C.c_int64]
+    lib.duet_count_lines.restype = C.c_int64
     _lib = lib
     return lib

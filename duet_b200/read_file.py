@@ -1,0 +1,141 @@
+"""SV-VCF reader: the host-side decode that replaces the reference's
+/root/reference/src/duet/read_file.py (same function names, same argument meaning, same
+accepted inputs) but returns COLUMNS for the device instead of nested lists.
+
+Reference behaviour kept (file:line of the reference):
+  * contig list = 1..22,X,Y or `tabix --list-chroms` of the pileup VCF          read_file.py:6-16
+  * every line is stripped and whitespace-split, header lines included          :18-23
+  * a record belongs to contig c when CHROM is 'c' or 'chr'+c                   :30
+  * SVLEN: first INFO item containing 'SVLEN=', missing or 'SVLEN=.' -> 0,
+    'SVLEN=>N' handled                                                          :34-36
+  * SVTYPE: first INFO item containing 'SVTYPE='                                :38
+  * support count: first INFO item containing SUPPORT= / SR= / RE=; the prefix
+    length (8 or 3) is decided by the FIRST record of the contig                :40-47
+  * read names: first item containing RNAMES= / READS=, prefix from the first
+    record (7 or 6), split on ','                                               :48-55
+  * GT / counts from the sample column, layout decided by the first record      :56-76
+    (cuteSV GT:DR:DV:PL:GQ, Sniffles2 GT:GQ:DR:DV -> column [15] is GQ, SVIM GT:DP:AD)
+The reference scans all lines once per contig (24 passes); this reader makes one pass.
+Inputs the reference would silently mis-index (first record of a contig without a support or
+read-name item, sample column with fewer than 3 fields) raise ValueError here.
+"""
+from __future__ import annotations
+
+import shlex
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+I32_MIN, I32_MAX = -(1 << 31), (1 << 31) - 1
+
+
+def init_chrom_list(include_all_ctgs, home):
+    if not include_all_ctgs:
+        return [str(i) for i in range(1, 23)] + ["X", "Y"]
+    pileup_vcf_path = home + "/snp_calling/pileup.vcf.gz"
+    out = subprocess.check_output(shlex.split("tabix --list-chroms " + pileup_vcf_path))
+    return out.decode("ascii").split("\n")[:-1]
+
+
+def read_file(vcf_path):
+    with open(vcf_path, "r") as fh:
+        return [ln.strip().split() for ln in fh.readlines()]
+
+
+@dataclass
+class ContigSvs:
+    """Decoded SV records of one contig, VCF order (one shard's SV side)."""
+    chrom: list = field(default_factory=list)     # CHROM string per record
+    pos: list = field(default_factory=list)
+    ref: list = field(default_factory=list)
+    alt: list = field(default_factory=list)
+    svlen: list = field(default_factory=list)     # signed, as parsed (:36)
+    svtype: list = field(default_factory=list)
+    svread: list = field(default_factory=list)
+    names: list = field(default_factory=list)     # list[list[str]]
+    gt: list = field(default_factory=list)
+    refread: list = field(default_factory=list)   # column [15]
+    altread: list = field(default_factory=list)   # column [16]
+
+    def __len__(self):
+        return len(self.pos)
+
+
+def _first_with(items, needles):
+    for it in items:
+        for nd in needles:
+            if nd in it:
+                return it
+    return None
+
+
+def _count(txt):
+    return 0 if txt == "." else int(txt)
+
+
+def _i32(v, what):
+    if not (I32_MIN <= v <= I32_MAX):
+        raise OverflowError(f"{what}={v} does not fit the device's int32 column")
+    return v
+
+
+def parse_vcf(vcf_file, include_all_ctgs):
+    """-> list[ContigSvs], one per entry of init_chrom_list (empty when the contig has no record)."""
+    chrom_list = init_chrom_list(include_all_ctgs, vcf_file[:len(vcf_file) - 24])
+    accept: dict[str, list[int]] = {}
+    for ch, c in enumerate(chrom_list):
+        for nm in ("chr" + c, c):
+            lst = accept.setdefault(nm, [])
+            if ch not in lst:
+                lst.append(ch)
+    buckets: list[list[list[str]]] = [[] for _ in chrom_list]
+    for row in read_file(vcf_file):
+        for ch in accept.get(row[0], ()):          # row[0] on an empty line raises IndexError, as :30 does
+            buckets[ch].append(row)
+    out = []
+    for ch, rows in enumerate(buckets):
+        cs = ContigSvs()
+        out.append(cs)
+        if not rows:
+            continue
+        infos = [r[7].split(";") for r in rows]
+        sup_keys, name_keys = ("SUPPORT=", "SR=", "RE="), ("RNAMES=", "READS=")
+        first_sup, first_nm = _first_with(infos[0], sup_keys), _first_with(infos[0], name_keys)
+        if first_sup is None or first_nm is None:
+            raise ValueError(f"contig {chrom_list[ch]}: first record lacks a SUPPORT=/RE=/SR= or RNAMES=/READS= "
+                             "INFO item (the reference mis-indexes its columns on such input)")
+        sup_cut = 8 if "SUPPORT=" in first_sup else 3
+        nm_cut = 7 if "RNAMES=" in first_nm else 6
+        head = rows[0][9].split(":")
+        if len(head) > 4:
+            ad_mode = False
+        elif len(head) >= 3:
+            ad_mode = head[-1].find(",") != -1
+        else:
+            raise ValueError(f"contig {chrom_list[ch]}: sample column '{rows[0][9]}' has fewer than 3 fields")
+        for r, info in zip(rows, infos):
+            item = _first_with(info, ("SVLEN=",))
+            if item is None or item == "SVLEN=.":
+                item = "SVLEN=0"
+            cs.svlen.append(int(item[7:]) if ">" in item else int(item[6:]))
+            cs.svtype.append(_first_with(info, ("SVTYPE=",))[7:])
+            cs.svread.append(_i32(int(_first_with(info, sup_keys)[sup_cut:]), "support"))
+            cs.names.append(_first_with(info, name_keys)[nm_cut:].split(","))
+            smp = r[9].split(":")
+            cs.gt.append(smp[0])
+            if ad_mode:
+                last = smp[-1]
+                k = last.find(",")
+                cs.refread.append(_i32(_count(last[:k]), "refread"))
+                cs.altread.append(_count(last[k + 1:]))
+            else:
+                cs.refread.append(_i32(_count(smp[1]), "refread"))
+                cs.altread.append(_count(smp[2]))
+            cs.chrom.append(r[0])
+            cs.pos.append(_i32(int(r[1]), "pos"))
+            cs.ref.append(r[3])
+            cs.alt.append(r[4])
+        for v in cs.svlen:
+            _i32(abs(v), "svlen")
+    return out

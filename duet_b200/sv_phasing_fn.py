@@ -1,0 +1,207 @@
+"""Drop-in for /root/reference/src/duet/sv_phasing_fn.py: same public functions, same
+arguments, same return value of `generate_phased_callset` -- computed on the GPU.
+
+    reference                         here
+    read_hap_bam      (:11-34)   ->   read_hap_bam: `samtools view` text -> per-contig read columns (C++ scan)
+    generate_callinfo (:36-68)   ->   generate_callinfo: read columns + SV columns -> one PhaseBatch
+                                      (the JOIN itself happens on the device)
+    get_phase_info / predict_hp  ->   device kernels (csrc/phase_kernels.cuh)
+    generate_phased_callset      ->   decode, one device call, rows
+
+There is no CPU compute path: without libduet_b200.so and a CUDA device these functions raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import os
+import shlex
+import subprocess
+import time
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from .columnar import PhaseBatch
+from .engine import DuetError, PhaseEngine
+from .read_file import ContigSvs, init_chrom_list, parse_vcf
+
+_ENGINES: dict[int, PhaseEngine] = {}
+last_timings: dict = {}          # host decode / device / row-building seconds of the last call
+
+
+def get_engine(device: int | None = None) -> PhaseEngine:
+    if device is None:
+        device = int(os.environ.get("DUET_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    eng = _ENGINES.get(device)
+    if eng is None:
+        eng = _ENGINES[device] = PhaseEngine(device)
+    return eng
+
+
+@dataclass
+class ReadColumns:
+    """Kept rows of one per-contig haplotagged BAM, file order (sv_phasing_fn.py:26-29)."""
+    key: np.ndarray
+    key_hi: np.ndarray
+    hp: np.ndarray
+    ps: np.ndarray
+    pc: np.ndarray
+    n_lines: int = 0
+
+    def __len__(self):
+        return int(self.key.shape[0])
+
+    @staticmethod
+    def empty():
+        return ReadColumns(np.zeros(0, np.uint64), np.zeros(0, np.uint64), np.zeros(0, np.uint8),
+                           np.zeros(0, np.int32), np.zeros(0, np.int32))
+
+
+_DECODE_EXC = {
+    _lib.DECODE_ERR_INDEX: (IndexError, "list index out of range"),
+    _lib.DECODE_ERR_VALUE: (ValueError, "invalid literal for int() in an HP/PC/PS field"),
+    _lib.DECODE_ERR_ASCII: (UnicodeDecodeError, None),
+    _lib.DECODE_ERR_RANGE: (OverflowError, "HP outside 0..255 or PS/PC outside int32"),
+}
+
+
+def decode_sam_text(text: bytes) -> ReadColumns:
+    """One contig's `samtools view` output -> columns (C++: csrc/decode.cpp)."""
+    lib = _lib.load()
+    n = len(text)
+    buf = (C.c_char * max(n, 1)).from_buffer_copy(text) if not isinstance(text, (bytearray, memoryview)) else \
+        (C.c_char * max(n, 1)).from_buffer(text)
+    cap = int(lib.duet_count_lines(buf, n))
+    key, key_hi = np.empty(cap, np.uint64), np.empty(cap, np.uint64)
+    hp, ps, pc = np.empty(cap, np.uint8), np.empty(cap, np.int32), np.empty(cap, np.int32)
+    n_rows, n_lines, err_line = C.c_int64(), C.c_int64(), C.c_int64()
+    rc = lib.duet_decode_sam_text(buf, n, cap, key.ctypes.data, key_hi.ctypes.data, hp.ctypes.data, ps.ctypes.data,
+                                  pc.ctypes.data, C.byref(n_rows), C.byref(n_lines), C.byref(err_line))
+    if rc != _lib.DUET_OK:
+        exc, msg = _DECODE_EXC.get(rc, (RuntimeError, f"decode error {rc}"))
+        if exc is UnicodeDecodeError:
+            raise UnicodeDecodeError("ascii", bytes(text[:1]), 0, 1, f"ordinal not in range(128) (line {err_line.value})")
+        raise exc(f"{msg} (alignment line {err_line.value})")
+    k = n_rows.value
+    return ReadColumns(key[:k].copy(), key_hi[:k].copy(), hp[:k].copy(), ps[:k].copy(), pc[:k].copy(), n_lines.value)
+
+
+def _sam_text(path: str, thread: int) -> bytes:
+    """`samtools view -@thread <bam>` (sv_phasing_fn.py:25).  A file that is not gzip/BGZF already
+    is SAM text and is read directly (no samtools needed)."""
+    with open(path, "rb") as fh:
+        magic = fh.read(2)
+        if magic != b"\x1f\x8b":
+            return magic + fh.read()
+    return subprocess.check_output(shlex.split("samtools view -@" + str(thread) + " " + path))
+
+
+def read_hap_bam(path, thread, include_all_ctgs):
+    """-> list[ReadColumns], one per contig of init_chrom_list; a missing BAM gives an empty table
+    (sv_phasing_fn.py:19-24).  `path` = '<home>/snp_phasing/'."""
+    logging.info("extract SNP signatures")
+    chrom_list = init_chrom_list(include_all_ctgs, path[:len(path) - 13])
+    read_hap = []
+    for ctg in chrom_list:
+        if os.path.exists(path + "chr" + ctg + ".bam"):
+            hap_bam_path = path + "chr" + ctg + ".bam"
+        elif os.path.exists(path + ctg + ".bam"):
+            hap_bam_path = path + ctg + ".bam"
+        else:
+            read_hap.append(ReadColumns.empty())
+            continue
+        cols = decode_sam_text(_sam_text(hap_bam_path, thread))
+        read_hap.append(cols)
+        logging.info(("  signatures extracted from " if cols.n_lines else "  no signature from ") + ctg)
+    return read_hap
+
+
+def hash_name_lists(lists: list[list[str]]):
+    """Hash every support-read name of every SV; returns (csr lengths, lo, hi)."""
+    lib = _lib.load()
+    lens = np.fromiter((len(l) for l in lists), np.int64, len(lists))
+    flat = [n for l in lists for n in l]
+    blob = "".join(flat).encode("ascii")
+    off = np.zeros(len(flat) + 1, np.int64)
+    if flat:
+        np.cumsum(np.fromiter((len(n) for n in flat), np.int64, len(flat)), out=off[1:])
+    lo, hi = np.empty(len(flat), np.uint64), np.empty(len(flat), np.uint64)
+    if flat:
+        lib.duet_hash_names(blob, off.ctypes.data, len(flat), lo.ctypes.data, hi.ctypes.data)
+    return lens, lo, hi
+
+
+def generate_callinfo(caller_path, read_hap, include_all_ctgs) -> PhaseBatch:
+    """The reference joins here on the host (:46-48); this version only lays the two sides out as
+    one columnar batch -- shard = contig -- and leaves the join to the device."""
+    logging.info("extract SV signatures")
+    comp_call = parse_vcf(caller_path, include_all_ctgs)
+    chrom_list = init_chrom_list(include_all_ctgs, caller_path[:len(caller_path) - 24])
+    return build_batch(chrom_list, read_hap, comp_call)
+
+
+def build_batch(chrom_list, read_hap: list[ReadColumns], comp_call: list[ContigSvs], sample: int = 0) -> PhaseBatch:
+    ns = len(chrom_list)
+    read_off = np.zeros(ns + 1, np.int64)
+    sv_off = np.zeros(ns + 1, np.int64)
+    read_off[1:] = np.cumsum([len(r) for r in read_hap])
+    sv_off[1:] = np.cumsum([len(c) for c in comp_call])
+    cat = lambda parts, dt: (np.concatenate(parts) if parts else np.zeros(0)).astype(dt, copy=False)
+    chrom, svtype, ref, alt, pos, svlen, svread, refread, flags, group, lists = [], [], [], [], [], [], [], [], [], [], []
+    any_group = False
+    for cs in comp_call:
+        chrom += cs.chrom; svtype += cs.svtype; ref += cs.ref; alt += cs.alt
+        pos += cs.pos; svlen += [abs(v) for v in cs.svlen]; svread += cs.svread; refread += cs.refread
+        flags += [_lib.SV_GT_MISSING if g == "./." else 0 for g in cs.gt]
+        lists += cs.names
+        ranks = {c: i for i, c in enumerate(sorted(set(cs.chrom)))}     # 'chr1' and '1' rows in one contig
+        any_group |= len(ranks) > 1
+        group += [ranks[c] for c in cs.chrom]
+    lens, ck, ch = hash_name_lists(lists)
+    csr_off = np.zeros(len(lists) + 1, np.int64)
+    np.cumsum(lens, out=csr_off[1:])
+    b = PhaseBatch(
+        read_off, sv_off,
+        cat([r.key for r in read_hap], np.uint64), cat([r.key_hi for r in read_hap], np.uint64),
+        cat([r.hp for r in read_hap], np.uint8), cat([r.ps for r in read_hap], np.int32),
+        cat([r.pc for r in read_hap], np.int32),
+        np.asarray(pos, np.int32), np.asarray(svlen, np.int32), np.asarray(svread, np.int32),
+        np.asarray(refread, np.int32), np.asarray(flags, np.uint8),
+        np.asarray(group, np.int32) if any_group else None, csr_off, ck, ch,
+        [sample] * ns, list(chrom_list), chrom, svtype, ref, alt)
+    b.validate()
+    return b
+
+
+_STATUS_EXC = {_lib.ERR_BAD_HP: KeyError, _lib.ERR_ZERO_DIVISION: ZeroDivisionError}
+
+
+def phase_batch(batch: PhaseBatch, svlen_thres, suppread_thres, engine: PhaseEngine | None = None):
+    eng = engine or get_engine()
+    eng.set_thresholds(int(svlen_thres), int(suppread_thres))
+    try:
+        return eng.run(batch)
+    except DuetError as e:
+        exc = _STATUS_EXC.get(e.code)
+        if exc is None:
+            raise
+        raise exc(e.msg) from e      # the exception the reference raises at :96 / :123
+
+
+def generate_phased_callset(vcf_path, sam_home, svlen_thres, suppread_thres, thread, include_all_ctgs):
+    """Same signature and return value as the reference's (sv_phasing_fn.py:185-230)."""
+    t0 = time.perf_counter()
+    batch = generate_callinfo(vcf_path, read_hap_bam(sam_home, thread, include_all_ctgs), include_all_ctgs)
+    t1 = time.perf_counter()
+    logging.info("integrate read weight information")
+    logging.info("calculate read weight statistics")
+    logging.info("predict SV haplotypes in the callset")
+    res = phase_batch(batch, svlen_thres, suppread_thres)
+    t2 = time.perf_counter()
+    rows = res.rows(batch)
+    t3 = time.perf_counter()
+    last_timings.clear()
+    last_timings.update(host_decode_s=t1 - t0, device_call_s=t2 - t1, rows_s=t3 - t2, **get_engine().timings())
+    return rows

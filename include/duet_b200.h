@@ -173,6 +173,27 @@ int duet_host_alloc(void **ptr, int64_t bytes);
 int duet_host_free(void *ptr);
 
 int duet_sync(duet_handle *h);
+
+/* ---- host-side decoders (no GPU needed) -------------------------------------------------- */
+
+enum {
+    DUET_DECODE_ERR_INDEX = 20,    /* a line has fewer fields than the reference indexes -> IndexError  */
+    DUET_DECODE_ERR_VALUE = 21,    /* int() of a tag value fails -> ValueError                          */
+    DUET_DECODE_ERR_ASCII = 22,    /* byte >= 0x80 -> UnicodeDecodeError (.decode('ascii'), :25)        */
+    DUET_DECODE_ERR_RANGE = 23,    /* HP outside 0..255 or PS/PC outside int32 (BAM aux ints are 32 bit) */
+    DUET_DECODE_ERR_CAPACITY = 24  /* output arrays too small                                           */
+};
+
+/* 128-bit name hash (duet_b200/namehash.py): name i is buf[off[i] .. off[i+1]). */
+void duet_hash_names(const char *buf, const int64_t *off, int64_t n, uint64_t *lo, uint64_t *hi);
+
+/* `samtools view` text of one haplotagged BAM -> columns of the kept rows, in file order
+ * (sv_phasing_fn.py:25-29).  Output arrays hold `cap` rows (duet_count_lines(text) is enough).
+ * On error returns a DUET_DECODE_ERR_* code and the 0-based line number in *err_line. */
+int duet_decode_sam_text(const char *text, int64_t len, int64_t cap, uint64_t *key_lo, uint64_t *key_hi,
+                         uint8_t *hp, int32_t *ps, int32_t *pc, int64_t *n_rows, int64_t *n_lines,
+                         int64_t *err_line);
+int64_t duet_count_lines(const char *text, int64_t len);
 int duet_get_timings(duet_handle *h, duet_timings *t);
 /* Number of kernels this library launched on the handle since creation (bench "gpu_launches"). */
 int64_t duet_launch_count(const duet_handle *h);

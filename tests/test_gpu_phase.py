@@ -220,3 +220,44 @@ def test_big_shard_uses_global_sort_scratch(engine):
     """One shard with more SVs than the shared-memory sort tiles hold (16384 / 8192)."""
     s = synth.make_sample(12, contigs=["1"], n_reads=60000, n_svs=20000, bp_per_read=700, block_mean=2e5)
     run_and_compare(engine, s)
+
+
+# ---- the drop-in functions on the golden end-to-end cases recorded from the reference ----------
+from conftest import golden_e2e_names  # noqa: E402
+
+
+@pytest.mark.parametrize("name", golden_e2e_names())
+def test_dropin_against_reference_golden(name, golden_workdir):
+    """generate_phased_callset / sv_phasing with the reference's signature: rows equal and
+    phased_sv.vcf byte-identical to what the unmodified reference produced."""
+    from duet_b200 import sv_phasing, sv_phasing_fn
+    case, home = golden_workdir(name)
+    rows = sv_phasing_fn.generate_phased_callset(home + "/sv_calling/variants.vcf", home + "/snp_phasing/",
+                                                 case["svlen_thres"], case["suppread_thres"], 1, False)
+    assert rows == case["rows"]
+    sv_phasing.sv_phasing(home, case["svlen_thres"], case["suppread_thres"], 1, False)
+    with open(home + "/phased_sv.vcf") as f:
+        assert f.read() == case["phased_sv_vcf"]
+    # and the join / per-SV features the reference computed on the way
+    batch = sv_phasing_fn.generate_callinfo(home + "/sv_calling/variants.vcf",
+                                            sv_phasing_fn.read_hap_bam(home + "/snp_phasing/", 1, False), False)
+    res = sv_phasing_fn.phase_batch(batch, case["svlen_thres"], case["suppread_thres"])
+    assert batch.n_svs == len(case["joined"])
+    for i, g in enumerate(case["joined"]):
+        rows_i = res.join_row[int(batch.csr_off[i]):int(batch.csr_off[i + 1])].tolist()
+        got = [[int(batch.read_hp[r]), int(batch.read_ps[r]), int(batch.read_pc[r])] if r >= 0 else [] for r in rows_i]
+        assert got == g["reads"]
+    key = {}
+    for i in range(batch.n_svs):
+        key.setdefault((batch.sv_chrom[i], int(batch.sv_pos[i])), []).append(i)
+    used = set()
+    for t in case["trace"]:
+        cand = [i for i in key[(t["chrom"], t["pos"])] if i not in used and res.cls[i] == t["ps_num"]]
+        i = cand[0]
+        used.add(i)
+        f = t["f"]
+        assert (res.hap1[i], res.hap2[i], res.hap0[i], res.allhap[i], res.ps[i]) == \
+               (f["hap1"], f["hap2"], f["hap0"], f["allhap"], f["ps"])
+        assert (res.totsc1[i], res.totsc2[i]) == (f["hap1_totsc"], f["hap2_totsc"])
+        for nm in _lib.FEATURE_NAMES:
+            assert float(res.feature(nm)[i]) == float(f[nm])

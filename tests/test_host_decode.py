@@ -1,0 +1,129 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every declared symbol,
+the three name-hash implementations agree, and the text decoders reproduce what the oracle
+(hence the reference) extracts from the same files."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_e2e_names
+from duet_b200 import _lib, namehash, read_file, sv_phasing_fn, synth, write_file
+from duet_b200.columnar import from_synth
+from oracle import ref_port
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    with open(os.path.join(ROOT, "include", "duet_b200.h")) as f:
+        header = f.read()
+    declared = set(re.findall(r"\b(duet_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS)
+    for sym in declared:
+        assert getattr(lib, sym) is not None
+    assert lib.duet_abi_version() == 1
+    t = _lib.Thresholds()
+    lib.duet_default_thresholds(C.byref(t))
+    assert (t.svlen_thres, t.suppread_thres, t.pc_max, t.c2_sv_ratio_min, t.c1_totsc_ratio_max) == (50, 2, 8100, 0.72, 9.72)
+
+
+def test_struct_layouts_match_header():
+    # sizes the C side was compiled with (LP64): catches a drifted ctypes mirror
+    assert C.sizeof(_lib.Thresholds) == 8 * 4 + 10 * 8
+    assert C.sizeof(_lib.PhaseInput) == 8 + 3 * 8 + 16 * 8
+    assert C.sizeof(_lib.PhaseOutput) == 13 * 8 + 8
+    assert C.sizeof(_lib.Timings) == 3 * 4 + 8 * 4
+
+
+def test_no_device_fails_loudly():
+    """On a box without a GPU the product path must refuse, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from duet_b200.engine import DuetError, PhaseEngine
+    with pytest.raises(DuetError) as ei:
+        PhaseEngine(0)
+    assert ei.value.code == _lib.ERR_NO_DEVICE
+
+
+def test_name_hash_three_ways():
+    rng = np.random.default_rng(0)
+    names = [bytes(rng.integers(33, 127, size=int(n)).astype(np.uint8)) for n in list(range(0, 70)) + [36] * 50]
+    lo_py, hi_py = namehash.hash_names(names)
+    lens, lo_c, hi_c = sv_phasing_fn.hash_name_lists([[n.decode() for n in names]])
+    assert np.array_equal(lo_py, lo_c) and np.array_equal(hi_py, hi_c)
+    fixed = synth.names_from_ids(np.arange(1000))
+    lo_np, hi_np = namehash.hash128_fixed(fixed)
+    lo_py, hi_py = namehash.hash_names([r.tobytes() for r in fixed])
+    assert np.array_equal(lo_np, lo_py) and np.array_equal(hi_np, hi_py)
+    assert len(set(lo_np.tolist())) == 1000 and (lo_np != np.uint64(namehash.EMPTY_KEY)).all()
+
+
+@pytest.mark.parametrize("name", golden_e2e_names())
+def test_decoders_match_oracle_on_golden_inputs(name, golden_workdir):
+    case, home = golden_workdir(name)
+    vcf, sam_home = home + "/sv_calling/variants.vcf", home + "/snp_phasing/"
+    tables = ref_port.haplotag_tables(sam_home, 1, False)
+    cols = sv_phasing_fn.read_hap_bam(sam_home, 1, False)
+    for table, rc in zip(tables, cols):
+        # last row per key == dict content
+        last = {}
+        for i, k in enumerate(rc.key.tolist()):
+            last[k] = i
+        assert len(last) == len(table)
+        want = {namehash.hash128(nm)[0]: tag for nm, tag in table.items()}
+        got = {k: (int(rc.hp[i]), int(rc.ps[i]), int(rc.pc[i])) for k, i in last.items()}
+        assert got == want
+    recs = ref_port.sv_records(vcf, False)
+    svs = read_file.parse_vcf(vcf, False)
+    for rl, cs in zip(recs, svs):
+        assert len(rl) == len(cs)
+        for i, r in enumerate(rl):
+            assert (r.chrom, r.pos, r.ref, r.alt, r.svlen, r.svtype, r.svread, r.names, r.gt, r.refread, r.altread) == \
+                   (cs.chrom[i], cs.pos[i], cs.ref[i], cs.alt[i], cs.svlen[i], cs.svtype[i], cs.svread[i],
+                    cs.names[i], cs.gt[i], cs.refread[i], cs.altread[i])
+    assert write_file.header_text(vcf, False) == ref_port.header_text(vcf, False)
+    assert write_file.header_text(vcf, False) + write_file.format_rows(case["rows"]) == case["phased_sv_vcf"]
+
+
+def test_text_path_equals_direct_columnar(tmp_path):
+    s = synth.make_sample(3, contigs=["1", "5", "X"], n_reads=3000, n_svs=250, bp_per_read=700, block_mean=1e5)
+    home = str(tmp_path)
+    synth.write_workdir(s, home, "cutesv")
+    a = sv_phasing_fn.generate_callinfo(home + "/sv_calling/variants.vcf",
+                                        sv_phasing_fn.read_hap_bam(home + "/snp_phasing/", 1, False), False)
+    b = from_synth(s)
+    shard = {c: i for i, c in enumerate(a.shard_contig)}
+    a = a.select_shards([shard[c] for c in b.shard_contig])      # 24 reference contigs -> the 3 that have data
+    for k in ("read_off", "sv_off", "read_key", "read_key_hi", "read_hp", "read_ps", "read_pc", "sv_pos", "sv_svlen",
+              "sv_svread", "sv_refread", "sv_flags", "csr_off", "csr_key", "csr_key_hi"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert (a.sv_chrom, a.sv_type, a.sv_alt) == (b.sv_chrom, b.sv_type, b.sv_alt)
+
+
+@pytest.mark.parametrize("text,exc", [
+    (b"r1\t0\t1\t5\tHP:i:1\tPC:i:7\tPS:i:9\n\n", IndexError),                 # blank line
+    (b"lonely\n", IndexError),                                                # one field
+    (b"PC:i:5\tPS:i:9\n", IndexError),                                        # 'PC:i:' in s[-2] but no s[-3]
+    (b"r1\tHP:i:x\tPC:i:7\tPS:i:9\n", ValueError),
+    (b"r1\tHP:i:1\tPC:i:7\tPS:i:\n", ValueError),
+    (b"r1\tHP:i:1\tPC:i:7\tPS:i:9\xc3\xa9\n", UnicodeDecodeError),
+    (b"r1\tHP:i:999\tPC:i:7\tPS:i:9\n", OverflowError),
+])
+def test_sam_text_error_behaviour(text, exc):
+    with pytest.raises(exc):
+        sv_phasing_fn.decode_sam_text(text)
+
+
+def test_sam_text_quirks():
+    # tags are positional (last three fields), rows need 'PC:i:' in the second-to-last field,
+    # text after the final newline is dropped, any whitespace separates fields
+    text = (b"a 0 1 5 XX:i:1 HP:i:2 PC:i:30 PS:i:400\n"
+            b"b\t0\tHP:i:1\tPC:i:7\tPS:i:9\tNM:i:0\n"          # tags not last -> s[-2] is PS -> skipped
+            b"c\t0\tzz:i:1_0\tPC:i:+7\tqq:i:-9\n"                # 5 characters stripped by position, int() syntax
+            b"d\t0\tHP:i:1\tPC:i:7\tPS:i:9")                      # no trailing newline -> dropped
+    rc = sv_phasing_fn.decode_sam_text(text)
+    assert rc.n_lines == 3 and len(rc) == 2
+    assert (rc.hp.tolist(), rc.pc.tolist(), rc.ps.tolist()) == ([2, 10], [30, 7], [400, -9])
+    assert rc.key[0] == namehash.hash128("a")[0] and rc.key[1] == namehash.hash128("c")[0]
