@@ -46,7 +46,7 @@ class Timings(C.Structure):
                 ("kernel_ms", C.c_float * 8)]
 
 
-KERNEL_NAMES = ("init", "build", "probe", "reduce", "oneps", "predict", "order")
+KERNEL_NAMES = ("build", "probe", "reduce", "predict")
 
 # every symbol include/duet_b200.h declares
 SYMBOLS = (

@@ -36,7 +36,7 @@ struct DevBuf {
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-enum { EV_H2D0, EV_H2D1, EV_X0, EV_K0, EV_K1, EV_K2, EV_K3, EV_K4, EV_K5, EV_K6, EV_D2H0, EV_D2H1, EV_COUNT };
+enum { EV_H2D0, EV_H2D1, EV_X0, EV_K1, EV_K2, EV_K3, EV_K4, EV_D2H0, EV_D2H1, EV_COUNT };
 
 }  // namespace
 
@@ -54,14 +54,14 @@ struct duet_handle {
     PhaseArgs a;                    // device view
     std::vector<long long> h_read_off, h_sv_off;
     long long n_slots = 0;
-    size_t oneps_smem = 0, order_smem = 0;
+    int group = 16;                 // lanes per SV in k_build / k_reduce
 
     // staged input copies (HOST mode)
     DevBuf in_read_key, in_read_key_hi, in_read_hp, in_read_ps, in_read_pc;
     DevBuf in_sv_pos, in_sv_svlen, in_sv_svread, in_sv_refread, in_sv_flags, in_sv_group;
     DevBuf in_csr_off, in_csr_key, in_csr_key_hi;
     // descriptors, table, scratch, outputs
-    DevBuf d_read_off, d_sv_off, d_tab_off, d_tab_mask;
+    DevBuf d_read_off, d_sv_off, d_sv_shard, d_tab_off, d_tab_mask, d_done;
     DevBuf d_table;                 // [tab_key | tab_row] cleared with one memset
     DevBuf d_tab_hi, d_csr_slot, d_join_row, d_n_hit, d_cand, d_oneps, d_oneps_n, d_sort;
     DevBuf d_gt, d_cls, d_ps, d_hap1, d_hap2, d_hap0, d_allhap, d_t1, d_t2, d_feat, d_order, d_n_emit;
@@ -147,10 +147,10 @@ int duet_create(int device_id, duet_handle **out) {
     }
     h->stream = h->own_stream;
     for (auto &ev : h->ev) cudaEventCreate(&ev);
-    cudaFuncSetAttribute(k_oneps, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         kOnepsSmemMaxElems * (int)sizeof(long long));
-    cudaFuncSetAttribute(k_order, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         kOrderSmemMaxElems * (int)sizeof(u128));
+    {   // fails here, loudly, if the image was not built for this device (sm_100a only)
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, k_probe);
+    }
     if (cudaGetLastError() != cudaSuccess) {
         delete h;
         return fail(nullptr, DUET_ERR_CUDA, "duet_create: kernel image not loadable on this device (built for sm_100a)");
@@ -166,7 +166,7 @@ void duet_destroy(duet_handle *h) {
     DevBuf *bufs[] = {&h->in_read_key, &h->in_read_key_hi, &h->in_read_hp, &h->in_read_ps, &h->in_read_pc,
                       &h->in_sv_pos, &h->in_sv_svlen, &h->in_sv_svread, &h->in_sv_refread, &h->in_sv_flags,
                       &h->in_sv_group, &h->in_csr_off, &h->in_csr_key, &h->in_csr_key_hi, &h->d_read_off,
-                      &h->d_sv_off, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_tab_hi, &h->d_csr_slot,
+                      &h->d_sv_off, &h->d_sv_shard, &h->d_done, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_tab_hi, &h->d_csr_slot,
                       &h->d_join_row, &h->d_n_hit, &h->d_cand, &h->d_oneps, &h->d_oneps_n, &h->d_sort, &h->d_gt,
                       &h->d_cls, &h->d_ps, &h->d_hap1, &h->d_hap2, &h->d_hap0, &h->d_allhap, &h->d_t1, &h->d_t2,
                       &h->d_feat, &h->d_order, &h->d_n_emit, &h->d_counts, &h->d_status};
@@ -287,6 +287,12 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     a.read_off = static_cast<const long long *>(dv);
     if ((rc = stage(h, h->d_sv_off, h->h_sv_off.data(), sizeof(long long) * (ns + 1), DUET_MEM_HOST, &dv))) return rc;
     a.sv_off = static_cast<const long long *>(dv);
+    std::vector<int> sv_shard((size_t)S);
+    for (int s = 0; s < ns; ++s)
+        std::fill(sv_shard.begin() + in->sv_off[s], sv_shard.begin() + in->sv_off[s + 1], s);
+    if ((rc = stage(h, h->d_sv_shard, sv_shard.data(), sizeof(int) * (size_t)S, DUET_MEM_HOST, &dv))) return rc;
+    a.sv_shard = static_cast<const int *>(dv);
+    CU(h, cudaStreamSynchronize(st));          // sv_shard / tab_off are stack vectors: copies must finish
     if ((rc = stage(h, h->d_tab_off, tab_off.data(), sizeof(int) * ns, DUET_MEM_HOST, &dv))) return rc;
     a.tab_off = static_cast<const int *>(dv);
     if ((rc = stage(h, h->d_tab_mask, tab_mask.data(), sizeof(int) * ns, DUET_MEM_HOST, &dv))) return rc;
@@ -305,12 +311,10 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     CU(h, h->d_cand.reserve(S1 * 8));                    a.cand = h->d_cand.as<long long>();
     CU(h, h->d_oneps.reserve(S1 * 4));                   a.oneps = h->d_oneps.as<int>();
     CU(h, h->d_oneps_n.reserve((size_t)ns * 4));         a.oneps_n = h->d_oneps_n.as<int>();
-    const long long pad = pow2_at_least(std::max<long long>(max_sv, 1));
-    a.oneps_smem_elems = (int)std::min<long long>(pad, kOnepsSmemMaxElems);
-    a.order_smem_elems = (int)std::min<long long>(pad, kOrderSmemMaxElems);
-    h->oneps_smem = (size_t)a.oneps_smem_elems * sizeof(long long);
-    h->order_smem = (size_t)a.order_smem_elems * sizeof(u128);
-    if (pad > a.order_smem_elems) { CU(h, h->d_sort.reserve(S1 * 32)); a.sort_scratch = h->d_sort.as<long long>(); }
+    CU(h, h->d_done.reserve((size_t)ns * 8));            a.done_reduce = h->d_done.as<int>();
+    a.done_predict = a.done_reduce + ns;
+    CU(h, h->d_sort.reserve(S1 * 32));                   a.sort_scratch = h->d_sort.as<long long>();
+    h->group = (S > 0 && J / std::max<long long>(S, 1) > 24) ? 32 : 16;
     CU(h, h->d_gt.reserve(S1));                          a.gt = h->d_gt.as<uint8_t>();
     CU(h, h->d_cls.reserve(S1));                         a.cls = h->d_cls.as<uint8_t>();
     CU(h, h->d_ps.reserve(S1 * 4));                      a.ps = h->d_ps.as<int>();
@@ -325,6 +329,14 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     CU(h, h->d_n_emit.reserve((size_t)ns * 4));          a.n_emit = h->d_n_emit.as<int>();
     CU(h, h->d_counts.reserve((size_t)ns * 8 * DUET_N_COUNTERS)); a.shard_counts = h->d_counts.as<long long>();
     CU(h, h->d_status.reserve(sizeof(DevStatus)));       a.status = h->d_status.as<DevStatus>();
+    // state the kernels keep clean between calls: EMPTY table, zero counters / credits / status
+    CU(h, cudaMemsetAsync(h->d_table.p, 0xFF, (size_t)slots * 12, st));
+    CU(h, cudaMemsetAsync(h->d_done.p, 0, (size_t)ns * 8, st));
+    CU(h, cudaMemsetAsync(h->d_oneps_n.p, 0, (size_t)ns * 4, st));
+    CU(h, cudaMemsetAsync(h->d_n_emit.p, 0, (size_t)ns * 4, st));
+    CU(h, cudaMemsetAsync(h->d_counts.p, 0, (size_t)ns * 8 * DUET_N_COUNTERS, st));
+    CU(h, cudaMemsetAsync(h->d_status.p, 0, sizeof(DevStatus), st));
+    CU(h, cudaStreamSynchronize(st));          // tab_off / tab_mask host vectors go out of scope
     h->staged = true;
     return DUET_OK;
 }
@@ -342,40 +354,30 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
     h->per_kernel = per_kernel != 0;
     auto mark = [&](int ev) { if (h->per_kernel) cudaEventRecord(h->ev[ev], st); };
     CU(h, cudaEventRecord(h->ev[EV_X0], st));
-    // every slot EMPTY (all ones) and every row -1 (all ones): one memset; S-sized features
-    // are fully rewritten only for predicted SVs, so zero them with the status word
-    CU(h, cudaMemsetAsync(h->d_table.p, 0xFF, (size_t)h->n_slots * 12, st));
-    CU(h, cudaMemsetAsync(h->d_status.p, 0, sizeof(DevStatus), st));
-    CU(h, cudaMemsetAsync(h->d_feat.p, 0, (size_t)std::max(a.n_svs, 1) * 8 * DUET_N_FEATURES, st));
-    mark(EV_K0);
-    const int sv_blocks = (a.n_svs + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    if (a.n_svs) {
-        k_build<<<sv_blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+    const int S = a.n_svs, G = h->group;
+    if (S && a.n_joins) {
+        const int blocks = (S + kThreads / G - 1) / (kThreads / G);
+        if (G == 16) k_build<16><<<blocks, kThreads, 0, st>>>(a); else k_build<32><<<blocks, kThreads, 0, st>>>(a);
         ++h->launches;
     }
     mark(EV_K1);
     if (a.n_reads && a.n_joins) {
-        const int per_block = kProbeThreads * kProbePerThread;
-        k_probe<<<(a.n_reads + per_block - 1) / per_block, kProbeThreads, 0, st>>>(a);
+        k_probe<<<(a.n_reads + kProbeTile - 1) / kProbeTile, kThreads, 0, st>>>(a);
         ++h->launches;
     }
     mark(EV_K2);
-    if (a.n_svs) {
-        k_reduce<<<sv_blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+    if (S) {
+        const int blocks = (S + kThreads / G - 1) / (kThreads / G);
+        if (G == 16) k_reduce<16><<<blocks, kThreads, 0, st>>>(a); else k_reduce<32><<<blocks, kThreads, 0, st>>>(a);
         ++h->launches;
     }
     mark(EV_K3);
-    k_oneps<<<a.n_shards, kSortThreads, h->oneps_smem, st>>>(a);
-    ++h->launches;
-    mark(EV_K4);
-    if (a.n_svs) {
-        k_predict<<<sv_blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+    if (S) {
+        constexpr int per_block = kThreads / 32 * kSvPerWarpPredict;
+        k_predict<<<(S + per_block - 1) / per_block, kThreads, 0, st>>>(a);
         ++h->launches;
     }
-    mark(EV_K5);
-    k_order<<<a.n_shards, kSortThreads, h->order_smem, st>>>(a);
-    ++h->launches;
-    CU(h, cudaEventRecord(h->ev[EV_K6], st));
+    CU(h, cudaEventRecord(h->ev[EV_K4], st));
     CU(h, cudaGetLastError());
     h->executed = true;
     return DUET_OK;
@@ -429,6 +431,8 @@ int duet_phase_download(duet_handle *h, duet_phase_output *out) {
                          : status.code == DUET_ERR_ZERO_DIVISION ? "svread + refread == 0 (or empty read list)"
                          : "device error";
         std::snprintf(buf, sizeof(buf), "%s (sv=%d detail=%lld)", what, status.sv, status.detail);
+        cudaMemsetAsync(h->d_status.p, 0, sizeof(DevStatus), st);
+        cudaStreamSynchronize(st);
         return fail(h, status.code, buf);
     }
     // shard regions of `order` -> one compact list
@@ -456,10 +460,10 @@ int duet_get_timings(duet_handle *h, duet_timings *t) {
     CU(h, cudaStreamSynchronize(h->stream));
     if (h->have_h2d) cudaEventElapsedTime(&t->h2d_ms, h->ev[EV_H2D0], h->ev[EV_H2D1]);
     if (h->executed) {
-        cudaEventElapsedTime(&t->device_ms, h->ev[EV_X0], h->ev[EV_K6]);
+        cudaEventElapsedTime(&t->device_ms, h->ev[EV_X0], h->ev[EV_K4]);
         if (h->per_kernel) {
-            const int seq[] = {EV_X0, EV_K0, EV_K1, EV_K2, EV_K3, EV_K4, EV_K5, EV_K6};
-            for (int i = 0; i < 7; ++i) cudaEventElapsedTime(&t->kernel_ms[i], h->ev[seq[i]], h->ev[seq[i + 1]]);
+            const int seq[] = {EV_X0, EV_K1, EV_K2, EV_K3, EV_K4};
+            for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t->kernel_ms[i], h->ev[seq[i]], h->ev[seq[i + 1]]);
         }
     }
     if (h->have_d2h) cudaEventElapsedTime(&t->d2h_ms, h->ev[EV_D2H0], h->ev[EV_D2H1]);

@@ -1,18 +1,21 @@
 // sm_100a kernels of the sv_phasing hot path.
 //
 // Reference behaviour restated per kernel (citations: /root/reference/src/duet/sv_phasing_fn.py):
-//   k_build   + k_probe   the dict insert / lookup of :26-29 and :46-48 (the JOIN)
-//   k_reduce              per-SV class (:192-194), one-PS candidate (:195-203), class-1 counts (:74-84)
-//   k_oneps               per-contig set -> sorted unique list (:107)
-//   k_predict             class-2 statistics (:85-105), nearest-PS fallback (:106-111),
-//                         derived features (:112-139) and the T1-T5 tree (:142-183)
-//   k_order               emission order inside a shard (:206-229)
+//   k_build    dict insert side of the JOIN (:26-29 keyed by QNAME) -- here the SMALL side is
+//              inserted: the support-read names of the SVs (:46-48)
+//   k_probe    the haplotagged reads streamed through that table; a hit records the row index
+//              with atomicMax == "a later row overwrites an earlier one" (:29)
+//   k_reduce   per SV: resolve each support read to its row, class = #distinct PS (:192-194),
+//              one-PS candidate (:195-203), class-1 counts and score sums (:74-84);
+//              the last block to finish a shard turns the shard's candidates into the sorted
+//              unique one-PS list (:107)
+//   k_predict  class-2 statistics (:85-105), nearest-PS fallback (:106-111), features
+//              (:112-139), the T1-T5 tree (:142-183); clears the join table for the next call;
+//              the last block to finish a shard writes the shard's emission order (:206-229)
 //
-// Join direction: the table is built on the SMALL side -- the support-read names of the SVs
-// (J entries, L2 resident) -- and the haplotagged reads (R >> J rows) are STREAMED through it
-// once, fully coalesced.  A matching row does atomicMax(row index) on its slot, which is the
-// reference's "later row overwrites earlier row" rule.  Every shard owns a power-of-two slot
-// range, so equal names in different contigs never meet (the reference keeps one dict per contig).
+// Latency, not bandwidth, is what these kernels fight (the whole WGS-30x problem is ~130 MB):
+// every kernel is organised so that a thread's dependent-load chain is as short as possible and
+// all independent loads of a thread are issued before the first one is consumed.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -24,8 +27,11 @@ namespace duet {
 
 constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
 constexpr long long kNoCand = 0x7FFFFFFFFFFFFFFFll;   // "no one-PS candidate" (sorts last)
-constexpr int kWarpsPerBlock = 8;
+constexpr long long kNone = (long long)0x8000000000000000ull;
+constexpr int kThreads = 256;                         // every kernel
 constexpr int kMaxDistinct = 32;                      // distinct in-set PS per SV handled in smem
+constexpr int kSvPerWarpPredict = 8;
+constexpr int kSortSmemBytes = 16384;                 // slow-path sort tile in shared memory
 
 struct DevStatus {          // device -> host error report
     int code;               // first DUET_ERR_* seen (atomicCAS from 0)
@@ -33,13 +39,14 @@ struct DevStatus {          // device -> host error report
     long long detail;       // offending value (HP, key, ...)
 };
 
-// Everything a kernel needs; passed by value (fits the 4 KB parameter space).
+// Everything a kernel needs; passed by value.
 struct PhaseArgs {
     int n_shards;
     int n_reads, n_svs, n_joins;
     // inputs (device)
     const long long *read_off;   // [n_shards+1]
     const long long *sv_off;     // [n_shards+1]
+    const int *sv_shard;         // [S] shard of each SV (derived at upload)
     const unsigned long long *read_key, *read_key_hi;
     const uint8_t *read_hp;
     const int *read_ps, *read_pc;
@@ -51,7 +58,7 @@ struct PhaseArgs {
     // join table: shard s owns slots [tab_off[s], tab_off[s] + tab_mask[s] + 1)
     const int *tab_off;          // [n_shards]
     const int *tab_mask;         // [n_shards]
-    unsigned long long *tab_key; // [n_slots]
+    unsigned long long *tab_key; // [n_slots] EMPTY between calls (k_predict clears what k_build set)
     unsigned long long *tab_hi;  // [n_slots] hi word of the inserting name (collision check)
     int *tab_row;                // [n_slots] max matching read row, -1 = none
     int *csr_slot;               // [J] slot of each support-read name
@@ -61,9 +68,9 @@ struct PhaseArgs {
     long long *cand;             // [S] one-PS candidate or kNoCand
     int *oneps;                  // [S] shard s: sorted unique list at [sv_off[s], +oneps_n[s])
     int *oneps_n;                // [n_shards]
-    long long *sort_scratch;     // [4*S] global fallback for shards too big for shared memory
-    int oneps_smem_elems;        // long long elements of dynamic smem given to k_oneps
-    int order_smem_elems;        // u128 elements of dynamic smem given to k_order
+    int *done_reduce;            // [n_shards] SVs of the shard finished by k_reduce (self-resetting)
+    int *done_predict;           // [n_shards] same for k_predict
+    long long *sort_scratch;     // [4*S] global tile for slow-path sorts of big shards
     uint8_t *gt, *cls;
     int *ps, *hap1, *hap2, *hap0, *allhap;
     long long *totsc1, *totsc2;
@@ -103,177 +110,55 @@ __device__ __forceinline__ unsigned slot_hash(unsigned long long key) {
 }
 
 template <typename T>
-__device__ __forceinline__ T warp_sum(T v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+__device__ __forceinline__ T group_sum(T v, unsigned mask, int width) {
+    for (int o = width >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
     return v;
 }
-__device__ __forceinline__ int warp_min(int v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+template <typename T>
+__device__ __forceinline__ T group_min(T v, unsigned mask, int width) {
+    for (int o = width >> 1; o > 0; o >>= 1) { T u = __shfl_xor_sync(mask, v, o); v = u < v ? u : v; }
     return v;
 }
-__device__ __forceinline__ int warp_max(int v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+template <typename T>
+__device__ __forceinline__ T group_max(T v, unsigned mask, int width) {
+    for (int o = width >> 1; o > 0; o >>= 1) { T u = __shfl_xor_sync(mask, v, o); v = u > v ? u : v; }
     return v;
 }
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) { return group_sum(v, 0xffffffffu, 32); }
 
-// ------------------------------------------------------------------------------------------
-// k_build: insert every support-read name into its shard's slot range.  One warp per SV.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-k_build(PhaseArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int sv = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (sv >= a.n_svs) return;
-    const int s = shard_of(a.sv_off, a.n_shards, sv);
-    const int base = __ldg(a.tab_off + s);
-    const unsigned mask = (unsigned)__ldg(a.tab_mask + s);
-    const long long b = __ldg(a.csr_off + sv), e = __ldg(a.csr_off + sv + 1);
-    for (long long j = b + lane; j < e; j += 32) {
-        const unsigned long long key = __ldg(a.csr_key + j);
-        unsigned p = slot_hash(key) & mask;
-        for (;;) {
-            const unsigned long long prev = atomicCAS(a.tab_key + base + p, kEmptyKey, key);
-            if (prev == kEmptyKey) {
-                if (a.csr_key_hi) a.tab_hi[base + p] = __ldg(a.csr_key_hi + j);
-                break;
-            }
-            if (prev == key) break;
-            p = (p + 1) & mask;
-        }
-        a.csr_slot[j] = base + (int)p;
+struct OpSum { template <typename T> __device__ T operator()(T a, T b) const { return a + b; } };
+struct OpMax { template <typename T> __device__ T operator()(T a, T b) const { return a > b ? a : b; } };
+
+// exclusive block scan (blockDim.x == kThreads); *total receives the reduction over the block
+template <typename T, typename Op>
+__device__ T block_scan_exclusive(T v, T identity, Op op, T *total) {
+    __shared__ T warp_tot[kThreads / 32];
+    __shared__ T s_total;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    T inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const T n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc = op(n, inc);
     }
-}
-
-// ------------------------------------------------------------------------------------------
-// k_probe: stream the haplotagged reads through the table.  kProbePerThread keys per thread,
-// all loads issued before the first probe so each thread keeps several L2 requests in flight.
-// ------------------------------------------------------------------------------------------
-constexpr int kProbeThreads = 256;
-constexpr int kProbePerThread = 4;
-
-__device__ __forceinline__ void probe_one(const PhaseArgs &a, unsigned long long key, int row, int base,
-                                          unsigned mask) {
-    unsigned p = slot_hash(key) & mask;
-    for (;;) {
-        const unsigned long long k = a.tab_key[base + p];
-        if (k == key) {
-            if (a.read_key_hi && a.tab_hi[base + p] != __ldg(a.read_key_hi + row)) {
-                report(a.status, DUET_ERR_HASH_COLLISION, -1, (long long)key);
-                return;
-            }
-            atomicMax(a.tab_row + base + p, row);
-            return;
-        }
-        if (k == kEmptyKey) return;
-        p = (p + 1) & mask;
-    }
-}
-
-__global__ void __launch_bounds__(kProbeThreads)
-k_probe(PhaseArgs a) {
-    __shared__ int s_lo, s_hi;
-    const long long tile = (long long)blockIdx.x * (kProbeThreads * kProbePerThread);
+    T exc = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) exc = identity;
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
     if (threadIdx.x == 0) {
-        const long long last = min((long long)a.n_reads, tile + kProbeThreads * kProbePerThread) - 1;
-        s_lo = shard_of(a.read_off, a.n_shards, tile);
-        s_hi = shard_of(a.read_off, a.n_shards, last);
+        T run = identity;
+        for (int i = 0; i < kThreads / 32; ++i) { const T t = warp_tot[i]; warp_tot[i] = run; run = op(run, t); }
+        s_total = run;
     }
     __syncthreads();
-    const int lo = s_lo, hi = s_hi;
-    unsigned long long key[kProbePerThread];
-    int row[kProbePerThread];
-#pragma unroll
-    for (int u = 0; u < kProbePerThread; ++u) {
-        const long long r = tile + (long long)u * kProbeThreads + threadIdx.x;
-        row[u] = r < a.n_reads ? (int)r : -1;
-        key[u] = row[u] >= 0 ? __ldcs(a.read_key + r) : 0ull;
-    }
-    if (lo == hi) {
-        const int base = __ldg(a.tab_off + lo);
-        const unsigned mask = (unsigned)__ldg(a.tab_mask + lo);
-#pragma unroll
-        for (int u = 0; u < kProbePerThread; ++u)
-            if (row[u] >= 0) probe_one(a, key[u], row[u], base, mask);
-    } else {
-#pragma unroll
-        for (int u = 0; u < kProbePerThread; ++u) {
-            if (row[u] < 0) continue;
-            const int s = lo + shard_of(a.read_off + lo, hi - lo + 1, row[u]);
-            probe_one(a, key[u], row[u], __ldg(a.tab_off + s), (unsigned)__ldg(a.tab_mask + s));
-        }
-    }
+    const T res = op(warp_tot[w], exc);
+    if (total) *total = s_total;
+    __syncthreads();
+    return res;
 }
 
-// ------------------------------------------------------------------------------------------
-// k_reduce: one warp per SV.  Resolves each support read to its read row, then reduces.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-k_reduce(PhaseArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int sv = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (sv >= a.n_svs) return;
-    const long long b = __ldg(a.csr_off + sv), e = __ldg(a.csr_off + sv + 1);
-    // filter of :189-190
-    const bool kept = __ldg(a.sv_svlen + sv) >= c_thr.svlen_thres &&
-                      __ldg(a.sv_svread + sv) >= c_thr.suppread_thres &&
-                      !(__ldg(a.sv_flags + sv) & DUET_SV_GT_MISSING);
-    int hits = 0, ps_lo = INT32_MAX, ps_hi = INT32_MIN;
-    int h1 = 0, h2 = 0, nq = 0;
-    long long t1 = 0, t2 = 0;
-    long long first_q = INT64_MAX;      // CSR index of the first read with pc <= pc_max
-    int first_q_ps = 0;
-    for (long long j = b + lane; j < e; j += 32) {
-        const int slot = a.csr_slot[j];
-        const int row = a.tab_row[slot];
-        if (a.csr_key_hi && a.tab_hi[slot] != __ldg(a.csr_key_hi + j))
-            report(a.status, DUET_ERR_HASH_COLLISION, sv, (long long)__ldg(a.csr_key + j));
-        a.join_row[j] = row;
-        if (row >= 0) {
-            const int ps = __ldg(a.read_ps + row);
-            const int pc = __ldg(a.read_pc + row);
-            const int hp = __ldg(a.read_hp + row);
-            ++hits;
-            ps_lo = min(ps_lo, ps);
-            ps_hi = max(ps_hi, ps);
-            if (pc <= c_thr.pc_max) {
-                ++nq;
-                if (j < first_q) { first_q = j; first_q_ps = ps; }
-                if (hp == 1) { ++h1; t1 += pc; }
-                else if (hp == 2) { ++h2; t2 += pc; }
-            }
-        }
-    }
-    hits = warp_sum(hits);
-    ps_lo = warp_min(ps_lo);
-    ps_hi = warp_max(ps_hi);
-    h1 = warp_sum(h1); h2 = warp_sum(h2); nq = warp_sum(nq);
-    t1 = warp_sum(t1); t2 = warp_sum(t2);
-    // lane holding the globally first qualifying read
-    long long fq = first_q;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) fq = min(fq, __shfl_xor_sync(0xffffffffu, fq, o));
-    const unsigned owner = __ballot_sync(0xffffffffu, first_q == fq && fq != INT64_MAX);
-    const int fps = owner ? __shfl_sync(0xffffffffu, first_q_ps, __ffs(owner) - 1) : 0;
-    if (lane == 0) {
-        const int cls = hits == 0 ? 0 : (ps_lo == ps_hi ? 1 : 2);
-        a.n_hit[sv] = hits;
-        a.cls[sv] = kept ? (uint8_t)cls : (uint8_t)DUET_CLS_FILTERED;
-        a.gt[sv] = 0;
-        a.cand[sv] = (kept && cls == 1 && owner) ? (long long)fps : kNoCand;
-        // class-1 view of the statistics (:74-84); k_predict overwrites them for class 2
-        a.hap1[sv] = h1; a.hap2[sv] = h2; a.hap0[sv] = 0;
-        a.allhap[sv] = cls == 2 ? nq : h1 + h2;
-        a.totsc1[sv] = t1; a.totsc2[sv] = t2;
-        a.ps[sv] = owner ? ps_lo : 0;   // class 1: every joined read carries the same PS
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // block-wide bitonic sort of n_pad (power of two) elements, in shared or global memory
-// ------------------------------------------------------------------------------------------
 template <typename T>
 __device__ void block_bitonic_sort(T *v, int n_pad) {
     for (int k = 2; k <= n_pad; k <<= 1) {
@@ -296,75 +181,270 @@ __device__ __forceinline__ int next_pow2(int n) {
     return p;
 }
 
-constexpr int kSortThreads = 1024;
-constexpr int kOnepsSmemMaxElems = 16384;    // 128 KB of long long
-constexpr int kOrderSmemMaxElems = 8192;     // 128 KB of unsigned __int128
-
-// exclusive block scan of one int per thread (blockDim.x == kSortThreads); returns the prefix,
-// *total gets the block sum
-__device__ int block_exclusive_scan(int v, int *total) {
-    __shared__ int warp_tot[32];
-    __shared__ int s_total;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int n = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += n;
-    }
-    if (lane == 31) warp_tot[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-        int t = warp_tot[lane];
-        int ti = t;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, ti, o);
-            if (lane >= o) ti += n;
+// After a block has finished the SVs [sv0, sv1): credit every shard they belong to; shards whose
+// last SV this block completed are returned in s_list (smem) -- the caller then finishes them.
+// Counters reset themselves, so the next call starts from zero.
+__device__ int credit_shards(const PhaseArgs &a, int *done, int sv0, int sv1, int *s_list, int *s_n) {
+    __threadfence();                 // this block's per-SV results are visible device-wide ...
+    __syncthreads();                 // ... before thread 0 publishes the credit
+    if (threadIdx.x == 0) {
+        int n = 0;
+        if (sv0 < sv1) {
+            const int s_first = a.sv_shard[sv0], s_last = a.sv_shard[sv1 - 1];
+            for (int s = s_first; s <= s_last; ++s) {
+                const int lo = max((int)a.sv_off[s], sv0), hi = min((int)a.sv_off[s + 1], sv1);
+                const int total = (int)(a.sv_off[s + 1] - a.sv_off[s]);
+                if (hi <= lo) continue;
+                const int old = atomicAdd(done + s, hi - lo);
+                if (old + (hi - lo) == total) {
+                    done[s] = 0;
+                    if (n < kThreads) s_list[n++] = s;
+                }
+            }
         }
-        warp_tot[lane] = ti - t;
-        if (lane == 31) s_total = ti;
+        *s_n = n;
+        __threadfence();
     }
     __syncthreads();
-    const int res = warp_tot[w] + inc - v;
-    *total = s_total;
-    __syncthreads();
-    return res;
+    return *s_n;
 }
 
 // ------------------------------------------------------------------------------------------
-// k_oneps: one block per shard: sort the candidates, keep the distinct ones.
+// k_build: insert every support-read name into its shard's slot range.  G lanes per SV.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSortThreads)
-k_oneps(PhaseArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int s = blockIdx.x;
+template <int G>
+__global__ void __launch_bounds__(kThreads)
+k_build(PhaseArgs a) {
+    const int lane = threadIdx.x % G;
+    const int sv = (blockIdx.x * kThreads + threadIdx.x) / G;
+    if (sv >= a.n_svs) return;
+    const long long b = __ldg(a.csr_off + sv), e = __ldg(a.csr_off + sv + 1);
+    const int s = __ldg(a.sv_shard + sv);
+    const int base = __ldg(a.tab_off + s);
+    const unsigned mask = (unsigned)__ldg(a.tab_mask + s);
+    for (long long j = b + lane; j < e; j += G) {
+        const unsigned long long key = __ldg(a.csr_key + j);
+        unsigned p = slot_hash(key) & mask;
+        for (;;) {
+            const unsigned long long prev = atomicCAS(a.tab_key + base + p, kEmptyKey, key);
+            if (prev == kEmptyKey) {
+                if (a.csr_key_hi) a.tab_hi[base + p] = __ldg(a.csr_key_hi + j);
+                break;
+            }
+            if (prev == key) break;
+            p = (p + 1) & mask;
+        }
+        a.csr_slot[j] = base + (int)p;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_probe: stream the haplotagged reads through the table.  Each thread owns kProbePerThread
+// keys (16-byte loads), issues the first probe of all of them back to back, then resolves.
+// ------------------------------------------------------------------------------------------
+constexpr int kProbePerThread = 8;
+constexpr int kProbeTile = kThreads * kProbePerThread;
+
+__device__ __forceinline__ void probe_finish(const PhaseArgs &a, unsigned long long key, unsigned long long k,
+                                             unsigned p, int row, int base, unsigned mask) {
+    for (;;) {
+        if (k == key) {
+            if (a.read_key_hi && a.tab_hi[base + p] != __ldg(a.read_key_hi + row)) {
+                report(a.status, DUET_ERR_HASH_COLLISION, -1, (long long)key);
+                return;
+            }
+            atomicMax(a.tab_row + base + p, row);
+            return;
+        }
+        if (k == kEmptyKey) return;
+        p = (p + 1) & mask;
+        k = __ldcg(a.tab_key + base + p);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_probe(PhaseArgs a) {
+    const long long tile = (long long)blockIdx.x * kProbeTile;
+    const long long last = min((long long)a.n_reads, tile + kProbeTile) - 1;
+    // shard range of the tile: count the offsets <= first / last row, all threads at once
+    int lo, hi;
+    if (a.n_shards < kThreads) {
+        const long long off = threadIdx.x <= a.n_shards ? __ldg(a.read_off + threadIdx.x) : INT64_MAX;
+        lo = __syncthreads_count(off <= tile) - 1;
+        hi = __syncthreads_count(off <= last) - 1;
+    } else {
+        lo = shard_of(a.read_off, a.n_shards, tile);
+        hi = shard_of(a.read_off, a.n_shards, last);
+    }
+    unsigned long long key[kProbePerThread];
+    int row[kProbePerThread];
+#pragma unroll
+    for (int u = 0; u < kProbePerThread / 2; ++u) {
+        const long long r = tile + 2ll * (u * kThreads + threadIdx.x);
+        if (r + 1 < a.n_reads) {
+            const ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2 *>(a.read_key + r));
+            key[2 * u] = v.x; key[2 * u + 1] = v.y;
+            row[2 * u] = (int)r; row[2 * u + 1] = (int)r + 1;
+        } else {
+            row[2 * u] = r < a.n_reads ? (int)r : -1;
+            key[2 * u] = r < a.n_reads ? __ldcs(a.read_key + r) : 0ull;
+            row[2 * u + 1] = -1; key[2 * u + 1] = 0ull;
+        }
+    }
+    int base[kProbePerThread];
+    unsigned mask[kProbePerThread], p[kProbePerThread];
+    unsigned long long k[kProbePerThread];
+    if (lo == hi) {
+        const int b0 = __ldg(a.tab_off + lo);
+        const unsigned m0 = (unsigned)__ldg(a.tab_mask + lo);
+#pragma unroll
+        for (int u = 0; u < kProbePerThread; ++u) { base[u] = b0; mask[u] = m0; }
+    } else {
+#pragma unroll
+        for (int u = 0; u < kProbePerThread; ++u) {
+            const int s = row[u] >= 0 ? lo + shard_of(a.read_off + lo, hi - lo + 1, row[u]) : lo;
+            base[u] = __ldg(a.tab_off + s); mask[u] = (unsigned)__ldg(a.tab_mask + s);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kProbePerThread; ++u) {
+        p[u] = slot_hash(key[u]) & mask[u];
+        k[u] = row[u] >= 0 ? __ldcg(a.tab_key + base[u] + p[u]) : kEmptyKey;
+    }
+#pragma unroll
+    for (int u = 0; u < kProbePerThread; ++u)
+        if (k[u] != kEmptyKey) probe_finish(a, key[u], k[u], p[u], row[u], base[u], mask[u]);
+}
+
+// ------------------------------------------------------------------------------------------
+// one-PS list of a shard (called by the block that finished the shard in k_reduce)
+// ------------------------------------------------------------------------------------------
+__device__ void oneps_block(const PhaseArgs &a, int s, long long *smem_tile) {
     const int b = (int)a.sv_off[s], n = (int)a.sv_off[s + 1] - b;
-    if (n == 0) {
-        if (threadIdx.x == 0) a.oneps_n[s] = 0;
+    const int per = (n + kThreads - 1) / kThreads;
+    const int c0 = min(n, (int)threadIdx.x * per), c1 = min(n, c0 + per);
+    // fast path: the candidates already are non-decreasing in VCF order (position-sorted VCF)
+    long long mx = kNone;
+    for (int i = c0; i < c1; ++i) {
+        const long long v = __ldcg(a.cand + b + i);
+        if (v != kNoCand) mx = max(mx, v);
+    }
+    const long long run = block_scan_exclusive(mx, kNone, OpMax(), (long long *)nullptr);
+    long long cur = run;
+    int cnt = 0;
+    bool ok = true;
+    for (int i = c0; i < c1; ++i) {
+        const long long v = __ldcg(a.cand + b + i);
+        if (v == kNoCand) continue;
+        if (v < cur) ok = false;
+        else if (v > cur) { ++cnt; cur = v; }
+    }
+    if (__syncthreads_and(ok)) {
+        int total;
+        int w = block_scan_exclusive(cnt, 0, OpSum(), &total);
+        cur = run;
+        for (int i = c0; i < c1; ++i) {
+            const long long v = __ldcg(a.cand + b + i);
+            if (v != kNoCand && v > cur) { a.oneps[b + w++] = (int)v; cur = v; }
+        }
+        if (threadIdx.x == 0) a.oneps_n[s] = total;
         return;
     }
+    // slow path: sort, then keep the distinct values
     const int n_pad = next_pow2(n);
-    long long *v = n_pad <= a.oneps_smem_elems ? reinterpret_cast<long long *>(smem_raw)
-                                            : a.sort_scratch + 2ll * b;
-    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) v[i] = i < n ? a.cand[b + i] : kNoCand;
+    long long *v = n_pad * (int)sizeof(long long) <= kSortSmemBytes ? smem_tile : a.sort_scratch + 2ll * b;
+    for (int i = threadIdx.x; i < n_pad; i += kThreads) v[i] = i < n ? __ldcg(a.cand + b + i) : kNoCand;
     __syncthreads();
     block_bitonic_sort(v, n_pad);
-    // unique compaction: thread t owns the contiguous chunk [t*per, (t+1)*per)
-    const int per = (n_pad + blockDim.x - 1) / blockDim.x;
-    const int c0 = threadIdx.x * per, c1 = min(n_pad, c0 + per);
-    int cnt = 0;
-    for (int i = c0; i < c1; ++i)
-        cnt += (v[i] != kNoCand && (i == 0 || v[i] != v[i - 1])) ? 1 : 0;
+    const int per2 = (n_pad + kThreads - 1) / kThreads;
+    const int d0 = min(n_pad, (int)threadIdx.x * per2), d1 = min(n_pad, d0 + per2);
+    cnt = 0;
+    for (int i = d0; i < d1; ++i) cnt += (v[i] != kNoCand && (i == 0 || v[i] != v[i - 1])) ? 1 : 0;
     int total;
-    int w = block_exclusive_scan(cnt, &total);
-    for (int i = c0; i < c1; ++i)
+    int w = block_scan_exclusive(cnt, 0, OpSum(), &total);
+    for (int i = d0; i < d1; ++i)
         if (v[i] != kNoCand && (i == 0 || v[i] != v[i - 1])) a.oneps[b + w++] = (int)v[i];
     if (threadIdx.x == 0) a.oneps_n[s] = total;
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------
-// k_predict: one warp per kept SV.
+// k_reduce: G lanes per SV.  Resolves each support read to its read row, then reduces.
+// ------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(kThreads)
+k_reduce(PhaseArgs a) {
+    __shared__ __align__(16) long long s_tile[kSortSmemBytes / 8];
+    __shared__ int s_list[kThreads];
+    __shared__ int s_n;
+    const int lane = threadIdx.x % G;
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) / G * G));
+    const int sv0 = blockIdx.x * (kThreads / G);
+    const int sv1 = min(a.n_svs, sv0 + kThreads / G);
+    const int sv = sv0 + threadIdx.x / G;
+    const bool live = sv < a.n_svs;
+    long long b = 0, e = 0;
+    bool kept = false;
+    if (live) {
+        b = __ldg(a.csr_off + sv); e = __ldg(a.csr_off + sv + 1);
+        kept = __ldg(a.sv_svlen + sv) >= c_thr.svlen_thres &&                 // filter of :189-190
+               __ldg(a.sv_svread + sv) >= c_thr.suppread_thres &&
+               !(__ldg(a.sv_flags + sv) & DUET_SV_GT_MISSING);
+    }
+    int hits = 0, ps_lo = INT32_MAX, ps_hi = INT32_MIN;
+    int h1 = 0, h2 = 0, nq = 0;
+    long long t1 = 0, t2 = 0;
+    long long first_q = INT64_MAX;      // CSR index of the first read with pc <= pc_max
+    int first_q_ps = 0;
+    for (long long j = b + lane; j < e; j += G) {
+        const int slot = a.csr_slot[j];
+        const int row = __ldcg(a.tab_row + slot);
+        if (a.csr_key_hi && __ldcg(a.tab_hi + slot) != __ldg(a.csr_key_hi + j))
+            report(a.status, DUET_ERR_HASH_COLLISION, sv, (long long)__ldg(a.csr_key + j));
+        a.join_row[j] = row;
+        if (row >= 0) {
+            const int ps = __ldg(a.read_ps + row);
+            const int pc = __ldg(a.read_pc + row);
+            const int hp = __ldg(a.read_hp + row);
+            ++hits;
+            ps_lo = min(ps_lo, ps);
+            ps_hi = max(ps_hi, ps);
+            if (pc <= c_thr.pc_max) {
+                ++nq;
+                if (j < first_q) { first_q = j; first_q_ps = ps; }
+                if (hp == 1) { ++h1; t1 += pc; }
+                else if (hp == 2) { ++h2; t2 += pc; }
+            }
+        }
+    }
+    hits = group_sum(hits, gmask, G);
+    ps_lo = group_min(ps_lo, gmask, G);
+    ps_hi = group_max(ps_hi, gmask, G);
+    h1 = group_sum(h1, gmask, G); h2 = group_sum(h2, gmask, G); nq = group_sum(nq, gmask, G);
+    t1 = group_sum(t1, gmask, G); t2 = group_sum(t2, gmask, G);
+    const long long fq = group_min(first_q, gmask, G);
+    const unsigned owner = __ballot_sync(gmask, first_q == fq && fq != INT64_MAX) & gmask;
+    const int fps = __shfl_sync(gmask, first_q_ps, owner ? __ffs(owner) - 1 : (threadIdx.x & 31));
+    if (live && lane == 0) {
+        const int cls = hits == 0 ? 0 : (ps_lo == ps_hi ? 1 : 2);
+        a.n_hit[sv] = hits;
+        a.cls[sv] = kept ? (uint8_t)cls : (uint8_t)DUET_CLS_FILTERED;
+        a.gt[sv] = 0;
+        a.cand[sv] = (kept && cls == 1 && owner) ? (long long)fps : kNoCand;
+        // class-1 view of the statistics (:74-84); k_predict overwrites them for class 2
+        a.hap1[sv] = h1; a.hap2[sv] = h2; a.hap0[sv] = 0;
+        a.allhap[sv] = cls == 2 ? nq : h1 + h2;
+        a.totsc1[sv] = t1; a.totsc2[sv] = t2;
+        a.ps[sv] = owner ? ps_lo : 0;   // class 1: every joined read carries the same PS
+    }
+    if (live && lane < DUET_N_FEATURES) a.features[(size_t)lane * a.n_svs + sv] = 0.0;
+
+    const int n_done = credit_shards(a, a.done_reduce, sv0, sv1, s_list, &s_n);
+    for (int i = 0; i < n_done; ++i) oneps_block(a, s_list[i], s_tile);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_predict helpers
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool in_sorted(const int *__restrict__ v, int n, int x) {
     int lo = 0, hi = n;
@@ -444,85 +524,78 @@ __device__ void class2_slow(const PhaseArgs &a, long long b, long long e, const 
     }
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-k_predict(PhaseArgs a) {
-    __shared__ int d_ps[kWarpsPerBlock][kMaxDistinct];
-    __shared__ int d_cnt[kWarpsPerBlock][kMaxDistinct][3];           // tot, n1, n2
-    __shared__ unsigned long long d_sc[kWarpsPerBlock][kMaxDistinct][2];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int sv = blockIdx.x * kWarpsPerBlock + w;
-    if (sv >= a.n_svs) return;
-    const int cls = a.cls[sv];
-    if (cls == DUET_CLS_FILTERED) return;
-    const int s = shard_of(a.sv_off, a.n_shards, sv);
-    const int n_one = a.oneps_n[s];
-    if (n_one == 0) return;                                          // :209-210, gt stays 0
-    const int *oneps = a.oneps + a.sv_off[s];
-    const long long b = __ldg(a.csr_off + sv), e = __ldg(a.csr_off + sv + 1);
-    const int pos = __ldg(a.sv_pos + sv);
+struct Class2Smem {
+    int ps[kMaxDistinct];
+    int cnt[kMaxDistinct][3];                  // tot, n1, n2
+    unsigned long long sc[kMaxDistinct][2];
+};
 
-    Class2Stats st{a.hap1[sv], a.hap2[sv], 0, a.allhap[sv], a.ps[sv], a.totsc1[sv], a.totsc2[sv]};
-    if (cls == 0) { st.h1 = st.h2 = st.allhap = 0; st.t1 = st.t2 = 0; st.ps = 0; }   // get_phase_info skips both loops
-    if (cls == 2) {
-        st.h1 = st.h2 = st.hap0 = 0; st.t1 = st.t2 = 0; st.ps = 0;
-        int n_d = 0;
-        bool overflow = false;
-        for (long long base = b; base < e && !overflow; base += 32) {
-            const Entry x = load_entry(a, base + lane, e, oneps, n_one);
-            if (x.in && x.hp != 1 && x.hp != 2) report(a.status, DUET_ERR_BAD_HP, sv, x.hp);
-            int id = -1;
-            for (int t = 0; t < n_d; ++t)
-                if (x.in && d_ps[w][t] == x.ps) id = t;
-            unsigned fresh = __ballot_sync(0xffffffffu, x.in && id < 0);
-            while (fresh) {                                          // lane order = first-seen order
-                const int l0 = __ffs(fresh) - 1;
-                const int v = __shfl_sync(0xffffffffu, x.ps, l0);
-                const bool mine = x.in && id < 0 && x.ps == v;
-                if (n_d == kMaxDistinct) { overflow = true; break; }
-                if (lane == 0) {
-                    d_ps[w][n_d] = v;
-                    d_cnt[w][n_d][0] = d_cnt[w][n_d][1] = d_cnt[w][n_d][2] = 0;
-                    d_sc[w][n_d][0] = d_sc[w][n_d][1] = 0ull;
-                }
-                if (mine) id = n_d;
-                ++n_d;
-                fresh &= ~__ballot_sync(0xffffffffu, mine);
+// all 32 lanes: per-PS statistics of one class-2 SV (:85-105); result is warp-uniform
+__device__ void class2_stats(const PhaseArgs &a, int sv, long long b, long long e, const int *oneps, int n_one,
+                             Class2Smem &m, Class2Stats &st) {
+    const int lane = threadIdx.x & 31;
+    st.h1 = st.h2 = st.hap0 = 0; st.t1 = st.t2 = 0; st.ps = 0;
+    int n_d = 0;
+    bool overflow = false;
+    for (long long base = b; base < e && !overflow; base += 32) {
+        const Entry x = load_entry(a, base + lane, e, oneps, n_one);
+        if (x.in && x.hp != 1 && x.hp != 2) report(a.status, DUET_ERR_BAD_HP, sv, x.hp);
+        int id = -1;
+        for (int t = 0; t < n_d; ++t)
+            if (x.in && m.ps[t] == x.ps) id = t;
+        unsigned fresh = __ballot_sync(0xffffffffu, x.in && id < 0);
+        while (fresh) {                                          // lane order = first-seen order
+            const int l0 = __ffs(fresh) - 1;
+            const int v = __shfl_sync(0xffffffffu, x.ps, l0);
+            const bool mine = x.in && id < 0 && x.ps == v;
+            if (n_d == kMaxDistinct) { overflow = true; break; }
+            if (lane == 0) {
+                m.ps[n_d] = v;
+                m.cnt[n_d][0] = m.cnt[n_d][1] = m.cnt[n_d][2] = 0;
+                m.sc[n_d][0] = m.sc[n_d][1] = 0ull;
             }
-            __syncwarp();
-            if (!overflow && x.in && id >= 0) {
-                atomicAdd(&d_cnt[w][id][0], 1);
-                if (x.hp == 1 || x.hp == 2) {
-                    atomicAdd(&d_cnt[w][id][x.hp], 1);
-                    atomicAdd(&d_sc[w][id][x.hp - 1], (unsigned long long)(long long)x.pc);
-                }
-            }
-            __syncwarp();
+            if (mine) id = n_d;
+            ++n_d;
+            fresh &= ~__ballot_sync(0xffffffffu, mine);
         }
-        if (overflow) {
-            class2_slow(a, b, e, oneps, n_one, st);
-        } else {
-            int best = 0;
-            for (int t = 0; t < n_d; ++t) {                          // strict '>' keeps the first seen (:101)
-                if (d_cnt[w][t][0] > best) {
-                    best = d_cnt[w][t][0];
-                    st.h1 = d_cnt[w][t][1]; st.h2 = d_cnt[w][t][2];
-                    st.t1 = (long long)d_sc[w][t][0]; st.t2 = (long long)d_sc[w][t][1];
-                    st.ps = d_ps[w][t];
-                    st.hap0 = st.allhap - st.h1 - st.h2;
-                }
+        __syncwarp();
+        if (!overflow && x.in && id >= 0) {
+            atomicAdd(&m.cnt[id][0], 1);
+            if (x.hp == 1 || x.hp == 2) {
+                atomicAdd(&m.cnt[id][x.hp], 1);
+                atomicAdd(&m.sc[id][x.hp - 1], (unsigned long long)(long long)x.pc);
+            }
+        }
+        __syncwarp();
+    }
+    if (overflow) {
+        class2_slow(a, b, e, oneps, n_one, st);
+    } else {
+        int best = 0;
+        for (int t = 0; t < n_d; ++t) {                          // strict '>' keeps the first seen (:101)
+            if (m.cnt[t][0] > best) {
+                best = m.cnt[t][0];
+                st.h1 = m.cnt[t][1]; st.h2 = m.cnt[t][2];
+                st.t1 = (long long)m.sc[t][0]; st.t2 = (long long)m.sc[t][1];
+                st.ps = m.ps[t];
+                st.hap0 = st.allhap - st.h1 - st.h2;
             }
         }
     }
-    if (lane != 0) return;
+    __syncwarp();
+}
 
+// features (:112-132) and the T1-T5 tree (:142-183) of one SV; one thread
+__device__ void decide_and_store(const PhaseArgs &a, int sv, int cls, Class2Stats st, const int *oneps, int n_one,
+                                 int n_list) {
+    const int pos = __ldg(a.sv_pos + sv);
     if (cls == 0 || (st.h1 == 0 && st.h2 == 0)) st.ps = nearest_ps(oneps, n_one, pos);     // :106-111
-    const int n_list = (int)(e - b);
     const int svread = __ldg(a.sv_svread + sv), refread = __ldg(a.sv_refread + sv);
     if ((long long)svread + refread == 0 || n_list == 0) {
         report(a.status, DUET_ERR_ZERO_DIVISION, sv, 0);
         return;
     }
-    // features (:112-132): Python int/int true division == correctly rounded fp64 division
+    // Python int/int true division == correctly rounded fp64 division of the exact operands
     const double hapread_ratio = (double)st.allhap / (double)n_list;
     const double a1 = st.h1 > 0 ? (double)st.t1 / (double)st.h1 : 0.0;
     const double a2 = st.h2 > 0 ? (double)st.t2 / (double)st.h2 : 0.0;
@@ -569,41 +642,34 @@ k_predict(PhaseArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// k_order: one block per shard: emitted SVs sorted by (group, pos, class, VCF order); counters.
+// emission order + counters of a shard (called by the block that finished the shard in k_predict)
 // ------------------------------------------------------------------------------------------
 typedef unsigned __int128 u128;
 
-__global__ void __launch_bounds__(kSortThreads)
-k_order(PhaseArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ long long order_key(const PhaseArgs &a, int sv, int cls) {
+    const unsigned long long grp = a.sv_group ? (unsigned long long)(unsigned)__ldg(a.sv_group + sv) : 0ull;
+    const unsigned long long upos = (unsigned long long)((unsigned)__ldg(a.sv_pos + sv) ^ 0x80000000u);
+    return (long long)((grp << 34) | (upos << 2) | (unsigned long long)cls);      // < 2^50
+}
+
+__device__ void order_block(const PhaseArgs &a, int s, long long *smem_tile) {
     __shared__ unsigned long long s_cnt[DUET_N_COUNTERS];
-    const int s = blockIdx.x;
     const int b = (int)a.sv_off[s], n = (int)a.sv_off[s + 1] - b;
     if (threadIdx.x < DUET_N_COUNTERS) s_cnt[threadIdx.x] = 0ull;
     __syncthreads();
-    const u128 kPad = ~(u128)0;
-    const int n_pad = next_pow2(max(n, 1));
-    u128 *v = n_pad <= a.order_smem_elems ? reinterpret_cast<u128 *>(smem_raw)
-                                          : reinterpret_cast<u128 *>(a.sort_scratch) + 2ll * b;
+    const int per = (n + kThreads - 1) / kThreads;
+    const int c0 = min(n, (int)threadIdx.x * per), c1 = min(n, c0 + per);
     unsigned long long c_kept = 0, c_emit = 0, c10 = 0, c01 = 0, c11 = 0, c_hits = 0;
-    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
-        u128 key = kPad;
-        if (i < n) {
-            const int sv = b + i;
-            const int g = a.gt[sv];
-            const int cls = a.cls[sv];
-            c_hits += (unsigned long long)a.n_hit[sv];
-            if (cls != DUET_CLS_FILTERED) ++c_kept;
-            if (g != 0) {
-                ++c_emit;
-                c10 += g == 1; c01 += g == 2; c11 += g == 3;
-                const unsigned long long grp = a.sv_group ? (unsigned long long)(unsigned)a.sv_group[sv] : 0ull;
-                const unsigned long long upos = (unsigned long long)((unsigned)a.sv_pos[sv] ^ 0x80000000u);
-                const unsigned long long hi = (grp << 34) | (upos << 2) | (unsigned long long)cls;
-                key = ((u128)hi << 64) | (u128)(unsigned)i;
-            }
+    long long mx = kNone;
+    for (int i = c0; i < c1; ++i) {
+        const int sv = b + i;
+        const int g = __ldcg(a.gt + sv), cls = __ldcg(a.cls + sv);
+        c_hits += (unsigned long long)__ldcg(a.n_hit + sv);
+        c_kept += cls != DUET_CLS_FILTERED;
+        if (g != 0) {
+            ++c_emit; c10 += g == 1; c01 += g == 2; c11 += g == 3;
+            mx = max(mx, order_key(a, sv, cls));
         }
-        v[i] = key;
     }
     c_kept = warp_sum(c_kept); c_emit = warp_sum(c_emit); c10 = warp_sum(c10);
     c01 = warp_sum(c01); c11 = warp_sum(c11); c_hits = warp_sum(c_hits);
@@ -611,19 +677,111 @@ k_order(PhaseArgs a) {
         atomicAdd(&s_cnt[1], c_kept); atomicAdd(&s_cnt[2], c_emit); atomicAdd(&s_cnt[3], c10);
         atomicAdd(&s_cnt[4], c01); atomicAdd(&s_cnt[5], c11); atomicAdd(&s_cnt[7], c_hits);
     }
-    __syncthreads();
-    block_bitonic_sort(v, n_pad);
+    // fast path: emitted SVs already sorted by (group, pos, class) in VCF order
+    const long long run = block_scan_exclusive(mx, kNone, OpMax(), (long long *)nullptr);
+    long long cur = run;
+    int cnt = 0;
+    bool ok = true;
+    for (int i = c0; i < c1; ++i) {
+        const int sv = b + i;
+        if (__ldcg(a.gt + sv) == 0) continue;
+        const long long k = order_key(a, sv, __ldcg(a.cls + sv));
+        if (k < cur) ok = false;
+        cur = max(cur, k);
+        ++cnt;
+    }
+    const bool sorted = __syncthreads_and(ok);
     const int n_emit = (int)s_cnt[2];
-    for (int i = threadIdx.x; i < n_emit; i += blockDim.x) a.order[b + i] = b + (int)(unsigned)v[i];
+    if (sorted) {
+        int w = block_scan_exclusive(cnt, 0, OpSum(), (int *)nullptr);
+        for (int i = c0; i < c1; ++i)
+            if (__ldcg(a.gt + b + i) != 0) a.order[b + w++] = b + i;
+    } else {
+        const u128 kPad = ~(u128)0;
+        const int n_pad = next_pow2(max(n, 1));
+        u128 *v = n_pad * (int)sizeof(u128) <= kSortSmemBytes ? reinterpret_cast<u128 *>(smem_tile)
+                                                             : reinterpret_cast<u128 *>(a.sort_scratch) + 2ll * b;
+        for (int i = threadIdx.x; i < n_pad; i += kThreads) {
+            u128 key = kPad;
+            if (i < n && __ldcg(a.gt + b + i) != 0)
+                key = ((u128)(unsigned long long)order_key(a, b + i, __ldcg(a.cls + b + i)) << 64) | (u128)(unsigned)i;
+            v[i] = key;
+        }
+        __syncthreads();
+        block_bitonic_sort(v, n_pad);
+        for (int i = threadIdx.x; i < n_emit; i += kThreads) a.order[b + i] = b + (int)(unsigned)v[i];
+    }
     if (threadIdx.x == 0) {
         a.n_emit[s] = n_emit;
         long long *c = a.shard_counts + (size_t)s * DUET_N_COUNTERS;
         c[0] = n;
         c[1] = (long long)s_cnt[1]; c[2] = (long long)s_cnt[2]; c[3] = (long long)s_cnt[3];
         c[4] = (long long)s_cnt[4]; c[5] = (long long)s_cnt[5];
-        c[6] = n ? a.csr_off[b + n] - a.csr_off[b] : 0;
+        c[6] = a.csr_off[b + n] - a.csr_off[b];
         c[7] = (long long)s_cnt[7];
     }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// k_predict: a warp owns kSvPerWarpPredict consecutive SVs: lanes 0..7 decide one SV each, the
+// whole warp helps with the SVs that need the per-PS statistics (class 2), then clears the join
+// table slots of its SVs.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_predict(PhaseArgs a) {
+    __shared__ Class2Smem s_c2[kThreads / 32];
+    __shared__ __align__(16) long long s_tile[kSortSmemBytes / 8];
+    __shared__ int s_list[kThreads];
+    __shared__ int s_n;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    constexpr int kPerBlock = kThreads / 32 * kSvPerWarpPredict;
+    const int blk0 = blockIdx.x * kPerBlock, blk1 = min(a.n_svs, blk0 + kPerBlock);
+    const int w0 = blk0 + w * kSvPerWarpPredict, w1 = min(a.n_svs, w0 + kSvPerWarpPredict);
+    const int sv = w0 + lane;
+    const bool mine = lane < kSvPerWarpPredict && sv < w1;
+    int cls = DUET_CLS_FILTERED, n_one = 0;
+    const int *oneps = nullptr;
+    long long b = 0, e = 0;
+    Class2Stats st{0, 0, 0, 0, 0, 0, 0};
+    if (mine) {
+        cls = a.cls[sv];
+        const int s = __ldg(a.sv_shard + sv);
+        b = __ldg(a.csr_off + sv); e = __ldg(a.csr_off + sv + 1);
+        if (cls != DUET_CLS_FILTERED) {
+            n_one = a.oneps_n[s];                                       // 0: contig skipped (:209-210)
+            oneps = a.oneps + __ldg(a.sv_off + s);
+            if (cls == 1) st = Class2Stats{a.hap1[sv], a.hap2[sv], 0, a.allhap[sv], a.ps[sv], a.totsc1[sv], a.totsc2[sv]};
+            if (cls == 2) st.allhap = a.allhap[sv];
+        }
+    }
+    const bool go = mine && cls != DUET_CLS_FILTERED && n_one > 0;
+    unsigned need = __ballot_sync(0xffffffffu, go && cls == 2);
+    while (need) {
+        const int l = __ffs(need) - 1;
+        need &= need - 1;
+        const int sv2 = w0 + l;
+        const long long b2 = __shfl_sync(0xffffffffu, b, l), e2 = __shfl_sync(0xffffffffu, e, l);
+        const int n2 = __shfl_sync(0xffffffffu, n_one, l);
+        const int *o2 = a.oneps + __ldg(a.sv_off + __ldg(a.sv_shard + sv2));
+        Class2Stats t{0, 0, 0, __shfl_sync(0xffffffffu, st.allhap, l), 0, 0, 0};
+        class2_stats(a, sv2, b2, e2, o2, n2, s_c2[w], t);
+        if (lane == l) st = t;
+    }
+    if (go) decide_and_store(a, sv, cls, st, oneps, n_one, (int)(e - b));
+
+    // the table is not read after k_reduce: hand it back EMPTY for the next call
+    if (w0 < w1) {
+        const long long jb = __ldg(a.csr_off + w0), je = __ldg(a.csr_off + w1);
+        for (long long j = jb + lane; j < je; j += 32) {
+            const int slot = a.csr_slot[j];
+            a.tab_key[slot] = kEmptyKey;
+            a.tab_row[slot] = -1;
+        }
+    }
+
+    const int n_done = credit_shards(a, a.done_predict, blk0, blk1, s_list, &s_n);
+    for (int i = 0; i < n_done; ++i) order_block(a, s_list[i], s_tile);
 }
 
 }  // namespace duet
