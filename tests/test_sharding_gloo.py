@@ -1,0 +1,88 @@
+"""Host-side multi-GPU plumbing on CPU: world_size-2 gloo processes run the contig-sharded stage
+with the oracle standing in for the device (phase_fn injection) and must produce the
+byte-identical phased_sv.vcf the unmodified reference produced, plus the same counter table."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from conftest import ROOT, load_golden, materialise
+from duet_b200 import sharding
+
+
+def test_lpt_assign_balances_and_is_deterministic():
+    w = [249, 243, 198, 191, 181, 171, 159, 146, 141, 135, 135, 133, 115, 107, 102, 90, 81, 78, 59, 63, 48, 51, 155, 59]
+    for n in (1, 2, 4, 8):
+        plan = sharding.lpt_assign(w, n)
+        assert sorted(i for p in plan for i in p) == list(range(24))
+        loads = [sum(w[i] for i in p) for p in plan]
+        assert max(loads) <= sum(w) / n * 1.12 + 1
+        assert plan == sharding.lpt_assign(w, n)
+
+
+def test_slice_first_ids():
+    assert sharding.slice_first_ids([["1"], ["10"], [], ["chr1"]], [5, 7, 0, 2]) == [1, 6, 0, 13]
+    assert sharding.slice_first_ids([["1"], ["1"]], [1, 1]) is None
+    assert sharding.slice_first_ids([["1", "chr1"]], [3]) is None
+
+
+def _oracle_phase_fn(batch, svlen_thres, suppread_thres):
+    from duet_b200.engine import PhaseResult
+    from oracle.columnar_adapter import phase_batch_oracle
+    o = phase_batch_oracle(batch, svlen_thres, suppread_thres)
+    return PhaseResult(o.gt, o.ps, o.cls, o.hap1, o.hap2, o.hap0, o.allhap, o.totsc1, o.totsc2, o.features,
+                       o.join_row, o.order, o.shard_counts)
+
+
+def _worker(rank, world, port, home, svlen, supp, out_q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        counts = sharding.sv_phasing_sharded(home, svlen, supp, 1, False, phase_fn=_oracle_phase_fn)
+        out_q.put((rank, counts))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("name", ["cutesv_3ctg", "mixed_prefix", "svim_shuffled"])
+def test_two_rank_stage_is_byte_identical(name, tmp_path):
+    case = load_golden(f"e2e_{name}.json.gz")
+    home = materialise(case, str(tmp_path))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, home, case["svlen_thres"], case["suppread_thres"], q))
+             for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    with open(home + "/phased_sv.vcf") as f:
+        assert f.read() == case["phased_sv_vcf"]
+    assert np.array_equal(got[0], got[1])                      # every rank holds the whole counter table
+    assert got[0][:, 2].sum() == len(case["rows"])
+    assert not [fn for fn in os.listdir(home) if ".slice." in fn]
+
+
+def test_single_process_path_matches_too(tmp_path):
+    case = load_golden("e2e_sniffles_chr.json.gz")
+    home = materialise(case, str(tmp_path))
+    counts = sharding.sv_phasing_sharded(home, case["svlen_thres"], case["suppread_thres"], 1, False,
+                                         phase_fn=_oracle_phase_fn, rank=0, world=1)
+    with open(home + "/phased_sv.vcf") as f:
+        assert f.read() == case["phased_sv_vcf"]
+    assert counts[:, 2].sum() == len(case["rows"])
