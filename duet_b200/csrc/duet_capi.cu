@@ -61,7 +61,7 @@ struct duet_handle {
     DevBuf in_sv_pos, in_sv_svlen, in_sv_svread, in_sv_refread, in_sv_flags, in_sv_group;
     DevBuf in_csr_off, in_csr_key, in_csr_key_hi;
     // descriptors, table, scratch, outputs
-    DevBuf d_read_off, d_sv_off, d_sv_shard, d_tab_off, d_tab_mask, d_done;
+    DevBuf d_read_off, d_sv_off, d_join_off, d_sv_shard, d_tab_off, d_tab_mask, d_done, d_c2;
     DevBuf d_table;                 // [tab_key | tab_row] cleared with one memset
     DevBuf d_tab_hi, d_csr_slot, d_join_row, d_n_hit, d_cand, d_oneps, d_oneps_n, d_sort;
     DevBuf d_gt, d_cls, d_ps, d_hap1, d_hap2, d_hap0, d_allhap, d_t1, d_t2, d_feat, d_order, d_n_emit;
@@ -166,7 +166,7 @@ void duet_destroy(duet_handle *h) {
     DevBuf *bufs[] = {&h->in_read_key, &h->in_read_key_hi, &h->in_read_hp, &h->in_read_ps, &h->in_read_pc,
                       &h->in_sv_pos, &h->in_sv_svlen, &h->in_sv_svread, &h->in_sv_refread, &h->in_sv_flags,
                       &h->in_sv_group, &h->in_csr_off, &h->in_csr_key, &h->in_csr_key_hi, &h->d_read_off,
-                      &h->d_sv_off, &h->d_sv_shard, &h->d_done, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_tab_hi, &h->d_csr_slot,
+                      &h->d_sv_off, &h->d_join_off, &h->d_c2, &h->d_sv_shard, &h->d_done, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_tab_hi, &h->d_csr_slot,
                       &h->d_join_row, &h->d_n_hit, &h->d_cand, &h->d_oneps, &h->d_oneps_n, &h->d_sort, &h->d_gt,
                       &h->d_cls, &h->d_ps, &h->d_hap1, &h->d_hap2, &h->d_hap0, &h->d_allhap, &h->d_t1, &h->d_t2,
                       &h->d_feat, &h->d_order, &h->d_n_emit, &h->d_counts, &h->d_status};
@@ -243,11 +243,15 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     }
     if (csr[0] != 0 || csr[S] != J) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: csr_off does not span csr_key");
     std::vector<int> tab_off(ns), tab_mask(ns);
+    std::vector<long long> join_off(ns + 1);
+    for (int s = 0; s <= ns; ++s) join_off[s] = csr[in->sv_off[s]];
+    // load factor <= 1/4 while the table stays comfortably inside L2, <= 1/2 beyond that
+    const long long fill = J <= (1ll << 20) ? 4 : 2;
     long long slots = 0, max_sv = 0;
     for (int s = 0; s < ns; ++s) {
-        const long long nj = csr[in->sv_off[s + 1]] - csr[in->sv_off[s]];
+        const long long nj = join_off[s + 1] - join_off[s];
         if (nj < 0) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: csr_off is not monotone");
-        const long long cap = pow2_at_least(std::max<long long>(2 * nj, 32));
+        const long long cap = pow2_at_least(std::max<long long>(fill * nj, 32));
         tab_off[s] = (int)slots;
         tab_mask[s] = (int)(cap - 1);
         slots += cap;
@@ -287,6 +291,8 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     a.read_off = static_cast<const long long *>(dv);
     if ((rc = stage(h, h->d_sv_off, h->h_sv_off.data(), sizeof(long long) * (ns + 1), DUET_MEM_HOST, &dv))) return rc;
     a.sv_off = static_cast<const long long *>(dv);
+    if ((rc = stage(h, h->d_join_off, join_off.data(), sizeof(long long) * (ns + 1), DUET_MEM_HOST, &dv))) return rc;
+    a.join_off = static_cast<const long long *>(dv);
     std::vector<int> sv_shard((size_t)S);
     for (int s = 0; s < ns; ++s)
         std::fill(sv_shard.begin() + in->sv_off[s], sv_shard.begin() + in->sv_off[s + 1], s);
@@ -314,6 +320,8 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     CU(h, h->d_done.reserve((size_t)ns * 8));            a.done_reduce = h->d_done.as<int>();
     a.done_predict = a.done_reduce + ns;
     CU(h, h->d_sort.reserve(S1 * 32));                   a.sort_scratch = h->d_sort.as<long long>();
+    CU(h, h->d_c2.reserve(S1 * 4 + 16));                 a.c2_count = h->d_c2.as<int>();
+    a.c2_list = a.c2_count + 4;
     h->group = (S > 0 && J / std::max<long long>(S, 1) > 24) ? 32 : 16;
     CU(h, h->d_gt.reserve(S1));                          a.gt = h->d_gt.as<uint8_t>();
     CU(h, h->d_cls.reserve(S1));                         a.cls = h->d_cls.as<uint8_t>();
@@ -332,6 +340,7 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     // state the kernels keep clean between calls: EMPTY table, zero counters / credits / status
     CU(h, cudaMemsetAsync(h->d_table.p, 0xFF, (size_t)slots * 12, st));
     CU(h, cudaMemsetAsync(h->d_done.p, 0, (size_t)ns * 8, st));
+    CU(h, cudaMemsetAsync(h->d_c2.p, 0, 16, st));
     CU(h, cudaMemsetAsync(h->d_oneps_n.p, 0, (size_t)ns * 4, st));
     CU(h, cudaMemsetAsync(h->d_n_emit.p, 0, (size_t)ns * 4, st));
     CU(h, cudaMemsetAsync(h->d_counts.p, 0, (size_t)ns * 8 * DUET_N_COUNTERS, st));
@@ -355,9 +364,8 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
     auto mark = [&](int ev) { if (h->per_kernel) cudaEventRecord(h->ev[ev], st); };
     CU(h, cudaEventRecord(h->ev[EV_X0], st));
     const int S = a.n_svs, G = h->group;
-    if (S && a.n_joins) {
-        const int blocks = (S + kThreads / G - 1) / (kThreads / G);
-        if (G == 16) k_build<16><<<blocks, kThreads, 0, st>>>(a); else k_build<32><<<blocks, kThreads, 0, st>>>(a);
+    if (a.n_joins) {
+        k_build<<<(a.n_joins + kThreads - 1) / kThreads, kThreads, 0, st>>>(a);
         ++h->launches;
     }
     mark(EV_K1);
@@ -373,8 +381,7 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
     }
     mark(EV_K3);
     if (S) {
-        constexpr int per_block = kThreads / 32 * kSvPerWarpPredict;
-        k_predict<<<(S + per_block - 1) / per_block, kThreads, 0, st>>>(a);
+        k_predict<<<(S + kPredictPerBlock - 1) / kPredictPerBlock, kThreads, 0, st>>>(a);
         ++h->launches;
     }
     CU(h, cudaEventRecord(h->ev[EV_K4], st));

@@ -46,6 +46,7 @@ struct PhaseArgs {
     // inputs (device)
     const long long *read_off;   // [n_shards+1]
     const long long *sv_off;     // [n_shards+1]
+    const long long *join_off;   // [n_shards+1] csr_off at the shard boundaries (derived at upload)
     const int *sv_shard;         // [S] shard of each SV (derived at upload)
     const unsigned long long *read_key, *read_key_hi;
     const uint8_t *read_hp;
@@ -70,6 +71,8 @@ struct PhaseArgs {
     int *oneps_n;                // [n_shards]
     int *done_reduce;            // [n_shards] SVs of the shard finished by k_reduce (self-resetting)
     int *done_predict;           // [n_shards] same for k_predict
+    int *c2_list;                // [S] kept class-2 SVs, any order (k_reduce appends, k_predict consumes)
+    int *c2_count;               // [1] reset by k_build
     long long *sort_scratch;     // [4*S] global tile for slow-path sorts of big shards
     uint8_t *gt, *cls;
     int *ps, *hap1, *hap2, *hap0, *allhap;
@@ -129,6 +132,7 @@ __device__ __forceinline__ T warp_sum(T v) { return group_sum(v, 0xffffffffu, 32
 
 struct OpSum { template <typename T> __device__ T operator()(T a, T b) const { return a + b; } };
 struct OpMax { template <typename T> __device__ T operator()(T a, T b) const { return a > b ? a : b; } };
+struct OpLast { __device__ long long operator()(long long a, long long b) const { return b != (long long)0x8000000000000000ull ? b : a; } };
 
 // exclusive block scan (blockDim.x == kThreads); *total receives the reduction over the block
 template <typename T, typename Op>
@@ -210,72 +214,81 @@ __device__ int credit_shards(const PhaseArgs &a, int *done, int sv0, int sv1, in
 }
 
 // ------------------------------------------------------------------------------------------
-// k_build: insert every support-read name into its shard's slot range.  G lanes per SV.
+// tile -> shard range: count the offsets <= first / last element of the tile, all threads at once
 // ------------------------------------------------------------------------------------------
-template <int G>
-__global__ void __launch_bounds__(kThreads)
-k_build(PhaseArgs a) {
-    const int lane = threadIdx.x % G;
-    const int sv = (blockIdx.x * kThreads + threadIdx.x) / G;
-    if (sv >= a.n_svs) return;
-    const long long b = __ldg(a.csr_off + sv), e = __ldg(a.csr_off + sv + 1);
-    const int s = __ldg(a.sv_shard + sv);
-    const int base = __ldg(a.tab_off + s);
-    const unsigned mask = (unsigned)__ldg(a.tab_mask + s);
-    for (long long j = b + lane; j < e; j += G) {
-        const unsigned long long key = __ldg(a.csr_key + j);
-        unsigned p = slot_hash(key) & mask;
-        for (;;) {
-            const unsigned long long prev = atomicCAS(a.tab_key + base + p, kEmptyKey, key);
-            if (prev == kEmptyKey) {
-                if (a.csr_key_hi) a.tab_hi[base + p] = __ldg(a.csr_key_hi + j);
-                break;
-            }
-            if (prev == key) break;
-            p = (p + 1) & mask;
-        }
-        a.csr_slot[j] = base + (int)p;
+__device__ __forceinline__ void tile_shards(const long long *__restrict__ off, int n_shards, long long first,
+                                            long long last, int &lo, int &hi) {
+    if (n_shards < kThreads) {
+        const long long o = (int)threadIdx.x <= n_shards ? __ldg(off + threadIdx.x) : INT64_MAX;
+        lo = __syncthreads_count(o <= first) - 1;
+        hi = __syncthreads_count(o <= last) - 1;
+    } else {
+        lo = shard_of(off, n_shards, first);
+        hi = shard_of(off, n_shards, last);
     }
 }
 
 // ------------------------------------------------------------------------------------------
+// k_build: insert every support-read name into its shard's slot range.  One thread per name.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_build(PhaseArgs a) {
+    const long long tile = (long long)blockIdx.x * kThreads;
+    const long long j = tile + threadIdx.x;
+    if (j == 0) *a.c2_count = 0;
+    int lo, hi;
+    tile_shards(a.join_off, a.n_shards, tile, min((long long)a.n_joins, tile + kThreads) - 1, lo, hi);
+    if (j >= a.n_joins) return;
+    const unsigned long long key = __ldcs(a.csr_key + j);
+    const int s = lo == hi ? lo : lo + shard_of(a.join_off + lo, hi - lo + 1, j);
+    const int base = __ldg(a.tab_off + s);
+    const unsigned mask = (unsigned)__ldg(a.tab_mask + s);
+    unsigned p = slot_hash(key) & mask;
+    for (;;) {
+        const unsigned long long prev = atomicCAS(a.tab_key + base + p, kEmptyKey, key);
+        if (prev == kEmptyKey) {
+            if (a.csr_key_hi) a.tab_hi[base + p] = __ldg(a.csr_key_hi + j);
+            break;
+        }
+        if (prev == key) break;
+        p = (p + 1) & mask;
+    }
+    a.csr_slot[j] = base + (int)p;
+}
+
+// ------------------------------------------------------------------------------------------
 // k_probe: stream the haplotagged reads through the table.  Each thread owns kProbePerThread
-// keys (16-byte loads), issues the first probe of all of them back to back, then resolves.
+// keys (16-byte loads), issues the first probe of all of them back to back, then resolves the
+// unfinished ones in lock step (one load per pending key per round; a continuation probe is the
+// adjacent slot, usually the same 32-byte sector, so it hits L1).
 // ------------------------------------------------------------------------------------------
 constexpr int kProbePerThread = 8;
 constexpr int kProbeTile = kThreads * kProbePerThread;
 
-__device__ __forceinline__ void probe_finish(const PhaseArgs &a, unsigned long long key, unsigned long long k,
-                                             unsigned p, int row, int base, unsigned mask) {
+__device__ __forceinline__ void probe_hit(const PhaseArgs &a, unsigned long long key, int slot, int row) {
+    if (a.read_key_hi && a.tab_hi[slot] != __ldg(a.read_key_hi + row)) {
+        report(a.status, DUET_ERR_HASH_COLLISION, -1, (long long)key);
+        return;
+    }
+    atomicMax(a.tab_row + slot, row);
+}
+
+__device__ __forceinline__ void probe_one(const PhaseArgs &a, unsigned long long key, int row, int base,
+                                          unsigned mask) {
+    unsigned p = slot_hash(key) & mask;
     for (;;) {
-        if (k == key) {
-            if (a.read_key_hi && a.tab_hi[base + p] != __ldg(a.read_key_hi + row)) {
-                report(a.status, DUET_ERR_HASH_COLLISION, -1, (long long)key);
-                return;
-            }
-            atomicMax(a.tab_row + base + p, row);
-            return;
-        }
+        const unsigned long long k = a.tab_key[base + p];
+        if (k == key) { probe_hit(a, key, base + (int)p, row); return; }
         if (k == kEmptyKey) return;
         p = (p + 1) & mask;
-        k = __ldcg(a.tab_key + base + p);
     }
 }
 
 __global__ void __launch_bounds__(kThreads)
 k_probe(PhaseArgs a) {
     const long long tile = (long long)blockIdx.x * kProbeTile;
-    const long long last = min((long long)a.n_reads, tile + kProbeTile) - 1;
-    // shard range of the tile: count the offsets <= first / last row, all threads at once
     int lo, hi;
-    if (a.n_shards < kThreads) {
-        const long long off = threadIdx.x <= a.n_shards ? __ldg(a.read_off + threadIdx.x) : INT64_MAX;
-        lo = __syncthreads_count(off <= tile) - 1;
-        hi = __syncthreads_count(off <= last) - 1;
-    } else {
-        lo = shard_of(a.read_off, a.n_shards, tile);
-        hi = shard_of(a.read_off, a.n_shards, last);
-    }
+    tile_shards(a.read_off, a.n_shards, tile, min((long long)a.n_reads, tile + kProbeTile) - 1, lo, hi);
     unsigned long long key[kProbePerThread];
     int row[kProbePerThread];
 #pragma unroll
@@ -291,29 +304,41 @@ k_probe(PhaseArgs a) {
             row[2 * u + 1] = -1; key[2 * u + 1] = 0ull;
         }
     }
-    int base[kProbePerThread];
-    unsigned mask[kProbePerThread], p[kProbePerThread];
-    unsigned long long k[kProbePerThread];
-    if (lo == hi) {
-        const int b0 = __ldg(a.tab_off + lo);
-        const unsigned m0 = (unsigned)__ldg(a.tab_mask + lo);
-#pragma unroll
-        for (int u = 0; u < kProbePerThread; ++u) { base[u] = b0; mask[u] = m0; }
-    } else {
+    if (lo != hi) {                      // a tile straddling a contig boundary: rare, generic path
 #pragma unroll
         for (int u = 0; u < kProbePerThread; ++u) {
-            const int s = row[u] >= 0 ? lo + shard_of(a.read_off + lo, hi - lo + 1, row[u]) : lo;
-            base[u] = __ldg(a.tab_off + s); mask[u] = (unsigned)__ldg(a.tab_mask + s);
+            if (row[u] < 0) continue;
+            const int s = lo + shard_of(a.read_off + lo, hi - lo + 1, row[u]);
+            probe_one(a, key[u], row[u], __ldg(a.tab_off + s), (unsigned)__ldg(a.tab_mask + s));
         }
+        return;
     }
+    const int base = __ldg(a.tab_off + lo);
+    const unsigned mask = (unsigned)__ldg(a.tab_mask + lo);
+    unsigned p[kProbePerThread];
+    unsigned long long k[kProbePerThread];
 #pragma unroll
     for (int u = 0; u < kProbePerThread; ++u) {
-        p[u] = slot_hash(key[u]) & mask[u];
-        k[u] = row[u] >= 0 ? __ldcg(a.tab_key + base[u] + p[u]) : kEmptyKey;
+        p[u] = slot_hash(key[u]) & mask;
+        k[u] = row[u] >= 0 ? a.tab_key[base + p[u]] : kEmptyKey;
     }
+    unsigned pend = 0;
 #pragma unroll
-    for (int u = 0; u < kProbePerThread; ++u)
-        if (k[u] != kEmptyKey) probe_finish(a, key[u], k[u], p[u], row[u], base[u], mask[u]);
+    for (int u = 0; u < kProbePerThread; ++u) {
+        if (k[u] == key[u] && row[u] >= 0) probe_hit(a, key[u], base + (int)p[u], row[u]);
+        else if (k[u] != kEmptyKey) pend |= 1u << u;
+    }
+    while (pend) {
+#pragma unroll
+        for (int u = 0; u < kProbePerThread; ++u)
+            if (pend >> u & 1u) { p[u] = (p[u] + 1) & mask; k[u] = a.tab_key[base + p[u]]; }
+#pragma unroll
+        for (int u = 0; u < kProbePerThread; ++u)
+            if (pend >> u & 1u) {
+                if (k[u] == key[u]) { probe_hit(a, key[u], base + (int)p[u], row[u]); pend &= ~(1u << u); }
+                else if (k[u] == kEmptyKey) pend &= ~(1u << u);
+            }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -350,10 +375,58 @@ __device__ void oneps_block(const PhaseArgs &a, int s, long long *smem_tile) {
         if (threadIdx.x == 0) a.oneps_n[s] = total;
         return;
     }
-    // slow path: sort, then keep the distinct values
-    const int n_pad = next_pow2(n);
-    long long *v = n_pad * (int)sizeof(long long) <= kSortSmemBytes ? smem_tile : a.sort_scratch + 2ll * b;
-    for (int i = threadIdx.x; i < n_pad; i += kThreads) v[i] = i < n ? __ldcg(a.cand + b + i) : kNoCand;
+    // slow path.  First squeeze runs of equal neighbours (a nearly sorted list of a few hundred
+    // phase sets stays a few hundred long), then rank-count small sets or sort big ones.
+    __shared__ unsigned char s_first[512];
+    long long lastv = kNone;
+    for (int i = c0; i < c1; ++i) {
+        const long long v = __ldcg(a.cand + b + i);
+        if (v != kNoCand) lastv = v;
+    }
+    const long long prev0 = block_scan_exclusive(lastv, kNone, OpLast(), (long long *)nullptr);
+    long long prev = prev0;
+    cnt = 0;
+    for (int i = c0; i < c1; ++i) {
+        const long long v = __ldcg(a.cand + b + i);
+        if (v == kNoCand) continue;
+        cnt += v != prev;
+        prev = v;
+    }
+    int r;
+    int w = block_scan_exclusive(cnt, 0, OpSum(), &r);
+    long long *v = (long long)next_pow2(max(r, 1)) * (long long)sizeof(long long) <= kSortSmemBytes
+                       ? smem_tile : a.sort_scratch + 2ll * b;
+    prev = prev0;
+    for (int i = c0; i < c1; ++i) {
+        const long long x = __ldcg(a.cand + b + i);
+        if (x == kNoCand) continue;
+        if (x != prev) v[w++] = x;
+        prev = x;
+    }
+    __syncthreads();
+    if (r <= 512) {
+        for (int h = threadIdx.x; h < r; h += kThreads) {
+            const long long x = v[h];
+            bool first = true;
+            for (int t = 0; t < h; ++t) first &= v[t] != x;
+            s_first[h] = first;
+        }
+        __syncthreads();
+        int total = 0;
+        for (int h = threadIdx.x; h < r; h += kThreads) {
+            if (!s_first[h]) continue;
+            const long long x = v[h];
+            int rank = 0;
+            for (int t = 0; t < r; ++t) rank += s_first[t] && v[t] < x;
+            a.oneps[b + rank] = (int)x;
+        }
+        for (int t = 0; t < r; ++t) total += s_first[t];
+        if (threadIdx.x == 0) a.oneps_n[s] = total;
+        __syncthreads();
+        return;
+    }
+    const int n_pad = next_pow2(r);
+    for (int i = r + threadIdx.x; i < n_pad; i += kThreads) v[i] = kNoCand;
     __syncthreads();
     block_bitonic_sort(v, n_pad);
     const int per2 = (n_pad + kThreads - 1) / kThreads;
@@ -361,7 +434,7 @@ __device__ void oneps_block(const PhaseArgs &a, int s, long long *smem_tile) {
     cnt = 0;
     for (int i = d0; i < d1; ++i) cnt += (v[i] != kNoCand && (i == 0 || v[i] != v[i - 1])) ? 1 : 0;
     int total;
-    int w = block_scan_exclusive(cnt, 0, OpSum(), &total);
+    w = block_scan_exclusive(cnt, 0, OpSum(), &total);
     for (int i = d0; i < d1; ++i)
         if (v[i] != kNoCand && (i == 0 || v[i] != v[i - 1])) a.oneps[b + w++] = (int)v[i];
     if (threadIdx.x == 0) a.oneps_n[s] = total;
@@ -436,6 +509,7 @@ k_reduce(PhaseArgs a) {
         a.allhap[sv] = cls == 2 ? nq : h1 + h2;
         a.totsc1[sv] = t1; a.totsc2[sv] = t2;
         a.ps[sv] = owner ? ps_lo : 0;   // class 1: every joined read carries the same PS
+        if (kept && cls == 2) a.c2_list[atomicAdd(a.c2_count, 1)] = sv;
     }
     if (live && lane < DUET_N_FEATURES) a.features[(size_t)lane * a.n_svs + sv] = 0.0;
 
@@ -528,9 +602,13 @@ struct Class2Smem {
     int ps[kMaxDistinct];
     int cnt[kMaxDistinct][3];                  // tot, n1, n2
     unsigned long long sc[kMaxDistinct][2];
+    int bad[kMaxDistinct];                     // an HP outside {1,2} was seen with this PS
 };
 
-// all 32 lanes: per-PS statistics of one class-2 SV (:85-105); result is warp-uniform
+// all 32 lanes: per-PS statistics of one class-2 SV (:85-105); result is warp-uniform.
+// The distinct PS values of the qualifying reads are collected in first-seen order; membership in
+// the one-PS set is then tested once per distinct value (not once per read) -- the in-set values
+// keep their relative first-seen order, which is what the reference's dict iteration sees.
 __device__ void class2_stats(const PhaseArgs &a, int sv, long long b, long long e, const int *oneps, int n_one,
                              Class2Smem &m, Class2Stats &st) {
     const int lane = threadIdx.x & 31;
@@ -538,42 +616,60 @@ __device__ void class2_stats(const PhaseArgs &a, int sv, long long b, long long 
     int n_d = 0;
     bool overflow = false;
     for (long long base = b; base < e && !overflow; base += 32) {
-        const Entry x = load_entry(a, base + lane, e, oneps, n_one);
-        if (x.in && x.hp != 1 && x.hp != 2) report(a.status, DUET_ERR_BAD_HP, sv, x.hp);
+        const long long j = base + lane;
+        bool q = false;
+        int ps = 0, pc = 0, hp = 0;
+        if (j < e) {
+            const int row = a.join_row[j];
+            if (row >= 0) {
+                pc = __ldg(a.read_pc + row); ps = __ldg(a.read_ps + row); hp = __ldg(a.read_hp + row);
+                q = pc <= c_thr.pc_max;
+            }
+        }
         int id = -1;
         for (int t = 0; t < n_d; ++t)
-            if (x.in && m.ps[t] == x.ps) id = t;
-        unsigned fresh = __ballot_sync(0xffffffffu, x.in && id < 0);
+            if (q && m.ps[t] == ps) id = t;
+        unsigned fresh = __ballot_sync(0xffffffffu, q && id < 0);
         while (fresh) {                                          // lane order = first-seen order
             const int l0 = __ffs(fresh) - 1;
-            const int v = __shfl_sync(0xffffffffu, x.ps, l0);
-            const bool mine = x.in && id < 0 && x.ps == v;
+            const int v = __shfl_sync(0xffffffffu, ps, l0);
+            const bool mine = q && id < 0 && ps == v;
             if (n_d == kMaxDistinct) { overflow = true; break; }
             if (lane == 0) {
                 m.ps[n_d] = v;
                 m.cnt[n_d][0] = m.cnt[n_d][1] = m.cnt[n_d][2] = 0;
                 m.sc[n_d][0] = m.sc[n_d][1] = 0ull;
+                m.bad[n_d] = 0;
             }
             if (mine) id = n_d;
             ++n_d;
             fresh &= ~__ballot_sync(0xffffffffu, mine);
         }
         __syncwarp();
-        if (!overflow && x.in && id >= 0) {
+        if (!overflow && q && id >= 0) {
             atomicAdd(&m.cnt[id][0], 1);
-            if (x.hp == 1 || x.hp == 2) {
-                atomicAdd(&m.cnt[id][x.hp], 1);
-                atomicAdd(&m.sc[id][x.hp - 1], (unsigned long long)(long long)x.pc);
+            if (hp == 1 || hp == 2) {
+                atomicAdd(&m.cnt[id][hp], 1);
+                atomicAdd(&m.sc[id][hp - 1], (unsigned long long)(long long)pc);
+            } else {
+                m.bad[id] = hp | 0x100;
             }
         }
         __syncwarp();
     }
     if (overflow) {
         class2_slow(a, b, e, oneps, n_one, st);
+        for (long long j = b + lane; j < e; j += 32) {           // the KeyError of :96
+            const Entry x = load_entry(a, j, e, oneps, n_one);
+            if (x.in && x.hp != 1 && x.hp != 2) report(a.status, DUET_ERR_BAD_HP, sv, x.hp);
+        }
     } else {
+        const bool in = lane < n_d && in_sorted(oneps, n_one, m.ps[lane]);
+        const unsigned in_mask = __ballot_sync(0xffffffffu, in);
+        if (in && m.bad[lane]) report(a.status, DUET_ERR_BAD_HP, sv, m.bad[lane] & 0xff);
         int best = 0;
         for (int t = 0; t < n_d; ++t) {                          // strict '>' keeps the first seen (:101)
-            if (m.cnt[t][0] > best) {
+            if ((in_mask >> t & 1u) && m.cnt[t][0] > best) {
                 best = m.cnt[t][0];
                 st.h1 = m.cnt[t][1]; st.h2 = m.cnt[t][2];
                 st.t1 = (long long)m.sc[t][0]; st.t2 = (long long)m.sc[t][1];
@@ -724,63 +820,95 @@ __device__ void order_block(const PhaseArgs &a, int s, long long *smem_tile) {
 }
 
 // ------------------------------------------------------------------------------------------
-// k_predict: a warp owns kSvPerWarpPredict consecutive SVs: lanes 0..7 decide one SV each, the
-// whole warp helps with the SVs that need the per-PS statistics (class 2), then clears the join
-// table slots of its SVs.
+// k_predict.  Three independent pieces of work per block:
+//   A  class-2 SVs come from the compact list k_reduce wrote -- one warp per SV, spread over the grid;
+//   B  threads 0..63 decide one class-0/1 SV each (SVs blockIdx*64 ...);
+//   C  the join table slots set by k_build are handed back EMPTY (grid-stride over the support reads).
+// Every finished SV credits its shard; whoever completes a shard queues it and the block then writes
+// that shard's emission order and counters.
 // ------------------------------------------------------------------------------------------
+constexpr int kPredictPerBlock = 64;
+
+__device__ __forceinline__ void credit_one(const PhaseArgs &a, int s, int n, int *s_list, int *s_n) {
+    const int total = (int)(a.sv_off[s + 1] - a.sv_off[s]);
+    __threadfence();
+    if (atomicAdd(a.done_predict + s, n) + n == total) {
+        a.done_predict[s] = 0;
+        const int k = atomicAdd(s_n, 1);
+        if (k < kThreads) s_list[k] = s;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_predict(PhaseArgs a) {
     __shared__ Class2Smem s_c2[kThreads / 32];
     __shared__ __align__(16) long long s_tile[kSortSmemBytes / 8];
     __shared__ int s_list[kThreads];
+    __shared__ int s_credit[kPredictPerBlock];
     __shared__ int s_n;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    constexpr int kPerBlock = kThreads / 32 * kSvPerWarpPredict;
-    const int blk0 = blockIdx.x * kPerBlock, blk1 = min(a.n_svs, blk0 + kPerBlock);
-    const int w0 = blk0 + w * kSvPerWarpPredict, w1 = min(a.n_svs, w0 + kSvPerWarpPredict);
-    const int sv = w0 + lane;
-    const bool mine = lane < kSvPerWarpPredict && sv < w1;
-    int cls = DUET_CLS_FILTERED, n_one = 0;
-    const int *oneps = nullptr;
-    long long b = 0, e = 0;
-    Class2Stats st{0, 0, 0, 0, 0, 0, 0};
-    if (mine) {
-        cls = a.cls[sv];
+    if (threadIdx.x == 0) s_n = 0;
+    if (threadIdx.x < kPredictPerBlock) s_credit[threadIdx.x] = -1;    // shard credited by thread t's SV
+    __syncthreads();
+
+    // ---- A: class-2 SVs, one warp each
+    const int n_c2 = *a.c2_count;
+    for (int k = blockIdx.x * (kThreads / 32) + w; k < n_c2; k += gridDim.x * (kThreads / 32)) {
+        const int sv2 = a.c2_list[k];
+        const int s = __ldg(a.sv_shard + sv2);
+        const int n_one = a.oneps_n[s];
+        if (n_one > 0) {                                             // else contig skipped (:209-210)
+            const long long b2 = __ldg(a.csr_off + sv2), e2 = __ldg(a.csr_off + sv2 + 1);
+            const int *o2 = a.oneps + __ldg(a.sv_off + s);
+            Class2Stats t{0, 0, 0, a.allhap[sv2], 0, 0, 0};
+            class2_stats(a, sv2, b2, e2, o2, n_one, s_c2[w], t);
+            if (lane == 0) decide_and_store(a, sv2, 2, t, o2, n_one, (int)(e2 - b2));
+        }
+        if (lane == 0) credit_one(a, s, 1, s_list, &s_n);
+    }
+
+    // ---- B: everything that is not a kept class-2 SV
+    const int blk0 = blockIdx.x * kPredictPerBlock, blk1 = min(a.n_svs, blk0 + kPredictPerBlock);
+    const int sv = blk0 + threadIdx.x;
+    if (threadIdx.x < kPredictPerBlock && sv < blk1) {
+        const int cls = a.cls[sv];
         const int s = __ldg(a.sv_shard + sv);
-        b = __ldg(a.csr_off + sv); e = __ldg(a.csr_off + sv + 1);
-        if (cls != DUET_CLS_FILTERED) {
-            n_one = a.oneps_n[s];                                       // 0: contig skipped (:209-210)
-            oneps = a.oneps + __ldg(a.sv_off + s);
-            if (cls == 1) st = Class2Stats{a.hap1[sv], a.hap2[sv], 0, a.allhap[sv], a.ps[sv], a.totsc1[sv], a.totsc2[sv]};
-            if (cls == 2) st.allhap = a.allhap[sv];
+        if (cls == 0 || cls == 1) {
+            const int n_one = a.oneps_n[s];
+            if (n_one > 0) {
+                Class2Stats st{0, 0, 0, 0, 0, 0, 0};
+                if (cls == 1) st = Class2Stats{a.hap1[sv], a.hap2[sv], 0, a.allhap[sv], a.ps[sv], a.totsc1[sv], a.totsc2[sv]};
+                decide_and_store(a, sv, cls, st, a.oneps + __ldg(a.sv_off + s), n_one,
+                                 (int)(__ldg(a.csr_off + sv + 1) - __ldg(a.csr_off + sv)));
+            }
         }
-    }
-    const bool go = mine && cls != DUET_CLS_FILTERED && n_one > 0;
-    unsigned need = __ballot_sync(0xffffffffu, go && cls == 2);
-    while (need) {
-        const int l = __ffs(need) - 1;
-        need &= need - 1;
-        const int sv2 = w0 + l;
-        const long long b2 = __shfl_sync(0xffffffffu, b, l), e2 = __shfl_sync(0xffffffffu, e, l);
-        const int n2 = __shfl_sync(0xffffffffu, n_one, l);
-        const int *o2 = a.oneps + __ldg(a.sv_off + __ldg(a.sv_shard + sv2));
-        Class2Stats t{0, 0, 0, __shfl_sync(0xffffffffu, st.allhap, l), 0, 0, 0};
-        class2_stats(a, sv2, b2, e2, o2, n2, s_c2[w], t);
-        if (lane == l) st = t;
-    }
-    if (go) decide_and_store(a, sv, cls, st, oneps, n_one, (int)(e - b));
-
-    // the table is not read after k_reduce: hand it back EMPTY for the next call
-    if (w0 < w1) {
-        const long long jb = __ldg(a.csr_off + w0), je = __ldg(a.csr_off + w1);
-        for (long long j = jb + lane; j < je; j += 32) {
-            const int slot = a.csr_slot[j];
-            a.tab_key[slot] = kEmptyKey;
-            a.tab_row[slot] = -1;
-        }
+        if (cls != 2) s_credit[threadIdx.x] = s;
     }
 
-    const int n_done = credit_shards(a, a.done_predict, blk0, blk1, s_list, &s_n);
+    // ---- C: the table is not read after k_reduce
+    for (long long j = (long long)blockIdx.x * kThreads + threadIdx.x; j < a.n_joins; j += (long long)gridDim.x * kThreads) {
+        const int slot = a.csr_slot[j];
+        a.tab_key[slot] = kEmptyKey;
+        a.tab_row[slot] = -1;
+    }
+
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run_s = -1, run_n = 0;
+        for (int t = 0; t < kPredictPerBlock; ++t) {                 // shards are contiguous in SV order
+            const int s = s_credit[t];
+            if (s < 0) continue;
+            if (s != run_s) {
+                if (run_n) credit_one(a, run_s, run_n, s_list, &s_n);
+                run_s = s; run_n = 0;
+            }
+            ++run_n;
+        }
+        if (run_n) credit_one(a, run_s, run_n, s_list, &s_n);
+    }
+    __syncthreads();
+    const int n_done = min(s_n, kThreads);
     for (int i = 0; i < n_done; ++i) order_block(a, s_list[i], s_tile);
 }
 
