@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between steps (not a valid bench line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -198,7 +199,8 @@ def main():
         evs = []
         with torch.cuda.stream(stream):
             for _ in range(n):
-                flush.zero_()                               # evict the previous step from L2
+                if not args.no_flush:
+                    flush.zero_()                           # evict the previous step from L2
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(stream)
                 eng.execute(per_kernel)
@@ -302,7 +304,8 @@ def main():
                        "reads_tagged_per_gpu": batch.n_reads, "svs_per_gpu": batch.n_svs,
                        "joins_per_gpu": batch.n_joins, "shards_per_gpu": batch.n_shards,
                        "parallelism": f"shard=(sample,contig); {world} GPU(s), no data-path collective",
-                       "l2": "flushed between steps (512 MiB memset outside the event pair)",
+                       "l2": "NOT FLUSHED (diagnostic run, invalid as a bench line)" if args.no_flush else
+                             "flushed between steps (512 MiB memset outside the event pair)",
                        "thresholds": "svlen>=50, support>=2 (reference defaults)"},
             "clocks": clocks.summary(),
             "e2e": {"value": n_svs / (e2e_s / args.steps), "unit": "SV/s", "ms_per_step": e2e_s / args.steps * 1e3,

@@ -53,7 +53,8 @@ struct duet_handle {
 
     PhaseArgs a;                    // device view
     std::vector<long long> h_read_off, h_sv_off;
-    long long n_slots = 0;
+    long long n_slots = 0, n_bm_words = 0;
+    int n_sm = 148;
     int group = 16;                 // lanes per SV in k_build / k_reduce
 
     // staged input copies (HOST mode)
@@ -62,8 +63,8 @@ struct duet_handle {
     DevBuf in_csr_off, in_csr_key, in_csr_key_hi;
     // descriptors, table, scratch, outputs
     DevBuf d_read_off, d_sv_off, d_join_off, d_sv_shard, d_tab_off, d_tab_mask, d_done, d_c2;
-    DevBuf d_table;                 // [tab_key | tab_row] cleared with one memset
-    DevBuf d_tab_hi, d_csr_slot, d_join_row, d_n_hit, d_cand, d_oneps, d_oneps_n, d_sort;
+    DevBuf d_table;                 // Slot[n_slots], all-ones when idle
+    DevBuf d_bitmap, d_bm_off, d_bm_wmask, d_next, d_bmword, d_csr_slot, d_join_row, d_n_hit, d_cand, d_oneps, d_oneps_n, d_sort;
     DevBuf d_gt, d_cls, d_ps, d_hap1, d_hap2, d_hap0, d_allhap, d_t1, d_t2, d_feat, d_order, d_n_emit;
     DevBuf d_counts, d_status;
 };
@@ -150,6 +151,8 @@ int duet_create(int device_id, duet_handle **out) {
     {   // fails here, loudly, if the image was not built for this device (sm_100a only)
         cudaFuncAttributes fa;
         cudaFuncGetAttributes(&fa, k_probe);
+        cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, kBloomMaxWords * 4);
+        cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device_id);
     }
     if (cudaGetLastError() != cudaSuccess) {
         delete h;
@@ -166,7 +169,7 @@ void duet_destroy(duet_handle *h) {
     DevBuf *bufs[] = {&h->in_read_key, &h->in_read_key_hi, &h->in_read_hp, &h->in_read_ps, &h->in_read_pc,
                       &h->in_sv_pos, &h->in_sv_svlen, &h->in_sv_svread, &h->in_sv_refread, &h->in_sv_flags,
                       &h->in_sv_group, &h->in_csr_off, &h->in_csr_key, &h->in_csr_key_hi, &h->d_read_off,
-                      &h->d_sv_off, &h->d_join_off, &h->d_c2, &h->d_sv_shard, &h->d_done, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_tab_hi, &h->d_csr_slot,
+                      &h->d_sv_off, &h->d_join_off, &h->d_c2, &h->d_sv_shard, &h->d_done, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_bitmap, &h->d_bm_off, &h->d_bm_wmask, &h->d_next, &h->d_bmword, &h->d_csr_slot,
                       &h->d_join_row, &h->d_n_hit, &h->d_cand, &h->d_oneps, &h->d_oneps_n, &h->d_sort, &h->d_gt,
                       &h->d_cls, &h->d_ps, &h->d_hap1, &h->d_hap2, &h->d_hap0, &h->d_allhap, &h->d_t1, &h->d_t2,
                       &h->d_feat, &h->d_order, &h->d_n_emit, &h->d_counts, &h->d_status};
@@ -242,12 +245,13 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         csr = csr_host.data();
     }
     if (csr[0] != 0 || csr[S] != J) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: csr_off does not span csr_key");
-    std::vector<int> tab_off(ns), tab_mask(ns);
+    std::vector<int> tab_off(ns), tab_mask(ns), bm_off(ns), bm_wmask(ns);
     std::vector<long long> join_off(ns + 1);
     for (int s = 0; s <= ns; ++s) join_off[s] = csr[in->sv_off[s]];
-    // load factor <= 1/4 while the table stays comfortably inside L2, <= 1/2 beyond that
-    const long long fill = J <= (1ll << 20) ? 4 : 2;
-    long long slots = 0, max_sv = 0;
+    // slot table: load factor <= 1/2 (32-byte slots; only occupied sectors are ever touched by hits).
+    // Bloom filter: 16 bits per name, at most 128 KB per shard (it has to fit in shared memory).
+    const long long fill = 2;
+    long long slots = 0, max_sv = 0, bm_words = 0;
     for (int s = 0; s < ns; ++s) {
         const long long nj = join_off[s + 1] - join_off[s];
         if (nj < 0) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: csr_off is not monotone");
@@ -255,10 +259,15 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         tab_off[s] = (int)slots;
         tab_mask[s] = (int)(cap - 1);
         slots += cap;
+        const long long words = std::min<long long>(pow2_at_least(std::max<long long>(nj / 2, 32)), kBloomMaxWords);
+        bm_off[s] = (int)bm_words;
+        bm_wmask[s] = (int)(words - 1);
+        bm_words += words;
         max_sv = std::max<long long>(max_sv, in->sv_off[s + 1] - in->sv_off[s]);
         if (slots >= (1ll << 31)) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: join table too large");
     }
     h->n_slots = slots;
+    h->n_bm_words = bm_words;
     h->h_read_off.assign(in->read_off, in->read_off + ns + 1);
     h->h_sv_off.assign(in->sv_off, in->sv_off + ns + 1);
 
@@ -303,14 +312,18 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     a.tab_off = static_cast<const int *>(dv);
     if ((rc = stage(h, h->d_tab_mask, tab_mask.data(), sizeof(int) * ns, DUET_MEM_HOST, &dv))) return rc;
     a.tab_mask = static_cast<const int *>(dv);
+    if ((rc = stage(h, h->d_bm_off, bm_off.data(), sizeof(int) * ns, DUET_MEM_HOST, &dv))) return rc;
+    a.bm_off = static_cast<const int *>(dv);
+    if ((rc = stage(h, h->d_bm_wmask, bm_wmask.data(), sizeof(int) * ns, DUET_MEM_HOST, &dv))) return rc;
+    a.bm_wmask = static_cast<const int *>(dv);
     CU(h, cudaEventRecord(h->ev[EV_H2D1], st));
     h->have_h2d = true;
 
     const size_t S1 = (size_t)std::max<long long>(S, 1), J1 = (size_t)std::max<long long>(J, 1);
-    CU(h, h->d_table.reserve((size_t)slots * 12));
-    a.tab_key = h->d_table.as<unsigned long long>();
-    a.tab_row = reinterpret_cast<int *>(a.tab_key + slots);
-    CU(h, h->d_tab_hi.reserve((size_t)slots * 8));       a.tab_hi = h->d_tab_hi.as<unsigned long long>();
+    CU(h, h->d_table.reserve((size_t)slots * sizeof(Slot)));  a.tab = h->d_table.as<Slot>();
+    CU(h, h->d_bitmap.reserve((size_t)bm_words * 4));    a.bitmap = h->d_bitmap.as<unsigned>();
+    CU(h, h->d_next.reserve(J1 * 4));                    a.next = h->d_next.as<int>();
+    CU(h, h->d_bmword.reserve(J1 * 4));                  a.csr_bmword = h->d_bmword.as<int>();
     CU(h, h->d_csr_slot.reserve(J1 * 4));                a.csr_slot = h->d_csr_slot.as<int>();
     CU(h, h->d_join_row.reserve(J1 * 4));                a.join_row = h->d_join_row.as<int>();
     CU(h, h->d_n_hit.reserve(S1 * 4));                   a.n_hit = h->d_n_hit.as<int>();
@@ -338,7 +351,9 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     CU(h, h->d_counts.reserve((size_t)ns * 8 * DUET_N_COUNTERS)); a.shard_counts = h->d_counts.as<long long>();
     CU(h, h->d_status.reserve(sizeof(DevStatus)));       a.status = h->d_status.as<DevStatus>();
     // state the kernels keep clean between calls: EMPTY table, zero counters / credits / status
-    CU(h, cudaMemsetAsync(h->d_table.p, 0xFF, (size_t)slots * 12, st));
+    CU(h, cudaMemsetAsync(h->d_table.p, 0xFF, (size_t)slots * sizeof(Slot), st));
+    CU(h, cudaMemsetAsync(h->d_bitmap.p, 0, (size_t)bm_words * 4, st));
+    CU(h, cudaMemsetAsync(h->d_join_row.p, 0xFF, J1 * 4, st));
     CU(h, cudaMemsetAsync(h->d_done.p, 0, (size_t)ns * 8, st));
     CU(h, cudaMemsetAsync(h->d_c2.p, 0, 16, st));
     CU(h, cudaMemsetAsync(h->d_oneps_n.p, 0, (size_t)ns * 4, st));
@@ -370,7 +385,7 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
     }
     mark(EV_K1);
     if (a.n_reads && a.n_joins) {
-        k_probe<<<(a.n_reads + kProbeTile - 1) / kProbeTile, kThreads, 0, st>>>(a);
+        k_probe<<<h->n_sm, kProbeThreads, kBloomMaxWords * 4, st>>>(a);
         ++h->launches;
     }
     mark(EV_K2);

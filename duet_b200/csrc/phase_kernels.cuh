@@ -32,6 +32,17 @@ constexpr int kThreads = 256;                         // every kernel
 constexpr int kMaxDistinct = 32;                      // distinct in-set PS per SV handled in smem
 constexpr int kSvPerWarpPredict = 8;
 constexpr int kSortSmemBytes = 16384;                 // slow-path sort tile in shared memory
+constexpr int kStage = 16;                            // per-thread register staging in the shard epilogues
+constexpr int kBloomMaxWords = 32768;                 // 128 KB of shared memory per shard filter
+
+// One slot of the join table = one 32-byte sector: everything a probe needs arrives together.
+struct __align__(32) Slot {
+    unsigned long long key;   // low 64 bits of the name hash, kEmptyKey when free
+    unsigned long long hi;    // high 64 bits (collision check)
+    int head;                 // most recently inserted support-read entry with this name, -1 none
+    int multi;                // the name occurs in more than one entry (chain through `next`)
+    int pad[2];
+};
 
 struct DevStatus {          // device -> host error report
     int code;               // first DUET_ERR_* seen (atomicCAS from 0)
@@ -59,12 +70,16 @@ struct PhaseArgs {
     // join table: shard s owns slots [tab_off[s], tab_off[s] + tab_mask[s] + 1)
     const int *tab_off;          // [n_shards]
     const int *tab_mask;         // [n_shards]
-    unsigned long long *tab_key; // [n_slots] EMPTY between calls (k_predict clears what k_build set)
-    unsigned long long *tab_hi;  // [n_slots] hi word of the inserting name (collision check)
-    int *tab_row;                // [n_slots] max matching read row, -1 = none
+    Slot *tab;                   // [n_slots] all-ones between calls (k_predict clears what k_build set)
     int *csr_slot;               // [J] slot of each support-read name
+    int *next;                   // [J] next entry carrying the same name, -1 none
+    int *csr_bmword;             // [J] filter word of each support-read name
+    // per-shard Bloom filter over the support-read names: words [bm_off[s], bm_off[s] + bm_wmask[s] + 1)
+    const int *bm_off;           // [n_shards]
+    const int *bm_wmask;         // [n_shards] (power of two) - 1
+    unsigned *bitmap;            // zero between calls (k_predict clears what k_build set)
     // per-SV intermediates / outputs (device)
-    int *join_row;               // [J]
+    int *join_row;               // [J] row each support read joined to (atomicMax by k_probe), -1 = miss
     int *n_hit;                  // [S] joined reads of the SV
     long long *cand;             // [S] one-PS candidate or kNoCand
     int *oneps;                  // [S] shard s: sorted unique list at [sv_off[s], +oneps_n[s])
@@ -229,180 +244,186 @@ __device__ __forceinline__ void tile_shards(const long long *__restrict__ off, i
 }
 
 // ------------------------------------------------------------------------------------------
-// k_build: insert every support-read name into its shard's slot range.  One thread per name.
+// Bloom filter bit pattern of a key: one 32-bit word, two bits (a probe is one shared-memory load)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned bloom_word(unsigned long long key, unsigned wmask) {
+    return (unsigned)(key >> 40) & wmask;
+}
+__device__ __forceinline__ unsigned bloom_bits(unsigned long long key) {
+    return (1u << ((unsigned)(key >> 5) & 31u)) | (1u << ((unsigned)(key >> 10) & 31u));
+}
+
+// ------------------------------------------------------------------------------------------
+// k_build: one thread per support-read name: insert it into its shard's slot range, chain the
+// entry to the slot, set its filter bits, reset its join result.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 k_build(PhaseArgs a) {
     const long long tile = (long long)blockIdx.x * kThreads;
     const long long j = tile + threadIdx.x;
+    const unsigned long long key = j < a.n_joins ? __ldcs(a.csr_key + j) : 0ull;     // in flight during the lookup
     if (j == 0) *a.c2_count = 0;
     int lo, hi;
     tile_shards(a.join_off, a.n_shards, tile, min((long long)a.n_joins, tile + kThreads) - 1, lo, hi);
     if (j >= a.n_joins) return;
-    const unsigned long long key = __ldcs(a.csr_key + j);
     const int s = lo == hi ? lo : lo + shard_of(a.join_off + lo, hi - lo + 1, j);
     const int base = __ldg(a.tab_off + s);
     const unsigned mask = (unsigned)__ldg(a.tab_mask + s);
+    const int bmo = __ldg(a.bm_off + s);
+    const unsigned bmw = (unsigned)__ldg(a.bm_wmask + s);
+    a.join_row[j] = -1;
+    const int word = bmo + (int)bloom_word(key, bmw);
+    atomicOr(a.bitmap + word, bloom_bits(key));
+    a.csr_bmword[j] = word;
     unsigned p = slot_hash(key) & mask;
     for (;;) {
-        const unsigned long long prev = atomicCAS(a.tab_key + base + p, kEmptyKey, key);
+        const unsigned long long prev = atomicCAS(&a.tab[base + p].key, kEmptyKey, key);
         if (prev == kEmptyKey) {
-            if (a.csr_key_hi) a.tab_hi[base + p] = __ldg(a.csr_key_hi + j);
+            if (a.csr_key_hi) a.tab[base + p].hi = __ldg(a.csr_key_hi + j);
             break;
         }
         if (prev == key) break;
         p = (p + 1) & mask;
     }
-    a.csr_slot[j] = base + (int)p;
+    const int slot = base + (int)p;
+    const int before = atomicExch(&a.tab[slot].head, (int)j);
+    a.next[j] = before;
+    if (before >= 0) a.tab[slot].multi = 1;
+    a.csr_slot[j] = slot;
 }
 
 // ------------------------------------------------------------------------------------------
-// k_probe: stream the haplotagged reads through the table.  Each thread owns kProbePerThread
-// keys (16-byte loads), issues the first probe of all of them back to back, then resolves the
-// unfinished ones in lock step (one load per pending key per round; a continuation probe is the
-// adjacent slot, usually the same 32-byte sector, so it hits L1).
+// k_probe: the haplotagged reads are STREAMED once (16-byte loads, kProbeUnroll pairs in flight
+// per thread) by a persistent grid -- one block per SM, each owning a contiguous row range.  The
+// block keeps the current contig's Bloom filter in shared memory, so ~90 % of the rows (reads that
+// support no SV) are rejected without leaving the SM; the rest probe the slot table in L2 and
+// push their row index to every support-read entry of that name with atomicMax (a later row
+// overrides an earlier one, sv_phasing_fn.py:29).
 // ------------------------------------------------------------------------------------------
-constexpr int kProbePerThread = 8;
-constexpr int kProbeTile = kThreads * kProbePerThread;
+constexpr int kProbeThreads = 1024;
+constexpr int kProbeUnroll = 4;
 
-__device__ __forceinline__ void probe_hit(const PhaseArgs &a, unsigned long long key, int slot, int row) {
-    if (a.read_key_hi && a.tab_hi[slot] != __ldg(a.read_key_hi + row)) {
-        report(a.status, DUET_ERR_HASH_COLLISION, -1, (long long)key);
-        return;
-    }
-    atomicMax(a.tab_row + slot, row);
-}
-
-__device__ __forceinline__ void probe_one(const PhaseArgs &a, unsigned long long key, int row, int base,
-                                          unsigned mask) {
+__device__ __forceinline__ void probe_slot(const PhaseArgs &a, unsigned long long key, int row, int base,
+                                           unsigned mask) {
     unsigned p = slot_hash(key) & mask;
     for (;;) {
-        const unsigned long long k = a.tab_key[base + p];
-        if (k == key) { probe_hit(a, key, base + (int)p, row); return; }
+        const Slot *sl = a.tab + base + p;
+        const unsigned long long k = sl->key;
+        if (k == key) {
+            int j = sl->head;
+            const int multi = sl->multi;
+            if (a.read_key_hi && sl->hi != __ldg(a.read_key_hi + row))
+                report(a.status, DUET_ERR_HASH_COLLISION, -1, (long long)key);
+            atomicMax(a.join_row + j, row);
+            if (multi == 1)
+                for (j = a.next[j]; j >= 0; j = a.next[j]) atomicMax(a.join_row + j, row);
+            return;
+        }
         if (k == kEmptyKey) return;
         p = (p + 1) & mask;
     }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kProbeThreads, 1)
 k_probe(PhaseArgs a) {
-    const long long tile = (long long)blockIdx.x * kProbeTile;
-    int lo, hi;
-    tile_shards(a.read_off, a.n_shards, tile, min((long long)a.n_reads, tile + kProbeTile) - 1, lo, hi);
-    unsigned long long key[kProbePerThread];
-    int row[kProbePerThread];
+    extern __shared__ unsigned s_bm[];
+    const long long R = a.n_reads;
+    long long per = (R + gridDim.x - 1) / gridDim.x;
+    per += per & 1;                                              // ranges start on a 16-byte boundary
+    long long r0 = min(R, (long long)blockIdx.x * per);
+    const long long r_end = min(R, r0 + per);
+    if (r0 >= r_end) return;
+    int s = shard_of(a.read_off, a.n_shards, r0);
+    while (r0 < r_end) {
+        while (__ldg(a.read_off + s + 1) <= r0) ++s;             // skip contigs without reads
+        const long long r1 = min(r_end, (long long)__ldg(a.read_off + s + 1));
+        const int base = __ldg(a.tab_off + s);
+        const unsigned mask = (unsigned)__ldg(a.tab_mask + s);
+        const unsigned bmw = (unsigned)__ldg(a.bm_wmask + s);
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.bitmap + __ldg(a.bm_off + s));
+        for (int i = threadIdx.x; i < (int)(bmw + 1) / 4; i += kProbeThreads)
+            reinterpret_cast<uint4 *>(s_bm)[i] = src[i];
+        __syncthreads();
+        // pairs of rows (2q, 2q+1); a pair cut by the range edge is shared with the neighbour
+        const long long q1 = (r1 + 1) >> 1;
+        for (long long q = (r0 >> 1) + threadIdx.x; q < q1; q += (long long)kProbeThreads * kProbeUnroll) {
+            ulonglong2 v[kProbeUnroll];
 #pragma unroll
-    for (int u = 0; u < kProbePerThread / 2; ++u) {
-        const long long r = tile + 2ll * (u * kThreads + threadIdx.x);
-        if (r + 1 < a.n_reads) {
-            const ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2 *>(a.read_key + r));
-            key[2 * u] = v.x; key[2 * u + 1] = v.y;
-            row[2 * u] = (int)r; row[2 * u + 1] = (int)r + 1;
-        } else {
-            row[2 * u] = r < a.n_reads ? (int)r : -1;
-            key[2 * u] = r < a.n_reads ? __ldcs(a.read_key + r) : 0ull;
-            row[2 * u + 1] = -1; key[2 * u + 1] = 0ull;
-        }
-    }
-    if (lo != hi) {                      // a tile straddling a contig boundary: rare, generic path
-#pragma unroll
-        for (int u = 0; u < kProbePerThread; ++u) {
-            if (row[u] < 0) continue;
-            const int s = lo + shard_of(a.read_off + lo, hi - lo + 1, row[u]);
-            probe_one(a, key[u], row[u], __ldg(a.tab_off + s), (unsigned)__ldg(a.tab_mask + s));
-        }
-        return;
-    }
-    const int base = __ldg(a.tab_off + lo);
-    const unsigned mask = (unsigned)__ldg(a.tab_mask + lo);
-    unsigned p[kProbePerThread];
-    unsigned long long k[kProbePerThread];
-#pragma unroll
-    for (int u = 0; u < kProbePerThread; ++u) {
-        p[u] = slot_hash(key[u]) & mask;
-        k[u] = row[u] >= 0 ? a.tab_key[base + p[u]] : kEmptyKey;
-    }
-    unsigned pend = 0;
-#pragma unroll
-    for (int u = 0; u < kProbePerThread; ++u) {
-        if (k[u] == key[u] && row[u] >= 0) probe_hit(a, key[u], base + (int)p[u], row[u]);
-        else if (k[u] != kEmptyKey) pend |= 1u << u;
-    }
-    while (pend) {
-#pragma unroll
-        for (int u = 0; u < kProbePerThread; ++u)
-            if (pend >> u & 1u) { p[u] = (p[u] + 1) & mask; k[u] = a.tab_key[base + p[u]]; }
-#pragma unroll
-        for (int u = 0; u < kProbePerThread; ++u)
-            if (pend >> u & 1u) {
-                if (k[u] == key[u]) { probe_hit(a, key[u], base + (int)p[u], row[u]); pend &= ~(1u << u); }
-                else if (k[u] == kEmptyKey) pend &= ~(1u << u);
+            for (int u = 0; u < kProbeUnroll; ++u) {
+                const long long qq = q + (long long)u * kProbeThreads;
+                v[u] = make_ulonglong2(0ull, 0ull);
+                if (qq < q1) {
+                    if (2 * qq + 1 < R) v[u] = __ldcs(reinterpret_cast<const ulonglong2 *>(a.read_key) + qq);
+                    else v[u].x = __ldcs(a.read_key + 2 * qq);
+                }
             }
+#pragma unroll
+            for (int u = 0; u < kProbeUnroll; ++u) {
+                const long long row = 2 * (q + (long long)u * kProbeThreads);
+                const unsigned mx = bloom_bits(v[u].x), my = bloom_bits(v[u].y);
+                const bool px = row >= r0 && row < r1 && (s_bm[bloom_word(v[u].x, bmw)] & mx) == mx;
+                const bool py = row + 1 >= r0 && row + 1 < r1 && (s_bm[bloom_word(v[u].y, bmw)] & my) == my;
+                if (px) probe_slot(a, v[u].x, (int)row, base, mask);
+                if (py) probe_slot(a, v[u].y, (int)row + 1, base, mask);
+            }
+        }
+        __syncthreads();                                         // the filter is replaced for the next contig
+        r0 = r1;
+        ++s;
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// one-PS list of a shard (called by the block that finished the shard in k_reduce)
+// one-PS list of a shard (called by the block that finished the shard in k_reduce).
+// Thread t owns the contiguous chunk [t*per, (t+1)*per) of the shard's candidates; shards of up to
+// kThreads*kStage SVs keep the chunk in registers so the list is read from L2 exactly once.
 // ------------------------------------------------------------------------------------------
+template <bool kStaged>
 __device__ void oneps_block(const PhaseArgs &a, int s, long long *smem_tile) {
+    __shared__ unsigned char s_first[512];
     const int b = (int)a.sv_off[s], n = (int)a.sv_off[s + 1] - b;
     const int per = (n + kThreads - 1) / kThreads;
     const int c0 = min(n, (int)threadIdx.x * per), c1 = min(n, c0 + per);
-    // fast path: the candidates already are non-decreasing in VCF order (position-sorted VCF)
-    long long mx = kNone;
-    for (int i = c0; i < c1; ++i) {
-        const long long v = __ldcg(a.cand + b + i);
-        if (v != kNoCand) mx = max(mx, v);
+    long long reg[kStaged ? kStage : 1];
+    if (kStaged) {
+#pragma unroll
+        for (int u = 0; u < kStage; ++u) reg[u] = c0 + u < c1 ? __ldcg(a.cand + b + c0 + u) : kNoCand;
     }
+#define CAND(u) (kStaged ? reg[u] : __ldcg(a.cand + b + c0 + (u)))
+#define FOR_CHUNK(u) _Pragma("unroll") for (int u = 0; u < (kStaged ? kStage : c1 - c0); ++u) if (kStaged ? c0 + u < c1 : true)
+    // fast path: the candidates already are non-decreasing in VCF order (position-sorted VCF)
+    long long mx = kNone, lastv = kNone;
+    FOR_CHUNK(u) { const long long v = CAND(u); if (v != kNoCand) { mx = max(mx, v); lastv = v; } }
     const long long run = block_scan_exclusive(mx, kNone, OpMax(), (long long *)nullptr);
     long long cur = run;
     int cnt = 0;
     bool ok = true;
-    for (int i = c0; i < c1; ++i) {
-        const long long v = __ldcg(a.cand + b + i);
-        if (v == kNoCand) continue;
-        if (v < cur) ok = false;
-        else if (v > cur) { ++cnt; cur = v; }
+    FOR_CHUNK(u) {
+        const long long v = CAND(u);
+        if (v != kNoCand) { if (v < cur) ok = false; else if (v > cur) { ++cnt; cur = v; } }
     }
     if (__syncthreads_and(ok)) {
         int total;
         int w = block_scan_exclusive(cnt, 0, OpSum(), &total);
         cur = run;
-        for (int i = c0; i < c1; ++i) {
-            const long long v = __ldcg(a.cand + b + i);
-            if (v != kNoCand && v > cur) { a.oneps[b + w++] = (int)v; cur = v; }
-        }
+        FOR_CHUNK(u) { const long long v = CAND(u); if (v != kNoCand && v > cur) { a.oneps[b + w++] = (int)v; cur = v; } }
         if (threadIdx.x == 0) a.oneps_n[s] = total;
         return;
     }
-    // slow path.  First squeeze runs of equal neighbours (a nearly sorted list of a few hundred
+    // slow path.  Squeeze runs of equal neighbours first (a nearly sorted list of a few hundred
     // phase sets stays a few hundred long), then rank-count small sets or sort big ones.
-    __shared__ unsigned char s_first[512];
-    long long lastv = kNone;
-    for (int i = c0; i < c1; ++i) {
-        const long long v = __ldcg(a.cand + b + i);
-        if (v != kNoCand) lastv = v;
-    }
     const long long prev0 = block_scan_exclusive(lastv, kNone, OpLast(), (long long *)nullptr);
     long long prev = prev0;
     cnt = 0;
-    for (int i = c0; i < c1; ++i) {
-        const long long v = __ldcg(a.cand + b + i);
-        if (v == kNoCand) continue;
-        cnt += v != prev;
-        prev = v;
-    }
+    FOR_CHUNK(u) { const long long v = CAND(u); if (v != kNoCand) { cnt += v != prev; prev = v; } }
     int r;
     int w = block_scan_exclusive(cnt, 0, OpSum(), &r);
     long long *v = (long long)next_pow2(max(r, 1)) * (long long)sizeof(long long) <= kSortSmemBytes
                        ? smem_tile : a.sort_scratch + 2ll * b;
     prev = prev0;
-    for (int i = c0; i < c1; ++i) {
-        const long long x = __ldcg(a.cand + b + i);
-        if (x == kNoCand) continue;
-        if (x != prev) v[w++] = x;
-        prev = x;
-    }
+    FOR_CHUNK(u) { const long long x = CAND(u); if (x != kNoCand) { if (x != prev) v[w++] = x; prev = x; } }
+#undef CAND
+#undef FOR_CHUNK
     __syncthreads();
     if (r <= 512) {
         for (int h = threadIdx.x; h < r; h += kThreads) {
@@ -420,8 +441,10 @@ __device__ void oneps_block(const PhaseArgs &a, int s, long long *smem_tile) {
             for (int t = 0; t < r; ++t) rank += s_first[t] && v[t] < x;
             a.oneps[b + rank] = (int)x;
         }
-        for (int t = 0; t < r; ++t) total += s_first[t];
-        if (threadIdx.x == 0) a.oneps_n[s] = total;
+        if (threadIdx.x == 0) {
+            for (int t = 0; t < r; ++t) total += s_first[t];
+            a.oneps_n[s] = total;
+        }
         __syncthreads();
         return;
     }
@@ -441,11 +464,16 @@ __device__ void oneps_block(const PhaseArgs &a, int s, long long *smem_tile) {
     __syncthreads();
 }
 
+__device__ __forceinline__ void oneps_any(const PhaseArgs &a, int s, long long *smem_tile) {
+    if ((int)(a.sv_off[s + 1] - a.sv_off[s]) <= kThreads * kStage) oneps_block<true>(a, s, smem_tile);
+    else oneps_block<false>(a, s, smem_tile);
+}
+
 // ------------------------------------------------------------------------------------------
 // k_reduce: G lanes per SV.  Resolves each support read to its read row, then reduces.
 // ------------------------------------------------------------------------------------------
 template <int G>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 6)
 k_reduce(PhaseArgs a) {
     __shared__ __align__(16) long long s_tile[kSortSmemBytes / 8];
     __shared__ int s_list[kThreads];
@@ -470,11 +498,7 @@ k_reduce(PhaseArgs a) {
     long long first_q = INT64_MAX;      // CSR index of the first read with pc <= pc_max
     int first_q_ps = 0;
     for (long long j = b + lane; j < e; j += G) {
-        const int slot = a.csr_slot[j];
-        const int row = __ldcg(a.tab_row + slot);
-        if (a.csr_key_hi && __ldcg(a.tab_hi + slot) != __ldg(a.csr_key_hi + j))
-            report(a.status, DUET_ERR_HASH_COLLISION, sv, (long long)__ldg(a.csr_key + j));
-        a.join_row[j] = row;
+        const int row = a.join_row[j];
         if (row >= 0) {
             const int ps = __ldg(a.read_ps + row);
             const int pc = __ldg(a.read_pc + row);
@@ -514,7 +538,7 @@ k_reduce(PhaseArgs a) {
     if (live && lane < DUET_N_FEATURES) a.features[(size_t)lane * a.n_svs + sv] = 0.0;
 
     const int n_done = credit_shards(a, a.done_reduce, sv0, sv1, s_list, &s_n);
-    for (int i = 0; i < n_done; ++i) oneps_block(a, s_list[i], s_tile);
+    for (int i = 0; i < n_done; ++i) oneps_any(a, s_list[i], s_tile);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -888,8 +912,13 @@ k_predict(PhaseArgs a) {
     // ---- C: the table is not read after k_reduce
     for (long long j = (long long)blockIdx.x * kThreads + threadIdx.x; j < a.n_joins; j += (long long)gridDim.x * kThreads) {
         const int slot = a.csr_slot[j];
-        a.tab_key[slot] = kEmptyKey;
-        a.tab_row[slot] = -1;
+        const unsigned long long key = __ldg(a.csr_key + j);
+        if (a.csr_key_hi && a.tab[slot].hi != __ldg(a.csr_key_hi + j))      // two names, one 64-bit key
+            report(a.status, DUET_ERR_HASH_COLLISION, -1, (long long)key);
+        a.tab[slot].key = kEmptyKey;
+        a.tab[slot].head = -1;
+        a.tab[slot].multi = -1;
+        a.bitmap[a.csr_bmword[j]] = 0u;
     }
 
     __threadfence();
