@@ -46,6 +46,16 @@ class Timings(C.Structure):
                 ("kernel_ms", C.c_float * 8)]
 
 
+class ClusterParams(C.Structure):
+    _fields_ = [("max_distance", C.c_double), ("position_normalizer", C.c_double), ("partition_window", C.c_int32),
+                ("_pad", C.c_int32)]
+
+
+class ClusterInput(C.Structure):
+    _fields_ = [("mem", C.c_int32), ("_pad", C.c_int32), ("n", C.c_int64)] + \
+               [(n, C.c_void_p) for n in ("contig", "type", "start", "end")]
+
+
 KERNEL_NAMES = ("build", "probe", "reduce", "predict")
 
 # every symbol include/duet_b200.h declares
@@ -53,7 +63,7 @@ SYMBOLS = (
     "duet_abi_version", "duet_default_thresholds", "duet_create", "duet_destroy", "duet_last_error",
     "duet_set_thresholds", "duet_set_stream", "duet_phase_upload", "duet_phase_execute",
     "duet_phase_download", "duet_phase_run", "duet_host_alloc", "duet_host_free", "duet_sync",
-    "duet_get_timings", "duet_launch_count", "duet_hash_names", "duet_decode_sam_text", "duet_count_lines",
+    "duet_get_timings", "duet_launch_count", "duet_default_cluster_params", "duet_cluster_run", "duet_hash_names", "duet_decode_sam_text", "duet_count_lines",
 )
 DECODE_ERR_INDEX, DECODE_ERR_VALUE, DECODE_ERR_ASCII, DECODE_ERR_RANGE, DECODE_ERR_CAPACITY = 20, 21, 22, 23, 24
 
@@ -99,6 +109,10 @@ def load() -> C.CDLL:
     lib.duet_get_timings.argtypes = [H, C.POINTER(Timings)]
     lib.duet_launch_count.argtypes = [H]
     lib.duet_launch_count.restype = C.c_int64
+    lib.duet_default_cluster_params.argtypes = [C.POINTER(ClusterParams)]
+    lib.duet_default_cluster_params.restype = None
+    lib.duet_cluster_run.argtypes = [H, C.POINTER(ClusterInput), C.POINTER(ClusterParams), C.c_void_p,
+                                     C.POINTER(C.c_int64), C.POINTER(C.c_float)]
     lib.duet_hash_names.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.duet_hash_names.restype = None
     lib.duet_decode_sam_text.argtypes = [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 5 + \

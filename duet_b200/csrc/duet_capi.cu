@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "phase_kernels.cuh"
+#include "cluster_kernels.cuh"
 
 using namespace duet;
 
@@ -67,6 +68,9 @@ struct duet_handle {
     DevBuf d_bitmap, d_bm_off, d_bm_wmask, d_next, d_bmword, d_csr_slot, d_join_row, d_n_hit, d_cand, d_oneps, d_oneps_n, d_sort;
     DevBuf d_gt, d_cls, d_ps, d_hap1, d_hap2, d_hap0, d_allhap, d_t1, d_t2, d_feat, d_order, d_n_emit;
     DevBuf d_counts, d_status;
+    // kernel set B (signature clustering)
+    DevBuf cl_in[4], cl_key[2], cl_idx[2], cl_span, cl_parent, cl_minidx, cl_out, cl_hist, cl_misc;
+    cudaEvent_t cl_ev[2] = {};
 };
 
 namespace {
@@ -148,6 +152,7 @@ int duet_create(int device_id, duet_handle **out) {
     }
     h->stream = h->own_stream;
     for (auto &ev : h->ev) cudaEventCreate(&ev);
+    for (auto &ev : h->cl_ev) cudaEventCreate(&ev);
     {   // fails here, loudly, if the image was not built for this device (sm_100a only)
         cudaFuncAttributes fa;
         cudaFuncGetAttributes(&fa, k_probe);
@@ -174,6 +179,10 @@ void duet_destroy(duet_handle *h) {
                       &h->d_cls, &h->d_ps, &h->d_hap1, &h->d_hap2, &h->d_hap0, &h->d_allhap, &h->d_t1, &h->d_t2,
                       &h->d_feat, &h->d_order, &h->d_n_emit, &h->d_counts, &h->d_status};
     for (DevBuf *b : bufs) b->release();
+    for (DevBuf &b : h->cl_in) b.release();
+    for (DevBuf *b : {&h->cl_key[0], &h->cl_key[1], &h->cl_idx[0], &h->cl_idx[1], &h->cl_span, &h->cl_parent,
+                      &h->cl_minidx, &h->cl_out, &h->cl_hist, &h->cl_misc}) b->release();
+    for (auto &ev : h->cl_ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -494,5 +503,101 @@ int duet_get_timings(duet_handle *h, duet_timings *t) {
 }
 
 int64_t duet_launch_count(const duet_handle *h) { return h ? h->launches : 0; }
+
+// ---- kernel set B: signature clustering -----------------------------------------------------------
+
+void duet_default_cluster_params(duet_cluster_params *p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->max_distance = 0.9;            // --cluster_max_distance default, utils.py:27-28
+    p->position_normalizer = 900.0;
+    p->partition_window = 1000;
+}
+
+int duet_cluster_run(duet_handle *h, const duet_cluster_input *in, const duet_cluster_params *params,
+                     int32_t *cluster_id, int64_t *n_clusters, float *device_ms) {
+    if (!h || !in || !params || !cluster_id) return fail(h, DUET_ERR_INVALID, "duet_cluster_run: NULL argument");
+    const long long n = in->n;
+    if (n < 0 || n >= (1ll << 31)) return fail(h, DUET_ERR_INVALID, "duet_cluster_run: n out of range");
+    if (n_clusters) *n_clusters = 0;
+    if (device_ms) *device_ms = 0.f;
+    if (n == 0) return DUET_OK;
+    if (!in->contig || !in->type || !in->start || !in->end)
+        return fail(h, DUET_ERR_INVALID, "duet_cluster_run: a column is NULL");
+    if (!(params->max_distance >= 0) || !(params->position_normalizer > 0) || params->partition_window < 0)
+        return fail(h, DUET_ERR_INVALID, "duet_cluster_run: bad parameters");
+    CU(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    ClusterArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.n = (int)n;
+    const void *dv;
+    int rc;
+    const int32_t *cols[4] = {in->contig, in->type, in->start, in->end};
+    const int **dst[4] = {&a.contig, &a.type, &a.start, &a.end};
+    for (int c = 0; c < 4; ++c) {
+        if ((rc = stage(h, h->cl_in[c], cols[c], sizeof(int32_t) * (size_t)n, in->mem, &dv))) return rc;
+        *dst[c] = static_cast<const int *>(dv);
+    }
+    const size_t N = (size_t)n;
+    const int n_tiles = (int)((n + kRsTile - 1) / kRsTile);
+    for (int k = 0; k < 2; ++k) {
+        CU(h, h->cl_key[k].reserve(N * 8));
+        CU(h, h->cl_idx[k].reserve(N * 4));
+    }
+    CU(h, h->cl_span.reserve(N * 4));    a.span = h->cl_span.as<int>();
+    CU(h, h->cl_parent.reserve(N * 4));  a.parent = h->cl_parent.as<int>();
+    CU(h, h->cl_minidx.reserve(N * 4));  a.minidx = h->cl_minidx.as<int>();
+    CU(h, h->cl_hist.reserve((size_t)n_tiles * 256 * 4));
+    CU(h, h->cl_misc.reserve(64));
+    a.vary = h->cl_misc.as<unsigned long long>();
+    a.n_clusters = reinterpret_cast<int *>(a.vary + 2);
+    if (in->mem == DUET_MEM_DEVICE) a.out = cluster_id;
+    else { CU(h, h->cl_out.reserve(N * 4)); a.out = h->cl_out.as<int>(); }
+    a.max_distance = params->max_distance;
+    a.normalizer = params->position_normalizer;
+    a.window2 = 2u * (unsigned)params->partition_window;
+
+    const int blocks = (int)((n + kClThreads - 1) / kClThreads);
+    CU(h, cudaEventRecord(h->cl_ev[0], st));
+    CU(h, cudaMemsetAsync(h->cl_misc.p, 0, 64, st));
+    a.key = h->cl_key[0].as<unsigned long long>();
+    a.idx = h->cl_idx[0].as<int>();
+    k_cl_keys<<<blocks, kClThreads, 0, st>>>(a);
+    ++h->launches;
+    unsigned long long vary[2];
+    CU(h, cudaMemcpyAsync(vary, a.vary, 16, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));                   // which key bytes differ decides the sort passes
+    if (vary[1]) return fail(h, DUET_ERR_INVALID, "duet_cluster_run: need 0 <= start <= end, start+end < 2^32, contig < 65536, type < 256");
+    int cur = 0;
+    for (int shift = 0; shift < 64; shift += 8) {
+        if (!((vary[0] >> shift) & 0xFFull)) continue;
+        unsigned *hist = h->cl_hist.as<unsigned>();
+        k_rs_hist<<<n_tiles, kClThreads, 0, st>>>(h->cl_key[cur].as<unsigned long long>(), (int)n, shift, hist, n_tiles);
+        k_rs_scan<<<1, 1024, 0, st>>>(hist, n_tiles * 256);
+        k_rs_scatter<<<n_tiles, kClThreads, 0, st>>>(h->cl_key[cur].as<unsigned long long>(), h->cl_idx[cur].as<int>(),
+                                                      h->cl_key[cur ^ 1].as<unsigned long long>(),
+                                                      h->cl_idx[cur ^ 1].as<int>(), (int)n, shift, hist, n_tiles);
+        h->launches += 3;
+        cur ^= 1;
+    }
+    a.key = h->cl_key[cur].as<unsigned long long>();
+    a.idx = h->cl_idx[cur].as<int>();
+    k_cl_span<<<blocks, kClThreads, 0, st>>>(a);
+    k_cl_edges<<<blocks, kClThreads, 0, st>>>(a);
+    k_cl_label<<<blocks, kClThreads, 0, st>>>(a);
+    k_cl_write<<<blocks, kClThreads, 0, st>>>(a);
+    h->launches += 4;
+    CU(h, cudaEventRecord(h->cl_ev[1], st));
+    int nc = 0;
+    CU(h, cudaMemcpyAsync(&nc, a.n_clusters, 4, cudaMemcpyDeviceToHost, st));
+    if (in->mem != DUET_MEM_DEVICE)
+        CU(h, cudaMemcpyAsync(cluster_id, a.out, N * 4, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    CU(h, cudaGetLastError());
+    if (n_clusters) *n_clusters = nc;
+    if (device_ms) cudaEventElapsedTime(device_ms, h->cl_ev[0], h->cl_ev[1]);
+    return DUET_OK;
+}
 
 }  // extern "C"

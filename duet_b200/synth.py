@@ -345,3 +345,33 @@ def write_workdir(sample: SynthSample, home: str, dialect: str = "cutesv") -> No
         fn = ("chr" if sample.chr_prefix else "") + c.name + ".bam"
         write_sam_text(c, os.path.join(home, "snp_phasing", fn))
     write_vcf(sample, os.path.join(home, "sv_calling", "variants.vcf"), dialect)
+
+
+# ----------------------------------------------------------------------------
+# SV signatures for kernel set B (BASELINE.json configs[2])
+# ----------------------------------------------------------------------------
+
+def make_signatures(seed: int = 0, n: int = 2_000_000, contigs=None, shuffle: bool = True):
+    """True events Poisson along each contig, 1-40 signatures per event, start jitter N(0, 50),
+    span lognormal(median 300) x (1 +- 0.1); types DEL/INS/INV/DUP_TAN 45/45/5/5 %.
+    Returns int32 arrays (contig, type, start, end); insertions use end = start + length."""
+    rng = np.random.default_rng(seed)
+    contigs = list(contigs) if contigs is not None else CHROM_LIST
+    lengths = np.array([GRCH37.get(c, 50_000_000) for c in contigs], np.float64)
+    per = rng.integers(1, 41, size=int(n / 20.5) + 64)
+    per = per[np.cumsum(per) <= n]
+    n_ev = per.shape[0]
+    ev_contig = rng.choice(len(contigs), size=n_ev, p=lengths / lengths.sum())
+    ev_pos = (rng.random(n_ev) * (lengths[ev_contig] - 20_000) + 10_000).astype(np.int64)
+    ev_type = rng.choice(4, size=n_ev, p=[0.45, 0.45, 0.05, 0.05])
+    ev_span = np.maximum(30, rng.lognormal(np.log(300.0), 0.8, size=n_ev)).astype(np.int64)
+    ev = np.repeat(np.arange(n_ev), per)
+    m = ev.shape[0]
+    start = ev_pos[ev] + np.rint(rng.normal(0.0, 50.0, size=m)).astype(np.int64)
+    span = np.maximum(1, np.rint(ev_span[ev] * (1.0 + rng.uniform(-0.1, 0.1, size=m)))).astype(np.int64)
+    contig, typ = ev_contig[ev], ev_type[ev]
+    if shuffle:
+        p = rng.permutation(m)
+        contig, typ, start, span = contig[p], typ[p], start[p], span[p]
+    start = np.maximum(start, 0)
+    return (contig.astype(np.int32), typ.astype(np.int32), start.astype(np.int32), (start + span).astype(np.int32))

@@ -174,6 +174,34 @@ int duet_host_free(void *ptr);
 
 int duet_sync(duet_handle *h);
 
+/* ---- kernel set B: span-position-distance clustering of SV signatures --------------------------
+ * Stands where the reference shells out to `svim alignment ... --cluster_max_distance c`
+ * (src/duet/sv_calling.py:14-15; default 0.9, src/duet/utils.py:27-28).  The clustering arithmetic
+ * is NOT in the reference (svim 1.4.2 is an external tool): the spec implemented is written down in
+ * csrc/cluster_kernels.cuh and DESIGN.md; parity with svim itself is unpinned. */
+typedef struct duet_cluster_params {
+    double max_distance;          /* 0.9                                                       */
+    double position_normalizer;   /* 900                                                       */
+    int32_t partition_window;     /* 1000: centres further apart are never compared            */
+    int32_t _pad;
+} duet_cluster_params;
+
+typedef struct duet_cluster_input {
+    int32_t mem;                  /* DUET_MEM_HOST | DUET_MEM_DEVICE (cluster_id lives there too) */
+    int32_t _pad;
+    int64_t n;                    /* signatures, < 2^31                                         */
+    const int32_t *contig;        /* [n] contig id, < 65536                                     */
+    const int32_t *type;          /* [n] signature type id, < 256 (DEL / INS / INV / DUP_TAN ...) */
+    const int32_t *start;         /* [n] 0 <= start                                             */
+    const int32_t *end;           /* [n] start <= end (insertions: start + length); start+end < 2^32 */
+} duet_cluster_input;
+
+void duet_default_cluster_params(duet_cluster_params *p);
+/* cluster_id[i] = smallest signature index in i's cluster; *n_clusters = number of clusters;
+ * *device_ms (optional) = device time of the call. */
+int duet_cluster_run(duet_handle *h, const duet_cluster_input *in, const duet_cluster_params *params,
+                     int32_t *cluster_id, int64_t *n_clusters, float *device_ms);
+
 /* ---- host-side decoders (no GPU needed) -------------------------------------------------- */
 
 enum {

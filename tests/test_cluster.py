@@ -1,0 +1,82 @@
+"""Kernel set B.  CPU: the scipy oracle against an independent O(n^2) restatement of the same
+spec.  GPU: the CUDA path (through the C-ABI) against the oracle, bit-exact cluster membership.
+SVIM parity is unpinned (see oracle/cluster_oracle.py)."""
+import numpy as np
+import pytest
+
+from duet_b200 import synth
+from oracle import cluster_oracle
+
+
+def small_cases():
+    yield "events", synth.make_signatures(1, n=900, contigs=["1", "2", "X"])
+    yield "one_contig", synth.make_signatures(2, n=400, contigs=["21"])
+    rng = np.random.default_rng(3)
+    n = 600                                     # dense: everything inside a few windows, chains of links
+    st = rng.integers(1000, 4000, size=n)
+    yield "dense", (rng.integers(0, 2, size=n), rng.integers(0, 3, size=n), st, st + rng.integers(0, 700, size=n))
+    # exact-threshold pairs: |dc|/900 + |ds|/max = 0.9 exactly representable cases and zero spans
+    yield "edges", (np.zeros(8, int), np.zeros(8, int),
+                    np.array([100, 100, 505, 505, 5000, 5000, 9000, 9900]),
+                    np.array([200, 200, 605, 605, 5000, 5000, 9100, 10000]))
+
+
+@pytest.mark.parametrize("name,cols", list(small_cases()), ids=lambda x: x if isinstance(x, str) else "")
+def test_oracle_matches_bruteforce(name, cols):
+    for md in (0.9, 0.3):
+        a, na = cluster_oracle.cluster(*cols, max_distance=md)
+        b, nb = cluster_oracle.cluster_bruteforce(*[np.asarray(c).tolist() for c in cols], max_distance=md)
+        assert na == nb and np.array_equal(a, b)
+    assert cluster_oracle.cluster([], [], [], [])[1] == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,cols", list(small_cases()), ids=lambda x: x if isinstance(x, str) else "")
+def test_gpu_small(name, cols):
+    from duet_b200.sv_clustering import cluster_signatures
+    for md, win in ((0.9, 1000), (0.3, 1000), (0.9, 50)):
+        want, n_want = cluster_oracle.cluster(*cols, max_distance=md, window=win)
+        got, n_got, _ = cluster_signatures(*cols, cluster_max_distance=md, partition_window=win)
+        assert n_got == n_want
+        assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_gpu_200k_and_properties():
+    from duet_b200.sv_clustering import cluster_signatures
+    cols = synth.make_signatures(5, n=200_000)
+    want, n_want = cluster_oracle.cluster(*cols)
+    got, n_got, ms = cluster_signatures(*cols)
+    assert n_got == n_want and np.array_equal(got, want)
+    # size-independent properties: ids are fixed points, members share (contig, type), permutation
+    # of the input permutes the partition
+    assert np.array_equal(got[got], got)
+    assert np.array_equal(cols[0][got], cols[0]) and np.array_equal(cols[1][got], cols[1])
+    p = np.random.default_rng(0).permutation(len(got))
+    got_p, n_p, _ = cluster_signatures(*[c[p] for c in cols])
+    assert n_p == n_got
+    inv = np.empty_like(p); inv[p] = np.arange(len(p))
+    # same partition: two signatures share a cluster before iff they share one after
+    a = got; b = got_p[inv]
+    _, ia = np.unique(a, return_inverse=True); _, ib = np.unique(b, return_inverse=True)
+    assert len(set(zip(ia.tolist(), ib.tolist()))) == n_got
+
+
+@pytest.mark.gpu
+def test_gpu_c3_full_size_properties():
+    """BASELINE.json configs[2]: 2 M signatures, cluster_max_distance 0.9."""
+    from duet_b200.sv_clustering import cluster_signatures
+    cols = synth.make_signatures(0, n=2_000_000)
+    got, n_got, ms = cluster_signatures(*cols)
+    want, n_want = cluster_oracle.cluster(*cols)
+    assert n_got == n_want and np.array_equal(got, want)
+    assert np.array_equal(got[got], got)
+
+
+@pytest.mark.gpu
+def test_gpu_rejects_bad_input():
+    from duet_b200.engine import DuetError
+    from duet_b200.sv_clustering import cluster_signatures
+    with pytest.raises(DuetError):
+        cluster_signatures([0], [0], [10], [5])          # end < start
+    assert cluster_signatures([], [], [], [])[1] == 0
