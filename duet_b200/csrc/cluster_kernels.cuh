@@ -170,11 +170,17 @@ k_cl_span(ClusterArgs a) {
 }
 
 // ---- union-find ----------------------------------------------------------------------------------
+// Path halving: every write re-points x to its CURRENT grandparent, an ancestor read just now.
+// Parents only ever move to smaller indices (roots hang under smaller roots), so concurrent
+// finds / unions can never create a cycle.
 __device__ __forceinline__ int uf_find(volatile int *p, int x) {
-    int r = x;
-    for (int pr = p[r]; pr != r; pr = p[r]) r = pr;
-    for (int px = p[x]; px != r && px != x; px = p[x]) { p[x] = r; x = px; }       // compress
-    return r;
+    for (;;) {
+        const int px = p[x];
+        if (px == x) return x;
+        const int ppx = p[px];
+        if (ppx != px) p[x] = ppx;
+        x = px;
+    }
 }
 
 __device__ __forceinline__ void uf_unite(int *parent, int x, int y) {
