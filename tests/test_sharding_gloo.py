@@ -37,14 +37,18 @@ def _oracle_phase_fn(batch, svlen_thres, suppread_thres):
                        o.join_row, o.order, o.shard_counts)
 
 
-def _worker(rank, world, port, home, svlen, supp, out_q):
+def _worker(rank, world, port, home, svlen, supp, out_q, on_gpu=False):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if on_gpu:
+        import torch
+        os.environ["DUET_DEVICE"] = str(rank % torch.cuda.device_count())
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        counts = sharding.sv_phasing_sharded(home, svlen, supp, 1, False, phase_fn=_oracle_phase_fn)
+        counts = sharding.sv_phasing_sharded(home, svlen, supp, 1, False,
+                                             phase_fn=None if on_gpu else _oracle_phase_fn)
         out_q.put((rank, counts))
     finally:
         dist.destroy_process_group()
@@ -56,14 +60,13 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("name", ["cutesv_3ctg", "mixed_prefix", "svim_shuffled"])
-def test_two_rank_stage_is_byte_identical(name, tmp_path):
+def _run_two_ranks(name, tmp_path, on_gpu):
     case = load_golden(f"e2e_{name}.json.gz")
     home = materialise(case, str(tmp_path))
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, home, case["svlen_thres"], case["suppread_thres"], q))
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, home, case["svlen_thres"], case["suppread_thres"], q, on_gpu))
              for r in range(2)]
     for p in procs:
         p.start()
@@ -76,6 +79,19 @@ def test_two_rank_stage_is_byte_identical(name, tmp_path):
     assert np.array_equal(got[0], got[1])                      # every rank holds the whole counter table
     assert got[0][:, 2].sum() == len(case["rows"])
     assert not [fn for fn in os.listdir(home) if ".slice." in fn]
+
+
+@pytest.mark.parametrize("name", ["cutesv_3ctg", "mixed_prefix", "svim_shuffled"])
+def test_two_rank_stage_is_byte_identical(name, tmp_path):
+    _run_two_ranks(name, tmp_path, on_gpu=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cutesv_3ctg", "dense"])
+def test_two_rank_stage_on_gpu(name, tmp_path):
+    """Same, with the real device path in both ranks (two processes share the GPU when only one is
+    visible; with >= 2 GPUs each rank takes its own)."""
+    _run_two_ranks(name, tmp_path, on_gpu=True)
 
 
 def test_single_process_path_matches_too(tmp_path):
