@@ -64,6 +64,8 @@ struct duet_handle {
     DevBuf in_csr_off, in_csr_key, in_csr_key_hi;
     // descriptors, table, scratch, outputs
     DevBuf d_read_off, d_sv_off, d_join_off, d_sv_shard, d_tab_off, d_tab_mask, d_done, d_c2;
+    DevBuf d_btiles, d_rtiles, d_ptiles;
+    size_t probe_smem = 0;
     DevBuf d_table;                 // Slot[n_slots], all-ones when idle
     DevBuf d_bitmap, d_bm_off, d_bm_wmask, d_next, d_bmword, d_csr_slot, d_join_row, d_n_hit, d_cand, d_oneps, d_oneps_n, d_sort;
     DevBuf d_gt, d_cls, d_ps, d_hap1, d_hap2, d_hap0, d_allhap, d_t1, d_t2, d_feat, d_order, d_n_emit;
@@ -156,7 +158,7 @@ int duet_create(int device_id, duet_handle **out) {
     {   // fails here, loudly, if the image was not built for this device (sm_100a only)
         cudaFuncAttributes fa;
         cudaFuncGetAttributes(&fa, k_probe);
-        cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, kBloomMaxWords * 4);
+        cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, kBloomMaxWords * 4 + 4096 * 12);
         cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device_id);
     }
     if (cudaGetLastError() != cudaSuccess) {
@@ -174,7 +176,7 @@ void duet_destroy(duet_handle *h) {
     DevBuf *bufs[] = {&h->in_read_key, &h->in_read_key_hi, &h->in_read_hp, &h->in_read_ps, &h->in_read_pc,
                       &h->in_sv_pos, &h->in_sv_svlen, &h->in_sv_svread, &h->in_sv_refread, &h->in_sv_flags,
                       &h->in_sv_group, &h->in_csr_off, &h->in_csr_key, &h->in_csr_key_hi, &h->d_read_off,
-                      &h->d_sv_off, &h->d_join_off, &h->d_c2, &h->d_sv_shard, &h->d_done, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_bitmap, &h->d_bm_off, &h->d_bm_wmask, &h->d_next, &h->d_bmword, &h->d_csr_slot,
+                      &h->d_sv_off, &h->d_join_off, &h->d_c2, &h->d_btiles, &h->d_rtiles, &h->d_ptiles, &h->d_sv_shard, &h->d_done, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_bitmap, &h->d_bm_off, &h->d_bm_wmask, &h->d_next, &h->d_bmword, &h->d_csr_slot,
                       &h->d_join_row, &h->d_n_hit, &h->d_cand, &h->d_oneps, &h->d_oneps_n, &h->d_sort, &h->d_gt,
                       &h->d_cls, &h->d_ps, &h->d_hap1, &h->d_hap2, &h->d_hap0, &h->d_allhap, &h->d_t1, &h->d_t2,
                       &h->d_feat, &h->d_order, &h->d_n_emit, &h->d_counts, &h->d_status};
@@ -316,7 +318,33 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         std::fill(sv_shard.begin() + in->sv_off[s], sv_shard.begin() + in->sv_off[s + 1], s);
     if ((rc = stage(h, h->d_sv_shard, sv_shard.data(), sizeof(int) * (size_t)S, DUET_MEM_HOST, &dv))) return rc;
     a.sv_shard = static_cast<const int *>(dv);
-    CU(h, cudaStreamSynchronize(st));          // sv_shard / tab_off are stack vectors: copies must finish
+    // per-block tile descriptors (what each block would otherwise look up with dependent loads)
+    auto shard_at = [&](const std::vector<long long> &off, long long x) {
+        return (int)(std::upper_bound(off.begin(), off.end(), x) - off.begin()) - 1;
+    };
+    std::vector<BuildTile> btiles((size_t)((J + kThreads - 1) / kThreads));
+    for (size_t t = 0; t < btiles.size(); ++t) {
+        const long long first = (long long)t * kThreads, last = std::min<long long>(J, first + kThreads) - 1;
+        const int lo = shard_at(join_off, first), hi = shard_at(join_off, last);
+        btiles[t] = BuildTile{lo, hi, tab_off[lo], tab_mask[lo], bm_off[lo], bm_wmask[lo], {0, 0}};
+    }
+    auto sv_tiles = [&](int per_block) {
+        std::vector<SvTile> v((size_t)((S + per_block - 1) / per_block));
+        for (size_t t = 0; t < v.size(); ++t) {
+            const long long sv0 = (long long)t * per_block, sv1 = std::min<long long>(S, sv0 + per_block);
+            const int sf = sv_shard[sv0], sl = sv_shard[sv1 - 1];
+            v[t] = SvTile{sf, sl, (int)in->sv_off[sf], (int)in->sv_off[sf + 1]};
+        }
+        return v;
+    };
+    std::vector<SvTile> rtiles = sv_tiles(kReducePerBlock), ptiles = sv_tiles(kPredictPerBlock);
+    if ((rc = stage(h, h->d_btiles, btiles.data(), sizeof(BuildTile) * btiles.size(), DUET_MEM_HOST, &dv))) return rc;
+    a.build_tiles = static_cast<const BuildTile *>(dv);
+    if ((rc = stage(h, h->d_rtiles, rtiles.data(), sizeof(SvTile) * rtiles.size(), DUET_MEM_HOST, &dv))) return rc;
+    a.reduce_tiles = static_cast<const SvTile *>(dv);
+    if ((rc = stage(h, h->d_ptiles, ptiles.data(), sizeof(SvTile) * ptiles.size(), DUET_MEM_HOST, &dv))) return rc;
+    a.predict_tiles = static_cast<const SvTile *>(dv);
+    CU(h, cudaStreamSynchronize(st));          // the descriptor vectors live on this stack frame
     if ((rc = stage(h, h->d_tab_off, tab_off.data(), sizeof(int) * ns, DUET_MEM_HOST, &dv))) return rc;
     a.tab_off = static_cast<const int *>(dv);
     if ((rc = stage(h, h->d_tab_mask, tab_mask.data(), sizeof(int) * ns, DUET_MEM_HOST, &dv))) return rc;
@@ -342,9 +370,13 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     CU(h, h->d_done.reserve((size_t)ns * 8));            a.done_reduce = h->d_done.as<int>();
     a.done_predict = a.done_reduce + ns;
     CU(h, h->d_sort.reserve(S1 * 32));                   a.sort_scratch = h->d_sort.as<long long>();
-    CU(h, h->d_c2.reserve(S1 * 4 + 16));                 a.c2_count = h->d_c2.as<int>();
-    a.c2_list = a.c2_count + 4;
-    h->group = (S > 0 && J / std::max<long long>(S, 1) > 24) ? 32 : 16;
+    CU(h, h->d_c2.reserve(S1 * sizeof(C2Rec)));          a.c2rec = h->d_c2.as<C2Rec>();
+    {
+        long long max_words = 32;
+        for (int s = 0; s < ns; ++s) max_words = std::max<long long>(max_words, (long long)bm_wmask[s] + 1);
+        a.probe_qcap = 4096;
+        h->probe_smem = (size_t)a.probe_qcap * 12 + (size_t)max_words * 4;
+    }
     CU(h, h->d_gt.reserve(S1));                          a.gt = h->d_gt.as<uint8_t>();
     CU(h, h->d_cls.reserve(S1));                         a.cls = h->d_cls.as<uint8_t>();
     CU(h, h->d_ps.reserve(S1 * 4));                      a.ps = h->d_ps.as<int>();
@@ -364,7 +396,6 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     CU(h, cudaMemsetAsync(h->d_bitmap.p, 0, (size_t)bm_words * 4, st));
     CU(h, cudaMemsetAsync(h->d_join_row.p, 0xFF, J1 * 4, st));
     CU(h, cudaMemsetAsync(h->d_done.p, 0, (size_t)ns * 8, st));
-    CU(h, cudaMemsetAsync(h->d_c2.p, 0, 16, st));
     CU(h, cudaMemsetAsync(h->d_oneps_n.p, 0, (size_t)ns * 4, st));
     CU(h, cudaMemsetAsync(h->d_n_emit.p, 0, (size_t)ns * 4, st));
     CU(h, cudaMemsetAsync(h->d_counts.p, 0, (size_t)ns * 8 * DUET_N_COUNTERS, st));
@@ -387,20 +418,19 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
     h->per_kernel = per_kernel != 0;
     auto mark = [&](int ev) { if (h->per_kernel) cudaEventRecord(h->ev[ev], st); };
     CU(h, cudaEventRecord(h->ev[EV_X0], st));
-    const int S = a.n_svs, G = h->group;
+    const int S = a.n_svs;
     if (a.n_joins) {
         k_build<<<(a.n_joins + kThreads - 1) / kThreads, kThreads, 0, st>>>(a);
         ++h->launches;
     }
     mark(EV_K1);
     if (a.n_reads && a.n_joins) {
-        k_probe<<<h->n_sm, kProbeThreads, kBloomMaxWords * 4, st>>>(a);
+        k_probe<<<h->n_sm, kProbeThreads, h->probe_smem, st>>>(a);
         ++h->launches;
     }
     mark(EV_K2);
     if (S) {
-        const int blocks = (S + kThreads / G - 1) / (kThreads / G);
-        if (G == 16) k_reduce<16><<<blocks, kThreads, 0, st>>>(a); else k_reduce<32><<<blocks, kThreads, 0, st>>>(a);
+        k_reduce<<<(S + kReducePerBlock - 1) / kReducePerBlock, kThreads, 0, st>>>(a);
         ++h->launches;
     }
     mark(EV_K3);

@@ -30,19 +30,28 @@ constexpr long long kNoCand = 0x7FFFFFFFFFFFFFFFll;   // "no one-PS candidate" (
 constexpr long long kNone = (long long)0x8000000000000000ull;
 constexpr int kThreads = 256;                         // every kernel
 constexpr int kMaxDistinct = 32;                      // distinct in-set PS per SV handled in smem
-constexpr int kSvPerWarpPredict = 8;
+constexpr int kReduceLanes = 8;                       // lanes per SV in k_reduce
+constexpr int kReducePerBlock = kThreads / kReduceLanes;
+constexpr int kPredictPerBlock = 64;
 constexpr int kSortSmemBytes = 16384;                 // slow-path sort tile in shared memory
-constexpr int kStage = 16;                            // per-thread register staging in the shard epilogues
 constexpr int kBloomMaxWords = 32768;                 // 128 KB of shared memory per shard filter
 
 // One slot of the join table = one 32-byte sector: everything a probe needs arrives together.
 struct __align__(32) Slot {
     unsigned long long key;   // low 64 bits of the name hash, kEmptyKey when free
     unsigned long long hi;    // high 64 bits (collision check)
-    int head;                 // most recently inserted support-read entry with this name, -1 none
-    int multi;                // the name occurs in more than one entry (chain through `next`)
+    int first;                // the support-read entry that claimed the slot
+    int head;                 // further entries carrying the same name (chain through `next`), -1 none
     int pad[2];
 };
+
+// host-built descriptors: what a block needs to know about its tile, in one 32- / 16-byte load
+struct BuildTile { int lo, hi, base, mask, bmo, bmw, pad[2]; };   // shards of 256 consecutive support reads
+struct SvTile { int s_first, s_last, off0, off1; };               // shards of a block's SVs; SV range of s_first
+
+constexpr int kC2Max = 8;    // distinct PS per class-2 SV recorded by k_reduce (more -> warp fallback)
+struct C2Ent { int ps, tot, n1, n2; long long s1, s2; int bad, pad; };
+struct C2Rec { int n_d, overflow, pad[2]; C2Ent d[kC2Max]; };
 
 struct DevStatus {          // device -> host error report
     int code;               // first DUET_ERR_* seen (atomicCAS from 0)
@@ -59,6 +68,9 @@ struct PhaseArgs {
     const long long *sv_off;     // [n_shards+1]
     const long long *join_off;   // [n_shards+1] csr_off at the shard boundaries (derived at upload)
     const int *sv_shard;         // [S] shard of each SV (derived at upload)
+    const BuildTile *build_tiles;   // [ceil(J / 256)]
+    const SvTile *reduce_tiles;     // [ceil(S / kReducePerBlock)]
+    const SvTile *predict_tiles;    // [ceil(S / kPredictPerBlock)]
     const unsigned long long *read_key, *read_key_hi;
     const uint8_t *read_hp;
     const int *read_ps, *read_pc;
@@ -86,8 +98,8 @@ struct PhaseArgs {
     int *oneps_n;                // [n_shards]
     int *done_reduce;            // [n_shards] SVs of the shard finished by k_reduce (self-resetting)
     int *done_predict;           // [n_shards] same for k_predict
-    int *c2_list;                // [S] kept class-2 SVs, any order (k_reduce appends, k_predict consumes)
-    int *c2_count;               // [1] reset by k_build
+    C2Rec *c2rec;                // [S] per-PS statistics of class-2 SVs (k_reduce -> k_predict)
+    int probe_qcap;              // candidate queue entries in k_probe's shared memory
     long long *sort_scratch;     // [4*S] global tile for slow-path sorts of big shards
     uint8_t *gt, *cls;
     int *ps, *hap1, *hap2, *hap0, *allhap;
@@ -200,34 +212,6 @@ __device__ __forceinline__ int next_pow2(int n) {
     return p;
 }
 
-// After a block has finished the SVs [sv0, sv1): credit every shard they belong to; shards whose
-// last SV this block completed are returned in s_list (smem) -- the caller then finishes them.
-// Counters reset themselves, so the next call starts from zero.
-__device__ int credit_shards(const PhaseArgs &a, int *done, int sv0, int sv1, int *s_list, int *s_n) {
-    __threadfence();                 // this block's per-SV results are visible device-wide ...
-    __syncthreads();                 // ... before thread 0 publishes the credit
-    if (threadIdx.x == 0) {
-        int n = 0;
-        if (sv0 < sv1) {
-            const int s_first = a.sv_shard[sv0], s_last = a.sv_shard[sv1 - 1];
-            for (int s = s_first; s <= s_last; ++s) {
-                const int lo = max((int)a.sv_off[s], sv0), hi = min((int)a.sv_off[s + 1], sv1);
-                const int total = (int)(a.sv_off[s + 1] - a.sv_off[s]);
-                if (hi <= lo) continue;
-                const int old = atomicAdd(done + s, hi - lo);
-                if (old + (hi - lo) == total) {
-                    done[s] = 0;
-                    if (n < kThreads) s_list[n++] = s;
-                }
-            }
-        }
-        *s_n = n;
-        __threadfence();
-    }
-    __syncthreads();
-    return *s_n;
-}
-
 // ------------------------------------------------------------------------------------------
 // tile -> shard range: count the offsets <= first / last element of the tile, all threads at once
 // ------------------------------------------------------------------------------------------
@@ -254,86 +238,101 @@ __device__ __forceinline__ unsigned bloom_bits(unsigned long long key) {
 }
 
 // ------------------------------------------------------------------------------------------
-// k_build: one thread per support-read name: insert it into its shard's slot range, chain the
-// entry to the slot, set its filter bits, reset its join result.
+// k_build: one thread per support-read name: claim a slot (CAS), set the filter bits, reset the
+// join result.  The first entry of a name owns the slot (plain stores, nothing waited for);
+// further entries with the same name chain themselves behind it.
+// Dependent chain of a thread: [key, tile descriptor] -> CAS (-> CAS on a collision) -> stores.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 k_build(PhaseArgs a) {
-    const long long tile = (long long)blockIdx.x * kThreads;
-    const long long j = tile + threadIdx.x;
-    const unsigned long long key = j < a.n_joins ? __ldcs(a.csr_key + j) : 0ull;     // in flight during the lookup
-    if (j == 0) *a.c2_count = 0;
-    int lo, hi;
-    tile_shards(a.join_off, a.n_shards, tile, min((long long)a.n_joins, tile + kThreads) - 1, lo, hi);
-    if (j >= a.n_joins) return;
-    const int s = lo == hi ? lo : lo + shard_of(a.join_off + lo, hi - lo + 1, j);
-    const int base = __ldg(a.tab_off + s);
-    const unsigned mask = (unsigned)__ldg(a.tab_mask + s);
-    const int bmo = __ldg(a.bm_off + s);
-    const unsigned bmw = (unsigned)__ldg(a.bm_wmask + s);
+    const long long j = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const bool live = j < a.n_joins;
+    const unsigned long long key = live ? __ldcs(a.csr_key + j) : 0ull;
+    const unsigned long long khi = live && a.csr_key_hi ? __ldcs(a.csr_key_hi + j) : 0ull;
+    const BuildTile t = a.build_tiles[blockIdx.x];
+    if (!live) return;
+    int base = t.base, bmo = t.bmo;
+    unsigned mask = (unsigned)t.mask, bmw = (unsigned)t.bmw;
+    if (t.lo != t.hi) {                                          // the tile straddles a contig boundary
+        const int s = t.lo + shard_of(a.join_off + t.lo, t.hi - t.lo + 1, j);
+        base = __ldg(a.tab_off + s); mask = (unsigned)__ldg(a.tab_mask + s);
+        bmo = __ldg(a.bm_off + s); bmw = (unsigned)__ldg(a.bm_wmask + s);
+    }
     a.join_row[j] = -1;
     const int word = bmo + (int)bloom_word(key, bmw);
     atomicOr(a.bitmap + word, bloom_bits(key));
     a.csr_bmword[j] = word;
     unsigned p = slot_hash(key) & mask;
+    bool won;
     for (;;) {
         const unsigned long long prev = atomicCAS(&a.tab[base + p].key, kEmptyKey, key);
-        if (prev == kEmptyKey) {
-            if (a.csr_key_hi) a.tab[base + p].hi = __ldg(a.csr_key_hi + j);
-            break;
-        }
-        if (prev == key) break;
+        won = prev == kEmptyKey;
+        if (won || prev == key) break;
         p = (p + 1) & mask;
     }
-    const int slot = base + (int)p;
-    const int before = atomicExch(&a.tab[slot].head, (int)j);
-    a.next[j] = before;
-    if (before >= 0) a.tab[slot].multi = 1;
-    a.csr_slot[j] = slot;
+    Slot *sl = a.tab + base + p;
+    a.csr_slot[j] = base + (int)p;
+    if (won) {
+        sl->hi = khi;
+        sl->first = (int)j;
+    } else {
+        a.next[j] = atomicExch(&sl->head, (int)j);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
-// k_probe: the haplotagged reads are STREAMED once (16-byte loads, kProbeUnroll pairs in flight
-// per thread) by a persistent grid -- one block per SM, each owning a contiguous row range.  The
-// block keeps the current contig's Bloom filter in shared memory, so ~90 % of the rows (reads that
-// support no SV) are rejected without leaving the SM; the rest probe the slot table in L2 and
-// push their row index to every support-read entry of that name with atomicMax (a later row
-// overrides an earlier one, sv_phasing_fn.py:29).
+// k_probe: the haplotagged reads are STREAMED once (16-byte loads, 8 rows in flight per thread,
+// the next batch already requested while the current one is processed) by a persistent grid --
+// one block per SM, each owning a contiguous row range.  The block keeps the current contig's
+// Bloom filter in shared memory, so ~90 % of the rows (reads that support no SV) never leave the
+// SM.  Rows that pass are queued in shared memory and resolved one per thread: a single 32-byte
+// slot load (plus the row's hi word) decides, and a hit pushes the row index to every
+// support-read entry of that name with atomicMax -- a later row overrides an earlier one
+// (sv_phasing_fn.py:29).
 // ------------------------------------------------------------------------------------------
 constexpr int kProbeThreads = 1024;
-constexpr int kProbeUnroll = 4;
+constexpr int kProbeUnroll = 4;                                  // 16-byte pairs per thread per batch
+constexpr int kProbeBatch = kProbeThreads * kProbeUnroll;        // pairs per block per batch
 
-__device__ __forceinline__ void probe_slot(const PhaseArgs &a, unsigned long long key, int row, int base,
-                                           unsigned mask) {
+__device__ __forceinline__ void probe_candidate(const PhaseArgs &a, unsigned long long key, int row, int base,
+                                                unsigned mask) {
     unsigned p = slot_hash(key) & mask;
+    const unsigned long long rhi = a.read_key_hi ? __ldg(a.read_key_hi + row) : 0ull;     // in flight with the slot
     for (;;) {
         const Slot *sl = a.tab + base + p;
-        const unsigned long long k = sl->key;
-        if (k == key) {
-            int j = sl->head;
-            const int multi = sl->multi;
-            if (a.read_key_hi && sl->hi != __ldg(a.read_key_hi + row))
-                report(a.status, DUET_ERR_HASH_COLLISION, -1, (long long)key);
-            atomicMax(a.join_row + j, row);
-            if (multi == 1)
-                for (j = a.next[j]; j >= 0; j = a.next[j]) atomicMax(a.join_row + j, row);
+        const ulonglong2 kh = *reinterpret_cast<const ulonglong2 *>(sl);                 // key, hi
+        const int2 fh = *reinterpret_cast<const int2 *>(&sl->first);                     // first, head: same sector
+        if (kh.x == key) {
+            if (a.read_key_hi && kh.y != rhi) report(a.status, DUET_ERR_HASH_COLLISION, -1, (long long)key);
+            atomicMax(a.join_row + fh.x, row);
+            for (int h = fh.y; h >= 0; h = a.next[h]) atomicMax(a.join_row + h, row);
             return;
         }
-        if (k == kEmptyKey) return;
+        if (kh.x == kEmptyKey) return;
         p = (p + 1) & mask;
     }
 }
 
 __global__ void __launch_bounds__(kProbeThreads, 1)
 k_probe(PhaseArgs a) {
-    extern __shared__ unsigned s_bm[];
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ int s_qn;
+    // layout: [queue keys | queue rows | filter words]
+    unsigned long long *s_qkey = reinterpret_cast<unsigned long long *>(s_raw);
+    int *s_qrow = reinterpret_cast<int *>(s_qkey + a.probe_qcap);
+    unsigned *s_bm = reinterpret_cast<unsigned *>(s_qrow + a.probe_qcap);
+    const int qcap = a.probe_qcap;
+    const int lane = threadIdx.x & 31;
+
     const long long R = a.n_reads;
     long long per = (R + gridDim.x - 1) / gridDim.x;
     per += per & 1;                                              // ranges start on a 16-byte boundary
     long long r0 = min(R, (long long)blockIdx.x * per);
     const long long r_end = min(R, r0 + per);
     if (r0 >= r_end) return;
+    if (threadIdx.x == 0) s_qn = 0;
     int s = shard_of(a.read_off, a.n_shards, r0);
+    const ulonglong2 *pairs = reinterpret_cast<const ulonglong2 *>(a.read_key);
     while (r0 < r_end) {
         while (__ldg(a.read_off + s + 1) <= r0) ++s;             // skip contigs without reads
         const long long r1 = min(r_end, (long long)__ldg(a.read_off + s + 1));
@@ -341,33 +340,68 @@ k_probe(PhaseArgs a) {
         const unsigned mask = (unsigned)__ldg(a.tab_mask + s);
         const unsigned bmw = (unsigned)__ldg(a.bm_wmask + s);
         const uint4 *src = reinterpret_cast<const uint4 *>(a.bitmap + __ldg(a.bm_off + s));
+        const long long q1 = (r1 + 1) >> 1;                      // pairs of rows (2q, 2q+1)
+        long long q = (r0 >> 1) + threadIdx.x;
+        ulonglong2 nxt[kProbeUnroll];
+        auto fetch = [&](long long qb) {
+#pragma unroll
+            for (int u = 0; u < kProbeUnroll; ++u) {
+                const long long qq = qb + (long long)u * kProbeThreads;
+                nxt[u] = make_ulonglong2(0ull, 0ull);
+                if (qq < q1) {
+                    if (2 * qq + 1 < R) nxt[u] = __ldcs(pairs + qq);
+                    else nxt[u].x = __ldcs(a.read_key + 2 * qq);
+                }
+            }
+        };
+        fetch(q);                                                // first batch in flight during the filter load
         for (int i = threadIdx.x; i < (int)(bmw + 1) / 4; i += kProbeThreads)
             reinterpret_cast<uint4 *>(s_bm)[i] = src[i];
         __syncthreads();
-        // pairs of rows (2q, 2q+1); a pair cut by the range edge is shared with the neighbour
-        const long long q1 = (r1 + 1) >> 1;
-        for (long long q = (r0 >> 1) + threadIdx.x; q < q1; q += (long long)kProbeThreads * kProbeUnroll) {
+        for (long long qb = r0 >> 1; qb < q1; qb += kProbeBatch, q += kProbeBatch) {
             ulonglong2 v[kProbeUnroll];
 #pragma unroll
-            for (int u = 0; u < kProbeUnroll; ++u) {
-                const long long qq = q + (long long)u * kProbeThreads;
-                v[u] = make_ulonglong2(0ull, 0ull);
-                if (qq < q1) {
-                    if (2 * qq + 1 < R) v[u] = __ldcs(reinterpret_cast<const ulonglong2 *>(a.read_key) + qq);
-                    else v[u].x = __ldcs(a.read_key + 2 * qq);
-                }
-            }
+            for (int u = 0; u < kProbeUnroll; ++u) v[u] = nxt[u];
+            if (qb + kProbeBatch < q1) fetch(q + kProbeBatch);   // next batch requested before this one is used
+            unsigned pass = 0;
 #pragma unroll
             for (int u = 0; u < kProbeUnroll; ++u) {
                 const long long row = 2 * (q + (long long)u * kProbeThreads);
                 const unsigned mx = bloom_bits(v[u].x), my = bloom_bits(v[u].y);
-                const bool px = row >= r0 && row < r1 && (s_bm[bloom_word(v[u].x, bmw)] & mx) == mx;
-                const bool py = row + 1 >= r0 && row + 1 < r1 && (s_bm[bloom_word(v[u].y, bmw)] & my) == my;
-                if (px) probe_slot(a, v[u].x, (int)row, base, mask);
-                if (py) probe_slot(a, v[u].y, (int)row + 1, base, mask);
+                if (row >= r0 && row < r1 && (s_bm[bloom_word(v[u].x, bmw)] & mx) == mx) pass |= 1u << (2 * u);
+                if (row + 1 >= r0 && row + 1 < r1 && (s_bm[bloom_word(v[u].y, bmw)] & my) == my) pass |= 2u << (2 * u);
             }
+            // queue the candidates: one shared-memory atomic per warp
+            const int cnt = __popc(pass);
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            int wbase = 0;
+            if (lane == 31 && inc) wbase = atomicAdd(&s_qn, inc);
+            wbase = __shfl_sync(0xffffffffu, wbase, 31);
+            int pos = wbase + inc - cnt;
+#pragma unroll
+            for (int u = 0; u < kProbeUnroll; ++u) {
+                const int row = (int)(2 * (q + (long long)u * kProbeThreads));
+                if (pass >> (2 * u) & 1u) {
+                    if (pos < qcap) { s_qkey[pos] = v[u].x; s_qrow[pos] = row; } else probe_candidate(a, v[u].x, row, base, mask);
+                    ++pos;
+                }
+                if (pass >> (2 * u + 1) & 1u) {
+                    if (pos < qcap) { s_qkey[pos] = v[u].y; s_qrow[pos] = row + 1; } else probe_candidate(a, v[u].y, row + 1, base, mask);
+                    ++pos;
+                }
+            }
+            __syncthreads();                                     // all candidates of the batch are queued
+            const int qn = min(s_qn, qcap);
+            __syncthreads();                                     // ... and everybody has read the count
+            if (threadIdx.x == 0) s_qn = 0;
+            for (int i = threadIdx.x; i < qn; i += kProbeThreads) probe_candidate(a, s_qkey[i], s_qrow[i], base, mask);
+            __syncthreads();                                     // queue free again, reset visible
         }
-        __syncthreads();                                         // the filter is replaced for the next contig
         r0 = r1;
         ++s;
     }
@@ -384,29 +418,27 @@ __device__ void oneps_block(const PhaseArgs &a, int s, long long *smem_tile) {
     const int b = (int)a.sv_off[s], n = (int)a.sv_off[s + 1] - b;
     const int per = (n + kThreads - 1) / kThreads;
     const int c0 = min(n, (int)threadIdx.x * per), c1 = min(n, c0 + per);
-    long long reg[kStaged ? kStage : 1];
-    if (kStaged) {
-#pragma unroll
-        for (int u = 0; u < kStage; ++u) reg[u] = c0 + u < c1 ? __ldcg(a.cand + b + c0 + u) : kNoCand;
+    if (kStaged) {                                   // n <= kSortSmemBytes / 8: one coalesced read of the shard
+        for (int i = threadIdx.x; i < n; i += kThreads) smem_tile[i] = __ldcg(a.cand + b + i);
+        __syncthreads();
     }
-#define CAND(u) (kStaged ? reg[u] : __ldcg(a.cand + b + c0 + (u)))
-#define FOR_CHUNK(u) _Pragma("unroll") for (int u = 0; u < (kStaged ? kStage : c1 - c0); ++u) if (kStaged ? c0 + u < c1 : true)
+#define CAND(i) (kStaged ? smem_tile[i] : __ldcg(a.cand + b + (i)))
     // fast path: the candidates already are non-decreasing in VCF order (position-sorted VCF)
     long long mx = kNone, lastv = kNone;
-    FOR_CHUNK(u) { const long long v = CAND(u); if (v != kNoCand) { mx = max(mx, v); lastv = v; } }
+    for (int i = c0; i < c1; ++i) { const long long v = CAND(i); if (v != kNoCand) { mx = max(mx, v); lastv = v; } }
     const long long run = block_scan_exclusive(mx, kNone, OpMax(), (long long *)nullptr);
     long long cur = run;
     int cnt = 0;
     bool ok = true;
-    FOR_CHUNK(u) {
-        const long long v = CAND(u);
+    for (int i = c0; i < c1; ++i) {
+        const long long v = CAND(i);
         if (v != kNoCand) { if (v < cur) ok = false; else if (v > cur) { ++cnt; cur = v; } }
     }
     if (__syncthreads_and(ok)) {
         int total;
         int w = block_scan_exclusive(cnt, 0, OpSum(), &total);
         cur = run;
-        FOR_CHUNK(u) { const long long v = CAND(u); if (v != kNoCand && v > cur) { a.oneps[b + w++] = (int)v; cur = v; } }
+        for (int i = c0; i < c1; ++i) { const long long v = CAND(i); if (v != kNoCand && v > cur) { a.oneps[b + w++] = (int)v; cur = v; } }
         if (threadIdx.x == 0) a.oneps_n[s] = total;
         return;
     }
@@ -415,15 +447,24 @@ __device__ void oneps_block(const PhaseArgs &a, int s, long long *smem_tile) {
     const long long prev0 = block_scan_exclusive(lastv, kNone, OpLast(), (long long *)nullptr);
     long long prev = prev0;
     cnt = 0;
-    FOR_CHUNK(u) { const long long v = CAND(u); if (v != kNoCand) { cnt += v != prev; prev = v; } }
+    for (int i = c0; i < c1; ++i) { const long long v = CAND(i); if (v != kNoCand) { cnt += v != prev; prev = v; } }
     int r;
     int w = block_scan_exclusive(cnt, 0, OpSum(), &r);
-    long long *v = (long long)next_pow2(max(r, 1)) * (long long)sizeof(long long) <= kSortSmemBytes
-                       ? smem_tile : a.sort_scratch + 2ll * b;
-    prev = prev0;
-    FOR_CHUNK(u) { const long long x = CAND(u); if (x != kNoCand) { if (x != prev) v[w++] = x; prev = x; } }
+    long long *v;
+    if (kStaged) {                                   // heads go back into the tile once everybody has read it
+        long long hd[kSortSmemBytes / 8 / kThreads];
+        int nh = 0;
+        prev = prev0;
+        for (int i = c0; i < c1; ++i) { const long long x = CAND(i); if (x != kNoCand) { if (x != prev) hd[nh++] = x; prev = x; } }
+        __syncthreads();
+        v = smem_tile;
+        for (int k = 0; k < nh; ++k) v[w + k] = hd[k];
+    } else {
+        v = a.sort_scratch + 2ll * b;
+        prev = prev0;
+        for (int i = c0; i < c1; ++i) { const long long x = CAND(i); if (x != kNoCand) { if (x != prev) v[w++] = x; prev = x; } }
+    }
 #undef CAND
-#undef FOR_CHUNK
     __syncthreads();
     if (r <= 512) {
         for (int h = threadIdx.x; h < r; h += kThreads) {
@@ -465,24 +506,68 @@ __device__ void oneps_block(const PhaseArgs &a, int s, long long *smem_tile) {
 }
 
 __device__ __forceinline__ void oneps_any(const PhaseArgs &a, int s, long long *smem_tile) {
-    if ((int)(a.sv_off[s + 1] - a.sv_off[s]) <= kThreads * kStage) oneps_block<true>(a, s, smem_tile);
+    if ((int)(a.sv_off[s + 1] - a.sv_off[s]) * (int)sizeof(long long) <= kSortSmemBytes) oneps_block<true>(a, s, smem_tile);
     else oneps_block<false>(a, s, smem_tile);
 }
 
 // ------------------------------------------------------------------------------------------
-// k_reduce: G lanes per SV.  Resolves each support read to its read row, then reduces.
+// k_reduce: kReduceLanes lanes per SV.  A lane requests the join rows of up to kReduceUnroll of its
+// support reads at once, then their (ps, pc, hp) together, then reduces: class = #distinct PS
+// (:192-194), one-PS candidate = PS of the first read with pc <= 8100 (:195-203), class-1 counts and
+// score sums (:74-84).  SVs that turn out to span several phase sets (class 2) also get their
+// per-PS statistics here, while the tags are still in registers, in first-seen order (:85-105);
+// k_predict only has to filter them by the one-PS set.
+// Dependent chain: csr_off -> join_row -> tags -> (shuffles) -> stores -> credit.
 // ------------------------------------------------------------------------------------------
-template <int G>
+constexpr int kReduceUnroll = 4;
+
+struct C2Group {                                   // shared-memory table of one lane group
+    int ps[kC2Max], tot[kC2Max], n1[kC2Max], n2[kC2Max], bad[kC2Max];
+    unsigned long long s1[kC2Max], s2[kC2Max];
+};
+
+// one step of the per-PS table: every lane of the group offers one read (q = qualifying)
+__device__ __forceinline__ void c2_update(C2Group &g, unsigned gmask, bool q, int ps, int pc, int hp, int &n_d) {
+    const int wl = threadIdx.x & 31;
+    int id = -1;
+    const int known = min(n_d, kC2Max);
+    for (int k = 0; k < known; ++k)
+        if (q && g.ps[k] == ps) id = k;
+    const bool fresh = q && id < 0;
+    // lanes offering the same new PS; the lowest lane of each set speaks for it, in lane (= read) order
+    const unsigned peers = __match_any_sync(gmask, fresh ? (long long)ps : (long long)0x4000000000000000ll + wl);
+    const int leader = __ffs(peers) - 1;
+    const unsigned leaders = __ballot_sync(gmask, fresh && leader == wl) & gmask;
+    if (fresh) {
+        id = n_d + __popc(leaders & ((1u << leader) - 1u));
+        if (leader == wl && id < kC2Max) {
+            g.ps[id] = ps; g.tot[id] = 0; g.n1[id] = 0; g.n2[id] = 0; g.bad[id] = 0; g.s1[id] = 0ull; g.s2[id] = 0ull;
+        }
+    }
+    n_d += __popc(leaders);
+    __syncwarp(gmask);
+    if (q && id < kC2Max) {
+        atomicAdd(&g.tot[id], 1);
+        if (hp == 1) { atomicAdd(&g.n1[id], 1); atomicAdd(&g.s1[id], (unsigned long long)(long long)pc); }
+        else if (hp == 2) { atomicAdd(&g.n2[id], 1); atomicAdd(&g.s2[id], (unsigned long long)(long long)pc); }
+        else g.bad[id] = hp | 0x100;
+    }
+    __syncwarp(gmask);
+}
+
 __global__ void __launch_bounds__(kThreads, 6)
 k_reduce(PhaseArgs a) {
+    constexpr int G = kReduceLanes;
     __shared__ __align__(16) long long s_tile[kSortSmemBytes / 8];
+    __shared__ C2Group s_c2[kReducePerBlock];
     __shared__ int s_list[kThreads];
     __shared__ int s_n;
-    const int lane = threadIdx.x % G;
-    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) / G * G));
-    const int sv0 = blockIdx.x * (kThreads / G);
-    const int sv1 = min(a.n_svs, sv0 + kThreads / G);
-    const int sv = sv0 + threadIdx.x / G;
+    const SvTile tile = threadIdx.x == 0 ? a.reduce_tiles[blockIdx.x] : SvTile{0, 0, 0, 0};   // for the credit, requested early
+    const int lane = threadIdx.x % G, grp = threadIdx.x / G;
+    const unsigned gmask = ((1u << G) - 1u) << ((threadIdx.x & 31) / G * G);
+    const int sv0 = blockIdx.x * kReducePerBlock;
+    const int sv1 = min(a.n_svs, sv0 + kReducePerBlock);
+    const int sv = sv0 + grp;
     const bool live = sv < a.n_svs;
     long long b = 0, e = 0;
     bool kept = false;
@@ -497,20 +582,30 @@ k_reduce(PhaseArgs a) {
     long long t1 = 0, t2 = 0;
     long long first_q = INT64_MAX;      // CSR index of the first read with pc <= pc_max
     int first_q_ps = 0;
-    for (long long j = b + lane; j < e; j += G) {
-        const int row = a.join_row[j];
-        if (row >= 0) {
-            const int ps = __ldg(a.read_ps + row);
-            const int pc = __ldg(a.read_pc + row);
-            const int hp = __ldg(a.read_hp + row);
+    int row[kReduceUnroll], ps[kReduceUnroll], pc[kReduceUnroll], hp[kReduceUnroll];
+    for (long long base = b; base < e; base += G * kReduceUnroll) {
+#pragma unroll
+        for (int u = 0; u < kReduceUnroll; ++u) {
+            const long long j = base + u * G + lane;
+            row[u] = j < e ? a.join_row[j] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < kReduceUnroll; ++u) {
+            ps[u] = pc[u] = hp[u] = 0;
+            if (row[u] >= 0) { ps[u] = __ldg(a.read_ps + row[u]); pc[u] = __ldg(a.read_pc + row[u]); hp[u] = __ldg(a.read_hp + row[u]); }
+        }
+#pragma unroll
+        for (int u = 0; u < kReduceUnroll; ++u) {
+            if (row[u] < 0) continue;
             ++hits;
-            ps_lo = min(ps_lo, ps);
-            ps_hi = max(ps_hi, ps);
-            if (pc <= c_thr.pc_max) {
+            ps_lo = min(ps_lo, ps[u]);
+            ps_hi = max(ps_hi, ps[u]);
+            if (pc[u] <= c_thr.pc_max) {
                 ++nq;
-                if (j < first_q) { first_q = j; first_q_ps = ps; }
-                if (hp == 1) { ++h1; t1 += pc; }
-                else if (hp == 2) { ++h2; t2 += pc; }
+                const long long j = base + u * G + lane;
+                if (j < first_q) { first_q = j; first_q_ps = ps[u]; }
+                if (hp[u] == 1) { ++h1; t1 += pc[u]; }
+                else if (hp[u] == 2) { ++h2; t2 += pc[u]; }
             }
         }
     }
@@ -522,8 +617,8 @@ k_reduce(PhaseArgs a) {
     const long long fq = group_min(first_q, gmask, G);
     const unsigned owner = __ballot_sync(gmask, first_q == fq && fq != INT64_MAX) & gmask;
     const int fps = __shfl_sync(gmask, first_q_ps, owner ? __ffs(owner) - 1 : (threadIdx.x & 31));
+    const int cls = hits == 0 ? 0 : (ps_lo == ps_hi ? 1 : 2);
     if (live && lane == 0) {
-        const int cls = hits == 0 ? 0 : (ps_lo == ps_hi ? 1 : 2);
         a.n_hit[sv] = hits;
         a.cls[sv] = kept ? (uint8_t)cls : (uint8_t)DUET_CLS_FILTERED;
         a.gt[sv] = 0;
@@ -533,38 +628,81 @@ k_reduce(PhaseArgs a) {
         a.allhap[sv] = cls == 2 ? nq : h1 + h2;
         a.totsc1[sv] = t1; a.totsc2[sv] = t2;
         a.ps[sv] = owner ? ps_lo : 0;   // class 1: every joined read carries the same PS
-        if (kept && cls == 2) a.c2_list[atomicAdd(a.c2_count, 1)] = sv;
     }
     if (live && lane < DUET_N_FEATURES) a.features[(size_t)lane * a.n_svs + sv] = 0.0;
 
-    const int n_done = credit_shards(a, a.done_reduce, sv0, sv1, s_list, &s_n);
+    if (live && kept && cls == 2) {                  // group-uniform: per-PS statistics in read order
+        C2Group &g = s_c2[grp];
+        int n_d = 0;
+        if (e - b <= G * kReduceUnroll) {            // the tags are still in registers
+#pragma unroll
+            for (int u = 0; u < kReduceUnroll; ++u)
+                c2_update(g, gmask, row[u] >= 0 && pc[u] <= c_thr.pc_max, ps[u], pc[u], hp[u], n_d);
+        } else {
+            for (long long base = b; base < e; base += G) {
+                const long long j = base + lane;
+                const int r = j < e ? a.join_row[j] : -1;
+                int xps = 0, xpc = 0, xhp = 0;
+                if (r >= 0) { xps = __ldg(a.read_ps + r); xpc = __ldg(a.read_pc + r); xhp = __ldg(a.read_hp + r); }
+                c2_update(g, gmask, r >= 0 && xpc <= c_thr.pc_max, xps, xpc, xhp, n_d);
+            }
+        }
+        C2Rec *rec = a.c2rec + sv;
+        if (lane == 0) { rec->n_d = min(n_d, kC2Max); rec->overflow = n_d > kC2Max; }
+        if (lane < min(n_d, kC2Max))
+            rec->d[lane] = C2Ent{g.ps[lane], g.tot[lane], g.n1[lane], g.n2[lane], (long long)g.s1[lane], (long long)g.s2[lane], g.bad[lane], 0};
+    }
+
+    // credit the shards of this block's SVs; the block completing a shard builds its one-PS list
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int n = 0;
+        if (sv0 < sv1) {
+            for (int s = tile.s_first; s <= tile.s_last; ++s) {
+                const int o0 = s == tile.s_first ? tile.off0 : (int)a.sv_off[s];
+                const int o1 = s == tile.s_first ? tile.off1 : (int)a.sv_off[s + 1];
+                const int lo = max(o0, sv0), hi = min(o1, sv1);
+                if (hi <= lo) continue;
+                if (atomicAdd(a.done_reduce + s, hi - lo) + (hi - lo) == o1 - o0) {
+                    a.done_reduce[s] = 0;
+                    s_list[n++] = s;
+                }
+            }
+        }
+        s_n = n;
+        __threadfence();
+    }
+    __syncthreads();
+    const int n_done = s_n;
     for (int i = 0; i < n_done; ++i) oneps_any(a, s_list[i], s_tile);
 }
 
 // ------------------------------------------------------------------------------------------
 // k_predict helpers
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool in_sorted(const int *__restrict__ v, int n, int x) {
+__device__ __forceinline__ bool in_sorted(const int *v, int n, int x) {       // v: global or shared
     int lo = 0, hi = n;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const int m = __ldg(v + mid);
+        const int m = v[mid];
         if (m < x) lo = mid + 1; else hi = mid;
     }
-    return lo < n && __ldg(v + lo) == x;
+    return lo < n && v[lo] == x;
 }
 
 // :107-111 -- nearest element of the sorted one-PS list to pos, an exact tie goes up
-__device__ __forceinline__ int nearest_ps(const int *__restrict__ v, int n, int pos) {
+__device__ __forceinline__ int nearest_ps(const int *v, int n, int pos) {
     int lo = 0, hi = n;               // searchsorted(side='left')
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (__ldg(v + mid) < pos) lo = mid + 1; else hi = mid;
+        if (v[mid] < pos) lo = mid + 1; else hi = mid;
     }
     const int below = max(lo - 1, 0), above = min(lo, n - 1);
-    const long long db = llabs((long long)pos - __ldg(v + below));
-    const long long da = llabs((long long)pos - __ldg(v + above));
-    return db < da ? __ldg(v + below) : __ldg(v + above);
+    const int vb = v[below], va = v[above];
+    const long long db = llabs((long long)pos - vb);
+    const long long da = llabs((long long)pos - va);
+    return db < da ? vb : va;
 }
 
 struct Class2Stats { int h1, h2, hap0, allhap, ps; long long t1, t2; };
@@ -844,17 +982,18 @@ __device__ void order_block(const PhaseArgs &a, int s, long long *smem_tile) {
 }
 
 // ------------------------------------------------------------------------------------------
-// k_predict.  Three independent pieces of work per block:
-//   A  class-2 SVs come from the compact list k_reduce wrote -- one warp per SV, spread over the grid;
-//   B  threads 0..63 decide one class-0/1 SV each (SVs blockIdx*64 ...);
-//   C  the join table slots set by k_build are handed back EMPTY (grid-stride over the support reads).
-// Every finished SV credits its shard; whoever completes a shard queues it and the block then writes
-// that shard's emission order and counters.
+// k_predict: one thread per SV (threads 0..63 of a block; all 256 help with the rest).
+//   * the one-PS list of the block's first contig is staged in shared memory (binary searches stay
+//     on chip); class-2 SVs read the per-PS statistics k_reduce recorded and keep the first-seen
+//     in-set phase set with the most reads (:99-105); then features and the T1-T5 tree;
+//   * SVs whose reads span more than kC2Max phase sets fall back to a warp-cooperative exact path;
+//   * the join table slots and filter bits set by k_build are handed back clean;
+//   * every SV credits its shard; the block completing a shard writes its emission order + counters.
+// Dependent chain: [tile, per-SV state] -> [oneps_n, staged list, class-2 record] -> decide -> stores.
 // ------------------------------------------------------------------------------------------
-constexpr int kPredictPerBlock = 64;
+constexpr int kOneSmem = 2048;
 
-__device__ __forceinline__ void credit_one(const PhaseArgs &a, int s, int n, int *s_list, int *s_n) {
-    const int total = (int)(a.sv_off[s + 1] - a.sv_off[s]);
+__device__ __forceinline__ void credit_one(const PhaseArgs &a, int s, int n, int total, int *s_list, int *s_n) {
     __threadfence();
     if (atomicAdd(a.done_predict + s, n) + n == total) {
         a.done_predict[s] = 0;
@@ -867,74 +1006,102 @@ __global__ void __launch_bounds__(kThreads)
 k_predict(PhaseArgs a) {
     __shared__ Class2Smem s_c2[kThreads / 32];
     __shared__ __align__(16) long long s_tile[kSortSmemBytes / 8];
+    __shared__ int s_one[kOneSmem];
     __shared__ int s_list[kThreads];
     __shared__ int s_credit[kPredictPerBlock];
-    __shared__ int s_n;
+    __shared__ int s_fb[kPredictPerBlock];
+    __shared__ int s_n, s_nfb;
+    const SvTile tile = a.predict_tiles[blockIdx.x];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_n = 0;
-    if (threadIdx.x < kPredictPerBlock) s_credit[threadIdx.x] = -1;    // shard credited by thread t's SV
-    __syncthreads();
-
-    // ---- A: class-2 SVs, one warp each
-    const int n_c2 = *a.c2_count;
-    for (int k = blockIdx.x * (kThreads / 32) + w; k < n_c2; k += gridDim.x * (kThreads / 32)) {
-        const int sv2 = a.c2_list[k];
-        const int s = __ldg(a.sv_shard + sv2);
-        const int n_one = a.oneps_n[s];
-        if (n_one > 0) {                                             // else contig skipped (:209-210)
-            const long long b2 = __ldg(a.csr_off + sv2), e2 = __ldg(a.csr_off + sv2 + 1);
-            const int *o2 = a.oneps + __ldg(a.sv_off + s);
-            Class2Stats t{0, 0, 0, a.allhap[sv2], 0, 0, 0};
-            class2_stats(a, sv2, b2, e2, o2, n_one, s_c2[w], t);
-            if (lane == 0) decide_and_store(a, sv2, 2, t, o2, n_one, (int)(e2 - b2));
-        }
-        if (lane == 0) credit_one(a, s, 1, s_list, &s_n);
-    }
-
-    // ---- B: everything that is not a kept class-2 SV
     const int blk0 = blockIdx.x * kPredictPerBlock, blk1 = min(a.n_svs, blk0 + kPredictPerBlock);
     const int sv = blk0 + threadIdx.x;
-    if (threadIdx.x < kPredictPerBlock && sv < blk1) {
-        const int cls = a.cls[sv];
-        const int s = __ldg(a.sv_shard + sv);
-        if (cls == 0 || cls == 1) {
-            const int n_one = a.oneps_n[s];
-            if (n_one > 0) {
-                Class2Stats st{0, 0, 0, 0, 0, 0, 0};
-                if (cls == 1) st = Class2Stats{a.hap1[sv], a.hap2[sv], 0, a.allhap[sv], a.ps[sv], a.totsc1[sv], a.totsc2[sv]};
-                decide_and_store(a, sv, cls, st, a.oneps + __ldg(a.sv_off + s), n_one,
-                                 (int)(__ldg(a.csr_off + sv + 1) - __ldg(a.csr_off + sv)));
+    const bool mine = threadIdx.x < kPredictPerBlock && sv < blk1;
+    int cls = DUET_CLS_FILTERED, shard = 0, n_list = 0;
+    Class2Stats st{0, 0, 0, 0, 0, 0, 0};
+    if (mine) {                                                  // everything that does not depend on the tile
+        cls = a.cls[sv];
+        shard = __ldg(a.sv_shard + sv);
+        n_list = (int)(__ldg(a.csr_off + sv + 1) - __ldg(a.csr_off + sv));
+        st = Class2Stats{a.hap1[sv], a.hap2[sv], 0, a.allhap[sv], a.ps[sv], a.totsc1[sv], a.totsc2[sv]};
+    }
+    const int n0 = a.oneps_n[tile.s_first];
+    const int n_stage = min(tile.off1 - tile.off0, kOneSmem);
+    for (int i = threadIdx.x; i < n_stage; i += kThreads) s_one[i] = a.oneps[tile.off0 + i];   // only [0, n0) is meaningful
+    if (threadIdx.x == 0) { s_n = 0; s_nfb = 0; }
+    if (threadIdx.x < kPredictPerBlock) s_credit[threadIdx.x] = mine ? shard : -1;
+    __syncthreads();
+
+    if (mine && cls != DUET_CLS_FILTERED) {
+        const bool home = shard == tile.s_first;
+        const int n_one = home ? n0 : a.oneps_n[shard];              // 0: contig skipped (:209-210)
+        const int *one = home && n0 <= kOneSmem ? s_one : a.oneps + (home ? tile.off0 : (int)a.sv_off[shard]);
+        if (n_one > 0) {
+            bool ready = true;
+            if (cls == 0) st = Class2Stats{0, 0, 0, 0, 0, 0, 0};     // get_phase_info skips both loops
+            if (cls == 2) {
+                const C2Rec *rec = a.c2rec + sv;
+                const int allhap = st.allhap;
+                st = Class2Stats{0, 0, 0, allhap, 0, 0, 0};
+                if (rec->overflow) {
+                    s_fb[atomicAdd(&s_nfb, 1)] = threadIdx.x;
+                    ready = false;
+                } else {
+                    const int n_d = rec->n_d;
+                    int best = 0;
+                    for (int t = 0; t < n_d; ++t) {                  // first-seen order; strict '>' (:101)
+                        const C2Ent ent = rec->d[t];
+                        if (!in_sorted(one, n_one, ent.ps)) continue;
+                        if (ent.bad) report(a.status, DUET_ERR_BAD_HP, sv, ent.bad & 0xff);
+                        if (ent.tot > best) {
+                            best = ent.tot;
+                            st.h1 = ent.n1; st.h2 = ent.n2; st.t1 = ent.s1; st.t2 = ent.s2; st.ps = ent.ps;
+                            st.hap0 = allhap - ent.n1 - ent.n2;
+                        }
+                    }
+                }
             }
+            if (ready) decide_and_store(a, sv, cls, st, one, n_one, n_list);
         }
-        if (cls != 2) s_credit[threadIdx.x] = s;
+    }
+    __syncthreads();
+    for (int k = w; k < s_nfb; k += kThreads / 32) {                 // rare: > kC2Max phase sets in one SV
+        const int sv2 = blk0 + s_fb[k];
+        const int s2 = __ldg(a.sv_shard + sv2);
+        const long long b2 = __ldg(a.csr_off + sv2), e2 = __ldg(a.csr_off + sv2 + 1);
+        const int *o2 = a.oneps + a.sv_off[s2];
+        const int n2 = a.oneps_n[s2];
+        Class2Stats t{0, 0, 0, a.allhap[sv2], 0, 0, 0};
+        class2_stats(a, sv2, b2, e2, o2, n2, s_c2[w], t);
+        if (lane == 0) decide_and_store(a, sv2, 2, t, o2, n2, (int)(e2 - b2));
     }
 
-    // ---- C: the table is not read after k_reduce
+    // the table is not read after k_probe: hand it back clean
     for (long long j = (long long)blockIdx.x * kThreads + threadIdx.x; j < a.n_joins; j += (long long)gridDim.x * kThreads) {
         const int slot = a.csr_slot[j];
-        const unsigned long long key = __ldg(a.csr_key + j);
+        const int word = a.csr_bmword[j];
         if (a.csr_key_hi && a.tab[slot].hi != __ldg(a.csr_key_hi + j))      // two names, one 64-bit key
-            report(a.status, DUET_ERR_HASH_COLLISION, -1, (long long)key);
+            report(a.status, DUET_ERR_HASH_COLLISION, -1, (long long)__ldg(a.csr_key + j));
         a.tab[slot].key = kEmptyKey;
         a.tab[slot].head = -1;
-        a.tab[slot].multi = -1;
-        a.bitmap[a.csr_bmword[j]] = 0u;
+        a.bitmap[word] = 0u;
     }
 
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         int run_s = -1, run_n = 0;
-        for (int t = 0; t < kPredictPerBlock; ++t) {                 // shards are contiguous in SV order
-            const int s = s_credit[t];
-            if (s < 0) continue;
+        for (int t = 0; t <= kPredictPerBlock; ++t) {                // shards are contiguous in SV order
+            const int s = t < kPredictPerBlock ? s_credit[t] : -1;
             if (s != run_s) {
-                if (run_n) credit_one(a, run_s, run_n, s_list, &s_n);
+                if (run_n) {
+                    const int total = run_s == tile.s_first ? tile.off1 - tile.off0
+                                                            : (int)(a.sv_off[run_s + 1] - a.sv_off[run_s]);
+                    credit_one(a, run_s, run_n, total, s_list, &s_n);
+                }
                 run_s = s; run_n = 0;
             }
-            ++run_n;
+            if (s >= 0) ++run_n;
         }
-        if (run_n) credit_one(a, run_s, run_n, s_list, &s_n);
     }
     __syncthreads();
     const int n_done = min(s_n, kThreads);

@@ -180,13 +180,15 @@ def test_tie_order_and_filters(engine):
     assert res.order.tolist() == [4, 2, 1, 3, 0]
 
 
-def test_more_than_32_phase_sets_in_one_sv(engine):
-    """The shared-memory distinct-PS list holds 32 entries; beyond that the exact slow path runs."""
-    rng = np.random.default_rng(0)
-    pss = list(range(1000, 1000 + 45 * 10, 10))
+@pytest.mark.parametrize("n_ps", [5, 8, 9, 12, 45])
+def test_many_phase_sets_in_one_sv(engine, n_ps):
+    """k_reduce records up to 8 distinct PS per SV; 9..32 take the warp-cooperative fallback with its
+    shared-memory list; beyond 32 the exact quadratic path runs.  All must agree with the oracle."""
+    rng = np.random.default_rng(n_ps)
+    pss = list(range(1000, 1000 + n_ps * 10, 10))
     reads, names = [], []
     for k in range(400):
-        ps = int(rng.choice(pss)) if k >= 45 else pss[k]
+        ps = int(rng.choice(pss)) if k >= n_ps else pss[k]
         reads.append((f"r{k}", int(rng.integers(1, 3)), ps, int(rng.integers(0, 9000))))
         names.append(f"r{k}")
     helpers, hsv = [], []
