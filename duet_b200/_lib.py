@@ -18,6 +18,10 @@ FEATURE_NAMES = ("hapread_ratio", "sv_ratio", "hap1_avgsc", "hap2_avgsc", "totsc
 COUNTER_NAMES = ("n_sv", "n_kept", "n_emitted", "n_1|0", "n_0|1", "n_1|1", "n_joins", "n_hits")
 
 
+INPUT_COLUMNS = ("read_off", "sv_off", "read_key", "read_tag", "sv_pos", "sv_svlen", "sv_svread", "sv_refread",
+                 "sv_flags", "sv_group", "csr_off", "csr_key", "csr_chk")
+
+
 class Thresholds(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("svlen_thres", "suppread_thres", "pc_max", "c0_sv_num_min",
                                          "c2_sv_num_min", "c2_hap0_min", "c1_ref_num_max", "_pad")] + \
@@ -30,9 +34,7 @@ class Thresholds(C.Structure):
 class PhaseInput(C.Structure):
     _fields_ = [("mem", C.c_int32), ("n_shards", C.c_int32), ("n_reads", C.c_int64), ("n_svs", C.c_int64),
                 ("n_joins", C.c_int64)] + \
-               [(n, C.c_void_p) for n in ("read_off", "sv_off", "read_key", "read_key_hi", "read_hp", "read_ps",
-                                          "read_pc", "sv_pos", "sv_svlen", "sv_svread", "sv_refread", "sv_flags",
-                                          "sv_group", "csr_off", "csr_key", "csr_key_hi")]
+               [(n, C.c_void_p) for n in INPUT_COLUMNS]
 
 
 class PhaseOutput(C.Structure):
@@ -63,7 +65,8 @@ SYMBOLS = (
     "duet_abi_version", "duet_default_thresholds", "duet_create", "duet_destroy", "duet_last_error",
     "duet_set_thresholds", "duet_set_stream", "duet_phase_upload", "duet_phase_execute",
     "duet_phase_download", "duet_phase_run", "duet_host_alloc", "duet_host_free", "duet_sync",
-    "duet_get_timings", "duet_launch_count", "duet_default_cluster_params", "duet_cluster_run", "duet_hash_names", "duet_decode_sam_text", "duet_count_lines",
+    "duet_get_timings", "duet_launch_count", "duet_default_cluster_params", "duet_cluster_run", "duet_hash_names",
+    "duet_pack_tags", "duet_decode_sam_text", "duet_count_lines",
 )
 DECODE_ERR_INDEX, DECODE_ERR_VALUE, DECODE_ERR_ASCII, DECODE_ERR_RANGE, DECODE_ERR_CAPACITY = 20, 21, 22, 23, 24
 
@@ -115,8 +118,10 @@ def load() -> C.CDLL:
                                      C.POINTER(C.c_int64), C.POINTER(C.c_float)]
     lib.duet_hash_names.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.duet_hash_names.restype = None
-    lib.duet_decode_sam_text.argtypes = [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 5 + \
+    lib.duet_decode_sam_text.argtypes = [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 2 + \
                                        [C.POINTER(C.c_int64)] * 3
+    lib.duet_pack_tags.argtypes = [C.c_int64] + [C.c_void_p] * 5
+    lib.duet_pack_tags.restype = None
     lib.duet_count_lines.argtypes = [C.c_void_p, C.c_int64]
     lib.duet_count_lines.restype = C.c_int64
     _lib = lib

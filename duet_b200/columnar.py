@@ -14,6 +14,20 @@ import numpy as np
 from . import _lib
 from .namehash import hash128_fixed
 
+# include/duet_b200.h :: duet_read_tag (16 bytes)
+TAG_DTYPE = np.dtype([("ps", "<i4"), ("pc", "<i4"), ("chk", "<u4"), ("hp", "u1"), ("pad", "u1", (3,))])
+assert TAG_DTYPE.itemsize == 16
+
+
+def pack_tags(hp, ps, pc, hi=None) -> np.ndarray:
+    """HP / PS / PC (+ hash high words) -> duet_read_tag records; chk = low 32 bits of `hi`."""
+    n = len(hp)
+    t = np.zeros(n, TAG_DTYPE)
+    t["hp"], t["ps"], t["pc"] = hp, ps, pc
+    if hi is not None:
+        t["chk"] = (np.asarray(hi, np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    return t
+
 
 @dataclass
 class PhaseBatch:
@@ -21,11 +35,8 @@ class PhaseBatch:
     read_off: np.ndarray      # int64 [n_shards+1]
     sv_off: np.ndarray        # int64 [n_shards+1]
     # haplotagged reads, file order inside a shard (sv_phasing_fn.py:28-29)
-    read_key: np.ndarray      # uint64 [R]
-    read_key_hi: np.ndarray | None
-    read_hp: np.ndarray       # uint8  [R]
-    read_ps: np.ndarray       # int32  [R]
-    read_pc: np.ndarray       # int32  [R]
+    read_key: np.ndarray      # uint64 [R]  low word of the name hash
+    read_tag: np.ndarray      # TAG_DTYPE [R]  HP / PS / PC + check word
     # SV records, VCF order inside a shard (read_file.py:30)
     sv_pos: np.ndarray        # int32 [S]
     sv_svlen: np.ndarray      # int32 [S]  |SVLEN|
@@ -35,7 +46,7 @@ class PhaseBatch:
     sv_group: np.ndarray | None   # int32 [S] rank of the CHROM string inside the shard
     csr_off: np.ndarray       # int64 [S+1]
     csr_key: np.ndarray       # uint64 [J]
-    csr_key_hi: np.ndarray | None
+    csr_chk: np.ndarray | None    # uint32 [J] check word, None = no collision check
     # host-only row text (never sent to the device)
     shard_sample: list = field(default_factory=list)     # sample index per shard
     shard_contig: list = field(default_factory=list)     # chrom_list name per shard
@@ -43,6 +54,18 @@ class PhaseBatch:
     sv_type: list = field(default_factory=list)          # SVTYPE string per SV
     sv_ref: list = field(default_factory=list)
     sv_alt: list = field(default_factory=list)
+
+    @property
+    def read_hp(self) -> np.ndarray:
+        return self.read_tag["hp"]
+
+    @property
+    def read_ps(self) -> np.ndarray:
+        return self.read_tag["ps"]
+
+    @property
+    def read_pc(self) -> np.ndarray:
+        return self.read_tag["pc"]
 
     @property
     def n_shards(self) -> int:
@@ -63,9 +86,7 @@ class PhaseBatch:
     def input_bytes(self) -> int:
         """Bytes a host->device upload moves (the h2d_bytes_per_step of bench.py)."""
         tot = 0
-        for name in ("read_off", "sv_off", "read_key", "read_key_hi", "read_hp", "read_ps", "read_pc", "sv_pos",
-                     "sv_svlen", "sv_svread", "sv_refread", "sv_flags", "sv_group", "csr_off", "csr_key",
-                     "csr_key_hi"):
+        for name in _lib.INPUT_COLUMNS:
             arr = getattr(self, name)
             if arr is not None:
                 tot += arr.nbytes
@@ -83,8 +104,10 @@ class PhaseBatch:
         assert self.sv_off[0] == 0 and self.sv_off[ns] == self.n_svs
         assert self.csr_off[0] == 0 and self.csr_off[self.n_svs] == self.n_joins
         assert self.read_key.dtype == np.uint64 and self.csr_key.dtype == np.uint64
-        assert self.read_hp.dtype == np.uint8 and self.sv_flags.dtype == np.uint8
-        for a in (self.read_ps, self.read_pc, self.sv_pos, self.sv_svlen, self.sv_svread, self.sv_refread):
+        assert self.read_tag.dtype == TAG_DTYPE and self.read_tag.shape[0] == self.n_reads
+        assert self.sv_flags.dtype == np.uint8
+        assert self.csr_chk is None or self.csr_chk.dtype == np.uint32
+        for a in (self.sv_pos, self.sv_svlen, self.sv_svread, self.sv_refread):
             assert a.dtype == np.int32
 
     def select_shards(self, idx) -> "PhaseBatch":
@@ -92,7 +115,7 @@ class PhaseBatch:
         idx = [int(i) for i in idx]
 
         def cat(parts, dtype):
-            return np.concatenate(parts).astype(dtype, copy=False) if parts else np.zeros(0, dtype)
+            return np.ascontiguousarray(np.concatenate(parts).astype(dtype, copy=False)) if parts else np.zeros(0, dtype)
 
         r_sl = [slice(int(self.read_off[s]), int(self.read_off[s + 1])) for s in idx]
         v_sl = [slice(int(self.sv_off[s]), int(self.sv_off[s + 1])) for s in idx]
@@ -108,12 +131,11 @@ class PhaseBatch:
         pick_list = lambda lst: [x for v in v_sl for x in lst[v]] if lst else []
         return PhaseBatch(
             read_off, sv_off,
-            pick(self.read_key, r_sl, np.uint64), pick(self.read_key_hi, r_sl, np.uint64),
-            pick(self.read_hp, r_sl, np.uint8), pick(self.read_ps, r_sl, np.int32), pick(self.read_pc, r_sl, np.int32),
+            pick(self.read_key, r_sl, np.uint64), pick(self.read_tag, r_sl, TAG_DTYPE),
             pick(self.sv_pos, v_sl, np.int32), pick(self.sv_svlen, v_sl, np.int32),
             pick(self.sv_svread, v_sl, np.int32), pick(self.sv_refread, v_sl, np.int32),
             pick(self.sv_flags, v_sl, np.uint8), pick(self.sv_group, v_sl, np.int32),
-            csr_off, pick(self.csr_key, j_sl, np.uint64), pick(self.csr_key_hi, j_sl, np.uint64),
+            csr_off, pick(self.csr_key, j_sl, np.uint64), pick(self.csr_chk, j_sl, np.uint32),
             [self.shard_sample[s] for s in idx] if self.shard_sample else [],
             [self.shard_contig[s] for s in idx] if self.shard_contig else [],
             pick_list(self.sv_chrom), pick_list(self.sv_type), pick_list(self.sv_ref), pick_list(self.sv_alt))
@@ -126,14 +148,14 @@ def from_synth(samples, *, with_hi: bool = True, with_text: bool = True) -> Phas
     if not isinstance(samples, (list, tuple)):
         samples = [samples]
     read_off, sv_off = [0], [0]
-    cols = {k: [] for k in ("rk", "rh", "hp", "ps", "pc", "pos", "len", "svr", "ref", "flg", "ck", "ch", "cl")}
+    cols = {k: [] for k in ("rk", "rt", "pos", "len", "svr", "ref", "flg", "ck", "ch", "cl")}
     shard_sample, shard_contig, sv_chrom, sv_type, sv_alt = [], [], [], [], []
     for si, sample in enumerate(samples):
         for c in sample.contigs:
             t = c.row_tagged
             lo, hi = hash128_fixed(sy.names_from_ids(c.row_id[t]))
-            cols["rk"].append(lo); cols["rh"].append(hi)
-            cols["hp"].append(c.row_hp[t]); cols["ps"].append(c.row_ps[t]); cols["pc"].append(c.row_pc[t])
+            cols["rk"].append(lo)
+            cols["rt"].append(pack_tags(c.row_hp[t], c.row_ps[t], c.row_pc[t], hi if with_hi else None))
             read_off.append(read_off[-1] + int(t.sum()))
             n = c.sv_pos.shape[0]
             sv_off.append(sv_off[-1] + n)
@@ -141,7 +163,7 @@ def from_synth(samples, *, with_hi: bool = True, with_text: bool = True) -> Phas
             cols["svr"].append(c.sv_svread); cols["ref"].append(c.sv_refread)
             cols["flg"].append((c.sv_gt == sy.GTS.index("./.")).astype(np.uint8) * _lib.SV_GT_MISSING)
             lo, hi = hash128_fixed(sy.names_from_ids(c.sup_id))
-            cols["ck"].append(lo); cols["ch"].append(hi)
+            cols["ck"].append(lo); cols["ch"].append((hi & np.uint64(0xFFFFFFFF)).astype(np.uint32))
             cols["cl"].append(np.diff(c.sup_off))
             shard_sample.append(si); shard_contig.append(c.name)
             if with_text:
@@ -150,16 +172,15 @@ def from_synth(samples, *, with_hi: bool = True, with_text: bool = True) -> Phas
                 types = [sy.SVTYPES[int(x)] for x in c.sv_type]
                 sv_type += types
                 sv_alt += ["<" + x + ">" for x in types]
-    cat = lambda k, dt: (np.concatenate(cols[k]) if cols[k] else np.zeros(0)).astype(dt, copy=False)
+    cat = lambda k, dt: (np.concatenate(cols[k]) if cols[k] else np.zeros(0, dt)).astype(dt, copy=False)
     lens = cat("cl", np.int64)
     csr_off = np.zeros(lens.shape[0] + 1, np.int64)
     csr_off[1:] = np.cumsum(lens)
     b = PhaseBatch(
         np.asarray(read_off, np.int64), np.asarray(sv_off, np.int64),
-        cat("rk", np.uint64), cat("rh", np.uint64) if with_hi else None,
-        cat("hp", np.uint8), cat("ps", np.int32), cat("pc", np.int32),
+        cat("rk", np.uint64), cat("rt", TAG_DTYPE),
         cat("pos", np.int32), cat("len", np.int32), cat("svr", np.int32), cat("ref", np.int32),
-        cat("flg", np.uint8), None, csr_off, cat("ck", np.uint64), cat("ch", np.uint64) if with_hi else None,
+        cat("flg", np.uint8), None, csr_off, cat("ck", np.uint64), cat("ch", np.uint32) if with_hi else None,
         shard_sample, shard_contig, sv_chrom, sv_type, ["N"] * len(sv_chrom), sv_alt)
     b.validate()
     return b

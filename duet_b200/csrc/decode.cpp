@@ -88,9 +88,19 @@ void duet_hash_names(const char *buf, const int64_t *off, int64_t n, uint64_t *l
         hash128(reinterpret_cast<const unsigned char *>(buf) + off[i], (size_t)(off[i + 1] - off[i]), lo + i, hi + i);
 }
 
-int duet_decode_sam_text(const char *text, int64_t len, int64_t cap, uint64_t *key_lo, uint64_t *key_hi,
-                         uint8_t *hp, int32_t *ps, int32_t *pc, int64_t *n_rows, int64_t *n_lines,
-                         int64_t *err_line) {
+void duet_pack_tags(int64_t n, const uint8_t *hp, const int32_t *ps, const int32_t *pc, const uint64_t *hi,
+                    duet_read_tag *out) {
+    for (int64_t i = 0; i < n; ++i) {
+        duet_read_tag t;
+        std::memset(&t, 0, sizeof(t));
+        t.ps = ps[i]; t.pc = pc[i]; t.hp = hp[i];
+        t.chk = hi ? (uint32_t)hi[i] : 0u;
+        out[i] = t;
+    }
+}
+
+int duet_decode_sam_text(const char *text, int64_t len, int64_t cap, uint64_t *key, duet_read_tag *tag,
+                         int64_t *n_rows, int64_t *n_lines, int64_t *err_line) {
     const unsigned char *p = reinterpret_cast<const unsigned char *>(text);
     const unsigned char *end = p + len;
     int64_t rows = 0, line_no = 0;
@@ -133,10 +143,15 @@ int duet_decode_sam_text(const char *text, int64_t len, int64_t cap, uint64_t *k
                 *err_line = line_no; return DUET_DECODE_ERR_RANGE;
             }
             if (rows >= cap) { *err_line = line_no; return DUET_DECODE_ERR_CAPACITY; }
-            hash128(f0b, (size_t)(f0e - f0b), key_lo + rows, key_hi + rows);
-            hp[rows] = (uint8_t)v[0];
-            pc[rows] = (int32_t)v[1];
-            ps[rows] = (int32_t)v[2];
+            uint64_t hi;
+            hash128(f0b, (size_t)(f0e - f0b), key + rows, &hi);
+            duet_read_tag t;
+            std::memset(&t, 0, sizeof(t));
+            t.hp = (uint8_t)v[0];
+            t.pc = (int32_t)v[1];
+            t.ps = (int32_t)v[2];
+            t.chk = (uint32_t)hi;
+            tag[rows] = t;
             ++rows;
         }
         ++line_no;

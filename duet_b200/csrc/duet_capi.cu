@@ -59,15 +59,15 @@ struct duet_handle {
     int group = 16;                 // lanes per SV in k_build / k_reduce
 
     // staged input copies (HOST mode)
-    DevBuf in_read_key, in_read_key_hi, in_read_hp, in_read_ps, in_read_pc;
+    DevBuf in_read_key, in_read_tag;
     DevBuf in_sv_pos, in_sv_svlen, in_sv_svread, in_sv_refread, in_sv_flags, in_sv_group;
-    DevBuf in_csr_off, in_csr_key, in_csr_key_hi;
+    DevBuf in_csr_off, in_csr_key, in_csr_chk;
     // descriptors, table, scratch, outputs
     DevBuf d_read_off, d_sv_off, d_join_off, d_sv_shard, d_tab_off, d_tab_mask, d_done, d_c2;
     DevBuf d_btiles, d_rtiles, d_ptiles;
     size_t probe_smem = 0;
-    DevBuf d_table;                 // Slot[n_slots], all-ones when idle
-    DevBuf d_bitmap, d_bm_off, d_bm_wmask, d_next, d_bmword, d_csr_slot, d_join_row, d_n_hit, d_cand, d_oneps, d_oneps_n, d_sort;
+    DevBuf d_table;                 // Slot[n_slots] followed by the Bloom filter words
+    DevBuf d_bm_off, d_bm_wmask, d_next, d_join_row, d_n_hit, d_cand, d_oneps, d_oneps_n, d_sort;
     DevBuf d_gt, d_cls, d_ps, d_hap1, d_hap2, d_hap0, d_allhap, d_t1, d_t2, d_feat, d_order, d_n_emit;
     DevBuf d_counts, d_status;
     // kernel set B (signature clustering)
@@ -173,10 +173,10 @@ void duet_destroy(duet_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->in_read_key, &h->in_read_key_hi, &h->in_read_hp, &h->in_read_ps, &h->in_read_pc,
+    DevBuf *bufs[] = {&h->in_read_key, &h->in_read_tag,
                       &h->in_sv_pos, &h->in_sv_svlen, &h->in_sv_svread, &h->in_sv_refread, &h->in_sv_flags,
-                      &h->in_sv_group, &h->in_csr_off, &h->in_csr_key, &h->in_csr_key_hi, &h->d_read_off,
-                      &h->d_sv_off, &h->d_join_off, &h->d_c2, &h->d_btiles, &h->d_rtiles, &h->d_ptiles, &h->d_sv_shard, &h->d_done, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_bitmap, &h->d_bm_off, &h->d_bm_wmask, &h->d_next, &h->d_bmword, &h->d_csr_slot,
+                      &h->in_sv_group, &h->in_csr_off, &h->in_csr_key, &h->in_csr_chk, &h->d_read_off,
+                      &h->d_sv_off, &h->d_join_off, &h->d_c2, &h->d_btiles, &h->d_rtiles, &h->d_ptiles, &h->d_sv_shard, &h->d_done, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_bm_off, &h->d_bm_wmask, &h->d_next,
                       &h->d_join_row, &h->d_n_hit, &h->d_cand, &h->d_oneps, &h->d_oneps_n, &h->d_sort, &h->d_gt,
                       &h->d_cls, &h->d_ps, &h->d_hap1, &h->d_hap2, &h->d_hap0, &h->d_allhap, &h->d_t1, &h->d_t2,
                       &h->d_feat, &h->d_order, &h->d_n_emit, &h->d_counts, &h->d_status};
@@ -231,12 +231,12 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         return fail(h, DUET_ERR_INVALID, "duet_phase_upload: sizes out of range");
     if (!in->read_off || !in->sv_off || !in->csr_off)
         return fail(h, DUET_ERR_INVALID, "duet_phase_upload: offset arrays are required");
-    if ((R && (!in->read_key || !in->read_hp || !in->read_ps || !in->read_pc)) ||
+    if ((R && (!in->read_key || !in->read_tag)) ||
         (S && (!in->sv_pos || !in->sv_svlen || !in->sv_svread || !in->sv_refread || !in->sv_flags)) ||
         (J && !in->csr_key))
         return fail(h, DUET_ERR_INVALID, "duet_phase_upload: a required column is NULL");
-    if ((in->read_key_hi == nullptr) != (in->csr_key_hi == nullptr) && R && J)
-        return fail(h, DUET_ERR_INVALID, "duet_phase_upload: read_key_hi and csr_key_hi must both be given or both NULL");
+    if (in->mem == DUET_MEM_DEVICE && (reinterpret_cast<uintptr_t>(in->read_key) & 15u))
+        return fail(h, DUET_ERR_INVALID, "duet_phase_upload: read_key must be 16-byte aligned");
     if (in->read_off[0] != 0 || in->sv_off[0] != 0 || in->read_off[ns] != R || in->sv_off[ns] != S)
         return fail(h, DUET_ERR_INVALID, "duet_phase_upload: shard offsets do not span the columns");
     for (int s = 0; s < ns; ++s)
@@ -259,8 +259,9 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     std::vector<int> tab_off(ns), tab_mask(ns), bm_off(ns), bm_wmask(ns);
     std::vector<long long> join_off(ns + 1);
     for (int s = 0; s <= ns; ++s) join_off[s] = csr[in->sv_off[s]];
-    // slot table: load factor <= 1/2 (32-byte slots; only occupied sectors are ever touched by hits).
-    // Bloom filter: 16 bits per name, at most 128 KB per shard (it has to fit in shared memory).
+    // slot table: 16-byte slots, load factor <= 1/2.  Bloom filter: 16 bits per name, at most 128 KB
+    // per shard (it has to fit in shared memory).  Both are (re)initialised by one sequential memset
+    // at the start of every call, which also makes them L2 resident for the random traffic that follows.
     const long long fill = 2;
     long long slots = 0, max_sv = 0, bm_words = 0;
     for (int s = 0; s < ns; ++s) {
@@ -291,10 +292,7 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     if ((rc = stage(h, h->buf, in->field, sizeof(T) * (size_t)(count), mem,                          \
                     reinterpret_cast<const void **>(&a.field))) != DUET_OK) return rc;
     STAGE(in_read_key, read_key, uint64_t, R)
-    STAGE(in_read_key_hi, read_key_hi, uint64_t, R)
-    STAGE(in_read_hp, read_hp, uint8_t, R)
-    STAGE(in_read_ps, read_ps, int32_t, R)
-    STAGE(in_read_pc, read_pc, int32_t, R)
+    STAGE(in_read_tag, read_tag, duet_read_tag, R)
     STAGE(in_sv_pos, sv_pos, int32_t, S)
     STAGE(in_sv_svlen, sv_svlen, int32_t, S)
     STAGE(in_sv_svread, sv_svread, int32_t, S)
@@ -303,7 +301,7 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     STAGE(in_sv_group, sv_group, int32_t, S)
     STAGE(in_csr_off, csr_off, int64_t, S + 1)
     STAGE(in_csr_key, csr_key, uint64_t, J)
-    STAGE(in_csr_key_hi, csr_key_hi, uint64_t, J)
+    STAGE(in_csr_chk, csr_chk, uint32_t, J)
 #undef STAGE
     // descriptors are host arrays in both modes
     const void *dv;
@@ -357,11 +355,10 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     h->have_h2d = true;
 
     const size_t S1 = (size_t)std::max<long long>(S, 1), J1 = (size_t)std::max<long long>(J, 1);
-    CU(h, h->d_table.reserve((size_t)slots * sizeof(Slot)));  a.tab = h->d_table.as<Slot>();
-    CU(h, h->d_bitmap.reserve((size_t)bm_words * 4));    a.bitmap = h->d_bitmap.as<unsigned>();
+    CU(h, h->d_table.reserve((size_t)slots * sizeof(Slot) + (size_t)bm_words * 4));
+    a.tab = h->d_table.as<Slot>();
+    a.bitmap = reinterpret_cast<unsigned *>(a.tab + slots);
     CU(h, h->d_next.reserve(J1 * 4));                    a.next = h->d_next.as<int>();
-    CU(h, h->d_bmword.reserve(J1 * 4));                  a.csr_bmword = h->d_bmword.as<int>();
-    CU(h, h->d_csr_slot.reserve(J1 * 4));                a.csr_slot = h->d_csr_slot.as<int>();
     CU(h, h->d_join_row.reserve(J1 * 4));                a.join_row = h->d_join_row.as<int>();
     CU(h, h->d_n_hit.reserve(S1 * 4));                   a.n_hit = h->d_n_hit.as<int>();
     CU(h, h->d_cand.reserve(S1 * 8));                    a.cand = h->d_cand.as<long long>();
@@ -391,9 +388,7 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     CU(h, h->d_n_emit.reserve((size_t)ns * 4));          a.n_emit = h->d_n_emit.as<int>();
     CU(h, h->d_counts.reserve((size_t)ns * 8 * DUET_N_COUNTERS)); a.shard_counts = h->d_counts.as<long long>();
     CU(h, h->d_status.reserve(sizeof(DevStatus)));       a.status = h->d_status.as<DevStatus>();
-    // state the kernels keep clean between calls: EMPTY table, zero counters / credits / status
-    CU(h, cudaMemsetAsync(h->d_table.p, 0xFF, (size_t)slots * sizeof(Slot), st));
-    CU(h, cudaMemsetAsync(h->d_bitmap.p, 0, (size_t)bm_words * 4, st));
+    // state the kernels keep clean between calls: zero counters / credits / status
     CU(h, cudaMemsetAsync(h->d_join_row.p, 0xFF, J1 * 4, st));
     CU(h, cudaMemsetAsync(h->d_done.p, 0, (size_t)ns * 8, st));
     CU(h, cudaMemsetAsync(h->d_oneps_n.p, 0, (size_t)ns * 4, st));
@@ -420,6 +415,9 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
     CU(h, cudaEventRecord(h->ev[EV_X0], st));
     const int S = a.n_svs;
     if (a.n_joins) {
+        // EMPTY slots (all ones) and a zero filter, written sequentially: also pulls both into L2
+        CU(h, cudaMemsetAsync(a.tab, 0xFF, (size_t)h->n_slots * sizeof(Slot), st));
+        CU(h, cudaMemsetAsync(a.bitmap, 0, (size_t)h->n_bm_words * 4, st));
         k_build<<<(a.n_joins + kThreads - 1) / kThreads, kThreads, 0, st>>>(a);
         ++h->launches;
     }

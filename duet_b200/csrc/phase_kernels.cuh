@@ -36,14 +36,15 @@ constexpr int kPredictPerBlock = 64;
 constexpr int kSortSmemBytes = 16384;                 // slow-path sort tile in shared memory
 constexpr int kBloomMaxWords = 32768;                 // 128 KB of shared memory per shard filter
 
-// One slot of the join table = one 32-byte sector: everything a probe needs arrives together.
-struct __align__(32) Slot {
+// One slot of the join table: 16 bytes, loaded in one request.
+struct __align__(16) Slot {
     unsigned long long key;   // low 64 bits of the name hash, kEmptyKey when free
-    unsigned long long hi;    // high 64 bits (collision check)
     int first;                // the support-read entry that claimed the slot
     int head;                 // further entries carrying the same name (chain through `next`), -1 none
-    int pad[2];
 };
+
+// include/duet_b200.h :: duet_read_tag as the device reads it (one 16-byte load)
+struct __align__(16) ReadTag { int ps, pc; unsigned chk, hp; };       // hp: low byte
 
 // host-built descriptors: what a block needs to know about its tile, in one 32- / 16-byte load
 struct BuildTile { int lo, hi, base, mask, bmo, bmw, pad[2]; };   // shards of 256 consecutive support reads
@@ -71,25 +72,23 @@ struct PhaseArgs {
     const BuildTile *build_tiles;   // [ceil(J / 256)]
     const SvTile *reduce_tiles;     // [ceil(S / kReducePerBlock)]
     const SvTile *predict_tiles;    // [ceil(S / kPredictPerBlock)]
-    const unsigned long long *read_key, *read_key_hi;
-    const uint8_t *read_hp;
-    const int *read_ps, *read_pc;
+    const unsigned long long *read_key;
+    const ReadTag *read_tag;
     const int *sv_pos, *sv_svlen, *sv_svread, *sv_refread;
     const uint8_t *sv_flags;
     const int *sv_group;
     const long long *csr_off;
-    const unsigned long long *csr_key, *csr_key_hi;
+    const unsigned long long *csr_key;
+    const unsigned *csr_chk;
     // join table: shard s owns slots [tab_off[s], tab_off[s] + tab_mask[s] + 1)
     const int *tab_off;          // [n_shards]
     const int *tab_mask;         // [n_shards]
-    Slot *tab;                   // [n_slots] all-ones between calls (k_predict clears what k_build set)
-    int *csr_slot;               // [J] slot of each support-read name
+    Slot *tab;                   // [n_slots] set to all-ones at the start of every call
     int *next;                   // [J] next entry carrying the same name, -1 none
-    int *csr_bmword;             // [J] filter word of each support-read name
     // per-shard Bloom filter over the support-read names: words [bm_off[s], bm_off[s] + bm_wmask[s] + 1)
     const int *bm_off;           // [n_shards]
     const int *bm_wmask;         // [n_shards] (power of two) - 1
-    unsigned *bitmap;            // zero between calls (k_predict clears what k_build set)
+    unsigned *bitmap;            // zeroed at the start of every call
     // per-SV intermediates / outputs (device)
     int *join_row;               // [J] row each support read joined to (atomicMax by k_probe), -1 = miss
     int *n_hit;                  // [S] joined reads of the SV
@@ -248,7 +247,6 @@ k_build(PhaseArgs a) {
     const long long j = (long long)blockIdx.x * kThreads + threadIdx.x;
     const bool live = j < a.n_joins;
     const unsigned long long key = live ? __ldcs(a.csr_key + j) : 0ull;
-    const unsigned long long khi = live && a.csr_key_hi ? __ldcs(a.csr_key_hi + j) : 0ull;
     const BuildTile t = a.build_tiles[blockIdx.x];
     if (!live) return;
     int base = t.base, bmo = t.bmo;
@@ -259,9 +257,7 @@ k_build(PhaseArgs a) {
         bmo = __ldg(a.bm_off + s); bmw = (unsigned)__ldg(a.bm_wmask + s);
     }
     a.join_row[j] = -1;
-    const int word = bmo + (int)bloom_word(key, bmw);
-    atomicOr(a.bitmap + word, bloom_bits(key));
-    a.csr_bmword[j] = word;
+    atomicOr(a.bitmap + bmo + (int)bloom_word(key, bmw), bloom_bits(key));
     unsigned p = slot_hash(key) & mask;
     bool won;
     for (;;) {
@@ -271,9 +267,7 @@ k_build(PhaseArgs a) {
         p = (p + 1) & mask;
     }
     Slot *sl = a.tab + base + p;
-    a.csr_slot[j] = base + (int)p;
     if (won) {
-        sl->hi = khi;
         sl->first = (int)j;
     } else {
         a.next[j] = atomicExch(&sl->head, (int)j);
@@ -297,18 +291,15 @@ constexpr int kProbeBatch = kProbeThreads * kProbeUnroll;        // pairs per bl
 __device__ __forceinline__ void probe_candidate(const PhaseArgs &a, unsigned long long key, int row, int base,
                                                 unsigned mask) {
     unsigned p = slot_hash(key) & mask;
-    const unsigned long long rhi = a.read_key_hi ? __ldg(a.read_key_hi + row) : 0ull;     // in flight with the slot
     for (;;) {
-        const Slot *sl = a.tab + base + p;
-        const ulonglong2 kh = *reinterpret_cast<const ulonglong2 *>(sl);                 // key, hi
-        const int2 fh = *reinterpret_cast<const int2 *>(&sl->first);                     // first, head: same sector
-        if (kh.x == key) {
-            if (a.read_key_hi && kh.y != rhi) report(a.status, DUET_ERR_HASH_COLLISION, -1, (long long)key);
-            atomicMax(a.join_row + fh.x, row);
-            for (int h = fh.y; h >= 0; h = a.next[h]) atomicMax(a.join_row + h, row);
+        const uint4 sl = *reinterpret_cast<const uint4 *>(a.tab + base + p);          // key, first, head
+        const unsigned long long k = ((unsigned long long)sl.y << 32) | sl.x;
+        if (k == key) {
+            atomicMax(a.join_row + (int)sl.z, row);
+            for (int h = (int)sl.w; h >= 0; h = a.next[h]) atomicMax(a.join_row + h, row);
             return;
         }
-        if (kh.x == kEmptyKey) return;
+        if (k == kEmptyKey) return;
         p = (p + 1) & mask;
     }
 }
@@ -521,6 +512,11 @@ __device__ __forceinline__ void oneps_any(const PhaseArgs &a, int s, long long *
 // ------------------------------------------------------------------------------------------
 constexpr int kReduceUnroll = 4;
 
+__device__ __forceinline__ ReadTag load_tag(const PhaseArgs &a, int row) {
+    const int4 v = __ldg(reinterpret_cast<const int4 *>(a.read_tag + row));
+    return ReadTag{v.x, v.y, (unsigned)v.z, (unsigned)v.w};
+}
+
 struct C2Group {                                   // shared-memory table of one lane group
     int ps[kC2Max], tot[kC2Max], n1[kC2Max], n2[kC2Max], bad[kC2Max];
     unsigned long long s1[kC2Max], s2[kC2Max];
@@ -584,15 +580,22 @@ k_reduce(PhaseArgs a) {
     int first_q_ps = 0;
     int row[kReduceUnroll], ps[kReduceUnroll], pc[kReduceUnroll], hp[kReduceUnroll];
     for (long long base = b; base < e; base += G * kReduceUnroll) {
+        unsigned want[kReduceUnroll];
 #pragma unroll
         for (int u = 0; u < kReduceUnroll; ++u) {
             const long long j = base + u * G + lane;
             row[u] = j < e ? a.join_row[j] : -1;
+            want[u] = j < e && a.csr_chk ? __ldg(a.csr_chk + j) : 0u;
         }
 #pragma unroll
         for (int u = 0; u < kReduceUnroll; ++u) {
             ps[u] = pc[u] = hp[u] = 0;
-            if (row[u] >= 0) { ps[u] = __ldg(a.read_ps + row[u]); pc[u] = __ldg(a.read_pc + row[u]); hp[u] = __ldg(a.read_hp + row[u]); }
+            if (row[u] >= 0) {                                   // one 16-byte record = one sector per joined read
+                const ReadTag t = load_tag(a, row[u]);
+                ps[u] = t.ps; pc[u] = t.pc; hp[u] = (int)(t.hp & 0xffu);
+                if (a.csr_chk && t.chk != want[u])               // two different names share the 64-bit key
+                    report(a.status, DUET_ERR_HASH_COLLISION, sv, (long long)__ldg(a.csr_key + base + u * G + lane));
+            }
         }
 #pragma unroll
         for (int u = 0; u < kReduceUnroll; ++u) {
@@ -643,7 +646,7 @@ k_reduce(PhaseArgs a) {
                 const long long j = base + lane;
                 const int r = j < e ? a.join_row[j] : -1;
                 int xps = 0, xpc = 0, xhp = 0;
-                if (r >= 0) { xps = __ldg(a.read_ps + r); xpc = __ldg(a.read_pc + r); xhp = __ldg(a.read_hp + r); }
+                if (r >= 0) { const ReadTag t = load_tag(a, r); xps = t.ps; xpc = t.pc; xhp = (int)(t.hp & 0xffu); }
                 c2_update(g, gmask, r >= 0 && xpc <= c_thr.pc_max, xps, xpc, xhp, n_d);
             }
         }
@@ -715,11 +718,12 @@ __device__ __forceinline__ Entry load_entry(const PhaseArgs &a, long long j, lon
     if (j < e) {
         const int row = a.join_row[j];
         if (row >= 0) {
-            r.pc = __ldg(a.read_pc + row);
+            const ReadTag t = load_tag(a, row);
+            r.pc = t.pc;
             if (r.pc <= c_thr.pc_max) {
                 r.q = true;
-                r.ps = __ldg(a.read_ps + row);
-                r.hp = __ldg(a.read_hp + row);
+                r.ps = t.ps;
+                r.hp = (int)(t.hp & 0xffu);
                 r.in = in_sorted(oneps, n_one, r.ps);
             }
         }
@@ -784,7 +788,8 @@ __device__ void class2_stats(const PhaseArgs &a, int sv, long long b, long long 
         if (j < e) {
             const int row = a.join_row[j];
             if (row >= 0) {
-                pc = __ldg(a.read_pc + row); ps = __ldg(a.read_ps + row); hp = __ldg(a.read_hp + row);
+                const ReadTag t = load_tag(a, row);
+                pc = t.pc; ps = t.ps; hp = (int)(t.hp & 0xffu);
                 q = pc <= c_thr.pc_max;
             }
         }
@@ -987,7 +992,6 @@ __device__ void order_block(const PhaseArgs &a, int s, long long *smem_tile) {
 //     on chip); class-2 SVs read the per-PS statistics k_reduce recorded and keep the first-seen
 //     in-set phase set with the most reads (:99-105); then features and the T1-T5 tree;
 //   * SVs whose reads span more than kC2Max phase sets fall back to a warp-cooperative exact path;
-//   * the join table slots and filter bits set by k_build are handed back clean;
 //   * every SV credits its shard; the block completing a shard writes its emission order + counters.
 // Dependent chain: [tile, per-SV state] -> [oneps_n, staged list, class-2 record] -> decide -> stores.
 // ------------------------------------------------------------------------------------------
@@ -1073,17 +1077,6 @@ k_predict(PhaseArgs a) {
         Class2Stats t{0, 0, 0, a.allhap[sv2], 0, 0, 0};
         class2_stats(a, sv2, b2, e2, o2, n2, s_c2[w], t);
         if (lane == 0) decide_and_store(a, sv2, 2, t, o2, n2, (int)(e2 - b2));
-    }
-
-    // the table is not read after k_probe: hand it back clean
-    for (long long j = (long long)blockIdx.x * kThreads + threadIdx.x; j < a.n_joins; j += (long long)gridDim.x * kThreads) {
-        const int slot = a.csr_slot[j];
-        const int word = a.csr_bmword[j];
-        if (a.csr_key_hi && a.tab[slot].hi != __ldg(a.csr_key_hi + j))      // two names, one 64-bit key
-            report(a.status, DUET_ERR_HASH_COLLISION, -1, (long long)__ldg(a.csr_key + j));
-        a.tab[slot].key = kEmptyKey;
-        a.tab[slot].head = -1;
-        a.bitmap[word] = 0u;
     }
 
     __threadfence();

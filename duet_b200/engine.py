@@ -107,9 +107,7 @@ class PhaseEngine:
         inp = _lib.PhaseInput()
         inp.mem = _lib.MEM_HOST
         inp.n_shards, inp.n_reads, inp.n_svs, inp.n_joins = batch.n_shards, batch.n_reads, batch.n_svs, batch.n_joins
-        for name in ("read_off", "sv_off", "read_key", "read_key_hi", "read_hp", "read_ps", "read_pc", "sv_pos",
-                     "sv_svlen", "sv_svread", "sv_refread", "sv_flags", "sv_group", "csr_off", "csr_key",
-                     "csr_key_hi"):
+        for name in _lib.INPUT_COLUMNS:
             arr = getattr(batch, name)
             if arr is not None and not arr.flags["C_CONTIGUOUS"]:
                 raise ValueError(f"{name} must be C-contiguous")
@@ -187,8 +185,7 @@ def pinned_empty(shape, dtype) -> np.ndarray:
     return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
 
 
-_COLUMNS = ("read_off", "sv_off", "read_key", "read_key_hi", "read_hp", "read_ps", "read_pc", "sv_pos", "sv_svlen",
-            "sv_svread", "sv_refread", "sv_flags", "sv_group", "csr_off", "csr_key", "csr_key_hi")
+_COLUMNS = _lib.INPUT_COLUMNS
 
 
 def pin_batch(batch: PhaseBatch) -> PhaseBatch:

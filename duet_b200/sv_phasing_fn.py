@@ -23,7 +23,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from .columnar import PhaseBatch
+from .columnar import TAG_DTYPE, PhaseBatch
 from .engine import DuetError, PhaseEngine
 from .read_file import ContigSvs, init_chrom_list, parse_vcf
 
@@ -43,20 +43,28 @@ def get_engine(device: int | None = None) -> PhaseEngine:
 @dataclass
 class ReadColumns:
     """Kept rows of one per-contig haplotagged BAM, file order (sv_phasing_fn.py:26-29)."""
-    key: np.ndarray
-    key_hi: np.ndarray
-    hp: np.ndarray
-    ps: np.ndarray
-    pc: np.ndarray
+    key: np.ndarray          # uint64 low hash word
+    tag: np.ndarray          # TAG_DTYPE: HP / PS / PC + check word
     n_lines: int = 0
+
+    @property
+    def hp(self):
+        return self.tag["hp"]
+
+    @property
+    def ps(self):
+        return self.tag["ps"]
+
+    @property
+    def pc(self):
+        return self.tag["pc"]
 
     def __len__(self):
         return int(self.key.shape[0])
 
     @staticmethod
     def empty():
-        return ReadColumns(np.zeros(0, np.uint64), np.zeros(0, np.uint64), np.zeros(0, np.uint8),
-                           np.zeros(0, np.int32), np.zeros(0, np.int32))
+        return ReadColumns(np.zeros(0, np.uint64), np.zeros(0, TAG_DTYPE))
 
 
 _DECODE_EXC = {
@@ -74,18 +82,17 @@ def decode_sam_text(text: bytes) -> ReadColumns:
     buf = (C.c_char * max(n, 1)).from_buffer_copy(text) if not isinstance(text, (bytearray, memoryview)) else \
         (C.c_char * max(n, 1)).from_buffer(text)
     cap = int(lib.duet_count_lines(buf, n))
-    key, key_hi = np.empty(cap, np.uint64), np.empty(cap, np.uint64)
-    hp, ps, pc = np.empty(cap, np.uint8), np.empty(cap, np.int32), np.empty(cap, np.int32)
+    key, tag = np.empty(cap, np.uint64), np.empty(cap, TAG_DTYPE)
     n_rows, n_lines, err_line = C.c_int64(), C.c_int64(), C.c_int64()
-    rc = lib.duet_decode_sam_text(buf, n, cap, key.ctypes.data, key_hi.ctypes.data, hp.ctypes.data, ps.ctypes.data,
-                                  pc.ctypes.data, C.byref(n_rows), C.byref(n_lines), C.byref(err_line))
+    rc = lib.duet_decode_sam_text(buf, n, cap, key.ctypes.data, tag.ctypes.data, C.byref(n_rows), C.byref(n_lines),
+                                  C.byref(err_line))
     if rc != _lib.DUET_OK:
         exc, msg = _DECODE_EXC.get(rc, (RuntimeError, f"decode error {rc}"))
         if exc is UnicodeDecodeError:
             raise UnicodeDecodeError("ascii", bytes(text[:1]), 0, 1, f"ordinal not in range(128) (line {err_line.value})")
         raise exc(f"{msg} (alignment line {err_line.value})")
     k = n_rows.value
-    return ReadColumns(key[:k].copy(), key_hi[:k].copy(), hp[:k].copy(), ps[:k].copy(), pc[:k].copy(), n_lines.value)
+    return ReadColumns(key[:k].copy(), tag[:k].copy(), n_lines.value)
 
 
 def _sam_text(path: str, thread: int) -> bytes:
@@ -148,7 +155,7 @@ def build_batch(chrom_list, read_hap: list[ReadColumns], comp_call: list[ContigS
     sv_off = np.zeros(ns + 1, np.int64)
     read_off[1:] = np.cumsum([len(r) for r in read_hap])
     sv_off[1:] = np.cumsum([len(c) for c in comp_call])
-    cat = lambda parts, dt: (np.concatenate(parts) if parts else np.zeros(0)).astype(dt, copy=False)
+    cat = lambda parts, dt: (np.concatenate(parts) if parts else np.zeros(0, dt)).astype(dt, copy=False)
     chrom, svtype, ref, alt, pos, svlen, svread, refread, flags, group, lists = [], [], [], [], [], [], [], [], [], [], []
     any_group = False
     for cs in comp_call:
@@ -164,12 +171,11 @@ def build_batch(chrom_list, read_hap: list[ReadColumns], comp_call: list[ContigS
     np.cumsum(lens, out=csr_off[1:])
     b = PhaseBatch(
         read_off, sv_off,
-        cat([r.key for r in read_hap], np.uint64), cat([r.key_hi for r in read_hap], np.uint64),
-        cat([r.hp for r in read_hap], np.uint8), cat([r.ps for r in read_hap], np.int32),
-        cat([r.pc for r in read_hap], np.int32),
+        cat([r.key for r in read_hap], np.uint64), cat([r.tag for r in read_hap], TAG_DTYPE),
         np.asarray(pos, np.int32), np.asarray(svlen, np.int32), np.asarray(svread, np.int32),
         np.asarray(refread, np.int32), np.asarray(flags, np.uint8),
-        np.asarray(group, np.int32) if any_group else None, csr_off, ck, ch,
+        np.asarray(group, np.int32) if any_group else None, csr_off, ck,
+        (ch & np.uint64(0xFFFFFFFF)).astype(np.uint32),
         [sample] * ns, list(chrom_list), chrom, svtype, ref, alt)
     b.validate()
     return b

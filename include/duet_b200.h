@@ -75,6 +75,18 @@ typedef struct duet_thresholds {
     double c1_totsc_ratio_max;  /* 9.72   :177                                          */
 } duet_thresholds;
 
+/* Tags of one haplotagged read, one 16-byte record = half a DRAM sector: a joined read costs the
+ * device exactly one random access.  `chk` is the low 32 bits of the HIGH word of the read-name hash
+ * (the join key is the low word): a joined pair whose checks differ is two different names sharing a
+ * 64-bit key and aborts the call (DUET_ERR_HASH_COLLISION). */
+typedef struct duet_read_tag {
+    int32_t ps;       /* PS:i  (sv_phasing_fn.py:29 int(s[-1][5:]))  */
+    int32_t pc;       /* PC:i  (int(s[-2][5:]))                      */
+    uint32_t chk;     /* name-hash check word                        */
+    uint8_t hp;       /* HP:i  (int(s[-3][5:]))                      */
+    uint8_t _pad[3];
+} duet_read_tag;
+
 /* Columnar input of one call: any number of shards, laid out back to back.
  *
  * Reads of shard s are rows [read_off[s], read_off[s+1]) IN FILE ORDER (a later row with the
@@ -85,7 +97,7 @@ typedef struct duet_thresholds {
  * read_off / sv_off are ALWAYS host pointers (tiny descriptors).  Every other array lives
  * where `mem` says: DUET_MEM_HOST (pageable or pinned; duet_phase_upload copies it) or
  * DUET_MEM_DEVICE (used in place, must stay valid and unchanged until the next upload).
- * `*_key_hi` may both be NULL: then 64-bit key equality is trusted (no collision check).
+ * `csr_chk` may be NULL: then 64-bit key equality is trusted (no collision check).
  * `sv_group` may be NULL (= all zero).
  */
 typedef struct duet_phase_input {
@@ -96,11 +108,8 @@ typedef struct duet_phase_input {
     int64_t n_joins;             /* J < 2^30                                                     */
     const int64_t *read_off;     /* [n_shards+1] host                                            */
     const int64_t *sv_off;       /* [n_shards+1] host                                            */
-    const uint64_t *read_key;    /* [R] low 64 bits of the name hash, never 0xFFFF...F           */
-    const uint64_t *read_key_hi; /* [R] or NULL                                                  */
-    const uint8_t *read_hp;      /* [R] HP tag                                                   */
-    const int32_t *read_ps;      /* [R] PS tag                                                   */
-    const int32_t *read_pc;      /* [R] PC tag                                                   */
+    const uint64_t *read_key;    /* [R] low 64 bits of the name hash, never 0xFFFF...F; 16-byte aligned */
+    const duet_read_tag *read_tag; /* [R] HP / PS / PC + check word                              */
     const int32_t *sv_pos;       /* [S]                                                          */
     const int32_t *sv_svlen;     /* [S] |SVLEN| (sv_phasing_fn.py:62)                            */
     const int32_t *sv_svread;    /* [S] SUPPORT / RE / SR value (read_file.py:40-47)             */
@@ -109,7 +118,7 @@ typedef struct duet_phase_input {
     const int32_t *sv_group;     /* [S] or NULL: rank of the SV's CHROM string inside its shard  */
     const int64_t *csr_off;      /* [S+1]                                                        */
     const uint64_t *csr_key;     /* [J]                                                          */
-    const uint64_t *csr_key_hi;  /* [J] or NULL                                                  */
+    const uint32_t *csr_chk;     /* [J] check word of each support-read name, or NULL            */
 } duet_phase_input;
 
 #define DUET_N_FEATURES 6        /* hapread_ratio, sv_ratio, hap1_avgsc, hap2_avgsc, totsc_ratio,
@@ -212,15 +221,19 @@ enum {
     DUET_DECODE_ERR_CAPACITY = 24  /* output arrays too small                                           */
 };
 
-/* 128-bit name hash (duet_b200/namehash.py): name i is buf[off[i] .. off[i+1]). */
+/* 128-bit name hash (duet_b200/namehash.py): name i is buf[off[i] .. off[i+1]).  key = lo,
+ * check word = (uint32_t)hi. */
 void duet_hash_names(const char *buf, const int64_t *off, int64_t n, uint64_t *lo, uint64_t *hi);
+
+/* Separate HP / PS / PC (+ hash high words, may be NULL -> chk 0) columns -> tag records. */
+void duet_pack_tags(int64_t n, const uint8_t *hp, const int32_t *ps, const int32_t *pc, const uint64_t *hi,
+                    duet_read_tag *out);
 
 /* `samtools view` text of one haplotagged BAM -> columns of the kept rows, in file order
  * (sv_phasing_fn.py:25-29).  Output arrays hold `cap` rows (duet_count_lines(text) is enough).
  * On error returns a DUET_DECODE_ERR_* code and the 0-based line number in *err_line. */
-int duet_decode_sam_text(const char *text, int64_t len, int64_t cap, uint64_t *key_lo, uint64_t *key_hi,
-                         uint8_t *hp, int32_t *ps, int32_t *pc, int64_t *n_rows, int64_t *n_lines,
-                         int64_t *err_line);
+int duet_decode_sam_text(const char *text, int64_t len, int64_t cap, uint64_t *key, duet_read_tag *tag,
+                         int64_t *n_rows, int64_t *n_lines, int64_t *err_line);
 int64_t duet_count_lines(const char *text, int64_t len);
 int duet_get_timings(duet_handle *h, duet_timings *t);
 /* Number of kernels this library launched on the handle since creation (bench "gpu_launches"). */

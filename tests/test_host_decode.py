@@ -31,7 +31,9 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     # sizes the C side was compiled with (LP64): catches a drifted ctypes mirror
     assert C.sizeof(_lib.Thresholds) == 8 * 4 + 10 * 8
-    assert C.sizeof(_lib.PhaseInput) == 8 + 3 * 8 + 16 * 8
+    assert C.sizeof(_lib.PhaseInput) == 8 + 3 * 8 + 13 * 8
+    from duet_b200.columnar import TAG_DTYPE
+    assert TAG_DTYPE.itemsize == 16 and TAG_DTYPE.fields['chk'][1] == 8 and TAG_DTYPE.fields['hp'][1] == 12
     assert C.sizeof(_lib.PhaseOutput) == 13 * 8 + 8
     assert C.sizeof(_lib.Timings) == 3 * 4 + 8 * 4
 
@@ -96,8 +98,8 @@ def test_text_path_equals_direct_columnar(tmp_path):
     b = from_synth(s)
     shard = {c: i for i, c in enumerate(a.shard_contig)}
     a = a.select_shards([shard[c] for c in b.shard_contig])      # 24 reference contigs -> the 3 that have data
-    for k in ("read_off", "sv_off", "read_key", "read_key_hi", "read_hp", "read_ps", "read_pc", "sv_pos", "sv_svlen",
-              "sv_svread", "sv_refread", "sv_flags", "csr_off", "csr_key", "csr_key_hi"):
+    for k in ("read_off", "sv_off", "read_key", "read_tag", "read_hp", "read_ps", "read_pc", "sv_pos", "sv_svlen",
+              "sv_svread", "sv_refread", "sv_flags", "csr_off", "csr_key", "csr_chk"):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
     assert (a.sv_chrom, a.sv_type, a.sv_alt) == (b.sv_chrom, b.sv_type, b.sv_alt)
 

@@ -4,7 +4,7 @@ from __future__ import annotations
 import numpy as np
 
 from duet_b200 import _lib
-from duet_b200.columnar import PhaseBatch
+from duet_b200.columnar import PhaseBatch, pack_tags
 from duet_b200.namehash import hash_names
 
 
@@ -42,10 +42,11 @@ class BatchBuilder:
         csr_off = np.zeros(len(self.lists) + 1, np.int64)
         csr_off[1:] = np.cumsum([len(l) for l in self.lists])
         i32 = lambda x: np.asarray(x, np.int32).reshape(-1)
+        tags = pack_tags(np.asarray(self.hp, np.uint8).reshape(-1), i32(self.ps), i32(self.pc), rh if with_hi else None)
         b = PhaseBatch(np.asarray(self.read_off, np.int64), np.asarray(self.sv_off, np.int64),
-                       rk, rh if with_hi else None, np.asarray(self.hp, np.uint8).reshape(-1), i32(self.ps),
-                       i32(self.pc), i32(self.pos), i32(self.svlen), i32(self.svread), i32(self.refread),
-                       np.asarray(self.flags, np.uint8).reshape(-1), None, csr_off, ck, ch if with_hi else None,
+                       rk, tags, i32(self.pos), i32(self.svlen), i32(self.svread), i32(self.refread),
+                       np.asarray(self.flags, np.uint8).reshape(-1), None, csr_off, ck,
+                       (ch & np.uint64(0xFFFFFFFF)).astype(np.uint32) if with_hi else None,
                        [0] * len(self.contig), list(self.contig), list(self.chrom), list(self.svtype),
                        ["N"] * len(self.chrom), ["<" + t + ">" for t in self.svtype])
         b.validate()
