@@ -64,7 +64,8 @@ struct duet_handle {
     DevBuf in_csr_off, in_csr_key, in_csr_chk;
     // descriptors, table, scratch, outputs
     DevBuf d_read_off, d_sv_off, d_join_off, d_sv_shard, d_tab_off, d_tab_mask, d_done, d_c2;
-    DevBuf d_btiles, d_rtiles, d_ptiles;
+    DevBuf d_btiles, d_rtiles, d_ptiles, d_dbg;
+    bool dbg_on = false;
     size_t probe_smem = 0;
     DevBuf d_table;                 // Slot[n_slots] followed by the Bloom filter words
     DevBuf d_bm_off, d_bm_wmask, d_next, d_join_row, d_n_hit, d_cand, d_oneps, d_oneps_n, d_sort;
@@ -176,7 +177,7 @@ void duet_destroy(duet_handle *h) {
     DevBuf *bufs[] = {&h->in_read_key, &h->in_read_tag,
                       &h->in_sv_pos, &h->in_sv_svlen, &h->in_sv_svread, &h->in_sv_refread, &h->in_sv_flags,
                       &h->in_sv_group, &h->in_csr_off, &h->in_csr_key, &h->in_csr_chk, &h->d_read_off,
-                      &h->d_sv_off, &h->d_join_off, &h->d_c2, &h->d_btiles, &h->d_rtiles, &h->d_ptiles, &h->d_sv_shard, &h->d_done, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_bm_off, &h->d_bm_wmask, &h->d_next,
+                      &h->d_sv_off, &h->d_join_off, &h->d_c2, &h->d_btiles, &h->d_rtiles, &h->d_ptiles, &h->d_dbg, &h->d_sv_shard, &h->d_done, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_bm_off, &h->d_bm_wmask, &h->d_next,
                       &h->d_join_row, &h->d_n_hit, &h->d_cand, &h->d_oneps, &h->d_oneps_n, &h->d_sort, &h->d_gt,
                       &h->d_cls, &h->d_ps, &h->d_hap1, &h->d_hap2, &h->d_hap0, &h->d_allhap, &h->d_t1, &h->d_t2,
                       &h->d_feat, &h->d_order, &h->d_n_emit, &h->d_counts, &h->d_status};
@@ -396,6 +397,10 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     CU(h, cudaMemsetAsync(h->d_counts.p, 0, (size_t)ns * 8 * DUET_N_COUNTERS, st));
     CU(h, cudaMemsetAsync(h->d_status.p, 0, sizeof(DevStatus), st));
     CU(h, cudaStreamSynchronize(st));          // tab_off / tab_mask host vectors go out of scope
+    if (h->dbg_on) {
+        CU(h, h->d_dbg.reserve((size_t)4 * kDbgBlocks * kDbgMarks * 2 * 8));
+        a.dbg = h->d_dbg.as<long long>();
+    }
     h->staged = true;
     return DUET_OK;
 }
@@ -531,6 +536,19 @@ int duet_get_timings(duet_handle *h, duet_timings *t) {
 }
 
 int64_t duet_launch_count(const duet_handle *h) { return h ? h->launches : 0; }
+
+int duet_debug_timers(duet_handle *h, int enable, int64_t *out) {
+    if (!h) return DUET_ERR_INVALID;
+    const size_t bytes = (size_t)4 * kDbgBlocks * kDbgMarks * 2 * 8;
+    if (out && h->dbg_on && h->d_dbg.p) {
+        CU(h, cudaSetDevice(h->device));
+        CU(h, cudaStreamSynchronize(h->stream));
+        CU(h, cudaMemcpy(out, h->d_dbg.p, bytes, cudaMemcpyDeviceToHost));
+        CU(h, cudaMemset(h->d_dbg.p, 0, bytes));
+    }
+    h->dbg_on = enable != 0;          // takes effect at the next duet_phase_upload
+    return DUET_OK;
+}
 
 // ---- kernel set B: signature clustering -----------------------------------------------------------
 

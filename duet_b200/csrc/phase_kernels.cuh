@@ -108,7 +108,20 @@ struct PhaseArgs {
     int *n_emit;                 // [n_shards]
     long long *shard_counts;     // [n_shards][8]
     DevStatus *status;
+    long long *dbg;              // optional per-block timestamps (duet_debug_timers), NULL in production
 };
+
+// ---- optional instrumentation: thread 0 of every block stamps (globaltimer, clock64) at mark k ----
+constexpr int kDbgBlocks = 2048, kDbgMarks = 8;
+__device__ __forceinline__ void dbg_mark(const PhaseArgs &a, int kernel, int k) {
+    if (a.dbg && threadIdx.x == 0 && blockIdx.x < kDbgBlocks) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        long long *p = a.dbg + (((size_t)kernel * kDbgBlocks + blockIdx.x) * kDbgMarks + k) * 2;
+        p[0] = t;
+        p[1] = clock64();
+    }
+}
 
 __constant__ duet_thresholds c_thr;
 
@@ -244,6 +257,7 @@ __device__ __forceinline__ unsigned bloom_bits(unsigned long long key) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 k_build(PhaseArgs a) {
+    dbg_mark(a, 0, 0);
     const long long j = (long long)blockIdx.x * kThreads + threadIdx.x;
     const bool live = j < a.n_joins;
     const unsigned long long key = live ? __ldcs(a.csr_key + j) : 0ull;
@@ -266,12 +280,14 @@ k_build(PhaseArgs a) {
         if (won || prev == key) break;
         p = (p + 1) & mask;
     }
+    dbg_mark(a, 0, 1);
     Slot *sl = a.tab + base + p;
     if (won) {
         sl->first = (int)j;
     } else {
         a.next[j] = atomicExch(&sl->head, (int)j);
     }
+    dbg_mark(a, 0, 2);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -315,6 +331,7 @@ k_probe(PhaseArgs a) {
     const int qcap = a.probe_qcap;
     const int lane = threadIdx.x & 31;
 
+    dbg_mark(a, 1, 0);
     const long long R = a.n_reads;
     long long per = (R + gridDim.x - 1) / gridDim.x;
     per += per & 1;                                              // ranges start on a 16-byte boundary
@@ -349,6 +366,7 @@ k_probe(PhaseArgs a) {
         for (int i = threadIdx.x; i < (int)(bmw + 1) / 4; i += kProbeThreads)
             reinterpret_cast<uint4 *>(s_bm)[i] = src[i];
         __syncthreads();
+        dbg_mark(a, 1, 1);
         for (long long qb = r0 >> 1; qb < q1; qb += kProbeBatch, q += kProbeBatch) {
             ulonglong2 v[kProbeUnroll];
 #pragma unroll
@@ -396,6 +414,7 @@ k_probe(PhaseArgs a) {
         r0 = r1;
         ++s;
     }
+    dbg_mark(a, 1, 2);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -554,6 +573,7 @@ __device__ __forceinline__ void c2_update(C2Group &g, unsigned gmask, bool q, in
 __global__ void __launch_bounds__(kThreads, 6)
 k_reduce(PhaseArgs a) {
     constexpr int G = kReduceLanes;
+    dbg_mark(a, 2, 0);
     __shared__ __align__(16) long long s_tile[kSortSmemBytes / 8];
     __shared__ C2Group s_c2[kReducePerBlock];
     __shared__ int s_list[kThreads];
@@ -612,6 +632,7 @@ k_reduce(PhaseArgs a) {
             }
         }
     }
+    dbg_mark(a, 2, 1);
     hits = group_sum(hits, gmask, G);
     ps_lo = group_min(ps_lo, gmask, G);
     ps_hi = group_max(ps_hi, gmask, G);
@@ -657,8 +678,10 @@ k_reduce(PhaseArgs a) {
     }
 
     // credit the shards of this block's SVs; the block completing a shard builds its one-PS list
+    dbg_mark(a, 2, 2);
     __threadfence();
     __syncthreads();
+    dbg_mark(a, 2, 3);
     if (threadIdx.x == 0) {
         int n = 0;
         if (sv0 < sv1) {
@@ -678,7 +701,9 @@ k_reduce(PhaseArgs a) {
     }
     __syncthreads();
     const int n_done = s_n;
+    dbg_mark(a, 2, 4);
     for (int i = 0; i < n_done; ++i) oneps_any(a, s_list[i], s_tile);
+    dbg_mark(a, 2, 5);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1015,6 +1040,7 @@ k_predict(PhaseArgs a) {
     __shared__ int s_credit[kPredictPerBlock];
     __shared__ int s_fb[kPredictPerBlock];
     __shared__ int s_n, s_nfb;
+    dbg_mark(a, 3, 0);
     const SvTile tile = a.predict_tiles[blockIdx.x];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int blk0 = blockIdx.x * kPredictPerBlock, blk1 = min(a.n_svs, blk0 + kPredictPerBlock);
@@ -1034,6 +1060,7 @@ k_predict(PhaseArgs a) {
     if (threadIdx.x == 0) { s_n = 0; s_nfb = 0; }
     if (threadIdx.x < kPredictPerBlock) s_credit[threadIdx.x] = mine ? shard : -1;
     __syncthreads();
+    dbg_mark(a, 3, 1);
 
     if (mine && cls != DUET_CLS_FILTERED) {
         const bool home = shard == tile.s_first;
@@ -1067,6 +1094,7 @@ k_predict(PhaseArgs a) {
             if (ready) decide_and_store(a, sv, cls, st, one, n_one, n_list);
         }
     }
+    dbg_mark(a, 3, 2);
     __syncthreads();
     for (int k = w; k < s_nfb; k += kThreads / 32) {                 // rare: > kC2Max phase sets in one SV
         const int sv2 = blk0 + s_fb[k];
@@ -1081,6 +1109,7 @@ k_predict(PhaseArgs a) {
 
     __threadfence();
     __syncthreads();
+    dbg_mark(a, 3, 3);
     if (threadIdx.x == 0) {
         int run_s = -1, run_n = 0;
         for (int t = 0; t <= kPredictPerBlock; ++t) {                // shards are contiguous in SV order
@@ -1098,7 +1127,9 @@ k_predict(PhaseArgs a) {
     }
     __syncthreads();
     const int n_done = min(s_n, kThreads);
+    dbg_mark(a, 3, 4);
     for (int i = 0; i < n_done; ++i) order_block(a, s_list[i], s_tile);
+    dbg_mark(a, 3, 5);
 }
 
 }  // namespace duet
