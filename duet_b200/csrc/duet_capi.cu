@@ -64,7 +64,8 @@ struct duet_handle {
     DevBuf in_csr_off, in_csr_key, in_csr_chk;
     // descriptors, table, scratch, outputs
     DevBuf d_read_off, d_sv_off, d_join_off, d_sv_shard, d_tab_off, d_tab_mask, d_done, d_c2;
-    DevBuf d_btiles, d_rtiles, d_ptiles, d_dbg;
+    DevBuf d_btiles, d_rtiles, d_ptiles, d_qtiles, d_dbg;
+    int probe_grid = 0;
     bool dbg_on = false;
     size_t probe_smem = 0;
     DevBuf d_table;                 // Slot[n_slots] followed by the Bloom filter words
@@ -159,7 +160,12 @@ int duet_create(int device_id, duet_handle **out) {
     {   // fails here, loudly, if the image was not built for this device (sm_100a only)
         cudaFuncAttributes fa;
         cudaFuncGetAttributes(&fa, k_probe);
-        cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, kBloomMaxWords * 4 + 4096 * 12);
+        cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, kBloomMaxWords * 4);
+        // one shared-memory carveout for all four kernels: switching it between launches drains the SMs
+        cudaFuncSetAttribute(k_build, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_probe, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_reduce, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_predict, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device_id);
     }
     if (cudaGetLastError() != cudaSuccess) {
@@ -177,7 +183,7 @@ void duet_destroy(duet_handle *h) {
     DevBuf *bufs[] = {&h->in_read_key, &h->in_read_tag,
                       &h->in_sv_pos, &h->in_sv_svlen, &h->in_sv_svread, &h->in_sv_refread, &h->in_sv_flags,
                       &h->in_sv_group, &h->in_csr_off, &h->in_csr_key, &h->in_csr_chk, &h->d_read_off,
-                      &h->d_sv_off, &h->d_join_off, &h->d_c2, &h->d_btiles, &h->d_rtiles, &h->d_ptiles, &h->d_dbg, &h->d_sv_shard, &h->d_done, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_bm_off, &h->d_bm_wmask, &h->d_next,
+                      &h->d_sv_off, &h->d_join_off, &h->d_c2, &h->d_btiles, &h->d_rtiles, &h->d_ptiles, &h->d_qtiles, &h->d_dbg, &h->d_sv_shard, &h->d_done, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_bm_off, &h->d_bm_wmask, &h->d_next,
                       &h->d_join_row, &h->d_n_hit, &h->d_cand, &h->d_oneps, &h->d_oneps_n, &h->d_sort, &h->d_gt,
                       &h->d_cls, &h->d_ps, &h->d_hap1, &h->d_hap2, &h->d_hap0, &h->d_allhap, &h->d_t1, &h->d_t2,
                       &h->d_feat, &h->d_order, &h->d_n_emit, &h->d_counts, &h->d_status};
@@ -343,6 +349,19 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     a.reduce_tiles = static_cast<const SvTile *>(dv);
     if ((rc = stage(h, h->d_ptiles, ptiles.data(), sizeof(SvTile) * ptiles.size(), DUET_MEM_HOST, &dv))) return rc;
     a.predict_tiles = static_cast<const SvTile *>(dv);
+    // k_probe: persistent grid, contiguous row ranges starting on 16-byte boundaries
+    h->probe_grid = std::max(1, h->n_sm * kProbeBlocksPerSm);
+    std::vector<ProbeTile> qtiles((size_t)h->probe_grid);
+    {
+        long long per = (R + h->probe_grid - 1) / h->probe_grid;
+        per += per & 1;
+        for (int b = 0; b < h->probe_grid; ++b) {
+            const long long q0 = std::min<long long>(R, (long long)b * per), q1 = std::min<long long>(R, q0 + per);
+            qtiles[b] = ProbeTile{q0, q1, q0 < q1 ? shard_at(h->h_read_off, q0) : 0, 0};
+        }
+    }
+    if ((rc = stage(h, h->d_qtiles, qtiles.data(), sizeof(ProbeTile) * qtiles.size(), DUET_MEM_HOST, &dv))) return rc;
+    a.probe_tiles = static_cast<const ProbeTile *>(dv);
     CU(h, cudaStreamSynchronize(st));          // the descriptor vectors live on this stack frame
     if ((rc = stage(h, h->d_tab_off, tab_off.data(), sizeof(int) * ns, DUET_MEM_HOST, &dv))) return rc;
     a.tab_off = static_cast<const int *>(dv);
@@ -372,8 +391,7 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     {
         long long max_words = 32;
         for (int s = 0; s < ns; ++s) max_words = std::max<long long>(max_words, (long long)bm_wmask[s] + 1);
-        a.probe_qcap = 4096;
-        h->probe_smem = (size_t)a.probe_qcap * 12 + (size_t)max_words * 4;
+        h->probe_smem = (size_t)max_words * 4;
     }
     CU(h, h->d_gt.reserve(S1));                          a.gt = h->d_gt.as<uint8_t>();
     CU(h, h->d_cls.reserve(S1));                         a.cls = h->d_cls.as<uint8_t>();
@@ -428,7 +446,7 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
     }
     mark(EV_K1);
     if (a.n_reads && a.n_joins) {
-        k_probe<<<h->n_sm, kProbeThreads, h->probe_smem, st>>>(a);
+        k_probe<<<h->probe_grid, kProbeThreads, h->probe_smem, st>>>(a);
         ++h->launches;
     }
     mark(EV_K2);

@@ -49,6 +49,7 @@ struct __align__(16) ReadTag { int ps, pc; unsigned chk, hp; };       // hp: low
 // host-built descriptors: what a block needs to know about its tile, in one 32- / 16-byte load
 struct BuildTile { int lo, hi, base, mask, bmo, bmw, pad[2]; };   // shards of 256 consecutive support reads
 struct SvTile { int s_first, s_last, off0, off1; };               // shards of a block's SVs; SV range of s_first
+struct ProbeTile { long long r0, r1; int s_first, pad; };         // row range of a k_probe block, its first shard
 
 constexpr int kC2Max = 8;    // distinct PS per class-2 SV recorded by k_reduce (more -> warp fallback)
 struct C2Ent { int ps, tot, n1, n2; long long s1, s2; int bad, pad; };
@@ -72,6 +73,7 @@ struct PhaseArgs {
     const BuildTile *build_tiles;   // [ceil(J / 256)]
     const SvTile *reduce_tiles;     // [ceil(S / kReducePerBlock)]
     const SvTile *predict_tiles;    // [ceil(S / kPredictPerBlock)]
+    const ProbeTile *probe_tiles;   // [k_probe grid]
     const unsigned long long *read_key;
     const ReadTag *read_tag;
     const int *sv_pos, *sv_svlen, *sv_svread, *sv_refread;
@@ -98,7 +100,6 @@ struct PhaseArgs {
     int *done_reduce;            // [n_shards] SVs of the shard finished by k_reduce (self-resetting)
     int *done_predict;           // [n_shards] same for k_predict
     C2Rec *c2rec;                // [S] per-PS statistics of class-2 SVs (k_reduce -> k_predict)
-    int probe_qcap;              // candidate queue entries in k_probe's shared memory
     long long *sort_scratch;     // [4*S] global tile for slow-path sorts of big shards
     uint8_t *gt, *cls;
     int *ps, *hap1, *hap2, *hap0, *allhap;
@@ -295,20 +296,18 @@ k_build(PhaseArgs a) {
 // the next batch already requested while the current one is processed) by a persistent grid --
 // one block per SM, each owning a contiguous row range.  The block keeps the current contig's
 // Bloom filter in shared memory, so ~90 % of the rows (reads that support no SV) never leave the
-// SM.  Rows that pass are queued in shared memory and resolved one per thread: a single 32-byte
-// slot load (plus the row's hi word) decides, and a hit pushes the row index to every
-// support-read entry of that name with atomicMax -- a later row overrides an earlier one
-// (sv_phasing_fn.py:29).
+// SM.  For the rows that pass, a thread issues the 16-byte slot loads of all of them together; a hit
+// pushes the row index to every support-read entry of that name with atomicMax -- a later row
+// overrides an earlier one (sv_phasing_fn.py:29).  Nothing inside the stream synchronises the block.
 // ------------------------------------------------------------------------------------------
-constexpr int kProbeThreads = 1024;
+constexpr int kProbeThreads = 512;
+constexpr int kProbeBlocksPerSm = 2;
 constexpr int kProbeUnroll = 4;                                  // 16-byte pairs per thread per batch
 constexpr int kProbeBatch = kProbeThreads * kProbeUnroll;        // pairs per block per batch
 
-__device__ __forceinline__ void probe_candidate(const PhaseArgs &a, unsigned long long key, int row, int base,
-                                                unsigned mask) {
-    unsigned p = slot_hash(key) & mask;
-    for (;;) {
-        const uint4 sl = *reinterpret_cast<const uint4 *>(a.tab + base + p);          // key, first, head
+__device__ __forceinline__ void probe_resolve(const PhaseArgs &a, unsigned long long key, int row, int base,
+                                              unsigned mask, unsigned p, uint4 sl) {
+    for (;;) {                                                   // sl = slot p: key, first, head
         const unsigned long long k = ((unsigned long long)sl.y << 32) | sl.x;
         if (k == key) {
             atomicMax(a.join_row + (int)sl.z, row);
@@ -317,29 +316,20 @@ __device__ __forceinline__ void probe_candidate(const PhaseArgs &a, unsigned lon
         }
         if (k == kEmptyKey) return;
         p = (p + 1) & mask;
+        sl = *reinterpret_cast<const uint4 *>(a.tab + base + p);
     }
 }
 
-__global__ void __launch_bounds__(kProbeThreads, 1)
+__global__ void __launch_bounds__(kProbeThreads, kProbeBlocksPerSm)
 k_probe(PhaseArgs a) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ int s_qn;
-    // layout: [queue keys | queue rows | filter words]
-    unsigned long long *s_qkey = reinterpret_cast<unsigned long long *>(s_raw);
-    int *s_qrow = reinterpret_cast<int *>(s_qkey + a.probe_qcap);
-    unsigned *s_bm = reinterpret_cast<unsigned *>(s_qrow + a.probe_qcap);
-    const int qcap = a.probe_qcap;
-    const int lane = threadIdx.x & 31;
-
+    extern __shared__ __align__(16) unsigned s_bm[];
     dbg_mark(a, 1, 0);
+    const ProbeTile tile = a.probe_tiles[blockIdx.x];
     const long long R = a.n_reads;
-    long long per = (R + gridDim.x - 1) / gridDim.x;
-    per += per & 1;                                              // ranges start on a 16-byte boundary
-    long long r0 = min(R, (long long)blockIdx.x * per);
-    const long long r_end = min(R, r0 + per);
+    long long r0 = tile.r0;
+    const long long r_end = tile.r1;
     if (r0 >= r_end) return;
-    if (threadIdx.x == 0) s_qn = 0;
-    int s = shard_of(a.read_off, a.n_shards, r0);
+    int s = tile.s_first;
     const ulonglong2 *pairs = reinterpret_cast<const ulonglong2 *>(a.read_key);
     while (r0 < r_end) {
         while (__ldg(a.read_off + s + 1) <= r0) ++s;             // skip contigs without reads
@@ -367,50 +357,34 @@ k_probe(PhaseArgs a) {
             reinterpret_cast<uint4 *>(s_bm)[i] = src[i];
         __syncthreads();
         dbg_mark(a, 1, 1);
+        // no block-wide synchronisation inside the stream: warps run ahead of each other freely
         for (long long qb = r0 >> 1; qb < q1; qb += kProbeBatch, q += kProbeBatch) {
-            ulonglong2 v[kProbeUnroll];
+            unsigned long long key[2 * kProbeUnroll];
 #pragma unroll
-            for (int u = 0; u < kProbeUnroll; ++u) v[u] = nxt[u];
+            for (int u = 0; u < kProbeUnroll; ++u) { key[2 * u] = nxt[u].x; key[2 * u + 1] = nxt[u].y; }
             if (qb + kProbeBatch < q1) fetch(q + kProbeBatch);   // next batch requested before this one is used
             unsigned pass = 0;
 #pragma unroll
-            for (int u = 0; u < kProbeUnroll; ++u) {
-                const long long row = 2 * (q + (long long)u * kProbeThreads);
-                const unsigned mx = bloom_bits(v[u].x), my = bloom_bits(v[u].y);
-                if (row >= r0 && row < r1 && (s_bm[bloom_word(v[u].x, bmw)] & mx) == mx) pass |= 1u << (2 * u);
-                if (row + 1 >= r0 && row + 1 < r1 && (s_bm[bloom_word(v[u].y, bmw)] & my) == my) pass |= 2u << (2 * u);
+            for (int u = 0; u < 2 * kProbeUnroll; ++u) {
+                const long long row = 2 * (q + (long long)(u >> 1) * kProbeThreads) + (u & 1);
+                const unsigned m = bloom_bits(key[u]);
+                if (row >= r0 && row < r1 && (s_bm[bloom_word(key[u], bmw)] & m) == m) pass |= 1u << u;
             }
-            // queue the candidates: one shared-memory atomic per warp
-            const int cnt = __popc(pass);
-            int inc = cnt;
+            if (pass == 0) continue;
+            // rows that passed the filter: all first probes issued together, then resolved
+            uint4 sl[2 * kProbeUnroll];
+            unsigned p[2 * kProbeUnroll];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
+            for (int u = 0; u < 2 * kProbeUnroll; ++u) {
+                p[u] = slot_hash(key[u]) & mask;
+                if (pass >> u & 1u) sl[u] = *reinterpret_cast<const uint4 *>(a.tab + base + p[u]);
             }
-            int wbase = 0;
-            if (lane == 31 && inc) wbase = atomicAdd(&s_qn, inc);
-            wbase = __shfl_sync(0xffffffffu, wbase, 31);
-            int pos = wbase + inc - cnt;
 #pragma unroll
-            for (int u = 0; u < kProbeUnroll; ++u) {
-                const int row = (int)(2 * (q + (long long)u * kProbeThreads));
-                if (pass >> (2 * u) & 1u) {
-                    if (pos < qcap) { s_qkey[pos] = v[u].x; s_qrow[pos] = row; } else probe_candidate(a, v[u].x, row, base, mask);
-                    ++pos;
-                }
-                if (pass >> (2 * u + 1) & 1u) {
-                    if (pos < qcap) { s_qkey[pos] = v[u].y; s_qrow[pos] = row + 1; } else probe_candidate(a, v[u].y, row + 1, base, mask);
-                    ++pos;
-                }
-            }
-            __syncthreads();                                     // all candidates of the batch are queued
-            const int qn = min(s_qn, qcap);
-            __syncthreads();                                     // ... and everybody has read the count
-            if (threadIdx.x == 0) s_qn = 0;
-            for (int i = threadIdx.x; i < qn; i += kProbeThreads) probe_candidate(a, s_qkey[i], s_qrow[i], base, mask);
-            __syncthreads();                                     // queue free again, reset visible
+            for (int u = 0; u < 2 * kProbeUnroll; ++u)
+                if (pass >> u & 1u)
+                    probe_resolve(a, key[u], (int)(2 * (q + (long long)(u >> 1) * kProbeThreads) + (u & 1)), base, mask, p[u], sl[u]);
         }
+        __syncthreads();                                         // the filter is replaced for the next contig
         r0 = r1;
         ++s;
     }
@@ -424,7 +398,6 @@ k_probe(PhaseArgs a) {
 // ------------------------------------------------------------------------------------------
 template <bool kStaged>
 __device__ void oneps_block(const PhaseArgs &a, int s, long long *smem_tile) {
-    __shared__ unsigned char s_first[512];
     const int b = (int)a.sv_off[s], n = (int)a.sv_off[s + 1] - b;
     const int per = (n + kThreads - 1) / kThreads;
     const int c0 = min(n, (int)threadIdx.x * per), c1 = min(n, c0 + per);
@@ -453,7 +426,7 @@ __device__ void oneps_block(const PhaseArgs &a, int s, long long *smem_tile) {
         return;
     }
     // slow path.  Squeeze runs of equal neighbours first (a nearly sorted list of a few hundred
-    // phase sets stays a few hundred long), then rank-count small sets or sort big ones.
+    // phase sets stays a few hundred long), then sort what is left.
     const long long prev0 = block_scan_exclusive(lastv, kNone, OpLast(), (long long *)nullptr);
     long long prev = prev0;
     cnt = 0;
@@ -476,30 +449,8 @@ __device__ void oneps_block(const PhaseArgs &a, int s, long long *smem_tile) {
     }
 #undef CAND
     __syncthreads();
-    if (r <= 512) {
-        for (int h = threadIdx.x; h < r; h += kThreads) {
-            const long long x = v[h];
-            bool first = true;
-            for (int t = 0; t < h; ++t) first &= v[t] != x;
-            s_first[h] = first;
-        }
-        __syncthreads();
-        int total = 0;
-        for (int h = threadIdx.x; h < r; h += kThreads) {
-            if (!s_first[h]) continue;
-            const long long x = v[h];
-            int rank = 0;
-            for (int t = 0; t < r; ++t) rank += s_first[t] && v[t] < x;
-            a.oneps[b + rank] = (int)x;
-        }
-        if (threadIdx.x == 0) {
-            for (int t = 0; t < r; ++t) total += s_first[t];
-            a.oneps_n[s] = total;
-        }
-        __syncthreads();
-        return;
-    }
-    const int n_pad = next_pow2(r);
+    __syncthreads();
+    const int n_pad = next_pow2(max(r, 1));
     for (int i = r + threadIdx.x; i < n_pad; i += kThreads) v[i] = kNoCand;
     __syncthreads();
     block_bitonic_sort(v, n_pad);
@@ -679,10 +630,10 @@ k_reduce(PhaseArgs a) {
 
     // credit the shards of this block's SVs; the block completing a shard builds its one-PS list
     dbg_mark(a, 2, 2);
-    __threadfence();
     __syncthreads();
     dbg_mark(a, 2, 3);
     if (threadIdx.x == 0) {
+        __threadfence();                 // cumulative: orders the whole block's stores (after the barrier)
         int n = 0;
         if (sv0 < sv1) {
             for (int s = tile.s_first; s <= tile.s_last; ++s) {
@@ -940,7 +891,87 @@ __device__ __forceinline__ long long order_key(const PhaseArgs &a, int sv, int c
     return (long long)((grp << 34) | (upos << 2) | (unsigned long long)cls);      // < 2^50
 }
 
-__device__ void order_block(const PhaseArgs &a, int s, long long *smem_tile) {
+constexpr int kOrdStage = 8;
+
+// shards of up to kThreads*kOrdStage SVs: every thread fetches its chunk's per-SV state with
+// independent loads (one round trip), everything after that runs out of registers
+__device__ void order_block_small(const PhaseArgs &a, int s, long long *smem_tile) {
+    __shared__ unsigned long long s_cnt[DUET_N_COUNTERS];
+    const int b = (int)a.sv_off[s], n = (int)a.sv_off[s + 1] - b;
+    if (threadIdx.x < DUET_N_COUNTERS) s_cnt[threadIdx.x] = 0ull;
+    __syncthreads();
+    const int per = (n + kThreads - 1) / kThreads;                       // <= kOrdStage
+    const int c0 = min(n, (int)threadIdx.x * per), c1 = min(n, c0 + per);
+    int g[kOrdStage], cl[kOrdStage], nh[kOrdStage], pos[kOrdStage], grp[kOrdStage];
+#pragma unroll
+    for (int u = 0; u < kOrdStage; ++u) {
+        const bool live = c0 + u < c1;
+        const int sv = b + c0 + u;
+        g[u] = live ? (int)__ldcg(a.gt + sv) : 0;
+        cl[u] = live ? (int)__ldcg(a.cls + sv) : DUET_CLS_FILTERED;
+        nh[u] = live ? __ldcg(a.n_hit + sv) : 0;
+        pos[u] = live ? __ldg(a.sv_pos + sv) : 0;
+        grp[u] = live && a.sv_group ? __ldg(a.sv_group + sv) : 0;
+    }
+    unsigned long long c_kept = 0, c_emit = 0, c10 = 0, c01 = 0, c11 = 0, c_hits = 0;
+    long long key[kOrdStage];
+    long long mx = kNone;
+#pragma unroll
+    for (int u = 0; u < kOrdStage; ++u) {
+        c_hits += (unsigned long long)nh[u];
+        c_kept += (c0 + u < c1) && cl[u] != DUET_CLS_FILTERED;
+        key[u] = kNone;
+        if (g[u] != 0) {
+            ++c_emit; c10 += g[u] == 1; c01 += g[u] == 2; c11 += g[u] == 3;
+            key[u] = (long long)(((unsigned long long)(unsigned)grp[u] << 34) |
+                                 ((unsigned long long)((unsigned)pos[u] ^ 0x80000000u) << 2) | (unsigned long long)cl[u]);
+            mx = max(mx, key[u]);
+        }
+    }
+    c_kept = warp_sum(c_kept); c_emit = warp_sum(c_emit); c10 = warp_sum(c10);
+    c01 = warp_sum(c01); c11 = warp_sum(c11); c_hits = warp_sum(c_hits);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_cnt[1], c_kept); atomicAdd(&s_cnt[2], c_emit); atomicAdd(&s_cnt[3], c10);
+        atomicAdd(&s_cnt[4], c01); atomicAdd(&s_cnt[5], c11); atomicAdd(&s_cnt[7], c_hits);
+    }
+    const long long run = block_scan_exclusive(mx, kNone, OpMax(), (long long *)nullptr);
+    long long cur = run;
+    int cnt = 0;
+    bool ok = true;
+#pragma unroll
+    for (int u = 0; u < kOrdStage; ++u)
+        if (key[u] != kNone) { if (key[u] < cur) ok = false; cur = max(cur, key[u]); ++cnt; }
+    const bool sorted = __syncthreads_and(ok);
+    const int n_emit = (int)s_cnt[2];
+    int w = block_scan_exclusive(cnt, 0, OpSum(), (int *)nullptr);
+    if (sorted) {                                    // VCF already in (group, pos, class) order: just compact
+#pragma unroll
+        for (int u = 0; u < kOrdStage; ++u)
+            if (key[u] != kNone) a.order[b + w++] = b + c0 + u;
+    } else {                                         // sort (key, index in shard) packed in 62 bits
+        unsigned long long *v = reinterpret_cast<unsigned long long *>(smem_tile);
+        const int n_pad = next_pow2(max(n_emit, 1));
+#pragma unroll
+        for (int u = 0; u < kOrdStage; ++u)
+            if (key[u] != kNone) v[w++] = ((unsigned long long)key[u] << 12) | (unsigned)(c0 + u);
+        for (int i = n_emit + threadIdx.x; i < n_pad; i += kThreads) v[i] = ~0ull;
+        __syncthreads();
+        block_bitonic_sort(v, n_pad);
+        for (int i = threadIdx.x; i < n_emit; i += kThreads) a.order[b + i] = b + (int)(v[i] & 0xFFFull);
+    }
+    if (threadIdx.x == 0) {
+        a.n_emit[s] = n_emit;
+        long long *c = a.shard_counts + (size_t)s * DUET_N_COUNTERS;
+        c[0] = n;
+        c[1] = (long long)s_cnt[1]; c[2] = (long long)s_cnt[2]; c[3] = (long long)s_cnt[3];
+        c[4] = (long long)s_cnt[4]; c[5] = (long long)s_cnt[5];
+        c[6] = a.csr_off[b + n] - a.csr_off[b];
+        c[7] = (long long)s_cnt[7];
+    }
+    __syncthreads();
+}
+
+__device__ void order_block_big(const PhaseArgs &a, int s, long long *smem_tile) {
     __shared__ unsigned long long s_cnt[DUET_N_COUNTERS];
     const int b = (int)a.sv_off[s], n = (int)a.sv_off[s + 1] - b;
     if (threadIdx.x < DUET_N_COUNTERS) s_cnt[threadIdx.x] = 0ull;
@@ -1011,6 +1042,12 @@ __device__ void order_block(const PhaseArgs &a, int s, long long *smem_tile) {
     __syncthreads();
 }
 
+__device__ __forceinline__ void order_block(const PhaseArgs &a, int s, long long *smem_tile) {
+    // the packed sort key keeps 12 bits for the index in the shard and the tile holds 2048 keys
+    if ((int)(a.sv_off[s + 1] - a.sv_off[s]) <= kThreads * kOrdStage) order_block_small(a, s, smem_tile);
+    else order_block_big(a, s, smem_tile);
+}
+
 // ------------------------------------------------------------------------------------------
 // k_predict: one thread per SV (threads 0..63 of a block; all 256 help with the rest).
 //   * the one-PS list of the block's first contig is staged in shared memory (binary searches stay
@@ -1023,7 +1060,6 @@ __device__ void order_block(const PhaseArgs &a, int s, long long *smem_tile) {
 constexpr int kOneSmem = 2048;
 
 __device__ __forceinline__ void credit_one(const PhaseArgs &a, int s, int n, int total, int *s_list, int *s_n) {
-    __threadfence();
     if (atomicAdd(a.done_predict + s, n) + n == total) {
         a.done_predict[s] = 0;
         const int k = atomicAdd(s_n, 1);
@@ -1107,10 +1143,10 @@ k_predict(PhaseArgs a) {
         if (lane == 0) decide_and_store(a, sv2, 2, t, o2, n2, (int)(e2 - b2));
     }
 
-    __threadfence();
     __syncthreads();
     dbg_mark(a, 3, 3);
     if (threadIdx.x == 0) {
+        __threadfence();                 // cumulative: orders the whole block's stores (after the barrier)
         int run_s = -1, run_n = 0;
         for (int t = 0; t <= kPredictPerBlock; ++t) {                // shards are contiguous in SV order
             const int s = t < kPredictPerBlock ? s_credit[t] : -1;
@@ -1124,6 +1160,7 @@ k_predict(PhaseArgs a) {
             }
             if (s >= 0) ++run_n;
         }
+        __threadfence();
     }
     __syncthreads();
     const int n_done = min(s_n, kThreads);
