@@ -327,9 +327,9 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     auto shard_at = [&](const std::vector<long long> &off, long long x) {
         return (int)(std::upper_bound(off.begin(), off.end(), x) - off.begin()) - 1;
     };
-    std::vector<BuildTile> btiles((size_t)((J + kThreads - 1) / kThreads));
+    std::vector<BuildTile> btiles((size_t)((J + kBuildTile - 1) / kBuildTile));
     for (size_t t = 0; t < btiles.size(); ++t) {
-        const long long first = (long long)t * kThreads, last = std::min<long long>(J, first + kThreads) - 1;
+        const long long first = (long long)t * kBuildTile, last = std::min<long long>(J, first + kBuildTile) - 1;
         const int lo = shard_at(join_off, first), hi = shard_at(join_off, last);
         btiles[t] = BuildTile{lo, hi, tab_off[lo], tab_mask[lo], bm_off[lo], bm_wmask[lo], {0, 0}};
     }
@@ -357,7 +357,8 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         per += per & 1;
         for (int b = 0; b < h->probe_grid; ++b) {
             const long long q0 = std::min<long long>(R, (long long)b * per), q1 = std::min<long long>(R, q0 + per);
-            qtiles[b] = ProbeTile{q0, q1, q0 < q1 ? shard_at(h->h_read_off, q0) : 0, 0};
+            const int sf = q0 < q1 ? shard_at(h->h_read_off, q0) : 0;
+            qtiles[b] = ProbeTile{q0, q1, h->h_read_off[sf + 1], sf, tab_off[sf], tab_mask[sf], bm_off[sf], bm_wmask[sf], 0};
         }
     }
     if ((rc = stage(h, h->d_qtiles, qtiles.data(), sizeof(ProbeTile) * qtiles.size(), DUET_MEM_HOST, &dv))) return rc;
@@ -441,7 +442,7 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
         // EMPTY slots (all ones) and a zero filter, written sequentially: also pulls both into L2
         CU(h, cudaMemsetAsync(a.tab, 0xFF, (size_t)h->n_slots * sizeof(Slot), st));
         CU(h, cudaMemsetAsync(a.bitmap, 0, (size_t)h->n_bm_words * 4, st));
-        k_build<<<(a.n_joins + kThreads - 1) / kThreads, kThreads, 0, st>>>(a);
+        k_build<<<(a.n_joins + kBuildTile - 1) / kBuildTile, kThreads, 0, st>>>(a);
         ++h->launches;
     }
     mark(EV_K1);

@@ -49,7 +49,7 @@ struct __align__(16) ReadTag { int ps, pc; unsigned chk, hp; };       // hp: low
 // host-built descriptors: what a block needs to know about its tile, in one 32- / 16-byte load
 struct BuildTile { int lo, hi, base, mask, bmo, bmw, pad[2]; };   // shards of 256 consecutive support reads
 struct SvTile { int s_first, s_last, off0, off1; };               // shards of a block's SVs; SV range of s_first
-struct ProbeTile { long long r0, r1; int s_first, pad; };         // row range of a k_probe block, its first shard
+struct ProbeTile { long long r0, r1, seg_end; int s_first, base, mask, bmo, bmw, pad; };   // row range of a k_probe block + its first shard
 
 constexpr int kC2Max = 8;    // distinct PS per class-2 SV recorded by k_reduce (more -> warp fallback)
 struct C2Ent { int ps, tot, n1, n2; long long s1, s2; int bad, pad; };
@@ -256,39 +256,56 @@ __device__ __forceinline__ unsigned bloom_bits(unsigned long long key) {
 // further entries with the same name chain themselves behind it.
 // Dependent chain of a thread: [key, tile descriptor] -> CAS (-> CAS on a collision) -> stores.
 // ------------------------------------------------------------------------------------------
+constexpr int kBuildPerThread = 2;
+constexpr int kBuildTile = kThreads * kBuildPerThread;
+
 __global__ void __launch_bounds__(kThreads)
 k_build(PhaseArgs a) {
     dbg_mark(a, 0, 0);
-    const long long j = (long long)blockIdx.x * kThreads + threadIdx.x;
-    const bool live = j < a.n_joins;
-    const unsigned long long key = live ? __ldcs(a.csr_key + j) : 0ull;
-    const BuildTile t = a.build_tiles[blockIdx.x];
-    if (!live) return;
-    int base = t.base, bmo = t.bmo;
-    unsigned mask = (unsigned)t.mask, bmw = (unsigned)t.bmw;
-    if (t.lo != t.hi) {                                          // the tile straddles a contig boundary
-        const int s = t.lo + shard_of(a.join_off + t.lo, t.hi - t.lo + 1, j);
-        base = __ldg(a.tab_off + s); mask = (unsigned)__ldg(a.tab_mask + s);
-        bmo = __ldg(a.bm_off + s); bmw = (unsigned)__ldg(a.bm_wmask + s);
+    const long long j0 = (long long)blockIdx.x * kBuildTile + threadIdx.x;
+    unsigned long long key[kBuildPerThread];
+#pragma unroll
+    for (int u = 0; u < kBuildPerThread; ++u) {
+        const long long j = j0 + u * kThreads;
+        key[u] = j < a.n_joins ? __ldcs(a.csr_key + j) : 0ull;
     }
-    a.join_row[j] = -1;
-    atomicOr(a.bitmap + bmo + (int)bloom_word(key, bmw), bloom_bits(key));
-    unsigned p = slot_hash(key) & mask;
-    bool won;
-    for (;;) {
-        const unsigned long long prev = atomicCAS(&a.tab[base + p].key, kEmptyKey, key);
-        won = prev == kEmptyKey;
-        if (won || prev == key) break;
-        p = (p + 1) & mask;
+    const BuildTile t = a.build_tiles[blockIdx.x];
+    unsigned p[kBuildPerThread], mask[kBuildPerThread];
+    int base[kBuildPerThread];
+    unsigned pend = 0;
+#pragma unroll
+    for (int u = 0; u < kBuildPerThread; ++u) {
+        const long long j = j0 + u * kThreads;
+        if (j >= a.n_joins) continue;
+        base[u] = t.base; mask[u] = (unsigned)t.mask;
+        int bmo = t.bmo;
+        unsigned bmw = (unsigned)t.bmw;
+        if (t.lo != t.hi) {                                      // the tile straddles a contig boundary
+            const int s = t.lo + shard_of(a.join_off + t.lo, t.hi - t.lo + 1, j);
+            base[u] = __ldg(a.tab_off + s); mask[u] = (unsigned)__ldg(a.tab_mask + s);
+            bmo = __ldg(a.bm_off + s); bmw = (unsigned)__ldg(a.bm_wmask + s);
+        }
+        a.join_row[j] = -1;
+        atomicOr(a.bitmap + bmo + (int)bloom_word(key[u], bmw), bloom_bits(key[u]));
+        p[u] = slot_hash(key[u]) & mask[u];
+        pend |= 1u << u;
+    }
+    while (pend) {                                               // both CAS of a round are in flight together
+        unsigned long long prev[kBuildPerThread];
+#pragma unroll
+        for (int u = 0; u < kBuildPerThread; ++u)
+            if (pend >> u & 1u) prev[u] = atomicCAS(&a.tab[base[u] + p[u]].key, kEmptyKey, key[u]);
+#pragma unroll
+        for (int u = 0; u < kBuildPerThread; ++u) {
+            if (!(pend >> u & 1u)) continue;
+            const int j = (int)(j0 + u * kThreads);
+            Slot *sl = a.tab + base[u] + p[u];
+            if (prev[u] == kEmptyKey) { sl->first = j; pend &= ~(1u << u); }
+            else if (prev[u] == key[u]) { a.next[j] = atomicExch(&sl->head, j); pend &= ~(1u << u); }
+            else p[u] = (p[u] + 1) & mask[u];
+        }
     }
     dbg_mark(a, 0, 1);
-    Slot *sl = a.tab + base + p;
-    if (won) {
-        sl->first = (int)j;
-    } else {
-        a.next[j] = atomicExch(&sl->head, (int)j);
-    }
-    dbg_mark(a, 0, 2);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -302,42 +319,26 @@ k_build(PhaseArgs a) {
 // ------------------------------------------------------------------------------------------
 constexpr int kProbeThreads = 512;
 constexpr int kProbeBlocksPerSm = 2;
-constexpr int kProbeUnroll = 4;                                  // 16-byte pairs per thread per batch
+constexpr int kProbeUnroll = 2;                                  // 16-byte pairs per thread per batch
+constexpr int kProbeRows = 2 * kProbeUnroll;                     // rows per thread per batch
 constexpr int kProbeBatch = kProbeThreads * kProbeUnroll;        // pairs per block per batch
-
-__device__ __forceinline__ void probe_resolve(const PhaseArgs &a, unsigned long long key, int row, int base,
-                                              unsigned mask, unsigned p, uint4 sl) {
-    for (;;) {                                                   // sl = slot p: key, first, head
-        const unsigned long long k = ((unsigned long long)sl.y << 32) | sl.x;
-        if (k == key) {
-            atomicMax(a.join_row + (int)sl.z, row);
-            for (int h = (int)sl.w; h >= 0; h = a.next[h]) atomicMax(a.join_row + h, row);
-            return;
-        }
-        if (k == kEmptyKey) return;
-        p = (p + 1) & mask;
-        sl = *reinterpret_cast<const uint4 *>(a.tab + base + p);
-    }
-}
 
 __global__ void __launch_bounds__(kProbeThreads, kProbeBlocksPerSm)
 k_probe(PhaseArgs a) {
     extern __shared__ __align__(16) unsigned s_bm[];
     dbg_mark(a, 1, 0);
-    const ProbeTile tile = a.probe_tiles[blockIdx.x];
+    const ProbeTile tile = a.probe_tiles[blockIdx.x];            // row range + everything about its first contig
     const long long R = a.n_reads;
     long long r0 = tile.r0;
     const long long r_end = tile.r1;
     if (r0 >= r_end) return;
     int s = tile.s_first;
+    long long r1 = min(r_end, tile.seg_end);
+    int base = tile.base, bmo = tile.bmo;
+    unsigned mask = (unsigned)tile.mask, bmw = (unsigned)tile.bmw;
     const ulonglong2 *pairs = reinterpret_cast<const ulonglong2 *>(a.read_key);
-    while (r0 < r_end) {
-        while (__ldg(a.read_off + s + 1) <= r0) ++s;             // skip contigs without reads
-        const long long r1 = min(r_end, (long long)__ldg(a.read_off + s + 1));
-        const int base = __ldg(a.tab_off + s);
-        const unsigned mask = (unsigned)__ldg(a.tab_mask + s);
-        const unsigned bmw = (unsigned)__ldg(a.bm_wmask + s);
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.bitmap + __ldg(a.bm_off + s));
+    for (;;) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.bitmap + bmo);
         const long long q1 = (r1 + 1) >> 1;                      // pairs of rows (2q, 2q+1)
         long long q = (r0 >> 1) + threadIdx.x;
         ulonglong2 nxt[kProbeUnroll];
@@ -359,34 +360,52 @@ k_probe(PhaseArgs a) {
         dbg_mark(a, 1, 1);
         // no block-wide synchronisation inside the stream: warps run ahead of each other freely
         for (long long qb = r0 >> 1; qb < q1; qb += kProbeBatch, q += kProbeBatch) {
-            unsigned long long key[2 * kProbeUnroll];
+            unsigned long long key[kProbeRows];
 #pragma unroll
             for (int u = 0; u < kProbeUnroll; ++u) { key[2 * u] = nxt[u].x; key[2 * u + 1] = nxt[u].y; }
             if (qb + kProbeBatch < q1) fetch(q + kProbeBatch);   // next batch requested before this one is used
-            unsigned pass = 0;
+            unsigned pend = 0;
 #pragma unroll
-            for (int u = 0; u < 2 * kProbeUnroll; ++u) {
+            for (int u = 0; u < kProbeRows; ++u) {
                 const long long row = 2 * (q + (long long)(u >> 1) * kProbeThreads) + (u & 1);
                 const unsigned m = bloom_bits(key[u]);
-                if (row >= r0 && row < r1 && (s_bm[bloom_word(key[u], bmw)] & m) == m) pass |= 1u << u;
+                if (row >= r0 && row < r1 && (s_bm[bloom_word(key[u], bmw)] & m) == m) pend |= 1u << u;
             }
-            if (pass == 0) continue;
-            // rows that passed the filter: all first probes issued together, then resolved
-            uint4 sl[2 * kProbeUnroll];
-            unsigned p[2 * kProbeUnroll];
+            // rows that passed the filter are resolved in lock step: one slot load per pending row per round
+            unsigned p[kProbeRows];
 #pragma unroll
-            for (int u = 0; u < 2 * kProbeUnroll; ++u) {
-                p[u] = slot_hash(key[u]) & mask;
-                if (pass >> u & 1u) sl[u] = *reinterpret_cast<const uint4 *>(a.tab + base + p[u]);
+            for (int u = 0; u < kProbeRows; ++u) p[u] = slot_hash(key[u]) & mask;
+            while (pend) {
+                uint4 sl[kProbeRows];
+#pragma unroll
+                for (int u = 0; u < kProbeRows; ++u)
+                    if (pend >> u & 1u) sl[u] = *reinterpret_cast<const uint4 *>(a.tab + base + p[u]);   // key, first, head
+#pragma unroll
+                for (int u = 0; u < kProbeRows; ++u) {
+                    if (!(pend >> u & 1u)) continue;
+                    const unsigned long long k = ((unsigned long long)sl[u].y << 32) | sl[u].x;
+                    if (k == key[u]) {
+                        const int row = (int)(2 * (q + (long long)(u >> 1) * kProbeThreads) + (u & 1));
+                        // the tags of a joined row are needed by k_reduce: start pulling them into L2 now
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.read_tag + row));
+                        atomicMax(a.join_row + (int)sl[u].z, row);
+                        for (int h = (int)sl[u].w; h >= 0; h = a.next[h]) atomicMax(a.join_row + h, row);
+                        pend &= ~(1u << u);
+                    } else if (k == kEmptyKey) {
+                        pend &= ~(1u << u);
+                    } else {
+                        p[u] = (p[u] + 1) & mask;
+                    }
+                }
             }
-#pragma unroll
-            for (int u = 0; u < 2 * kProbeUnroll; ++u)
-                if (pass >> u & 1u)
-                    probe_resolve(a, key[u], (int)(2 * (q + (long long)(u >> 1) * kProbeThreads) + (u & 1)), base, mask, p[u], sl[u]);
         }
-        __syncthreads();                                         // the filter is replaced for the next contig
         r0 = r1;
-        ++s;
+        if (r0 >= r_end) break;
+        __syncthreads();                                         // the filter is replaced for the next contig
+        do { ++s; } while (__ldg(a.read_off + s + 1) <= r0);     // skip contigs without reads
+        r1 = min(r_end, (long long)__ldg(a.read_off + s + 1));
+        base = __ldg(a.tab_off + s); mask = (unsigned)__ldg(a.tab_mask + s);
+        bmo = __ldg(a.bm_off + s); bmw = (unsigned)__ldg(a.bm_wmask + s);
     }
     dbg_mark(a, 1, 2);
 }
@@ -396,6 +415,55 @@ k_probe(PhaseArgs a) {
 // Thread t owns the contiguous chunk [t*per, (t+1)*per) of the shard's candidates; shards of up to
 // kThreads*kStage SVs keep the chunk in registers so the list is read from L2 exactly once.
 // ------------------------------------------------------------------------------------------
+// Small shards (<= kSortSmemBytes / 8 SVs): the distinct candidates are collected in a shared-memory
+// hash set (a contig has a few hundred phase sets however many SVs it has), and only those are sorted.
+__device__ void oneps_block_small(const PhaseArgs &a, int s, long long *smem_tile) {
+    constexpr int kSlots = kSortSmemBytes / 4;                   // 4096 ints
+    constexpr int kPer = kSlots / kThreads;                      // 16 slots per thread
+    __shared__ int s_has_min;
+    int *tab = reinterpret_cast<int *>(smem_tile);
+    const int b = (int)a.sv_off[s], n = (int)a.sv_off[s + 1] - b;
+    for (int i = threadIdx.x; i < kSlots; i += kThreads) tab[i] = INT32_MIN;
+    if (threadIdx.x == 0) s_has_min = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+        const long long v = __ldcg(a.cand + b + i);
+        if (v == kNoCand) continue;
+        const int x = (int)v;
+        if (x == INT32_MIN) { s_has_min = 1; continue; }         // the empty marker itself: tracked aside
+        unsigned h = ((unsigned)x * 2654435761u) >> 20;
+        for (;;) {
+            const int prev = atomicCAS(tab + h, INT32_MIN, x);
+            if (prev == INT32_MIN || prev == x) break;
+            h = (h + 1) & (kSlots - 1);
+        }
+    }
+    __syncthreads();
+    int found[kPer], cnt = 0;
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+        found[u] = tab[threadIdx.x * kPer + u];
+        cnt += found[u] != INT32_MIN;
+    }
+    int m;
+    int w = block_scan_exclusive(cnt, 0, OpSum(), &m);           // ends with a barrier: the table has been read
+#pragma unroll
+    for (int u = 0; u < kPer; ++u)
+        if (found[u] != INT32_MIN) tab[w++] = found[u];
+    const int m_pad = next_pow2(max(m, 1));
+    __syncthreads();
+    for (int i = m + threadIdx.x; i < m_pad; i += kThreads) tab[i] = INT32_MAX;
+    __syncthreads();
+    block_bitonic_sort(tab, m_pad);
+    const int off = s_has_min;
+    for (int i = threadIdx.x; i < m; i += kThreads) a.oneps[b + off + i] = tab[i];
+    if (threadIdx.x == 0) {
+        if (off) a.oneps[b] = INT32_MIN;
+        a.oneps_n[s] = m + off;
+    }
+    __syncthreads();
+}
+
 template <bool kStaged>
 __device__ void oneps_block(const PhaseArgs &a, int s, long long *smem_tile) {
     const int b = (int)a.sv_off[s], n = (int)a.sv_off[s + 1] - b;
@@ -467,7 +535,7 @@ __device__ void oneps_block(const PhaseArgs &a, int s, long long *smem_tile) {
 }
 
 __device__ __forceinline__ void oneps_any(const PhaseArgs &a, int s, long long *smem_tile) {
-    if ((int)(a.sv_off[s + 1] - a.sv_off[s]) * (int)sizeof(long long) <= kSortSmemBytes) oneps_block<true>(a, s, smem_tile);
+    if ((int)(a.sv_off[s + 1] - a.sv_off[s]) * (int)sizeof(long long) <= kSortSmemBytes) oneps_block_small(a, s, smem_tile);
     else oneps_block<false>(a, s, smem_tile);
 }
 
@@ -1067,7 +1135,7 @@ __device__ __forceinline__ void credit_one(const PhaseArgs &a, int s, int n, int
     }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 k_predict(PhaseArgs a) {
     __shared__ Class2Smem s_c2[kThreads / 32];
     __shared__ __align__(16) long long s_tile[kSortSmemBytes / 8];
@@ -1148,7 +1216,9 @@ k_predict(PhaseArgs a) {
     if (threadIdx.x == 0) {
         __threadfence();                 // cumulative: orders the whole block's stores (after the barrier)
         int run_s = -1, run_n = 0;
-        for (int t = 0; t <= kPredictPerBlock; ++t) {                // shards are contiguous in SV order
+        if (tile.s_first == tile.s_last && blk0 < blk1)              // the usual case: one contig per block
+            credit_one(a, tile.s_first, blk1 - blk0, tile.off1 - tile.off0, s_list, &s_n);
+        else for (int t = 0; t <= kPredictPerBlock; ++t) {           // shards are contiguous in SV order
             const int s = t < kPredictPerBlock ? s_credit[t] : -1;
             if (s != run_s) {
                 if (run_n) {
