@@ -426,10 +426,17 @@ __device__ void oneps_block_small(const PhaseArgs &a, int s, long long *smem_til
     for (int i = threadIdx.x; i < kSlots; i += kThreads) tab[i] = INT32_MIN;
     if (threadIdx.x == 0) s_has_min = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += kThreads) {
-        const long long v = __ldcg(a.cand + b + i);
-        if (v == kNoCand) continue;
-        const int x = (int)v;
+    constexpr int kLoads = kSortSmemBytes / 8 / kThreads;        // candidates per thread, requested together
+    long long cv[kLoads];
+#pragma unroll
+    for (int u = 0; u < kLoads; ++u) {
+        const int i = threadIdx.x + u * kThreads;
+        cv[u] = i < n ? __ldcg(a.cand + b + i) : kNoCand;
+    }
+#pragma unroll
+    for (int u = 0; u < kLoads; ++u) {
+        if (cv[u] == kNoCand) continue;
+        const int x = (int)cv[u];
         if (x == INT32_MIN) { s_has_min = 1; continue; }         // the empty marker itself: tracked aside
         unsigned h = ((unsigned)x * 2654435761u) >> 20;
         for (;;) {
@@ -981,6 +988,7 @@ __device__ void order_block_small(const PhaseArgs &a, int s, long long *smem_til
         pos[u] = live ? __ldg(a.sv_pos + sv) : 0;
         grp[u] = live && a.sv_group ? __ldg(a.sv_group + sv) : 0;
     }
+    dbg_mark(a, 3, 6);
     unsigned long long c_kept = 0, c_emit = 0, c10 = 0, c01 = 0, c11 = 0, c_hits = 0;
     long long key[kOrdStage];
     long long mx = kNone;
@@ -1012,6 +1020,7 @@ __device__ void order_block_small(const PhaseArgs &a, int s, long long *smem_til
     const bool sorted = __syncthreads_and(ok);
     const int n_emit = (int)s_cnt[2];
     int w = block_scan_exclusive(cnt, 0, OpSum(), (int *)nullptr);
+    dbg_mark(a, 3, 7);
     if (sorted) {                                    // VCF already in (group, pos, class) order: just compact
 #pragma unroll
         for (int u = 0; u < kOrdStage; ++u)
