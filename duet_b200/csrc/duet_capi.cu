@@ -66,6 +66,8 @@ struct duet_handle {
     DevBuf d_read_off, d_sv_off, d_join_off, d_sv_shard, d_tab_off, d_tab_mask, d_done, d_c2;
     DevBuf d_btiles, d_rtiles, d_ptiles, d_qtiles, d_dbg;
     int probe_grid = 0;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
     bool dbg_on = false;
     size_t probe_smem = 0;
     DevBuf d_table;                 // Slot[n_slots] followed by the Bloom filter words
@@ -193,6 +195,8 @@ void duet_destroy(duet_handle *h) {
                       &h->cl_minidx, &h->cl_out, &h->cl_hist, &h->cl_misc}) b->release();
     for (auto &ev : h->cl_ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->graph) cudaGraphDestroy(h->graph);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -232,6 +236,8 @@ int duet_host_free(void *ptr) {
 int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     if (!h || !in) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: NULL argument");
     h->staged = h->executed = false;
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
     const int ns = in->n_shards;
     const long long R = in->n_reads, S = in->n_svs, J = in->n_joins;
     if (ns < 1 || R < 0 || S < 0 || J < 0 || R >= (1ll << 31) || S >= (1ll << 31) || J >= (1ll << 30))
@@ -380,7 +386,7 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     a.tab = h->d_table.as<Slot>();
     a.bitmap = reinterpret_cast<unsigned *>(a.tab + slots);
     CU(h, h->d_next.reserve(J1 * 4));                    a.next = h->d_next.as<int>();
-    CU(h, h->d_join_row.reserve(J1 * 4));                a.join_row = h->d_join_row.as<int>();
+    CU(h, h->d_join_row.reserve(J1 * 4 + 16));                a.join_row = h->d_join_row.as<int>();
     CU(h, h->d_n_hit.reserve(S1 * 4));                   a.n_hit = h->d_n_hit.as<int>();
     CU(h, h->d_cand.reserve(S1 * 8));                    a.cand = h->d_cand.as<long long>();
     CU(h, h->d_oneps.reserve(S1 * 4));                   a.oneps = h->d_oneps.as<int>();
@@ -424,26 +430,15 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     return DUET_OK;
 }
 
-int duet_phase_execute(duet_handle *h, int per_kernel) {
-    if (!h) return DUET_ERR_INVALID;
-    if (!h->staged) return fail(h, DUET_ERR_STATE, "duet_phase_execute: nothing staged (call duet_phase_upload)");
-    CU(h, cudaSetDevice(h->device));
-    cudaStream_t st = h->stream;
-    if (h->thr_dirty) {
-        CU(h, cudaMemcpyToSymbolAsync(c_thr, &h->thr, sizeof(h->thr), 0, cudaMemcpyHostToDevice, st));
-        h->thr_dirty = false;
-    }
+// the five launches of one call; with `marks` an event is recorded after each kernel
+static void launch_all(duet_handle *h, cudaStream_t st, bool marks) {
+    auto mark = [&](int ev) { if (marks) cudaEventRecord(h->ev[ev], st); };
     const PhaseArgs &a = h->a;
-    h->per_kernel = per_kernel != 0;
-    auto mark = [&](int ev) { if (h->per_kernel) cudaEventRecord(h->ev[ev], st); };
-    CU(h, cudaEventRecord(h->ev[EV_X0], st));
     const int S = a.n_svs;
     if (a.n_joins) {
-        // EMPTY slots (all ones) and a zero filter, written sequentially: also pulls both into L2
-        CU(h, cudaMemsetAsync(a.tab, 0xFF, (size_t)h->n_slots * sizeof(Slot), st));
-        CU(h, cudaMemsetAsync(a.bitmap, 0, (size_t)h->n_bm_words * 4, st));
+        k_init<<<h->n_sm * 4, kThreads, 0, st>>>(a, h->n_slots, h->n_bm_words);
         k_build<<<(a.n_joins + kBuildTile - 1) / kBuildTile, kThreads, 0, st>>>(a);
-        ++h->launches;
+        h->launches += 2;
     }
     mark(EV_K1);
     if (a.n_reads && a.n_joins) {
@@ -459,6 +454,42 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
     if (S) {
         k_predict<<<(S + kPredictPerBlock - 1) / kPredictPerBlock, kThreads, 0, st>>>(a);
         ++h->launches;
+    }
+}
+
+int duet_phase_execute(duet_handle *h, int per_kernel) {
+    if (!h) return DUET_ERR_INVALID;
+    if (!h->staged) return fail(h, DUET_ERR_STATE, "duet_phase_execute: nothing staged (call duet_phase_upload)");
+    CU(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    if (h->thr_dirty) {
+        CU(h, cudaMemcpyToSymbolAsync(c_thr, &h->thr, sizeof(h->thr), 0, cudaMemcpyHostToDevice, st));
+        h->thr_dirty = false;
+    }
+    h->per_kernel = per_kernel != 0;
+    CU(h, cudaEventRecord(h->ev[EV_X0], st));
+    if (h->per_kernel) {
+        launch_all(h, st, true);
+    } else {
+        // the launch sequence of a staged batch never changes: replay it as a CUDA graph
+        if (!h->graph_exec) {
+            const int64_t before = h->launches;
+            if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                launch_all(h, st, false);
+                if (cudaStreamEndCapture(st, &h->graph) != cudaSuccess ||
+                    cudaGraphInstantiate(&h->graph_exec, h->graph, 0) != cudaSuccess) {
+                    h->graph_exec = nullptr;
+                }
+            }
+            h->launches = before;
+            cudaGetLastError();
+        }
+        if (h->graph_exec) {
+            CU(h, cudaGraphLaunch(h->graph_exec, st));
+            h->launches += (h->a.n_joins ? 2 : 0) + (h->a.n_reads && h->a.n_joins ? 1 : 0) + (h->a.n_svs ? 2 : 0);
+        } else {
+            launch_all(h, st, false);
+        }
     }
     CU(h, cudaEventRecord(h->ev[EV_K4], st));
     CU(h, cudaGetLastError());

@@ -241,6 +241,24 @@ __device__ __forceinline__ void tile_shards(const long long *__restrict__ off, i
 }
 
 // ------------------------------------------------------------------------------------------
+// k_init: start-of-call state in one sequential sweep: EMPTY slots (all ones), zero filter words,
+// join results -1.  Sequential 16-byte stores also leave all three L2 resident for the random
+// traffic of k_build / k_probe that follows.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_init(PhaseArgs a, long long n_slots, long long n_bm_words) {
+    const long long stride = (long long)gridDim.x * kThreads;
+    const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+    uint4 *tab = reinterpret_cast<uint4 *>(a.tab);
+    const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0u, 0u, 0u, 0u);
+    for (long long i = t; i < n_slots; i += stride) tab[i] = ones;
+    uint4 *bm = reinterpret_cast<uint4 *>(a.bitmap);
+    for (long long i = t; i < n_bm_words / 4; i += stride) bm[i] = zero;
+    uint4 *jr = reinterpret_cast<uint4 *>(a.join_row);                       // allocation padded to 16 bytes
+    for (long long i = t; i < ((long long)a.n_joins + 3) / 4; i += stride) jr[i] = ones;
+}
+
+// ------------------------------------------------------------------------------------------
 // Bloom filter bit pattern of a key: one 32-bit word, two bits (a probe is one shared-memory load)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned bloom_word(unsigned long long key, unsigned wmask) {
@@ -285,7 +303,6 @@ k_build(PhaseArgs a) {
             base[u] = __ldg(a.tab_off + s); mask[u] = (unsigned)__ldg(a.tab_mask + s);
             bmo = __ldg(a.bm_off + s); bmw = (unsigned)__ldg(a.bm_wmask + s);
         }
-        a.join_row[j] = -1;
         atomicOr(a.bitmap + bmo + (int)bloom_word(key[u], bmw), bloom_bits(key[u]));
         p[u] = slot_hash(key[u]) & mask[u];
         pend |= 1u << u;
