@@ -285,8 +285,8 @@ def main():
         alg = batch.algorithmic_bytes()
         dom = max(kernel_ms, key=kernel_ms.get)
         # algorithmic bytes of each kernel of THIS design
-        kbytes = {"build": 28 * batch.n_joins, "probe": 8 * batch.n_reads,
-                  "reduce": 17 * batch.n_joins + 64 * batch.n_svs, "predict": 16 * batch.n_joins + 96 * batch.n_svs}
+        kbytes = {"init": 20 * 3 * batch.n_joins, "build": 28 * batch.n_joins, "probe": 8 * batch.n_reads,
+                  "reduce": 24 * batch.n_joins + 64 * batch.n_svs, "predict": 96 * batch.n_svs}
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:

@@ -37,7 +37,7 @@ struct DevBuf {
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-enum { EV_H2D0, EV_H2D1, EV_X0, EV_K1, EV_K2, EV_K3, EV_K4, EV_D2H0, EV_D2H1, EV_COUNT };
+enum { EV_H2D0, EV_H2D1, EV_X0, EV_K0, EV_K1, EV_K2, EV_K3, EV_K4, EV_D2H0, EV_D2H1, EV_COUNT };
 
 }  // namespace
 
@@ -64,7 +64,7 @@ struct duet_handle {
     DevBuf in_csr_off, in_csr_key, in_csr_chk;
     // descriptors, table, scratch, outputs
     DevBuf d_read_off, d_sv_off, d_join_off, d_sv_shard, d_tab_off, d_tab_mask, d_done, d_c2;
-    DevBuf d_btiles, d_rtiles, d_ptiles, d_qtiles, d_dbg;
+    DevBuf d_btiles, d_rtiles, d_ptiles, d_qtiles, d_dbg, d_cand_key, d_cand_row, d_cand_n;
     int probe_grid = 0;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
@@ -168,6 +168,8 @@ int duet_create(int device_id, duet_handle **out) {
         cudaFuncSetAttribute(k_probe, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_reduce, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_predict, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_resolve, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_init, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device_id);
     }
     if (cudaGetLastError() != cudaSuccess) {
@@ -185,7 +187,7 @@ void duet_destroy(duet_handle *h) {
     DevBuf *bufs[] = {&h->in_read_key, &h->in_read_tag,
                       &h->in_sv_pos, &h->in_sv_svlen, &h->in_sv_svread, &h->in_sv_refread, &h->in_sv_flags,
                       &h->in_sv_group, &h->in_csr_off, &h->in_csr_key, &h->in_csr_chk, &h->d_read_off,
-                      &h->d_sv_off, &h->d_join_off, &h->d_c2, &h->d_btiles, &h->d_rtiles, &h->d_ptiles, &h->d_qtiles, &h->d_dbg, &h->d_sv_shard, &h->d_done, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_bm_off, &h->d_bm_wmask, &h->d_next,
+                      &h->d_sv_off, &h->d_join_off, &h->d_c2, &h->d_btiles, &h->d_rtiles, &h->d_ptiles, &h->d_qtiles, &h->d_dbg, &h->d_cand_key, &h->d_cand_row, &h->d_cand_n, &h->d_sv_shard, &h->d_done, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_bm_off, &h->d_bm_wmask, &h->d_next,
                       &h->d_join_row, &h->d_n_hit, &h->d_cand, &h->d_oneps, &h->d_oneps_n, &h->d_sort, &h->d_gt,
                       &h->d_cls, &h->d_ps, &h->d_hap1, &h->d_hap2, &h->d_hap0, &h->d_allhap, &h->d_t1, &h->d_t2,
                       &h->d_feat, &h->d_order, &h->d_n_emit, &h->d_counts, &h->d_status};
@@ -355,18 +357,26 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     a.reduce_tiles = static_cast<const SvTile *>(dv);
     if ((rc = stage(h, h->d_ptiles, ptiles.data(), sizeof(SvTile) * ptiles.size(), DUET_MEM_HOST, &dv))) return rc;
     a.predict_tiles = static_cast<const SvTile *>(dv);
-    // k_probe: persistent grid, contiguous row ranges starting on 16-byte boundaries
-    h->probe_grid = std::max(1, h->n_sm * kProbeBlocksPerSm);
-    std::vector<ProbeTile> qtiles((size_t)h->probe_grid);
+    // k_probe tiles: row ranges that never cross a contig, about two per SM in total
+    std::vector<ProbeTile> qtiles;
     {
-        long long per = (R + h->probe_grid - 1) / h->probe_grid;
-        per += per & 1;
-        for (int b = 0; b < h->probe_grid; ++b) {
-            const long long q0 = std::min<long long>(R, (long long)b * per), q1 = std::min<long long>(R, q0 + per);
-            const int sf = q0 < q1 ? shard_at(h->h_read_off, q0) : 0;
-            qtiles[b] = ProbeTile{q0, q1, h->h_read_off[sf + 1], sf, tab_off[sf], tab_mask[sf], bm_off[sf], bm_wmask[sf], 0};
+        const long long want = std::max(1, h->n_sm * kProbeBlocksPerSm);
+        const long long per = std::max<long long>((R + want - 1) / want, 1);
+        for (int s = 0; s < ns; ++s) {
+            const long long b0 = h->h_read_off[s], b1 = h->h_read_off[s + 1];
+            if (b1 <= b0) continue;
+            const long long pieces = std::max<long long>(1, (b1 - b0 + per / 2) / per);
+            for (long long k = 0; k < pieces; ++k) {
+                long long q0 = b0 + (b1 - b0) * k / pieces, q1 = b0 + (b1 - b0) * (k + 1) / pieces;
+                if (k > 0) q0 += q0 & 1;                         // interior cuts on 16-byte boundaries
+                if (k + 1 < pieces) q1 += q1 & 1;
+                if (q0 < q1) qtiles.push_back(ProbeTile{q0, q1, s, tab_off[s], tab_mask[s], bm_off[s], bm_wmask[s], 0});
+            }
         }
+        if (qtiles.empty()) qtiles.push_back(ProbeTile{0, 0, 0, 0, 0, 0, 31, 0});
     }
+    h->probe_grid = (int)qtiles.size();
+    a.n_probe_tiles = h->probe_grid;
     if ((rc = stage(h, h->d_qtiles, qtiles.data(), sizeof(ProbeTile) * qtiles.size(), DUET_MEM_HOST, &dv))) return rc;
     a.probe_tiles = static_cast<const ProbeTile *>(dv);
     CU(h, cudaStreamSynchronize(st));          // the descriptor vectors live on this stack frame
@@ -386,6 +396,9 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     a.tab = h->d_table.as<Slot>();
     a.bitmap = reinterpret_cast<unsigned *>(a.tab + slots);
     CU(h, h->d_next.reserve(J1 * 4));                    a.next = h->d_next.as<int>();
+    CU(h, h->d_cand_key.reserve((size_t)std::max<long long>(R, 1) * 8)); a.cand_key = h->d_cand_key.as<unsigned long long>();
+    CU(h, h->d_cand_row.reserve((size_t)std::max<long long>(R, 1) * 4)); a.cand_row = h->d_cand_row.as<int>();
+    CU(h, h->d_cand_n.reserve((size_t)h->probe_grid * 4));               a.cand_n = h->d_cand_n.as<int>();
     CU(h, h->d_join_row.reserve(J1 * 4 + 16));                a.join_row = h->d_join_row.as<int>();
     CU(h, h->d_n_hit.reserve(S1 * 4));                   a.n_hit = h->d_n_hit.as<int>();
     CU(h, h->d_cand.reserve(S1 * 8));                    a.cand = h->d_cand.as<long long>();
@@ -437,13 +450,15 @@ static void launch_all(duet_handle *h, cudaStream_t st, bool marks) {
     const int S = a.n_svs;
     if (a.n_joins) {
         k_init<<<h->n_sm * 4, kThreads, 0, st>>>(a, h->n_slots, h->n_bm_words);
+        mark(EV_K0);
         k_build<<<(a.n_joins + kBuildTile - 1) / kBuildTile, kThreads, 0, st>>>(a);
         h->launches += 2;
     }
     mark(EV_K1);
     if (a.n_reads && a.n_joins) {
         k_probe<<<h->probe_grid, kProbeThreads, h->probe_smem, st>>>(a);
-        ++h->launches;
+        k_resolve<<<h->n_sm * 4, kThreads, (size_t)(h->probe_grid + 1) * 4, st>>>(a);
+        h->launches += 2;
     }
     mark(EV_K2);
     if (S) {
@@ -486,7 +501,7 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
         }
         if (h->graph_exec) {
             CU(h, cudaGraphLaunch(h->graph_exec, st));
-            h->launches += (h->a.n_joins ? 2 : 0) + (h->a.n_reads && h->a.n_joins ? 1 : 0) + (h->a.n_svs ? 2 : 0);
+            h->launches += (h->a.n_joins ? 2 : 0) + (h->a.n_reads && h->a.n_joins ? 2 : 0) + (h->a.n_svs ? 2 : 0);
         } else {
             launch_all(h, st, false);
         }
@@ -576,8 +591,9 @@ int duet_get_timings(duet_handle *h, duet_timings *t) {
     if (h->executed) {
         cudaEventElapsedTime(&t->device_ms, h->ev[EV_X0], h->ev[EV_K4]);
         if (h->per_kernel) {
-            const int seq[] = {EV_X0, EV_K1, EV_K2, EV_K3, EV_K4};
-            for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t->kernel_ms[i], h->ev[seq[i]], h->ev[seq[i + 1]]);
+            const int seq[] = {EV_X0, EV_K0, EV_K1, EV_K2, EV_K3, EV_K4};
+            for (int i = 0; i < 5; ++i)
+                if (cudaEventElapsedTime(&t->kernel_ms[i], h->ev[seq[i]], h->ev[seq[i + 1]]) != cudaSuccess) t->kernel_ms[i] = 0.f;
         }
     }
     if (h->have_d2h) cudaEventElapsedTime(&t->d2h_ms, h->ev[EV_D2H0], h->ev[EV_D2H1]);

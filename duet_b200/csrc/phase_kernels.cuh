@@ -49,7 +49,7 @@ struct __align__(16) ReadTag { int ps, pc; unsigned chk, hp; };       // hp: low
 // host-built descriptors: what a block needs to know about its tile, in one 32- / 16-byte load
 struct BuildTile { int lo, hi, base, mask, bmo, bmw, pad[2]; };   // shards of 256 consecutive support reads
 struct SvTile { int s_first, s_last, off0, off1; };               // shards of a block's SVs; SV range of s_first
-struct ProbeTile { long long r0, r1, seg_end; int s_first, base, mask, bmo, bmw, pad; };   // row range of a k_probe block + its first shard
+struct ProbeTile { long long r0, r1; int shard, base, mask, bmo, bmw, pad; };   // rows [r0, r1) of ONE contig + its table / filter
 
 constexpr int kC2Max = 8;    // distinct PS per class-2 SV recorded by k_reduce (more -> warp fallback)
 struct C2Ent { int ps, tot, n1, n2; long long s1, s2; int bad, pad; };
@@ -73,7 +73,11 @@ struct PhaseArgs {
     const BuildTile *build_tiles;   // [ceil(J / 256)]
     const SvTile *reduce_tiles;     // [ceil(S / kReducePerBlock)]
     const SvTile *predict_tiles;    // [ceil(S / kPredictPerBlock)]
-    const ProbeTile *probe_tiles;   // [k_probe grid]
+    const ProbeTile *probe_tiles;   // [n_probe_tiles] = k_probe grid
+    int n_probe_tiles;
+    unsigned long long *cand_key;   // [R] rows that passed their contig's filter: tile t appends at [r0(t), ...)
+    int *cand_row;                  // [R]
+    int *cand_n;                    // [n_probe_tiles] candidates each tile found
     const unsigned long long *read_key;
     const ReadTag *read_tag;
     const int *sv_pos, *sv_svlen, *sv_svread, *sv_refread;
@@ -326,13 +330,12 @@ k_build(PhaseArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// k_probe: the haplotagged reads are STREAMED once (16-byte loads, 8 rows in flight per thread,
-// the next batch already requested while the current one is processed) by a persistent grid --
-// one block per SM, each owning a contiguous row range.  The block keeps the current contig's
-// Bloom filter in shared memory, so ~90 % of the rows (reads that support no SV) never leave the
-// SM.  For the rows that pass, a thread issues the 16-byte slot loads of all of them together; a hit
-// pushes the row index to every support-read entry of that name with atomicMax -- a later row
-// overrides an earlier one (sv_phasing_fn.py:29).  Nothing inside the stream synchronises the block.
+// k_probe: the haplotagged reads are STREAMED once (16-byte loads, the next batch already requested
+// while the current one is filtered) by one block per tile -- a tile is a row range of ONE contig,
+// sized so that the grid is about two blocks per SM.  The block keeps the contig's Bloom filter in
+// shared memory, so ~90 % of the rows (reads that support no SV) never leave the SM; the survivors are
+// appended to the block's private stretch of the candidate list for k_resolve.  Nothing inside the
+// stream waits on L2 or synchronises the block.
 // ------------------------------------------------------------------------------------------
 constexpr int kProbeThreads = 512;
 constexpr int kProbeBlocksPerSm = 2;
@@ -343,88 +346,141 @@ constexpr int kProbeBatch = kProbeThreads * kProbeUnroll;        // pairs per bl
 __global__ void __launch_bounds__(kProbeThreads, kProbeBlocksPerSm)
 k_probe(PhaseArgs a) {
     extern __shared__ __align__(16) unsigned s_bm[];
+    __shared__ int s_count;
     dbg_mark(a, 1, 0);
-    const ProbeTile tile = a.probe_tiles[blockIdx.x];            // row range + everything about its first contig
+    const ProbeTile tile = a.probe_tiles[blockIdx.x];            // one contig, one row range, everything needed
     const long long R = a.n_reads;
-    long long r0 = tile.r0;
-    const long long r_end = tile.r1;
-    if (r0 >= r_end) return;
-    int s = tile.s_first;
-    long long r1 = min(r_end, tile.seg_end);
-    int base = tile.base, bmo = tile.bmo;
-    unsigned mask = (unsigned)tile.mask, bmw = (unsigned)tile.bmw;
+    const long long r0 = tile.r0, r1 = tile.r1;
+    const unsigned bmw = (unsigned)tile.bmw;
+    const int lane = threadIdx.x & 31;
     const ulonglong2 *pairs = reinterpret_cast<const ulonglong2 *>(a.read_key);
-    for (;;) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.bitmap + bmo);
-        const long long q1 = (r1 + 1) >> 1;                      // pairs of rows (2q, 2q+1)
-        long long q = (r0 >> 1) + threadIdx.x;
-        ulonglong2 nxt[kProbeUnroll];
-        auto fetch = [&](long long qb) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(a.bitmap + tile.bmo);
+    const long long q1 = (r1 + 1) >> 1;                          // pairs of rows (2q, 2q+1)
+    long long q = (r0 >> 1) + threadIdx.x;
+    ulonglong2 nxt[kProbeUnroll];
+    auto fetch = [&](long long qb) {
 #pragma unroll
-            for (int u = 0; u < kProbeUnroll; ++u) {
-                const long long qq = qb + (long long)u * kProbeThreads;
-                nxt[u] = make_ulonglong2(0ull, 0ull);
-                if (qq < q1) {
-                    if (2 * qq + 1 < R) nxt[u] = __ldcs(pairs + qq);
-                    else nxt[u].x = __ldcs(a.read_key + 2 * qq);
-                }
+        for (int u = 0; u < kProbeUnroll; ++u) {
+            const long long qq = qb + (long long)u * kProbeThreads;
+            nxt[u] = make_ulonglong2(0ull, 0ull);
+            if (qq < q1) {
+                if (2 * qq + 1 < R) nxt[u] = __ldcs(pairs + qq);
+                else nxt[u].x = __ldcs(a.read_key + 2 * qq);
             }
-        };
-        fetch(q);                                                // first batch in flight during the filter load
-        for (int i = threadIdx.x; i < (int)(bmw + 1) / 4; i += kProbeThreads)
-            reinterpret_cast<uint4 *>(s_bm)[i] = src[i];
-        __syncthreads();
-        dbg_mark(a, 1, 1);
-        // no block-wide synchronisation inside the stream: warps run ahead of each other freely
-        for (long long qb = r0 >> 1; qb < q1; qb += kProbeBatch, q += kProbeBatch) {
-            unsigned long long key[kProbeRows];
+        }
+    };
+    fetch(q);                                                    // first batch in flight during the filter load
+    for (int i = threadIdx.x; i < (int)(bmw + 1) / 4; i += kProbeThreads)
+        reinterpret_cast<uint4 *>(s_bm)[i] = src[i];
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    dbg_mark(a, 1, 1);
+    unsigned long long *out_key = a.cand_key + r0;               // this block's private stretch of the list
+    int *out_row = a.cand_row + r0;
+    // no block-wide synchronisation inside the stream: warps run ahead of each other freely
+    for (long long qb = r0 >> 1; qb < q1; qb += kProbeBatch, q += kProbeBatch) {
+        unsigned long long key[kProbeRows];
 #pragma unroll
-            for (int u = 0; u < kProbeUnroll; ++u) { key[2 * u] = nxt[u].x; key[2 * u + 1] = nxt[u].y; }
-            if (qb + kProbeBatch < q1) fetch(q + kProbeBatch);   // next batch requested before this one is used
-            unsigned pend = 0;
+        for (int u = 0; u < kProbeUnroll; ++u) { key[2 * u] = nxt[u].x; key[2 * u + 1] = nxt[u].y; }
+        if (qb + kProbeBatch < q1) fetch(q + kProbeBatch);       // next batch requested before this one is used
+        unsigned pass = 0;
 #pragma unroll
-            for (int u = 0; u < kProbeRows; ++u) {
-                const long long row = 2 * (q + (long long)(u >> 1) * kProbeThreads) + (u & 1);
-                const unsigned m = bloom_bits(key[u]);
-                if (row >= r0 && row < r1 && (s_bm[bloom_word(key[u], bmw)] & m) == m) pend |= 1u << u;
+        for (int u = 0; u < kProbeRows; ++u) {
+            const long long row = 2 * (q + (long long)(u >> 1) * kProbeThreads) + (u & 1);
+            const unsigned m = bloom_bits(key[u]);
+            if (row >= r0 && row < r1 && (s_bm[bloom_word(key[u], bmw)] & m) == m) pass |= 1u << u;
+        }
+        // rows that passed the filter go to the candidate list: one shared-memory atomic per warp
+        const int cnt = __popc(pass);
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        int wbase = 0;
+        if (lane == 31 && inc) wbase = atomicAdd(&s_count, inc);
+        int pos = __shfl_sync(0xffffffffu, wbase, 31) + inc - cnt;
+#pragma unroll
+        for (int u = 0; u < kProbeRows; ++u)
+            if (pass >> u & 1u) {
+                out_key[pos] = key[u];
+                out_row[pos] = (int)(2 * (q + (long long)(u >> 1) * kProbeThreads) + (u & 1));
+                ++pos;
             }
-            // rows that passed the filter are resolved in lock step: one slot load per pending row per round
-            unsigned p[kProbeRows];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) a.cand_n[blockIdx.x] = s_count;
+    dbg_mark(a, 1, 2);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_resolve: one thread per candidate row (a read that passed its contig's filter): one 16-byte slot
+// load decides; a hit pushes the row index to every support-read entry of that name with atomicMax
+// -- a later row overrides an earlier one (sv_phasing_fn.py:29) -- and starts pulling the row's tag
+// record into L2 for k_reduce.
+// ------------------------------------------------------------------------------------------
+constexpr int kResolveUnroll = 3;
+
+__global__ void __launch_bounds__(kThreads)
+k_resolve(PhaseArgs a) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int nt = a.n_probe_tiles;
+    int *s_pre = reinterpret_cast<int *>(s_raw);                 // [nt + 1] candidates before each tile
+    for (int i = threadIdx.x; i < nt; i += kThreads) s_pre[i + 1] = a.cand_n[i];
+    if (threadIdx.x == 0) s_pre[0] = 0;
+    __syncthreads();
+    // inclusive scan of s_pre[1..nt] (nt is a few hundred to a few thousand): chunk per thread
+    const int per = (nt + kThreads - 1) / kThreads;
+    const int c0 = min(nt, (int)threadIdx.x * per), c1 = min(nt, c0 + per);
+    int sum = 0;
+    for (int i = c0; i < c1; ++i) sum += s_pre[i + 1];
+    int run = block_scan_exclusive(sum, 0, OpSum(), (int *)nullptr);
+    for (int i = c0; i < c1; ++i) { run += s_pre[i + 1]; s_pre[i + 1] = run; }
+    __syncthreads();
+    const int total = s_pre[nt];
+    const int stride = gridDim.x * kThreads;
+    for (int g0 = blockIdx.x * kThreads + threadIdx.x; g0 < total; g0 += stride * kResolveUnroll) {
+        unsigned long long key[kResolveUnroll];
+        int row[kResolveUnroll], base[kResolveUnroll];
+        unsigned mask[kResolveUnroll], p[kResolveUnroll];
+        unsigned pend = 0;
 #pragma unroll
-            for (int u = 0; u < kProbeRows; ++u) p[u] = slot_hash(key[u]) & mask;
-            while (pend) {
-                uint4 sl[kProbeRows];
+        for (int u = 0; u < kResolveUnroll; ++u) {
+            const int g = g0 + u * stride;
+            if (g >= total) continue;
+            int lo = 0, hi = nt;                                 // tile t with s_pre[t] <= g < s_pre[t+1]
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pre[mid] <= g) lo = mid; else hi = mid; }
+            const ProbeTile t = a.probe_tiles[lo];
+            const long long at = t.r0 + (g - s_pre[lo]);
+            key[u] = a.cand_key[at]; row[u] = a.cand_row[at];
+            base[u] = t.base; mask[u] = (unsigned)t.mask;
+            pend |= 1u << u;
+        }
 #pragma unroll
-                for (int u = 0; u < kProbeRows; ++u)
-                    if (pend >> u & 1u) sl[u] = *reinterpret_cast<const uint4 *>(a.tab + base + p[u]);   // key, first, head
+        for (int u = 0; u < kResolveUnroll; ++u) p[u] = slot_hash(key[u]) & mask[u];
+        while (pend) {                                           // lock step: one slot load per pending candidate
+            uint4 sl[kResolveUnroll];
 #pragma unroll
-                for (int u = 0; u < kProbeRows; ++u) {
-                    if (!(pend >> u & 1u)) continue;
-                    const unsigned long long k = ((unsigned long long)sl[u].y << 32) | sl[u].x;
-                    if (k == key[u]) {
-                        const int row = (int)(2 * (q + (long long)(u >> 1) * kProbeThreads) + (u & 1));
-                        // the tags of a joined row are needed by k_reduce: start pulling them into L2 now
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.read_tag + row));
-                        atomicMax(a.join_row + (int)sl[u].z, row);
-                        for (int h = (int)sl[u].w; h >= 0; h = a.next[h]) atomicMax(a.join_row + h, row);
-                        pend &= ~(1u << u);
-                    } else if (k == kEmptyKey) {
-                        pend &= ~(1u << u);
-                    } else {
-                        p[u] = (p[u] + 1) & mask;
-                    }
+            for (int u = 0; u < kResolveUnroll; ++u)
+                if (pend >> u & 1u) sl[u] = *reinterpret_cast<const uint4 *>(a.tab + base[u] + p[u]);     // key, first, head
+#pragma unroll
+            for (int u = 0; u < kResolveUnroll; ++u) {
+                if (!(pend >> u & 1u)) continue;
+                const unsigned long long k = ((unsigned long long)sl[u].y << 32) | sl[u].x;
+                if (k == key[u]) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.read_tag + row[u]));
+                    atomicMax(a.join_row + (int)sl[u].z, row[u]);
+                    for (int h = (int)sl[u].w; h >= 0; h = a.next[h]) atomicMax(a.join_row + h, row[u]);
+                    pend &= ~(1u << u);
+                } else if (k == kEmptyKey) {
+                    pend &= ~(1u << u);
+                } else {
+                    p[u] = (p[u] + 1) & mask[u];
                 }
             }
         }
-        r0 = r1;
-        if (r0 >= r_end) break;
-        __syncthreads();                                         // the filter is replaced for the next contig
-        do { ++s; } while (__ldg(a.read_off + s + 1) <= r0);     // skip contigs without reads
-        r1 = min(r_end, (long long)__ldg(a.read_off + s + 1));
-        base = __ldg(a.tab_off + s); mask = (unsigned)__ldg(a.tab_mask + s);
-        bmo = __ldg(a.bm_off + s); bmw = (unsigned)__ldg(a.bm_wmask + s);
     }
-    dbg_mark(a, 1, 2);
 }
 
 // ------------------------------------------------------------------------------------------
