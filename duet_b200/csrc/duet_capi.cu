@@ -360,12 +360,15 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     // k_probe tiles: row ranges that never cross a contig, about two per SM in total
     std::vector<ProbeTile> qtiles;
     {
-        const long long want = std::max(1, h->n_sm * kProbeBlocksPerSm);
+        // all tiles resident at once when possible: pieces are rounded DOWN (a contig gets at least one)
+        int live = 0;
+        for (int s = 0; s < ns; ++s) live += h->h_read_off[s + 1] > h->h_read_off[s];
+        const long long want = std::max(1, h->n_sm * kProbeBlocksPerSm - live / 2);
         const long long per = std::max<long long>((R + want - 1) / want, 1);
         for (int s = 0; s < ns; ++s) {
             const long long b0 = h->h_read_off[s], b1 = h->h_read_off[s + 1];
             if (b1 <= b0) continue;
-            const long long pieces = std::max<long long>(1, (b1 - b0 + per / 2) / per);
+            const long long pieces = std::max<long long>(1, (b1 - b0) / per);
             for (long long k = 0; k < pieces; ++k) {
                 long long q0 = b0 + (b1 - b0) * k / pieces, q1 = b0 + (b1 - b0) * (k + 1) / pieces;
                 if (k > 0) q0 += q0 & 1;                         // interior cuts on 16-byte boundaries

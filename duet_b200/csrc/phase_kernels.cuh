@@ -425,6 +425,7 @@ constexpr int kResolveUnroll = 3;
 __global__ void __launch_bounds__(kThreads)
 k_resolve(PhaseArgs a) {
     extern __shared__ __align__(16) unsigned char s_raw[];
+    dbg_mark(a, 1, 4);
     const int nt = a.n_probe_tiles;
     int *s_pre = reinterpret_cast<int *>(s_raw);                 // [nt + 1] candidates before each tile
     for (int i = threadIdx.x; i < nt; i += kThreads) s_pre[i + 1] = a.cand_n[i];
@@ -440,6 +441,7 @@ k_resolve(PhaseArgs a) {
     __syncthreads();
     const int total = s_pre[nt];
     const int stride = gridDim.x * kThreads;
+    dbg_mark(a, 1, 5);
     for (int g0 = blockIdx.x * kThreads + threadIdx.x; g0 < total; g0 += stride * kResolveUnroll) {
         unsigned long long key[kResolveUnroll];
         int row[kResolveUnroll], base[kResolveUnroll];
@@ -481,6 +483,7 @@ k_resolve(PhaseArgs a) {
             }
         }
     }
+    dbg_mark(a, 1, 6);
 }
 
 // ------------------------------------------------------------------------------------------
