@@ -471,7 +471,7 @@ k_resolve(PhaseArgs a) {
                 if (!(pend >> u & 1u)) continue;
                 const unsigned long long k = ((unsigned long long)sl[u].y << 32) | sl[u].x;
                 if (k == key[u]) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.read_tag + row[u]));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.read_tag + row[u]));     // k_reduce needs it next
                     atomicMax(a.join_row + (int)sl[u].z, row[u]);
                     for (int h = (int)sl[u].w; h >= 0; h = a.next[h]) atomicMax(a.join_row + h, row[u]);
                     pend &= ~(1u << u);
