@@ -66,6 +66,7 @@ struct duet_handle {
     DevBuf d_read_off, d_sv_off, d_join_off, d_sv_shard, d_tab_off, d_tab_mask, d_done, d_c2;
     DevBuf d_btiles, d_rtiles, d_ptiles, d_qtiles, d_dbg, d_cand_key, d_cand_row, d_cand_n;
     int probe_grid = 0;
+    int reduce_lanes = kReduceLanesSparse;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     bool dbg_on = false;
@@ -166,7 +167,8 @@ int duet_create(int device_id, duet_handle **out) {
         // one shared-memory carveout for all four kernels: switching it between launches drains the SMs
         cudaFuncSetAttribute(k_build, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_probe, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(k_reduce, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_reduce<kReduceLanesSparse>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_reduce<kReduceLanesDense>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_predict, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_resolve, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_init, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -350,7 +352,8 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         }
         return v;
     };
-    std::vector<SvTile> rtiles = sv_tiles(kReducePerBlock), ptiles = sv_tiles(kPredictPerBlock);
+    h->reduce_lanes = (S > 0 && J / std::max<long long>(S, 1) > 32) ? kReduceLanesDense : kReduceLanesSparse;
+    std::vector<SvTile> rtiles = sv_tiles(kThreads / h->reduce_lanes), ptiles = sv_tiles(kPredictPerBlock);
     if ((rc = stage(h, h->d_btiles, btiles.data(), sizeof(BuildTile) * btiles.size(), DUET_MEM_HOST, &dv))) return rc;
     a.build_tiles = static_cast<const BuildTile *>(dv);
     if ((rc = stage(h, h->d_rtiles, rtiles.data(), sizeof(SvTile) * rtiles.size(), DUET_MEM_HOST, &dv))) return rc;
@@ -465,7 +468,9 @@ static void launch_all(duet_handle *h, cudaStream_t st, bool marks) {
     }
     mark(EV_K2);
     if (S) {
-        k_reduce<<<(S + kReducePerBlock - 1) / kReducePerBlock, kThreads, 0, st>>>(a);
+        const int per = kThreads / h->reduce_lanes;
+        if (h->reduce_lanes == kReduceLanesDense) k_reduce<kReduceLanesDense><<<(S + per - 1) / per, kThreads, 0, st>>>(a);
+        else k_reduce<kReduceLanesSparse><<<(S + per - 1) / per, kThreads, 0, st>>>(a);
         ++h->launches;
     }
     mark(EV_K3);

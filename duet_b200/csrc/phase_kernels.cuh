@@ -30,8 +30,8 @@ constexpr long long kNoCand = 0x7FFFFFFFFFFFFFFFll;   // "no one-PS candidate" (
 constexpr long long kNone = (long long)0x8000000000000000ull;
 constexpr int kThreads = 256;                         // every kernel
 constexpr int kMaxDistinct = 32;                      // distinct in-set PS per SV handled in smem
-constexpr int kReduceLanes = 8;                       // lanes per SV in k_reduce
-constexpr int kReducePerBlock = kThreads / kReduceLanes;
+constexpr int kReduceLanesSparse = 8;                 // lanes per SV in k_reduce, typical support lists (~16 reads)
+constexpr int kReduceLanesDense = 32;                 // ... dense lists (mean > 32 reads)
 constexpr int kPredictPerBlock = 64;
 constexpr int kSortSmemBytes = 16384;                 // slow-path sort tile in shared memory
 constexpr int kBloomMaxWords = 32768;                 // 128 KB of shared memory per shard filter
@@ -71,7 +71,7 @@ struct PhaseArgs {
     const long long *join_off;   // [n_shards+1] csr_off at the shard boundaries (derived at upload)
     const int *sv_shard;         // [S] shard of each SV (derived at upload)
     const BuildTile *build_tiles;   // [ceil(J / 256)]
-    const SvTile *reduce_tiles;     // [ceil(S / kReducePerBlock)]
+    const SvTile *reduce_tiles;     // [ceil(S / (kThreads / lanes per SV))]
     const SvTile *predict_tiles;    // [ceil(S / kPredictPerBlock)]
     const ProbeTile *probe_tiles;   // [n_probe_tiles] = k_probe grid
     int n_probe_tiles;
@@ -493,16 +493,20 @@ k_resolve(PhaseArgs a) {
 // ------------------------------------------------------------------------------------------
 // Small shards (<= kSortSmemBytes / 8 SVs): the distinct candidates are collected in a shared-memory
 // hash set (a contig has a few hundred phase sets however many SVs it has), and only those are sorted.
+constexpr int kOnepsSmall = 4096;                                // SVs per shard handled by the hash-set path
+
+template <bool kStaged> __device__ void oneps_block(const PhaseArgs &a, int s, long long *smem_tile);
+
 __device__ void oneps_block_small(const PhaseArgs &a, int s, long long *smem_tile) {
     constexpr int kSlots = kSortSmemBytes / 4;                   // 4096 ints
     constexpr int kPer = kSlots / kThreads;                      // 16 slots per thread
-    __shared__ int s_has_min;
+    __shared__ int s_has_min, s_overflow;
     int *tab = reinterpret_cast<int *>(smem_tile);
     const int b = (int)a.sv_off[s], n = (int)a.sv_off[s + 1] - b;
     for (int i = threadIdx.x; i < kSlots; i += kThreads) tab[i] = INT32_MIN;
-    if (threadIdx.x == 0) s_has_min = 0;
+    if (threadIdx.x == 0) { s_has_min = 0; s_overflow = 0; }
     __syncthreads();
-    constexpr int kLoads = kSortSmemBytes / 8 / kThreads;        // candidates per thread, requested together
+    constexpr int kLoads = kOnepsSmall / kThreads;               // candidates per thread, requested together
     long long cv[kLoads];
 #pragma unroll
     for (int u = 0; u < kLoads; ++u) {
@@ -513,15 +517,18 @@ __device__ void oneps_block_small(const PhaseArgs &a, int s, long long *smem_til
     for (int u = 0; u < kLoads; ++u) {
         if (cv[u] == kNoCand) continue;
         const int x = (int)cv[u];
-        if (x == INT32_MIN) { s_has_min = 1; continue; }         // the empty marker itself: tracked aside
+        if (x == INT32_MIN) { atomicMax(&s_has_min, 1); continue; }   // the empty marker itself: tracked aside
         unsigned h = ((unsigned)x * 2654435761u) >> 20;
-        for (;;) {
+        int tries = 0;
+        for (; tries < kSlots; ++tries) {
             const int prev = atomicCAS(tab + h, INT32_MIN, x);
             if (prev == INT32_MIN || prev == x) break;
             h = (h + 1) & (kSlots - 1);
         }
+        if (tries == kSlots) s_overflow = 1;                     // more distinct phase sets than slots
     }
     __syncthreads();
+    if (s_overflow) { __syncthreads(); oneps_block<false>(a, s, smem_tile); return; }
     int found[kPer], cnt = 0;
 #pragma unroll
     for (int u = 0; u < kPer; ++u) {
@@ -618,7 +625,7 @@ __device__ void oneps_block(const PhaseArgs &a, int s, long long *smem_tile) {
 }
 
 __device__ __forceinline__ void oneps_any(const PhaseArgs &a, int s, long long *smem_tile) {
-    if ((int)(a.sv_off[s + 1] - a.sv_off[s]) * (int)sizeof(long long) <= kSortSmemBytes) oneps_block_small(a, s, smem_tile);
+    if ((int)(a.sv_off[s + 1] - a.sv_off[s]) <= kOnepsSmall) oneps_block_small(a, s, smem_tile);
     else oneps_block<false>(a, s, smem_tile);
 }
 
@@ -672,9 +679,10 @@ __device__ __forceinline__ void c2_update(C2Group &g, unsigned gmask, bool q, in
     __syncwarp(gmask);
 }
 
+template <int G>
 __global__ void __launch_bounds__(kThreads, 6)
 k_reduce(PhaseArgs a) {
-    constexpr int G = kReduceLanes;
+    constexpr int kReducePerBlock = kThreads / G;
     dbg_mark(a, 2, 0);
     __shared__ __align__(16) long long s_tile[kSortSmemBytes / 8];
     __shared__ C2Group s_c2[kReducePerBlock];
@@ -682,7 +690,7 @@ k_reduce(PhaseArgs a) {
     __shared__ int s_n;
     const SvTile tile = threadIdx.x == 0 ? a.reduce_tiles[blockIdx.x] : SvTile{0, 0, 0, 0};   // for the credit, requested early
     const int lane = threadIdx.x % G, grp = threadIdx.x / G;
-    const unsigned gmask = ((1u << G) - 1u) << ((threadIdx.x & 31) / G * G);
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) / G * G));
     const int sv0 = blockIdx.x * kReducePerBlock;
     const int sv1 = min(a.n_svs, sv0 + kReducePerBlock);
     const int sv = sv0 + grp;
@@ -1042,7 +1050,7 @@ __device__ __forceinline__ long long order_key(const PhaseArgs &a, int sv, int c
     return (long long)((grp << 34) | (upos << 2) | (unsigned long long)cls);      // < 2^50
 }
 
-constexpr int kOrdStage = 8;
+constexpr int kOrdStage = 16;
 
 // shards of up to kThreads*kOrdStage SVs: every thread fetches its chunk's per-SV state with
 // independent loads (one round trip), everything after that runs out of registers
@@ -1102,8 +1110,9 @@ __device__ void order_block_small(const PhaseArgs &a, int s, long long *smem_til
         for (int u = 0; u < kOrdStage; ++u)
             if (key[u] != kNone) a.order[b + w++] = b + c0 + u;
     } else {                                         // sort (key, index in shard) packed in 62 bits
-        unsigned long long *v = reinterpret_cast<unsigned long long *>(smem_tile);
         const int n_pad = next_pow2(max(n_emit, 1));
+        unsigned long long *v = n_pad * 8 <= kSortSmemBytes ? reinterpret_cast<unsigned long long *>(smem_tile)
+                                                            : reinterpret_cast<unsigned long long *>(a.sort_scratch) + 4ll * b;
 #pragma unroll
         for (int u = 0; u < kOrdStage; ++u)
             if (key[u] != kNone) v[w++] = ((unsigned long long)key[u] << 12) | (unsigned)(c0 + u);
