@@ -1050,10 +1050,10 @@ __device__ __forceinline__ long long order_key(const PhaseArgs &a, int sv, int c
     return (long long)((grp << 34) | (upos << 2) | (unsigned long long)cls);      // < 2^50
 }
 
-constexpr int kOrdStage = 16;
 
 // shards of up to kThreads*kOrdStage SVs: every thread fetches its chunk's per-SV state with
 // independent loads (one round trip), everything after that runs out of registers
+template <int kOrdStage>
 __device__ void order_block_small(const PhaseArgs &a, int s, long long *smem_tile) {
     __shared__ unsigned long long s_cnt[DUET_N_COUNTERS];
     const int b = (int)a.sv_off[s], n = (int)a.sv_off[s + 1] - b;
@@ -1205,8 +1205,10 @@ __device__ void order_block_big(const PhaseArgs &a, int s, long long *smem_tile)
 }
 
 __device__ __forceinline__ void order_block(const PhaseArgs &a, int s, long long *smem_tile) {
-    // the packed sort key keeps 12 bits for the index in the shard and the tile holds 2048 keys
-    if ((int)(a.sv_off[s + 1] - a.sv_off[s]) <= kThreads * kOrdStage) order_block_small(a, s, smem_tile);
+    // register-staged paths (the packed sort key keeps 12 bits for the index in the shard)
+    const int n = (int)(a.sv_off[s + 1] - a.sv_off[s]);
+    if (n <= kThreads * 8) order_block_small<8>(a, s, smem_tile);
+    else if (n <= kThreads * 16) order_block_small<16>(a, s, smem_tile);
     else order_block_big(a, s, smem_tile);
 }
 
