@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libduet_b200.so")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB + ".tmp", *_sources()]
+    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB + ".tmp", *_sources(), "-lz"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)

@@ -127,7 +127,7 @@ def sv_phasing_sharded(home, svlen_thres, suppread_thres, thread, include_all_ct
     for ch in mine:                                                    # the heavy decode: own contigs only
         ctg = chrom_list[ch]
         path = next((p for p in (sam_home + "chr" + ctg + ".bam", sam_home + ctg + ".bam") if os.path.exists(p)), None)
-        read_hap.append(fn.decode_sam_text(fn._sam_text(path, thread)) if path else fn.ReadColumns.empty())
+        read_hap.append(fn.load_hap_bam(path, thread) if path else fn.ReadColumns.empty())
     batch = fn.build_batch([chrom_list[ch] for ch in mine], read_hap, [comp_call[ch] for ch in mine])
     res = phase_fn(batch, svlen_thres, suppread_thres)
 

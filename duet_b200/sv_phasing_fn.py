@@ -95,6 +95,45 @@ def decode_sam_text(text: bytes) -> ReadColumns:
     return ReadColumns(key[:k].copy(), tag[:k].copy(), n_lines.value)
 
 
+def decode_bam(data: bytes) -> ReadColumns:
+    """A whole BGZF/BAM file -> columns, natively (csrc/bam_decode.cpp): same rows, same values as
+    `samtools view` piped through decode_sam_text."""
+    lib = _lib.load()
+    key_p, tag_p = C.c_void_p(), C.c_void_p()
+    n_rows, n_rec, err = C.c_int64(), C.c_int64(), C.c_int64()
+    buf = (C.c_char * max(len(data), 1)).from_buffer_copy(data)
+    rc = lib.duet_decode_bam(buf, len(data), C.byref(key_p), C.byref(tag_p), C.byref(n_rows), C.byref(n_rec), C.byref(err))
+    if rc != _lib.DUET_OK:
+        exc, msg = _DECODE_EXC.get(rc, (ValueError, f"not a readable BAM (decode error {rc})"))
+        if exc is UnicodeDecodeError:
+            raise UnicodeDecodeError("ascii", b"\xff", 0, 1, f"ordinal not in range(128) (record {err.value})")
+        raise exc(f"{msg} (alignment record {err.value})")
+    k = n_rows.value
+    try:
+        key = np.ctypeslib.as_array(C.cast(key_p, C.POINTER(C.c_uint64)), shape=(max(k, 1),))[:k].copy()
+        raw = np.ctypeslib.as_array(C.cast(tag_p, C.POINTER(C.c_uint8)), shape=(max(k, 1) * 16,))[:k * 16].copy()
+    finally:
+        lib.duet_free(key_p)
+        lib.duet_free(tag_p)
+    return ReadColumns(key, raw.view(TAG_DTYPE), n_rec.value)
+
+
+def load_hap_bam(path: str, thread: int) -> ReadColumns:
+    """One per-contig haplotagged BAM -> columns.  BGZF/BAM files are decoded natively; anything
+    else gzip-compressed goes through `samtools view` like the reference (sv_phasing_fn.py:25);
+    uncompressed files are SAM text already."""
+    with open(path, "rb") as fh:
+        data = fh.read()
+    if data[:2] != b"\x1f\x8b":
+        return decode_sam_text(data)
+    try:
+        return decode_bam(data)
+    except ValueError as e:
+        if "not a readable BAM" not in str(e):
+            raise
+    return decode_sam_text(subprocess.check_output(shlex.split("samtools view -@" + str(thread) + " " + path)))
+
+
 def _sam_text(path: str, thread: int) -> bytes:
     """`samtools view -@thread <bam>` (sv_phasing_fn.py:25).  A file that is not gzip/BGZF already
     is SAM text and is read directly (no samtools needed)."""
@@ -110,18 +149,22 @@ def read_hap_bam(path, thread, include_all_ctgs):
     (sv_phasing_fn.py:19-24).  `path` = '<home>/snp_phasing/'."""
     logging.info("extract SNP signatures")
     chrom_list = init_chrom_list(include_all_ctgs, path[:len(path) - 13])
-    read_hap = []
+    paths = []
     for ctg in chrom_list:
         if os.path.exists(path + "chr" + ctg + ".bam"):
-            hap_bam_path = path + "chr" + ctg + ".bam"
+            paths.append(path + "chr" + ctg + ".bam")
         elif os.path.exists(path + ctg + ".bam"):
-            hap_bam_path = path + ctg + ".bam"
+            paths.append(path + ctg + ".bam")
         else:
-            read_hap.append(ReadColumns.empty())
-            continue
-        cols = decode_sam_text(_sam_text(hap_bam_path, thread))
-        read_hap.append(cols)
-        logging.info(("  signatures extracted from " if cols.n_lines else "  no signature from ") + ctg)
+            paths.append(None)
+    # the reference gives its `thread` count to samtools; here the contigs are decoded in parallel
+    # (the C++ scanners release the GIL)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=max(1, int(thread))) as pool:
+        read_hap = list(pool.map(lambda p: load_hap_bam(p, 1) if p else ReadColumns.empty(), paths))
+    for ctg, cols, p in zip(chrom_list, read_hap, paths):
+        if p:
+            logging.info(("  signatures extracted from " if cols.n_lines else "  no signature from ") + ctg)
     return read_hap
 
 

@@ -223,7 +223,8 @@ enum {
     DUET_DECODE_ERR_VALUE = 21,    /* int() of a tag value fails -> ValueError                          */
     DUET_DECODE_ERR_ASCII = 22,    /* byte >= 0x80 -> UnicodeDecodeError (.decode('ascii'), :25)        */
     DUET_DECODE_ERR_RANGE = 23,    /* HP outside 0..255 or PS/PC outside int32 (BAM aux ints are 32 bit) */
-    DUET_DECODE_ERR_CAPACITY = 24  /* output arrays too small                                           */
+    DUET_DECODE_ERR_CAPACITY = 24, /* output arrays too small / out of memory                           */
+    DUET_DECODE_ERR_FORMAT = 25    /* not a BGZF-compressed BAM / truncated record                       */
 };
 
 /* 128-bit name hash (duet_b200/namehash.py): name i is buf[off[i] .. off[i+1]).  key = lo,
@@ -240,6 +241,14 @@ void duet_pack_tags(int64_t n, const uint8_t *hp, const int32_t *ps, const int32
 int duet_decode_sam_text(const char *text, int64_t len, int64_t cap, uint64_t *key, duet_read_tag *tag,
                          int64_t *n_rows, int64_t *n_lines, int64_t *err_line);
 int64_t duet_count_lines(const char *text, int64_t len);
+
+/* A whole haplotagged BAM file (BGZF bytes) -> the same columns `samtools view` + duet_decode_sam_text
+ * would give: every record's last three text tokens are reconstructed and the reference's rule
+ * (sv_phasing_fn.py:28-29) is applied to them.  *key_out / *tag_out are malloc'ed; release them with
+ * duet_free.  On error *err_record is the 0-based record number. */
+int duet_decode_bam(const unsigned char *data, int64_t len, uint64_t **key_out, duet_read_tag **tag_out,
+                    int64_t *n_rows, int64_t *n_records, int64_t *err_record);
+void duet_free(void *p);
 int duet_get_timings(duet_handle *h, duet_timings *t);
 /* Number of kernels this library launched on the handle since creation (bench "gpu_launches"). */
 int64_t duet_launch_count(const duet_handle *h);

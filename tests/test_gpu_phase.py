@@ -263,3 +263,29 @@ def test_dropin_against_reference_golden(name, golden_workdir):
         assert (res.totsc1[i], res.totsc2[i]) == (f["hap1_totsc"], f["hap2_totsc"])
         for nm in _lib.FEATURE_NAMES:
             assert float(res.feature(nm)[i]) == float(f[nm])
+
+
+def test_dropin_reads_real_bam(golden_workdir):
+    """Same golden case with the per-contig haplotagged files as real BGZF/BAM: decoded natively
+    (no samtools), output byte-identical to the reference's."""
+    import os
+    from duet_b200 import sv_phasing
+    from util_bam import record, write_bam
+    case, home = golden_workdir("cutesv_3ctg")
+    for fn in os.listdir(home + "/snp_phasing"):
+        path = os.path.join(home, "snp_phasing", fn)
+        recs = []
+        with open(path) as f:
+            for line in f:
+                s = line.rstrip("\n").split("\t")
+                aux = []
+                for a in s[11:]:
+                    tag, typ, val = a.split(":", 2)
+                    aux.append((tag, typ, int(val)) if typ == "i" else (tag, typ, val))
+                recs.append(record(s[0], int(s[3]), s[9], s[10], aux)[0])
+        write_bam(path, recs, block=30000)
+        with open(path, "rb") as f:
+            assert f.read(2) == b"\x1f\x8b"
+    sv_phasing.sv_phasing(home, case["svlen_thres"], case["suppread_thres"], 4, False)
+    with open(home + "/phased_sv.vcf") as f:
+        assert f.read() == case["phased_sv_vcf"]

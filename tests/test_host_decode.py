@@ -129,3 +129,62 @@ def test_sam_text_quirks():
     assert rc.n_lines == 3 and len(rc) == 2
     assert (rc.hp.tolist(), rc.pc.tolist(), rc.ps.tolist()) == ([2, 10], [30, 7], [400, -9])
     assert rc.key[0] == namehash.hash128("a")[0] and rc.key[1] == namehash.hash128("c")[0]
+
+
+# ---- native BAM reader vs the SAM-text path (records written by tests/util_bam.py) -------------------
+def _bam_and_text(rows):
+    from util_bam import record
+    recs, text = [], []
+    for r in rows:
+        b, t = record(*r)
+        recs.append(b)
+        text.append(t)
+    return recs, "".join(text).encode()
+
+
+def test_bam_reader_equals_text_path(tmp_path):
+    from util_bam import write_bam
+    s = synth.make_sample(4, contigs=["21"], n_reads=5000, n_svs=10, bp_per_read=700)
+    c = s.contigs[0]
+    names = synth.name_strings(c.row_id)
+    rows = []
+    for i, nm in enumerate(names):
+        aux = [("NM", "C", 3), ("MD", "Z", "4"), ("AS", "i", 8)]
+        if c.row_tagged[i]:
+            aux += [("HP", "C", int(c.row_hp[i])), ("PC", "I" if i % 3 else "S", int(min(c.row_pc[i], 60000))), ("PS", "i", int(c.row_ps[i]))]
+        rows.append((nm, int(c.row_pos[i]), "ACGT", "IIII", aux))
+    recs, text = _bam_and_text(rows)
+    path = str(tmp_path / "21.bam")
+    write_bam(path, recs, block=20000)
+    a = sv_phasing_fn.load_hap_bam(path, 1)                  # gzip magic -> native BAM decode
+    b = sv_phasing_fn.decode_sam_text(text)
+    assert a.n_lines == b.n_lines == len(rows) and len(a) == len(b) == int(c.row_tagged.sum())
+    assert np.array_equal(a.key, b.key) and np.array_equal(a.tag, b.tag)
+
+
+def test_bam_reader_text_quirks(tmp_path):
+    """The reference looks at the last three WHITESPACE tokens of the text line, whatever they are."""
+    from util_bam import write_bam
+    rows = [
+        ("tagged", 5, "ACGT", "IIII", [("HP", "i", 2), ("PC", "i", 30), ("PS", "i", 400)]),
+        ("tags_not_last", 6, "ACGT", "IIII", [("HP", "i", 1), ("PC", "i", 7), ("PS", "i", 9), ("NM", "i", 0)]),
+        ("blank_in_string", 7, "ACGT", "IIII", [("HP", "i", 1), ("CO", "Z", "7 PC:i:5 PS:i:6")]),     # tokens: CO:Z:7 PC:i:5 PS:i:6
+        ("few_aux", 8, "ACGT", "IIII", [("PS", "i", 9)]),                                            # s[-2] is QUAL
+        ("no_aux", 9, "AC", "*", []),
+        ("float_hp", 10, "ACGT", "IIII", [("HP", "f", 2.0), ("PC", "i", 1), ("PS", "i", 3)]),        # int('2') works
+        ("array_last", 11, "ACGT", "IIII", [("HP", "i", 1), ("PC", "i", 2), ("ZB", "B", ("c", [1, 2]))]),
+    ]
+    recs, text = _bam_and_text(rows)
+    path = str(tmp_path / "x.bam")
+    write_bam(path, recs)
+    with pytest.raises(ValueError):                          # ZB:B:c,1,2 -> int('c,1,2') fails, in both paths
+        sv_phasing_fn.decode_sam_text(text)
+    with pytest.raises(ValueError):
+        sv_phasing_fn.load_hap_bam(path, 1)
+    recs, text = _bam_and_text(rows[:-1])
+    write_bam(path, recs)
+    a, b = sv_phasing_fn.load_hap_bam(path, 1), sv_phasing_fn.decode_sam_text(text)
+    assert len(b) == 3                                       # tagged, blank_in_string (HP 7 from 'CO:Z:7'), float_hp
+    assert b.hp.tolist() == [2, 7, 2] and b.pc.tolist() == [30, 5, 1] and b.ps.tolist() == [400, 6, 3]
+    assert np.array_equal(a.key, b.key) and np.array_equal(a.tag, b.tag)
+    assert a.n_lines == b.n_lines == 6
