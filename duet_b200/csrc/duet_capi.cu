@@ -44,6 +44,8 @@ enum { EV_H2D0, EV_H2D1, EV_X0, EV_K0, EV_K1, EV_K2, EV_K3, EV_K4, EV_D2H0, EV_D
 struct duet_handle {
     int device = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t side_stream = nullptr;    // second branch of the per-call graph
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[EV_COUNT] = {};
     duet_thresholds thr;
@@ -158,6 +160,9 @@ int duet_create(int device_id, duet_handle **out) {
         return fail(nullptr, DUET_ERR_CUDA, msg);
     }
     h->stream = h->own_stream;
+    cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     for (auto &ev : h->cl_ev) cudaEventCreate(&ev);
     {   // fails here, loudly, if the image was not built for this device (sm_100a only)
@@ -165,7 +170,8 @@ int duet_create(int device_id, duet_handle **out) {
         cudaFuncGetAttributes(&fa, k_probe);
         cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, kBloomMaxWords * 4);
         // one shared-memory carveout for all four kernels: switching it between launches drains the SMs
-        cudaFuncSetAttribute(k_build, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_bloom, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_table, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_probe, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_reduce<kReduceLanesSparse>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_reduce<kReduceLanesDense>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -201,6 +207,9 @@ void duet_destroy(duet_handle *h) {
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->graph) cudaGraphDestroy(h->graph);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -449,22 +458,45 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     return DUET_OK;
 }
 
-// the five launches of one call; with `marks` an event is recorded after each kernel
-static void launch_all(duet_handle *h, cudaStream_t st, bool marks) {
+// The launches of one call.  Dependencies: filter init -> k_bloom -> k_probe (the read stream needs only the
+// filter) and table init -> k_table (slot inserts) are independent branches that meet at k_resolve.
+// `concurrent`: the two branches run on two streams (fork/join with events; this is what the CUDA graph
+// captures).  Otherwise everything is serial on `st` and, with `marks`, an event follows each stage.
+static void launch_all(duet_handle *h, cudaStream_t st, bool marks, bool concurrent) {
     auto mark = [&](int ev) { if (marks) cudaEventRecord(h->ev[ev], st); };
     const PhaseArgs &a = h->a;
     const int S = a.n_svs;
-    if (a.n_joins) {
-        k_init<<<h->n_sm * 4, kThreads, 0, st>>>(a, h->n_slots, h->n_bm_words);
+    const bool join = a.n_joins > 0, probe = a.n_reads && a.n_joins;
+    const int build_blocks = (int)((a.n_joins + kBuildTile - 1) / kBuildTile);
+    if (join) {
+        cudaStream_t tb = st;                       // stream of the table branch
+        if (concurrent) {
+            tb = h->side_stream;
+            cudaEventRecord(h->ev_fork, st);
+            cudaStreamWaitEvent(tb, h->ev_fork, 0);
+        }
+        k_init<<<h->n_sm * 2, kThreads, 0, st>>>(a, h->n_slots, h->n_bm_words, kInitFilter);
+        k_init<<<h->n_sm * 4, kThreads, 0, tb>>>(a, h->n_slots, h->n_bm_words, kInitTable);
         mark(EV_K0);
-        k_build<<<(a.n_joins + kBuildTile - 1) / kBuildTile, kThreads, 0, st>>>(a);
-        h->launches += 2;
-    }
-    mark(EV_K1);
-    if (a.n_reads && a.n_joins) {
-        k_probe<<<h->probe_grid, kProbeThreads, h->probe_smem, st>>>(a);
-        k_resolve<<<h->n_sm * 4, kThreads, (size_t)(h->probe_grid + 1) * 4, st>>>(a);
-        h->launches += 2;
+        k_bloom<<<build_blocks, kThreads, 0, st>>>(a);
+        k_table<<<build_blocks, kThreads, 0, tb>>>(a);
+        h->launches += 4;
+        mark(EV_K1);
+        if (probe) {
+            k_probe<<<h->probe_grid, kProbeThreads, h->probe_smem, st>>>(a);
+            ++h->launches;
+        }
+        if (concurrent) {
+            cudaEventRecord(h->ev_join, tb);
+            cudaStreamWaitEvent(st, h->ev_join, 0);
+        }
+        if (probe) {
+            k_resolve<<<h->n_sm * 4, kThreads, (size_t)(h->probe_grid + 1) * 4, st>>>(a);
+            ++h->launches;
+        }
+    } else {
+        mark(EV_K0);
+        mark(EV_K1);
     }
     mark(EV_K2);
     if (S) {
@@ -492,13 +524,13 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
     h->per_kernel = per_kernel != 0;
     CU(h, cudaEventRecord(h->ev[EV_X0], st));
     if (h->per_kernel) {
-        launch_all(h, st, true);
+        launch_all(h, st, true, false);
     } else {
         // the launch sequence of a staged batch never changes: replay it as a CUDA graph
         if (!h->graph_exec) {
             const int64_t before = h->launches;
             if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-                launch_all(h, st, false);
+                launch_all(h, st, false, true);
                 if (cudaStreamEndCapture(st, &h->graph) != cudaSuccess ||
                     cudaGraphInstantiate(&h->graph_exec, h->graph, 0) != cudaSuccess) {
                     h->graph_exec = nullptr;
@@ -509,9 +541,9 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
         }
         if (h->graph_exec) {
             CU(h, cudaGraphLaunch(h->graph_exec, st));
-            h->launches += (h->a.n_joins ? 2 : 0) + (h->a.n_reads && h->a.n_joins ? 2 : 0) + (h->a.n_svs ? 2 : 0);
+            h->launches += (h->a.n_joins ? 4 : 0) + (h->a.n_reads && h->a.n_joins ? 2 : 0) + (h->a.n_svs ? 2 : 0);
         } else {
-            launch_all(h, st, false);
+            launch_all(h, st, false, false);
         }
     }
     CU(h, cudaEventRecord(h->ev[EV_K4], st));

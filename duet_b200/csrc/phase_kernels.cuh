@@ -249,17 +249,23 @@ __device__ __forceinline__ void tile_shards(const long long *__restrict__ off, i
 // join results -1.  Sequential 16-byte stores also leave all three L2 resident for the random
 // traffic of k_build / k_probe that follows.
 // ------------------------------------------------------------------------------------------
+enum { kInitTable = 1, kInitFilter = 2 };
+
 __global__ void __launch_bounds__(kThreads)
-k_init(PhaseArgs a, long long n_slots, long long n_bm_words) {
+k_init(PhaseArgs a, long long n_slots, long long n_bm_words, int what) {
     const long long stride = (long long)gridDim.x * kThreads;
     const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
-    uint4 *tab = reinterpret_cast<uint4 *>(a.tab);
     const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0u, 0u, 0u, 0u);
-    for (long long i = t; i < n_slots; i += stride) tab[i] = ones;
-    uint4 *bm = reinterpret_cast<uint4 *>(a.bitmap);
-    for (long long i = t; i < n_bm_words / 4; i += stride) bm[i] = zero;
-    uint4 *jr = reinterpret_cast<uint4 *>(a.join_row);                       // allocation padded to 16 bytes
-    for (long long i = t; i < ((long long)a.n_joins + 3) / 4; i += stride) jr[i] = ones;
+    if (what & kInitTable) {
+        uint4 *tab = reinterpret_cast<uint4 *>(a.tab);
+        for (long long i = t; i < n_slots; i += stride) tab[i] = ones;
+        uint4 *jr = reinterpret_cast<uint4 *>(a.join_row);                   // allocation padded to 16 bytes
+        for (long long i = t; i < ((long long)a.n_joins + 3) / 4; i += stride) jr[i] = ones;
+    }
+    if (what & kInitFilter) {
+        uint4 *bm = reinterpret_cast<uint4 *>(a.bitmap);
+        for (long long i = t; i < n_bm_words / 4; i += stride) bm[i] = zero;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -273,16 +279,51 @@ __device__ __forceinline__ unsigned bloom_bits(unsigned long long key) {
 }
 
 // ------------------------------------------------------------------------------------------
-// k_build: one thread per support-read name: claim a slot (CAS), set the filter bits, reset the
-// join result.  The first entry of a name owns the slot (plain stores, nothing waited for);
-// further entries with the same name chain themselves behind it.
-// Dependent chain of a thread: [key, tile descriptor] -> CAS (-> CAS on a collision) -> stores.
+// The build side, two kernels so that the probe stream (which needs only the filter) overlaps the
+// slot inserts: k_bloom sets the filter bits, k_table claims the slots.
+// Dependent chain of a k_table thread: [key, tile descriptor] -> CAS (-> CAS on a collision) -> stores.
 // ------------------------------------------------------------------------------------------
 constexpr int kBuildPerThread = 2;
 constexpr int kBuildTile = kThreads * kBuildPerThread;
 
+// which shard (table range, filter range) support-read entry j of this tile belongs to
+__device__ __forceinline__ void build_where(const PhaseArgs &a, const BuildTile &t, long long j, int &base,
+                                            unsigned &mask, int &bmo, unsigned &bmw) {
+    base = t.base; mask = (unsigned)t.mask; bmo = t.bmo; bmw = (unsigned)t.bmw;
+    if (t.lo != t.hi) {                                          // the tile straddles a contig boundary
+        const int s = t.lo + shard_of(a.join_off + t.lo, t.hi - t.lo + 1, j);
+        base = __ldg(a.tab_off + s); mask = (unsigned)__ldg(a.tab_mask + s);
+        bmo = __ldg(a.bm_off + s); bmw = (unsigned)__ldg(a.bm_wmask + s);
+    }
+}
+
+// k_bloom: two filter bits per support-read name, fire-and-forget (the probe stream only needs these,
+// so it can start while k_table is still inserting)
 __global__ void __launch_bounds__(kThreads)
-k_build(PhaseArgs a) {
+k_bloom(PhaseArgs a) {
+    const long long j0 = (long long)blockIdx.x * kBuildTile + threadIdx.x;
+    unsigned long long key[kBuildPerThread];
+#pragma unroll
+    for (int u = 0; u < kBuildPerThread; ++u) {
+        const long long j = j0 + u * kThreads;
+        key[u] = j < a.n_joins ? __ldg(a.csr_key + j) : 0ull;
+    }
+    const BuildTile t = a.build_tiles[blockIdx.x];
+#pragma unroll
+    for (int u = 0; u < kBuildPerThread; ++u) {
+        const long long j = j0 + u * kThreads;
+        if (j >= a.n_joins) continue;
+        int base, bmo;
+        unsigned mask, bmw;
+        build_where(a, t, j, base, mask, bmo, bmw);
+        atomicOr(a.bitmap + bmo + (int)bloom_word(key[u], bmw), bloom_bits(key[u]));
+    }
+}
+
+// k_table: claim a slot per name (CAS; both names of a thread in flight together); the first entry of
+// a name owns the slot, further entries chain themselves behind it
+__global__ void __launch_bounds__(kThreads)
+k_table(PhaseArgs a) {
     dbg_mark(a, 0, 0);
     const long long j0 = (long long)blockIdx.x * kBuildTile + threadIdx.x;
     unsigned long long key[kBuildPerThread];
@@ -299,19 +340,13 @@ k_build(PhaseArgs a) {
     for (int u = 0; u < kBuildPerThread; ++u) {
         const long long j = j0 + u * kThreads;
         if (j >= a.n_joins) continue;
-        base[u] = t.base; mask[u] = (unsigned)t.mask;
-        int bmo = t.bmo;
-        unsigned bmw = (unsigned)t.bmw;
-        if (t.lo != t.hi) {                                      // the tile straddles a contig boundary
-            const int s = t.lo + shard_of(a.join_off + t.lo, t.hi - t.lo + 1, j);
-            base[u] = __ldg(a.tab_off + s); mask[u] = (unsigned)__ldg(a.tab_mask + s);
-            bmo = __ldg(a.bm_off + s); bmw = (unsigned)__ldg(a.bm_wmask + s);
-        }
-        atomicOr(a.bitmap + bmo + (int)bloom_word(key[u], bmw), bloom_bits(key[u]));
+        int bmo;
+        unsigned bmw;
+        build_where(a, t, j, base[u], mask[u], bmo, bmw);
         p[u] = slot_hash(key[u]) & mask[u];
         pend |= 1u << u;
     }
-    while (pend) {                                               // both CAS of a round are in flight together
+    while (pend) {
         unsigned long long prev[kBuildPerThread];
 #pragma unroll
         for (int u = 0; u < kBuildPerThread; ++u)
