@@ -160,7 +160,11 @@ int duet_create(int device_id, duet_handle **out) {
         return fail(nullptr, DUET_ERR_CUDA, msg);
     }
     h->stream = h->own_stream;
-    cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
+    {   // the table branch yields to the probe branch: lowest priority for its stream / graph nodes
+        int lo_prio = 0, hi_prio = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+        cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, lo_prio);
+    }
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     for (auto &ev : h->ev) cudaEventCreate(&ev);
@@ -532,7 +536,7 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
             if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
                 launch_all(h, st, false, true);
                 if (cudaStreamEndCapture(st, &h->graph) != cudaSuccess ||
-                    cudaGraphInstantiate(&h->graph_exec, h->graph, 0) != cudaSuccess) {
+                    cudaGraphInstantiateWithFlags(&h->graph_exec, h->graph, cudaGraphInstantiateFlagUseNodePriority) != cudaSuccess) {
                     h->graph_exec = nullptr;
                 }
             }

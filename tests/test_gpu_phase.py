@@ -289,3 +289,65 @@ def test_dropin_reads_real_bam(golden_workdir):
     sv_phasing.sv_phasing(home, case["svlen_thres"], case["suppread_thres"], 4, False)
     with open(home + "/phased_sv.vcf") as f:
         assert f.read() == case["phased_sv_vcf"]
+
+
+# ---- cohort batches and randomized differential testing against the columnar oracle adapter ---------
+def _compare_with_columnar_oracle(engine, batch, svlen, supp):
+    from oracle.columnar_adapter import phase_batch_oracle
+    engine.set_thresholds(svlen, supp)
+    res = engine.run(batch)
+    want = phase_batch_oracle(batch, svlen, supp)
+    assert np.array_equal(res.join_row, want.join_row)
+    assert np.array_equal(res.cls, want.cls)
+    assert np.array_equal(res.gt, want.gt)
+    t = want.traced
+    for k in ("ps", "hap1", "hap2", "hap0", "allhap", "totsc1", "totsc2"):
+        assert np.array_equal(getattr(res, k)[t], getattr(want, k)[t]), k
+    assert np.array_equal(res.features[:, t], want.features[:, t])
+    assert np.array_equal(res.order, want.order)
+    assert np.array_equal(res.shard_counts, want.shard_counts)
+    return res
+
+
+def test_cohort_batch_many_samples_one_call(engine):
+    """BASELINE.json configs[4] in miniature: several samples x contigs = many shards in ONE device call;
+    every sample's rows equal the oracle's for that sample alone."""
+    samples = [synth.make_sample(100 + i, contigs=["1", "2", "3", "X"], n_reads=5000, n_svs=400, bp_per_read=700,
+                                 block_mean=1.2e5, id_base=i << 44) for i in range(6)]
+    batch = from_synth(samples)
+    assert batch.n_shards == 24
+    res = _compare_with_columnar_oracle(engine, batch, 50, 2)
+    for i, s in enumerate(samples):
+        rows, _ = synth_adapter.phase_sample(s)
+        assert res.rows(batch, sample=i) == rows
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_batches_against_columnar_oracle(engine, seed):
+    """Arbitrary (not genome-like) batches: negative PS / PC, HP 1/2, PC around the 8100 edge, empty
+    shards, reads nobody supports, lists with repeats and misses, unsorted positions, equal positions."""
+    rng = np.random.default_rng(1000 + seed)
+    bb = BatchBuilder()
+    n_shards = int(rng.integers(1, 12))
+    for s in range(n_shards):
+        n_reads = int(rng.choice([0, 1, 5, 40, 300]))
+        names = [f"s{s}r{k}" for k in range(max(n_reads, 1))]
+        pss = [int(x) for x in rng.choice([-5, 0, 7, 100, 2**31 - 1, -2**31 + 1, 4242], size=int(rng.integers(1, 6)))]
+        reads = []
+        for k in range(n_reads):
+            nm = names[int(rng.integers(0, len(names)))] if rng.random() < 0.15 else names[k]     # duplicate QNAMEs
+            reads.append((nm, int(rng.integers(1, 3)), int(rng.choice(pss)),
+                          int(rng.choice([-3, 0, 1, 8099, 8100, 8101, 20000, int(rng.integers(0, 9000))]))))
+        svs = []
+        for v in range(int(rng.choice([0, 1, 3, 30]))):
+            k = int(rng.integers(1, 60))
+            lst = [names[int(rng.integers(0, len(names)))] if rng.random() < 0.8 else f"ghost{v}_{i}" for i in range(k)]
+            svs.append(dict(pos=int(rng.choice([10, 10, 500, int(rng.integers(-50, 10**6))])),
+                            svread=int(rng.integers(1, 40)), refread=int(rng.integers(0, 40)), names=lst,
+                            svlen=int(rng.choice([10, 50, 3000])), gt_missing=bool(rng.random() < 0.1)))
+        bb.shard(reads, svs, contig=str(s))
+    batch = bb.build()
+    if batch.n_svs == 0:
+        bb.shard([("a", 1, 5, 5)], [dict(pos=1, svread=3, refread=0, names=["a"])], contig="z")
+        batch = bb.build()
+    _compare_with_columnar_oracle(engine, batch, int(rng.choice([0, 50])), int(rng.choice([0, 2, 10])))
