@@ -81,17 +81,19 @@ k_rs_hist(const unsigned long long *__restrict__ key, int n, int shift, unsigned
     block_hist[threadIdx.x * n_blocks + blockIdx.x] = s_h[threadIdx.x];      // bin-major
 }
 
-// exclusive scan of `len` counters in place, one block
-__global__ void __launch_bounds__(1024)
-k_rs_scan(unsigned *v, int len) {
-    __shared__ unsigned s_w[32];
+// per-bin scan: block b turns row b of the bin-major histogram (n_blocks counters) into exclusive
+// offsets inside the bin and records the bin total; k_rs_scatter adds the bins' bases itself
+__global__ void __launch_bounds__(kClThreads)
+k_rs_scan(unsigned *block_hist, int n_blocks, unsigned *bin_total) {
+    __shared__ unsigned s_w[kClThreads / 32];
     __shared__ unsigned s_carry;
+    unsigned *row = block_hist + (size_t)blockIdx.x * n_blocks;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int base = 0; base < len; base += 1024) {
+    for (int base = 0; base < n_blocks; base += kClThreads) {
         const int i = base + threadIdx.x;
-        const unsigned x = i < len ? v[i] : 0u;
+        const unsigned x = i < n_blocks ? row[i] : 0u;
         unsigned inc = x;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -100,32 +102,39 @@ k_rs_scan(unsigned *v, int len) {
         }
         if (lane == 31) s_w[w] = inc;
         __syncthreads();
-        if (w == 0) {
-            unsigned t = s_w[lane], ti = t;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned u = __shfl_up_sync(0xffffffffu, ti, o);
-                if (lane >= o) ti += u;
-            }
-            s_w[lane] = ti - t;
-        }
-        __syncthreads();
+        unsigned before = 0, total = 0;
+        for (int k = 0; k < kClThreads / 32; ++k) { const unsigned t = s_w[k]; if (k < w) before += t; total += t; }
         const unsigned carry = s_carry;
-        if (i < len) v[i] = carry + s_w[w] + inc - x;
+        if (i < n_blocks) row[i] = carry + before + inc - x;
         __syncthreads();
-        if (threadIdx.x == 1023) s_carry = carry + s_w[w] + inc;
+        if (threadIdx.x == 0) s_carry = carry + total;
         __syncthreads();
     }
+    if (threadIdx.x == 0) bin_total[blockIdx.x] = s_carry;
 }
 
 __global__ void __launch_bounds__(kClThreads)
 k_rs_scatter(const unsigned long long *__restrict__ key_in, const int *__restrict__ idx_in,
              unsigned long long *__restrict__ key_out, int *__restrict__ idx_out, int n, int shift,
-             const unsigned *__restrict__ block_off, int n_blocks) {
+             const unsigned *__restrict__ block_off, int n_blocks, const unsigned *__restrict__ bin_total) {
     __shared__ unsigned s_base[256];
     __shared__ unsigned s_cnt[kClThreads / 32][256];
+    __shared__ unsigned s_w[kClThreads / 32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    s_base[threadIdx.x] = block_off[threadIdx.x * n_blocks + blockIdx.x];
+    {   // base of bin t = totals of the bins before it (block-wide exclusive scan of 256 totals)
+        const unsigned x = bin_total[threadIdx.x];
+        unsigned inc = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_w[w] = inc;
+        __syncthreads();
+        unsigned before = 0;
+        for (int k = 0; k < w; ++k) before += s_w[k];
+        s_base[threadIdx.x] = before + inc - x + block_off[threadIdx.x * n_blocks + blockIdx.x];
+    }
     const int base = blockIdx.x * kRsTile;
     for (int r = 0; r < kRsItems; ++r) {                 // rounds keep the tile's order: the sort is stable
         for (int k = 0; k < kClThreads / 32; ++k) s_cnt[k][threadIdx.x] = 0;
@@ -211,6 +220,7 @@ k_cl_edges(ClusterArgs a) {
     const unsigned long long ki = s_key[threadIdx.x];
     const unsigned seg = (unsigned)(ki >> 32), c2 = (unsigned)ki;
     const int si = s_span[threadIdx.x];
+    const float nf = (float)a.normalizer, mdf = (float)a.max_distance;
     for (int j = i + 1; j < a.n; ++j) {
         const int t = j - i0;
         const unsigned long long kj = t < kClThreads + kClHalo ? s_key[t] : a.key[j];
@@ -219,9 +229,17 @@ k_cl_edges(ClusterArgs a) {
         if (d2 > a.window2) break;
         const int sj = t < kClThreads + kClHalo ? s_span[t] : a.span[j];
         const int mx = max(si, sj);
-        const double dpos = ((double)d2 * 0.5) / a.normalizer;
-        const double dspan = mx > 0 ? (double)abs(si - sj) / (double)mx : 0.0;
-        if (dpos + dspan <= a.max_distance) uf_unite(a.parent, i, j);
+        // single precision first: only pairs within 1e-4 of the threshold need the exact fp64 quotients
+        const float approx = (float)d2 * 0.5f / nf + (mx > 0 ? (float)abs(si - sj) / (float)mx : 0.0f);
+        bool edge;
+        if (approx > mdf + 1e-4f) edge = false;
+        else if (approx < mdf - 1e-4f) edge = true;
+        else {
+            const double dpos = ((double)d2 * 0.5) / a.normalizer;
+            const double dspan = mx > 0 ? (double)abs(si - sj) / (double)mx : 0.0;
+            edge = dpos + dspan <= a.max_distance;
+        }
+        if (edge && a.parent[i] != a.parent[j]) uf_unite(a.parent, i, j);
     }
 }
 

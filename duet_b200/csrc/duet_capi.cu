@@ -704,7 +704,7 @@ int duet_cluster_run(duet_handle *h, const duet_cluster_input *in, const duet_cl
     CU(h, h->cl_span.reserve(N * 4));    a.span = h->cl_span.as<int>();
     CU(h, h->cl_parent.reserve(N * 4));  a.parent = h->cl_parent.as<int>();
     CU(h, h->cl_minidx.reserve(N * 4));  a.minidx = h->cl_minidx.as<int>();
-    CU(h, h->cl_hist.reserve((size_t)n_tiles * 256 * 4));
+    CU(h, h->cl_hist.reserve(((size_t)n_tiles + 1) * 256 * 4));
     CU(h, h->cl_misc.reserve(64));
     a.vary = h->cl_misc.as<unsigned long long>();
     a.n_clusters = reinterpret_cast<int *>(a.vary + 2);
@@ -730,10 +730,11 @@ int duet_cluster_run(duet_handle *h, const duet_cluster_input *in, const duet_cl
         if (!((vary[0] >> shift) & 0xFFull)) continue;
         unsigned *hist = h->cl_hist.as<unsigned>();
         k_rs_hist<<<n_tiles, kClThreads, 0, st>>>(h->cl_key[cur].as<unsigned long long>(), (int)n, shift, hist, n_tiles);
-        k_rs_scan<<<1, 1024, 0, st>>>(hist, n_tiles * 256);
+        unsigned *bin_total = hist + (size_t)n_tiles * 256;
+        k_rs_scan<<<256, kClThreads, 0, st>>>(hist, n_tiles, bin_total);
         k_rs_scatter<<<n_tiles, kClThreads, 0, st>>>(h->cl_key[cur].as<unsigned long long>(), h->cl_idx[cur].as<int>(),
                                                       h->cl_key[cur ^ 1].as<unsigned long long>(),
-                                                      h->cl_idx[cur ^ 1].as<int>(), (int)n, shift, hist, n_tiles);
+                                                      h->cl_idx[cur ^ 1].as<int>(), (int)n, shift, hist, n_tiles, bin_total);
         h->launches += 3;
         cur ^= 1;
     }
