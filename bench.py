@@ -168,7 +168,7 @@ def main():
     import torch
     import torch.distributed as dist
     from duet_b200.columnar import from_synth
-    from duet_b200.engine import PhaseEngine, pin_batch
+    from duet_b200.engine import PhaseEngine, pin_batch, pinned_outputs
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -234,13 +234,14 @@ def main():
     kernel_ms = {k: v / args.steps for k, v in ksum.items()}
 
     # ---- end to end through the public API: pinned host columns -> results on the host ----
+    out_bufs = pinned_outputs(batch)                  # results land in page-locked host memory too
     for _ in range(args.warmup):
-        eng.run(batch)
+        eng.run(batch, buffers=out_bufs)
     barrier()
     with clocks:
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            r2 = eng.run(batch)
+            r2 = eng.run(batch, buffers=out_bufs)
         e2e_s = time.perf_counter() - t0
     barrier()
     tm = eng.timings()

@@ -156,10 +156,12 @@ class PhaseEngine:
         arr["order"] = arr["order"][:n]
         return PhaseResult(**arr)
 
-    def run(self, batch: PhaseBatch, *, join: bool = True) -> PhaseResult:
+    def run(self, batch: PhaseBatch, *, join: bool = True, buffers: dict | None = None) -> PhaseResult:
+        """upload + execute + download.  `buffers` (see `pinned_outputs`) lets the results land in
+        page-locked memory, so the device->host copies run as plain DMA."""
         self.upload(batch)
         self.execute()
-        return self.download(join=join)
+        return self.download(join=join, buffers=buffers)
 
     def timings(self) -> dict:
         t = _lib.Timings()
@@ -186,6 +188,16 @@ def pinned_empty(shape, dtype) -> np.ndarray:
 
 
 _COLUMNS = _lib.INPUT_COLUMNS
+
+
+def pinned_outputs(batch: PhaseBatch) -> dict:
+    """Page-locked result arrays for `PhaseEngine.run(batch, buffers=...)` / `download(buffers=...)`."""
+    S, J, ns = batch.n_svs, batch.n_joins, batch.n_shards
+    shapes = {"gt": (S, np.uint8), "ps": (S, np.int32), "cls": (S, np.uint8), "hap1": (S, np.int32),
+              "hap2": (S, np.int32), "hap0": (S, np.int32), "allhap": (S, np.int32), "totsc1": (S, np.int64),
+              "totsc2": (S, np.int64), "features": ((_lib.N_FEATURES, S), np.float64), "join_row": (J, np.int32),
+              "order": (S, np.int32), "shard_counts": ((ns, _lib.N_COUNTERS), np.int64)}
+    return {k: pinned_empty(shape, dt) for k, (shape, dt) in shapes.items()}
 
 
 def pin_batch(batch: PhaseBatch) -> PhaseBatch:
