@@ -175,6 +175,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"             # keep stdout to the one JSON line (no version banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     t0 = time.perf_counter()
