@@ -1,21 +1,26 @@
 // sm_100a kernels of the sv_phasing hot path.
 //
 // Reference behaviour restated per kernel (citations: /root/reference/src/duet/sv_phasing_fn.py):
-//   k_build    dict insert side of the JOIN (:26-29 keyed by QNAME) -- here the SMALL side is
-//              inserted: the support-read names of the SVs (:46-48)
-//   k_probe    the haplotagged reads streamed through that table; a hit records the row index
-//              with atomicMax == "a later row overwrites an earlier one" (:29)
-//   k_reduce   per SV: resolve each support read to its row, class = #distinct PS (:192-194),
-//              one-PS candidate (:195-203), class-1 counts and score sums (:74-84);
-//              the last block to finish a shard turns the shard's candidates into the sorted
-//              unique one-PS list (:107)
-//   k_predict  class-2 statistics (:85-105), nearest-PS fallback (:106-111), features
-//              (:112-139), the T1-T5 tree (:142-183); clears the join table for the next call;
-//              the last block to finish a shard writes the shard's emission order (:206-229)
+//   k_init     start-of-call state: EMPTY slot table, zero Bloom filter, join results -1
+//   k_bloom    + k_table: the dict-insert side of the JOIN (:26-29 keyed by QNAME) -- here the SMALL
+//              side is inserted: the support-read names of the SVs (:46-48)
+//   k_probe    the haplotagged reads streamed once through the contig's Bloom filter (shared memory);
+//              survivors go to a candidate list
+//   k_resolve  candidates looked up in the slot table; a hit records the row index on every support-read
+//              entry of that name with atomicMax == "a later row overwrites an earlier one" (:29)
+//   k_reduce   per SV: gather the joined reads' tags, class = #distinct PS (:192-194), one-PS candidate
+//              (:195-203), class-1 counts and score sums (:74-84), per-PS statistics of class-2 SVs in
+//              first-seen order (:85-105); the block completing a contig builds its sorted unique
+//              one-PS list (:107)
+//   k_predict  per SV: in-set PS with most reads (:99-105), nearest-PS fallback (:106-111), features
+//              (:112-139), the T1-T5 tree (:142-183); the block completing a contig writes its emission
+//              order (:206-229) and counters
 //
-// Latency, not bandwidth, is what these kernels fight (the whole WGS-30x problem is ~130 MB):
-// every kernel is organised so that a thread's dependent-load chain is as short as possible and
-// all independent loads of a thread are issued before the first one is consumed.
+// What bounds these kernels at WGS size is not bandwidth (the whole problem is ~130 MB) but the ~1 us
+// round trip of a dependent global access, L2 atomic throughput and the HBM's random-sector rate.  So
+// every kernel requests everything independent at once and only then consumes it, every block starts
+// from a host-built tile descriptor instead of looking its contig up, random traffic is kept L2
+// resident (sequential init sweep, prefetches), and a joined read costs one 16-byte record.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -227,21 +232,6 @@ __device__ __forceinline__ int next_pow2(int n) {
     int p = 1;
     while (p < n) p <<= 1;
     return p;
-}
-
-// ------------------------------------------------------------------------------------------
-// tile -> shard range: count the offsets <= first / last element of the tile, all threads at once
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tile_shards(const long long *__restrict__ off, int n_shards, long long first,
-                                            long long last, int &lo, int &hi) {
-    if (n_shards < kThreads) {
-        const long long o = (int)threadIdx.x <= n_shards ? __ldg(off + threadIdx.x) : INT64_MAX;
-        lo = __syncthreads_count(o <= first) - 1;
-        hi = __syncthreads_count(o <= last) - 1;
-    } else {
-        lo = shard_of(off, n_shards, first);
-        hi = shard_of(off, n_shards, last);
-    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -530,7 +520,7 @@ k_resolve(PhaseArgs a) {
 // hash set (a contig has a few hundred phase sets however many SVs it has), and only those are sorted.
 constexpr int kOnepsSmall = 4096;                                // SVs per shard handled by the hash-set path
 
-template <bool kStaged> __device__ void oneps_block(const PhaseArgs &a, int s, long long *smem_tile);
+__device__ void oneps_block_big(const PhaseArgs &a, int s, long long *smem_tile);
 
 __device__ void oneps_block_small(const PhaseArgs &a, int s, long long *smem_tile) {
     constexpr int kSlots = kSortSmemBytes / 4;                   // 4096 ints
@@ -563,7 +553,7 @@ __device__ void oneps_block_small(const PhaseArgs &a, int s, long long *smem_til
         if (tries == kSlots) s_overflow = 1;                     // more distinct phase sets than slots
     }
     __syncthreads();
-    if (s_overflow) { __syncthreads(); oneps_block<false>(a, s, smem_tile); return; }
+    if (s_overflow) { __syncthreads(); oneps_block_big(a, s, smem_tile); return; }
     int found[kPer], cnt = 0;
 #pragma unroll
     for (int u = 0; u < kPer; ++u) {
@@ -589,62 +579,49 @@ __device__ void oneps_block_small(const PhaseArgs &a, int s, long long *smem_til
     __syncthreads();
 }
 
-template <bool kStaged>
-__device__ void oneps_block(const PhaseArgs &a, int s, long long *smem_tile) {
+// Big shards (more SVs than the hash-set path holds): multi-pass over the candidates in L2 / global
+// scratch.  Position-sorted candidates are compacted directly; otherwise runs of equal neighbours
+// are squeezed first and what is left is sorted.
+__device__ void oneps_block_big(const PhaseArgs &a, int s, long long *smem_tile) {
     const int b = (int)a.sv_off[s], n = (int)a.sv_off[s + 1] - b;
     const int per = (n + kThreads - 1) / kThreads;
     const int c0 = min(n, (int)threadIdx.x * per), c1 = min(n, c0 + per);
-    if (kStaged) {                                   // n <= kSortSmemBytes / 8: one coalesced read of the shard
-        for (int i = threadIdx.x; i < n; i += kThreads) smem_tile[i] = __ldcg(a.cand + b + i);
-        __syncthreads();
-    }
-#define CAND(i) (kStaged ? smem_tile[i] : __ldcg(a.cand + b + (i)))
-    // fast path: the candidates already are non-decreasing in VCF order (position-sorted VCF)
+    const long long *cand = a.cand + b;
     long long mx = kNone, lastv = kNone;
-    for (int i = c0; i < c1; ++i) { const long long v = CAND(i); if (v != kNoCand) { mx = max(mx, v); lastv = v; } }
+    for (int i = c0; i < c1; ++i) { const long long v = __ldcg(cand + i); if (v != kNoCand) { mx = max(mx, v); lastv = v; } }
     const long long run = block_scan_exclusive(mx, kNone, OpMax(), (long long *)nullptr);
     long long cur = run;
     int cnt = 0;
     bool ok = true;
     for (int i = c0; i < c1; ++i) {
-        const long long v = CAND(i);
+        const long long v = __ldcg(cand + i);
         if (v != kNoCand) { if (v < cur) ok = false; else if (v > cur) { ++cnt; cur = v; } }
     }
-    if (__syncthreads_and(ok)) {
+    if (__syncthreads_and(ok)) {                     // already non-decreasing in VCF order
         int total;
         int w = block_scan_exclusive(cnt, 0, OpSum(), &total);
         cur = run;
-        for (int i = c0; i < c1; ++i) { const long long v = CAND(i); if (v != kNoCand && v > cur) { a.oneps[b + w++] = (int)v; cur = v; } }
+        for (int i = c0; i < c1; ++i) { const long long v = __ldcg(cand + i); if (v != kNoCand && v > cur) { a.oneps[b + w++] = (int)v; cur = v; } }
         if (threadIdx.x == 0) a.oneps_n[s] = total;
         return;
     }
-    // slow path.  Squeeze runs of equal neighbours first (a nearly sorted list of a few hundred
-    // phase sets stays a few hundred long), then sort what is left.
     const long long prev0 = block_scan_exclusive(lastv, kNone, OpLast(), (long long *)nullptr);
     long long prev = prev0;
     cnt = 0;
-    for (int i = c0; i < c1; ++i) { const long long v = CAND(i); if (v != kNoCand) { cnt += v != prev; prev = v; } }
+    for (int i = c0; i < c1; ++i) { const long long v = __ldcg(cand + i); if (v != kNoCand) { cnt += v != prev; prev = v; } }
     int r;
     int w = block_scan_exclusive(cnt, 0, OpSum(), &r);
-    long long *v;
-    if (kStaged) {                                   // heads go back into the tile once everybody has read it
-        long long hd[kSortSmemBytes / 8 / kThreads];
-        int nh = 0;
-        prev = prev0;
-        for (int i = c0; i < c1; ++i) { const long long x = CAND(i); if (x != kNoCand) { if (x != prev) hd[nh++] = x; prev = x; } }
-        __syncthreads();
-        v = smem_tile;
-        for (int k = 0; k < nh; ++k) v[w + k] = hd[k];
-    } else {
-        v = a.sort_scratch + 2ll * b;
-        prev = prev0;
-        for (int i = c0; i < c1; ++i) { const long long x = CAND(i); if (x != kNoCand) { if (x != prev) v[w++] = x; prev = x; } }
-    }
-#undef CAND
-    __syncthreads();
+    long long *v = a.sort_scratch + 2ll * b;         // run heads: at most n of them
+    prev = prev0;
+    for (int i = c0; i < c1; ++i) { const long long x = __ldcg(cand + i); if (x != kNoCand) { if (x != prev) v[w++] = x; prev = x; } }
     __syncthreads();
     const int n_pad = next_pow2(max(r, 1));
-    for (int i = r + threadIdx.x; i < n_pad; i += kThreads) v[i] = kNoCand;
+    if (n_pad * (int)sizeof(long long) <= kSortSmemBytes) {      // few heads: sort them on chip
+        for (int i = threadIdx.x; i < n_pad; i += kThreads) smem_tile[i] = i < r ? v[i] : kNoCand;
+        v = smem_tile;
+    } else {
+        for (int i = r + threadIdx.x; i < n_pad; i += kThreads) v[i] = kNoCand;
+    }
     __syncthreads();
     block_bitonic_sort(v, n_pad);
     const int per2 = (n_pad + kThreads - 1) / kThreads;
@@ -661,7 +638,7 @@ __device__ void oneps_block(const PhaseArgs &a, int s, long long *smem_tile) {
 
 __device__ __forceinline__ void oneps_any(const PhaseArgs &a, int s, long long *smem_tile) {
     if ((int)(a.sv_off[s + 1] - a.sv_off[s]) <= kOnepsSmall) oneps_block_small(a, s, smem_tile);
-    else oneps_block<false>(a, s, smem_tile);
+    else oneps_block_big(a, s, smem_tile);
 }
 
 // ------------------------------------------------------------------------------------------
