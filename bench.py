@@ -33,12 +33,15 @@ WORKLOADS = {
     "c1": "C1 chr21 demo shape (70k ONT reads, 2.5k SVs)",
     "c2": "C2 synthetic GRCh37 WGS 30x ONT (4.5M reads, 25k cuteSV SVs)",
     "c4": "C4 synthetic WGS 60x ONT dense support lists (9M reads, 30k SVs)",
+    "c5": "C5 cohort share of one GPU: 4 samples x WGS 30x (32 samples over 8 GPUs), 96 shards in one call",
 }
 CPU_SAMPLE_CONTIGS = ["17", "18", "19", "20", "21", "22"]      # 12.3 % of GRCh37: bounded CPU sample
 
 
 def make_sample(workload: str, seed: int):
     from duet_b200 import synth
+    if workload == "c5":                               # the 4 samples a GPU owns in the 32-sample cohort
+        return [synth.config_c2(4 * seed + k, id_base=(4 * seed + k) << 44) for k in range(4)]
     return {"c1": synth.config_c1, "c2": synth.config_c2, "c4": synth.config_c4}[workload](seed)
 
 
@@ -325,7 +328,7 @@ def main():
                                  [int(x) for x in all_counts])),
             "gather_ms": gather_ms, "synth_seconds": gen_s,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and args.workload != "c5":
             cpu = CpuPort(args.workload, 0)
             sec = min(cpu.step() for _ in range(3))
             line["cpu_baseline"] = {"value": cpu.n_svs / sec, "unit": "SV/s", "cores": 1, "kind": "port",

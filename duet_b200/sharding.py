@@ -123,11 +123,17 @@ def sv_phasing_sharded(home, svlen_thres, suppread_thres, thread, include_all_ct
     mine = plan[rank]
 
     comp_call = parse_vcf(vcf_path, include_all_ctgs)                  # small; every rank reads it
+    sources = [next((p for p in (sam_home + "chr" + c + ".bam", sam_home + c + ".bam") if os.path.exists(p)), None)
+               for c in chrom_list]
+    probe = [fn.ReadColumns.empty() for _ in chrom_list]               # only the file identities, for the
+    for cols, p in zip(probe, sources):                                # 'c' and 'chr'+c both listed check
+        cols.source = p
+    comp_call = fn.contig_records(chrom_list, comp_call, probe)
     read_hap = []
     for ch in mine:                                                    # the heavy decode: own contigs only
-        ctg = chrom_list[ch]
-        path = next((p for p in (sam_home + "chr" + ctg + ".bam", sam_home + ctg + ".bam") if os.path.exists(p)), None)
-        read_hap.append(fn.load_hap_bam(path, thread) if path else fn.ReadColumns.empty())
+        cols = fn.load_hap_bam(sources[ch], thread) if sources[ch] else fn.ReadColumns.empty()
+        cols.source = sources[ch]
+        read_hap.append(cols)
     batch = fn.build_batch([chrom_list[ch] for ch in mine], read_hap, [comp_call[ch] for ch in mine])
     res = phase_fn(batch, svlen_thres, suppread_thres)
 

@@ -46,6 +46,7 @@ class ReadColumns:
     key: np.ndarray          # uint64 low hash word
     tag: np.ndarray          # TAG_DTYPE: HP / PS / PC + check word
     n_lines: int = 0
+    source: str | None = None    # the file the rows came from
 
     @property
     def hp(self):
@@ -162,6 +163,8 @@ def read_hap_bam(path, thread, include_all_ctgs):
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=max(1, int(thread))) as pool:
         read_hap = list(pool.map(lambda p: load_hap_bam(p, 1) if p else ReadColumns.empty(), paths))
+    for cols, p in zip(read_hap, paths):
+        cols.source = p
     for ctg, cols, p in zip(chrom_list, read_hap, paths):
         if p:
             logging.info(("  signatures extracted from " if cols.n_lines else "  no signature from ") + ctg)
@@ -189,7 +192,41 @@ def generate_callinfo(caller_path, read_hap, include_all_ctgs) -> PhaseBatch:
     logging.info("extract SV signatures")
     comp_call = parse_vcf(caller_path, include_all_ctgs)
     chrom_list = init_chrom_list(include_all_ctgs, caller_path[:len(caller_path) - 24])
-    return build_batch(chrom_list, read_hap, comp_call)
+    return build_batch(chrom_list, read_hap, contig_records(chrom_list, comp_call, read_hap))
+
+
+def contig_records(chrom_list, comp_call: list[ContigSvs], read_hap: list[ReadColumns] | None = None):
+    """SV records each contig's prediction loop sees, in the reference's order.
+
+    The reference flattens the per-contig record lists and later selects, for contig c, every flat record
+    whose CHROM is 'c' or 'chr'+c (sv_phasing_fn.py:198,208).  Normally that is contig c's own list.  With
+    `include_all_ctgs` the list may name both 'c' and 'chr'+c: then a 'chrc' record was parsed (and joined)
+    once per naming contig and EVERY copy is selected by each of them -- reproduced here.  A copy parsed
+    under another contig was joined against that contig's BAM; that is only reproducible when both
+    contigs read the same file, anything else is refused."""
+    owners: dict[str, list[int]] = {}
+    for ch, c in enumerate(chrom_list):
+        for nm in ("chr" + c, c):
+            if ch not in owners.setdefault(nm, []):
+                owners[nm].append(ch)
+    if all(len(v) == 1 for v in owners.values()):
+        return comp_call
+    out = []
+    for ch, c in enumerate(chrom_list):
+        accept = ("chr" + c, c)
+        cs = ContigSvs()
+        for o, src in enumerate(comp_call):
+            idx = [i for i, nm in enumerate(src.chrom) if nm in accept]
+            if not idx:
+                continue
+            if o != ch and read_hap is not None and read_hap[o].source != read_hap[ch].source:
+                raise NotImplementedError(
+                    f"contigs {chrom_list[o]!r} and {c!r} both claim CHROM {src.chrom[idx[0]]!r} but read different "
+                    "haplotagged BAMs; the reference's result for such a contig list cannot be reproduced per contig")
+            for f in ("chrom", "pos", "ref", "alt", "svlen", "svtype", "svread", "names", "gt", "refread", "altread"):
+                getattr(cs, f).extend(getattr(src, f)[i] for i in idx)
+        out.append(cs)
+    return out
 
 
 def build_batch(chrom_list, read_hap: list[ReadColumns], comp_call: list[ContigSvs], sample: int = 0) -> PhaseBatch:

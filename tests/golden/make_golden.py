@@ -36,6 +36,12 @@ def install_shim():
     with open(p, "w") as f:
         f.write('#!/bin/bash\nexec cat "${@: -1}"\n')
     os.chmod(p, os.stat(p).st_mode | stat.S_IEXEC)
+    # `tabix --list-chroms <home>/snp_calling/pileup.vcf.gz` (read_file.py:15): the shim prints the
+    # contig list stored next to the (non-existent) pileup file
+    p = os.path.join(d, "tabix")
+    with open(p, "w") as f:
+        f.write('#!/bin/bash\nexec cat "$(dirname "${@: -1}")/contigs.txt"\n')
+    os.chmod(p, os.stat(p).st_mode | stat.S_IEXEC)
     os.environ["PATH"] = d + os.pathsep + os.environ["PATH"]
 
 
@@ -123,21 +129,26 @@ def kat_cases(ref):
     return cases
 
 
-def e2e_case(ref, sp, name, sample, dialect, svlen_thres=50, suppread_thres=2, mutate=None):
+def e2e_case(ref, sp, name, sample, dialect, svlen_thres=50, suppread_thres=2, mutate=None, all_ctgs=None):
     home = tempfile.mkdtemp(prefix="duet_golden_")
     synth.write_workdir(sample, home, dialect)
     if mutate:
         mutate(home)
+    inc = all_ctgs is not None
+    if inc:
+        os.makedirs(home + "/snp_calling")
+        with open(home + "/snp_calling/contigs.txt", "w") as f:
+            f.write("".join(c + "\n" for c in all_ctgs))
     vcf = home + "/sv_calling/variants.vcf"
     sam_home = home + "/snp_phasing/"
     files = {}
-    for sub in ("snp_phasing", "sv_calling"):
+    for sub in ("snp_phasing", "sv_calling") + (("snp_calling",) if inc else ()):
         for fn in sorted(os.listdir(os.path.join(home, sub))):
             with open(os.path.join(home, sub, fn)) as f:
                 files[sub + "/" + fn] = f.read()
     # the join, straight from the reference
-    read_hap = ref.read_hap_bam(sam_home, 1, False)
-    callinfo = ref.generate_callinfo(vcf, read_hap, False)
+    read_hap = ref.read_hap_bam(sam_home, 1, inc)
+    callinfo = ref.generate_callinfo(vcf, read_hap, inc)
     joined = [{"chrom": c["chrom"], "pos": c["pos"], "svlen": c["svlen"], "svtype": c["svtype"],
                "svread": c["svread"], "refread": c["refread"], "callgt": c["callgt"],
                "reads": [r[1:] for r in c["svreadinfo"]]} for c in callinfo]
@@ -155,14 +166,15 @@ def e2e_case(ref, sp, name, sample, dialect, svlen_thres=50, suppread_thres=2, m
 
     ref.get_phase_info = spy
     try:
-        rows = ref.generate_phased_callset(vcf, sam_home, svlen_thres, suppread_thres, 1, False)
+        rows = ref.generate_phased_callset(vcf, sam_home, svlen_thres, suppread_thres, 1, inc)
     finally:
         ref.get_phase_info = orig
-    sp.sv_phasing(home, svlen_thres, suppread_thres, 1, False)
+    sp.sv_phasing(home, svlen_thres, suppread_thres, 1, inc)
     with open(home + "/phased_sv.vcf") as f:
         out_text = f.read()
     dump(f"e2e_{name}.json.gz", {
         "name": name, "dialect": dialect, "svlen_thres": svlen_thres, "suppread_thres": suppread_thres,
+        "include_all_ctgs": inc,
         "files": files, "joined": joined, "trace": trace, "rows": rows, "phased_sv_vcf": out_text})
     print(f"  {name}: {len(joined)} SVs, {len(rows)} phased rows")
 
@@ -204,6 +216,30 @@ def main():
 
     e2e_case(ref, sp, "mixed_prefix", mk(5, contigs=["1", "10"], n_reads=2000, n_svs=150, bp_per_read=700, block_mean=1e5,
                                         empty_oneps_contig=None), "cutesv", mutate=mixed_prefix)
+
+
+    # -a / include_all_ctgs: the contig list comes from `tabix --list-chroms`; decoys, and a list naming
+    # both '7' and 'chr7' (every 'chr7' record then belongs to two contigs and is phased twice)
+    def rename_contigs(home):
+        os.rename(home + "/snp_phasing/3.bam", home + "/snp_phasing/GL000192.1.bam")
+        os.rename(home + "/snp_phasing/7.bam", home + "/snp_phasing/chr7.bam")
+        p = home + "/sv_calling/variants.vcf"
+        with open(p) as f:
+            lines = f.readlines()
+        out = []
+        for ln in lines:
+            ln = ln.replace("##contig=<ID=3,", "##contig=<ID=GL000192.1,").replace("##contig=<ID=7,", "##contig=<ID=chr7,")
+            if ln.startswith("3\t"):
+                ln = "GL000192.1" + ln[1:]
+            elif ln.startswith("7\t"):
+                ln = "chr" + ln
+            out.append(ln)
+        with open(p, "w") as f:
+            f.writelines(out)
+
+    e2e_case(ref, sp, "all_ctgs", mk(6, contigs=["2", "3", "7"], n_reads=2400, n_svs=180, bp_per_read=700, block_mean=1e5,
+                                    empty_oneps_contig=None), "cutesv", mutate=rename_contigs,
+             all_ctgs=["2", "GL000192.1", "7", "chr7", "MT"])
 
 
 if __name__ == "__main__":

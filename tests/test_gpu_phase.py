@@ -234,15 +234,16 @@ def test_dropin_against_reference_golden(name, golden_workdir):
     phased_sv.vcf byte-identical to what the unmodified reference produced."""
     from duet_b200 import sv_phasing, sv_phasing_fn
     case, home = golden_workdir(name)
+    inc = case.get("include_all_ctgs", False)
     rows = sv_phasing_fn.generate_phased_callset(home + "/sv_calling/variants.vcf", home + "/snp_phasing/",
-                                                 case["svlen_thres"], case["suppread_thres"], 1, False)
+                                                 case["svlen_thres"], case["suppread_thres"], 1, inc)
     assert rows == case["rows"]
-    sv_phasing.sv_phasing(home, case["svlen_thres"], case["suppread_thres"], 1, False)
+    sv_phasing.sv_phasing(home, case["svlen_thres"], case["suppread_thres"], 1, inc)
     with open(home + "/phased_sv.vcf") as f:
         assert f.read() == case["phased_sv_vcf"]
     # and the join / per-SV features the reference computed on the way
     batch = sv_phasing_fn.generate_callinfo(home + "/sv_calling/variants.vcf",
-                                            sv_phasing_fn.read_hap_bam(home + "/snp_phasing/", 1, False), False)
+                                            sv_phasing_fn.read_hap_bam(home + "/snp_phasing/", 1, inc), inc)
     res = sv_phasing_fn.phase_batch(batch, case["svlen_thres"], case["suppread_thres"])
     assert batch.n_svs == len(case["joined"])
     for i, g in enumerate(case["joined"]):

@@ -65,9 +65,10 @@ def test_name_hash_three_ways():
 @pytest.mark.parametrize("name", golden_e2e_names())
 def test_decoders_match_oracle_on_golden_inputs(name, golden_workdir):
     case, home = golden_workdir(name)
+    inc = case.get("include_all_ctgs", False)
     vcf, sam_home = home + "/sv_calling/variants.vcf", home + "/snp_phasing/"
-    tables = ref_port.haplotag_tables(sam_home, 1, False)
-    cols = sv_phasing_fn.read_hap_bam(sam_home, 1, False)
+    tables = ref_port.haplotag_tables(sam_home, 1, inc)
+    cols = sv_phasing_fn.read_hap_bam(sam_home, 1, inc)
     for table, rc in zip(tables, cols):
         # last row per key == dict content
         last = {}
@@ -77,16 +78,16 @@ def test_decoders_match_oracle_on_golden_inputs(name, golden_workdir):
         want = {namehash.hash128(nm)[0]: tag for nm, tag in table.items()}
         got = {k: (int(rc.hp[i]), int(rc.ps[i]), int(rc.pc[i])) for k, i in last.items()}
         assert got == want
-    recs = ref_port.sv_records(vcf, False)
-    svs = read_file.parse_vcf(vcf, False)
+    recs = ref_port.sv_records(vcf, inc)
+    svs = read_file.parse_vcf(vcf, inc)
     for rl, cs in zip(recs, svs):
         assert len(rl) == len(cs)
         for i, r in enumerate(rl):
             assert (r.chrom, r.pos, r.ref, r.alt, r.svlen, r.svtype, r.svread, r.names, r.gt, r.refread, r.altread) == \
                    (cs.chrom[i], cs.pos[i], cs.ref[i], cs.alt[i], cs.svlen[i], cs.svtype[i], cs.svread[i],
                     cs.names[i], cs.gt[i], cs.refread[i], cs.altread[i])
-    assert write_file.header_text(vcf, False) == ref_port.header_text(vcf, False)
-    assert write_file.header_text(vcf, False) + write_file.format_rows(case["rows"]) == case["phased_sv_vcf"]
+    assert write_file.header_text(vcf, inc) == ref_port.header_text(vcf, inc)
+    assert write_file.header_text(vcf, inc) + write_file.format_rows(case["rows"]) == case["phased_sv_vcf"]
 
 
 def test_text_path_equals_direct_columnar(tmp_path):

@@ -40,11 +40,12 @@ def test_kat_phase_info():
 @pytest.mark.parametrize("name", golden_e2e_names())
 def test_e2e_against_reference(name, golden_workdir):
     case, home = golden_workdir(name)
+    inc = case.get("include_all_ctgs", False)
     vcf = home + "/sv_calling/variants.vcf"
     sam_home = home + "/snp_phasing/"
     # the join
-    tables = ref_port.haplotag_tables(sam_home, 1, False)
-    flat = ref_port.join_support_reads(ref_port.sv_records(vcf, False), tables)
+    tables = ref_port.haplotag_tables(sam_home, 1, inc)
+    flat = ref_port.join_support_reads(ref_port.sv_records(vcf, inc), tables)
     assert len(flat) == len(case["joined"])
     for r, g in zip(flat, case["joined"]):
         assert (r.chrom, r.pos, r.svlen, r.svtype, r.svread, r.refread, r.gt) == \
@@ -53,7 +54,7 @@ def test_e2e_against_reference(name, golden_workdir):
     # per-SV features in the reference's evaluation order, then the rows
     trace = []
     rows = ref_port.generate_phased_callset(vcf, sam_home, case["svlen_thres"], case["suppread_thres"], 1,
-                                            False, trace=trace)
+                                            inc, trace=trace)
     assert len(trace) == len(case["trace"])
     for (ci, ps_num, r, pred, f), g in zip(trace, case["trace"]):
         assert (r.chrom, r.pos, ps_num) == (g["chrom"], g["pos"], g["ps_num"])
@@ -61,6 +62,6 @@ def test_e2e_against_reference(name, golden_workdir):
             assert f[k] == g["f"][k], (k, g)
     assert rows == case["rows"]
     # the output file, byte for byte
-    ref_port.sv_phasing(home, case["svlen_thres"], case["suppread_thres"], 1, False)
+    ref_port.sv_phasing(home, case["svlen_thres"], case["suppread_thres"], 1, inc)
     with open(home + "/phased_sv.vcf") as fh:
         assert fh.read() == case["phased_sv_vcf"]

@@ -37,7 +37,7 @@ def _oracle_phase_fn(batch, svlen_thres, suppread_thres):
                        o.join_row, o.order, o.shard_counts)
 
 
-def _worker(rank, world, port, home, svlen, supp, out_q, on_gpu=False):
+def _worker(rank, world, port, home, svlen, supp, out_q, on_gpu=False, inc=False):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -47,7 +47,7 @@ def _worker(rank, world, port, home, svlen, supp, out_q, on_gpu=False):
         os.environ["DUET_DEVICE"] = str(rank % torch.cuda.device_count())
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        counts = sharding.sv_phasing_sharded(home, svlen, supp, 1, False,
+        counts = sharding.sv_phasing_sharded(home, svlen, supp, 1, inc,
                                              phase_fn=None if on_gpu else _oracle_phase_fn)
         out_q.put((rank, counts))
     finally:
@@ -66,7 +66,8 @@ def _run_two_ranks(name, tmp_path, on_gpu):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, home, case["svlen_thres"], case["suppread_thres"], q, on_gpu))
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, home, case["svlen_thres"], case["suppread_thres"], q, on_gpu,
+                                               case.get("include_all_ctgs", False)))
              for r in range(2)]
     for p in procs:
         p.start()
@@ -81,7 +82,7 @@ def _run_two_ranks(name, tmp_path, on_gpu):
     assert not [fn for fn in os.listdir(home) if ".slice." in fn]
 
 
-@pytest.mark.parametrize("name", ["cutesv_3ctg", "mixed_prefix", "svim_shuffled"])
+@pytest.mark.parametrize("name", ["cutesv_3ctg", "mixed_prefix", "svim_shuffled", "all_ctgs"])
 def test_two_rank_stage_is_byte_identical(name, tmp_path):
     _run_two_ranks(name, tmp_path, on_gpu=False)
 
