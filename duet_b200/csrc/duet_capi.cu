@@ -71,6 +71,9 @@ struct duet_handle {
     int reduce_lanes = kReduceLanesSparse;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
+    PhaseArgs graph_args;           // what the captured launches were given
+    int graph_dims[4] = {0, 0, 0, 0};
+    bool graph_valid = false;       // cleared when n_slots / n_bm_words change (they are launch arguments)
     bool dbg_on = false;
     size_t probe_smem = 0;
     DevBuf d_table;                 // Slot[n_slots] followed by the Bloom filter words
@@ -253,8 +256,6 @@ int duet_host_free(void *ptr) {
 int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     if (!h || !in) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: NULL argument");
     h->staged = h->executed = false;
-    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
-    if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
     const int ns = in->n_shards;
     const long long R = in->n_reads, S = in->n_svs, J = in->n_joins;
     if (ns < 1 || R < 0 || S < 0 || J < 0 || R >= (1ll << 31) || S >= (1ll << 31) || J >= (1ll << 30))
@@ -308,6 +309,7 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         max_sv = std::max<long long>(max_sv, in->sv_off[s + 1] - in->sv_off[s]);
         if (slots >= (1ll << 31)) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: join table too large");
     }
+    if (h->n_slots != slots || h->n_bm_words != bm_words) h->graph_valid = false;
     h->n_slots = slots;
     h->n_bm_words = bm_words;
     h->h_read_off.assign(in->read_off, in->read_off + ns + 1);
@@ -530,8 +532,18 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
     if (h->per_kernel) {
         launch_all(h, st, true, false);
     } else {
-        // the launch sequence of a staged batch never changes: replay it as a CUDA graph
+        // the launch sequence of a staged batch never changes: replay it as a CUDA graph.  A re-upload
+        // of the same shapes lands in the same buffers, so the captured graph stays valid.
+        const int dims[4] = {h->probe_grid, h->reduce_lanes, (int)h->probe_smem, h->n_sm};
+        if (h->graph_exec && (std::memcmp(&h->graph_args, &h->a, sizeof(PhaseArgs)) != 0 ||
+                              std::memcmp(h->graph_dims, dims, sizeof(dims)) != 0 || !h->graph_valid)) {
+            cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr;
+            cudaGraphDestroy(h->graph); h->graph = nullptr;
+        }
         if (!h->graph_exec) {
+            h->graph_args = h->a;
+            std::memcpy(h->graph_dims, dims, sizeof(dims));
+            h->graph_valid = true;
             const int64_t before = h->launches;
             if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
                 launch_all(h, st, false, true);
