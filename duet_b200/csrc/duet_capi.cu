@@ -175,7 +175,7 @@ int duet_create(int device_id, duet_handle **out) {
     {   // fails here, loudly, if the image was not built for this device (sm_100a only)
         cudaFuncAttributes fa;
         cudaFuncGetAttributes(&fa, k_probe);
-        cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, kBloomMaxWords * 4);
+        cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, kBloomMaxWords * 4 + kProbeRingBytes);
         // one shared-memory carveout for all four kernels: switching it between launches drains the SMs
         cudaFuncSetAttribute(k_bloom, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_table, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -432,7 +432,7 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     {
         long long max_words = 32;
         for (int s = 0; s < ns; ++s) max_words = std::max<long long>(max_words, (long long)bm_wmask[s] + 1);
-        h->probe_smem = (size_t)max_words * 4;
+        h->probe_smem = (size_t)kProbeRingBytes + (size_t)max_words * 4;
     }
     CU(h, h->d_gt.reserve(S1));                          a.gt = h->d_gt.as<uint8_t>();
     CU(h, h->d_cls.reserve(S1));                         a.cls = h->d_cls.as<uint8_t>();

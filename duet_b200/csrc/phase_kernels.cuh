@@ -355,63 +355,112 @@ k_table(PhaseArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// k_probe: the haplotagged reads are STREAMED once (16-byte loads, the next batch already requested
-// while the current one is filtered) by one block per tile -- a tile is a row range of ONE contig,
-// sized so that the grid is about two blocks per SM.  The block keeps the contig's Bloom filter in
-// shared memory, so ~90 % of the rows (reads that support no SV) never leave the SM; the survivors are
-// appended to the block's private stretch of the candidate list for k_resolve.  Nothing inside the
-// stream waits on L2 or synchronises the block.
+// k_probe: the haplotagged reads are STREAMED once by one block per tile -- a tile is a row range of ONE
+// contig, sized so that the grid is about two blocks per SM.  One thread keeps a ring of 16 KB key tiles
+// in flight with bulk asynchronous copies (TMA, cp.async.bulk + mbarrier complete_tx); warps consume a
+// tile as soon as its barrier flips and hand the stage back through an `empty` barrier -- no block-wide
+// synchronisation inside the stream.  The block keeps the contig's Bloom filter in shared memory, so
+// ~90 % of the rows (reads that support no SV) never leave the SM; the survivors are appended to the
+// block's private stretch of the candidate list for k_resolve.
 // ------------------------------------------------------------------------------------------
 constexpr int kProbeThreads = 512;
 constexpr int kProbeBlocksPerSm = 2;
-constexpr int kProbeUnroll = 2;                                  // 16-byte pairs per thread per batch
-constexpr int kProbeRows = 2 * kProbeUnroll;                     // rows per thread per batch
-constexpr int kProbeBatch = kProbeThreads * kProbeUnroll;        // pairs per block per batch
+constexpr int kProbeUnroll = 2;                                  // 16-byte pairs per thread per tile
+constexpr int kProbeRows = 2 * kProbeUnroll;                     // rows per thread per tile
+constexpr int kProbeBatch = kProbeThreads * kProbeUnroll;        // pairs per tile (16 KB)
+constexpr int kProbeStages = 3;                                  // tiles in flight per block
+constexpr int kProbeRingBytes = kProbeStages * kProbeBatch * 16;
+
+// ---- mbarrier / bulk-copy (TMA) primitives ------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+// one thread: `bytes` (multiple of 16) from 16-byte aligned global memory into shared memory; completion
+// is signalled on `bar` (complete_tx)
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 __global__ void __launch_bounds__(kProbeThreads, kProbeBlocksPerSm)
 k_probe(PhaseArgs a) {
-    extern __shared__ __align__(16) unsigned s_bm[];
+    extern __shared__ __align__(128) unsigned char s_raw[];      // [key ring | filter words]
+    __shared__ __align__(8) unsigned long long s_full[kProbeStages], s_empty[kProbeStages];
     __shared__ int s_count;
     dbg_mark(a, 1, 0);
     const ProbeTile tile = a.probe_tiles[blockIdx.x];            // one contig, one row range, everything needed
+    ulonglong2 *ring = reinterpret_cast<ulonglong2 *>(s_raw);
+    unsigned *s_bm = reinterpret_cast<unsigned *>(s_raw + kProbeRingBytes);
     const long long R = a.n_reads;
     const long long r0 = tile.r0, r1 = tile.r1;
     const unsigned bmw = (unsigned)tile.bmw;
     const int lane = threadIdx.x & 31;
     const ulonglong2 *pairs = reinterpret_cast<const ulonglong2 *>(a.read_key);
-    const uint4 *src = reinterpret_cast<const uint4 *>(a.bitmap + tile.bmo);
-    const long long q1 = (r1 + 1) >> 1;                          // pairs of rows (2q, 2q+1)
-    long long q = (r0 >> 1) + threadIdx.x;
-    ulonglong2 nxt[kProbeUnroll];
-    auto fetch = [&](long long qb) {
-#pragma unroll
-        for (int u = 0; u < kProbeUnroll; ++u) {
-            const long long qq = qb + (long long)u * kProbeThreads;
-            nxt[u] = make_ulonglong2(0ull, 0ull);
-            if (qq < q1) {
-                if (2 * qq + 1 < R) nxt[u] = __ldcs(pairs + qq);
-                else nxt[u].x = __ldcs(a.read_key + 2 * qq);
-            }
+    const long long q0 = r0 >> 1;                                // pairs of rows (2q, 2q+1)
+    const long long q1 = (r1 + 1) >> 1;
+    const long long q_full = min(q1, R >> 1);                    // pairs that lie completely inside the column
+    const int n_tiles = (int)((q1 - q0 + kProbeBatch - 1) / kProbeBatch);
+    auto tile_pairs = [&](int t) { return (unsigned)max(0ll, min(q_full, q0 + (long long)(t + 1) * kProbeBatch) - (q0 + (long long)t * kProbeBatch)); };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kProbeStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kProbeThreads / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_count = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                                      // fill the ring: the stream starts before the filter is in
+        for (int t = 0; t < min(n_tiles, kProbeStages); ++t) {
+            const unsigned bytes = tile_pairs(t) * 16u;
+            mbar_expect_tx(&s_full[t], bytes);
+            if (bytes) bulk_load(ring + (size_t)t * kProbeBatch, pairs + q0 + (long long)t * kProbeBatch, bytes, &s_full[t]);
         }
-    };
-    fetch(q);                                                    // first batch in flight during the filter load
+    }
+    const uint4 *src = reinterpret_cast<const uint4 *>(a.bitmap + tile.bmo);
     for (int i = threadIdx.x; i < (int)(bmw + 1) / 4; i += kProbeThreads)
         reinterpret_cast<uint4 *>(s_bm)[i] = src[i];
-    if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
     dbg_mark(a, 1, 1);
     unsigned long long *out_key = a.cand_key + r0;               // this block's private stretch of the list
     int *out_row = a.cand_row + r0;
-    // no block-wide synchronisation inside the stream: warps run ahead of each other freely
-    for (long long qb = r0 >> 1; qb < q1; qb += kProbeBatch, q += kProbeBatch) {
+    for (int t = 0; t < n_tiles; ++t) {
+        const int stage = t % kProbeStages;
+        const unsigned parity = (unsigned)(t / kProbeStages) & 1u;
+        const long long qt = q0 + (long long)t * kProbeBatch;
+        mbar_wait(&s_full[stage], parity);                       // the tile's bytes have landed
         unsigned long long key[kProbeRows];
 #pragma unroll
-        for (int u = 0; u < kProbeUnroll; ++u) { key[2 * u] = nxt[u].x; key[2 * u + 1] = nxt[u].y; }
-        if (qb + kProbeBatch < q1) fetch(q + kProbeBatch);       // next batch requested before this one is used
+        for (int u = 0; u < kProbeUnroll; ++u) {
+            const long long qq = qt + (long long)u * kProbeThreads + threadIdx.x;
+            ulonglong2 v = make_ulonglong2(0ull, 0ull);
+            if (qq < q_full) v = ring[(size_t)stage * kProbeBatch + u * kProbeThreads + threadIdx.x];
+            else if (qq < q1) v.x = __ldcs(a.read_key + 2 * qq);                       // the column's odd last row
+            key[2 * u] = v.x; key[2 * u + 1] = v.y;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[stage]);             // this warp is done with the stage
+        if (threadIdx.x == 0 && t + kProbeStages < n_tiles) {    // refill it once every warp is
+            mbar_wait(&s_empty[stage], parity);
+            const unsigned bytes = tile_pairs(t + kProbeStages) * 16u;
+            mbar_expect_tx(&s_full[stage], bytes);
+            if (bytes) bulk_load(ring + (size_t)stage * kProbeBatch, pairs + qt + (long long)kProbeStages * kProbeBatch, bytes, &s_full[stage]);
+        }
         unsigned pass = 0;
 #pragma unroll
         for (int u = 0; u < kProbeRows; ++u) {
-            const long long row = 2 * (q + (long long)(u >> 1) * kProbeThreads) + (u & 1);
+            const long long row = 2 * (qt + (long long)(u >> 1) * kProbeThreads + threadIdx.x) + (u & 1);
             const unsigned m = bloom_bits(key[u]);
             if (row >= r0 && row < r1 && (s_bm[bloom_word(key[u], bmw)] & m) == m) pass |= 1u << u;
         }
@@ -420,8 +469,8 @@ k_probe(PhaseArgs a) {
         int inc = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
+            const int x = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += x;
         }
         int wbase = 0;
         if (lane == 31 && inc) wbase = atomicAdd(&s_count, inc);
@@ -430,7 +479,7 @@ k_probe(PhaseArgs a) {
         for (int u = 0; u < kProbeRows; ++u)
             if (pass >> u & 1u) {
                 out_key[pos] = key[u];
-                out_row[pos] = (int)(2 * (q + (long long)(u >> 1) * kProbeThreads) + (u & 1));
+                out_row[pos] = (int)(2 * (qt + (long long)(u >> 1) * kProbeThreads + threadIdx.x) + (u & 1));
                 ++pos;
             }
     }
@@ -449,7 +498,7 @@ constexpr int kResolveUnroll = 3;
 
 __global__ void __launch_bounds__(kThreads)
 k_resolve(PhaseArgs a) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
+    extern __shared__ __align__(128) unsigned char s_raw[];
     dbg_mark(a, 1, 4);
     const int nt = a.n_probe_tiles;
     int *s_pre = reinterpret_cast<int *>(s_raw);                 // [nt + 1] candidates before each tile
