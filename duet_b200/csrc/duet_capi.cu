@@ -497,7 +497,7 @@ static void launch_all(duet_handle *h, cudaStream_t st, bool marks, bool concurr
             cudaStreamWaitEvent(st, h->ev_join, 0);
         }
         if (probe) {
-            k_resolve<<<h->n_sm * 4, kThreads, (size_t)(h->probe_grid + 1) * 4, st>>>(a);
+            k_resolve<<<h->n_sm * 8, kThreads, (size_t)(h->probe_grid + 1) * 20, st>>>(a);
             ++h->launches;
         }
     } else {

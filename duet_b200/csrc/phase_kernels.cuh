@@ -501,8 +501,16 @@ k_resolve(PhaseArgs a) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     dbg_mark(a, 1, 4);
     const int nt = a.n_probe_tiles;
-    int *s_pre = reinterpret_cast<int *>(s_raw);                 // [nt + 1] candidates before each tile
-    for (int i = threadIdx.x; i < nt; i += kThreads) s_pre[i + 1] = a.cand_n[i];
+    // per tile, staged once per block: where its candidates start, and its contig's slot range
+    long long *s_r0 = reinterpret_cast<long long *>(s_raw);      // [nt]
+    int *s_pre = reinterpret_cast<int *>(s_r0 + nt);             // [nt + 1] candidates before each tile
+    int *s_base = s_pre + nt + 1;                                // [nt]
+    unsigned *s_mask = reinterpret_cast<unsigned *>(s_base + nt);    // [nt]
+    for (int i = threadIdx.x; i < nt; i += kThreads) {
+        s_pre[i + 1] = a.cand_n[i];
+        const ProbeTile t = a.probe_tiles[i];
+        s_r0[i] = t.r0; s_base[i] = t.base; s_mask[i] = (unsigned)t.mask;
+    }
     if (threadIdx.x == 0) s_pre[0] = 0;
     __syncthreads();
     // inclusive scan of s_pre[1..nt] (nt is a few hundred to a few thousand): chunk per thread
@@ -527,10 +535,9 @@ k_resolve(PhaseArgs a) {
             if (g >= total) continue;
             int lo = 0, hi = nt;                                 // tile t with s_pre[t] <= g < s_pre[t+1]
             while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pre[mid] <= g) lo = mid; else hi = mid; }
-            const ProbeTile t = a.probe_tiles[lo];
-            const long long at = t.r0 + (g - s_pre[lo]);
+            const long long at = s_r0[lo] + (g - s_pre[lo]);
             key[u] = a.cand_key[at]; row[u] = a.cand_row[at];
-            base[u] = t.base; mask[u] = (unsigned)t.mask;
+            base[u] = s_base[lo]; mask[u] = s_mask[lo];
             pend |= 1u << u;
         }
 #pragma unroll
