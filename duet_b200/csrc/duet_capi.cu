@@ -378,15 +378,28 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     // k_probe tiles: row ranges that never cross a contig, about two per SM in total
     std::vector<ProbeTile> qtiles;
     {
-        // all tiles resident at once when possible: pieces are rounded DOWN (a contig gets at least one)
-        int live = 0;
-        for (int s = 0; s < ns; ++s) live += h->h_read_off[s + 1] > h->h_read_off[s];
-        const long long want = std::max(1, h->n_sm * kProbeBlocksPerSm - live / 2);
-        const long long per = std::max<long long>((R + want - 1) / want, 1);
+        // tiles of about equal size (a contig's rows are cut into round(rows / per) pieces), as many as fit
+        // on the device at once: more would mean a second wave costing a whole block time
+        long long max_words = 32;
+        for (int s = 0; s < ns; ++s) max_words = std::max<long long>(max_words, (long long)bm_wmask[s] + 1);
+        h->probe_smem = (size_t)kProbeRingBytes + (size_t)max_words * 4;
+        int occ = kProbeBlocksPerSm;                             // big filters leave room for one block per SM only
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_probe, kProbeThreads, h->probe_smem) != cudaSuccess || occ < 1) occ = 1;
+        const long long cap = std::max(1, h->n_sm * std::min(occ, kProbeBlocksPerSm));
+        long long per = std::max<long long>((R + cap - 1) / cap, 1);
+        for (;;) {
+            long long total = 0;
+            for (int s = 0; s < ns; ++s) {
+                const long long rows = h->h_read_off[s + 1] - h->h_read_off[s];
+                if (rows > 0) total += std::max<long long>(1, (rows + per / 2) / per);
+            }
+            if (total <= cap || per >= R) break;
+            per += per / 16 + 1;
+        }
         for (int s = 0; s < ns; ++s) {
             const long long b0 = h->h_read_off[s], b1 = h->h_read_off[s + 1];
             if (b1 <= b0) continue;
-            const long long pieces = std::max<long long>(1, (b1 - b0) / per);
+            const long long pieces = std::max<long long>(1, (b1 - b0 + per / 2) / per);
             for (long long k = 0; k < pieces; ++k) {
                 long long q0 = b0 + (b1 - b0) * k / pieces, q1 = b0 + (b1 - b0) * (k + 1) / pieces;
                 if (k > 0) q0 += q0 & 1;                         // interior cuts on 16-byte boundaries
@@ -429,11 +442,7 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     a.done_predict = a.done_reduce + ns;
     CU(h, h->d_sort.reserve(S1 * 32));                   a.sort_scratch = h->d_sort.as<long long>();
     CU(h, h->d_c2.reserve(S1 * sizeof(C2Rec)));          a.c2rec = h->d_c2.as<C2Rec>();
-    {
-        long long max_words = 32;
-        for (int s = 0; s < ns; ++s) max_words = std::max<long long>(max_words, (long long)bm_wmask[s] + 1);
-        h->probe_smem = (size_t)kProbeRingBytes + (size_t)max_words * 4;
-    }
+
     CU(h, h->d_gt.reserve(S1));                          a.gt = h->d_gt.as<uint8_t>();
     CU(h, h->d_cls.reserve(S1));                         a.cls = h->d_cls.as<uint8_t>();
     CU(h, h->d_ps.reserve(S1 * 4));                      a.ps = h->d_ps.as<int>();
