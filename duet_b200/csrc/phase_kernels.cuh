@@ -273,7 +273,7 @@ __device__ __forceinline__ unsigned bloom_bits(unsigned long long key) {
 // slot inserts: k_bloom sets the filter bits, k_table claims the slots.
 // Dependent chain of a k_table thread: [key, tile descriptor] -> CAS (-> CAS on a collision) -> stores.
 // ------------------------------------------------------------------------------------------
-constexpr int kBuildPerThread = 2;
+constexpr int kBuildPerThread = 1;
 constexpr int kBuildTile = kThreads * kBuildPerThread;
 
 // which shard (table range, filter range) support-read entry j of this tile belongs to
