@@ -87,9 +87,13 @@ def load() -> C.CDLL:
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m duet_b200.build` "
-            "(duet_b200 has no CPU fallback)")
+        try:                                   # a fresh checkout: compile the library (needs nvcc), never fall back
+            from . import build as _build
+            _build.build()
+        except Exception as e:
+            raise ImportError(
+                f"{LIB_PATH} is missing and could not be built ({e}): run `python -m duet_b200.build` "
+                "(duet_b200 has no CPU fallback)") from e
     lib = C.CDLL(LIB_PATH)
     H = C.c_void_p
     lib.duet_abi_version.restype = C.c_int
