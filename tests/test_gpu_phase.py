@@ -355,3 +355,28 @@ def test_random_batches_against_columnar_oracle(engine, seed):
         bb.shard([("a", 1, 5, 5)], [dict(pos=1, svread=3, refread=0, names=["a"])], contig="z")
         batch = bb.build()
     _compare_with_columnar_oracle(engine, batch, int(rng.choice([0, 50])), int(rng.choice([0, 2, 10])))
+
+
+def test_c2_full_size_parity(engine):
+    """BASELINE.json configs[1] at FULL size (4.5 M reads / 3.7 M haplotagged, 25 k SVs, 402 k joins, 24
+    contigs): every join row, class, genotype, PS, count, score sum, fp64 feature, the emission order and
+    the per-contig counters equal the oracle's."""
+    batch = from_synth(synth.config_c2(0), with_text=False)
+    assert batch.n_reads > 3_500_000 and batch.n_svs == 25_001
+    res = _compare_with_columnar_oracle(engine, batch, 50, 2)
+    assert res.shard_counts[:, 2].sum() == res.order.shape[0] > 15_000
+    # size-independent properties: emitted SVs are exactly those with a genotype; order is a permutation
+    # of them, sorted by position inside every contig
+    emitted = np.nonzero(res.gt)[0]
+    assert np.array_equal(np.sort(res.order), emitted)
+    shard = np.searchsorted(batch.sv_off, res.order, side="right") - 1
+    assert (np.diff(shard) >= 0).all()
+    same = np.diff(shard) == 0
+    assert (np.diff(batch.sv_pos[res.order])[same] >= 0).all()
+
+
+def test_c4_dense_full_size_parity(engine):
+    """BASELINE.json configs[3] shape (60x, dense support lists with a tail to 2 000 reads) at full size."""
+    batch = from_synth(synth.config_c4(0), with_text=False)
+    assert batch.n_joins > 1_500_000 and np.diff(batch.csr_off).max() >= 1500
+    _compare_with_columnar_oracle(engine, batch, 50, 2)
