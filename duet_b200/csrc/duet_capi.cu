@@ -384,7 +384,7 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         for (int s = 0; s < ns; ++s) max_words = std::max<long long>(max_words, (long long)bm_wmask[s] + 1);
         h->probe_smem = (size_t)kProbeRingBytes + (size_t)max_words * 4;
         int occ = kProbeBlocksPerSm;                             // big filters leave room for one block per SM only
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_probe, kProbeThreads, h->probe_smem) != cudaSuccess || occ < 1) occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_probe, kProbeBlock, h->probe_smem) != cudaSuccess || occ < 1) occ = 1;
         const long long cap = std::max(1, h->n_sm * std::min(occ, kProbeBlocksPerSm));
         long long per = std::max<long long>((R + cap - 1) / cap, 1);
         for (;;) {
@@ -498,7 +498,7 @@ static void launch_all(duet_handle *h, cudaStream_t st, bool marks, bool concurr
         h->launches += 4;
         mark(EV_K1);
         if (probe) {
-            k_probe<<<h->probe_grid, kProbeThreads, h->probe_smem, st>>>(a);
+            k_probe<<<h->probe_grid, kProbeBlock, h->probe_smem, st>>>(a);
             ++h->launches;
         }
         if (concurrent) {

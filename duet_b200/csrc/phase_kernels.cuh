@@ -363,7 +363,8 @@ k_table(PhaseArgs a) {
 // ~90 % of the rows (reads that support no SV) never leave the SM; the survivors are appended to the
 // block's private stretch of the candidate list for k_resolve.
 // ------------------------------------------------------------------------------------------
-constexpr int kProbeThreads = 512;
+constexpr int kProbeThreads = 512;                               // consumer threads
+constexpr int kProbeBlock = kProbeThreads + 32;                  // + one producer warp that only issues copies
 constexpr int kProbeBlocksPerSm = 2;
 constexpr int kProbeUnroll = 2;                                  // 16-byte pairs per thread per tile
 constexpr int kProbeRows = 2 * kProbeUnroll;                     // rows per thread per tile
@@ -396,7 +397,7 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned b
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(kProbeThreads, kProbeBlocksPerSm)
+__global__ void __launch_bounds__(kProbeBlock, kProbeBlocksPerSm)
 k_probe(PhaseArgs a) {
     extern __shared__ __align__(128) unsigned char s_raw[];      // [key ring | filter words]
     __shared__ __align__(8) unsigned long long s_full[kProbeStages], s_empty[kProbeStages];
@@ -429,10 +430,24 @@ k_probe(PhaseArgs a) {
         }
     }
     const uint4 *src = reinterpret_cast<const uint4 *>(a.bitmap + tile.bmo);
-    for (int i = threadIdx.x; i < (int)(bmw + 1) / 4; i += kProbeThreads)
+    for (int i = threadIdx.x; i < (int)(bmw + 1) / 4; i += kProbeBlock)
         reinterpret_cast<uint4 *>(s_bm)[i] = src[i];
     __syncthreads();
     dbg_mark(a, 1, 1);
+    if (threadIdx.x >= kProbeThreads) {
+        // producer warp: refill a stage as soon as every consumer warp has handed it back.  The wait is
+        // warp-uniform (all 32 lanes spin together), one lane issues the copy.
+        for (int t = kProbeStages; t < n_tiles; ++t) {
+            const int stage = t % kProbeStages;
+            mbar_wait(&s_empty[stage], (unsigned)(t / kProbeStages - 1) & 1u);
+            if (lane == 0) {
+                const unsigned bytes = tile_pairs(t) * 16u;
+                mbar_expect_tx(&s_full[stage], bytes);
+                if (bytes) bulk_load(ring + (size_t)stage * kProbeBatch, pairs + q0 + (long long)t * kProbeBatch, bytes, &s_full[stage]);
+            }
+            __syncwarp();
+        }
+    } else {
     unsigned long long *out_key = a.cand_key + r0;               // this block's private stretch of the list
     int *out_row = a.cand_row + r0;
     for (int t = 0; t < n_tiles; ++t) {
@@ -449,14 +464,6 @@ k_probe(PhaseArgs a) {
             else if (qq < q1) v.x = __ldcs(a.read_key + 2 * qq);                       // the column's odd last row
             key[2 * u] = v.x; key[2 * u + 1] = v.y;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[stage]);             // this warp is done with the stage
-        if (threadIdx.x == 0 && t + kProbeStages < n_tiles) {    // refill it once every warp is
-            mbar_wait(&s_empty[stage], parity);
-            const unsigned bytes = tile_pairs(t + kProbeStages) * 16u;
-            mbar_expect_tx(&s_full[stage], bytes);
-            if (bytes) bulk_load(ring + (size_t)stage * kProbeBatch, pairs + qt + (long long)kProbeStages * kProbeBatch, bytes, &s_full[stage]);
-        }
         unsigned pass = 0;
 #pragma unroll
         for (int u = 0; u < kProbeRows; ++u) {
@@ -472,6 +479,12 @@ k_probe(PhaseArgs a) {
             const int x = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += x;
         }
+        // Hand the stage back only HERE: the scan has consumed every lane's filter result, so every lane's
+        // ring loads have returned their data.  An arrive placed right after the loads is issued while they
+        // are still in flight (nothing waits on their scoreboard); with another kernel's atomics backing up
+        // the load/store unit on the same SM the refill then overtook them (measured: a warp read the tile
+        // three ahead, lost joins).
+        if (lane == 0) mbar_arrive(&s_empty[stage]);
         int wbase = 0;
         if (lane == 31 && inc) wbase = atomicAdd(&s_count, inc);
         int pos = __shfl_sync(0xffffffffu, wbase, 31) + inc - cnt;
@@ -482,6 +495,7 @@ k_probe(PhaseArgs a) {
                 out_row[pos] = (int)(2 * (qt + (long long)(u >> 1) * kProbeThreads + threadIdx.x) + (u & 1));
                 ++pos;
             }
+    }
     }
     __syncthreads();
     if (threadIdx.x == 0) a.cand_n[blockIdx.x] = s_count;
