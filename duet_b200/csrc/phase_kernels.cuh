@@ -636,12 +636,29 @@ __device__ void oneps_block_small(const PhaseArgs &a, int s, long long *smem_til
     for (int u = 0; u < kPer; ++u)
         if (found[u] != INT32_MIN) tab[w++] = found[u];
     const int m_pad = next_pow2(max(m, 1));
-    __syncthreads();
-    for (int i = m + threadIdx.x; i < m_pad; i += kThreads) tab[i] = INT32_MAX;
-    __syncthreads();
-    block_bitonic_sort(tab, m_pad);
     const int off = s_has_min;
-    for (int i = threadIdx.x; i < m; i += kThreads) a.oneps[b + off + i] = tab[i];
+    __syncthreads();
+    if (m <= 2 * kThreads) {
+        // the values are distinct, so a value's rank IS its place in the sorted list: one pass over the
+        // list in shared memory (four values per load) instead of a sorting network of barriers
+        if (threadIdx.x < 4) tab[m + threadIdx.x] = INT32_MAX;
+        __syncthreads();
+        const int i0 = threadIdx.x, i1 = threadIdx.x + kThreads;
+        const int v0 = i0 < m ? tab[i0] : 0, v1 = i1 < m ? tab[i1] : 0;
+        int r0 = 0, r1 = 0;
+        for (int j = 0; j < m; j += 4) {
+            const int4 x = *reinterpret_cast<const int4 *>(tab + j);
+            r0 += (x.x < v0) + (x.y < v0) + (x.z < v0) + (x.w < v0);
+            r1 += (x.x < v1) + (x.y < v1) + (x.z < v1) + (x.w < v1);
+        }
+        if (i0 < m) a.oneps[b + off + r0] = v0;
+        if (i1 < m) a.oneps[b + off + r1] = v1;
+    } else {
+        for (int i = m + threadIdx.x; i < m_pad; i += kThreads) tab[i] = INT32_MAX;
+        __syncthreads();
+        block_bitonic_sort(tab, m_pad);
+        for (int i = threadIdx.x; i < m; i += kThreads) a.oneps[b + off + i] = tab[i];
+    }
     if (threadIdx.x == 0) {
         if (off) a.oneps[b] = INT32_MIN;
         a.oneps_n[s] = m + off;
