@@ -3,6 +3,7 @@
 // column pointers.  No CPU fallback exists: every entry point needs a CUDA device.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -44,8 +45,6 @@ enum { EV_H2D0, EV_H2D1, EV_X0, EV_K0, EV_K1, EV_K2, EV_K3, EV_K4, EV_D2H0, EV_D
 struct duet_handle {
     int device = 0;
     cudaStream_t own_stream = nullptr;
-    cudaStream_t side_stream = nullptr;    // second branch of the per-call graph
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[EV_COUNT] = {};
     duet_thresholds thr;
@@ -66,7 +65,7 @@ struct duet_handle {
     DevBuf in_csr_off, in_csr_key, in_csr_chk;
     // descriptors, table, scratch, outputs
     DevBuf d_read_off, d_sv_off, d_join_off, d_sv_shard, d_tab_off, d_tab_mask, d_done, d_c2;
-    DevBuf d_btiles, d_rtiles, d_ptiles, d_qtiles, d_dbg, d_cand_key, d_cand_row, d_cand_n;
+    DevBuf d_btiles, d_rtiles, d_ptiles, d_qtiles, d_dbg, d_cand_key, d_cand_row;
     int probe_grid = 0;
     int reduce_lanes = kReduceLanesSparse;
     cudaGraph_t graph = nullptr;
@@ -116,6 +115,21 @@ long long pow2_at_least(long long n) {
 
 }  // namespace
 
+// One launch of the chain.  `pdl`: with the programmatic-serialization attribute the kernel's blocks may be
+// scheduled once every block of the previous kernel has started; the kernel itself waits (pdl_wait in
+// phase_kernels.cuh) before it touches anything the previous kernel writes.
+template <typename... Params, typename... Args>
+static void launch(void (*kernel)(Params...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, Params(args)...);
+}
+
 extern "C" {
 
 int duet_abi_version(void) { return DUET_ABI_VERSION; }
@@ -163,13 +177,6 @@ int duet_create(int device_id, duet_handle **out) {
         return fail(nullptr, DUET_ERR_CUDA, msg);
     }
     h->stream = h->own_stream;
-    {   // the table branch yields to the probe branch: lowest priority for its stream / graph nodes
-        int lo_prio = 0, hi_prio = 0;
-        cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
-        cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, lo_prio);
-    }
-    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     for (auto &ev : h->cl_ev) cudaEventCreate(&ev);
     {   // fails here, loudly, if the image was not built for this device (sm_100a only)
@@ -177,13 +184,11 @@ int duet_create(int device_id, duet_handle **out) {
         cudaFuncGetAttributes(&fa, k_probe);
         cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, kBloomMaxWords * 4 + kProbeRingBytes);
         // one shared-memory carveout for all four kernels: switching it between launches drains the SMs
-        cudaFuncSetAttribute(k_bloom, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_table, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_probe, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_reduce<kReduceLanesSparse>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_reduce<kReduceLanesDense>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_predict, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(k_resolve, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_init, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device_id);
     }
@@ -202,7 +207,7 @@ void duet_destroy(duet_handle *h) {
     DevBuf *bufs[] = {&h->in_read_key, &h->in_read_tag,
                       &h->in_sv_pos, &h->in_sv_svlen, &h->in_sv_svread, &h->in_sv_refread, &h->in_sv_flags,
                       &h->in_sv_group, &h->in_csr_off, &h->in_csr_key, &h->in_csr_chk, &h->d_read_off,
-                      &h->d_sv_off, &h->d_join_off, &h->d_c2, &h->d_btiles, &h->d_rtiles, &h->d_ptiles, &h->d_qtiles, &h->d_dbg, &h->d_cand_key, &h->d_cand_row, &h->d_cand_n, &h->d_sv_shard, &h->d_done, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_bm_off, &h->d_bm_wmask, &h->d_next,
+                      &h->d_sv_off, &h->d_join_off, &h->d_c2, &h->d_btiles, &h->d_rtiles, &h->d_ptiles, &h->d_qtiles, &h->d_dbg, &h->d_cand_key, &h->d_cand_row, &h->d_sv_shard, &h->d_done, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_bm_off, &h->d_bm_wmask, &h->d_next,
                       &h->d_join_row, &h->d_n_hit, &h->d_cand, &h->d_oneps, &h->d_oneps_n, &h->d_sort, &h->d_gt,
                       &h->d_cls, &h->d_ps, &h->d_hap1, &h->d_hap2, &h->d_hap0, &h->d_allhap, &h->d_t1, &h->d_t2,
                       &h->d_feat, &h->d_order, &h->d_n_emit, &h->d_counts, &h->d_status};
@@ -214,9 +219,6 @@ void duet_destroy(duet_handle *h) {
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->graph) cudaGraphDestroy(h->graph);
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->ev_join) cudaEventDestroy(h->ev_join);
-    if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -432,7 +434,6 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     CU(h, h->d_next.reserve(J1 * 4));                    a.next = h->d_next.as<int>();
     CU(h, h->d_cand_key.reserve((size_t)std::max<long long>(R, 1) * 8)); a.cand_key = h->d_cand_key.as<unsigned long long>();
     CU(h, h->d_cand_row.reserve((size_t)std::max<long long>(R, 1) * 4)); a.cand_row = h->d_cand_row.as<int>();
-    CU(h, h->d_cand_n.reserve((size_t)h->probe_grid * 4));               a.cand_n = h->d_cand_n.as<int>();
     CU(h, h->d_join_row.reserve(J1 * 4 + 16));                a.join_row = h->d_join_row.as<int>();
     CU(h, h->d_n_hit.reserve(S1 * 4));                   a.n_hit = h->d_n_hit.as<int>();
     CU(h, h->d_cand.reserve(S1 * 8));                    a.cand = h->d_cand.as<long long>();
@@ -473,40 +474,24 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     return DUET_OK;
 }
 
-// The launches of one call.  Dependencies: filter init -> k_bloom -> k_probe (the read stream needs only the
-// filter) and table init -> k_table (slot inserts) are independent branches that meet at k_resolve.
-// `concurrent`: the two branches run on two streams (fork/join with events; this is what the CUDA graph
-// captures).  Otherwise everything is serial on `st` and, with `marks`, an event follows each stage.
-static void launch_all(duet_handle *h, cudaStream_t st, bool marks, bool concurrent) {
+// The launches of one call, a serial chain on `st`: k_init -> k_table -> k_probe -> k_reduce -> k_predict
+// (with `marks`, an event follows each stage).
+static void launch_all(duet_handle *h, cudaStream_t st, bool marks) {
     auto mark = [&](int ev) { if (marks) cudaEventRecord(h->ev[ev], st); };
+    static const bool no_pdl = std::getenv("DUET_NO_PDL") != nullptr;      // diagnostic switch
+    const bool pdl = !marks && !no_pdl;
     const PhaseArgs &a = h->a;
     const int S = a.n_svs;
     const bool join = a.n_joins > 0, probe = a.n_reads && a.n_joins;
     const int build_blocks = (int)((a.n_joins + kBuildTile - 1) / kBuildTile);
     if (join) {
-        cudaStream_t tb = st;                       // stream of the table branch
-        if (concurrent) {
-            tb = h->side_stream;
-            cudaEventRecord(h->ev_fork, st);
-            cudaStreamWaitEvent(tb, h->ev_fork, 0);
-        }
-        k_init<<<h->n_sm * 2, kThreads, 0, st>>>(a, h->n_slots, h->n_bm_words, kInitFilter);
-        k_init<<<h->n_sm * 4, kThreads, 0, tb>>>(a, h->n_slots, h->n_bm_words, kInitTable);
+        launch(k_init, h->n_sm * 4, kThreads, 0, st, false, a, h->n_slots, h->n_bm_words, (int)(kInitTable | kInitFilter));
         mark(EV_K0);
-        k_bloom<<<build_blocks, kThreads, 0, st>>>(a);
-        k_table<<<build_blocks, kThreads, 0, tb>>>(a);
-        h->launches += 4;
+        launch(k_table, build_blocks, kThreads, 0, st, pdl, a);
+        h->launches += 2;
         mark(EV_K1);
         if (probe) {
-            k_probe<<<h->probe_grid, kProbeBlock, h->probe_smem, st>>>(a);
-            ++h->launches;
-        }
-        if (concurrent) {
-            cudaEventRecord(h->ev_join, tb);
-            cudaStreamWaitEvent(st, h->ev_join, 0);
-        }
-        if (probe) {
-            k_resolve<<<h->n_sm * 8, kThreads, (size_t)(h->probe_grid + 1) * 20, st>>>(a);
+            launch(k_probe, h->probe_grid, kProbeBlock, h->probe_smem, st, pdl, a);
             ++h->launches;
         }
     } else {
@@ -516,13 +501,13 @@ static void launch_all(duet_handle *h, cudaStream_t st, bool marks, bool concurr
     mark(EV_K2);
     if (S) {
         const int per = kThreads / h->reduce_lanes;
-        if (h->reduce_lanes == kReduceLanesDense) k_reduce<kReduceLanesDense><<<(S + per - 1) / per, kThreads, 0, st>>>(a);
-        else k_reduce<kReduceLanesSparse><<<(S + per - 1) / per, kThreads, 0, st>>>(a);
+        if (h->reduce_lanes == kReduceLanesDense) launch(k_reduce<kReduceLanesDense>, (S + per - 1) / per, kThreads, 0, st, pdl, a);
+        else launch(k_reduce<kReduceLanesSparse>, (S + per - 1) / per, kThreads, 0, st, pdl, a);
         ++h->launches;
     }
     mark(EV_K3);
     if (S) {
-        k_predict<<<(S + kPredictPerBlock - 1) / kPredictPerBlock, kThreads, 0, st>>>(a);
+        launch(k_predict, (S + kPredictPerBlock - 1) / kPredictPerBlock, kThreads, 0, st, pdl, a);
         ++h->launches;
     }
 }
@@ -539,7 +524,7 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
     h->per_kernel = per_kernel != 0;
     CU(h, cudaEventRecord(h->ev[EV_X0], st));
     if (h->per_kernel) {
-        launch_all(h, st, true, false);
+        launch_all(h, st, true);
     } else {
         // the launch sequence of a staged batch never changes: replay it as a CUDA graph.  A re-upload
         // of the same shapes lands in the same buffers, so the captured graph stays valid.
@@ -555,9 +540,9 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
             h->graph_valid = true;
             const int64_t before = h->launches;
             if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-                launch_all(h, st, false, true);
+                launch_all(h, st, false);
                 if (cudaStreamEndCapture(st, &h->graph) != cudaSuccess ||
-                    cudaGraphInstantiateWithFlags(&h->graph_exec, h->graph, cudaGraphInstantiateFlagUseNodePriority) != cudaSuccess) {
+                    cudaGraphInstantiate(&h->graph_exec, h->graph, 0) != cudaSuccess) {
                     h->graph_exec = nullptr;
                 }
             }
@@ -566,9 +551,9 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
         }
         if (h->graph_exec) {
             CU(h, cudaGraphLaunch(h->graph_exec, st));
-            h->launches += (h->a.n_joins ? 4 : 0) + (h->a.n_reads && h->a.n_joins ? 2 : 0) + (h->a.n_svs ? 2 : 0);
+            h->launches += (h->a.n_joins ? 2 : 0) + (h->a.n_reads && h->a.n_joins ? 1 : 0) + (h->a.n_svs ? 2 : 0);
         } else {
-            launch_all(h, st, false, false);
+            launch_all(h, st, false);
         }
     }
     CU(h, cudaEventRecord(h->ev[EV_K4], st));

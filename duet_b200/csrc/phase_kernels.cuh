@@ -2,12 +2,12 @@
 //
 // Reference behaviour restated per kernel (citations: /root/reference/src/duet/sv_phasing_fn.py):
 //   k_init     start-of-call state: EMPTY slot table, zero Bloom filter, join results -1
-//   k_bloom    + k_table: the dict-insert side of the JOIN (:26-29 keyed by QNAME) -- here the SMALL
-//              side is inserted: the support-read names of the SVs (:46-48)
+//   k_table    the dict-insert side of the JOIN (:26-29 keyed by QNAME) -- here the SMALL side is
+//              inserted: the support-read names of the SVs (:46-48); also sets their Bloom filter bits
 //   k_probe    the haplotagged reads streamed once through the contig's Bloom filter (shared memory);
-//              survivors go to a candidate list
-//   k_resolve  candidates looked up in the slot table; a hit records the row index on every support-read
-//              entry of that name with atomicMax == "a later row overwrites an earlier one" (:29)
+//              the block then looks its survivors up in the slot table: a hit records the row index on
+//              every support-read entry of that name with atomicMax == "a later row overwrites an
+//              earlier one" (:29)
 //   k_reduce   per SV: gather the joined reads' tags, class = #distinct PS (:192-194), one-PS candidate
 //              (:195-203), class-1 counts and score sums (:74-84), per-PS statistics of class-2 SVs in
 //              first-seen order (:85-105); the block completing a contig builds its sorted unique
@@ -39,7 +39,7 @@ constexpr int kReduceLanesSparse = 8;                 // lanes per SV in k_reduc
 constexpr int kReduceLanesDense = 32;                 // ... dense lists (mean > 32 reads)
 constexpr int kPredictPerBlock = 64;
 constexpr int kSortSmemBytes = 16384;                 // slow-path sort tile in shared memory
-constexpr int kBloomMaxWords = 32768;                 // 128 KB of shared memory per shard filter
+constexpr int kBloomMaxWords = 16384;                 // 64 KB of shared memory per shard filter: two k_probe blocks per SM
 
 // One slot of the join table: 16 bytes, loaded in one request.
 struct __align__(16) Slot {
@@ -82,7 +82,6 @@ struct PhaseArgs {
     int n_probe_tiles;
     unsigned long long *cand_key;   // [R] rows that passed their contig's filter: tile t appends at [r0(t), ...)
     int *cand_row;                  // [R]
-    int *cand_n;                    // [n_probe_tiles] candidates each tile found
     const unsigned long long *read_key;
     const ReadTag *read_tag;
     const int *sv_pos, *sv_svlen, *sv_svread, *sv_refread;
@@ -120,6 +119,14 @@ struct PhaseArgs {
     DevStatus *status;
     long long *dbg;              // optional per-block timestamps (duet_debug_timers), NULL in production
 };
+
+// ---- programmatic dependent launch: the kernels of one call are launched back to back with the
+// programmatic-serialization attribute, so a kernel's blocks are scheduled as soon as every block of its
+// predecessor has STARTED (pdl_trigger) and do their own set-up -- tile descriptors, barrier init, first
+// copies of the INPUT columns -- under the predecessor's tail; pdl_wait() returns once the predecessor
+// has completed and its writes are visible.  Every kernel calls both, so completion is transitive.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- optional instrumentation: thread 0 of every block stamps (globaltimer, clock64) at mark k ----
 constexpr int kDbgBlocks = 2048, kDbgMarks = 8;
@@ -243,6 +250,8 @@ enum { kInitTable = 1, kInitFilter = 2 };
 
 __global__ void __launch_bounds__(kThreads)
 k_init(PhaseArgs a, long long n_slots, long long n_bm_words, int what) {
+    pdl_trigger();
+    pdl_wait();
     const long long stride = (long long)gridDim.x * kThreads;
     const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
     const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0u, 0u, 0u, 0u);
@@ -269,8 +278,7 @@ __device__ __forceinline__ unsigned bloom_bits(unsigned long long key) {
 }
 
 // ------------------------------------------------------------------------------------------
-// The build side, two kernels so that the probe stream (which needs only the filter) overlaps the
-// slot inserts: k_bloom sets the filter bits, k_table claims the slots.
+// The build side: k_table claims a slot per support-read name and sets the name's filter bits.
 // Dependent chain of a k_table thread: [key, tile descriptor] -> CAS (-> CAS on a collision) -> stores.
 // ------------------------------------------------------------------------------------------
 constexpr int kBuildPerThread = 1;
@@ -287,29 +295,6 @@ __device__ __forceinline__ void build_where(const PhaseArgs &a, const BuildTile 
     }
 }
 
-// k_bloom: two filter bits per support-read name, fire-and-forget (the probe stream only needs these,
-// so it can start while k_table is still inserting)
-__global__ void __launch_bounds__(kThreads)
-k_bloom(PhaseArgs a) {
-    const long long j0 = (long long)blockIdx.x * kBuildTile + threadIdx.x;
-    unsigned long long key[kBuildPerThread];
-#pragma unroll
-    for (int u = 0; u < kBuildPerThread; ++u) {
-        const long long j = j0 + u * kThreads;
-        key[u] = j < a.n_joins ? __ldg(a.csr_key + j) : 0ull;
-    }
-    const BuildTile t = a.build_tiles[blockIdx.x];
-#pragma unroll
-    for (int u = 0; u < kBuildPerThread; ++u) {
-        const long long j = j0 + u * kThreads;
-        if (j >= a.n_joins) continue;
-        int base, bmo;
-        unsigned mask, bmw;
-        build_where(a, t, j, base, mask, bmo, bmw);
-        atomicOr(a.bitmap + bmo + (int)bloom_word(key[u], bmw), bloom_bits(key[u]));
-    }
-}
-
 // k_table: claim a slot per name (CAS; both names of a thread in flight together); the first entry of
 // a name owns the slot, further entries chain themselves behind it
 __global__ void __launch_bounds__(kThreads)
@@ -323,6 +308,8 @@ k_table(PhaseArgs a) {
         key[u] = j < a.n_joins ? __ldcs(a.csr_key + j) : 0ull;
     }
     const BuildTile t = a.build_tiles[blockIdx.x];
+    pdl_trigger();
+    pdl_wait();                                                  // the slots and the filter words are initialised
     unsigned p[kBuildPerThread], mask[kBuildPerThread];
     int base[kBuildPerThread];
     unsigned pend = 0;
@@ -333,6 +320,7 @@ k_table(PhaseArgs a) {
         int bmo;
         unsigned bmw;
         build_where(a, t, j, base[u], mask[u], bmo, bmw);
+        atomicOr(a.bitmap + bmo + (int)bloom_word(key[u], bmw), bloom_bits(key[u]));    // fire and forget
         p[u] = slot_hash(key[u]) & mask[u];
         pend |= 1u << u;
     }
@@ -356,12 +344,13 @@ k_table(PhaseArgs a) {
 
 // ------------------------------------------------------------------------------------------
 // k_probe: the haplotagged reads are STREAMED once by one block per tile -- a tile is a row range of ONE
-// contig, sized so that the grid is about two blocks per SM.  One thread keeps a ring of 16 KB key tiles
-// in flight with bulk asynchronous copies (TMA, cp.async.bulk + mbarrier complete_tx); warps consume a
-// tile as soon as its barrier flips and hand the stage back through an `empty` barrier -- no block-wide
-// synchronisation inside the stream.  The block keeps the contig's Bloom filter in shared memory, so
-// ~90 % of the rows (reads that support no SV) never leave the SM; the survivors are appended to the
-// block's private stretch of the candidate list for k_resolve.
+// contig, sized so that the grid is about two blocks per SM.  A producer warp keeps a ring of 16 KB key
+// tiles in flight with bulk asynchronous copies (TMA, cp.async.bulk + mbarrier complete_tx); the consumer
+// warps take a tile as soon as its barrier flips and hand the stage back through an `empty` barrier --
+// no block-wide synchronisation inside the stream.  The block keeps the contig's Bloom filter in shared
+// memory, so ~90 % of the rows (reads that support no SV) never leave the SM; the survivors are appended
+// to the block's private stretch of the candidate list, and when the stream is done the whole block
+// resolves them against the slot table, a few candidates per thread in flight together.
 // ------------------------------------------------------------------------------------------
 constexpr int kProbeThreads = 512;                               // consumer threads
 constexpr int kProbeBlock = kProbeThreads + 32;                  // + one producer warp that only issues copies
@@ -371,6 +360,7 @@ constexpr int kProbeRows = 2 * kProbeUnroll;                     // rows per thr
 constexpr int kProbeBatch = kProbeThreads * kProbeUnroll;        // pairs per tile (16 KB)
 constexpr int kProbeStages = 3;                                  // tiles in flight per block
 constexpr int kProbeRingBytes = kProbeStages * kProbeBatch * 16;
+constexpr int kResolveUnroll = 4;                                // candidates per thread in flight in the drain
 
 // ---- mbarrier / bulk-copy (TMA) primitives ------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -429,6 +419,8 @@ k_probe(PhaseArgs a) {
             if (bytes) bulk_load(ring + (size_t)t * kProbeBatch, pairs + q0 + (long long)t * kProbeBatch, bytes, &s_full[t]);
         }
     }
+    pdl_trigger();
+    pdl_wait();                                                  // k_table is done: filter bits and slots are final
     const uint4 *src = reinterpret_cast<const uint4 *>(a.bitmap + tile.bmo);
     for (int i = threadIdx.x; i < (int)(bmw + 1) / 4; i += kProbeBlock)
         reinterpret_cast<uint4 *>(s_bm)[i] = src[i];
@@ -498,69 +490,34 @@ k_probe(PhaseArgs a) {
     }
     }
     __syncthreads();
-    if (threadIdx.x == 0) a.cand_n[blockIdx.x] = s_count;
     dbg_mark(a, 1, 2);
-}
-
-// ------------------------------------------------------------------------------------------
-// k_resolve: one thread per candidate row (a read that passed its contig's filter): one 16-byte slot
-// load decides; a hit pushes the row index to every support-read entry of that name with atomicMax
-// -- a later row overrides an earlier one (sv_phasing_fn.py:29) -- and starts pulling the row's tag
-// record into L2 for k_reduce.
-// ------------------------------------------------------------------------------------------
-constexpr int kResolveUnroll = 3;
-
-__global__ void __launch_bounds__(kThreads)
-k_resolve(PhaseArgs a) {
-    extern __shared__ __align__(128) unsigned char s_raw[];
-    dbg_mark(a, 1, 4);
-    const int nt = a.n_probe_tiles;
-    // per tile, staged once per block: where its candidates start, and its contig's slot range
-    long long *s_r0 = reinterpret_cast<long long *>(s_raw);      // [nt]
-    int *s_pre = reinterpret_cast<int *>(s_r0 + nt);             // [nt + 1] candidates before each tile
-    int *s_base = s_pre + nt + 1;                                // [nt]
-    unsigned *s_mask = reinterpret_cast<unsigned *>(s_base + nt);    // [nt]
-    for (int i = threadIdx.x; i < nt; i += kThreads) {
-        s_pre[i + 1] = a.cand_n[i];
-        const ProbeTile t = a.probe_tiles[i];
-        s_r0[i] = t.r0; s_base[i] = t.base; s_mask[i] = (unsigned)t.mask;
-    }
-    if (threadIdx.x == 0) s_pre[0] = 0;
-    __syncthreads();
-    // inclusive scan of s_pre[1..nt] (nt is a few hundred to a few thousand): chunk per thread
-    const int per = (nt + kThreads - 1) / kThreads;
-    const int c0 = min(nt, (int)threadIdx.x * per), c1 = min(nt, c0 + per);
-    int sum = 0;
-    for (int i = c0; i < c1; ++i) sum += s_pre[i + 1];
-    int run = block_scan_exclusive(sum, 0, OpSum(), (int *)nullptr);
-    for (int i = c0; i < c1; ++i) { run += s_pre[i + 1]; s_pre[i + 1] = run; }
-    __syncthreads();
-    const int total = s_pre[nt];
-    const int stride = gridDim.x * kThreads;
-    dbg_mark(a, 1, 5);
-    for (int g0 = blockIdx.x * kThreads + threadIdx.x; g0 < total; g0 += stride * kResolveUnroll) {
+    // Resolve the block's candidates (all 17 warps): one 16-byte slot load decides; a hit pushes the row
+    // index to every support-read entry of that name with atomicMax -- a later row overrides an earlier
+    // one (sv_phasing_fn.py:29) -- and starts pulling the row's tag record into L2 for k_reduce.
+    // Dependent chain: candidate (L2, written by this block) -> slot -> [chain of duplicate entries].
+    const int total = s_count;
+    const unsigned long long *q_key = a.cand_key + r0;
+    const int *q_row = a.cand_row + r0;
+    const int base = tile.base;
+    const unsigned mask = (unsigned)tile.mask;
+    for (int g0 = threadIdx.x; g0 < total; g0 += kProbeBlock * kResolveUnroll) {
         unsigned long long key[kResolveUnroll];
-        int row[kResolveUnroll], base[kResolveUnroll];
-        unsigned mask[kResolveUnroll], p[kResolveUnroll];
+        int row[kResolveUnroll];
+        unsigned p[kResolveUnroll];
         unsigned pend = 0;
 #pragma unroll
         for (int u = 0; u < kResolveUnroll; ++u) {
-            const int g = g0 + u * stride;
-            if (g >= total) continue;
-            int lo = 0, hi = nt;                                 // tile t with s_pre[t] <= g < s_pre[t+1]
-            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pre[mid] <= g) lo = mid; else hi = mid; }
-            const long long at = s_r0[lo] + (g - s_pre[lo]);
-            key[u] = a.cand_key[at]; row[u] = a.cand_row[at];
-            base[u] = s_base[lo]; mask[u] = s_mask[lo];
-            pend |= 1u << u;
+            const int g = g0 + u * kProbeBlock;
+            key[u] = 0ull; row[u] = 0;
+            if (g < total) { key[u] = __ldcg(q_key + g); row[u] = __ldcg(q_row + g); pend |= 1u << u; }
         }
 #pragma unroll
-        for (int u = 0; u < kResolveUnroll; ++u) p[u] = slot_hash(key[u]) & mask[u];
+        for (int u = 0; u < kResolveUnroll; ++u) p[u] = slot_hash(key[u]) & mask;
         while (pend) {                                           // lock step: one slot load per pending candidate
             uint4 sl[kResolveUnroll];
 #pragma unroll
             for (int u = 0; u < kResolveUnroll; ++u)
-                if (pend >> u & 1u) sl[u] = *reinterpret_cast<const uint4 *>(a.tab + base[u] + p[u]);     // key, first, head
+                if (pend >> u & 1u) sl[u] = __ldcg(reinterpret_cast<const uint4 *>(a.tab + base + p[u]));     // key, first, head
 #pragma unroll
             for (int u = 0; u < kResolveUnroll; ++u) {
                 if (!(pend >> u & 1u)) continue;
@@ -568,17 +525,17 @@ k_resolve(PhaseArgs a) {
                 if (k == key[u]) {
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(a.read_tag + row[u]));     // k_reduce needs it next
                     atomicMax(a.join_row + (int)sl[u].z, row[u]);
-                    for (int h = (int)sl[u].w; h >= 0; h = a.next[h]) atomicMax(a.join_row + h, row[u]);
+                    for (int h = (int)sl[u].w; h >= 0; h = __ldcg(a.next + h)) atomicMax(a.join_row + h, row[u]);
                     pend &= ~(1u << u);
                 } else if (k == kEmptyKey) {
                     pend &= ~(1u << u);
                 } else {
-                    p[u] = (p[u] + 1) & mask[u];
+                    p[u] = (p[u] + 1) & mask;
                 }
             }
         }
     }
-    dbg_mark(a, 1, 6);
+    dbg_mark(a, 1, 3);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -802,6 +759,8 @@ k_reduce(PhaseArgs a) {
                __ldg(a.sv_svread + sv) >= c_thr.suppread_thres &&
                !(__ldg(a.sv_flags + sv) & DUET_SV_GT_MISSING);
     }
+    pdl_trigger();
+    pdl_wait();                                                  // the join rows are final
     int hits = 0, ps_lo = INT32_MAX, ps_hi = INT32_MIN;
     int h1 = 0, h2 = 0, nq = 0;
     long long t1 = 0, t2 = 0;
@@ -1347,10 +1306,14 @@ k_predict(PhaseArgs a) {
     const bool mine = threadIdx.x < kPredictPerBlock && sv < blk1;
     int cls = DUET_CLS_FILTERED, shard = 0, n_list = 0;
     Class2Stats st{0, 0, 0, 0, 0, 0, 0};
-    if (mine) {                                                  // everything that does not depend on the tile
-        cls = a.cls[sv];
+    if (mine) {                                                  // inputs: requested before the wait
         shard = __ldg(a.sv_shard + sv);
         n_list = (int)(__ldg(a.csr_off + sv + 1) - __ldg(a.csr_off + sv));
+    }
+    pdl_trigger();
+    pdl_wait();                                                  // k_reduce's per-SV results and one-PS lists are final
+    if (mine) {                                                  // everything that does not depend on the tile
+        cls = a.cls[sv];
         st = Class2Stats{a.hap1[sv], a.hap2[sv], 0, a.allhap[sv], a.ps[sv], a.totsc1[sv], a.totsc2[sv]};
     }
     const int n0 = a.oneps_n[tile.s_first];

@@ -29,7 +29,7 @@ for it in range(4):
     eng.execute()
     eng.sync()
     eng.lib.duet_debug_timers(eng.h, 1, out.ctypes.data)
-names = ["k_build", "k_probe (+ k_resolve: marks 4-6)", "k_reduce", "k_predict"]
+names = ["k_table", "k_probe (mark 2: stream done, 3: candidates resolved)", "k_reduce", "k_predict"]
 t_first = None
 for k, nm in enumerate(names):
     g = out[k, :, :, 0].astype(np.float64)
@@ -47,7 +47,7 @@ for k, nm in enumerate(names):
           f"last block start +{(g[:, 0].max() - t0) / 1e3:.1f} us")
     for m in marks[1:]:
         ok = g[:, m] > 0
-        base_mark = 4 if (k == 1 and m >= 4) else 0      # marks 4.. of slot 1 belong to k_resolve
+        base_mark = 0
         d = (clk[ok, m] - clk[ok, base_mark]) / 1.965e3  # SM cycles -> us at 1965 MHz
         late = (g[ok, m] - t0) / 1e3
         print(f"    mark {m}: blocks {ok.sum():5d}  since block start mean {d.mean():7.2f} us  max {d.max():7.2f} us   "
