@@ -831,12 +831,20 @@ k_reduce(PhaseArgs a) {
             for (int u = 0; u < kReduceUnroll; ++u)
                 c2_update(g, gmask, row[u] >= 0 && pc[u] <= c_thr.pc_max, ps[u], pc[u], hp[u], n_d);
         } else {
-            for (long long base = b; base < e; base += G) {
-                const long long j = base + lane;
-                const int r = j < e ? a.join_row[j] : -1;
-                int xps = 0, xpc = 0, xhp = 0;
-                if (r >= 0) { const ReadTag t = load_tag(a, r); xps = t.ps; xpc = t.pc; xhp = (int)(t.hp & 0xffu); }
-                c2_update(g, gmask, r >= 0 && xpc <= c_thr.pc_max, xps, xpc, xhp, n_d);
+            for (long long base = b; base < e; base += G * kReduceUnroll) {      // same batching as the first pass
+#pragma unroll
+                for (int u = 0; u < kReduceUnroll; ++u) {
+                    const long long j = base + u * G + lane;
+                    row[u] = j < e ? a.join_row[j] : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < kReduceUnroll; ++u) {
+                    ps[u] = pc[u] = hp[u] = 0;
+                    if (row[u] >= 0) { const ReadTag t = load_tag(a, row[u]); ps[u] = t.ps; pc[u] = t.pc; hp[u] = (int)(t.hp & 0xffu); }
+                }
+#pragma unroll
+                for (int u = 0; u < kReduceUnroll; ++u)                          // u-major == read order
+                    c2_update(g, gmask, row[u] >= 0 && pc[u] <= c_thr.pc_max, ps[u], pc[u], hp[u], n_d);
             }
         }
         C2Rec *rec = a.c2rec + sv;
@@ -974,18 +982,27 @@ __device__ void class2_stats(const PhaseArgs &a, int sv, long long b, long long 
     st.h1 = st.h2 = st.hap0 = 0; st.t1 = st.t2 = 0; st.ps = 0;
     int n_d = 0;
     bool overflow = false;
+    constexpr int kBatch = 4;                                    // reads per lane requested together
+    int b_row[kBatch], b_ps[kBatch], b_pc[kBatch], b_hp[kBatch];
     for (long long base = b; base < e && !overflow; base += 32) {
-        const long long j = base + lane;
-        bool q = false;
-        int ps = 0, pc = 0, hp = 0;
-        if (j < e) {
-            const int row = a.join_row[j];
-            if (row >= 0) {
-                const ReadTag t = load_tag(a, row);
-                pc = t.pc; ps = t.ps; hp = (int)(t.hp & 0xffu);
-                q = pc <= c_thr.pc_max;
+        const int u = (int)((base - b) / 32) % kBatch;
+        if (u == 0) {                                            // refill: kBatch x 32 reads, two round trips
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) {
+                const long long j = base + k * 32 + lane;
+                b_row[k] = j < e ? a.join_row[j] : -1;
+            }
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) {
+                b_ps[k] = b_pc[k] = b_hp[k] = 0;
+                if (b_row[k] >= 0) { const ReadTag t = load_tag(a, b_row[k]); b_ps[k] = t.ps; b_pc[k] = t.pc; b_hp[k] = (int)(t.hp & 0xffu); }
             }
         }
+        int row = -1, ps = 0, pc = 0, hp = 0;
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k)
+            if (k == u) { row = b_row[k]; ps = b_ps[k]; pc = b_pc[k]; hp = b_hp[k]; }
+        const bool q = row >= 0 && pc <= c_thr.pc_max;
         int id = -1;
         for (int t = 0; t < n_d; ++t)
             if (q && m.ps[t] == ps) id = t;
