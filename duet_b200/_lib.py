@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libduet_b200.so")
 
 DUET_OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_HASH_COLLISION, ERR_BAD_HP, ERR_ZERO_DIVISION, ERR_STATE = range(1, 8)
-MEM_HOST, MEM_DEVICE = 0, 1
+MEM_HOST, MEM_DEVICE, MEM_HOST_MAPPED = 0, 1, 2
 SV_GT_MISSING = 1
 CLS_FILTERED = 255
 N_FEATURES = 6

@@ -268,6 +268,8 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         (S && (!in->sv_pos || !in->sv_svlen || !in->sv_svread || !in->sv_refread || !in->sv_flags)) ||
         (J && !in->csr_key))
         return fail(h, DUET_ERR_INVALID, "duet_phase_upload: a required column is NULL");
+    if (in->mem != DUET_MEM_HOST && in->mem != DUET_MEM_DEVICE && in->mem != DUET_MEM_HOST_MAPPED)
+        return fail(h, DUET_ERR_INVALID, "duet_phase_upload: unknown `mem`");
     if (in->mem == DUET_MEM_DEVICE && (reinterpret_cast<uintptr_t>(in->read_key) & 15u))
         return fail(h, DUET_ERR_INVALID, "duet_phase_upload: read_key must be 16-byte aligned");
     if (in->read_off[0] != 0 || in->sv_off[0] != 0 || in->read_off[ns] != R || in->sv_off[ns] != S)
@@ -320,13 +322,23 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     PhaseArgs &a = h->a;
     std::memset(&a, 0, sizeof(a));
     a.n_shards = ns; a.n_reads = (int)R; a.n_svs = (int)S; a.n_joins = (int)J;
-    const int mem = in->mem;
+    const int mem = in->mem == DUET_MEM_HOST_MAPPED ? DUET_MEM_HOST : in->mem;      // only read_tag is special
     int rc;
 #define STAGE(buf, field, T, count)                                                                  \
     if ((rc = stage(h, h->buf, in->field, sizeof(T) * (size_t)(count), mem,                          \
                     reinterpret_cast<const void **>(&a.field))) != DUET_OK) return rc;
     STAGE(in_read_key, read_key, uint64_t, R)
-    STAGE(in_read_tag, read_tag, duet_read_tag, R)
+    if (in->mem == DUET_MEM_HOST_MAPPED && R) {
+        // the tag records stay where they are: k_reduce gathers the joined rows' records over the bus
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, in->read_tag) != cudaSuccess || pa.type != cudaMemoryTypeHost || !pa.devicePointer) {
+            cudaGetLastError();
+            return fail(h, DUET_ERR_INVALID, "duet_phase_upload: DUET_MEM_HOST_MAPPED needs read_tag in page-locked host memory");
+        }
+        a.read_tag = static_cast<const ReadTag *>(pa.devicePointer);
+    } else {
+        STAGE(in_read_tag, read_tag, duet_read_tag, R)
+    }
     STAGE(in_sv_pos, sv_pos, int32_t, S)
     STAGE(in_sv_svlen, sv_svlen, int32_t, S)
     STAGE(in_sv_svread, sv_svread, int32_t, S)

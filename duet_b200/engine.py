@@ -102,10 +102,13 @@ class PhaseEngine:
         self._check(self.lib.duet_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
 
     # -- data path --------------------------------------------------------------------------
-    def upload(self, batch: PhaseBatch):
-        """Host columns -> device (copies; pinned arrays copy at PCIe speed)."""
+    def upload(self, batch: PhaseBatch, *, tags_in_place: bool = False):
+        """Host columns -> device (copies; pinned arrays copy at PCIe speed).  `tags_in_place`: the
+        per-read tag records -- the largest column, of which only the joined rows are ever read --
+        are NOT copied; the kernels read them over the bus from `batch.read_tag`, which must be
+        page-locked (`pin_batch`, `pinned_empty`) and stay untouched until the results are down."""
         inp = _lib.PhaseInput()
-        inp.mem = _lib.MEM_HOST
+        inp.mem = _lib.MEM_HOST_MAPPED if tags_in_place else _lib.MEM_HOST
         inp.n_shards, inp.n_reads, inp.n_svs, inp.n_joins = batch.n_shards, batch.n_reads, batch.n_svs, batch.n_joins
         for name in _lib.INPUT_COLUMNS:
             arr = getattr(batch, name)
@@ -156,10 +159,11 @@ class PhaseEngine:
         arr["order"] = arr["order"][:n]
         return PhaseResult(**arr)
 
-    def run(self, batch: PhaseBatch, *, join: bool = True, buffers: dict | None = None) -> PhaseResult:
+    def run(self, batch: PhaseBatch, *, join: bool = True, buffers: dict | None = None,
+            tags_in_place: bool = False) -> PhaseResult:
         """upload + execute + download.  `buffers` (see `pinned_outputs`) lets the results land in
-        page-locked memory, so the device->host copies run as plain DMA."""
-        self.upload(batch)
+        page-locked memory, so the device->host copies run as plain DMA; `tags_in_place`: see upload."""
+        self.upload(batch, tags_in_place=tags_in_place)
         self.execute()
         return self.download(join=join, buffers=buffers)
 

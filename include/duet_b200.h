@@ -44,7 +44,15 @@ enum {
     DUET_ERR_STATE = 7           /* call order violated (execute before upload, ...)          */
 };
 
-enum { DUET_MEM_HOST = 0, DUET_MEM_DEVICE = 1 };
+enum {
+    DUET_MEM_HOST = 0,           /* host columns (pageable or page-locked): duet_phase_upload copies them    */
+    DUET_MEM_DEVICE = 1,         /* device columns, used in place                                            */
+    DUET_MEM_HOST_MAPPED = 2     /* page-locked host columns (duet_host_alloc / cudaHostAlloc /
+                                    cudaHostRegister): everything is copied EXCEPT read_tag, which the
+                                    kernels read in place over the bus -- only the rows that joined are
+                                    ever touched (~8 % of them at WGS 30x), so the largest column never
+                                    crosses PCIe in full                                                     */
+};
 
 /* sv_flags bits */
 enum { DUET_SV_GT_MISSING = 1 };   /* GT == "./." (sv_phasing_fn.py:190) */
@@ -95,13 +103,15 @@ typedef struct duet_read_tag {
  * [csr_off[i], csr_off[i+1]) in RNAMES order.
  *
  * read_off / sv_off are ALWAYS host pointers (tiny descriptors).  Every other array lives
- * where `mem` says: DUET_MEM_HOST (pageable or pinned; duet_phase_upload copies it) or
- * DUET_MEM_DEVICE (used in place, must stay valid and unchanged until the next upload).
+ * where `mem` says: DUET_MEM_HOST (pageable or pinned; duet_phase_upload copies it),
+ * DUET_MEM_DEVICE (used in place, must stay valid and unchanged until the next upload) or
+ * DUET_MEM_HOST_MAPPED (as DUET_MEM_HOST, but `read_tag` must be page-locked and is read in place
+ * by duet_phase_execute: keep it valid and unchanged until the results have been downloaded).
  * `csr_chk` may be NULL: then 64-bit key equality is trusted (no collision check).
  * `sv_group` may be NULL (= all zero).
  */
 typedef struct duet_phase_input {
-    int32_t mem;                 /* DUET_MEM_HOST | DUET_MEM_DEVICE                              */
+    int32_t mem;                 /* DUET_MEM_HOST | DUET_MEM_DEVICE | DUET_MEM_HOST_MAPPED       */
     int32_t n_shards;
     int64_t n_reads;             /* R < 2^31                                                     */
     int64_t n_svs;               /* S < 2^31                                                     */

@@ -87,6 +87,26 @@ def test_pinned_input_same_result(engine):
     assert np.array_equal(a.gt, c.gt) and np.array_equal(a.ps, c.ps) and np.array_equal(a.order, c.order)
 
 
+def test_tags_read_in_place_from_pinned_host_memory(engine):
+    """DUET_MEM_HOST_MAPPED: the tag records are not copied, the kernels read the joined rows' records
+    over the bus -- same results; pageable memory is refused."""
+    s = synth.make_sample(10, contigs=["1", "2", "X"], n_reads=9000, n_svs=700, bp_per_read=700, block_mean=1e5)
+    batch = from_synth(s)
+    engine.set_thresholds(50, 2)
+    a = engine.run(batch)
+    pinned = pin_batch(batch)
+    b = engine.run(pinned, tags_in_place=True)
+    c = engine.run(pinned, tags_in_place=True)                  # replay with the same host buffer
+    d = engine.run(batch)                                        # and back to copies
+    for k in ("gt", "ps", "cls", "hap1", "hap2", "hap0", "allhap", "totsc1", "totsc2", "join_row", "order", "shard_counts"):
+        for other in (b, c, d):
+            assert np.array_equal(getattr(a, k), getattr(other, k)), k
+    assert np.array_equal(a.features, b.features)
+    with pytest.raises(DuetError) as ei:
+        engine.run(batch, tags_in_place=True)                    # numpy-owned (pageable) memory
+    assert ei.value.code == _lib.ERR_INVALID
+
+
 def test_golden_kat_on_device(engine):
     """Every known-answer case recorded from the reference's get_phase_info / predict_hp whose
     class is reachable through the pipeline, run as one shard each in ONE device call."""
