@@ -294,10 +294,14 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     std::vector<int> tab_off(ns), tab_mask(ns), bm_off(ns), bm_wmask(ns);
     std::vector<long long> join_off(ns + 1);
     for (int s = 0; s <= ns; ++s) join_off[s] = csr[in->sv_off[s]];
-    // slot table: 16-byte slots, load factor <= 1/2.  Bloom filter: 16 bits per name, at most 128 KB
-    // per shard (it has to fit in shared memory).  Both are (re)initialised by one sequential memset
+    // slot table: 16-byte slots.  Bloom filter: 16 bits per name, at most 64 KB per shard (it has to fit in
+    // shared memory twice per SM).  Both are (re)initialised by one sequential memset
     // at the start of every call, which also makes them L2 resident for the random traffic that follows.
-    const long long fill = 2;
+    // Load factor <= 1/4 while such a table (<= 8 slots of 16 B per name after rounding up to a power of
+    // two) stays within half of the 126 MB L2, else <= 1/2: a sparser table means fewer CAS retry rounds
+    // in k_table and fewer probe rounds in k_probe (a warp waits for its unluckiest lane), but one that
+    // spills out of L2 costs more than it saves (measured: WGS 30x -5 % device time, 60x dense +3.5 %).
+    const long long fill = J * 8 * (long long)sizeof(Slot) <= (64ll << 20) ? 4 : 2;
     long long slots = 0, max_sv = 0, bm_words = 0;
     for (int s = 0; s < ns; ++s) {
         const long long nj = join_off[s + 1] - join_off[s];
