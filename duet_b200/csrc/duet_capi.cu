@@ -66,7 +66,7 @@ struct duet_handle {
     // descriptors, table, scratch, outputs
     DevBuf d_read_off, d_sv_off, d_join_off, d_sv_shard, d_tab_off, d_tab_mask, d_done, d_c2;
     DevBuf d_btiles, d_rtiles, d_ptiles, d_qtiles, d_dbg, d_cand_key, d_cand_row;
-    int probe_grid = 0;
+    int probe_grid = 0, predict_grid = 0;
     int reduce_lanes = kReduceLanesSparse;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
@@ -386,13 +386,20 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         return v;
     };
     h->reduce_lanes = (S > 0 && J / std::max<long long>(S, 1) > 32) ? kReduceLanesDense : kReduceLanesSparse;
-    std::vector<SvTile> rtiles = sv_tiles(kThreads / h->reduce_lanes), ptiles = sv_tiles(kPredictPerBlock);
+    std::vector<SvTile> rtiles = sv_tiles(kThreads / h->reduce_lanes);
+    std::vector<PredictTile> ptiles;                             // k_predict blocks never span shards
+    for (int s = 0; s < ns; ++s) {
+        const int b = (int)in->sv_off[s], n = (int)(in->sv_off[s + 1] - in->sv_off[s]);
+        for (int o = 0; o < n; o += kPredictPerBlock)
+            ptiles.push_back(PredictTile{b + o, std::min(b + n, b + o + kPredictPerBlock), s, b, n, {0, 0, 0}});
+    }
+    h->predict_grid = (int)ptiles.size();
     if ((rc = stage(h, h->d_btiles, btiles.data(), sizeof(BuildTile) * btiles.size(), DUET_MEM_HOST, &dv))) return rc;
     a.build_tiles = static_cast<const BuildTile *>(dv);
     if ((rc = stage(h, h->d_rtiles, rtiles.data(), sizeof(SvTile) * rtiles.size(), DUET_MEM_HOST, &dv))) return rc;
     a.reduce_tiles = static_cast<const SvTile *>(dv);
-    if ((rc = stage(h, h->d_ptiles, ptiles.data(), sizeof(SvTile) * ptiles.size(), DUET_MEM_HOST, &dv))) return rc;
-    a.predict_tiles = static_cast<const SvTile *>(dv);
+    if ((rc = stage(h, h->d_ptiles, ptiles.data(), sizeof(PredictTile) * std::max<size_t>(ptiles.size(), 1), DUET_MEM_HOST, &dv))) return rc;
+    a.predict_tiles = static_cast<const PredictTile *>(dv);
     // k_probe tiles: row ranges that never cross a contig, about two per SM in total
     std::vector<ProbeTile> qtiles;
     {
@@ -523,7 +530,7 @@ static void launch_all(duet_handle *h, cudaStream_t st, bool marks) {
     }
     mark(EV_K3);
     if (S) {
-        launch(k_predict, (S + kPredictPerBlock - 1) / kPredictPerBlock, kThreads, 0, st, pdl, a);
+        launch(k_predict, h->predict_grid, kThreads, 0, st, pdl, a);
         ++h->launches;
     }
 }
@@ -544,7 +551,7 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
     } else {
         // the launch sequence of a staged batch never changes: replay it as a CUDA graph.  A re-upload
         // of the same shapes lands in the same buffers, so the captured graph stays valid.
-        const int dims[4] = {h->probe_grid, h->reduce_lanes, (int)h->probe_smem, h->n_sm};
+        const int dims[4] = {h->probe_grid, h->reduce_lanes, (int)h->probe_smem, h->predict_grid};
         if (h->graph_exec && (std::memcmp(&h->graph_args, &h->a, sizeof(PhaseArgs)) != 0 ||
                               std::memcmp(h->graph_dims, dims, sizeof(dims)) != 0 || !h->graph_valid)) {
             cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr;

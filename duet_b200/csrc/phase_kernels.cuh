@@ -54,6 +54,7 @@ struct __align__(16) ReadTag { int ps, pc; unsigned chk, hp; };       // hp: low
 // host-built descriptors: what a block needs to know about its tile, in one 32- / 16-byte load
 struct BuildTile { int lo, hi, base, mask, bmo, bmw, pad[2]; };   // shards of 256 consecutive support reads
 struct SvTile { int s_first, s_last, off0, off1; };               // shards of a block's SVs; SV range of s_first
+struct PredictTile { int sv0, sv1, shard, b, n, pad[3]; };        // SVs [sv0, sv1) of ONE shard = SVs [b, b + n)
 struct ProbeTile { long long r0, r1; int shard, base, mask, bmo, bmw, pad; };   // rows [r0, r1) of ONE contig + its table / filter
 
 constexpr int kC2Max = 8;    // distinct PS per class-2 SV recorded by k_reduce (more -> warp fallback)
@@ -77,7 +78,7 @@ struct PhaseArgs {
     const int *sv_shard;         // [S] shard of each SV (derived at upload)
     const BuildTile *build_tiles;   // [ceil(J / 256)]
     const SvTile *reduce_tiles;     // [ceil(S / (kThreads / lanes per SV))]
-    const SvTile *predict_tiles;    // [ceil(S / kPredictPerBlock)]
+    const PredictTile *predict_tiles;   // [sum over shards of ceil(n / kPredictPerBlock)] = k_predict grid
     const ProbeTile *probe_tiles;   // [n_probe_tiles] = k_probe grid
     int n_probe_tiles;
     unsigned long long *cand_key;   // [R] rows that passed their contig's filter: tile t appends at [r0(t), ...)
@@ -594,6 +595,7 @@ __device__ void oneps_block_small(const PhaseArgs &a, int s, long long *smem_til
         if (found[u] != INT32_MIN) tab[w++] = found[u];
     const int m_pad = next_pow2(max(m, 1));
     const int off = s_has_min;
+    int *dst = a.oneps + b;
     __syncthreads();
     if (m <= 2 * kThreads) {
         // the values are distinct, so a value's rank IS its place in the sorted list: one pass over the
@@ -608,16 +610,16 @@ __device__ void oneps_block_small(const PhaseArgs &a, int s, long long *smem_til
             r0 += (x.x < v0) + (x.y < v0) + (x.z < v0) + (x.w < v0);
             r1 += (x.x < v1) + (x.y < v1) + (x.z < v1) + (x.w < v1);
         }
-        if (i0 < m) a.oneps[b + off + r0] = v0;
-        if (i1 < m) a.oneps[b + off + r1] = v1;
+        if (i0 < m) dst[off + r0] = v0;
+        if (i1 < m) dst[off + r1] = v1;
     } else {
         for (int i = m + threadIdx.x; i < m_pad; i += kThreads) tab[i] = INT32_MAX;
         __syncthreads();
         block_bitonic_sort(tab, m_pad);
-        for (int i = threadIdx.x; i < m; i += kThreads) a.oneps[b + off + i] = tab[i];
+        for (int i = threadIdx.x; i < m; i += kThreads) dst[off + i] = tab[i];
     }
     if (threadIdx.x == 0) {
-        if (off) a.oneps[b] = INT32_MIN;
+        if (off) dst[0] = INT32_MIN;
         a.oneps_n[s] = m + off;
     }
     __syncthreads();
@@ -1312,39 +1314,35 @@ k_predict(PhaseArgs a) {
     __shared__ __align__(16) long long s_tile[kSortSmemBytes / 8];
     __shared__ int s_one[kOneSmem];
     __shared__ int s_list[kThreads];
-    __shared__ int s_credit[kPredictPerBlock];
     __shared__ int s_fb[kPredictPerBlock];
-    __shared__ int s_n, s_nfb;
+    __shared__ int s_n, s_nfb, s_n_one;
     dbg_mark(a, 3, 0);
-    const SvTile tile = a.predict_tiles[blockIdx.x];
+    const PredictTile tile = a.predict_tiles[blockIdx.x];        // SVs [sv0, sv1) of ONE shard
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int blk0 = blockIdx.x * kPredictPerBlock, blk1 = min(a.n_svs, blk0 + kPredictPerBlock);
+    const int blk0 = tile.sv0, blk1 = tile.sv1, shard = tile.shard;
     const int sv = blk0 + threadIdx.x;
     const bool mine = threadIdx.x < kPredictPerBlock && sv < blk1;
-    int cls = DUET_CLS_FILTERED, shard = 0, n_list = 0;
+    int cls = DUET_CLS_FILTERED, n_list = 0;
     Class2Stats st{0, 0, 0, 0, 0, 0, 0};
-    if (mine) {                                                  // inputs: requested before the wait
-        shard = __ldg(a.sv_shard + sv);
-        n_list = (int)(__ldg(a.csr_off + sv + 1) - __ldg(a.csr_off + sv));
-    }
+    if (mine) n_list = (int)(__ldg(a.csr_off + sv + 1) - __ldg(a.csr_off + sv));     // input: requested before the wait
     pdl_trigger();
     pdl_wait();                                                  // k_reduce's per-SV results and one-PS lists are final
-    if (mine) {                                                  // everything that does not depend on the tile
+    if (mine) {                                                  // everything that does not depend on the list
         cls = a.cls[sv];
         st = Class2Stats{a.hap1[sv], a.hap2[sv], 0, a.allhap[sv], a.ps[sv], a.totsc1[sv], a.totsc2[sv]};
     }
-    const int n0 = a.oneps_n[tile.s_first];
-    const int n_stage = min(tile.off1 - tile.off0, kOneSmem);
-    for (int i = threadIdx.x; i < n_stage; i += kThreads) s_one[i] = a.oneps[tile.off0 + i];   // only [0, n0) is meaningful
     if (threadIdx.x == 0) { s_n = 0; s_nfb = 0; }
-    if (threadIdx.x < kPredictPerBlock) s_credit[threadIdx.x] = mine ? shard : -1;
-    __syncthreads();
+    {   // the shard's sorted unique one-PS list (:107), built by the k_reduce block that completed the shard
+        const int n_stage = min(tile.n, kOneSmem);
+        for (int i = threadIdx.x; i < n_stage; i += kThreads) s_one[i] = a.oneps[tile.b + i];   // only [0, n) is meaningful
+        if (threadIdx.x == 0) s_n_one = a.oneps_n[shard];
+        __syncthreads();
+    }
+    const int n_one = s_n_one;                                   // 0: contig skipped (:209-210)
+    const int *one = n_one <= kOneSmem ? s_one : a.oneps + tile.b;
     dbg_mark(a, 3, 1);
 
     if (mine && cls != DUET_CLS_FILTERED) {
-        const bool home = shard == tile.s_first;
-        const int n_one = home ? n0 : a.oneps_n[shard];              // 0: contig skipped (:209-210)
-        const int *one = home && n0 <= kOneSmem ? s_one : a.oneps + (home ? tile.off0 : (int)a.sv_off[shard]);
         if (n_one > 0) {
             bool ready = true;
             if (cls == 0) st = Class2Stats{0, 0, 0, 0, 0, 0, 0};     // get_phase_info skips both loops
@@ -1377,34 +1375,17 @@ k_predict(PhaseArgs a) {
     __syncthreads();
     for (int k = w; k < s_nfb; k += kThreads / 32) {                 // rare: > kC2Max phase sets in one SV
         const int sv2 = blk0 + s_fb[k];
-        const int s2 = __ldg(a.sv_shard + sv2);
         const long long b2 = __ldg(a.csr_off + sv2), e2 = __ldg(a.csr_off + sv2 + 1);
-        const int *o2 = a.oneps + a.sv_off[s2];
-        const int n2 = a.oneps_n[s2];
         Class2Stats t{0, 0, 0, a.allhap[sv2], 0, 0, 0};
-        class2_stats(a, sv2, b2, e2, o2, n2, s_c2[w], t);
-        if (lane == 0) decide_and_store(a, sv2, 2, t, o2, n2, (int)(e2 - b2));
+        class2_stats(a, sv2, b2, e2, one, n_one, s_c2[w], t);
+        if (lane == 0) decide_and_store(a, sv2, 2, t, one, n_one, (int)(e2 - b2));
     }
 
     __syncthreads();
     dbg_mark(a, 3, 3);
     if (threadIdx.x == 0) {
         __threadfence();                 // cumulative: orders the whole block's stores (after the barrier)
-        int run_s = -1, run_n = 0;
-        if (tile.s_first == tile.s_last && blk0 < blk1)              // the usual case: one contig per block
-            credit_one(a, tile.s_first, blk1 - blk0, tile.off1 - tile.off0, s_list, &s_n);
-        else for (int t = 0; t <= kPredictPerBlock; ++t) {           // shards are contiguous in SV order
-            const int s = t < kPredictPerBlock ? s_credit[t] : -1;
-            if (s != run_s) {
-                if (run_n) {
-                    const int total = run_s == tile.s_first ? tile.off1 - tile.off0
-                                                            : (int)(a.sv_off[run_s + 1] - a.sv_off[run_s]);
-                    credit_one(a, run_s, run_n, total, s_list, &s_n);
-                }
-                run_s = s; run_n = 0;
-            }
-            if (s >= 0) ++run_n;
-        }
+        if (blk0 < blk1) credit_one(a, shard, blk1 - blk0, tile.n, s_list, &s_n);
         __threadfence();
     }
     __syncthreads();
