@@ -64,7 +64,7 @@ struct duet_handle {
     DevBuf in_sv_pos, in_sv_svlen, in_sv_svread, in_sv_refread, in_sv_flags, in_sv_group;
     DevBuf in_csr_off, in_csr_key, in_csr_chk;
     // descriptors, table, scratch, outputs
-    DevBuf d_read_off, d_sv_off, d_join_off, d_sv_shard, d_tab_off, d_tab_mask, d_done, d_c2;
+    DevBuf d_read_off, d_sv_off, d_join_off, d_tab_off, d_tab_mask, d_done, d_c2;
     DevBuf d_btiles, d_rtiles, d_ptiles, d_qtiles, d_dbg, d_cand_key, d_cand_row;
     int probe_grid = 0, predict_grid = 0;
     int reduce_lanes = kReduceLanesSparse;
@@ -207,7 +207,7 @@ void duet_destroy(duet_handle *h) {
     DevBuf *bufs[] = {&h->in_read_key, &h->in_read_tag,
                       &h->in_sv_pos, &h->in_sv_svlen, &h->in_sv_svread, &h->in_sv_refread, &h->in_sv_flags,
                       &h->in_sv_group, &h->in_csr_off, &h->in_csr_key, &h->in_csr_chk, &h->d_read_off,
-                      &h->d_sv_off, &h->d_join_off, &h->d_c2, &h->d_btiles, &h->d_rtiles, &h->d_ptiles, &h->d_qtiles, &h->d_dbg, &h->d_cand_key, &h->d_cand_row, &h->d_sv_shard, &h->d_done, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_bm_off, &h->d_bm_wmask, &h->d_next,
+                      &h->d_sv_off, &h->d_join_off, &h->d_c2, &h->d_btiles, &h->d_rtiles, &h->d_ptiles, &h->d_qtiles, &h->d_dbg, &h->d_cand_key, &h->d_cand_row, &h->d_done, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_bm_off, &h->d_bm_wmask, &h->d_next,
                       &h->d_join_row, &h->d_n_hit, &h->d_cand, &h->d_oneps, &h->d_oneps_n, &h->d_sort, &h->d_gt,
                       &h->d_cls, &h->d_ps, &h->d_hap1, &h->d_hap2, &h->d_hap0, &h->d_allhap, &h->d_t1, &h->d_t2,
                       &h->d_feat, &h->d_order, &h->d_n_emit, &h->d_counts, &h->d_status};
@@ -364,8 +364,6 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     std::vector<int> sv_shard((size_t)S);
     for (int s = 0; s < ns; ++s)
         std::fill(sv_shard.begin() + in->sv_off[s], sv_shard.begin() + in->sv_off[s + 1], s);
-    if ((rc = stage(h, h->d_sv_shard, sv_shard.data(), sizeof(int) * (size_t)S, DUET_MEM_HOST, &dv))) return rc;
-    a.sv_shard = static_cast<const int *>(dv);
     // per-block tile descriptors (what each block would otherwise look up with dependent loads)
     auto shard_at = [&](const std::vector<long long> &off, long long x) {
         return (int)(std::upper_bound(off.begin(), off.end(), x) - off.begin()) - 1;

@@ -75,7 +75,6 @@ struct PhaseArgs {
     const long long *read_off;   // [n_shards+1]
     const long long *sv_off;     // [n_shards+1]
     const long long *join_off;   // [n_shards+1] csr_off at the shard boundaries (derived at upload)
-    const int *sv_shard;         // [S] shard of each SV (derived at upload)
     const BuildTile *build_tiles;   // [ceil(J / 256)]
     const SvTile *reduce_tiles;     // [ceil(S / (kThreads / lanes per SV))]
     const PredictTile *predict_tiles;   // [sum over shards of ceil(n / kPredictPerBlock)] = k_predict grid
