@@ -57,7 +57,6 @@ struct duet_handle {
     std::vector<long long> h_read_off, h_sv_off;
     long long n_slots = 0, n_bm_words = 0;
     int n_sm = 148;
-    int group = 16;                 // lanes per SV in k_build / k_reduce
 
     // staged input copies (HOST mode)
     DevBuf in_read_key, in_read_tag;
@@ -183,7 +182,7 @@ int duet_create(int device_id, duet_handle **out) {
         cudaFuncAttributes fa;
         cudaFuncGetAttributes(&fa, k_probe);
         cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, kBloomMaxWords * 4 + kProbeRingBytes);
-        // one shared-memory carveout for all four kernels: switching it between launches drains the SMs
+        // one shared-memory carveout for all the kernels: switching it between launches drains the SMs
         cudaFuncSetAttribute(k_table, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_probe, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_reduce<kReduceLanesSparse>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

@@ -244,7 +244,7 @@ __device__ __forceinline__ int next_pow2(int n) {
 // ------------------------------------------------------------------------------------------
 // k_init: start-of-call state in one sequential sweep: EMPTY slots (all ones), zero filter words,
 // join results -1.  Sequential 16-byte stores also leave all three L2 resident for the random
-// traffic of k_build / k_probe that follows.
+// traffic of k_table / k_probe that follows.
 // ------------------------------------------------------------------------------------------
 enum { kInitTable = 1, kInitFilter = 2 };
 

@@ -195,7 +195,8 @@ int duet_sync(duet_handle *h);
 
 /* Developer instrumentation: with `enable` != 0 the kernels launched after the next upload stamp
  * (globaltimer ns, SM clock) per block at up to 8 marks; `out` (may be NULL) receives the stamps of
- * the last execute as int64[4 kernels][2048 blocks][8 marks][2].  Off by default: costs nothing. */
+ * the last execute as int64[4 kernels: k_table, k_probe, k_reduce, k_predict][2048 blocks][8 marks][2].
+ * Off by default: costs nothing. */
 int duet_debug_timers(duet_handle *h, int enable, int64_t *out);
 
 /* ---- kernel set B: span-position-distance clustering of SV signatures --------------------------
