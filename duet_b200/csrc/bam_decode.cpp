@@ -15,7 +15,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/duet_b200.h"
@@ -28,11 +30,32 @@ inline uint32_t rd32(const unsigned char *p) { uint32_t v; std::memcpy(&v, p, 4)
 inline uint16_t rd16(const unsigned char *p) { uint16_t v; std::memcpy(&v, p, 2); return v; }
 
 // ---- BGZF ---------------------------------------------------------------------------------------
+std::atomic<int> g_inflate_threads{1};                        // duet_set_decode_threads
+
+// one BGZF block (a raw-deflate member with its own ISIZE) -> its slice of the output
+bool inflate_block(const unsigned char *blk, int64_t bsize, unsigned char *dst) {
+    const int xlen = rd16(blk + 10);
+    const uint32_t isize = rd32(blk + bsize - 4);
+    if (isize == 0) return true;
+    z_stream zs;
+    std::memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) return false;
+    zs.next_in = const_cast<unsigned char *>(blk + 12 + xlen);
+    zs.avail_in = (uInt)(bsize - xlen - 20);
+    zs.next_out = dst;
+    zs.avail_out = isize;
+    const int rc = inflate(&zs, Z_FINISH);
+    inflateEnd(&zs);
+    return rc == Z_STREAM_END && zs.avail_out == 0;
+}
+
 int inflate_bgzf(const unsigned char *data, int64_t len, std::vector<unsigned char> &out) {
     int64_t pos = 0;
     size_t total = 0;
-    // first pass: sizes
+    // first pass: sizes (every block states its own compressed and uncompressed size, so the blocks can
+    // be inflated independently, each into its own slice of the output)
     std::vector<std::pair<int64_t, int64_t>> blocks;          // (offset, block size)
+    std::vector<size_t> dst_off;
     while (pos < len) {
         if (len - pos < 18 || data[pos] != 31 || data[pos + 1] != 139 || data[pos + 2] != 8 || !(data[pos + 3] & 4))
             return DUET_DECODE_ERR_FORMAT;
@@ -45,29 +68,27 @@ int inflate_bgzf(const unsigned char *data, int64_t len, std::vector<unsigned ch
             x += 4 + slen;
         }
         if (bsize < 0 || pos + bsize > len || bsize < xlen + 20) return DUET_DECODE_ERR_FORMAT;
+        dst_off.push_back(total);
         total += rd32(data + pos + bsize - 4);
         blocks.emplace_back(pos, bsize);
         pos += bsize;
     }
     out.resize(total);
-    size_t w = 0;
-    for (auto &b : blocks) {
-        const unsigned char *blk = data + b.first;
-        const int xlen = rd16(blk + 10);
-        const uint32_t isize = rd32(blk + b.second - 4);
-        if (isize == 0) continue;
-        z_stream zs;
-        std::memset(&zs, 0, sizeof(zs));
-        if (inflateInit2(&zs, -15) != Z_OK) return DUET_DECODE_ERR_FORMAT;
-        zs.next_in = const_cast<unsigned char *>(blk + 12 + xlen);
-        zs.avail_in = (uInt)(b.second - xlen - 20);
-        zs.next_out = out.data() + w;
-        zs.avail_out = isize;
-        const int rc = inflate(&zs, Z_FINISH);
-        inflateEnd(&zs);
-        if (rc != Z_STREAM_END || zs.avail_out != 0) return DUET_DECODE_ERR_FORMAT;
-        w += isize;
+    const int n_thr = (int)std::min<size_t>((size_t)std::max(1, g_inflate_threads.load()), blocks.size() / 16 + 1);
+    if (n_thr > 1) {                                          // contiguous runs of blocks per worker
+        std::atomic<bool> ok{true};
+        std::vector<std::thread> pool;
+        for (int t = 0; t < n_thr; ++t)
+            pool.emplace_back([&, t] {
+                const size_t b0 = blocks.size() * (size_t)t / n_thr, b1 = blocks.size() * (size_t)(t + 1) / n_thr;
+                for (size_t i = b0; i < b1 && ok.load(std::memory_order_relaxed); ++i)
+                    if (!inflate_block(data + blocks[i].first, blocks[i].second, out.data() + dst_off[i])) ok = false;
+            });
+        for (auto &th : pool) th.join();
+        return ok ? (int)DUET_OK : (int)DUET_DECODE_ERR_FORMAT;
     }
+    for (size_t i = 0; i < blocks.size(); ++i)
+        if (!inflate_block(data + blocks[i].first, blocks[i].second, out.data() + dst_off[i])) return DUET_DECODE_ERR_FORMAT;
     return DUET_OK;
 }
 
@@ -173,6 +194,10 @@ bool parse_int(const char *p, const char *e, long long *out, bool *overflow) {
 extern "C" {
 
 void duet_free(void *p) { std::free(p); }
+
+int duet_set_decode_threads(int n) {
+    return g_inflate_threads.exchange(n < 1 ? 1 : n);
+}
 
 int duet_decode_bam(const unsigned char *data, int64_t len, uint64_t **key_out, duet_read_tag **tag_out,
                     int64_t *n_rows, int64_t *n_records, int64_t *err_record) {

@@ -161,8 +161,16 @@ def read_hap_bam(path, thread, include_all_ctgs):
     # the reference gives its `thread` count to samtools; here the contigs are decoded in parallel
     # (the C++ scanners release the GIL)
     from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max_workers=max(1, int(thread))) as pool:
-        read_hap = list(pool.map(lambda p: load_hap_bam(p, 1) if p else ReadColumns.empty(), paths))
+    thread = max(1, int(thread))
+    n_files = max(1, sum(p is not None for p in paths))
+    workers = min(thread, n_files)
+    # fewer files than threads (the one-contig demo): the rest go to the BGZF blocks inside each file
+    prev = _lib.load().duet_set_decode_threads(max(1, thread // workers))
+    try:
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            read_hap = list(pool.map(lambda p: load_hap_bam(p, 1) if p else ReadColumns.empty(), paths))
+    finally:
+        _lib.load().duet_set_decode_threads(prev)
     for cols, p in zip(read_hap, paths):
         cols.source = p
     for ctg, cols, p in zip(chrom_list, read_hap, paths):

@@ -253,6 +253,12 @@ int duet_decode_sam_text(const char *text, int64_t len, int64_t cap, uint64_t *k
                          int64_t *n_rows, int64_t *n_lines, int64_t *err_line);
 int64_t duet_count_lines(const char *text, int64_t len);
 
+/* Threads ONE duet_decode_bam call may use to inflate its BGZF blocks (each block carries its own
+ * sizes, so they inflate independently); default 1.  Process-wide; returns the previous value.  The
+ * reference hands its `thread` count to `samtools view -@` (sv_phasing_fn.py:25); the host layer
+ * here decodes contigs in parallel first and gives what is left to the blocks of each file. */
+int duet_set_decode_threads(int n);
+
 /* A whole haplotagged BAM file (BGZF bytes) -> the same columns `samtools view` + duet_decode_sam_text
  * would give: every record's last three text tokens are reconstructed and the reference's rule
  * (sv_phasing_fn.py:28-29) is applied to them.  *key_out / *tag_out are malloc'ed; release them with

@@ -163,6 +163,38 @@ def test_bam_reader_equals_text_path(tmp_path):
     assert np.array_equal(a.key, b.key) and np.array_equal(a.tag, b.tag)
 
 
+def test_bam_blocks_inflated_in_parallel(tmp_path):
+    """duet_set_decode_threads: the BGZF blocks of one file inflate independently; same columns as the
+    single-threaded read, a corrupt block is still reported, and read_hap_bam hands spare threads to
+    the blocks when there are fewer files than threads (the one-contig demo)."""
+    from util_bam import write_bam
+    rows = [(f"read{i:06d}", 10 + i, "ACGT" * 8, "I" * 32, [("HP", "C", 1 + i % 2), ("PC", "i", i % 9000), ("PS", "i", 1000 + i // 50)])
+            for i in range(30000)]
+    recs, text = _bam_and_text(rows)
+    home = tmp_path / "snp_phasing"
+    home.mkdir()
+    path = str(home / "21.bam")
+    write_bam(path, recs, block=8000)                        # a few hundred blocks
+    lib = _lib.load()
+    one = sv_phasing_fn.load_hap_bam(path, 1)
+    prev = lib.duet_set_decode_threads(4)
+    try:
+        assert prev == 1
+        four = sv_phasing_fn.load_hap_bam(path, 1)
+        raw = bytearray(open(path, "rb").read())
+        raw[len(raw) // 2] ^= 0xFF                           # damage one block in the middle
+        with pytest.raises(ValueError):
+            sv_phasing_fn.decode_bam(bytes(raw))
+    finally:
+        assert lib.duet_set_decode_threads(prev) == 4
+    assert len(one) == len(four) == len(rows)
+    assert np.array_equal(one.key, four.key) and np.array_equal(one.tag, four.tag)
+    via_stage = sv_phasing_fn.read_hap_bam(str(home) + "/", 8, False)       # 1 file, 8 threads
+    got = [c for c in via_stage if len(c)]
+    assert len(got) == 1 and np.array_equal(got[0].key, one.key) and np.array_equal(got[0].tag, one.tag)
+    assert lib.duet_set_decode_threads(1) == 1               # the stage restored the setting
+
+
 def test_bam_reader_text_quirks(tmp_path):
     """The reference looks at the last three WHITESPACE tokens of the text line, whatever they are."""
     from util_bam import write_bam
