@@ -378,7 +378,9 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": {"build": "k_table"}.get(dom, "k_" + dom), "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": traffic, "peak_kind": peak_kind,
-                         "algorithmic_bytes": kbytes[dom], "kernel_ms": kernel_ms[dom]},
+                         "algorithmic_bytes": kbytes[dom], "kernel_ms": kernel_ms[dom],
+                         "note": "dominant = longest kernel (ties within 5 % go to the one moving most bytes); every kernel's "
+                                 "own figure is under `stages`, the whole path's under `path_roofline`"},
             "kernel_ms": kernel_ms,
             "stages": {k: {"ms": kernel_ms[k], "algorithmic_bytes": kbytes[k],
                            "GBps": kbytes[k] / (kernel_ms[k] * 1e-3) / 1e9 if kernel_ms[k] > 0 else 0.0,
