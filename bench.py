@@ -338,7 +338,8 @@ def main():
         alg = batch.algorithmic_bytes()
         # algorithmic bytes of each kernel of THIS design
         kbytes = {"init": 20 * 3 * batch.n_joins, "build": 28 * batch.n_joins, "probe": 8 * batch.n_reads,
-                  "reduce": 24 * batch.n_joins + 64 * batch.n_svs, "predict": 96 * batch.n_svs}
+                  "reduce": 24 * batch.n_joins + 64 * batch.n_svs, "oneps": 12 * batch.n_svs,
+                  "predict": 96 * batch.n_svs, "order": 18 * batch.n_svs}
         # dominant kernel = the longest one; the four big kernels run within a few percent of each other,
         # so kernels within 5 % of the longest count as tied and the tie goes to the one that moves the
         # most bytes (otherwise the reported kernel flips from run to run).  `stages` lists all of them.

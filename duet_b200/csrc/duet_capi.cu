@@ -38,7 +38,7 @@ struct DevBuf {
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-enum { EV_H2D0, EV_H2D1, EV_X0, EV_K0, EV_K1, EV_K2, EV_K3, EV_K4, EV_D2H0, EV_D2H1, EV_COUNT };
+enum { EV_H2D0, EV_H2D1, EV_X0, EV_K0, EV_K1, EV_K2, EV_K3, EV_K4, EV_K5, EV_K6, EV_D2H0, EV_D2H1, EV_COUNT };
 
 }  // namespace
 
@@ -63,8 +63,8 @@ struct duet_handle {
     DevBuf in_sv_pos, in_sv_svlen, in_sv_svread, in_sv_refread, in_sv_flags, in_sv_group;
     DevBuf in_csr_off, in_csr_key, in_csr_chk;
     // descriptors, table, scratch, outputs
-    DevBuf d_read_off, d_sv_off, d_join_off, d_tab_off, d_tab_mask, d_done, d_c2;
-    DevBuf d_btiles, d_rtiles, d_ptiles, d_qtiles, d_dbg, d_cand_key, d_cand_row;
+    DevBuf d_read_off, d_sv_off, d_join_off, d_tab_off, d_tab_mask, d_c2;
+    DevBuf d_btiles, d_ptiles, d_qtiles, d_dbg, d_cand_key, d_cand_row;
     int probe_grid = 0, predict_grid = 0;
     int reduce_lanes = kReduceLanesSparse;
     cudaGraph_t graph = nullptr;
@@ -188,6 +188,8 @@ int duet_create(int device_id, duet_handle **out) {
         cudaFuncSetAttribute(k_reduce<kReduceLanesSparse>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_reduce<kReduceLanesDense>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_predict, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_oneps, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_order, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_init, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device_id);
     }
@@ -206,7 +208,7 @@ void duet_destroy(duet_handle *h) {
     DevBuf *bufs[] = {&h->in_read_key, &h->in_read_tag,
                       &h->in_sv_pos, &h->in_sv_svlen, &h->in_sv_svread, &h->in_sv_refread, &h->in_sv_flags,
                       &h->in_sv_group, &h->in_csr_off, &h->in_csr_key, &h->in_csr_chk, &h->d_read_off,
-                      &h->d_sv_off, &h->d_join_off, &h->d_c2, &h->d_btiles, &h->d_rtiles, &h->d_ptiles, &h->d_qtiles, &h->d_dbg, &h->d_cand_key, &h->d_cand_row, &h->d_done, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_bm_off, &h->d_bm_wmask, &h->d_next,
+                      &h->d_sv_off, &h->d_join_off, &h->d_c2, &h->d_btiles, &h->d_ptiles, &h->d_qtiles, &h->d_dbg, &h->d_cand_key, &h->d_cand_row, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_bm_off, &h->d_bm_wmask, &h->d_next,
                       &h->d_join_row, &h->d_n_hit, &h->d_cand, &h->d_oneps, &h->d_oneps_n, &h->d_sort, &h->d_gt,
                       &h->d_cls, &h->d_ps, &h->d_hap1, &h->d_hap2, &h->d_hap0, &h->d_allhap, &h->d_t1, &h->d_t2,
                       &h->d_feat, &h->d_order, &h->d_n_emit, &h->d_counts, &h->d_status};
@@ -373,17 +375,7 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         const int lo = shard_at(join_off, first), hi = shard_at(join_off, last);
         btiles[t] = BuildTile{lo, hi, tab_off[lo], tab_mask[lo], bm_off[lo], bm_wmask[lo], {0, 0}};
     }
-    auto sv_tiles = [&](int per_block) {
-        std::vector<SvTile> v((size_t)((S + per_block - 1) / per_block));
-        for (size_t t = 0; t < v.size(); ++t) {
-            const long long sv0 = (long long)t * per_block, sv1 = std::min<long long>(S, sv0 + per_block);
-            const int sf = sv_shard[sv0], sl = sv_shard[sv1 - 1];
-            v[t] = SvTile{sf, sl, (int)in->sv_off[sf], (int)in->sv_off[sf + 1]};
-        }
-        return v;
-    };
     h->reduce_lanes = (S > 0 && J / std::max<long long>(S, 1) > 32) ? kReduceLanesDense : kReduceLanesSparse;
-    std::vector<SvTile> rtiles = sv_tiles(kThreads / h->reduce_lanes);
     std::vector<PredictTile> ptiles;                             // k_predict blocks never span shards
     for (int s = 0; s < ns; ++s) {
         const int b = (int)in->sv_off[s], n = (int)(in->sv_off[s + 1] - in->sv_off[s]);
@@ -393,8 +385,6 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     h->predict_grid = (int)ptiles.size();
     if ((rc = stage(h, h->d_btiles, btiles.data(), sizeof(BuildTile) * btiles.size(), DUET_MEM_HOST, &dv))) return rc;
     a.build_tiles = static_cast<const BuildTile *>(dv);
-    if ((rc = stage(h, h->d_rtiles, rtiles.data(), sizeof(SvTile) * rtiles.size(), DUET_MEM_HOST, &dv))) return rc;
-    a.reduce_tiles = static_cast<const SvTile *>(dv);
     if ((rc = stage(h, h->d_ptiles, ptiles.data(), sizeof(PredictTile) * std::max<size_t>(ptiles.size(), 1), DUET_MEM_HOST, &dv))) return rc;
     a.predict_tiles = static_cast<const PredictTile *>(dv);
     // k_probe tiles: row ranges that never cross a contig, about two per SM in total
@@ -459,8 +449,6 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     CU(h, h->d_cand.reserve(S1 * 8));                    a.cand = h->d_cand.as<long long>();
     CU(h, h->d_oneps.reserve(S1 * 4));                   a.oneps = h->d_oneps.as<int>();
     CU(h, h->d_oneps_n.reserve((size_t)ns * 4));         a.oneps_n = h->d_oneps_n.as<int>();
-    CU(h, h->d_done.reserve((size_t)ns * 8));            a.done_reduce = h->d_done.as<int>();
-    a.done_predict = a.done_reduce + ns;
     CU(h, h->d_sort.reserve(S1 * 32));                   a.sort_scratch = h->d_sort.as<long long>();
     CU(h, h->d_c2.reserve(S1 * sizeof(C2Rec)));          a.c2rec = h->d_c2.as<C2Rec>();
 
@@ -480,7 +468,6 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     CU(h, h->d_status.reserve(sizeof(DevStatus)));       a.status = h->d_status.as<DevStatus>();
     // state the kernels keep clean between calls: zero counters / credits / status
     CU(h, cudaMemsetAsync(h->d_join_row.p, 0xFF, J1 * 4, st));
-    CU(h, cudaMemsetAsync(h->d_done.p, 0, (size_t)ns * 8, st));
     CU(h, cudaMemsetAsync(h->d_oneps_n.p, 0, (size_t)ns * 4, st));
     CU(h, cudaMemsetAsync(h->d_n_emit.p, 0, (size_t)ns * 4, st));
     CU(h, cudaMemsetAsync(h->d_counts.p, 0, (size_t)ns * 8 * DUET_N_COUNTERS, st));
@@ -494,7 +481,8 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     return DUET_OK;
 }
 
-// The launches of one call, a serial chain on `st`: k_init -> k_table -> k_probe -> k_reduce -> k_predict
+// The launches of one call, a serial chain on `st`: k_init -> k_table -> k_probe -> k_reduce -> k_oneps ->
+// k_predict -> k_order
 // (with `marks`, an event follows each stage).
 static void launch_all(duet_handle *h, cudaStream_t st, bool marks) {
     auto mark = [&](int ev) { if (marks) cudaEventRecord(h->ev[ev], st); };
@@ -527,7 +515,17 @@ static void launch_all(duet_handle *h, cudaStream_t st, bool marks) {
     }
     mark(EV_K3);
     if (S) {
+        launch(k_oneps, a.n_shards, kThreads, 0, st, pdl, a);
+        ++h->launches;
+    }
+    mark(EV_K4);
+    if (S) {
         launch(k_predict, h->predict_grid, kThreads, 0, st, pdl, a);
+        ++h->launches;
+    }
+    mark(EV_K5);
+    if (S) {
+        launch(k_order, a.n_shards, kThreads, 0, st, pdl, a);
         ++h->launches;
     }
 }
@@ -571,12 +569,12 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
         }
         if (h->graph_exec) {
             CU(h, cudaGraphLaunch(h->graph_exec, st));
-            h->launches += (h->a.n_joins ? 2 : 0) + (h->a.n_reads && h->a.n_joins ? 1 : 0) + (h->a.n_svs ? 2 : 0);
+            h->launches += (h->a.n_joins ? 2 : 0) + (h->a.n_reads && h->a.n_joins ? 1 : 0) + (h->a.n_svs ? 4 : 0);
         } else {
             launch_all(h, st, false);
         }
     }
-    CU(h, cudaEventRecord(h->ev[EV_K4], st));
+    CU(h, cudaEventRecord(h->ev[EV_K6], st));
     CU(h, cudaGetLastError());
     h->executed = true;
     return DUET_OK;
@@ -659,10 +657,10 @@ int duet_get_timings(duet_handle *h, duet_timings *t) {
     CU(h, cudaStreamSynchronize(h->stream));
     if (h->have_h2d) cudaEventElapsedTime(&t->h2d_ms, h->ev[EV_H2D0], h->ev[EV_H2D1]);
     if (h->executed) {
-        cudaEventElapsedTime(&t->device_ms, h->ev[EV_X0], h->ev[EV_K4]);
+        cudaEventElapsedTime(&t->device_ms, h->ev[EV_X0], h->ev[EV_K6]);
         if (h->per_kernel) {
-            const int seq[] = {EV_X0, EV_K0, EV_K1, EV_K2, EV_K3, EV_K4};
-            for (int i = 0; i < 5; ++i)
+            const int seq[] = {EV_X0, EV_K0, EV_K1, EV_K2, EV_K3, EV_K4, EV_K5, EV_K6};
+            for (int i = 0; i < 7; ++i)
                 if (cudaEventElapsedTime(&t->kernel_ms[i], h->ev[seq[i]], h->ev[seq[i + 1]]) != cudaSuccess) t->kernel_ms[i] = 0.f;
         }
     }

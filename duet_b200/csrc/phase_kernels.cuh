@@ -10,11 +10,11 @@
 //              earlier one" (:29)
 //   k_reduce   per SV: gather the joined reads' tags, class = #distinct PS (:192-194), one-PS candidate
 //              (:195-203), class-1 counts and score sums (:74-84), per-PS statistics of class-2 SVs in
-//              first-seen order (:85-105); the block completing a contig builds its sorted unique
-//              one-PS list (:107)
+//              first-seen order (:85-105)
+//   k_oneps    per contig: its sorted unique one-PS list (:107)
 //   k_predict  per SV: in-set PS with most reads (:99-105), nearest-PS fallback (:106-111), features
-//              (:112-139), the T1-T5 tree (:142-183); the block completing a contig writes its emission
-//              order (:206-229) and counters
+//              (:112-139), the T1-T5 tree (:142-183)
+//   k_order    per contig: emission order (:206-229) and counters
 //
 // What bounds these kernels at WGS size is not bandwidth (the whole problem is ~130 MB) but the ~1 us
 // round trip of a dependent global access, L2 atomic throughput and the HBM's random-sector rate.  So
@@ -53,7 +53,6 @@ struct __align__(16) ReadTag { int ps, pc; unsigned chk, hp; };       // hp: low
 
 // host-built descriptors: what a block needs to know about its tile, in one 32- / 16-byte load
 struct BuildTile { int lo, hi, base, mask, bmo, bmw, pad[2]; };   // shards of 256 consecutive support reads
-struct SvTile { int s_first, s_last, off0, off1; };               // shards of a block's SVs; SV range of s_first
 struct PredictTile { int sv0, sv1, shard, b, n, pad[3]; };        // SVs [sv0, sv1) of ONE shard = SVs [b, b + n)
 struct ProbeTile { long long r0, r1; int shard, base, mask, bmo, bmw, pad; };   // rows [r0, r1) of ONE contig + its table / filter
 
@@ -76,7 +75,6 @@ struct PhaseArgs {
     const long long *sv_off;     // [n_shards+1]
     const long long *join_off;   // [n_shards+1] csr_off at the shard boundaries (derived at upload)
     const BuildTile *build_tiles;   // [ceil(J / 256)]
-    const SvTile *reduce_tiles;     // [ceil(S / (kThreads / lanes per SV))]
     const PredictTile *predict_tiles;   // [sum over shards of ceil(n / kPredictPerBlock)] = k_predict grid
     const ProbeTile *probe_tiles;   // [n_probe_tiles] = k_probe grid
     int n_probe_tiles;
@@ -105,8 +103,6 @@ struct PhaseArgs {
     long long *cand;             // [S] one-PS candidate or kNoCand
     int *oneps;                  // [S] shard s: sorted unique list at [sv_off[s], +oneps_n[s])
     int *oneps_n;                // [n_shards]
-    int *done_reduce;            // [n_shards] SVs of the shard finished by k_reduce (self-resetting)
-    int *done_predict;           // [n_shards] same for k_predict
     C2Rec *c2rec;                // [S] per-PS statistics of class-2 SVs (k_reduce -> k_predict)
     long long *sort_scratch;     // [4*S] global tile for slow-path sorts of big shards
     uint8_t *gt, *cls;
@@ -741,11 +737,7 @@ __global__ void __launch_bounds__(kThreads, 6)
 k_reduce(PhaseArgs a) {
     constexpr int kReducePerBlock = kThreads / G;
     dbg_mark(a, 2, 0);
-    __shared__ __align__(16) long long s_tile[kSortSmemBytes / 8];
     __shared__ C2Group s_c2[kReducePerBlock];
-    __shared__ int s_list[kThreads];
-    __shared__ int s_n;
-    const SvTile tile = threadIdx.x == 0 ? a.reduce_tiles[blockIdx.x] : SvTile{0, 0, 0, 0};   // for the credit, requested early
     const int lane = threadIdx.x % G, grp = threadIdx.x / G;
     const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) / G * G));
     const int sv0 = blockIdx.x * kReducePerBlock;
@@ -854,33 +846,19 @@ k_reduce(PhaseArgs a) {
             rec->d[lane] = C2Ent{g.ps[lane], g.tot[lane], g.n1[lane], g.n2[lane], (long long)g.s1[lane], (long long)g.s2[lane], g.bad[lane], 0};
     }
 
-    // credit the shards of this block's SVs; the block completing a shard builds its one-PS list
     dbg_mark(a, 2, 2);
-    __syncthreads();
-    dbg_mark(a, 2, 3);
-    if (threadIdx.x == 0) {
-        __threadfence();                 // cumulative: orders the whole block's stores (after the barrier)
-        int n = 0;
-        if (sv0 < sv1) {
-            for (int s = tile.s_first; s <= tile.s_last; ++s) {
-                const int o0 = s == tile.s_first ? tile.off0 : (int)a.sv_off[s];
-                const int o1 = s == tile.s_first ? tile.off1 : (int)a.sv_off[s + 1];
-                const int lo = max(o0, sv0), hi = min(o1, sv1);
-                if (hi <= lo) continue;
-                if (atomicAdd(a.done_reduce + s, hi - lo) + (hi - lo) == o1 - o0) {
-                    a.done_reduce[s] = 0;
-                    s_list[n++] = s;
-                }
-            }
-        }
-        s_n = n;
-        __threadfence();
-    }
-    __syncthreads();
-    const int n_done = s_n;
-    dbg_mark(a, 2, 4);
-    for (int i = 0; i < n_done; ++i) oneps_any(a, s_list[i], s_tile);
-    dbg_mark(a, 2, 5);
+}
+
+// k_oneps: one block per shard -- the contig's sorted unique one-PS list (:107) from the candidates
+// k_reduce left behind.  Its blocks are resident before k_reduce ends (programmatic launch) and start the
+// moment it has.
+__global__ void __launch_bounds__(kThreads)
+k_oneps(PhaseArgs a) {
+    __shared__ __align__(16) long long s_tile[kSortSmemBytes / 8];
+    pdl_trigger();
+    pdl_wait();                                                  // every SV of the shard has been reduced
+    const int s = blockIdx.x;
+    if (a.sv_off[s + 1] > a.sv_off[s]) oneps_any(a, s, s_tile);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1148,7 +1126,6 @@ __device__ void order_block_small(const PhaseArgs &a, int s, long long *smem_til
         pos[u] = live ? __ldg(a.sv_pos + sv) : 0;
         grp[u] = live && a.sv_group ? __ldg(a.sv_group + sv) : 0;
     }
-    dbg_mark(a, 3, 6);
     unsigned long long c_kept = 0, c_emit = 0, c10 = 0, c01 = 0, c11 = 0, c_hits = 0;
     long long key[kOrdStage];
     long long mx = kNone;
@@ -1180,7 +1157,6 @@ __device__ void order_block_small(const PhaseArgs &a, int s, long long *smem_til
     const bool sorted = __syncthreads_and(ok);
     const int n_emit = (int)s_cnt[2];
     int w = block_scan_exclusive(cnt, 0, OpSum(), (int *)nullptr);
-    dbg_mark(a, 3, 7);
     if (sorted) {                                    // VCF already in (group, pos, class) order: just compact
 #pragma unroll
         for (int u = 0; u < kOrdStage; ++u)
@@ -1299,22 +1275,12 @@ __device__ __forceinline__ void order_block(const PhaseArgs &a, int s, long long
 // ------------------------------------------------------------------------------------------
 constexpr int kOneSmem = 2048;
 
-__device__ __forceinline__ void credit_one(const PhaseArgs &a, int s, int n, int total, int *s_list, int *s_n) {
-    if (atomicAdd(a.done_predict + s, n) + n == total) {
-        a.done_predict[s] = 0;
-        const int k = atomicAdd(s_n, 1);
-        if (k < kThreads) s_list[k] = s;
-    }
-}
-
 __global__ void __launch_bounds__(kThreads, 4)
 k_predict(PhaseArgs a) {
     __shared__ Class2Smem s_c2[kThreads / 32];
-    __shared__ __align__(16) long long s_tile[kSortSmemBytes / 8];
     __shared__ int s_one[kOneSmem];
-    __shared__ int s_list[kThreads];
     __shared__ int s_fb[kPredictPerBlock];
-    __shared__ int s_n, s_nfb, s_n_one;
+    __shared__ int s_nfb, s_n_one;
     dbg_mark(a, 3, 0);
     const PredictTile tile = a.predict_tiles[blockIdx.x];        // SVs [sv0, sv1) of ONE shard
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1330,7 +1296,7 @@ k_predict(PhaseArgs a) {
         cls = a.cls[sv];
         st = Class2Stats{a.hap1[sv], a.hap2[sv], 0, a.allhap[sv], a.ps[sv], a.totsc1[sv], a.totsc2[sv]};
     }
-    if (threadIdx.x == 0) { s_n = 0; s_nfb = 0; }
+    if (threadIdx.x == 0) s_nfb = 0;
     {   // the shard's sorted unique one-PS list (:107), built by the k_reduce block that completed the shard
         const int n_stage = min(tile.n, kOneSmem);
         for (int i = threadIdx.x; i < n_stage; i += kThreads) s_one[i] = a.oneps[tile.b + i];   // only [0, n) is meaningful
@@ -1380,18 +1346,18 @@ k_predict(PhaseArgs a) {
         if (lane == 0) decide_and_store(a, sv2, 2, t, one, n_one, (int)(e2 - b2));
     }
 
-    __syncthreads();
     dbg_mark(a, 3, 3);
-    if (threadIdx.x == 0) {
-        __threadfence();                 // cumulative: orders the whole block's stores (after the barrier)
-        if (blk0 < blk1) credit_one(a, shard, blk1 - blk0, tile.n, s_list, &s_n);
-        __threadfence();
-    }
-    __syncthreads();
-    const int n_done = min(s_n, kThreads);
-    dbg_mark(a, 3, 4);
-    for (int i = 0; i < n_done; ++i) order_block(a, s_list[i], s_tile);
-    dbg_mark(a, 3, 5);
+}
+
+// k_order: one block per shard -- emission order (:206-229) and counters, once every SV of the shard has
+// been decided.
+__global__ void __launch_bounds__(kThreads)
+k_order(PhaseArgs a) {
+    __shared__ __align__(16) long long s_tile[kSortSmemBytes / 8];
+    pdl_trigger();
+    pdl_wait();
+    const int s = blockIdx.x;
+    if (a.sv_off[s + 1] > a.sv_off[s]) order_block(a, s, s_tile);
 }
 
 }  // namespace duet

@@ -157,7 +157,7 @@ typedef struct duet_timings {
     float h2d_ms;          /* upload: host -> device copies                       */
     float device_ms;       /* all kernels of one execute                          */
     float d2h_ms;          /* download                                            */
-    float kernel_ms[8];    /* init, build, probe, reduce(+one-PS lists), predict(+order), unused... */
+    float kernel_ms[8];    /* init, build (k_table), probe, reduce, oneps, predict, order, unused */
 } duet_timings;
 
 typedef struct duet_handle duet_handle;

@@ -14,7 +14,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 tag = sys.argv[1] if len(sys.argv) > 1 else "rX"
-STAGES = ["init", "build", "probe", "reduce", "predict"]      # bench.py's names, in launch order
+STAGES = ["init", "build", "probe", "reduce", "oneps", "predict", "order"]      # bench.py's names, in launch order
 
 for w in ("c1", "c2", "c4", "c5", "ref"):
     src = os.path.join(G, f"bench_{w}.json")
@@ -67,9 +67,9 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 bench = json.loads(open(os.path.join(G, "bench_c2.json")).read().strip().splitlines()[-1])
 km = bench["kernel_ms"]
 tot = sum(km.values())
-L = [f"# {tag}: ncu --set full of the five launches of one call, C2 (caches flushed by ncu before each kernel; kernels "
+L = [f"# {tag}: ncu --set full of the seven launches of one call, C2 (caches flushed by ncu before each kernel; kernels "
      "serialised, so no programmatic-launch overlap)", "",
-     "`ncu --set full --clock-control none --import-source on -k regex:k_ -s 20 -c 5 python bench.py --steps 3 --warmup 3` "
+     "`ncu --set full --clock-control none --import-source on -k regex:k_ -s 28 -c 7 python bench.py --steps 3 --warmup 3` "
      "(tools/collect_profiles.sh; this file: tools/summarize_profiles.py)", "",
      "| metric | " + " | ".join(names) + " | unit |", "|---|" + "---|" * (len(names) + 1)]
 for w in want:
@@ -88,7 +88,7 @@ L += [f"- ({k} with the tag records left in page-locked host memory, `e2e` mode:
       "launches -- the gather over PCIe)" for k, v in bus.items()]
 L += ["", f"Event-timed stages of the same kernels inside bench.py ({tag}_bench_c2.json, serial, L2 flushed between steps): "
       + ", ".join(f"{k} {km[k] * 1e3:.1f} us ({100 * km[k] / tot:.1f} %)" for k in STAGES)
-      + f" -- the shares agree. The graph replay that `value` measures takes {bench['ms_per_step'] * 1e3:.1f} us for the five "
+      + f" -- the shares agree. The graph replay that `value` measures takes {bench['ms_per_step'] * 1e3:.1f} us for the seven "
       "(programmatic dependent launch overlaps each kernel's set-up with its predecessor's tail).",
       f"{tag}_timeline_c2.txt -- per-block stamps in graph-replay mode: where inside each kernel the microseconds go."]
 open(os.path.join(P, f"{tag}_ncu_all_kernels_c2.md"), "w").write("\n".join(L) + "\n")
