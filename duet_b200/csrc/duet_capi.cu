@@ -273,6 +273,8 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         return fail(h, DUET_ERR_INVALID, "duet_phase_upload: unknown `mem`");
     if (in->mem == DUET_MEM_DEVICE && (reinterpret_cast<uintptr_t>(in->read_key) & 15u))
         return fail(h, DUET_ERR_INVALID, "duet_phase_upload: read_key must be 16-byte aligned");
+    if (in->mem != DUET_MEM_HOST && (reinterpret_cast<uintptr_t>(in->read_tag) & 15u))      // read in place, 16 bytes at a time
+        return fail(h, DUET_ERR_INVALID, "duet_phase_upload: read_tag must be 16-byte aligned");
     if (in->read_off[0] != 0 || in->sv_off[0] != 0 || in->read_off[ns] != R || in->sv_off[ns] != S)
         return fail(h, DUET_ERR_INVALID, "duet_phase_upload: shard offsets do not span the columns");
     for (int s = 0; s < ns; ++s)

@@ -105,6 +105,16 @@ def test_tags_read_in_place_from_pinned_host_memory(engine):
     with pytest.raises(DuetError) as ei:
         engine.run(batch, tags_in_place=True)                    # numpy-owned (pageable) memory
     assert ei.value.code == _lib.ERR_INVALID
+    import dataclasses
+    from duet_b200.engine import pinned_empty
+    raw = pinned_empty(batch.read_tag.nbytes + 8, np.uint8)     # page-locked but 8 bytes off a 16-byte boundary
+    skew = raw[8:8 + batch.read_tag.nbytes].view(batch.read_tag.dtype)
+    skew[...] = batch.read_tag
+    with pytest.raises(DuetError) as ei:
+        engine.run(dataclasses.replace(pinned, read_tag=skew), tags_in_place=True)
+    assert ei.value.code == _lib.ERR_INVALID and "aligned" in str(ei.value)
+    e = engine.run(pinned, tags_in_place=True)                   # the handle is still usable
+    assert np.array_equal(a.gt, e.gt) and np.array_equal(a.order, e.order)
 
 
 def test_golden_kat_on_device(engine):
