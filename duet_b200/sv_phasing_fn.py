@@ -76,12 +76,19 @@ _DECODE_EXC = {
 }
 
 
+def _read_only_view(data):
+    """What ctypes should pass for a `const char *` parameter: `bytes` go by pointer (the C side only
+    reads), writable buffers are wrapped in place."""
+    if isinstance(data, bytes):
+        return C.c_char_p(data) if data else C.c_char_p(b"\0")
+    return (C.c_char * max(len(data), 1)).from_buffer(data)
+
+
 def decode_sam_text(text: bytes) -> ReadColumns:
     """One contig's `samtools view` output -> columns (C++: csrc/decode.cpp)."""
     lib = _lib.load()
     n = len(text)
-    buf = (C.c_char * max(n, 1)).from_buffer_copy(text) if not isinstance(text, (bytearray, memoryview)) else \
-        (C.c_char * max(n, 1)).from_buffer(text)
+    buf = _read_only_view(text)                    # no copy: a 40 MB memcpy per contig under the GIL serialises the threads
     cap = int(lib.duet_count_lines(buf, n))
     key, tag = np.empty(cap, np.uint64), np.empty(cap, TAG_DTYPE)
     n_rows, n_lines, err_line = C.c_int64(), C.c_int64(), C.c_int64()
@@ -93,7 +100,7 @@ def decode_sam_text(text: bytes) -> ReadColumns:
             raise UnicodeDecodeError("ascii", bytes(text[:1]), 0, 1, f"ordinal not in range(128) (line {err_line.value})")
         raise exc(f"{msg} (alignment line {err_line.value})")
     k = n_rows.value
-    return ReadColumns(key[:k].copy(), tag[:k].copy(), n_lines.value)
+    return ReadColumns(key[:k], tag[:k], n_lines.value)
 
 
 def decode_bam(data: bytes) -> ReadColumns:
@@ -102,7 +109,7 @@ def decode_bam(data: bytes) -> ReadColumns:
     lib = _lib.load()
     key_p, tag_p = C.c_void_p(), C.c_void_p()
     n_rows, n_rec, err = C.c_int64(), C.c_int64(), C.c_int64()
-    buf = (C.c_char * max(len(data), 1)).from_buffer_copy(data)
+    buf = _read_only_view(data)
     rc = lib.duet_decode_bam(buf, len(data), C.byref(key_p), C.byref(tag_p), C.byref(n_rows), C.byref(n_rec), C.byref(err))
     if rc != _lib.DUET_OK:
         exc, msg = _DECODE_EXC.get(rc, (ValueError, f"not a readable BAM (decode error {rc})"))
@@ -194,11 +201,13 @@ def hash_name_lists(lists: list[list[str]]):
     return lens, lo, hi
 
 
-def generate_callinfo(caller_path, read_hap, include_all_ctgs) -> PhaseBatch:
+def generate_callinfo(caller_path, read_hap, include_all_ctgs, comp_call=None) -> PhaseBatch:
     """The reference joins here on the host (:46-48); this version only lays the two sides out as
-    one columnar batch -- shard = contig -- and leaves the join to the device."""
-    logging.info("extract SV signatures")
-    comp_call = parse_vcf(caller_path, include_all_ctgs)
+    one columnar batch -- shard = contig -- and leaves the join to the device.  `comp_call`: the
+    already parsed VCF (generate_phased_callset parses it while the BAMs are being decoded)."""
+    if comp_call is None:
+        logging.info("extract SV signatures")
+        comp_call = parse_vcf(caller_path, include_all_ctgs)
     chrom_list = init_chrom_list(include_all_ctgs, caller_path[:len(caller_path) - 24])
     return build_batch(chrom_list, read_hap, contig_records(chrom_list, comp_call, read_hap))
 
@@ -287,7 +296,21 @@ def phase_batch(batch: PhaseBatch, svlen_thres, suppread_thres, engine: PhaseEng
 def generate_phased_callset(vcf_path, sam_home, svlen_thres, suppread_thres, thread, include_all_ctgs):
     """Same signature and return value as the reference's (sv_phasing_fn.py:185-230)."""
     t0 = time.perf_counter()
-    batch = generate_callinfo(vcf_path, read_hap_bam(sam_home, thread, include_all_ctgs), include_all_ctgs)
+    # The two decodes are independent: the haplotagged BAMs are scanned by C++ threads (GIL released) while
+    # this thread parses the SV VCF.  Errors surface in the reference's order: it reads the BAMs first (:186).
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=1) as background:
+        pending = background.submit(read_hap_bam, sam_home, thread, include_all_ctgs)
+        vcf_error = comp_call = None
+        try:
+            logging.info("extract SV signatures")
+            comp_call = parse_vcf(vcf_path, include_all_ctgs)
+        except Exception as e:                                   # noqa: BLE001 -- re-raised below, after the BAM errors
+            vcf_error = e
+        read_hap = pending.result()
+    if vcf_error is not None:
+        raise vcf_error
+    batch = generate_callinfo(vcf_path, read_hap, include_all_ctgs, comp_call)
     t1 = time.perf_counter()
     logging.info("integrate read weight information")
     logging.info("calculate read weight statistics")
