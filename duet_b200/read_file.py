@@ -15,7 +15,8 @@ Reference behaviour kept (file:line of the reference):
     record (7 or 6), split on ','                                               :48-55
   * GT / counts from the sample column, layout decided by the first record      :56-76
     (cuteSV GT:DR:DV:PL:GQ, Sniffles2 GT:GQ:DR:DV -> column [15] is GQ, SVIM GT:DP:AD)
-The reference scans all lines once per contig (24 passes); this reader makes one pass.
+The reference scans all lines once per contig (24 passes) and splits every INFO string into its
+items; this reader makes one pass and locates the four items it needs with str.find.
 Inputs the reference would silently mis-index (first record of a contig without a support or
 read-name item, sample column with fewer than 3 fields) raise ValueError here.
 """
@@ -40,7 +41,7 @@ def init_chrom_list(include_all_ctgs, home):
 
 def read_file(vcf_path):
     with open(vcf_path, "r") as fh:
-        return [ln.strip().split() for ln in fh.readlines()]
+        return [ln.split() for ln in fh.readlines()]          # == ln.strip().split() (:20-21)
 
 
 @dataclass
@@ -62,12 +63,20 @@ class ContigSvs:
         return len(self.pos)
 
 
-def _first_with(items, needles):
-    for it in items:
-        for nd in needles:
-            if nd in it:
-                return it
-    return None
+def _first_with(info: str, needles):
+    """The first ';'-separated item of INFO that contains any of `needles` -- what the reference finds by
+    scanning `info.split(';')` item by item (:34-55) -- located with str.find instead: the earliest
+    occurrence of a needle lies in exactly that item (no needle contains ';')."""
+    at = -1
+    for nd in needles:
+        k = info.find(nd)
+        if k >= 0 and (at < 0 or k < at):
+            at = k
+    if at < 0:
+        return None
+    a = info.rfind(";", 0, at) + 1
+    b = info.find(";", at)
+    return info[a:] if b < 0 else info[a:b]
 
 
 def _count(txt):
@@ -99,9 +108,8 @@ def parse_vcf(vcf_file, include_all_ctgs):
         out.append(cs)
         if not rows:
             continue
-        infos = [r[7].split(";") for r in rows]
         sup_keys, name_keys = ("SUPPORT=", "SR=", "RE="), ("RNAMES=", "READS=")
-        first_sup, first_nm = _first_with(infos[0], sup_keys), _first_with(infos[0], name_keys)
+        first_sup, first_nm = _first_with(rows[0][7], sup_keys), _first_with(rows[0][7], name_keys)
         if first_sup is None or first_nm is None:
             raise ValueError(f"contig {chrom_list[ch]}: first record lacks a SUPPORT=/RE=/SR= or RNAMES=/READS= "
                              "INFO item (the reference mis-indexes its columns on such input)")
@@ -114,12 +122,14 @@ def parse_vcf(vcf_file, include_all_ctgs):
             ad_mode = head[-1].find(",") != -1
         else:
             raise ValueError(f"contig {chrom_list[ch]}: sample column '{rows[0][9]}' has fewer than 3 fields")
-        for r, info in zip(rows, infos):
-            item = _first_with(info, ("SVLEN=",))
+        svlen_key, svtype_key = ("SVLEN=",), ("SVTYPE=",)
+        for r in rows:
+            info = r[7]
+            item = _first_with(info, svlen_key)
             if item is None or item == "SVLEN=.":
                 item = "SVLEN=0"
             cs.svlen.append(int(item[7:]) if ">" in item else int(item[6:]))
-            cs.svtype.append(_first_with(info, ("SVTYPE=",))[7:])
+            cs.svtype.append(_first_with(info, svtype_key)[7:])
             cs.svread.append(_i32(int(_first_with(info, sup_keys)[sup_cut:]), "support"))
             cs.names.append(_first_with(info, name_keys)[nm_cut:].split(","))
             smp = r[9].split(":")

@@ -90,6 +90,27 @@ def test_decoders_match_oracle_on_golden_inputs(name, golden_workdir):
     assert write_file.header_text(vcf, inc) + write_file.format_rows(case["rows"]) == case["phased_sv_vcf"]
 
 
+def test_info_item_lookup_equals_the_item_scan():
+    """read_file._first_with finds 'the first INFO item containing a needle' with str.find; the reference
+    scans info.split(';') item by item (read_file.py:34-55).  Same item on adversarial strings: needles
+    inside other keys, repeated keys, empty items, no match."""
+    rng = np.random.default_rng(7)
+    pieces = ["SVLEN=12", "XSVLEN=>7", "SVLEN=.", "SVTYPE=DEL", "RE=4", "SR=9", "SUPPORT=3", "PRE=1", "RNAMES=a,b", "READS=c",
+              "AF=0.5", "", "CORE=2", "STRANDS=+-", "FURTHERNAMES=x", "END=5"]
+    groups = [("SVLEN=",), ("SVTYPE=",), ("SUPPORT=", "SR=", "RE="), ("RNAMES=", "READS=")]
+
+    def scan(info, needles):
+        for it in info.split(";"):
+            if any(nd in it for nd in needles):
+                return it
+        return None
+
+    for _ in range(3000):
+        info = ";".join(pieces[i] for i in rng.integers(0, len(pieces), int(rng.integers(0, 9))))
+        for needles in groups:
+            assert read_file._first_with(info, needles) == scan(info, needles), (info, needles)
+
+
 def test_text_path_equals_direct_columnar(tmp_path):
     s = synth.make_sample(3, contigs=["1", "5", "X"], n_reads=3000, n_svs=250, bp_per_read=700, block_mean=1e5)
     home = str(tmp_path)
