@@ -66,7 +66,7 @@ SYMBOLS = (
     "duet_set_thresholds", "duet_set_stream", "duet_phase_upload", "duet_phase_execute",
     "duet_phase_download", "duet_phase_run", "duet_host_alloc", "duet_host_free", "duet_sync",
     "duet_get_timings", "duet_launch_count", "duet_default_cluster_params", "duet_cluster_run", "duet_hash_names",
-    "duet_pack_tags", "duet_debug_timers", "duet_decode_bam", "duet_set_decode_threads", "duet_free", "duet_decode_sam_text", "duet_count_lines",
+    "duet_pack_tags", "duet_hash_name_lists", "duet_debug_timers", "duet_decode_bam", "duet_set_decode_threads", "duet_free", "duet_decode_sam_text", "duet_count_lines",
 )
 DECODE_ERR_INDEX, DECODE_ERR_VALUE, DECODE_ERR_ASCII, DECODE_ERR_RANGE, DECODE_ERR_CAPACITY, DECODE_ERR_FORMAT = 20, 21, 22, 23, 24, 25
 
@@ -124,6 +124,8 @@ def load() -> C.CDLL:
     lib.duet_hash_names.restype = None
     lib.duet_decode_sam_text.argtypes = [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 2 + \
                                        [C.POINTER(C.c_int64)] * 3
+    lib.duet_hash_name_lists.argtypes = [C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.duet_hash_name_lists.restype = C.c_int64
     lib.duet_set_decode_threads.argtypes = [C.c_int]
     lib.duet_set_decode_threads.restype = C.c_int
     lib.duet_decode_bam.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)] + \

@@ -88,6 +88,33 @@ void duet_hash_names(const char *buf, const int64_t *off, int64_t n, uint64_t *l
         hash128(reinterpret_cast<const unsigned char *>(buf) + off[i], (size_t)(off[i + 1] - off[i]), lo + i, hi + i);
 }
 
+int64_t duet_hash_name_lists(const char *blob, int64_t len, int64_t n_lists, int64_t cap, int64_t *lens,
+                             uint64_t *lo, uint64_t *hi) {
+    // `blob` = the comma-separated name lists of n_lists records joined with '\n' (no trailing newline).
+    // Splits like Python's str.split(','): "" is one empty name, "a,,b" has an empty name in the middle.
+    const unsigned char *p = reinterpret_cast<const unsigned char *>(blob), *end = p + len;
+    int64_t k = 0, rec = 0;
+    if (n_lists <= 0) return 0;
+    const unsigned char *start = p;
+    int64_t in_rec = 0;
+    for (;; ++p) {
+        const bool at_end = p == end;
+        if (at_end || *p == ',' || *p == '\n') {
+            if (k >= cap) return -1;
+            hash128(start, (size_t)(p - start), lo + k, hi + k);
+            ++k; ++in_rec;
+            start = p + 1;
+            if (at_end || *p == '\n') {
+                if (rec >= n_lists) return -1;
+                lens[rec++] = in_rec;
+                in_rec = 0;
+                if (at_end) break;
+            }
+        }
+    }
+    return rec == n_lists ? k : -1;
+}
+
 void duet_pack_tags(int64_t n, const uint8_t *hp, const int32_t *ps, const int32_t *pc, const uint64_t *hi,
                     duet_read_tag *out) {
     for (int64_t i = 0; i < n; ++i) {

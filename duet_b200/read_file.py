@@ -54,13 +54,19 @@ class ContigSvs:
     svlen: list = field(default_factory=list)     # signed, as parsed (:36)
     svtype: list = field(default_factory=list)
     svread: list = field(default_factory=list)
-    names: list = field(default_factory=list)     # list[list[str]]
+    names_csv: list = field(default_factory=list) # the RNAMES / READS value per record, unsplit ("a,b,c")
     gt: list = field(default_factory=list)
     refread: list = field(default_factory=list)   # column [15]
     altread: list = field(default_factory=list)   # column [16]
 
     def __len__(self):
         return len(self.pos)
+
+    @property
+    def names(self):
+        """list[list[str]] -- what the reference keeps in column [13] (:48-55).  The device path hashes the
+        unsplit strings natively (duet_hash_name_lists) and never builds these."""
+        return [s.split(",") for s in self.names_csv]
 
 
 def _first_with(info: str, needles):
@@ -131,7 +137,7 @@ def parse_vcf(vcf_file, include_all_ctgs):
             cs.svlen.append(int(item[7:]) if ">" in item else int(item[6:]))
             cs.svtype.append(_first_with(info, svtype_key)[7:])
             cs.svread.append(_i32(int(_first_with(info, sup_keys)[sup_cut:]), "support"))
-            cs.names.append(_first_with(info, name_keys)[nm_cut:].split(","))
+            cs.names_csv.append(_first_with(info, name_keys)[nm_cut:])
             smp = r[9].split(":")
             cs.gt.append(smp[0])
             if ad_mode:

@@ -201,6 +201,23 @@ def hash_name_lists(lists: list[list[str]]):
     return lens, lo, hi
 
 
+def hash_name_csv(csv_lists: list[str]):
+    """Same result as hash_name_lists([s.split(',') for s in csv_lists]) without creating a Python string
+    per name: the C++ side splits and hashes (duet_hash_name_lists)."""
+    lib = _lib.load()
+    n = len(csv_lists)
+    lens = np.zeros(n, np.int64)
+    if n == 0:
+        return lens, np.empty(0, np.uint64), np.empty(0, np.uint64)
+    blob = "\n".join(csv_lists).encode("ascii")
+    cap = blob.count(b",") + n
+    lo, hi = np.empty(cap, np.uint64), np.empty(cap, np.uint64)
+    got = lib.duet_hash_name_lists(blob, len(blob), n, cap, lens.ctypes.data, lo.ctypes.data, hi.ctypes.data)
+    if got != cap:
+        raise ValueError("support-read name lists contain a line break")     # cannot come from a split VCF line
+    return lens, lo, hi
+
+
 def generate_callinfo(caller_path, read_hap, include_all_ctgs, comp_call=None) -> PhaseBatch:
     """The reference joins here on the host (:46-48); this version only lays the two sides out as
     one columnar batch -- shard = contig -- and leaves the join to the device.  `comp_call`: the
@@ -240,7 +257,7 @@ def contig_records(chrom_list, comp_call: list[ContigSvs], read_hap: list[ReadCo
                 raise NotImplementedError(
                     f"contigs {chrom_list[o]!r} and {c!r} both claim CHROM {src.chrom[idx[0]]!r} but read different "
                     "haplotagged BAMs; the reference's result for such a contig list cannot be reproduced per contig")
-            for f in ("chrom", "pos", "ref", "alt", "svlen", "svtype", "svread", "names", "gt", "refread", "altread"):
+            for f in ("chrom", "pos", "ref", "alt", "svlen", "svtype", "svread", "names_csv", "gt", "refread", "altread"):
                 getattr(cs, f).extend(getattr(src, f)[i] for i in idx)
         out.append(cs)
     return out
@@ -259,11 +276,11 @@ def build_batch(chrom_list, read_hap: list[ReadColumns], comp_call: list[ContigS
         chrom += cs.chrom; svtype += cs.svtype; ref += cs.ref; alt += cs.alt
         pos += cs.pos; svlen += [abs(v) for v in cs.svlen]; svread += cs.svread; refread += cs.refread
         flags += [_lib.SV_GT_MISSING if g == "./." else 0 for g in cs.gt]
-        lists += cs.names
+        lists += cs.names_csv
         ranks = {c: i for i, c in enumerate(sorted(set(cs.chrom)))}     # 'chr1' and '1' rows in one contig
         any_group |= len(ranks) > 1
         group += [ranks[c] for c in cs.chrom]
-    lens, ck, ch = hash_name_lists(lists)
+    lens, ck, ch = hash_name_csv(lists)
     csr_off = np.zeros(len(lists) + 1, np.int64)
     np.cumsum(lens, out=csr_off[1:])
     b = PhaseBatch(

@@ -242,6 +242,14 @@ enum {
  * check word = (uint32_t)hi. */
 void duet_hash_names(const char *buf, const int64_t *off, int64_t n, uint64_t *lo, uint64_t *hi);
 
+/* The same hash for whole RNAMES / READS lists without materialising the names: `blob` holds the
+ * comma-separated lists of `n_lists` records joined by '\n' (read_file.py:48-55 splits them on ',').
+ * Writes lens[n_lists] (names per record, an empty list string counts as one empty name, as
+ * str.split does) and lo/hi for every name in order; `cap` = room in lo/hi.  Returns the number
+ * of names, or -1 if the blob does not hold exactly n_lists records or cap is too small. */
+int64_t duet_hash_name_lists(const char *blob, int64_t len, int64_t n_lists, int64_t cap, int64_t *lens,
+                             uint64_t *lo, uint64_t *hi);
+
 /* Separate HP / PS / PC (+ hash high words, may be NULL -> chk 0) columns -> tag records. */
 void duet_pack_tags(int64_t n, const uint8_t *hp, const int32_t *ps, const int32_t *pc, const uint64_t *hi,
                     duet_read_tag *out);

@@ -90,6 +90,26 @@ def test_decoders_match_oracle_on_golden_inputs(name, golden_workdir):
     assert write_file.header_text(vcf, inc) + write_file.format_rows(case["rows"]) == case["phased_sv_vcf"]
 
 
+def test_name_lists_hashed_without_splitting():
+    """duet_hash_name_lists splits the unsplit RNAMES strings itself: same lengths and hashes as hashing
+    [s.split(',') for s in lists], including empty names and an empty list string."""
+    rng = np.random.default_rng(3)
+    alphabet = np.array(list("abcdefghijklmnopqrstuvwxyz0123456789-_/:"))
+    lists = []
+    for _ in range(500):
+        k = int(rng.integers(0, 12))
+        lists.append(",".join("".join(alphabet[rng.integers(0, len(alphabet), int(rng.integers(0, 40)))]) for _ in range(k)))
+    lists += ["", ",", "a,,b", "solo"]
+    lens_a, lo_a, hi_a = sv_phasing_fn.hash_name_csv(lists)
+    lens_b, lo_b, hi_b = sv_phasing_fn.hash_name_lists([s.split(",") for s in lists])
+    assert np.array_equal(lens_a, lens_b) and np.array_equal(lo_a, lo_b) and np.array_equal(hi_a, hi_b)
+    assert lens_a[-4:].tolist() == [1, 2, 3, 1]
+    lens_e, lo_e, _ = sv_phasing_fn.hash_name_csv([])
+    assert lens_e.size == 0 and lo_e.size == 0
+    with pytest.raises(ValueError):
+        sv_phasing_fn.hash_name_csv(["a\nb"])
+
+
 def test_info_item_lookup_equals_the_item_scan():
     """read_file._first_with finds 'the first INFO item containing a needle' with str.find; the reference
     scans info.split(';') item by item (read_file.py:34-55).  Same item on adversarial strings: needles
