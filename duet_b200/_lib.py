@@ -58,7 +58,7 @@ class ClusterInput(C.Structure):
                [(n, C.c_void_p) for n in ("contig", "type", "start", "end")]
 
 
-KERNEL_NAMES = ("init", "build", "probe", "reduce", "oneps", "predict", "order")
+KERNEL_NAMES = ("build", "probe", "reduce", "tail", "oneps", "predict", "order")
 
 # every symbol include/duet_b200.h declares
 SYMBOLS = (

@@ -20,14 +20,15 @@ thread_local std::string g_create_error;
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
-    cudaError_t reserve(size_t bytes) {
+    cudaError_t reserve(size_t bytes, bool *grew = nullptr) {
+        if (grew) *grew = false;
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
+        if (e == cudaSuccess) { cap = want; if (grew) *grew = true; }
         return e;
     }
     void release() {
@@ -38,7 +39,28 @@ struct DevBuf {
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-enum { EV_H2D0, EV_H2D1, EV_X0, EV_K0, EV_K1, EV_K2, EV_K3, EV_K4, EV_K5, EV_K6, EV_D2H0, EV_D2H1, EV_COUNT };
+// page-locked host staging (descriptors on the way in): grows, never shrinks
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+enum { EV_H2D0, EV_H2D1, EV_X0, EV_K0, EV_K1, EV_K2, EV_K3, EV_K4, EV_K5, EV_K6, EV_D2H0, EV_D2H1, EV_DESC, EV_COUNT };
 
 }  // namespace
 
@@ -57,25 +79,28 @@ struct duet_handle {
     std::vector<long long> h_read_off, h_sv_off;
     long long n_slots = 0, n_bm_words = 0;
     int n_sm = 148;
+    int flags = 0;                  // developer switches (DUET_FLAGS), see phase_kernels.cuh
 
     // staged input copies (HOST mode)
     DevBuf in_read_key, in_read_tag;
     DevBuf in_sv_pos, in_sv_svlen, in_sv_svread, in_sv_refread, in_sv_flags, in_sv_group;
     DevBuf in_csr_off, in_csr_key, in_csr_chk;
-    // descriptors, table, scratch, outputs
-    DevBuf d_read_off, d_sv_off, d_join_off, d_tab_off, d_tab_mask, d_c2;
-    DevBuf d_btiles, d_ptiles, d_qtiles, d_dbg, d_cand_key, d_cand_row;
-    int probe_grid = 0, predict_grid = 0;
+    // descriptors (one page-locked staging buffer -> one device buffer, one copy), table, scratch, outputs
+    PinBuf h_desc;
+    bool desc_in_flight = false;    // EV_DESC marks the end of the last descriptor copy
+    DevBuf d_desc, d_c2, d_dbg;
+    int probe_grid = 0, predict_grid = 0, tail_set = 0, tail_vals = 0;
+    bool tail_fused = true;         // every contig fits a cluster: k_tail; else k_oneps / k_predict / k_order
     int reduce_lanes = kReduceLanesSparse;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     PhaseArgs graph_args;           // what the captured launches were given
-    int graph_dims[4] = {0, 0, 0, 0};
-    bool graph_valid = false;       // cleared when n_slots / n_bm_words change (they are launch arguments)
+    int graph_dims[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool dbg_on = false;
     size_t probe_smem = 0;
-    DevBuf d_table;                 // Slot[n_slots] followed by the Bloom filter words
-    DevBuf d_bm_off, d_bm_wmask, d_next, d_join_row, d_n_hit, d_cand, d_oneps, d_oneps_n, d_sort;
+    DevBuf d_table;                 // Slot[n_slots]: all-ones between calls (k_scan claims, k_reduce frees)
+    DevBuf d_cand_key, d_cand_row, d_cand_n;
+    DevBuf d_next, d_join_row, d_n_hit, d_cand, d_oneps, d_oneps_n, d_sort;
     DevBuf d_gt, d_cls, d_ps, d_hap1, d_hap2, d_hap0, d_allhap, d_t1, d_t2, d_feat, d_order, d_n_emit;
     DevBuf d_counts, d_status;
     // kernel set B (signature clustering)
@@ -112,6 +137,17 @@ long long pow2_at_least(long long n) {
     return p;
 }
 
+// descriptor arena: sections of one host buffer, 256-byte aligned, copied to the device in one piece
+struct Arena {
+    std::vector<unsigned char> bytes;
+    template <typename T> size_t put(const std::vector<T> &v) {
+        const size_t off = (bytes.size() + 255) & ~(size_t)255;
+        bytes.resize(off + std::max<size_t>(v.size(), 1) * sizeof(T));
+        if (!v.empty()) std::memcpy(bytes.data() + off, v.data(), v.size() * sizeof(T));
+        return off;
+    }
+};
+
 }  // namespace
 
 // One launch of the chain.  `pdl`: with the programmatic-serialization attribute the kernel's blocks may be
@@ -128,6 +164,8 @@ static void launch(void (*kernel)(Params...), int grid, int block, size_t smem, 
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, Params(args)...);
 }
+
+static size_t tail_smem_bytes(int n_set, int n_vals) { return ((size_t)n_set + (size_t)n_vals) * sizeof(int); }
 
 extern "C" {
 
@@ -167,6 +205,7 @@ int duet_create(int device_id, duet_handle **out) {
     if (device_id < 0 || device_id >= n) return fail(nullptr, DUET_ERR_INVALID, "duet_create: bad device id");
     duet_handle *h = new duet_handle();
     h->device = device_id;
+    if (const char *f = std::getenv("DUET_FLAGS")) h->flags = std::atoi(f);
     duet_default_thresholds(&h->thr);
     std::memset(&h->a, 0, sizeof(h->a));
     if (cudaSetDevice(device_id) != cudaSuccess ||
@@ -180,17 +219,19 @@ int duet_create(int device_id, duet_handle **out) {
     for (auto &ev : h->cl_ev) cudaEventCreate(&ev);
     {   // fails here, loudly, if the image was not built for this device (sm_100a only)
         cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, k_probe);
-        cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, kBloomMaxWords * 4 + kProbeRingBytes);
+        cudaFuncGetAttributes(&fa, k_scan);
+        cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, kBloomMaxWords * 4 + kProbeRingBytes);
+        cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)tail_smem_bytes((int)pow2_at_least(2 * kTailMaxSvs), kTailMaxSvs + 8));
         // one shared-memory carveout for all the kernels: switching it between launches drains the SMs
-        cudaFuncSetAttribute(k_table, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_scan, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_probe, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_reduce<kReduceLanesSparse>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_reduce<kReduceLanesDense>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_tail, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_predict, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_oneps, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_order, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(k_init, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device_id);
     }
     if (cudaGetLastError() != cudaSuccess) {
@@ -207,12 +248,13 @@ void duet_destroy(duet_handle *h) {
     cudaStreamSynchronize(h->stream);
     DevBuf *bufs[] = {&h->in_read_key, &h->in_read_tag,
                       &h->in_sv_pos, &h->in_sv_svlen, &h->in_sv_svread, &h->in_sv_refread, &h->in_sv_flags,
-                      &h->in_sv_group, &h->in_csr_off, &h->in_csr_key, &h->in_csr_chk, &h->d_read_off,
-                      &h->d_sv_off, &h->d_join_off, &h->d_c2, &h->d_btiles, &h->d_ptiles, &h->d_qtiles, &h->d_dbg, &h->d_cand_key, &h->d_cand_row, &h->d_tab_off, &h->d_tab_mask, &h->d_table, &h->d_bm_off, &h->d_bm_wmask, &h->d_next,
+                      &h->in_sv_group, &h->in_csr_off, &h->in_csr_key, &h->in_csr_chk, &h->d_desc,
+                      &h->d_c2, &h->d_dbg, &h->d_table, &h->d_cand_key, &h->d_cand_row, &h->d_cand_n, &h->d_next,
                       &h->d_join_row, &h->d_n_hit, &h->d_cand, &h->d_oneps, &h->d_oneps_n, &h->d_sort, &h->d_gt,
                       &h->d_cls, &h->d_ps, &h->d_hap1, &h->d_hap2, &h->d_hap0, &h->d_allhap, &h->d_t1, &h->d_t2,
                       &h->d_feat, &h->d_order, &h->d_n_emit, &h->d_counts, &h->d_status};
     for (DevBuf *b : bufs) b->release();
+    h->h_desc.release();
     for (DevBuf &b : h->cl_in) b.release();
     for (DevBuf *b : {&h->cl_key[0], &h->cl_key[1], &h->cl_idx[0], &h->cl_idx[1], &h->cl_span, &h->cl_parent,
                       &h->cl_minidx, &h->cl_out, &h->cl_hist, &h->cl_misc}) b->release();
@@ -285,27 +327,28 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     CU(h, cudaEventRecord(h->ev[EV_H2D0], st));
 
     // CSR offsets at shard boundaries size the per-shard slot ranges
-    std::vector<long long> csr_host;
-    const long long *csr = reinterpret_cast<const long long *>(in->csr_off);
+    std::vector<long long> join_off(ns + 1);
     if (in->mem == DUET_MEM_DEVICE) {
-        csr_host.resize(S + 1);
+        // the columns are resident: fetch just the ns+1 boundary values (one small strided copy)
+        std::vector<long long> csr_host((size_t)S + 1);
         CU(h, cudaMemcpyAsync(csr_host.data(), in->csr_off, (S + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
         CU(h, cudaStreamSynchronize(st));
-        csr = csr_host.data();
+        if (csr_host[0] != 0 || csr_host[S] != J) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: csr_off does not span csr_key");
+        for (int s = 0; s <= ns; ++s) join_off[s] = csr_host[in->sv_off[s]];
+    } else {
+        const long long *csr = reinterpret_cast<const long long *>(in->csr_off);
+        if (csr[0] != 0 || csr[S] != J) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: csr_off does not span csr_key");
+        for (int s = 0; s <= ns; ++s) join_off[s] = csr[in->sv_off[s]];
     }
-    if (csr[0] != 0 || csr[S] != J) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: csr_off does not span csr_key");
-    std::vector<int> tab_off(ns), tab_mask(ns), bm_off(ns), bm_wmask(ns);
-    std::vector<long long> join_off(ns + 1);
-    for (int s = 0; s <= ns; ++s) join_off[s] = csr[in->sv_off[s]];
-    // slot table: 16-byte slots.  Bloom filter: 16 bits per name, at most 64 KB per shard (it has to fit in
-    // shared memory twice per SM).  Both are (re)initialised by one sequential memset
-    // at the start of every call, which also makes them L2 resident for the random traffic that follows.
-    // Load factor <= 1/4 while such a table (<= 8 slots of 16 B per name after rounding up to a power of
-    // two) stays within half of the 126 MB L2, else <= 1/2: a sparser table means fewer CAS retry rounds
-    // in k_table and fewer probe rounds in k_probe (a warp waits for its unluckiest lane), but one that
-    // spills out of L2 costs more than it saves (measured: WGS 30x -5 % device time, 60x dense +3.5 %).
-    const long long fill = J * 8 * (long long)sizeof(Slot) <= (64ll << 20) ? 4 : 2;
-    long long slots = 0, max_sv = 0, bm_words = 0;
+    std::vector<int> tab_off(ns), tab_mask(ns), bm_wmask(ns);
+    // slot table: 16-byte slots, load factor <= 1/4 while such a table (<= 8 slots of 16 B per name after
+    // rounding up to a power of two) stays within half of the 126 MB L2, else <= 1/2: a sparser table means
+    // fewer CAS retry rounds in k_scan and fewer probe rounds in k_probe (a warp waits for its unluckiest
+    // lane), but one that spills out of L2 costs more than it saves.  Only the claimed slots are ever
+    // touched -- the table is handed back clean by the call itself -- so its size costs no sweep.
+    // Bloom filter: 16 bits per name, at most 64 KB per shard (it lives in shared memory, two blocks per SM).
+    const long long fill = (J * 8 * (long long)sizeof(Slot) <= (64ll << 20) && !(h->flags & kFlagFill2)) ? 4 : 2;
+    long long slots = 0, max_sv = 0;
     for (int s = 0; s < ns; ++s) {
         const long long nj = join_off[s + 1] - join_off[s];
         if (nj < 0) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: csr_off is not monotone");
@@ -314,21 +357,19 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         tab_mask[s] = (int)(cap - 1);
         slots += cap;
         const long long words = std::min<long long>(pow2_at_least(std::max<long long>(nj / 2, 32)), kBloomMaxWords);
-        bm_off[s] = (int)bm_words;
         bm_wmask[s] = (int)(words - 1);
-        bm_words += words;
         max_sv = std::max<long long>(max_sv, in->sv_off[s + 1] - in->sv_off[s]);
         if (slots >= (1ll << 31)) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: join table too large");
     }
-    if (h->n_slots != slots || h->n_bm_words != bm_words) h->graph_valid = false;
     h->n_slots = slots;
-    h->n_bm_words = bm_words;
     h->h_read_off.assign(in->read_off, in->read_off + ns + 1);
     h->h_sv_off.assign(in->sv_off, in->sv_off + ns + 1);
 
     PhaseArgs &a = h->a;
     std::memset(&a, 0, sizeof(a));
     a.n_shards = ns; a.n_reads = (int)R; a.n_svs = (int)S; a.n_joins = (int)J;
+    a.n_slots = slots;
+    a.flags = h->flags;
     const int mem = in->mem == DUET_MEM_HOST_MAPPED ? DUET_MEM_HOST : in->mem;      // only read_tag is special
     int rc;
 #define STAGE(buf, field, T, count)                                                                  \
@@ -356,41 +397,28 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     STAGE(in_csr_key, csr_key, uint64_t, J)
     STAGE(in_csr_chk, csr_chk, uint32_t, J)
 #undef STAGE
-    // descriptors are host arrays in both modes
-    const void *dv;
-    if ((rc = stage(h, h->d_read_off, h->h_read_off.data(), sizeof(long long) * (ns + 1), DUET_MEM_HOST, &dv))) return rc;
-    a.read_off = static_cast<const long long *>(dv);
-    if ((rc = stage(h, h->d_sv_off, h->h_sv_off.data(), sizeof(long long) * (ns + 1), DUET_MEM_HOST, &dv))) return rc;
-    a.sv_off = static_cast<const long long *>(dv);
-    if ((rc = stage(h, h->d_join_off, join_off.data(), sizeof(long long) * (ns + 1), DUET_MEM_HOST, &dv))) return rc;
-    a.join_off = static_cast<const long long *>(dv);
-    std::vector<int> sv_shard((size_t)S);
-    for (int s = 0; s < ns; ++s)
-        std::fill(sv_shard.begin() + in->sv_off[s], sv_shard.begin() + in->sv_off[s + 1], s);
-    // per-block tile descriptors (what each block would otherwise look up with dependent loads)
+
+    // ---- descriptors: shard offsets, table / filter ranges and the per-block tiles of every kernel (what a
+    // block would otherwise look up with dependent loads), laid out in ONE page-locked buffer -> one copy ----
     auto shard_at = [&](const std::vector<long long> &off, long long x) {
         return (int)(std::upper_bound(off.begin(), off.end(), x) - off.begin()) - 1;
     };
-    std::vector<BuildTile> btiles((size_t)((J + kBuildTile - 1) / kBuildTile));
-    for (size_t t = 0; t < btiles.size(); ++t) {
-        const long long first = (long long)t * kBuildTile, last = std::min<long long>(J, first + kBuildTile) - 1;
-        const int lo = shard_at(join_off, first), hi = shard_at(join_off, last);
-        btiles[t] = BuildTile{lo, hi, tab_off[lo], tab_mask[lo], bm_off[lo], bm_wmask[lo], {0, 0}};
-    }
     h->reduce_lanes = (S > 0 && J / std::max<long long>(S, 1) > 32) ? kReduceLanesDense : kReduceLanesSparse;
+    // the per-contig steps: one cluster per contig (k_tail) when every contig fits one
+    h->tail_fused = max_sv <= kTailMaxSvs && !(h->flags & kFlagSplitTail);
+    h->tail_set = (int)pow2_at_least(std::max<long long>(2 * max_sv, kTailMinSet));
+    h->tail_vals = (int)((std::max<long long>(max_sv, 2 * kThreads) + 3) / 4 * 4 + 4);
     std::vector<PredictTile> ptiles;                             // k_predict blocks never span shards
-    for (int s = 0; s < ns; ++s) {
-        const int b = (int)in->sv_off[s], n = (int)(in->sv_off[s + 1] - in->sv_off[s]);
-        for (int o = 0; o < n; o += kPredictPerBlock)
-            ptiles.push_back(PredictTile{b + o, std::min(b + n, b + o + kPredictPerBlock), s, b, n, {0, 0, 0}});
-    }
+    if (!h->tail_fused)
+        for (int s = 0; s < ns; ++s) {
+            const int b = (int)in->sv_off[s], n = (int)(in->sv_off[s + 1] - in->sv_off[s]);
+            for (int o = 0; o < n; o += kPredictPerBlock)
+                ptiles.push_back(PredictTile{b + o, std::min(b + n, b + o + kPredictPerBlock), s, b, n, {0, 0, 0}});
+        }
     h->predict_grid = (int)ptiles.size();
-    if ((rc = stage(h, h->d_btiles, btiles.data(), sizeof(BuildTile) * btiles.size(), DUET_MEM_HOST, &dv))) return rc;
-    a.build_tiles = static_cast<const BuildTile *>(dv);
-    if ((rc = stage(h, h->d_ptiles, ptiles.data(), sizeof(PredictTile) * std::max<size_t>(ptiles.size(), 1), DUET_MEM_HOST, &dv))) return rc;
-    a.predict_tiles = static_cast<const PredictTile *>(dv);
-    // k_probe tiles: row ranges that never cross a contig, about two per SM in total
-    std::vector<ProbeTile> qtiles;
+    // k_scan / k_probe tiles: row ranges that never cross a contig, about two per SM in total; the names to
+    // insert are dealt out evenly over the same blocks
+    std::vector<ScanTile> qtiles;
     {
         // tiles of about equal size (a contig's rows are cut into round(rows / per) pieces), as many as fit
         // on the device at once: more would mean a second wave costing a whole block time
@@ -398,7 +426,7 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         for (int s = 0; s < ns; ++s) max_words = std::max<long long>(max_words, (long long)bm_wmask[s] + 1);
         h->probe_smem = (size_t)kProbeRingBytes + (size_t)max_words * 4;
         int occ = kProbeBlocksPerSm;                             // big filters leave room for one block per SM only
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_probe, kProbeBlock, h->probe_smem) != cudaSuccess || occ < 1) occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan, kProbeBlock, h->probe_smem) != cudaSuccess || occ < 1) occ = 1;
         const long long cap = std::max(1, h->n_sm * std::min(occ, kProbeBlocksPerSm));
         long long per = std::max<long long>((R + cap - 1) / cap, 1);
         for (;;) {
@@ -410,6 +438,13 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
             if (total <= cap || per >= R) break;
             per += per / 16 + 1;
         }
+        auto tile_of = [&](long long q0, long long q1, int s) {
+            ScanTile t;
+            std::memset(&t, 0, sizeof(t));
+            t.r0 = q0; t.r1 = q1; t.shard = s; t.base = tab_off[s]; t.mask = tab_mask[s]; t.bmw = bm_wmask[s];
+            t.nm0 = (int)join_off[s]; t.nm1 = (int)join_off[s + 1];
+            return t;
+        };
         for (int s = 0; s < ns; ++s) {
             const long long b0 = h->h_read_off[s], b1 = h->h_read_off[s + 1];
             if (b1 <= b0) continue;
@@ -418,34 +453,58 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
                 long long q0 = b0 + (b1 - b0) * k / pieces, q1 = b0 + (b1 - b0) * (k + 1) / pieces;
                 if (k > 0) q0 += q0 & 1;                         // interior cuts on 16-byte boundaries
                 if (k + 1 < pieces) q1 += q1 & 1;
-                if (q0 < q1) qtiles.push_back(ProbeTile{q0, q1, s, tab_off[s], tab_mask[s], bm_off[s], bm_wmask[s], 0});
+                if (q0 < q1) qtiles.push_back(tile_of(q0, q1, s));
             }
         }
-        if (qtiles.empty()) qtiles.push_back(ProbeTile{0, 0, 0, 0, 0, 0, 31, 0});
+        // no reads at all (or fewer tiles than would keep the device busy inserting): pad with row-less tiles
+        const size_t want = std::min<size_t>((size_t)cap, (size_t)std::max<long long>(1, (J + 2047) / 2048));
+        while (qtiles.size() < want) { ScanTile t = tile_of(0, 0, 0); t.nm0 = t.nm1 = 0; t.bmw = 31; qtiles.push_back(t); }
+        const long long nt = (long long)qtiles.size();
+        for (long long k = 0; k < nt; ++k) {
+            ScanTile &t = qtiles[(size_t)k];
+            const long long i0 = J * k / nt, i1 = J * (k + 1) / nt;
+            t.ins0 = (int)i0; t.ins1 = (int)i1;
+            t.ins_lo = i0 < i1 ? shard_at(join_off, i0) : 0;
+            t.ins_hi = i0 < i1 ? shard_at(join_off, i1 - 1) : 0;
+        }
     }
     h->probe_grid = (int)qtiles.size();
-    a.n_probe_tiles = h->probe_grid;
-    if ((rc = stage(h, h->d_qtiles, qtiles.data(), sizeof(ProbeTile) * qtiles.size(), DUET_MEM_HOST, &dv))) return rc;
-    a.probe_tiles = static_cast<const ProbeTile *>(dv);
-    CU(h, cudaStreamSynchronize(st));          // the descriptor vectors live on this stack frame
-    if ((rc = stage(h, h->d_tab_off, tab_off.data(), sizeof(int) * ns, DUET_MEM_HOST, &dv))) return rc;
-    a.tab_off = static_cast<const int *>(dv);
-    if ((rc = stage(h, h->d_tab_mask, tab_mask.data(), sizeof(int) * ns, DUET_MEM_HOST, &dv))) return rc;
-    a.tab_mask = static_cast<const int *>(dv);
-    if ((rc = stage(h, h->d_bm_off, bm_off.data(), sizeof(int) * ns, DUET_MEM_HOST, &dv))) return rc;
-    a.bm_off = static_cast<const int *>(dv);
-    if ((rc = stage(h, h->d_bm_wmask, bm_wmask.data(), sizeof(int) * ns, DUET_MEM_HOST, &dv))) return rc;
-    a.bm_wmask = static_cast<const int *>(dv);
+    a.n_scan_tiles = h->probe_grid;
+    {
+        Arena ar;
+        const size_t o_read = ar.put(h->h_read_off), o_sv = ar.put(h->h_sv_off), o_join = ar.put(join_off);
+        const size_t o_toff = ar.put(tab_off), o_tmask = ar.put(tab_mask);
+        const size_t o_pt = ar.put(ptiles), o_qt = ar.put(qtiles);
+        if (h->desc_in_flight) CU(h, cudaEventSynchronize(h->ev[EV_DESC]));      // the previous copy out of h_desc is over
+        CU(h, h->h_desc.reserve(ar.bytes.size()));
+        CU(h, h->d_desc.reserve(ar.bytes.size()));
+        std::memcpy(h->h_desc.p, ar.bytes.data(), ar.bytes.size());
+        CU(h, cudaMemcpyAsync(h->d_desc.p, h->h_desc.p, ar.bytes.size(), cudaMemcpyHostToDevice, st));
+        CU(h, cudaEventRecord(h->ev[EV_DESC], st));
+        h->desc_in_flight = true;
+        const unsigned char *d = h->d_desc.as<unsigned char>();
+        a.read_off = reinterpret_cast<const long long *>(d + o_read);
+        a.sv_off = reinterpret_cast<const long long *>(d + o_sv);
+        a.join_off = reinterpret_cast<const long long *>(d + o_join);
+        a.tab_off = reinterpret_cast<const int *>(d + o_toff);
+        a.tab_mask = reinterpret_cast<const int *>(d + o_tmask);
+        a.predict_tiles = reinterpret_cast<const PredictTile *>(d + o_pt);
+        a.scan_tiles = reinterpret_cast<const ScanTile *>(d + o_qt);
+    }
     CU(h, cudaEventRecord(h->ev[EV_H2D1], st));
     h->have_h2d = true;
 
     const size_t S1 = (size_t)std::max<long long>(S, 1), J1 = (size_t)std::max<long long>(J, 1);
-    CU(h, h->d_table.reserve((size_t)slots * sizeof(Slot) + (size_t)bm_words * 4));
+    // The join table and the filter are clean (all-ones / all-zero) between calls: k_reduce restores exactly
+    // what k_table touched.  Only fresh memory has to be initialised.
+    bool grew = false;
+    CU(h, h->d_table.reserve((size_t)std::max<long long>(slots, 1) * sizeof(Slot), &grew));
+    if (grew) CU(h, cudaMemsetAsync(h->d_table.p, 0xFF, h->d_table.cap, st));
     a.tab = h->d_table.as<Slot>();
-    a.bitmap = reinterpret_cast<unsigned *>(a.tab + slots);
-    CU(h, h->d_next.reserve(J1 * 4));                    a.next = h->d_next.as<int>();
     CU(h, h->d_cand_key.reserve((size_t)std::max<long long>(R, 1) * 8)); a.cand_key = h->d_cand_key.as<unsigned long long>();
     CU(h, h->d_cand_row.reserve((size_t)std::max<long long>(R, 1) * 4)); a.cand_row = h->d_cand_row.as<int>();
+    CU(h, h->d_cand_n.reserve((size_t)h->probe_grid * 4));               a.cand_n = h->d_cand_n.as<int>();
+    CU(h, h->d_next.reserve(J1 * 4));                    a.next = h->d_next.as<int>();
     CU(h, h->d_join_row.reserve(J1 * 4 + 16));                a.join_row = h->d_join_row.as<int>();
     CU(h, h->d_n_hit.reserve(S1 * 4));                   a.n_hit = h->d_n_hit.as<int>();
     CU(h, h->d_cand.reserve(S1 * 8));                    a.cand = h->d_cand.as<long long>();
@@ -468,13 +527,12 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     CU(h, h->d_n_emit.reserve((size_t)ns * 4));          a.n_emit = h->d_n_emit.as<int>();
     CU(h, h->d_counts.reserve((size_t)ns * 8 * DUET_N_COUNTERS)); a.shard_counts = h->d_counts.as<long long>();
     CU(h, h->d_status.reserve(sizeof(DevStatus)));       a.status = h->d_status.as<DevStatus>();
-    // state the kernels keep clean between calls: zero counters / credits / status
-    CU(h, cudaMemsetAsync(h->d_join_row.p, 0xFF, J1 * 4, st));
+    // state the kernels keep clean between calls: counters of shards without SVs stay zero, status zero
+    if (J == 0 && S) CU(h, cudaMemsetAsync(h->d_join_row.p, 0xFF, J1 * 4, st));
     CU(h, cudaMemsetAsync(h->d_oneps_n.p, 0, (size_t)ns * 4, st));
     CU(h, cudaMemsetAsync(h->d_n_emit.p, 0, (size_t)ns * 4, st));
     CU(h, cudaMemsetAsync(h->d_counts.p, 0, (size_t)ns * 8 * DUET_N_COUNTERS, st));
     CU(h, cudaMemsetAsync(h->d_status.p, 0, sizeof(DevStatus), st));
-    CU(h, cudaStreamSynchronize(st));          // tab_off / tab_mask host vectors go out of scope
     if (h->dbg_on) {
         CU(h, h->d_dbg.reserve((size_t)4 * kDbgBlocks * kDbgMarks * 2 * 8));
         a.dbg = h->d_dbg.as<long long>();
@@ -483,53 +541,40 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     return DUET_OK;
 }
 
-// The launches of one call, a serial chain on `st`: k_init -> k_table -> k_probe -> k_reduce -> k_oneps ->
-// k_predict -> k_order
-// (with `marks`, an event follows each stage).
-static void launch_all(duet_handle *h, cudaStream_t st, bool marks) {
+// The launches of one call, a serial chain on `st`: k_scan -> k_probe -> k_reduce -> k_tail (or, when a
+// contig has more SVs than a cluster holds, k_oneps -> k_predict -> k_order).  With `marks`, an event
+// follows each stage.
+static int launch_all(duet_handle *h, cudaStream_t st, bool marks) {
     auto mark = [&](int ev) { if (marks) cudaEventRecord(h->ev[ev], st); };
     static const bool no_pdl = std::getenv("DUET_NO_PDL") != nullptr;      // diagnostic switch
     const bool pdl = !marks && !no_pdl;
     const PhaseArgs &a = h->a;
     const int S = a.n_svs;
     const bool join = a.n_joins > 0, probe = a.n_reads && a.n_joins;
-    const int build_blocks = (int)((a.n_joins + kBuildTile - 1) / kBuildTile);
-    if (join) {
-        launch(k_init, h->n_sm * 4, kThreads, 0, st, false, a, h->n_slots, h->n_bm_words, (int)(kInitTable | kInitFilter));
-        mark(EV_K0);
-        launch(k_table, build_blocks, kThreads, 0, st, pdl, a);
-        h->launches += 2;
-        mark(EV_K1);
-        if (probe) {
-            launch(k_probe, h->probe_grid, kProbeBlock, h->probe_smem, st, pdl, a);
-            ++h->launches;
-        }
-    } else {
-        mark(EV_K0);
-        mark(EV_K1);
-    }
-    mark(EV_K2);
+    int n = 0;
+    if (join) { launch(k_scan, h->probe_grid, kProbeBlock, h->probe_smem, st, false, a); ++n; }
+    mark(EV_K0);
+    if (probe) { launch(k_probe, h->probe_grid, kProbeThreads, 0, st, pdl, a); ++n; }
+    mark(EV_K1);
     if (S) {
         const int per = kThreads / h->reduce_lanes;
-        if (h->reduce_lanes == kReduceLanesDense) launch(k_reduce<kReduceLanesDense>, (S + per - 1) / per, kThreads, 0, st, pdl, a);
-        else launch(k_reduce<kReduceLanesSparse>, (S + per - 1) / per, kThreads, 0, st, pdl, a);
-        ++h->launches;
+        if (h->reduce_lanes == kReduceLanesDense) launch(k_reduce<kReduceLanesDense>, (S + per - 1) / per, kThreads, 0, st, pdl && join, a);
+        else launch(k_reduce<kReduceLanesSparse>, (S + per - 1) / per, kThreads, 0, st, pdl && join, a);
+        ++n;
+    }
+    mark(EV_K2);
+    if (S && h->tail_fused) {
+        launch(k_tail, a.n_shards * kTailCluster, kThreads, tail_smem_bytes(h->tail_set, h->tail_vals), st, pdl, a,
+               h->tail_set, h->tail_vals);
+        ++n;
     }
     mark(EV_K3);
-    if (S) {
-        launch(k_oneps, a.n_shards, kThreads, 0, st, pdl, a);
-        ++h->launches;
-    }
+    if (S && !h->tail_fused) { launch(k_oneps, a.n_shards, kThreads, 0, st, pdl, a); ++n; }
     mark(EV_K4);
-    if (S) {
-        launch(k_predict, h->predict_grid, kThreads, 0, st, pdl, a);
-        ++h->launches;
-    }
+    if (S && !h->tail_fused) { launch(k_predict, h->predict_grid, kThreads, 0, st, pdl, a); ++n; }
     mark(EV_K5);
-    if (S) {
-        launch(k_order, a.n_shards, kThreads, 0, st, pdl, a);
-        ++h->launches;
-    }
+    if (S && !h->tail_fused) { launch(k_order, a.n_shards, kThreads, 0, st, pdl, a); ++n; }
+    return n;
 }
 
 int duet_phase_execute(duet_handle *h, int per_kernel) {
@@ -544,21 +589,21 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
     h->per_kernel = per_kernel != 0;
     CU(h, cudaEventRecord(h->ev[EV_X0], st));
     if (h->per_kernel) {
-        launch_all(h, st, true);
+        h->launches += launch_all(h, st, true);
     } else {
         // the launch sequence of a staged batch never changes: replay it as a CUDA graph.  A re-upload
         // of the same shapes lands in the same buffers, so the captured graph stays valid.
-        const int dims[4] = {h->probe_grid, h->reduce_lanes, (int)h->probe_smem, h->predict_grid};
+        const int dims[8] = {h->probe_grid, h->reduce_lanes, (int)h->probe_smem, h->predict_grid,
+                             0, 0, h->tail_fused ? h->tail_set : 0, h->tail_vals};
         if (h->graph_exec && (std::memcmp(&h->graph_args, &h->a, sizeof(PhaseArgs)) != 0 ||
-                              std::memcmp(h->graph_dims, dims, sizeof(dims)) != 0 || !h->graph_valid)) {
+                              std::memcmp(h->graph_dims, dims, sizeof(dims)) != 0)) {
             cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr;
             cudaGraphDestroy(h->graph); h->graph = nullptr;
         }
+        int n_graph = 0;
         if (!h->graph_exec) {
             h->graph_args = h->a;
             std::memcpy(h->graph_dims, dims, sizeof(dims));
-            h->graph_valid = true;
-            const int64_t before = h->launches;
             if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
                 launch_all(h, st, false);
                 if (cudaStreamEndCapture(st, &h->graph) != cudaSuccess ||
@@ -566,17 +611,19 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
                     h->graph_exec = nullptr;
                 }
             }
-            h->launches = before;
             cudaGetLastError();
         }
         if (h->graph_exec) {
             CU(h, cudaGraphLaunch(h->graph_exec, st));
-            h->launches += (h->a.n_joins ? 2 : 0) + (h->a.n_reads && h->a.n_joins ? 1 : 0) + (h->a.n_svs ? 4 : 0);
+            const PhaseArgs &a = h->a;
+            n_graph = (a.n_joins ? 1 : 0) + (a.n_reads && a.n_joins ? 1 : 0) + (a.n_svs ? (h->tail_fused ? 2 : 4) : 0);
+            h->launches += n_graph;
         } else {
-            launch_all(h, st, false);
+            h->launches += launch_all(h, st, false);
         }
     }
     CU(h, cudaEventRecord(h->ev[EV_K6], st));
+    if (h->flags & kFlagNoSlotFree) CU(h, cudaMemsetAsync(h->d_table.p, 0xFF, h->d_table.cap, st));      // diagnostics only
     CU(h, cudaGetLastError());
     h->executed = true;
     return DUET_OK;

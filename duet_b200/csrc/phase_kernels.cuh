@@ -1,28 +1,32 @@
 // sm_100a kernels of the sv_phasing hot path.
 //
 // Reference behaviour restated per kernel (citations: /root/reference/src/duet/sv_phasing_fn.py):
-//   k_init     start-of-call state: EMPTY slot table, zero Bloom filter, join results -1
-//   k_table    the dict-insert side of the JOIN (:26-29 keyed by QNAME) -- here the SMALL side is
-//              inserted: the support-read names of the SVs (:46-48); also sets their Bloom filter bits
-//   k_probe    the haplotagged reads streamed once through the contig's Bloom filter (shared memory);
-//              the block then looks its survivors up in the slot table: a hit records the row index on
-//              every support-read entry of that name with atomicMax == "a later row overwrites an
-//              earlier one" (:29)
+//   k_scan     the dict-insert side of the JOIN (:26-29 keyed by QNAME) -- here the SMALL side is
+//              inserted: the support-read names of the SVs (:46-48) claim slots of the join table -- and,
+//              in the same blocks at the same time, the haplotagged reads are streamed once through the
+//              contig's Bloom filter (built by the block itself, in shared memory, from the contig's
+//              names): the survivors become the candidate list
+//   k_probe    the candidates against the slot table: a hit records the row index on every support-read
+//              entry of that name with atomicMax == "a later row overwrites an earlier one" (:29)
 //   k_reduce   per SV: gather the joined reads' tags, class = #distinct PS (:192-194), one-PS candidate
 //              (:195-203), class-1 counts and score sums (:74-84), per-PS statistics of class-2 SVs in
-//              first-seen order (:85-105)
-//   k_oneps    per contig: its sorted unique one-PS list (:107)
-//   k_predict  per SV: in-set PS with most reads (:99-105), nearest-PS fallback (:106-111), features
-//              (:112-139), the T1-T5 tree (:142-183)
-//   k_order    per contig: emission order (:206-229) and counters
+//              first-seen order (:85-105); hands the join table back clean for the next call
+//   k_tail     one thread-block CLUSTER per contig: its sorted unique one-PS list (:107), then per SV the
+//              in-set PS with most reads (:99-105), nearest-PS fallback (:106-111), features (:112-139),
+//              the T1-T5 tree (:142-183), then the contig's emission order (:206-229) and counters
+//   k_oneps / k_predict / k_order   the same three steps as kernels of their own, for contigs with more
+//              SVs than a cluster holds
 //
-// What bounds these kernels at WGS size is not bandwidth (the whole problem is ~130 MB) but the ~1 us
-// round trip of a dependent global access, L2 atomic throughput and the HBM's random-sector rate.  So
-// every kernel requests everything independent at once and only then consumes it, every block starts
-// from a host-built tile descriptor instead of looking its contig up, random traffic is kept L2
-// resident (sequential init sweep, prefetches), and a joined read costs one 16-byte record.
+// What bounds these kernels at WGS size is not bandwidth (the whole problem is ~130 MB).  Measured on
+// B200 (tools/ubench_atomics.cu): a kernel that does ONE scattered access per element costs ~8 us however
+// few elements it has; an SM issues ~0.5 scattered atomics or ~0.7 scattered loads/stores per clock; a
+// dependent global access under load is a 1-2 us round trip.  So the design minimises (a) dependent round
+// trips per kernel, (b) scattered operations per element (one CAS per name, one slot load per candidate,
+// one 16-byte record per joined read), (c) what sits behind a kernel boundary: everything that does not
+// need the previous kernel's output runs before griddepcontrol.wait, under the predecessor's tail.
 #pragma once
 
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -51,10 +55,15 @@ struct __align__(16) Slot {
 // include/duet_b200.h :: duet_read_tag as the device reads it (one 16-byte load)
 struct __align__(16) ReadTag { int ps, pc; unsigned chk, hp; };       // hp: low byte
 
-// host-built descriptors: what a block needs to know about its tile, in one 32- / 16-byte load
-struct BuildTile { int lo, hi, base, mask, bmo, bmw, pad[2]; };   // shards of 256 consecutive support reads
+// host-built descriptors: what a block needs to know about its tile, in one 64- / 32-byte load
 struct PredictTile { int sv0, sv1, shard, b, n, pad[3]; };        // SVs [sv0, sv1) of ONE shard = SVs [b, b + n)
-struct ProbeTile { long long r0, r1; int shard, base, mask, bmo, bmw, pad; };   // rows [r0, r1) of ONE contig + its table / filter
+struct ScanTile {                   // one block of k_scan / k_probe
+    long long r0, r1;               // rows [r0, r1) of ONE contig: streamed through the filter
+    int shard, base, mask, bmw;     // that contig's slot range (base, mask) and filter size (words - 1)
+    int nm0, nm1;                   // the contig's support-read names: csr_key[nm0, nm1) -> the block's filter
+    int ins0, ins1, ins_lo, ins_hi; // names [ins0, ins1) (any contig: shards ins_lo..ins_hi) this block inserts
+    int pad[2];
+};
 
 constexpr int kC2Max = 8;    // distinct PS per class-2 SV recorded by k_reduce (more -> warp fallback)
 struct C2Ent { int ps, tot, n1, n2; long long s1, s2; int bad, pad; };
@@ -67,19 +76,29 @@ struct DevStatus {          // device -> host error report
 };
 
 // Everything a kernel needs; passed by value.
+// developer switches (environment DUET_FLAGS, read once per handle); 0 in production
+enum {
+    kFlagNoSlotFree = 1,      // k_reduce leaves the claimed slots alone (the host memsets the table after the call)
+    kFlagNoWarm = 2,          // k_probe does not warm L2 with k_reduce's input columns while it waits
+    kFlagFill2 = 16,          // host: load factor <= 1/2 always
+    kFlagSplitTail = 32,      // host: k_oneps / k_predict / k_order instead of k_tail
+};
+
 struct PhaseArgs {
     int n_shards;
     int n_reads, n_svs, n_joins;
+    int flags;
+    long long n_slots;
     // inputs (device)
     const long long *read_off;   // [n_shards+1]
     const long long *sv_off;     // [n_shards+1]
     const long long *join_off;   // [n_shards+1] csr_off at the shard boundaries (derived at upload)
-    const BuildTile *build_tiles;   // [ceil(J / 256)]
     const PredictTile *predict_tiles;   // [sum over shards of ceil(n / kPredictPerBlock)] = k_predict grid
-    const ProbeTile *probe_tiles;   // [n_probe_tiles] = k_probe grid
-    int n_probe_tiles;
+    const ScanTile *scan_tiles;     // [n_scan_tiles] = k_scan / k_probe grid
+    int n_scan_tiles;
     unsigned long long *cand_key;   // [R] rows that passed their contig's filter: tile t appends at [r0(t), ...)
     int *cand_row;                  // [R]
+    int *cand_n;                    // [n_scan_tiles] how many
     const unsigned long long *read_key;
     const ReadTag *read_tag;
     const int *sv_pos, *sv_svlen, *sv_svread, *sv_refread;
@@ -91,12 +110,9 @@ struct PhaseArgs {
     // join table: shard s owns slots [tab_off[s], tab_off[s] + tab_mask[s] + 1)
     const int *tab_off;          // [n_shards]
     const int *tab_mask;         // [n_shards]
-    Slot *tab;                   // [n_slots] set to all-ones at the start of every call
-    int *next;                   // [J] next entry carrying the same name, -1 none
-    // per-shard Bloom filter over the support-read names: words [bm_off[s], bm_off[s] + bm_wmask[s] + 1)
-    const int *bm_off;           // [n_shards]
-    const int *bm_wmask;         // [n_shards] (power of two) - 1
-    unsigned *bitmap;            // zeroed at the start of every call
+    Slot *tab;                   // [n_slots] all-ones (= free) between calls: k_reduce frees what k_table claimed
+    int *next;                   // [J] entry that shares a slot: next entry carrying the same name, -1 none;
+                                 //     entry that CLAIMED a slot: -2 - slot index (what k_reduce frees)
     // per-SV intermediates / outputs (device)
     int *join_row;               // [J] row each support read joined to (atomicMax by k_probe), -1 = miss
     int *n_hit;                  // [S] joined reads of the SV
@@ -238,32 +254,6 @@ __device__ __forceinline__ int next_pow2(int n) {
 }
 
 // ------------------------------------------------------------------------------------------
-// k_init: start-of-call state in one sequential sweep: EMPTY slots (all ones), zero filter words,
-// join results -1.  Sequential 16-byte stores also leave all three L2 resident for the random
-// traffic of k_table / k_probe that follows.
-// ------------------------------------------------------------------------------------------
-enum { kInitTable = 1, kInitFilter = 2 };
-
-__global__ void __launch_bounds__(kThreads)
-k_init(PhaseArgs a, long long n_slots, long long n_bm_words, int what) {
-    pdl_trigger();
-    pdl_wait();
-    const long long stride = (long long)gridDim.x * kThreads;
-    const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
-    const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0u, 0u, 0u, 0u);
-    if (what & kInitTable) {
-        uint4 *tab = reinterpret_cast<uint4 *>(a.tab);
-        for (long long i = t; i < n_slots; i += stride) tab[i] = ones;
-        uint4 *jr = reinterpret_cast<uint4 *>(a.join_row);                   // allocation padded to 16 bytes
-        for (long long i = t; i < ((long long)a.n_joins + 3) / 4; i += stride) jr[i] = ones;
-    }
-    if (what & kInitFilter) {
-        uint4 *bm = reinterpret_cast<uint4 *>(a.bitmap);
-        for (long long i = t; i < n_bm_words / 4; i += stride) bm[i] = zero;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // Bloom filter bit pattern of a key: one 32-bit word, two bits (a probe is one shared-memory load)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned bloom_word(unsigned long long key, unsigned wmask) {
@@ -272,91 +262,6 @@ __device__ __forceinline__ unsigned bloom_word(unsigned long long key, unsigned 
 __device__ __forceinline__ unsigned bloom_bits(unsigned long long key) {
     return (1u << ((unsigned)(key >> 5) & 31u)) | (1u << ((unsigned)(key >> 10) & 31u));
 }
-
-// ------------------------------------------------------------------------------------------
-// The build side: k_table claims a slot per support-read name and sets the name's filter bits.
-// Dependent chain of a k_table thread: [key, tile descriptor] -> CAS (-> CAS on a collision) -> stores.
-// ------------------------------------------------------------------------------------------
-constexpr int kBuildPerThread = 1;
-constexpr int kBuildTile = kThreads * kBuildPerThread;
-
-// which shard (table range, filter range) support-read entry j of this tile belongs to
-__device__ __forceinline__ void build_where(const PhaseArgs &a, const BuildTile &t, long long j, int &base,
-                                            unsigned &mask, int &bmo, unsigned &bmw) {
-    base = t.base; mask = (unsigned)t.mask; bmo = t.bmo; bmw = (unsigned)t.bmw;
-    if (t.lo != t.hi) {                                          // the tile straddles a contig boundary
-        const int s = t.lo + shard_of(a.join_off + t.lo, t.hi - t.lo + 1, j);
-        base = __ldg(a.tab_off + s); mask = (unsigned)__ldg(a.tab_mask + s);
-        bmo = __ldg(a.bm_off + s); bmw = (unsigned)__ldg(a.bm_wmask + s);
-    }
-}
-
-// k_table: claim a slot per name (CAS; both names of a thread in flight together); the first entry of
-// a name owns the slot, further entries chain themselves behind it
-__global__ void __launch_bounds__(kThreads)
-k_table(PhaseArgs a) {
-    dbg_mark(a, 0, 0);
-    const long long j0 = (long long)blockIdx.x * kBuildTile + threadIdx.x;
-    unsigned long long key[kBuildPerThread];
-#pragma unroll
-    for (int u = 0; u < kBuildPerThread; ++u) {
-        const long long j = j0 + u * kThreads;
-        key[u] = j < a.n_joins ? __ldcs(a.csr_key + j) : 0ull;
-    }
-    const BuildTile t = a.build_tiles[blockIdx.x];
-    pdl_trigger();
-    pdl_wait();                                                  // the slots and the filter words are initialised
-    unsigned p[kBuildPerThread], mask[kBuildPerThread];
-    int base[kBuildPerThread];
-    unsigned pend = 0;
-#pragma unroll
-    for (int u = 0; u < kBuildPerThread; ++u) {
-        const long long j = j0 + u * kThreads;
-        if (j >= a.n_joins) continue;
-        int bmo;
-        unsigned bmw;
-        build_where(a, t, j, base[u], mask[u], bmo, bmw);
-        atomicOr(a.bitmap + bmo + (int)bloom_word(key[u], bmw), bloom_bits(key[u]));    // fire and forget
-        p[u] = slot_hash(key[u]) & mask[u];
-        pend |= 1u << u;
-    }
-    while (pend) {
-        unsigned long long prev[kBuildPerThread];
-#pragma unroll
-        for (int u = 0; u < kBuildPerThread; ++u)
-            if (pend >> u & 1u) prev[u] = atomicCAS(&a.tab[base[u] + p[u]].key, kEmptyKey, key[u]);
-#pragma unroll
-        for (int u = 0; u < kBuildPerThread; ++u) {
-            if (!(pend >> u & 1u)) continue;
-            const int j = (int)(j0 + u * kThreads);
-            Slot *sl = a.tab + base[u] + p[u];
-            if (prev[u] == kEmptyKey) { sl->first = j; pend &= ~(1u << u); }
-            else if (prev[u] == key[u]) { a.next[j] = atomicExch(&sl->head, j); pend &= ~(1u << u); }
-            else p[u] = (p[u] + 1) & mask[u];
-        }
-    }
-    dbg_mark(a, 0, 1);
-}
-
-// ------------------------------------------------------------------------------------------
-// k_probe: the haplotagged reads are STREAMED once by one block per tile -- a tile is a row range of ONE
-// contig, sized so that the grid is about two blocks per SM.  A producer warp keeps a ring of 16 KB key
-// tiles in flight with bulk asynchronous copies (TMA, cp.async.bulk + mbarrier complete_tx); the consumer
-// warps take a tile as soon as its barrier flips and hand the stage back through an `empty` barrier --
-// no block-wide synchronisation inside the stream.  The block keeps the contig's Bloom filter in shared
-// memory, so ~90 % of the rows (reads that support no SV) never leave the SM; the survivors are appended
-// to the block's private stretch of the candidate list, and when the stream is done the whole block
-// resolves them against the slot table, a few candidates per thread in flight together.
-// ------------------------------------------------------------------------------------------
-constexpr int kProbeThreads = 512;                               // consumer threads
-constexpr int kProbeBlock = kProbeThreads + 32;                  // + one producer warp that only issues copies
-constexpr int kProbeBlocksPerSm = 2;
-constexpr int kProbeUnroll = 2;                                  // 16-byte pairs per thread per tile
-constexpr int kProbeRows = 2 * kProbeUnroll;                     // rows per thread per tile
-constexpr int kProbeBatch = kProbeThreads * kProbeUnroll;        // pairs per tile (16 KB)
-constexpr int kProbeStages = 3;                                  // tiles in flight per block
-constexpr int kProbeRingBytes = kProbeStages * kProbeBatch * 16;
-constexpr int kResolveUnroll = 4;                                // candidates per thread in flight in the drain
 
 // ---- mbarrier / bulk-copy (TMA) primitives ------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -383,13 +288,44 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned b
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------
+// k_scan: one block per tile -- a row range of ONE contig, sized so that the grid is about two blocks per
+// SM, all resident.  Nothing here depends on another kernel, and three things run side by side:
+//   * every consumer thread CLAIMS SLOTS for its share of the call's support-read names (one CAS per name,
+//     linear probing; all of a thread's names in flight together).  The first entry of a name owns the
+//     slot, later entries chain themselves behind it.  The table cleans itself: all slots are free
+//     (all-ones) BETWEEN calls; the entry that claims a slot leaves the slot's index in next[] (-2 - index)
+//     and k_reduce, which walks every entry anyway once the probe is over, frees exactly those slots.  A
+//     call therefore never sweeps the table (6x larger than what it touches).
+//   * the block builds its contig's Bloom filter in SHARED memory straight from the contig's names
+//     (16 bits per name, two bits per key, <= 64 KB): no global filter, no atomics on it, no copy;
+//   * the haplotagged reads are STREAMED once: a producer warp keeps a ring of 16 KB key tiles in flight
+//     with bulk asynchronous copies (TMA, cp.async.bulk + mbarrier complete_tx); the consumer warps take a
+//     tile as soon as its barrier flips and hand the stage back through an `empty` barrier -- no block-wide
+//     synchronisation inside the stream.  ~90 % of the rows (reads that support no SV) never leave the SM;
+//     the survivors are appended to the block's private stretch of the candidate list.
+// The table lookups of the candidates need EVERY block's names in place: they are k_probe, behind the
+// kernel boundary.
+// ------------------------------------------------------------------------------------------
+constexpr int kProbeThreads = 512;                               // consumer threads
+constexpr int kProbeBlock = kProbeThreads + 32;                  // + one producer warp that only issues copies
+constexpr int kProbeBlocksPerSm = 2;
+constexpr int kProbeUnroll = 2;                                  // 16-byte pairs per thread per tile
+constexpr int kProbeRows = 2 * kProbeUnroll;                     // rows per thread per tile
+constexpr int kProbeBatch = kProbeThreads * kProbeUnroll;        // pairs per tile (16 KB)
+constexpr int kProbeStages = 3;                                  // tiles in flight per block
+constexpr int kProbeRingBytes = kProbeStages * kProbeBatch * 16;
+constexpr int kInsertUnroll = 4;                                 // names per thread in flight
+constexpr int kFilterUnroll = 8;                                 // names per thread requested together for the filter
+constexpr int kResolveUnroll = 4;                                // candidates per thread in flight (k_probe)
+
 __global__ void __launch_bounds__(kProbeBlock, kProbeBlocksPerSm)
-k_probe(PhaseArgs a) {
+k_scan(PhaseArgs a) {
     extern __shared__ __align__(128) unsigned char s_raw[];      // [key ring | filter words]
     __shared__ __align__(8) unsigned long long s_full[kProbeStages], s_empty[kProbeStages];
     __shared__ int s_count;
-    dbg_mark(a, 1, 0);
-    const ProbeTile tile = a.probe_tiles[blockIdx.x];            // one contig, one row range, everything needed
+    dbg_mark(a, 0, 0);
+    const ScanTile tile = a.scan_tiles[blockIdx.x];              // one contig, one row range, everything needed
     ulonglong2 *ring = reinterpret_cast<ulonglong2 *>(s_raw);
     unsigned *s_bm = reinterpret_cast<unsigned *>(s_raw + kProbeRingBytes);
     const long long R = a.n_reads;
@@ -407,21 +343,108 @@ k_probe(PhaseArgs a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_count = 0;
     }
+    for (int i = threadIdx.x; i < (int)(bmw + 1) / 4; i += kProbeBlock)
+        reinterpret_cast<uint4 *>(s_bm)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    if (threadIdx.x == 0) {                                      // fill the ring: the stream starts before the filter is in
-        for (int t = 0; t < min(n_tiles, kProbeStages); ++t) {
+    if (threadIdx.x == 0) {                                      // fill the ring: the stream is on its way while the
+        for (int t = 0; t < min(n_tiles, kProbeStages); ++t) {   // names are being inserted and the filter built
             const unsigned bytes = tile_pairs(t) * 16u;
             mbar_expect_tx(&s_full[t], bytes);
             if (bytes) bulk_load(ring + (size_t)t * kProbeBatch, pairs + q0 + (long long)t * kProbeBatch, bytes, &s_full[t]);
         }
     }
-    pdl_trigger();
-    pdl_wait();                                                  // k_table is done: filter bits and slots are final
-    const uint4 *src = reinterpret_cast<const uint4 *>(a.bitmap + tile.bmo);
-    for (int i = threadIdx.x; i < (int)(bmw + 1) / 4; i += kProbeBlock)
-        reinterpret_cast<uint4 *>(s_bm)[i] = src[i];
+    pdl_trigger();                                               // k_probe's blocks may take their places and wait
+    // ---- this block's share of the names: claim a slot each.  The first batch's CAS round trip runs under
+    // the filter build; its results are looked at afterwards ----
+    const bool consumer = threadIdx.x < kProbeThreads;
+    unsigned long long ikey[kInsertUnroll], iprev[kInsertUnroll];
+    unsigned ip[kInsertUnroll], imask[kInsertUnroll];
+    int ibase[kInsertUnroll];
+    unsigned ipend = 0;
+    if (consumer) {
+        const int jb = tile.ins0 + (int)threadIdx.x;
+#pragma unroll
+        for (int u = 0; u < kInsertUnroll; ++u) {
+            const int j = jb + u * kProbeThreads;
+            ikey[u] = j < tile.ins1 ? __ldcs(a.csr_key + j) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < kInsertUnroll; ++u) {
+            const int j = jb + u * kProbeThreads;
+            if (j >= tile.ins1) continue;
+            int sh = tile.ins_lo;
+            if (tile.ins_lo != tile.ins_hi) sh += shard_of(a.join_off + tile.ins_lo, tile.ins_hi - tile.ins_lo + 1, j);
+            ibase[u] = __ldg(a.tab_off + sh); imask[u] = (unsigned)__ldg(a.tab_mask + sh);
+            a.join_row[j] = -1;                                  // "miss" until a row of k_probe says otherwise
+            ip[u] = slot_hash(ikey[u]) & imask[u];
+            ipend |= 1u << u;
+        }
+#pragma unroll
+        for (int u = 0; u < kInsertUnroll; ++u)
+            if (ipend >> u & 1u) iprev[u] = atomicCAS(&a.tab[ibase[u] + ip[u]].key, kEmptyKey, ikey[u]);
+    }
+    dbg_mark(a, 0, 1);
+    // ---- the contig's filter, in shared memory, from the contig's names (all 17 warps; kFilterUnroll keys
+    // per thread requested together) ----
+    for (int j0 = tile.nm0 + (int)threadIdx.x; j0 < tile.nm1; j0 += kProbeBlock * kFilterUnroll) {
+        unsigned long long k[kFilterUnroll];
+#pragma unroll
+        for (int u = 0; u < kFilterUnroll; ++u) {
+            const int j = j0 + u * kProbeBlock;
+            k[u] = j < tile.nm1 ? __ldg(a.csr_key + j) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < kFilterUnroll; ++u)
+            if (j0 + u * kProbeBlock < tile.nm1) atomicOr(s_bm + bloom_word(k[u], bmw), bloom_bits(k[u]));
+    }
+    dbg_mark(a, 0, 2);
+    // ---- the claims: first batch's answers, then any further batches (dense callsets) ----
+    if (consumer) {
+        for (int jb = tile.ins0 + (int)threadIdx.x;;) {
+            bool fresh = false;                                  // ipend's CAS of this round already issued above
+            while (ipend) {
+                if (fresh) {
+#pragma unroll
+                    for (int u = 0; u < kInsertUnroll; ++u)
+                        if (ipend >> u & 1u) iprev[u] = atomicCAS(&a.tab[ibase[u] + ip[u]].key, kEmptyKey, ikey[u]);
+                }
+                fresh = true;
+#pragma unroll
+                for (int u = 0; u < kInsertUnroll; ++u) {
+                    if (!(ipend >> u & 1u)) continue;
+                    const int j = jb + u * kProbeThreads;
+                    Slot *sl = a.tab + ibase[u] + ip[u];
+                    if (iprev[u] == kEmptyKey) { sl->first = j; a.next[j] = -2 - (ibase[u] + (int)ip[u]); ipend &= ~(1u << u); }
+                    else if (iprev[u] == ikey[u]) { a.next[j] = atomicExch(&sl->head, j); ipend &= ~(1u << u); }
+                    else ip[u] = (ip[u] + 1) & imask[u];
+                }
+            }
+            jb += kProbeThreads * kInsertUnroll;
+            if (jb >= tile.ins1) break;
+#pragma unroll
+            for (int u = 0; u < kInsertUnroll; ++u) {
+                const int j = jb + u * kProbeThreads;
+                ikey[u] = j < tile.ins1 ? __ldcs(a.csr_key + j) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < kInsertUnroll; ++u) {
+                const int j = jb + u * kProbeThreads;
+                if (j >= tile.ins1) continue;
+                int sh = tile.ins_lo;
+                if (tile.ins_lo != tile.ins_hi) sh += shard_of(a.join_off + tile.ins_lo, tile.ins_hi - tile.ins_lo + 1, j);
+                ibase[u] = __ldg(a.tab_off + sh); imask[u] = (unsigned)__ldg(a.tab_mask + sh);
+                a.join_row[j] = -1;
+                ip[u] = slot_hash(ikey[u]) & imask[u];
+                ipend |= 1u << u;
+            }
+#pragma unroll
+            for (int u = 0; u < kInsertUnroll; ++u)
+                if (ipend >> u & 1u) iprev[u] = atomicCAS(&a.tab[ibase[u] + ip[u]].key, kEmptyKey, ikey[u]);
+        }
+    }
+    dbg_mark(a, 0, 3);
     __syncthreads();
-    dbg_mark(a, 1, 1);
+    dbg_mark(a, 0, 4);
     if (threadIdx.x >= kProbeThreads) {
         // producer warp: refill a stage as soon as every consumer warp has handed it back.  The wait is
         // warp-uniform (all 32 lanes spin together), one lane issues the copy.
@@ -435,9 +458,15 @@ k_probe(PhaseArgs a) {
             }
             __syncwarp();
         }
-    } else {
+        return;
+    }
+    // consumer warps.  Rows are numbered inside the tile: local row lr <-> row 2*q0 + lr, valid in [lr0, lr1).
+    const int row_base = (int)(2 * q0);
+    const int lr0 = (int)(r0 - 2 * q0), lr1 = (int)(r1 - 2 * q0);
     unsigned long long *out_key = a.cand_key + r0;               // this block's private stretch of the list
     int *out_row = a.cand_row + r0;
+    const Slot *tab = a.tab + tile.base;
+    const unsigned mask = (unsigned)tile.mask;
     for (int t = 0; t < n_tiles; ++t) {
         const int stage = t % kProbeStages;
         const unsigned parity = (unsigned)(t / kProbeStages) & 1u;
@@ -452,12 +481,13 @@ k_probe(PhaseArgs a) {
             else if (qq < q1) v.x = __ldcs(a.read_key + 2 * qq);                       // the column's odd last row
             key[2 * u] = v.x; key[2 * u + 1] = v.y;
         }
+        const int lr_t = 2 * (t * kProbeBatch + (int)threadIdx.x);                    // local row of key[0]
         unsigned pass = 0;
 #pragma unroll
         for (int u = 0; u < kProbeRows; ++u) {
-            const long long row = 2 * (qt + (long long)(u >> 1) * kProbeThreads + threadIdx.x) + (u & 1);
+            const int lr = lr_t + (u >> 1) * (2 * kProbeThreads) + (u & 1);
             const unsigned m = bloom_bits(key[u]);
-            if (row >= r0 && row < r1 && (s_bm[bloom_word(key[u], bmw)] & m) == m) pass |= 1u << u;
+            if (lr >= lr0 && lr < lr1 && (s_bm[bloom_word(key[u], bmw)] & m) == m) pass |= 1u << u;
         }
         // rows that passed the filter go to the candidate list: one shared-memory atomic per warp
         const int cnt = __popc(pass);
@@ -469,9 +499,8 @@ k_probe(PhaseArgs a) {
         }
         // Hand the stage back only HERE: the scan has consumed every lane's filter result, so every lane's
         // ring loads have returned their data.  An arrive placed right after the loads is issued while they
-        // are still in flight (nothing waits on their scoreboard); with another kernel's atomics backing up
-        // the load/store unit on the same SM the refill then overtook them (measured: a warp read the tile
-        // three ahead, lost joins).
+        // are still in flight (nothing waits on their scoreboard) and the refill can overtake them
+        // (measured in round 1: a warp read the tile three ahead, lost joins).
         if (lane == 0) mbar_arrive(&s_empty[stage]);
         int wbase = 0;
         if (lane == 31 && inc) wbase = atomicAdd(&s_count, inc);
@@ -479,31 +508,64 @@ k_probe(PhaseArgs a) {
 #pragma unroll
         for (int u = 0; u < kProbeRows; ++u)
             if (pass >> u & 1u) {
+                const int row = row_base + lr_t + (u >> 1) * (2 * kProbeThreads) + (u & 1);
                 out_key[pos] = key[u];
-                out_row[pos] = (int)(2 * (qt + (long long)(u >> 1) * kProbeThreads + threadIdx.x) + (u & 1));
+                out_row[pos] = row;
                 ++pos;
+                // what k_probe and k_reduce will want from HBM at random -- the candidate's slot and the row's
+                // tag record -- starts moving into L2 now, under the stream
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(tab + (slot_hash(key[u]) & mask)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.read_tag + row));
             }
     }
+    asm volatile("bar.sync 1, %0;" ::"n"(kProbeThreads) : "memory");      // the consumer warps (the producer has left)
+    if (threadIdx.x == 0) a.cand_n[blockIdx.x] = s_count;
+    dbg_mark(a, 0, 5);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_probe: block t resolves the candidates tile t of k_scan left behind, kResolveUnroll per thread in
+// flight: one 16-byte slot load decides (lock-step rounds on collisions); a hit pushes the row index to
+// every support-read entry of that name with atomicMax -- a later row overrides an earlier one
+// (sv_phasing_fn.py:29).  Slots and tag records were requested into L2 by k_scan when the candidate was found.
+// While it waits for k_scan its blocks warm L2 with the input columns k_reduce and k_tail start from
+// (nobody has touched them yet in this call).
+// Dependent chain after the wait: [count] -> candidate (L2, written by k_scan) -> slot -> atomics.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warm_l2(const void *p, size_t bytes, long long tid, long long n_threads) {
+    const char *c = reinterpret_cast<const char *>(p);
+    const long long lines = (long long)((bytes + 127) >> 7);
+    for (long long i = tid; i < lines; i += n_threads) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + (i << 7)));
+}
+
+__global__ void __launch_bounds__(kProbeThreads)
+k_probe(PhaseArgs a) {
+    dbg_mark(a, 1, 0);
+    const ScanTile tile = a.scan_tiles[blockIdx.x];
+    if (!(a.flags & kFlagNoWarm)) {
+        const long long tid = (long long)blockIdx.x * kProbeThreads + threadIdx.x, nt = (long long)gridDim.x * kProbeThreads;
+        const size_t S = (size_t)a.n_svs, J = (size_t)a.n_joins;
+        warm_l2(a.csr_off, (S + 1) * 8, tid, nt);
+        if (a.csr_chk) warm_l2(a.csr_chk, J * 4, tid, nt);
+        warm_l2(a.sv_svlen, S * 4, tid, nt); warm_l2(a.sv_svread, S * 4, tid, nt); warm_l2(a.sv_flags, S, tid, nt);
+        warm_l2(a.sv_pos, S * 4, tid, nt); warm_l2(a.sv_refread, S * 4, tid, nt);
+        if (a.sv_group) warm_l2(a.sv_group, S * 4, tid, nt);
     }
-    __syncthreads();
-    dbg_mark(a, 1, 2);
-    // Resolve the block's candidates (all 17 warps): one 16-byte slot load decides; a hit pushes the row
-    // index to every support-read entry of that name with atomicMax -- a later row overrides an earlier
-    // one (sv_phasing_fn.py:29) -- and starts pulling the row's tag record into L2 for k_reduce.
-    // Dependent chain: candidate (L2, written by this block) -> slot -> [chain of duplicate entries].
-    const int total = s_count;
-    const unsigned long long *q_key = a.cand_key + r0;
-    const int *q_row = a.cand_row + r0;
-    const int base = tile.base;
+    pdl_trigger();
+    pdl_wait();                                                  // k_scan is done: every name has its slot, the lists are final
+    const int total = __ldcg(a.cand_n + blockIdx.x);
+    const unsigned long long *q_key = a.cand_key + tile.r0;
+    const int *q_row = a.cand_row + tile.r0;
+    const Slot *tab = a.tab + tile.base;
     const unsigned mask = (unsigned)tile.mask;
-    for (int g0 = threadIdx.x; g0 < total; g0 += kProbeBlock * kResolveUnroll) {
+    for (int g0 = threadIdx.x; g0 < total; g0 += kProbeThreads * kResolveUnroll) {
         unsigned long long key[kResolveUnroll];
         int row[kResolveUnroll];
         unsigned p[kResolveUnroll];
         unsigned pend = 0;
 #pragma unroll
         for (int u = 0; u < kResolveUnroll; ++u) {
-            const int g = g0 + u * kProbeBlock;
+            const int g = g0 + u * kProbeThreads;
             key[u] = 0ull; row[u] = 0;
             if (g < total) { key[u] = __ldcg(q_key + g); row[u] = __ldcg(q_row + g); pend |= 1u << u; }
         }
@@ -513,29 +575,28 @@ k_probe(PhaseArgs a) {
             uint4 sl[kResolveUnroll];
 #pragma unroll
             for (int u = 0; u < kResolveUnroll; ++u)
-                if (pend >> u & 1u) sl[u] = __ldcg(reinterpret_cast<const uint4 *>(a.tab + base + p[u]));     // key, first, head
+                if (pend >> u & 1u) sl[u] = __ldcg(reinterpret_cast<const uint4 *>(tab + p[u]));     // key, first, head
 #pragma unroll
             for (int u = 0; u < kResolveUnroll; ++u) {
                 if (!(pend >> u & 1u)) continue;
                 const unsigned long long k = ((unsigned long long)sl[u].y << 32) | sl[u].x;
                 if (k == key[u]) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.read_tag + row[u]));     // k_reduce needs it next
                     atomicMax(a.join_row + (int)sl[u].z, row[u]);
                     for (int h = (int)sl[u].w; h >= 0; h = __ldcg(a.next + h)) atomicMax(a.join_row + h, row[u]);
                     pend &= ~(1u << u);
                 } else if (k == kEmptyKey) {
-                    pend &= ~(1u << u);
+                    pend &= ~(1u << u);                          // filter false positive
                 } else {
                     p[u] = (p[u] + 1) & mask;
                 }
             }
         }
     }
-    dbg_mark(a, 1, 3);
+    dbg_mark(a, 1, 1);
 }
 
 // ------------------------------------------------------------------------------------------
-// one-PS list of a shard (called by the block that finished the shard in k_reduce).
+// one-PS list of a shard, as a block of its own (k_oneps: contigs too large for k_tail's cluster).
 // Thread t owns the contiguous chunk [t*per, (t+1)*per) of the shard's candidates; shards of up to
 // kThreads*kStage SVs keep the chunk in registers so the list is read from L2 exactly once.
 // ------------------------------------------------------------------------------------------
@@ -762,12 +823,17 @@ k_reduce(PhaseArgs a) {
     int row[kReduceUnroll], ps[kReduceUnroll], pc[kReduceUnroll], hp[kReduceUnroll];
     for (long long base = b; base < e; base += G * kReduceUnroll) {
         unsigned want[kReduceUnroll];
+        int own[kReduceUnroll];
 #pragma unroll
         for (int u = 0; u < kReduceUnroll; ++u) {
             const long long j = base + u * G + lane;
-            row[u] = j < e ? a.join_row[j] : -1;
+            row[u] = j < e ? __ldcg(a.join_row + j) : -1;
             want[u] = j < e && a.csr_chk ? __ldg(a.csr_chk + j) : 0u;
+            own[u] = j < e ? __ldcg(a.next + j) : 0;
         }
+#pragma unroll
+        for (int u = 0; u < kReduceUnroll; ++u)                  // entries that claimed a slot hand it back free
+            if (own[u] <= -2 && !(a.flags & kFlagNoSlotFree)) reinterpret_cast<uint4 *>(a.tab)[-2 - own[u]] = make_uint4(~0u, ~0u, ~0u, ~0u);
 #pragma unroll
         for (int u = 0; u < kReduceUnroll; ++u) {
             ps[u] = pc[u] = hp[u] = 0;
@@ -828,7 +894,7 @@ k_reduce(PhaseArgs a) {
 #pragma unroll
                 for (int u = 0; u < kReduceUnroll; ++u) {
                     const long long j = base + u * G + lane;
-                    row[u] = j < e ? a.join_row[j] : -1;
+                    row[u] = j < e ? __ldcg(a.join_row + j) : -1;
                 }
 #pragma unroll
                 for (int u = 0; u < kReduceUnroll; ++u) {
@@ -896,7 +962,7 @@ __device__ __forceinline__ Entry load_entry(const PhaseArgs &a, long long j, lon
                                             const int *__restrict__ oneps, int n_one) {
     Entry r{false, false, 0, 0, 0};
     if (j < e) {
-        const int row = a.join_row[j];
+        const int row = __ldcg(a.join_row + j);
         if (row >= 0) {
             const ReadTag t = load_tag(a, row);
             r.pc = t.pc;
@@ -969,7 +1035,7 @@ __device__ void class2_stats(const PhaseArgs &a, int sv, long long b, long long 
 #pragma unroll
             for (int k = 0; k < kBatch; ++k) {
                 const long long j = base + k * 32 + lane;
-                b_row[k] = j < e ? a.join_row[j] : -1;
+                b_row[k] = j < e ? __ldcg(a.join_row + j) : -1;
             }
 #pragma unroll
             for (int k = 0; k < kBatch; ++k) {
@@ -1038,15 +1104,28 @@ __device__ void class2_stats(const PhaseArgs &a, int sv, long long b, long long 
 }
 
 // features (:112-132) and the T1-T5 tree (:142-183) of one SV; one thread
-__device__ void decide_and_store(const PhaseArgs &a, int sv, int cls, Class2Stats st, const int *oneps, int n_one,
-                                 int n_list) {
+struct Decision {
+    int pred;                                  // 0 dropped, 1 "1|0", 2 "0|1", 3 "1|1"
+    bool valid;                                // false: the reference raises here (reported), nothing is stored
+    Class2Stats st;                            // with the phase set the row carries
+    double f[DUET_N_FEATURES];
+};
+
+__device__ __forceinline__ Decision decide(const PhaseArgs &a, int sv, int cls, Class2Stats st, const int *oneps, int n_one,
+                                           int n_list) {
+    Decision d;
+    d.pred = 0; d.valid = false;
     const int pos = __ldg(a.sv_pos + sv);
     if (cls == 0 || (st.h1 == 0 && st.h2 == 0)) st.ps = nearest_ps(oneps, n_one, pos);     // :106-111
+    d.st = st;
+#pragma unroll
+    for (int k = 0; k < DUET_N_FEATURES; ++k) d.f[k] = 0.0;
     const int svread = __ldg(a.sv_svread + sv), refread = __ldg(a.sv_refread + sv);
     if ((long long)svread + refread == 0 || n_list == 0) {
         report(a.status, DUET_ERR_ZERO_DIVISION, sv, 0);
-        return;
+        return d;
     }
+    d.valid = true;
     // Python int/int true division == correctly rounded fp64 division of the exact operands
     const double hapread_ratio = (double)st.allhap / (double)n_list;
     const double a1 = st.h1 > 0 ? (double)st.t1 / (double)st.h1 : 0.0;
@@ -1080,21 +1159,31 @@ __device__ void decide_and_store(const PhaseArgs &a, int sv, int cls, Class2Stat
             else pred = 3;
         }
     }
-    a.gt[sv] = (uint8_t)pred;
-    a.ps[sv] = st.ps;
-    a.hap1[sv] = st.h1; a.hap2[sv] = st.h2; a.hap0[sv] = st.hap0; a.allhap[sv] = st.allhap;
-    a.totsc1[sv] = st.t1; a.totsc2[sv] = st.t2;
+    d.pred = pred;
+    d.f[0] = hapread_ratio; d.f[1] = sv_ratio; d.f[2] = a1; d.f[3] = a2; d.f[4] = totsc_ratio; d.f[5] = avgsc_diff;
+    return d;
+}
+
+__device__ __forceinline__ void store_decision(const PhaseArgs &a, int sv, const Decision &d) {
+    if (!d.valid) return;
+    a.gt[sv] = (uint8_t)d.pred;
+    a.ps[sv] = d.st.ps;
+    a.hap1[sv] = d.st.h1; a.hap2[sv] = d.st.h2; a.hap0[sv] = d.st.hap0; a.allhap[sv] = d.st.allhap;
+    a.totsc1[sv] = d.st.t1; a.totsc2[sv] = d.st.t2;
     const size_t S = (size_t)a.n_svs;
-    a.features[0 * S + sv] = hapread_ratio;
-    a.features[1 * S + sv] = sv_ratio;
-    a.features[2 * S + sv] = a1;
-    a.features[3 * S + sv] = a2;
-    a.features[4 * S + sv] = totsc_ratio;
-    a.features[5 * S + sv] = avgsc_diff;
+#pragma unroll
+    for (int k = 0; k < DUET_N_FEATURES; ++k) a.features[k * S + sv] = d.f[k];
+}
+
+__device__ int decide_and_store(const PhaseArgs &a, int sv, int cls, Class2Stats st, const int *oneps, int n_one,
+                                int n_list) {
+    const Decision d = decide(a, sv, cls, st, oneps, n_one, n_list);
+    store_decision(a, sv, d);
+    return d.pred;
 }
 
 // ------------------------------------------------------------------------------------------
-// emission order + counters of a shard (called by the block that finished the shard in k_predict)
+// emission order + counters of a shard (k_order, and k_tail's block 0 when the VCF was not sorted)
 // ------------------------------------------------------------------------------------------
 typedef unsigned __int128 u128;
 
@@ -1270,7 +1359,6 @@ __device__ __forceinline__ void order_block(const PhaseArgs &a, int s, long long
 //     on chip); class-2 SVs read the per-PS statistics k_reduce recorded and keep the first-seen
 //     in-set phase set with the most reads (:99-105); then features and the T1-T5 tree;
 //   * SVs whose reads span more than kC2Max phase sets fall back to a warp-cooperative exact path;
-//   * every SV credits its shard; the block completing a shard writes its emission order + counters.
 // Dependent chain: [tile, per-SV state] -> [oneps_n, staged list, class-2 record] -> decide -> stores.
 // ------------------------------------------------------------------------------------------
 constexpr int kOneSmem = 2048;
@@ -1358,6 +1446,308 @@ k_order(PhaseArgs a) {
     pdl_wait();
     const int s = blockIdx.x;
     if (a.sv_off[s + 1] > a.sv_off[s]) order_block(a, s, s_tile);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_tail: ONE thread-block CLUSTER per contig does the three per-contig steps that follow k_reduce --
+// the sorted unique one-PS list (:107, :195-203), the per-SV decision (:85-183) and the emission order
+// with the counters (:206-229) -- in one launch.
+//   1. EVERY block reads the whole contig's candidates (a few thousand values out of L2) into a hash set
+//      in its own shared memory and sorts the distinct values (they are distinct: rank = place) -- the
+//      contig-wide dependency "every SV's candidate before any decision" costs no exchange at all;
+//   2. each block decides its slice's SVs against its copy of the list, keeping the results in registers;
+//   3. each block publishes how many of its SVs were emitted, whether they came out in order, their
+//      smallest / largest sort key and its counters -- cluster barrier -- and reads the other blocks'
+//      summaries through distributed shared memory, one lane per block: now it knows its offset in the
+//      contig's emission order and whether the contig was in order all the way (the normal case: a
+//      compaction; if not, block 0 sorts);
+//   4. only then do the per-SV results go out: no store is in flight when the barrier's release runs.
+// Host side: used when every contig of the call has at most kTailMaxSvs SVs (any real callset); larger
+// contigs take k_oneps / k_predict / k_order.
+// ------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+constexpr int kTailCluster = 8;
+constexpr int kTailPer = 2;                                      // SVs per thread
+constexpr int kTailSlice = kThreads * kTailPer;                  // SVs per block
+constexpr int kTailMaxSvs = kTailCluster * kTailSlice;           // SVs per contig
+constexpr int kTailLoads = kTailMaxSvs / kThreads;               // candidates per thread (whole contig)
+constexpr int kTailMinSet = 4096;                                // slots: the set's storage doubles as the 16 KB sort tile
+
+struct TailPub {                                                 // what a block shows its cluster
+    int n_emit, sorted;
+    long long mn, mx;                                            // smallest / largest sort key among the emitted SVs
+    unsigned long long cnt[DUET_N_COUNTERS];
+};
+
+__device__ __forceinline__ void set_insert(int *set, unsigned mask, int shift, int x) {
+    unsigned h = ((unsigned)x * 2654435761u) >> shift;
+    for (;;) {                                                   // never full: at most half the slots are ever taken
+        const int prev = atomicCAS(set + h, INT32_MIN, x);
+        if (prev == INT32_MIN || prev == x) return;
+        h = (h + 1) & mask;
+    }
+}
+
+// the values held by a hash set -> a dense list (in no particular order); returns how many (block-wide; ends
+// with a barrier).  Thread t looks at slots t, t + kThreads, ...: consecutive lanes, consecutive banks.
+__device__ int set_compact(const int *set, int n_set, int *dst) {
+    int cnt = 0;
+    for (int i = threadIdx.x; i < n_set; i += kThreads) cnt += set[i] != INT32_MIN;
+    int total;
+    int w = block_scan_exclusive(cnt, 0, OpSum(), &total);
+    for (int i = threadIdx.x; i < n_set; i += kThreads) { const int v = set[i]; if (v != INT32_MIN) dst[w++] = v; }
+    __syncthreads();
+    return total;
+}
+
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
+
+__global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(kThreads)
+k_tail(PhaseArgs a, int n_set, int n_vals) {
+    extern __shared__ __align__(16) int s_dyn[];                 // [hash set, later the sorted list | distinct values]
+    __shared__ TailPub s_pub;
+    __shared__ Class2Smem s_c2[kThreads / 32];
+    __shared__ int s_fb[kTailSlice];
+    __shared__ int s_nfb, s_has_min, s_base, s_all_sorted;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int s = (int)(blockIdx.x / kTailCluster);
+    int *s_set = s_dyn, *s_vals = s_dyn + n_set;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    dbg_mark(a, 3, 0);
+    const int b = (int)a.sv_off[s], n = (int)a.sv_off[s + 1] - b;
+    if (n == 0) return;                                          // the whole cluster leaves, before any barrier
+    const int per8 = (n + kTailCluster - 1) / kTailCluster;      // this block's slice of the contig ...
+    const int per = (per8 + kThreads - 1) / kThreads;            // ... and this thread's chunk of it: <= kTailPer
+    const int e_r = min(n, (rank + 1) * per8);
+    const int c0 = min(e_r, rank * per8 + (int)threadIdx.x * per), c1 = min(e_r, c0 + per);
+    int pos[kTailPer], grp[kTailPer], n_list[kTailPer];
+#pragma unroll
+    for (int u = 0; u < kTailPer; ++u) {                         // inputs: requested before the wait
+        const bool live = c0 + u < c1;
+        const int sv = b + c0 + u;
+        pos[u] = live ? __ldg(a.sv_pos + sv) : 0;
+        grp[u] = live && a.sv_group ? __ldg(a.sv_group + sv) : 0;
+        n_list[u] = live ? (int)(__ldg(a.csr_off + sv + 1) - __ldg(a.csr_off + sv)) : 0;
+    }
+    for (int i = threadIdx.x; i < n_set; i += kThreads) s_set[i] = INT32_MIN;
+    if (threadIdx.x == 0) {
+        s_pub.n_emit = 0; s_pub.sorted = 1; s_pub.mn = INT64_MAX; s_pub.mx = kNone;
+        for (int k = 0; k < DUET_N_COUNTERS; ++k) s_pub.cnt[k] = 0ull;
+        s_nfb = 0; s_has_min = 0;
+    }
+    pdl_trigger();
+    pdl_wait();                                                  // k_reduce's per-SV results are final
+    long long cv[kTailLoads];
+#pragma unroll
+    for (int u = 0; u < kTailLoads; ++u) {                       // the whole contig's candidates (coalesced, L2) ...
+        const int i = threadIdx.x + u * kThreads;
+        cv[u] = i < n ? __ldcg(a.cand + b + i) : kNoCand;
+    }
+    int cls[kTailPer], nh[kTailPer];
+    Class2Stats st[kTailPer];
+#pragma unroll
+    for (int u = 0; u < kTailPer; ++u) {                         // ... and what k_reduce left for this thread's SVs
+        const bool live = c0 + u < c1;
+        const int sv = b + c0 + u;
+        cls[u] = live ? (int)__ldcg(a.cls + sv) : DUET_CLS_FILTERED;
+        nh[u] = live ? __ldcg(a.n_hit + sv) : 0;
+        st[u] = Class2Stats{0, 0, 0, 0, 0, 0, 0};
+        if (live) st[u] = Class2Stats{__ldcg(a.hap1 + sv), __ldcg(a.hap2 + sv), 0, __ldcg(a.allhap + sv), __ldcg(a.ps + sv),
+                                      __ldcg(a.totsc1 + sv), __ldcg(a.totsc2 + sv)};
+    }
+    __syncthreads();                                             // the set is initialised
+    const unsigned set_mask = (unsigned)n_set - 1u;
+    const int set_shift = __clz(n_set) + 1;                      // 32 - log2(n_set)
+#pragma unroll
+    for (int u = 0; u < kTailLoads; ++u) {
+        if (cv[u] == kNoCand) continue;
+        const int x = (int)cv[u];
+        if (x == INT32_MIN) s_has_min = 1;                       // the set's empty marker itself: tracked aside
+        else set_insert(s_set, set_mask, set_shift, x);
+    }
+    __syncthreads();
+    dbg_mark(a, 3, 1);
+    const int m = set_compact(s_set, n_set, s_vals);             // the contig's distinct candidates
+    int *s_one = s_set;                                          // the set is dead: the sorted list goes there
+    const int off = s_has_min;
+    if (m <= 2 * kThreads) {
+        // the values are distinct, so a value's rank IS its place in the sorted list: one pass over the
+        // list in shared memory (four values per load) instead of a sorting network of barriers
+        if (threadIdx.x < 4) s_vals[m + threadIdx.x] = INT32_MAX;
+        __syncthreads();
+        const int i0 = threadIdx.x, i1 = threadIdx.x + kThreads;
+        const int v0 = i0 < m ? s_vals[i0] : 0, v1 = i1 < m ? s_vals[i1] : 0;
+        int k0 = 0, k1 = 0;
+        for (int j = 0; j < m; j += 4) {
+            const int4 x = *reinterpret_cast<const int4 *>(s_vals + j);
+            k0 += (x.x < v0) + (x.y < v0) + (x.z < v0) + (x.w < v0);
+            k1 += (x.x < v1) + (x.y < v1) + (x.z < v1) + (x.w < v1);
+        }
+        if (i0 < m) s_one[off + k0] = v0;
+        if (i1 < m) s_one[off + k1] = v1;
+    } else {
+        const int m_pad = next_pow2(m);
+        for (int i = threadIdx.x; i < m_pad; i += kThreads) s_one[off + i] = i < m ? s_vals[i] : INT32_MAX;
+        __syncthreads();
+        block_bitonic_sort(s_one + off, m_pad);
+    }
+    if (off && threadIdx.x == 0) s_one[0] = INT32_MIN;
+    const int n_one = m + off;                                   // 0: contig skipped (:209-210)
+    __syncthreads();
+    dbg_mark(a, 3, 2);
+
+    // ---- the decisions of this block's slice (what k_predict does per tile); results stay in registers ----
+    Decision dec[kTailPer];
+    int g[kTailPer];
+    unsigned deferred = 0;
+#pragma unroll
+    for (int u = 0; u < kTailPer; ++u) {
+        g[u] = 0;
+        dec[u].valid = false;
+        if (c0 + u >= c1 || cls[u] == DUET_CLS_FILTERED || n_one == 0) continue;
+        const int sv = b + c0 + u;
+        Class2Stats t = st[u];
+        if (cls[u] == 0) t = Class2Stats{0, 0, 0, 0, 0, 0, 0};  // get_phase_info skips both loops
+        if (cls[u] == 2) {
+            const C2Rec *rec = a.c2rec + sv;
+            const int allhap = t.allhap;
+            t = Class2Stats{0, 0, 0, allhap, 0, 0, 0};
+            if (rec->overflow) {                                 // > kC2Max phase sets: the warps take it together below
+                s_fb[atomicAdd(&s_nfb, 1)] = c0 + u;
+                deferred |= 1u << u;
+                continue;
+            }
+            const int n_d = rec->n_d;
+            int best = 0;
+            for (int k = 0; k < n_d; ++k) {                      // first-seen order; strict '>' (:101)
+                const C2Ent ent = rec->d[k];
+                if (!in_sorted(s_one, n_one, ent.ps)) continue;
+                if (ent.bad) report(a.status, DUET_ERR_BAD_HP, sv, ent.bad & 0xff);
+                if (ent.tot > best) {
+                    best = ent.tot;
+                    t.h1 = ent.n1; t.h2 = ent.n2; t.t1 = ent.s1; t.t2 = ent.s2; t.ps = ent.ps;
+                    t.hap0 = allhap - ent.n1 - ent.n2;
+                }
+            }
+        }
+        dec[u] = decide(a, sv, cls[u], t, s_one, n_one, n_list[u]);
+        g[u] = dec[u].pred;
+    }
+    __syncthreads();
+    if (s_nfb) {                                                 // rare: stored right away by the warp that computes them
+        for (int k = w; k < s_nfb; k += kThreads / 32) {
+            const int sv2 = b + s_fb[k];
+            const long long b2 = __ldg(a.csr_off + sv2), e2 = __ldg(a.csr_off + sv2 + 1);
+            Class2Stats t{0, 0, 0, __ldcg(a.allhap + sv2), 0, 0, 0};
+            class2_stats(a, sv2, b2, e2, s_one, n_one, s_c2[w], t);
+            if (lane == 0) decide_and_store(a, sv2, 2, t, s_one, n_one, (int)(e2 - b2));
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < kTailPer; ++u)
+            if (deferred >> u & 1u) g[u] = (int)__ldcg(a.gt + b + c0 + u);
+        __threadfence();                                         // block 0 may have to read them (unsorted contig)
+    }
+    dbg_mark(a, 3, 3);
+
+    // ---- emission order (:206-229) and counters ----
+    unsigned long long c_kept = 0, c_emit = 0, c10 = 0, c01 = 0, c11 = 0, c_hits = 0;
+    long long key[kTailPer];
+    long long mx = kNone, mn = INT64_MAX;
+#pragma unroll
+    for (int u = 0; u < kTailPer; ++u) {
+        c_hits += (unsigned long long)nh[u];
+        c_kept += (c0 + u < c1) && cls[u] != DUET_CLS_FILTERED;
+        key[u] = kNone;
+        if (g[u] != 0) {
+            ++c_emit; c10 += g[u] == 1; c01 += g[u] == 2; c11 += g[u] == 3;
+            key[u] = (long long)(((unsigned long long)(unsigned)grp[u] << 34) |
+                                 ((unsigned long long)((unsigned)pos[u] ^ 0x80000000u) << 2) | (unsigned long long)cls[u]);
+            mx = max(mx, key[u]);
+            mn = min(mn, key[u]);
+        }
+    }
+    // six small counters in one 64-bit word (a slice has <= 512 SVs: 10 bits each), hits in another
+    unsigned long long packed = c_kept | (c_emit << 10) | (c10 << 20) | (c01 << 30) | (c11 << 40);
+    packed = warp_sum(packed);
+    c_hits = warp_sum(c_hits);
+    mn = group_min(mn, 0xffffffffu, 32);
+    if (lane == 0) {
+        atomicAdd(&s_pub.cnt[1], packed & 1023ull); atomicAdd(&s_pub.cnt[2], (packed >> 10) & 1023ull);
+        atomicAdd(&s_pub.cnt[3], (packed >> 20) & 1023ull); atomicAdd(&s_pub.cnt[4], (packed >> 30) & 1023ull);
+        atomicAdd(&s_pub.cnt[5], (packed >> 40) & 1023ull); atomicAdd(&s_pub.cnt[7], c_hits);
+        if (mn != INT64_MAX) atomicMin(&s_pub.mn, mn);
+    }
+    long long blk_mx;
+    const long long run = block_scan_exclusive(mx, kNone, OpMax(), &blk_mx);
+    long long cur = run;
+    int cnt = 0;
+    bool ok = true;
+#pragma unroll
+    for (int u = 0; u < kTailPer; ++u)
+        if (key[u] != kNone) { if (key[u] < cur) ok = false; cur = max(cur, key[u]); ++cnt; }
+    const int sorted_here = __syncthreads_and(ok);
+    int n_emit_blk;
+    int w0 = block_scan_exclusive(cnt, 0, OpSum(), &n_emit_blk);
+    if (threadIdx.x == 0) { s_pub.n_emit = n_emit_blk; s_pub.sorted = sorted_here; s_pub.mx = blk_mx; }
+    cluster.sync();                                              // (1) every block's summary can be read
+
+    if (w == 0) {                                                // lane q reads block q's summary, all eight at once
+        const int q = lane & (kTailCluster - 1);
+        const TailPub *pp = cluster.map_shared_rank(&s_pub, q);
+        const int ne = pp->n_emit, so = pp->sorted;
+        const long long pmn = pp->mn, pmx = pp->mx;
+        unsigned long long tot[DUET_N_COUNTERS];
+#pragma unroll
+        for (int k = 0; k < DUET_N_COUNTERS; ++k) tot[k] = lane < kTailCluster ? pp->cnt[k] : 0ull;
+#pragma unroll
+        for (int k = 0; k < DUET_N_COUNTERS; ++k) tot[k] = warp_sum(tot[k]);
+        int base = 0, all = 1;
+        long long seen_mx = kNone;
+#pragma unroll
+        for (int r = 0; r < kTailCluster; ++r) {                 // in block order
+            const int ne_r = __shfl_sync(0xffffffffu, ne, r), so_r = __shfl_sync(0xffffffffu, so, r);
+            const long long mn_r = __shfl_sync(0xffffffffu, pmn, r), mx_r = __shfl_sync(0xffffffffu, pmx, r);
+            if (r < rank) base += ne_r;
+            all &= so_r;
+            if (ne_r) { if (mn_r < seen_mx) all = 0; seen_mx = max(seen_mx, mx_r); }
+        }
+        if (lane == 0) {
+            s_base = base; s_all_sorted = all;
+            if (rank == 0 && all) {
+                a.n_emit[s] = (int)tot[2];
+                long long *c = a.shard_counts + (size_t)s * DUET_N_COUNTERS;
+                c[0] = n;
+                c[1] = (long long)tot[1]; c[2] = (long long)tot[2]; c[3] = (long long)tot[3];
+                c[4] = (long long)tot[4]; c[5] = (long long)tot[5];
+                c[6] = a.csr_off[b + n] - a.csr_off[b];
+                c[7] = (long long)tot[7];
+            }
+        }
+    }
+    __syncthreads();
+    cluster_arrive_relaxed();                                    // (2) this block is done reading the others
+    const int all_sorted = s_all_sorted;
+#pragma unroll
+    for (int u = 0; u < kTailPer; ++u)                           // the per-SV results, at last
+        if (c0 + u < c1) store_decision(a, b + c0 + u, dec[u]);
+    if (all_sorted) {                                            // VCF already in (group, pos, class) order: a compaction
+        int wr = b + s_base + w0;
+#pragma unroll
+        for (int u = 0; u < kTailPer; ++u)
+            if (key[u] != kNone) a.order[wr++] = b + c0 + u;
+        dbg_mark(a, 3, 4);
+        cluster_wait();                                          // nobody leaves while its summary may still be read
+        return;
+    }
+    // the contig's VCF was not sorted: block 0 re-reads every block's decisions and sorts them
+    __threadfence();
+    cluster_wait();
+    cluster.sync();                                              // (3) all decisions are in global memory
+    if (rank == 0) order_block(a, s, reinterpret_cast<long long *>(s_dyn));
+    dbg_mark(a, 3, 4);
 }
 
 }  // namespace duet

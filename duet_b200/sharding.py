@@ -18,12 +18,14 @@ from . import _lib
 
 
 def lpt_assign(weights, n_bins: int) -> list[list[int]]:
-    """Longest-processing-time-first bin packing; deterministic on every rank."""
+    """Longest-processing-time-first bin packing; deterministic on every rank.  Items of equal load
+    (in particular the zero-weight ones: contigs without a haplotagged BAM) go to the bin holding the
+    fewest items, so they spread over the ranks instead of piling up on the first idle one."""
     order = sorted(range(len(weights)), key=lambda i: (-int(weights[i]), i))
     loads = [0] * n_bins
     bins: list[list[int]] = [[] for _ in range(n_bins)]
     for i in order:
-        k = min(range(n_bins), key=lambda b: (loads[b], b))
+        k = min(range(n_bins), key=lambda b: (loads[b], len(bins[b]), b))
         bins[k].append(i)
         loads[k] += int(weights[i])
     return [sorted(b) for b in bins]
@@ -134,15 +136,19 @@ def sv_phasing_sharded(home, svlen_thres, suppread_thres, thread, include_all_ct
         cols = fn.load_hap_bam(sources[ch], thread) if sources[ch] else fn.ReadColumns.empty()
         cols.source = sources[ch]
         read_hap.append(cols)
-    batch = fn.build_batch([chrom_list[ch] for ch in mine], read_hap, [comp_call[ch] for ch in mine])
-    res = phase_fn(batch, svlen_thres, suppread_thres)
-
-    counts = gather_counters(mine, res.shard_counts, plan, device)
     rows_by_shard = {}
-    shard_of = np.searchsorted(batch.sv_off, res.order, side="right") - 1
-    for k, ch in enumerate(mine):
-        sub = type(res)(**{**res.__dict__, "order": res.order[shard_of == k]})
-        rows_by_shard[ch] = sub.rows(batch)
+    if mine:
+        batch = fn.build_batch([chrom_list[ch] for ch in mine], read_hap, [comp_call[ch] for ch in mine])
+        res = phase_fn(batch, svlen_thres, suppread_thres)
+        local_counts = res.shard_counts
+        shard_of = np.searchsorted(batch.sv_off, res.order, side="right") - 1
+        for k, ch in enumerate(mine):
+            sub = type(res)(**{**res.__dict__, "order": res.order[shard_of == k]})
+            rows_by_shard[ch] = sub.rows(batch)
+    else:
+        # more ranks than contigs: this rank owns nothing, but it still takes part in every collective
+        local_counts = np.zeros((0, _lib.N_COUNTERS), np.int64)
+    counts = gather_counters(mine, local_counts, plan, device)
     keys_local = {ch: sorted({r["chrom"] for r in rows}) for ch, rows in rows_by_shard.items()}
     if world > 1:
         all_keys = [None] * world

@@ -23,6 +23,18 @@ def test_lpt_assign_balances_and_is_deterministic():
         assert plan == sharding.lpt_assign(w, n)
 
 
+def test_lpt_assign_spreads_zero_weight_items():
+    """One BAM present, 23 contigs without one (the chr21 demo): the idle ranks share the empty contigs
+    instead of the first idle rank taking them all; with more ranks than contigs some plans are empty."""
+    w = [0] * 24
+    w[20] = 5000
+    plan = sharding.lpt_assign(w, 4)
+    assert sorted(i for p in plan for i in p) == list(range(24))
+    assert [20] in plan and max(len(p) for p in plan) <= 8 and min(len(p) for p in plan) >= 1
+    plan = sharding.lpt_assign([7, 3], 4)
+    assert sorted(len(p) for p in plan) == [0, 0, 1, 1]
+
+
 def test_slice_first_ids():
     assert sharding.slice_first_ids([["1"], ["10"], [], ["chr1"]], [5, 7, 0, 2]) == [1, 6, 0, 13]
     assert sharding.slice_first_ids([["1"], ["1"]], [1, 1]) is None
@@ -60,15 +72,15 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run_two_ranks(name, tmp_path, on_gpu):
+def _run_two_ranks(name, tmp_path, on_gpu, world=2):
     case = load_golden(f"e2e_{name}.json.gz")
     home = materialise(case, str(tmp_path))
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, home, case["svlen_thres"], case["suppread_thres"], q, on_gpu,
+    procs = [ctx.Process(target=_worker, args=(r, world, port, home, case["svlen_thres"], case["suppread_thres"], q, on_gpu,
                                                case.get("include_all_ctgs", False)))
-             for r in range(2)]
+             for r in range(world)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=120) for _ in procs)
@@ -77,7 +89,8 @@ def _run_two_ranks(name, tmp_path, on_gpu):
         assert p.exitcode == 0
     with open(home + "/phased_sv.vcf") as f:
         assert f.read() == case["phased_sv_vcf"]
-    assert np.array_equal(got[0], got[1])                      # every rank holds the whole counter table
+    for r in range(1, world):
+        assert np.array_equal(got[0], got[r])                  # every rank holds the whole counter table
     assert got[0][:, 2].sum() == len(case["rows"])
     assert not [fn for fn in os.listdir(home) if ".slice." in fn]
 
@@ -87,11 +100,17 @@ def test_two_rank_stage_is_byte_identical(name, tmp_path):
     _run_two_ranks(name, tmp_path, on_gpu=False)
 
 
+def test_more_ranks_than_contigs(tmp_path):
+    """`all_ctgs` lists three contigs (tabix shim): with four ranks one owns nothing, must not call the
+    device with an empty batch, and must still take part in every collective."""
+    _run_two_ranks("all_ctgs", tmp_path, on_gpu=False, world=4)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["cutesv_3ctg", "dense"])
 def test_two_rank_stage_on_gpu(name, tmp_path):
-    """Same, with the real device path in both ranks (two processes share the GPU when only one is
-    visible; with >= 2 GPUs each rank takes its own)."""
+    """Same, with the real device path in both ranks: each rank takes its own GPU when >= 2 are visible
+    (asserted inside the workers through DUET_DEVICE); on a 1-GPU box both share it."""
     _run_two_ranks(name, tmp_path, on_gpu=True)
 
 
