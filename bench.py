@@ -54,7 +54,7 @@ WORKLOADS = {
 CPU_SAMPLE_CONTIGS = ["17", "18", "19", "20", "21", "22"]      # 12.3 % of GRCh37: bounded CPU sample
 C3_N = 2_000_000
 C3_CPU_SAMPLE = 200_000
-KERNEL_LABEL = {"build": "k_scan", "probe": "k_probe", "reduce": "k_reduce", "tail": "k_tail", "oneps": "k_oneps",
+KERNEL_LABEL = {"build": "k_init + k_table", "probe": "k_probe", "reduce": "k_reduce", "tail": "k_tail", "oneps": "k_oneps",
                 "predict": "k_predict", "order": "k_order"}
 
 
@@ -297,8 +297,9 @@ class Ctx:
 def kernel_bytes(batch, n_hits: int) -> dict:
     """Algorithmic bytes of each kernel of THIS design (kernels)."""
     J, R, S = batch.n_joins, batch.n_reads, batch.n_svs
-    return {"build": 8 * R + 40 * J,         # k_scan: the key stream; per name 8 key (insert) + 8 key (filter) + 16 slot + 4 result + 4 chain/owner word
-            "probe": 44 * n_hits,            # k_probe: per joined read 12 candidate + 16 slot + 4 result + 12 candidate written by k_scan
+    return {"build": 28 * J + 16 * 6 * J + 4 * J,    # k_table: per name 8 key + 16 slot + 4 filter word; k_init: the slot range (6 slots
+                                                     # of 16 B per name on average) and the 4-byte join result
+            "probe": 8 * R + 52 * n_hits,            # the key stream; per joined read 16 candidate out + 16 back in + 16 slot + 4 result
             "reduce": 28 * J + 64 * S,       # 4 join row + 4 check + 16 tag + 4 owner word per join; per-SV in/out
             "tail": 126 * S, "oneps": 12 * S, "predict": 96 * S, "order": 18 * S}
 

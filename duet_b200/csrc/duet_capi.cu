@@ -89,6 +89,7 @@ struct duet_handle {
     PinBuf h_desc;
     bool desc_in_flight = false;    // EV_DESC marks the end of the last descriptor copy
     DevBuf d_desc, d_c2, d_dbg;
+    int build_grid = 0, build_per_thread = 1, build_occ[4] = {8, 8, 8, 8};      // k_table<U>, U = 1, 2, 4, 8
     int probe_grid = 0, predict_grid = 0, tail_set = 0, tail_vals = 0;
     bool tail_fused = true;         // every contig fits a cluster: k_tail; else k_oneps / k_predict / k_order
     int reduce_lanes = kReduceLanesSparse;
@@ -98,8 +99,9 @@ struct duet_handle {
     int graph_dims[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool dbg_on = false;
     size_t probe_smem = 0;
-    DevBuf d_table;                 // Slot[n_slots]: all-ones between calls (k_scan claims, k_reduce frees)
-    DevBuf d_cand_key, d_cand_row, d_cand_n;
+    DevBuf d_table;                 // Slot[n_slots], swept to all-ones by k_init at the start of every call
+    DevBuf d_bitmap;                // Bloom filter words, zeroed by k_init
+    DevBuf d_cand_list;
     DevBuf d_next, d_join_row, d_n_hit, d_cand, d_oneps, d_oneps_n, d_sort;
     DevBuf d_gt, d_cls, d_ps, d_hap1, d_hap2, d_hap0, d_allhap, d_t1, d_t2, d_feat, d_order, d_n_emit;
     DevBuf d_counts, d_status;
@@ -153,16 +155,28 @@ struct Arena {
 // One launch of the chain.  `pdl`: with the programmatic-serialization attribute the kernel's blocks may be
 // scheduled once every block of the previous kernel has started; the kernel itself waits (pdl_wait in
 // phase_kernels.cuh) before it touches anything the previous kernel writes.
+// `coop`: cooperative launch -- every block of the grid is resident at once (the runtime refuses the launch
+// otherwise); not used by the current chain (a cooperative single-kernel join was measured and lost).
 template <typename... Params, typename... Args>
-static void launch(void (*kernel)(Params...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+static cudaError_t launch(void (*kernel)(Params...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, bool coop,
+                          Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block);
     cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kernel, Params(args)...);
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (coop) {
+        attr[n].id = cudaLaunchAttributeCooperative;
+        attr[n].val.cooperative = 1;
+        ++n;
+    }
+    cfg.attrs = attr; cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, Params(args)...);
 }
 
 static size_t tail_smem_bytes(int n_set, int n_vals) { return ((size_t)n_set + (size_t)n_vals) * sizeof(int); }
@@ -219,12 +233,16 @@ int duet_create(int device_id, duet_handle **out) {
     for (auto &ev : h->cl_ev) cudaEventCreate(&ev);
     {   // fails here, loudly, if the image was not built for this device (sm_100a only)
         cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, k_scan);
-        cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, kBloomMaxWords * 4 + kProbeRingBytes);
+        cudaFuncGetAttributes(&fa, k_probe);
+        cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, kBloomMaxWords * 4 + kProbeRingBytes);
         cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)tail_smem_bytes((int)pow2_at_least(2 * kTailMaxSvs), kTailMaxSvs + 8));
         // one shared-memory carveout for all the kernels: switching it between launches drains the SMs
-        cudaFuncSetAttribute(k_scan, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_init, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_table<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_table<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_table<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_table<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_probe, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_reduce<kReduceLanesSparse>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_reduce<kReduceLanesDense>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -233,6 +251,11 @@ int duet_create(int device_id, duet_handle **out) {
         cudaFuncSetAttribute(k_oneps, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_order, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device_id);
+        // k_table runs as ONE resident wave: how many of its blocks an SM holds, per names-per-thread variant
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->build_occ[0], k_table<1>, kThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->build_occ[1], k_table<2>, kThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->build_occ[2], k_table<4>, kThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->build_occ[3], k_table<8>, kThreads, 0);
     }
     if (cudaGetLastError() != cudaSuccess) {
         delete h;
@@ -249,7 +272,7 @@ void duet_destroy(duet_handle *h) {
     DevBuf *bufs[] = {&h->in_read_key, &h->in_read_tag,
                       &h->in_sv_pos, &h->in_sv_svlen, &h->in_sv_svread, &h->in_sv_refread, &h->in_sv_flags,
                       &h->in_sv_group, &h->in_csr_off, &h->in_csr_key, &h->in_csr_chk, &h->d_desc,
-                      &h->d_c2, &h->d_dbg, &h->d_table, &h->d_cand_key, &h->d_cand_row, &h->d_cand_n, &h->d_next,
+                      &h->d_c2, &h->d_dbg, &h->d_table, &h->d_bitmap, &h->d_cand_list, &h->d_next,
                       &h->d_join_row, &h->d_n_hit, &h->d_cand, &h->d_oneps, &h->d_oneps_n, &h->d_sort, &h->d_gt,
                       &h->d_cls, &h->d_ps, &h->d_hap1, &h->d_hap2, &h->d_hap0, &h->d_allhap, &h->d_t1, &h->d_t2,
                       &h->d_feat, &h->d_order, &h->d_n_emit, &h->d_counts, &h->d_status};
@@ -313,8 +336,8 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         return fail(h, DUET_ERR_INVALID, "duet_phase_upload: a required column is NULL");
     if (in->mem != DUET_MEM_HOST && in->mem != DUET_MEM_DEVICE && in->mem != DUET_MEM_HOST_MAPPED)
         return fail(h, DUET_ERR_INVALID, "duet_phase_upload: unknown `mem`");
-    if (in->mem == DUET_MEM_DEVICE && (reinterpret_cast<uintptr_t>(in->read_key) & 15u))
-        return fail(h, DUET_ERR_INVALID, "duet_phase_upload: read_key must be 16-byte aligned");
+    if (in->mem == DUET_MEM_DEVICE && ((reinterpret_cast<uintptr_t>(in->read_key) | reinterpret_cast<uintptr_t>(in->csr_key)) & 15u))
+        return fail(h, DUET_ERR_INVALID, "duet_phase_upload: read_key and csr_key must be 16-byte aligned");
     if (in->mem != DUET_MEM_HOST && (reinterpret_cast<uintptr_t>(in->read_tag) & 15u))      // read in place, 16 bytes at a time
         return fail(h, DUET_ERR_INVALID, "duet_phase_upload: read_tag must be 16-byte aligned");
     if (in->read_off[0] != 0 || in->sv_off[0] != 0 || in->read_off[ns] != R || in->sv_off[ns] != S)
@@ -340,15 +363,15 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         if (csr[0] != 0 || csr[S] != J) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: csr_off does not span csr_key");
         for (int s = 0; s <= ns; ++s) join_off[s] = csr[in->sv_off[s]];
     }
-    std::vector<int> tab_off(ns), tab_mask(ns), bm_wmask(ns);
+    std::vector<int> tab_off(ns), tab_mask(ns), bm_off(ns), bm_wmask(ns);
     // slot table: 16-byte slots, load factor <= 1/4 while such a table (<= 8 slots of 16 B per name after
     // rounding up to a power of two) stays within half of the 126 MB L2, else <= 1/2: a sparser table means
-    // fewer CAS retry rounds in k_scan and fewer probe rounds in k_probe (a warp waits for its unluckiest
-    // lane), but one that spills out of L2 costs more than it saves.  Only the claimed slots are ever
-    // touched -- the table is handed back clean by the call itself -- so its size costs no sweep.
+    // fewer CAS retry rounds in k_table and fewer probe rounds in k_probe (a warp waits for its unluckiest
+    // lane), but one that spills out of L2 costs more than it saves.  k_init sweeps it to all-ones at the start
+    // of every call, which is also what makes it L2 resident for the scattered traffic that follows.
     // Bloom filter: 16 bits per name, at most 64 KB per shard (it lives in shared memory, two blocks per SM).
     const long long fill = (J * 8 * (long long)sizeof(Slot) <= (64ll << 20) && !(h->flags & kFlagFill2)) ? 4 : 2;
-    long long slots = 0, max_sv = 0;
+    long long slots = 0, max_sv = 0, bm_words = 0;
     for (int s = 0; s < ns; ++s) {
         const long long nj = join_off[s + 1] - join_off[s];
         if (nj < 0) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: csr_off is not monotone");
@@ -357,11 +380,14 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         tab_mask[s] = (int)(cap - 1);
         slots += cap;
         const long long words = std::min<long long>(pow2_at_least(std::max<long long>(nj / 2, 32)), kBloomMaxWords);
+        bm_off[s] = (int)bm_words;
         bm_wmask[s] = (int)(words - 1);
+        bm_words += words;
         max_sv = std::max<long long>(max_sv, in->sv_off[s + 1] - in->sv_off[s]);
         if (slots >= (1ll << 31)) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: join table too large");
     }
     h->n_slots = slots;
+    h->n_bm_words = bm_words;
     h->h_read_off.assign(in->read_off, in->read_off + ns + 1);
     h->h_sv_off.assign(in->sv_off, in->sv_off + ns + 1);
 
@@ -369,6 +395,7 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     std::memset(&a, 0, sizeof(a));
     a.n_shards = ns; a.n_reads = (int)R; a.n_svs = (int)S; a.n_joins = (int)J;
     a.n_slots = slots;
+    a.n_bm_words = bm_words;
     a.flags = h->flags;
     const int mem = in->mem == DUET_MEM_HOST_MAPPED ? DUET_MEM_HOST : in->mem;      // only read_tag is special
     int rc;
@@ -416,9 +443,28 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
                 ptiles.push_back(PredictTile{b + o, std::min(b + n, b + o + kPredictPerBlock), s, b, n, {0, 0, 0}});
         }
     h->predict_grid = (int)ptiles.size();
-    // k_scan / k_probe tiles: row ranges that never cross a contig, about two per SM in total; the names to
-    // insert are dealt out evenly over the same blocks
-    std::vector<ScanTile> qtiles;
+    // k_table: names per thread so that the whole grid is resident at once (no second wave behind the first);
+    // when even eight per thread need a second wave (dense callsets, cohorts), two per thread: more, lighter
+    // threads then win (measured: 60x dense and the 4-sample cohort share)
+    {
+        static const int kU[4] = {1, 2, 4, 8};
+        int pick = 1;
+        for (int k = 0; k < 4; ++k) {
+            const long long blocks = (J + (long long)kThreads * kU[k] - 1) / ((long long)kThreads * kU[k]);
+            if (blocks <= (long long)h->n_sm * std::max(1, h->build_occ[k])) { pick = k; break; }
+        }
+        h->build_per_thread = kU[pick];
+    }
+    const long long build_tile = (long long)kThreads * h->build_per_thread;
+    std::vector<BuildTile> btiles((size_t)((J + build_tile - 1) / build_tile));
+    for (size_t t = 0; t < btiles.size(); ++t) {
+        const long long first = (long long)t * build_tile, last = std::min<long long>(J, first + build_tile) - 1;
+        const int lo = shard_at(join_off, first), hi = shard_at(join_off, last);
+        btiles[t] = BuildTile{lo, hi, tab_off[lo], tab_mask[lo], bm_off[lo], bm_wmask[lo], {0, 0}};
+    }
+    h->build_grid = (int)btiles.size();
+    // k_probe tiles: row ranges that never cross a contig, about two per SM in total
+    std::vector<ProbeTile> qtiles;
     {
         // tiles of about equal size (a contig's rows are cut into round(rows / per) pieces), as many as fit
         // on the device at once: more would mean a second wave costing a whole block time
@@ -426,7 +472,7 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         for (int s = 0; s < ns; ++s) max_words = std::max<long long>(max_words, (long long)bm_wmask[s] + 1);
         h->probe_smem = (size_t)kProbeRingBytes + (size_t)max_words * 4;
         int occ = kProbeBlocksPerSm;                             // big filters leave room for one block per SM only
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan, kProbeBlock, h->probe_smem) != cudaSuccess || occ < 1) occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_probe, kProbeBlock, h->probe_smem) != cudaSuccess || occ < 1) occ = 1;
         const long long cap = std::max(1, h->n_sm * std::min(occ, kProbeBlocksPerSm));
         long long per = std::max<long long>((R + cap - 1) / cap, 1);
         for (;;) {
@@ -438,13 +484,6 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
             if (total <= cap || per >= R) break;
             per += per / 16 + 1;
         }
-        auto tile_of = [&](long long q0, long long q1, int s) {
-            ScanTile t;
-            std::memset(&t, 0, sizeof(t));
-            t.r0 = q0; t.r1 = q1; t.shard = s; t.base = tab_off[s]; t.mask = tab_mask[s]; t.bmw = bm_wmask[s];
-            t.nm0 = (int)join_off[s]; t.nm1 = (int)join_off[s + 1];
-            return t;
-        };
         for (int s = 0; s < ns; ++s) {
             const long long b0 = h->h_read_off[s], b1 = h->h_read_off[s + 1];
             if (b1 <= b0) continue;
@@ -453,28 +492,18 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
                 long long q0 = b0 + (b1 - b0) * k / pieces, q1 = b0 + (b1 - b0) * (k + 1) / pieces;
                 if (k > 0) q0 += q0 & 1;                         // interior cuts on 16-byte boundaries
                 if (k + 1 < pieces) q1 += q1 & 1;
-                if (q0 < q1) qtiles.push_back(tile_of(q0, q1, s));
+                if (q0 < q1) qtiles.push_back(ProbeTile{q0, q1, s, tab_off[s], tab_mask[s], bm_off[s], bm_wmask[s], 0});
             }
         }
-        // no reads at all (or fewer tiles than would keep the device busy inserting): pad with row-less tiles
-        const size_t want = std::min<size_t>((size_t)cap, (size_t)std::max<long long>(1, (J + 2047) / 2048));
-        while (qtiles.size() < want) { ScanTile t = tile_of(0, 0, 0); t.nm0 = t.nm1 = 0; t.bmw = 31; qtiles.push_back(t); }
-        const long long nt = (long long)qtiles.size();
-        for (long long k = 0; k < nt; ++k) {
-            ScanTile &t = qtiles[(size_t)k];
-            const long long i0 = J * k / nt, i1 = J * (k + 1) / nt;
-            t.ins0 = (int)i0; t.ins1 = (int)i1;
-            t.ins_lo = i0 < i1 ? shard_at(join_off, i0) : 0;
-            t.ins_hi = i0 < i1 ? shard_at(join_off, i1 - 1) : 0;
-        }
+        if (qtiles.empty()) qtiles.push_back(ProbeTile{0, 0, 0, 0, 0, 0, 31, 0});
     }
     h->probe_grid = (int)qtiles.size();
-    a.n_scan_tiles = h->probe_grid;
+    a.n_probe_tiles = h->probe_grid;
     {
         Arena ar;
         const size_t o_read = ar.put(h->h_read_off), o_sv = ar.put(h->h_sv_off), o_join = ar.put(join_off);
-        const size_t o_toff = ar.put(tab_off), o_tmask = ar.put(tab_mask);
-        const size_t o_pt = ar.put(ptiles), o_qt = ar.put(qtiles);
+        const size_t o_toff = ar.put(tab_off), o_tmask = ar.put(tab_mask), o_boff = ar.put(bm_off), o_bmask = ar.put(bm_wmask);
+        const size_t o_bt = ar.put(btiles), o_pt = ar.put(ptiles), o_qt = ar.put(qtiles);
         if (h->desc_in_flight) CU(h, cudaEventSynchronize(h->ev[EV_DESC]));      // the previous copy out of h_desc is over
         CU(h, h->h_desc.reserve(ar.bytes.size()));
         CU(h, h->d_desc.reserve(ar.bytes.size()));
@@ -488,22 +517,21 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         a.join_off = reinterpret_cast<const long long *>(d + o_join);
         a.tab_off = reinterpret_cast<const int *>(d + o_toff);
         a.tab_mask = reinterpret_cast<const int *>(d + o_tmask);
+        a.bm_off = reinterpret_cast<const int *>(d + o_boff);
+        a.bm_wmask = reinterpret_cast<const int *>(d + o_bmask);
         a.predict_tiles = reinterpret_cast<const PredictTile *>(d + o_pt);
-        a.scan_tiles = reinterpret_cast<const ScanTile *>(d + o_qt);
+        a.build_tiles = reinterpret_cast<const BuildTile *>(d + o_bt);
+        a.probe_tiles = reinterpret_cast<const ProbeTile *>(d + o_qt);
     }
     CU(h, cudaEventRecord(h->ev[EV_H2D1], st));
     h->have_h2d = true;
 
     const size_t S1 = (size_t)std::max<long long>(S, 1), J1 = (size_t)std::max<long long>(J, 1);
-    // The join table and the filter are clean (all-ones / all-zero) between calls: k_reduce restores exactly
-    // what k_table touched.  Only fresh memory has to be initialised.
-    bool grew = false;
-    CU(h, h->d_table.reserve((size_t)std::max<long long>(slots, 1) * sizeof(Slot), &grew));
-    if (grew) CU(h, cudaMemsetAsync(h->d_table.p, 0xFF, h->d_table.cap, st));
+    CU(h, h->d_table.reserve((size_t)std::max<long long>(slots, 1) * sizeof(Slot)));
     a.tab = h->d_table.as<Slot>();
-    CU(h, h->d_cand_key.reserve((size_t)std::max<long long>(R, 1) * 8)); a.cand_key = h->d_cand_key.as<unsigned long long>();
-    CU(h, h->d_cand_row.reserve((size_t)std::max<long long>(R, 1) * 4)); a.cand_row = h->d_cand_row.as<int>();
-    CU(h, h->d_cand_n.reserve((size_t)h->probe_grid * 4));               a.cand_n = h->d_cand_n.as<int>();
+    CU(h, h->d_bitmap.reserve((size_t)std::max<long long>(bm_words, 32) * 4));
+    a.bitmap = h->d_bitmap.as<unsigned>();
+    CU(h, h->d_cand_list.reserve((size_t)std::max<long long>(R, 1) * 16)); a.cand_list = h->d_cand_list.as<ulonglong2>();
     CU(h, h->d_next.reserve(J1 * 4));                    a.next = h->d_next.as<int>();
     CU(h, h->d_join_row.reserve(J1 * 4 + 16));                a.join_row = h->d_join_row.as<int>();
     CU(h, h->d_n_hit.reserve(S1 * 4));                   a.n_hit = h->d_n_hit.as<int>();
@@ -528,7 +556,6 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     CU(h, h->d_counts.reserve((size_t)ns * 8 * DUET_N_COUNTERS)); a.shard_counts = h->d_counts.as<long long>();
     CU(h, h->d_status.reserve(sizeof(DevStatus)));       a.status = h->d_status.as<DevStatus>();
     // state the kernels keep clean between calls: counters of shards without SVs stay zero, status zero
-    if (J == 0 && S) CU(h, cudaMemsetAsync(h->d_join_row.p, 0xFF, J1 * 4, st));
     CU(h, cudaMemsetAsync(h->d_oneps_n.p, 0, (size_t)ns * 4, st));
     CU(h, cudaMemsetAsync(h->d_n_emit.p, 0, (size_t)ns * 4, st));
     CU(h, cudaMemsetAsync(h->d_counts.p, 0, (size_t)ns * 8 * DUET_N_COUNTERS, st));
@@ -541,7 +568,7 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     return DUET_OK;
 }
 
-// The launches of one call, a serial chain on `st`: k_scan -> k_probe -> k_reduce -> k_tail (or, when a
+// The launches of one call, a serial chain on `st`: k_init -> k_table -> k_probe -> k_reduce -> k_tail (or, when a
 // contig has more SVs than a cluster holds, k_oneps -> k_predict -> k_order).  With `marks`, an event
 // follows each stage.
 static int launch_all(duet_handle *h, cudaStream_t st, bool marks) {
@@ -550,30 +577,40 @@ static int launch_all(duet_handle *h, cudaStream_t st, bool marks) {
     const bool pdl = !marks && !no_pdl;
     const PhaseArgs &a = h->a;
     const int S = a.n_svs;
-    const bool join = a.n_joins > 0, probe = a.n_reads && a.n_joins;
+    const bool join = a.n_joins > 0;
+    const bool probe = a.n_reads && a.n_joins;
     int n = 0;
-    if (join) { launch(k_scan, h->probe_grid, kProbeBlock, h->probe_smem, st, false, a); ++n; }
+    if (join) {
+        launch(k_init, h->n_sm * 4, kThreads, 0, st, false, false, a);
+        switch (h->build_per_thread) {
+            case 1: launch(k_table<1>, h->build_grid, kThreads, 0, st, pdl, false, a); break;
+            case 2: launch(k_table<2>, h->build_grid, kThreads, 0, st, pdl, false, a); break;
+            case 4: launch(k_table<4>, h->build_grid, kThreads, 0, st, pdl, false, a); break;
+            default: launch(k_table<8>, h->build_grid, kThreads, 0, st, pdl, false, a); break;
+        }
+        n += 2;
+    }
     mark(EV_K0);
-    if (probe) { launch(k_probe, h->probe_grid, kProbeThreads, 0, st, pdl, a); ++n; }
+    if (probe) { launch(k_probe, h->probe_grid, kProbeBlock, h->probe_smem, st, pdl, false, a); ++n; }
     mark(EV_K1);
     if (S) {
         const int per = kThreads / h->reduce_lanes;
-        if (h->reduce_lanes == kReduceLanesDense) launch(k_reduce<kReduceLanesDense>, (S + per - 1) / per, kThreads, 0, st, pdl && join, a);
-        else launch(k_reduce<kReduceLanesSparse>, (S + per - 1) / per, kThreads, 0, st, pdl && join, a);
+        if (h->reduce_lanes == kReduceLanesDense) launch(k_reduce<kReduceLanesDense>, (S + per - 1) / per, kThreads, 0, st, pdl && join, false, a);
+        else launch(k_reduce<kReduceLanesSparse>, (S + per - 1) / per, kThreads, 0, st, pdl && join, false, a);
         ++n;
     }
     mark(EV_K2);
     if (S && h->tail_fused) {
-        launch(k_tail, a.n_shards * kTailCluster, kThreads, tail_smem_bytes(h->tail_set, h->tail_vals), st, pdl, a,
+        launch(k_tail, a.n_shards * kTailCluster, kThreads, tail_smem_bytes(h->tail_set, h->tail_vals), st, pdl, false, a,
                h->tail_set, h->tail_vals);
         ++n;
     }
     mark(EV_K3);
-    if (S && !h->tail_fused) { launch(k_oneps, a.n_shards, kThreads, 0, st, pdl, a); ++n; }
+    if (S && !h->tail_fused) { launch(k_oneps, a.n_shards, kThreads, 0, st, pdl, false, a); ++n; }
     mark(EV_K4);
-    if (S && !h->tail_fused) { launch(k_predict, h->predict_grid, kThreads, 0, st, pdl, a); ++n; }
+    if (S && !h->tail_fused) { launch(k_predict, h->predict_grid, kThreads, 0, st, pdl, false, a); ++n; }
     mark(EV_K5);
-    if (S && !h->tail_fused) { launch(k_order, a.n_shards, kThreads, 0, st, pdl, a); ++n; }
+    if (S && !h->tail_fused) { launch(k_order, a.n_shards, kThreads, 0, st, pdl, false, a); ++n; }
     return n;
 }
 
@@ -594,7 +631,7 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
         // the launch sequence of a staged batch never changes: replay it as a CUDA graph.  A re-upload
         // of the same shapes lands in the same buffers, so the captured graph stays valid.
         const int dims[8] = {h->probe_grid, h->reduce_lanes, (int)h->probe_smem, h->predict_grid,
-                             0, 0, h->tail_fused ? h->tail_set : 0, h->tail_vals};
+                             h->build_grid, h->build_per_thread, h->tail_fused ? h->tail_set : 0, h->tail_vals};
         if (h->graph_exec && (std::memcmp(&h->graph_args, &h->a, sizeof(PhaseArgs)) != 0 ||
                               std::memcmp(h->graph_dims, dims, sizeof(dims)) != 0)) {
             cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr;
@@ -616,14 +653,13 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
         if (h->graph_exec) {
             CU(h, cudaGraphLaunch(h->graph_exec, st));
             const PhaseArgs &a = h->a;
-            n_graph = (a.n_joins ? 1 : 0) + (a.n_reads && a.n_joins ? 1 : 0) + (a.n_svs ? (h->tail_fused ? 2 : 4) : 0);
+            n_graph = (a.n_joins ? 2 : 0) + (a.n_reads && a.n_joins ? 1 : 0) + (a.n_svs ? (h->tail_fused ? 2 : 4) : 0);
             h->launches += n_graph;
         } else {
             h->launches += launch_all(h, st, false);
         }
     }
     CU(h, cudaEventRecord(h->ev[EV_K6], st));
-    if (h->flags & kFlagNoSlotFree) CU(h, cudaMemsetAsync(h->d_table.p, 0xFF, h->d_table.cap, st));      // diagnostics only
     CU(h, cudaGetLastError());
     h->executed = true;
     return DUET_OK;

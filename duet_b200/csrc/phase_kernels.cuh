@@ -1,16 +1,18 @@
 // sm_100a kernels of the sv_phasing hot path.
 //
 // Reference behaviour restated per kernel (citations: /root/reference/src/duet/sv_phasing_fn.py):
-//   k_scan     the dict-insert side of the JOIN (:26-29 keyed by QNAME) -- here the SMALL side is
-//              inserted: the support-read names of the SVs (:46-48) claim slots of the join table -- and,
-//              in the same blocks at the same time, the haplotagged reads are streamed once through the
-//              contig's Bloom filter (built by the block itself, in shared memory, from the contig's
-//              names): the survivors become the candidate list
-//   k_probe    the candidates against the slot table: a hit records the row index on every support-read
-//              entry of that name with atomicMax == "a later row overwrites an earlier one" (:29)
+//   k_init     start-of-call state in one sequential sweep: EMPTY slot table, zero Bloom filter, join
+//              results -1 -- which also leaves all three L2 resident for the scattered traffic that follows
+//   k_table    the dict-insert side of the JOIN (:26-29 keyed by QNAME) -- here the SMALL side is
+//              inserted: every support-read name of the SVs (:46-48) claims a slot (one CAS) and sets its
+//              two Bloom-filter bits (one RED)
+//   k_probe    the haplotagged reads streamed once through the contig's Bloom filter (shared memory);
+//              the block then looks its survivors up in the slot table: a hit records the row index on
+//              every support-read entry of that name with atomicMax == "a later row overwrites an
+//              earlier one" (:29)
 //   k_reduce   per SV: gather the joined reads' tags, class = #distinct PS (:192-194), one-PS candidate
 //              (:195-203), class-1 counts and score sums (:74-84), per-PS statistics of class-2 SVs in
-//              first-seen order (:85-105); hands the join table back clean for the next call
+//              first-seen order (:85-105)
 //   k_tail     one thread-block CLUSTER per contig: its sorted unique one-PS list (:107), then per SV the
 //              in-set PS with most reads (:99-105), nearest-PS fallback (:106-111), features (:112-139),
 //              the T1-T5 tree (:142-183), then the contig's emission order (:206-229) and counters
@@ -18,12 +20,16 @@
 //              SVs than a cluster holds
 //
 // What bounds these kernels at WGS size is not bandwidth (the whole problem is ~130 MB).  Measured on
-// B200 (tools/ubench_atomics.cu): a kernel that does ONE scattered access per element costs ~8 us however
-// few elements it has; an SM issues ~0.5 scattered atomics or ~0.7 scattered loads/stores per clock; a
-// dependent global access under load is a 1-2 us round trip.  So the design minimises (a) dependent round
-// trips per kernel, (b) scattered operations per element (one CAS per name, one slot load per candidate,
-// one 16-byte record per joined read), (c) what sits behind a kernel boundary: everything that does not
-// need the previous kernel's output runs before griddepcontrol.wait, under the predecessor's tail.
+// B200 (tools/ubench_atomics.cu, profiles/r2_ubench.txt): a kernel that does ONE scattered access per
+// element costs ~8 us however few elements it has; an SM issues ~0.5 scattered atomics or ~0.8 scattered
+// loads / stores per clock (shared-memory atomics queue for the same unit); 400 k scattered accesses to lines
+// that are not in L2 cost ~8 us more than to lines that are, while WRITING 38 MB front to back costs ~6 us;
+// a dependent global access under load is a 1-2 us round trip.  So: (a) the join table is made L2 resident
+// by the sequential sweep that initialises it, never by the scattered accesses that use it; (b) as few
+// scattered operations per element as possible (one CAS + one RED per name, one slot load per candidate,
+// one 16-byte record per joined read); (c) every kernel requests everything independent at once, starts
+// from a host-built tile descriptor instead of looking its contig up, and does what does not need its
+// predecessor's output before griddepcontrol.wait; (d) the three per-contig steps are one cluster launch.
 #pragma once
 
 #include <cooperative_groups.h>
@@ -57,13 +63,8 @@ struct __align__(16) ReadTag { int ps, pc; unsigned chk, hp; };       // hp: low
 
 // host-built descriptors: what a block needs to know about its tile, in one 64- / 32-byte load
 struct PredictTile { int sv0, sv1, shard, b, n, pad[3]; };        // SVs [sv0, sv1) of ONE shard = SVs [b, b + n)
-struct ScanTile {                   // one block of k_scan / k_probe
-    long long r0, r1;               // rows [r0, r1) of ONE contig: streamed through the filter
-    int shard, base, mask, bmw;     // that contig's slot range (base, mask) and filter size (words - 1)
-    int nm0, nm1;                   // the contig's support-read names: csr_key[nm0, nm1) -> the block's filter
-    int ins0, ins1, ins_lo, ins_hi; // names [ins0, ins1) (any contig: shards ins_lo..ins_hi) this block inserts
-    int pad[2];
-};
+struct BuildTile { int lo, hi, base, mask, bmo, bmw, pad[2]; };   // kThreads * U consecutive support reads: shards lo..hi
+struct ProbeTile { long long r0, r1; int shard, base, mask, bmo, bmw, pad; };   // rows [r0, r1) of ONE contig + its table / filter
 
 constexpr int kC2Max = 8;    // distinct PS per class-2 SV recorded by k_reduce (more -> warp fallback)
 struct C2Ent { int ps, tot, n1, n2; long long s1, s2; int bad, pad; };
@@ -78,8 +79,7 @@ struct DevStatus {          // device -> host error report
 // Everything a kernel needs; passed by value.
 // developer switches (environment DUET_FLAGS, read once per handle); 0 in production
 enum {
-    kFlagNoSlotFree = 1,      // k_reduce leaves the claimed slots alone (the host memsets the table after the call)
-    kFlagNoWarm = 2,          // k_probe does not warm L2 with k_reduce's input columns while it waits
+    kFlagNoWarm = 2,          // k_init does not warm L2 with the input columns k_reduce / k_tail start from
     kFlagFill2 = 16,          // host: load factor <= 1/2 always
     kFlagSplitTail = 32,      // host: k_oneps / k_predict / k_order instead of k_tail
 };
@@ -94,11 +94,10 @@ struct PhaseArgs {
     const long long *sv_off;     // [n_shards+1]
     const long long *join_off;   // [n_shards+1] csr_off at the shard boundaries (derived at upload)
     const PredictTile *predict_tiles;   // [sum over shards of ceil(n / kPredictPerBlock)] = k_predict grid
-    const ScanTile *scan_tiles;     // [n_scan_tiles] = k_scan / k_probe grid
-    int n_scan_tiles;
-    unsigned long long *cand_key;   // [R] rows that passed their contig's filter: tile t appends at [r0(t), ...)
-    int *cand_row;                  // [R]
-    int *cand_n;                    // [n_scan_tiles] how many
+    const BuildTile *build_tiles;   // [k_table grid]
+    const ProbeTile *probe_tiles;   // [n_probe_tiles] = k_probe grid
+    int n_probe_tiles;
+    ulonglong2 *cand_list;          // [R] rows that passed their contig's filter, (key, row): tile t appends at [r0(t), ...)
     const unsigned long long *read_key;
     const ReadTag *read_tag;
     const int *sv_pos, *sv_svlen, *sv_svread, *sv_refread;
@@ -110,9 +109,13 @@ struct PhaseArgs {
     // join table: shard s owns slots [tab_off[s], tab_off[s] + tab_mask[s] + 1)
     const int *tab_off;          // [n_shards]
     const int *tab_mask;         // [n_shards]
-    Slot *tab;                   // [n_slots] all-ones (= free) between calls: k_reduce frees what k_table claimed
-    int *next;                   // [J] entry that shares a slot: next entry carrying the same name, -1 none;
-                                 //     entry that CLAIMED a slot: -2 - slot index (what k_reduce frees)
+    Slot *tab;                   // [n_slots] set to all-ones (= free) by k_init
+    int *next;                   // [J] next entry carrying the same name, -1 none
+    // per-shard Bloom filter over the support-read names: words [bm_off[s], bm_off[s] + bm_wmask[s] + 1)
+    const int *bm_off;           // [n_shards]
+    const int *bm_wmask;         // [n_shards] (power of two) - 1
+    unsigned *bitmap;            // zeroed by k_init
+    long long n_bm_words;
     // per-SV intermediates / outputs (device)
     int *join_row;               // [J] row each support read joined to (atomicMax by k_probe), -1 = miss
     int *n_hit;                  // [S] joined reads of the SV
@@ -289,23 +292,116 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned b
 }
 
 // ------------------------------------------------------------------------------------------
-// k_scan: one block per tile -- a row range of ONE contig, sized so that the grid is about two blocks per
-// SM, all resident.  Nothing here depends on another kernel, and three things run side by side:
-//   * every consumer thread CLAIMS SLOTS for its share of the call's support-read names (one CAS per name,
-//     linear probing; all of a thread's names in flight together).  The first entry of a name owns the
-//     slot, later entries chain themselves behind it.  The table cleans itself: all slots are free
-//     (all-ones) BETWEEN calls; the entry that claims a slot leaves the slot's index in next[] (-2 - index)
-//     and k_reduce, which walks every entry anyway once the probe is over, frees exactly those slots.  A
-//     call therefore never sweeps the table (6x larger than what it touches).
-//   * the block builds its contig's Bloom filter in SHARED memory straight from the contig's names
-//     (16 bits per name, two bits per key, <= 64 KB): no global filter, no atomics on it, no copy;
-//   * the haplotagged reads are STREAMED once: a producer warp keeps a ring of 16 KB key tiles in flight
-//     with bulk asynchronous copies (TMA, cp.async.bulk + mbarrier complete_tx); the consumer warps take a
-//     tile as soon as its barrier flips and hand the stage back through an `empty` barrier -- no block-wide
-//     synchronisation inside the stream.  ~90 % of the rows (reads that support no SV) never leave the SM;
-//     the survivors are appended to the block's private stretch of the candidate list.
-// The table lookups of the candidates need EVERY block's names in place: they are k_probe, behind the
-// kernel boundary.
+// k_init: start-of-call state in one sequential sweep: EMPTY slots (all ones), zero filter words, join
+// results -1.  Sequential 16-byte stores are the cheap way to get all three L2 resident for the scattered
+// traffic of k_table / k_probe (writing 38 MB front to back: ~6 us; 400 k scattered accesses to lines that
+// have to come from HBM: ~8 us on top of the same accesses to resident lines -- measured).  The input
+// columns the later kernels start from are pulled into L2 along the way (prefetch hints).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warm_l2(const void *p, size_t bytes, long long tid, long long n_threads) {
+    const char *c = reinterpret_cast<const char *>(p);
+    const long long lines = (long long)((bytes + 127) >> 7);
+    for (long long i = tid; i < lines; i += n_threads) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + (i << 7)));
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_init(PhaseArgs a) {
+    pdl_trigger();
+    pdl_wait();                                                  // first kernel of a call: returns at once
+    const long long stride = (long long)gridDim.x * kThreads;
+    const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0u, 0u, 0u, 0u);
+    uint4 *tab = reinterpret_cast<uint4 *>(a.tab);
+    for (long long i = t; i < a.n_slots; i += stride) tab[i] = ones;
+    uint4 *jr = reinterpret_cast<uint4 *>(a.join_row);           // allocation padded to 16 bytes
+    for (long long i = t; i < ((long long)a.n_joins + 3) / 4; i += stride) jr[i] = ones;
+    uint4 *bm = reinterpret_cast<uint4 *>(a.bitmap);
+    for (long long i = t; i < a.n_bm_words / 4; i += stride) bm[i] = zero;
+    if (!(a.flags & kFlagNoWarm)) {
+        const size_t S = (size_t)a.n_svs, J = (size_t)a.n_joins;
+        warm_l2(a.csr_off, (S + 1) * 8, t, stride);
+        if (a.csr_chk) warm_l2(a.csr_chk, J * 4, t, stride);
+        warm_l2(a.sv_svlen, S * 4, t, stride); warm_l2(a.sv_svread, S * 4, t, stride); warm_l2(a.sv_flags, S, t, stride);
+        warm_l2(a.sv_pos, S * 4, t, stride); warm_l2(a.sv_refread, S * 4, t, stride);
+        if (a.sv_group) warm_l2(a.sv_group, S * 4, t, stride);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// The build side: k_table claims a slot per support-read name and sets the name's filter bits.  U names
+// per thread, all of their atomics in flight together, and a grid that is resident in ONE wave: every block
+// has its keys in registers before k_init is over (they are requested before griddepcontrol.wait).
+// Dependent chain of a k_table thread: [keys, tile descriptor] -> CAS (-> CAS on a collision) -> stores.
+// ------------------------------------------------------------------------------------------
+// which shard (table range, filter range) support-read entry j of this tile belongs to
+__device__ __forceinline__ void build_where(const PhaseArgs &a, const BuildTile &t, long long j, int &base,
+                                            unsigned &mask, int &bmo, unsigned &bmw) {
+    base = t.base; mask = (unsigned)t.mask; bmo = t.bmo; bmw = (unsigned)t.bmw;
+    if (t.lo != t.hi) {                                          // the tile straddles a contig boundary
+        const int s = t.lo + shard_of(a.join_off + t.lo, t.hi - t.lo + 1, j);
+        base = __ldg(a.tab_off + s); mask = (unsigned)__ldg(a.tab_mask + s);
+        bmo = __ldg(a.bm_off + s); bmw = (unsigned)__ldg(a.bm_wmask + s);
+    }
+}
+
+template <int U>
+__global__ void __launch_bounds__(kThreads)
+k_table(PhaseArgs a) {
+    dbg_mark(a, 0, 0);
+    const long long j0 = (long long)blockIdx.x * (kThreads * U) + threadIdx.x;
+    unsigned long long key[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const long long j = j0 + u * kThreads;
+        key[u] = j < a.n_joins ? __ldcs(a.csr_key + j) : 0ull;
+    }
+    const BuildTile t = a.build_tiles[blockIdx.x];
+    unsigned p[U], mask[U], bmw[U];
+    int base[U], bmo[U];
+    unsigned pend = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const long long j = j0 + u * kThreads;
+        if (j >= a.n_joins) continue;
+        build_where(a, t, j, base[u], mask[u], bmo[u], bmw[u]);
+        p[u] = slot_hash(key[u]) & mask[u];
+        pend |= 1u << u;
+    }
+    pdl_trigger();
+    pdl_wait();                                                  // the slots and the filter words are initialised
+    dbg_mark(a, 0, 1);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (pend >> u & 1u) atomicOr(a.bitmap + bmo[u] + (int)bloom_word(key[u], bmw[u]), bloom_bits(key[u]));    // fire and forget
+    while (pend) {
+        unsigned long long prev[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (pend >> u & 1u) prev[u] = atomicCAS(&a.tab[base[u] + p[u]].key, kEmptyKey, key[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!(pend >> u & 1u)) continue;
+            const int j = (int)(j0 + u * kThreads);
+            Slot *sl = a.tab + base[u] + p[u];
+            if (prev[u] == kEmptyKey) { sl->first = j; pend &= ~(1u << u); }
+            else if (prev[u] == key[u]) { a.next[j] = atomicExch(&sl->head, j); pend &= ~(1u << u); }
+            else p[u] = (p[u] + 1) & mask[u];
+        }
+    }
+    dbg_mark(a, 0, 2);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_probe: the haplotagged reads are STREAMED once by one block per tile -- a tile is a row range of ONE
+// contig, sized so that the grid is about two blocks per SM.  A producer warp keeps a ring of 16 KB key
+// tiles in flight with bulk asynchronous copies (TMA, cp.async.bulk + mbarrier complete_tx); the consumer
+// warps take a tile as soon as its barrier flips and hand the stage back through an `empty` barrier --
+// no block-wide synchronisation inside the stream.  The ring is full before k_table is over; the contig's
+// Bloom filter arrives in shared memory by ONE bulk copy issued the moment k_table is known to be complete,
+// so ~90 % of the rows (reads that support no SV) never leave the SM.  The survivors are appended to the
+// block's private stretch of the candidate list, one 16-byte record each, and their tag records start
+// moving into L2; when the stream is done the whole block resolves its candidates against the slot table,
+// kResolveUnroll per thread in flight together.
 // ------------------------------------------------------------------------------------------
 constexpr int kProbeThreads = 512;                               // consumer threads
 constexpr int kProbeBlock = kProbeThreads + 32;                  // + one producer warp that only issues copies
@@ -315,17 +411,15 @@ constexpr int kProbeRows = 2 * kProbeUnroll;                     // rows per thr
 constexpr int kProbeBatch = kProbeThreads * kProbeUnroll;        // pairs per tile (16 KB)
 constexpr int kProbeStages = 3;                                  // tiles in flight per block
 constexpr int kProbeRingBytes = kProbeStages * kProbeBatch * 16;
-constexpr int kInsertUnroll = 4;                                 // names per thread in flight
-constexpr int kFilterUnroll = 8;                                 // names per thread requested together for the filter
-constexpr int kResolveUnroll = 4;                                // candidates per thread in flight (k_probe)
+constexpr int kResolveUnroll = 4;                                // candidates per thread in flight in the drain
 
 __global__ void __launch_bounds__(kProbeBlock, kProbeBlocksPerSm)
-k_scan(PhaseArgs a) {
+k_probe(PhaseArgs a) {
     extern __shared__ __align__(128) unsigned char s_raw[];      // [key ring | filter words]
-    __shared__ __align__(8) unsigned long long s_full[kProbeStages], s_empty[kProbeStages];
+    __shared__ __align__(8) unsigned long long s_full[kProbeStages], s_empty[kProbeStages], s_bm_full;
     __shared__ int s_count;
-    dbg_mark(a, 0, 0);
-    const ScanTile tile = a.scan_tiles[blockIdx.x];              // one contig, one row range, everything needed
+    dbg_mark(a, 1, 0);
+    const ProbeTile tile = a.probe_tiles[blockIdx.x];            // one contig, one row range, everything needed
     ulonglong2 *ring = reinterpret_cast<ulonglong2 *>(s_raw);
     unsigned *s_bm = reinterpret_cast<unsigned *>(s_raw + kProbeRingBytes);
     const long long R = a.n_reads;
@@ -340,111 +434,26 @@ k_scan(PhaseArgs a) {
     auto tile_pairs = [&](int t) { return (unsigned)max(0ll, min(q_full, q0 + (long long)(t + 1) * kProbeBatch) - (q0 + (long long)t * kProbeBatch)); };
     if (threadIdx.x == 0) {
         for (int s = 0; s < kProbeStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kProbeThreads / 32); }
+        mbar_init(&s_bm_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_count = 0;
     }
-    for (int i = threadIdx.x; i < (int)(bmw + 1) / 4; i += kProbeBlock)
-        reinterpret_cast<uint4 *>(s_bm)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    if (threadIdx.x == 0) {                                      // fill the ring: the stream is on its way while the
-        for (int t = 0; t < min(n_tiles, kProbeStages); ++t) {   // names are being inserted and the filter built
+    if (threadIdx.x == 0) {                                      // fill the ring: the stream starts before the filter is in
+        for (int t = 0; t < min(n_tiles, kProbeStages); ++t) {
             const unsigned bytes = tile_pairs(t) * 16u;
             mbar_expect_tx(&s_full[t], bytes);
             if (bytes) bulk_load(ring + (size_t)t * kProbeBatch, pairs + q0 + (long long)t * kProbeBatch, bytes, &s_full[t]);
         }
     }
-    pdl_trigger();                                               // k_probe's blocks may take their places and wait
-    // ---- this block's share of the names: claim a slot each.  The first batch's CAS round trip runs under
-    // the filter build; its results are looked at afterwards ----
-    const bool consumer = threadIdx.x < kProbeThreads;
-    unsigned long long ikey[kInsertUnroll], iprev[kInsertUnroll];
-    unsigned ip[kInsertUnroll], imask[kInsertUnroll];
-    int ibase[kInsertUnroll];
-    unsigned ipend = 0;
-    if (consumer) {
-        const int jb = tile.ins0 + (int)threadIdx.x;
-#pragma unroll
-        for (int u = 0; u < kInsertUnroll; ++u) {
-            const int j = jb + u * kProbeThreads;
-            ikey[u] = j < tile.ins1 ? __ldcs(a.csr_key + j) : 0ull;
-        }
-#pragma unroll
-        for (int u = 0; u < kInsertUnroll; ++u) {
-            const int j = jb + u * kProbeThreads;
-            if (j >= tile.ins1) continue;
-            int sh = tile.ins_lo;
-            if (tile.ins_lo != tile.ins_hi) sh += shard_of(a.join_off + tile.ins_lo, tile.ins_hi - tile.ins_lo + 1, j);
-            ibase[u] = __ldg(a.tab_off + sh); imask[u] = (unsigned)__ldg(a.tab_mask + sh);
-            a.join_row[j] = -1;                                  // "miss" until a row of k_probe says otherwise
-            ip[u] = slot_hash(ikey[u]) & imask[u];
-            ipend |= 1u << u;
-        }
-#pragma unroll
-        for (int u = 0; u < kInsertUnroll; ++u)
-            if (ipend >> u & 1u) iprev[u] = atomicCAS(&a.tab[ibase[u] + ip[u]].key, kEmptyKey, ikey[u]);
+    pdl_trigger();
+    pdl_wait();                                                  // k_table is done: filter bits and slots are final
+    if (threadIdx.x == 0) {                                      // the contig's filter: one bulk copy
+        const unsigned bytes = (bmw + 1u) * 4u;
+        mbar_expect_tx(&s_bm_full, bytes);
+        bulk_load(s_bm, a.bitmap + tile.bmo, bytes, &s_bm_full);
     }
-    dbg_mark(a, 0, 1);
-    // ---- the contig's filter, in shared memory, from the contig's names (all 17 warps; kFilterUnroll keys
-    // per thread requested together) ----
-    for (int j0 = tile.nm0 + (int)threadIdx.x; j0 < tile.nm1; j0 += kProbeBlock * kFilterUnroll) {
-        unsigned long long k[kFilterUnroll];
-#pragma unroll
-        for (int u = 0; u < kFilterUnroll; ++u) {
-            const int j = j0 + u * kProbeBlock;
-            k[u] = j < tile.nm1 ? __ldg(a.csr_key + j) : 0ull;
-        }
-#pragma unroll
-        for (int u = 0; u < kFilterUnroll; ++u)
-            if (j0 + u * kProbeBlock < tile.nm1) atomicOr(s_bm + bloom_word(k[u], bmw), bloom_bits(k[u]));
-    }
-    dbg_mark(a, 0, 2);
-    // ---- the claims: first batch's answers, then any further batches (dense callsets) ----
-    if (consumer) {
-        for (int jb = tile.ins0 + (int)threadIdx.x;;) {
-            bool fresh = false;                                  // ipend's CAS of this round already issued above
-            while (ipend) {
-                if (fresh) {
-#pragma unroll
-                    for (int u = 0; u < kInsertUnroll; ++u)
-                        if (ipend >> u & 1u) iprev[u] = atomicCAS(&a.tab[ibase[u] + ip[u]].key, kEmptyKey, ikey[u]);
-                }
-                fresh = true;
-#pragma unroll
-                for (int u = 0; u < kInsertUnroll; ++u) {
-                    if (!(ipend >> u & 1u)) continue;
-                    const int j = jb + u * kProbeThreads;
-                    Slot *sl = a.tab + ibase[u] + ip[u];
-                    if (iprev[u] == kEmptyKey) { sl->first = j; a.next[j] = -2 - (ibase[u] + (int)ip[u]); ipend &= ~(1u << u); }
-                    else if (iprev[u] == ikey[u]) { a.next[j] = atomicExch(&sl->head, j); ipend &= ~(1u << u); }
-                    else ip[u] = (ip[u] + 1) & imask[u];
-                }
-            }
-            jb += kProbeThreads * kInsertUnroll;
-            if (jb >= tile.ins1) break;
-#pragma unroll
-            for (int u = 0; u < kInsertUnroll; ++u) {
-                const int j = jb + u * kProbeThreads;
-                ikey[u] = j < tile.ins1 ? __ldcs(a.csr_key + j) : 0ull;
-            }
-#pragma unroll
-            for (int u = 0; u < kInsertUnroll; ++u) {
-                const int j = jb + u * kProbeThreads;
-                if (j >= tile.ins1) continue;
-                int sh = tile.ins_lo;
-                if (tile.ins_lo != tile.ins_hi) sh += shard_of(a.join_off + tile.ins_lo, tile.ins_hi - tile.ins_lo + 1, j);
-                ibase[u] = __ldg(a.tab_off + sh); imask[u] = (unsigned)__ldg(a.tab_mask + sh);
-                a.join_row[j] = -1;
-                ip[u] = slot_hash(ikey[u]) & imask[u];
-                ipend |= 1u << u;
-            }
-#pragma unroll
-            for (int u = 0; u < kInsertUnroll; ++u)
-                if (ipend >> u & 1u) iprev[u] = atomicCAS(&a.tab[ibase[u] + ip[u]].key, kEmptyKey, ikey[u]);
-        }
-    }
-    dbg_mark(a, 0, 3);
-    __syncthreads();
-    dbg_mark(a, 0, 4);
+    dbg_mark(a, 1, 1);
     if (threadIdx.x >= kProbeThreads) {
         // producer warp: refill a stage as soon as every consumer warp has handed it back.  The wait is
         // warp-uniform (all 32 lanes spin together), one lane issues the copy.
@@ -458,116 +467,82 @@ k_scan(PhaseArgs a) {
             }
             __syncwarp();
         }
-        return;
-    }
-    // consumer warps.  Rows are numbered inside the tile: local row lr <-> row 2*q0 + lr, valid in [lr0, lr1).
-    const int row_base = (int)(2 * q0);
-    const int lr0 = (int)(r0 - 2 * q0), lr1 = (int)(r1 - 2 * q0);
-    unsigned long long *out_key = a.cand_key + r0;               // this block's private stretch of the list
-    int *out_row = a.cand_row + r0;
-    const Slot *tab = a.tab + tile.base;
-    const unsigned mask = (unsigned)tile.mask;
-    for (int t = 0; t < n_tiles; ++t) {
-        const int stage = t % kProbeStages;
-        const unsigned parity = (unsigned)(t / kProbeStages) & 1u;
-        const long long qt = q0 + (long long)t * kProbeBatch;
-        mbar_wait(&s_full[stage], parity);                       // the tile's bytes have landed
-        unsigned long long key[kProbeRows];
+    } else {
+        // consumer warps.  Rows are numbered inside the tile: local row lr <-> row 2*q0 + lr, valid in [lr0, lr1).
+        const int row_base = (int)(2 * q0);
+        const int lr0 = (int)(r0 - 2 * q0), lr1 = (int)(r1 - 2 * q0);
+        ulonglong2 *out = a.cand_list + r0;                      // this block's private stretch of the list
+        mbar_wait(&s_bm_full, 0);                                // the filter has landed
+        dbg_mark(a, 1, 2);
+        for (int t = 0; t < n_tiles; ++t) {
+            const int stage = t % kProbeStages;
+            const unsigned parity = (unsigned)(t / kProbeStages) & 1u;
+            const long long qt = q0 + (long long)t * kProbeBatch;
+            mbar_wait(&s_full[stage], parity);                   // the tile's bytes have landed
+            unsigned long long key[kProbeRows];
 #pragma unroll
-        for (int u = 0; u < kProbeUnroll; ++u) {
-            const long long qq = qt + (long long)u * kProbeThreads + threadIdx.x;
-            ulonglong2 v = make_ulonglong2(0ull, 0ull);
-            if (qq < q_full) v = ring[(size_t)stage * kProbeBatch + u * kProbeThreads + threadIdx.x];
-            else if (qq < q1) v.x = __ldcs(a.read_key + 2 * qq);                       // the column's odd last row
-            key[2 * u] = v.x; key[2 * u + 1] = v.y;
-        }
-        const int lr_t = 2 * (t * kProbeBatch + (int)threadIdx.x);                    // local row of key[0]
-        unsigned pass = 0;
-#pragma unroll
-        for (int u = 0; u < kProbeRows; ++u) {
-            const int lr = lr_t + (u >> 1) * (2 * kProbeThreads) + (u & 1);
-            const unsigned m = bloom_bits(key[u]);
-            if (lr >= lr0 && lr < lr1 && (s_bm[bloom_word(key[u], bmw)] & m) == m) pass |= 1u << u;
-        }
-        // rows that passed the filter go to the candidate list: one shared-memory atomic per warp
-        const int cnt = __popc(pass);
-        int inc = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int x = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += x;
-        }
-        // Hand the stage back only HERE: the scan has consumed every lane's filter result, so every lane's
-        // ring loads have returned their data.  An arrive placed right after the loads is issued while they
-        // are still in flight (nothing waits on their scoreboard) and the refill can overtake them
-        // (measured in round 1: a warp read the tile three ahead, lost joins).
-        if (lane == 0) mbar_arrive(&s_empty[stage]);
-        int wbase = 0;
-        if (lane == 31 && inc) wbase = atomicAdd(&s_count, inc);
-        int pos = __shfl_sync(0xffffffffu, wbase, 31) + inc - cnt;
-#pragma unroll
-        for (int u = 0; u < kProbeRows; ++u)
-            if (pass >> u & 1u) {
-                const int row = row_base + lr_t + (u >> 1) * (2 * kProbeThreads) + (u & 1);
-                out_key[pos] = key[u];
-                out_row[pos] = row;
-                ++pos;
-                // what k_probe and k_reduce will want from HBM at random -- the candidate's slot and the row's
-                // tag record -- starts moving into L2 now, under the stream
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(tab + (slot_hash(key[u]) & mask)));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.read_tag + row));
+            for (int u = 0; u < kProbeUnroll; ++u) {
+                const long long qq = qt + (long long)u * kProbeThreads + threadIdx.x;
+                ulonglong2 v = make_ulonglong2(0ull, 0ull);
+                if (qq < q_full) v = ring[(size_t)stage * kProbeBatch + u * kProbeThreads + threadIdx.x];
+                else if (qq < q1) v.x = __ldcs(a.read_key + 2 * qq);                   // the column's odd last row
+                key[2 * u] = v.x; key[2 * u + 1] = v.y;
             }
+            const int lr_t = 2 * (t * kProbeBatch + (int)threadIdx.x);                // local row of key[0]
+            unsigned pass = 0;
+#pragma unroll
+            for (int u = 0; u < kProbeRows; ++u) {
+                const int lr = lr_t + (u >> 1) * (2 * kProbeThreads) + (u & 1);
+                const unsigned m = bloom_bits(key[u]);
+                if (lr >= lr0 && lr < lr1 && (s_bm[bloom_word(key[u], bmw)] & m) == m) pass |= 1u << u;
+            }
+            // rows that passed the filter go to the candidate list: one shared-memory atomic per warp
+            const int cnt = __popc(pass);
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int x = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += x;
+            }
+            // Hand the stage back only HERE: the scan has consumed every lane's filter result, so every lane's
+            // ring loads have returned their data.  An arrive placed right after the loads is issued while they
+            // are still in flight (nothing waits on their scoreboard) and the refill can overtake them
+            // (measured in round 1: a warp read the tile three ahead, lost joins).
+            if (lane == 0) mbar_arrive(&s_empty[stage]);
+            int wbase = 0;
+            if (lane == 31 && inc) wbase = atomicAdd(&s_count, inc);
+            int pos = __shfl_sync(0xffffffffu, wbase, 31) + inc - cnt;
+#pragma unroll
+            for (int u = 0; u < kProbeRows; ++u)
+                if (pass >> u & 1u) {
+                    const int row = row_base + lr_t + (u >> 1) * (2 * kProbeThreads) + (u & 1);
+                    out[pos++] = make_ulonglong2(key[u], (unsigned long long)(unsigned)row);
+                    // what k_reduce will want from HBM at random -- the row's tag record -- starts moving into
+                    // L2 now, under the stream
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.read_tag + row));
+                }
+        }
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(kProbeThreads) : "memory");      // the consumer warps (the producer has left)
-    if (threadIdx.x == 0) a.cand_n[blockIdx.x] = s_count;
-    dbg_mark(a, 0, 5);
-}
-
-// ------------------------------------------------------------------------------------------
-// k_probe: block t resolves the candidates tile t of k_scan left behind, kResolveUnroll per thread in
-// flight: one 16-byte slot load decides (lock-step rounds on collisions); a hit pushes the row index to
-// every support-read entry of that name with atomicMax -- a later row overrides an earlier one
-// (sv_phasing_fn.py:29).  Slots and tag records were requested into L2 by k_scan when the candidate was found.
-// While it waits for k_scan its blocks warm L2 with the input columns k_reduce and k_tail start from
-// (nobody has touched them yet in this call).
-// Dependent chain after the wait: [count] -> candidate (L2, written by k_scan) -> slot -> atomics.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warm_l2(const void *p, size_t bytes, long long tid, long long n_threads) {
-    const char *c = reinterpret_cast<const char *>(p);
-    const long long lines = (long long)((bytes + 127) >> 7);
-    for (long long i = tid; i < lines; i += n_threads) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + (i << 7)));
-}
-
-__global__ void __launch_bounds__(kProbeThreads)
-k_probe(PhaseArgs a) {
-    dbg_mark(a, 1, 0);
-    const ScanTile tile = a.scan_tiles[blockIdx.x];
-    if (!(a.flags & kFlagNoWarm)) {
-        const long long tid = (long long)blockIdx.x * kProbeThreads + threadIdx.x, nt = (long long)gridDim.x * kProbeThreads;
-        const size_t S = (size_t)a.n_svs, J = (size_t)a.n_joins;
-        warm_l2(a.csr_off, (S + 1) * 8, tid, nt);
-        if (a.csr_chk) warm_l2(a.csr_chk, J * 4, tid, nt);
-        warm_l2(a.sv_svlen, S * 4, tid, nt); warm_l2(a.sv_svread, S * 4, tid, nt); warm_l2(a.sv_flags, S, tid, nt);
-        warm_l2(a.sv_pos, S * 4, tid, nt); warm_l2(a.sv_refread, S * 4, tid, nt);
-        if (a.sv_group) warm_l2(a.sv_group, S * 4, tid, nt);
-    }
-    pdl_trigger();
-    pdl_wait();                                                  // k_scan is done: every name has its slot, the lists are final
-    const int total = __ldcg(a.cand_n + blockIdx.x);
-    const unsigned long long *q_key = a.cand_key + tile.r0;
-    const int *q_row = a.cand_row + tile.r0;
+    __syncthreads();
+    dbg_mark(a, 1, 3);
+    // Resolve the block's candidates (all 17 warps): one 16-byte slot load decides; a hit pushes the row
+    // index to every support-read entry of that name with atomicMax -- a later row overrides an earlier
+    // one (sv_phasing_fn.py:29).
+    // Dependent chain: candidate (L2, written by this block) -> slot (L2: k_init swept it) -> atomics.
+    const int total = s_count;
+    const ulonglong2 *q_cand = a.cand_list + r0;
     const Slot *tab = a.tab + tile.base;
     const unsigned mask = (unsigned)tile.mask;
-    for (int g0 = threadIdx.x; g0 < total; g0 += kProbeThreads * kResolveUnroll) {
+    for (int g0 = threadIdx.x; g0 < total; g0 += kProbeBlock * kResolveUnroll) {
         unsigned long long key[kResolveUnroll];
         int row[kResolveUnroll];
         unsigned p[kResolveUnroll];
         unsigned pend = 0;
 #pragma unroll
         for (int u = 0; u < kResolveUnroll; ++u) {
-            const int g = g0 + u * kProbeThreads;
+            const int g = g0 + u * kProbeBlock;
             key[u] = 0ull; row[u] = 0;
-            if (g < total) { key[u] = __ldcg(q_key + g); row[u] = __ldcg(q_row + g); pend |= 1u << u; }
+            if (g < total) { const ulonglong2 c = __ldcg(q_cand + g); key[u] = c.x; row[u] = (int)c.y; pend |= 1u << u; }
         }
 #pragma unroll
         for (int u = 0; u < kResolveUnroll; ++u) p[u] = slot_hash(key[u]) & mask;
@@ -592,7 +567,7 @@ k_probe(PhaseArgs a) {
             }
         }
     }
-    dbg_mark(a, 1, 1);
+    dbg_mark(a, 1, 4);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -823,17 +798,12 @@ k_reduce(PhaseArgs a) {
     int row[kReduceUnroll], ps[kReduceUnroll], pc[kReduceUnroll], hp[kReduceUnroll];
     for (long long base = b; base < e; base += G * kReduceUnroll) {
         unsigned want[kReduceUnroll];
-        int own[kReduceUnroll];
 #pragma unroll
         for (int u = 0; u < kReduceUnroll; ++u) {
             const long long j = base + u * G + lane;
             row[u] = j < e ? __ldcg(a.join_row + j) : -1;
             want[u] = j < e && a.csr_chk ? __ldg(a.csr_chk + j) : 0u;
-            own[u] = j < e ? __ldcg(a.next + j) : 0;
         }
-#pragma unroll
-        for (int u = 0; u < kReduceUnroll; ++u)                  // entries that claimed a slot hand it back free
-            if (own[u] <= -2 && !(a.flags & kFlagNoSlotFree)) reinterpret_cast<uint4 *>(a.tab)[-2 - own[u]] = make_uint4(~0u, ~0u, ~0u, ~0u);
 #pragma unroll
         for (int u = 0; u < kReduceUnroll; ++u) {
             ps[u] = pc[u] = hp[u] = 0;

@@ -127,7 +127,7 @@ typedef struct duet_phase_input {
     const uint8_t *sv_flags;     /* [S] DUET_SV_* bits                                           */
     const int32_t *sv_group;     /* [S] or NULL: rank of the SV's CHROM string inside its shard  */
     const int64_t *csr_off;      /* [S+1]                                                        */
-    const uint64_t *csr_key;     /* [J]                                                          */
+    const uint64_t *csr_key;     /* [J] 16-byte aligned (streamed with bulk copies, like read_key) */
     const uint32_t *csr_chk;     /* [J] check word of each support-read name, or NULL            */
 } duet_phase_input;
 
@@ -157,9 +157,9 @@ typedef struct duet_timings {
     float h2d_ms;          /* upload: host -> device copies                       */
     float device_ms;       /* all kernels of one execute                          */
     float d2h_ms;          /* download                                            */
-    float kernel_ms[8];    /* build (k_scan: slots claimed + read stream filtered), probe, reduce, tail (k_tail: the three per-contig steps in one
-                              cluster launch), oneps, predict, order (the same steps as separate kernels, only
-                              when a contig has more SVs than a cluster holds), unused */
+    float kernel_ms[8];    /* build (k_init + k_table), probe, reduce, tail (k_tail: the three per-contig steps
+                              in one cluster launch), oneps, predict, order (the same steps as separate kernels,
+                              only when a contig has more SVs than a cluster holds), unused */
 } duet_timings;
 
 typedef struct duet_handle duet_handle;
@@ -197,7 +197,7 @@ int duet_sync(duet_handle *h);
 
 /* Developer instrumentation: with `enable` != 0 the kernels launched after the next upload stamp
  * (globaltimer ns, SM clock) per block at up to 8 marks; `out` (may be NULL) receives the stamps of
- * the last execute as int64[4 kernels: k_scan, k_probe, k_reduce, k_tail][2048 blocks][8 marks][2].
+ * the last execute as int64[4 kernels: k_table, k_probe, k_reduce, k_tail][2048 blocks][8 marks][2].
  * Off by default: costs nothing. */
 int duet_debug_timers(duet_handle *h, int enable, int64_t *out);
 

@@ -262,3 +262,41 @@ def test_bam_reader_text_quirks(tmp_path):
     assert b.hp.tolist() == [2, 7, 2] and b.pc.tolist() == [30, 5, 1] and b.ps.tolist() == [400, 6, 3]
     assert np.array_equal(a.key, b.key) and np.array_equal(a.tag, b.tag)
     assert a.n_lines == b.n_lines == 6
+
+
+# ---- a BAM laid out byte by byte from the SAM/BAM specification (not by tests/util_bam.py) ---------------
+def test_bam_reader_on_spec_laid_out_fixture():
+    """tests/golden/spec_example.bam was assembled field by field from SAMv1 sections 4.1 / 4.2 by
+    tests/golden/make_spec_bam.py (the specification's own example alignments r001-r003 plus HP/PC/PS
+    tags; one BGZF block is a hand-written STORED deflate block, records straddle block boundaries, every
+    aux type appears, the 28-byte EOF marker is the spec's literal).  Python's gzip module -- a third
+    party to both writer and reader -- must inflate it, and the native reader must keep exactly the rows
+    the reference keeps from the `samtools view` text of the same records (spec_example.sam)."""
+    import gzip
+    import os
+    from conftest import GOLDEN
+    from duet_b200.namehash import hash128
+    with open(os.path.join(GOLDEN, "spec_example.bam"), "rb") as f:
+        data = f.read()
+    raw = gzip.decompress(data)                                 # checks every member's CRC32 and ISIZE
+    assert raw[:4] == b"BAM\x01" and data.endswith(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+    got = sv_phasing_fn.decode_bam(data)
+    kept = [("r001", 1, 7, 60), ("r003", 2, 100000, 300), ("r001", 2, 7, 10), ("r005", 1, 42, -5)]   # (QNAME, HP, PS, PC)
+    assert got.n_lines == 6 and len(got) == len(kept)
+    for i, (nm, hp, ps, pc) in enumerate(kept):
+        lo, hi = hash128(nm)
+        assert int(got.key[i]) == lo and int(got.tag["chk"][i]) == hi & 0xFFFFFFFF
+        assert (int(got.hp[i]), int(got.ps[i]), int(got.pc[i])) == (hp, ps, pc)
+    with open(os.path.join(GOLDEN, "spec_example.sam"), "rb") as f:
+        text = f.read()
+    via_text = sv_phasing_fn.decode_sam_text(text)
+    assert np.array_equal(got.key, via_text.key) and np.array_equal(got.tag, via_text.tag)
+    # and the oracle port's reading of the same text (dict semantics: the later r001 row wins)
+    import tempfile
+    from oracle import ref_port
+    with tempfile.TemporaryDirectory() as home:
+        os.makedirs(os.path.join(home, "snp_phasing"))
+        with open(os.path.join(home, "snp_phasing", "1.bam"), "wb") as f:
+            f.write(text)
+        table = ref_port.haplotag_tables(home + "/snp_phasing/", 1, False)[0]
+    assert table == {"r001": (2, 7, 10), "r003": (2, 100000, 300), "r005": (1, 42, -5)}

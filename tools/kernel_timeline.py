@@ -31,7 +31,7 @@ def do_flush_now():
     if clean:
         flush2.sum()
 
-names = ["k_scan (thread 0 -- 1: CAS issued, 2: filter loop done, 3: claims done, 4: block barrier passed, 5: stream done)", "k_probe (1: end)", "k_reduce (1: gathered, 2: end)",
+names = ["k_table (1: k_init done, 2: end)", "k_probe (1: k_table done; 2: filter in shared memory; 3: stream done; 4: candidates resolved)", "k_reduce (1: gathered, 2: end)",
          "k_tail (1: candidates in the set, 2: contig list sorted, 3: decided, 4: order written)"]
 ref = None
 for flags in variants:
