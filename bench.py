@@ -53,7 +53,7 @@ WORKLOADS = {
 }
 CPU_SAMPLE_CONTIGS = ["17", "18", "19", "20", "21", "22"]      # 12.3 % of GRCh37: bounded CPU sample
 C3_N = 2_000_000
-C3_CPU_SAMPLE = 200_000
+C3_CPU_SAMPLE = C3_N          # the CPU restatement is vectorised numpy + scipy: the whole workload takes ~2 s
 KERNEL_LABEL = {"build": "k_init + k_table", "probe": "k_probe", "reduce": "k_reduce", "tail": "k_tail", "oneps": "k_oneps",
                 "predict": "k_predict", "order": "k_order"}
 
@@ -186,9 +186,9 @@ def cpu_cluster(n: int, repeats: int = 1) -> dict:
     best = float("inf")
     for _ in range(repeats):
         t0 = time.perf_counter()
-        ids = cluster_oracle.cluster(*cols)
+        _ids, n_clusters = cluster_oracle.cluster(*cols)
         best = min(best, time.perf_counter() - t0)
-    return {"seconds": best, "n": n, "n_clusters": int(np.unique(ids).shape[0])}
+    return {"seconds": best, "n": n, "n_clusters": int(n_clusters)}
 
 
 def run_reference_arm(args):
@@ -199,7 +199,7 @@ def run_reference_arm(args):
         n = C3_CPU_SAMPLE
         r = cpu_cluster(n, repeats=max(1, min(args.steps, 3)))
         val = n / r["seconds"]
-        desc = (f"first {n} of the {C3_N} signatures; oracle/cluster_oracle.py (numpy + scipy connected components) "
+        desc = (f"{n} of the {C3_N} signatures; oracle/cluster_oracle.py (numpy + scipy connected components) "
                 f"on 1 core; SVIM parity unpinned (svim 1.4.2 is external to the reference)")
         line = {"impl": "reference", "metric": METRIC_C3, "value": val, "unit": "signatures/s", "n_gpus": args.gpus,
                 "steps": max(1, min(args.steps, 3)), "warmup": 0, "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True,
@@ -487,7 +487,7 @@ def cluster_config_result(ctx: Ctx, eng, steps: int, warmup: int, with_cpu: bool
         r = cpu_cluster(C3_CPU_SAMPLE)
         rec["cpu_baseline"] = {"value": r["n"] / r["seconds"], "unit": "signatures/s", "cores": 1, "kind": "port",
                                "seconds": r["seconds"],
-                               "sample": f"first {r['n']} of the {n} signatures; oracle/cluster_oracle.py (numpy + scipy) on 1 core; "
+                               "sample": f"{r["n"]} of the {n} signatures; oracle/cluster_oracle.py (numpy + scipy) on 1 core; "
                                          "SVIM parity unpinned"}
     return rec
 

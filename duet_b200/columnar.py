@@ -29,6 +29,32 @@ def pack_tags(hp, ps, pc, hi=None) -> np.ndarray:
     return t
 
 
+class TextColumn:
+    """Strings of one per-SV text column (CHROM, REF, ALT, SVTYPE) kept as (offset, length) spans into the
+    VCF bytes and decoded on access -- only the rows that end up in phased_sv.vcf are ever materialised."""
+
+    def __init__(self, text, spans: np.ndarray, prefix: str = "", suffix: str = ""):
+        self.text, self.spans, self.prefix, self.suffix = text, spans, prefix, suffix      # spans: int64 [n, 2]
+
+    def __len__(self):
+        return int(self.spans.shape[0])
+
+    def _one(self, i: int) -> str:
+        o, n = int(self.spans[i, 0]), int(self.spans[i, 1])
+        return self.prefix + bytes(self.text[o:o + n]).decode("ascii") + self.suffix
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._one(k) for k in range(*i.indices(len(self)))]
+        return self._one(int(i))
+
+    def __iter__(self):
+        return (self._one(i) for i in range(len(self)))
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+
 @dataclass
 class PhaseBatch:
     # shard descriptors

@@ -18,6 +18,8 @@
 #include <atomic>
 #include <string>
 #include <thread>
+#include <algorithm>
+#include <new>
 #include <vector>
 
 #include "../../include/duet_b200.h"
@@ -32,64 +34,49 @@ inline uint16_t rd16(const unsigned char *p) { uint16_t v; std::memcpy(&v, p, 2)
 // ---- BGZF ---------------------------------------------------------------------------------------
 std::atomic<int> g_inflate_threads{1};                        // duet_set_decode_threads
 
-// one BGZF block (a raw-deflate member with its own ISIZE) -> its slice of the output
-bool inflate_block(const unsigned char *blk, int64_t bsize, unsigned char *dst) {
+constexpr uint32_t kBgzfMaxIsize = 1u << 16;                  // a BGZF block inflates to at most 64 KiB (SAMv1 4.1)
+constexpr size_t kBatchBytes = 16u << 20;                     // inflated bytes walked per batch: bounds the memory
+
+struct Block { int64_t off; int32_t bsize; uint32_t isize; };
+
+// The header of the BGZF block at `pos`: total size and inflated size.  Every length is checked against the
+// end of the input before it is used.
+int read_block_header(const unsigned char *data, int64_t len, int64_t pos, Block *out) {
+    if (len - pos < 18 || data[pos] != 31 || data[pos + 1] != 139 || data[pos + 2] != 8 || !(data[pos + 3] & 4))
+        return DUET_DECODE_ERR_FORMAT;
+    const int xlen = rd16(data + pos + 10);
+    if (pos + 12 + xlen > len) return DUET_DECODE_ERR_FORMAT;
+    int64_t x = pos + 12;
+    const int64_t xend = x + xlen;
+    int bsize = -1;
+    while (x + 4 <= xend) {
+        const int slen = rd16(data + x + 2);
+        if (x + 4 + slen > xend) return DUET_DECODE_ERR_FORMAT;
+        if (data[x] == 'B' && data[x + 1] == 'C' && slen == 2) bsize = rd16(data + x + 4) + 1;
+        x += 4 + slen;
+    }
+    if (bsize < 0 || pos + bsize > len || bsize < xlen + 20) return DUET_DECODE_ERR_FORMAT;
+    const uint32_t isize = rd32(data + pos + bsize - 4);
+    if (isize > kBgzfMaxIsize) return DUET_DECODE_ERR_FORMAT;   // a forged ISIZE must not size a buffer
+    out->off = pos; out->bsize = bsize; out->isize = isize;
+    return DUET_OK;
+}
+
+// one BGZF block (a raw-deflate member with its own ISIZE) -> its slice of the batch buffer
+bool inflate_block(const unsigned char *data, const Block &b, unsigned char *dst) {
+    if (b.isize == 0) return true;
+    const unsigned char *blk = data + b.off;
     const int xlen = rd16(blk + 10);
-    const uint32_t isize = rd32(blk + bsize - 4);
-    if (isize == 0) return true;
     z_stream zs;
     std::memset(&zs, 0, sizeof(zs));
     if (inflateInit2(&zs, -15) != Z_OK) return false;
     zs.next_in = const_cast<unsigned char *>(blk + 12 + xlen);
-    zs.avail_in = (uInt)(bsize - xlen - 20);
+    zs.avail_in = (uInt)(b.bsize - xlen - 20);
     zs.next_out = dst;
-    zs.avail_out = isize;
+    zs.avail_out = b.isize;
     const int rc = inflate(&zs, Z_FINISH);
     inflateEnd(&zs);
     return rc == Z_STREAM_END && zs.avail_out == 0;
-}
-
-int inflate_bgzf(const unsigned char *data, int64_t len, std::vector<unsigned char> &out) {
-    int64_t pos = 0;
-    size_t total = 0;
-    // first pass: sizes (every block states its own compressed and uncompressed size, so the blocks can
-    // be inflated independently, each into its own slice of the output)
-    std::vector<std::pair<int64_t, int64_t>> blocks;          // (offset, block size)
-    std::vector<size_t> dst_off;
-    while (pos < len) {
-        if (len - pos < 18 || data[pos] != 31 || data[pos + 1] != 139 || data[pos + 2] != 8 || !(data[pos + 3] & 4))
-            return DUET_DECODE_ERR_FORMAT;
-        const int xlen = rd16(data + pos + 10);
-        int64_t x = pos + 12, xend = x + xlen;
-        int bsize = -1;
-        while (x + 4 <= xend) {
-            const int slen = rd16(data + x + 2);
-            if (data[x] == 'B' && data[x + 1] == 'C' && slen == 2) bsize = rd16(data + x + 4) + 1;
-            x += 4 + slen;
-        }
-        if (bsize < 0 || pos + bsize > len || bsize < xlen + 20) return DUET_DECODE_ERR_FORMAT;
-        dst_off.push_back(total);
-        total += rd32(data + pos + bsize - 4);
-        blocks.emplace_back(pos, bsize);
-        pos += bsize;
-    }
-    out.resize(total);
-    const int n_thr = (int)std::min<size_t>((size_t)std::max(1, g_inflate_threads.load()), blocks.size() / 16 + 1);
-    if (n_thr > 1) {                                          // contiguous runs of blocks per worker
-        std::atomic<bool> ok{true};
-        std::vector<std::thread> pool;
-        for (int t = 0; t < n_thr; ++t)
-            pool.emplace_back([&, t] {
-                const size_t b0 = blocks.size() * (size_t)t / n_thr, b1 = blocks.size() * (size_t)(t + 1) / n_thr;
-                for (size_t i = b0; i < b1 && ok.load(std::memory_order_relaxed); ++i)
-                    if (!inflate_block(data + blocks[i].first, blocks[i].second, out.data() + dst_off[i])) ok = false;
-            });
-        for (auto &th : pool) th.join();
-        return ok ? (int)DUET_OK : (int)DUET_DECODE_ERR_FORMAT;
-    }
-    for (size_t i = 0; i < blocks.size(); ++i)
-        if (!inflate_block(data + blocks[i].first, blocks[i].second, out.data() + dst_off[i])) return DUET_DECODE_ERR_FORMAT;
-    return DUET_OK;
 }
 
 // ---- text rendering of one aux field, as `samtools view` prints it ---------------------------------
@@ -189,48 +176,39 @@ bool parse_int(const char *p, const char *e, long long *out, bool *overflow) {
     return true;
 }
 
-}  // namespace
-
-extern "C" {
-
-void duet_free(void *p) { std::free(p); }
-
-int duet_set_decode_threads(int n) {
-    return g_inflate_threads.exchange(n < 1 ? 1 : n);
-}
-
-int duet_decode_bam(const unsigned char *data, int64_t len, uint64_t **key_out, duet_read_tag **tag_out,
-                    int64_t *n_rows, int64_t *n_records, int64_t *err_record) {
-    *key_out = nullptr; *tag_out = nullptr; *n_rows = 0; *n_records = 0; *err_record = -1;
-    std::vector<unsigned char> raw;
-    int rc = inflate_bgzf(data, len, raw);
-    if (rc != DUET_OK) return rc;
-    const unsigned char *p = raw.data(), *end = p + raw.size();
-    if (end - p < 12 || std::memcmp(p, "BAM\1", 4) != 0) return DUET_DECODE_ERR_FORMAT;
-    const uint32_t l_text = rd32(p + 4);
-    p += 8;
-    if ((size_t)(end - p) < (size_t)l_text + 4) return DUET_DECODE_ERR_FORMAT;
-    p += l_text;
-    const uint32_t n_ref = rd32(p);
-    p += 4;
-    for (uint32_t r = 0; r < n_ref; ++r) {
-        if (end - p < 4) return DUET_DECODE_ERR_FORMAT;
-        const uint32_t l_name = rd32(p);
-        if ((size_t)(end - p) < (size_t)l_name + 8) return DUET_DECODE_ERR_FORMAT;
-        p += 4 + l_name + 4;
-    }
+// ---- the record walk, fed batch by batch ------------------------------------------------------------
+// State of one file's walk: where in the BAM layout the stream is (magic, header text, reference list,
+// alignments), what has been kept so far.  feed() consumes whole items and reports how far it got; the
+// caller carries the rest over to the next batch, so memory is bounded by a batch plus one record.
+struct BamWalker {
+    enum { MAGIC, TEXT, NREF, REFS, RECORDS } state = MAGIC;
+    uint64_t skip = 0;                 // bytes of header text still to pass over
+    uint32_t refs_left = 0;
+    int64_t rec = 0;                   // alignments seen
+    int err = DUET_OK;
     std::vector<uint64_t> keys;
     std::vector<duet_read_tag> tags;
+    // scratch of the general (text) path
     std::vector<const unsigned char *> aux;
     std::vector<Tok> toks;
     std::string tail, piece;
-    int64_t rec = 0;
-    auto bail = [&](int code) { *err_record = rec; return code; };
-    while (p < end) {
-        if (end - p < 4) return bail(DUET_DECODE_ERR_FORMAT);
-        const uint32_t bs = rd32(p);
-        const unsigned char *r = p + 4, *rend = r + bs;
-        if (bs < 32 || rend > end) return bail(DUET_DECODE_ERR_FORMAT);
+
+    bool keep(const unsigned char *name, size_t nl, long long hp, long long pc, long long ps) {
+        if (hp < 0 || hp > 255 || pc < INT32_MIN || pc > INT32_MAX || ps < INT32_MIN || ps > INT32_MAX) { err = DUET_DECODE_ERR_RANGE; return false; }
+        for (size_t i = 0; i < nl; ++i) if (name[i] >= 0x80) { err = DUET_DECODE_ERR_ASCII; return false; }
+        const int64_t off[2] = {0, (int64_t)nl};
+        uint64_t lo, hi;
+        duet_hash_names(reinterpret_cast<const char *>(name), off, 1, &lo, &hi);
+        duet_read_tag t;
+        std::memset(&t, 0, sizeof(t));
+        t.hp = (uint8_t)hp; t.pc = (int32_t)pc; t.ps = (int32_t)ps; t.chk = (uint32_t)hi;
+        keys.push_back(lo);
+        tags.push_back(t);
+        return true;
+    }
+
+    // one complete alignment record [r, rend): the reference's rule on its last three text tokens
+    bool record(const unsigned char *r, const unsigned char *rend) {
         const unsigned l_read_name = r[8];
         const unsigned n_cigar = rd16(r + 12);
         const uint32_t l_seq = rd32(r + 16);
@@ -238,13 +216,13 @@ int duet_decode_bam(const unsigned char *data, int64_t len, uint64_t **key_out, 
         const unsigned char *name = r + 32;
         const unsigned char *cigar = name + l_read_name;
         const unsigned char *seq = cigar + 4ull * n_cigar;
-        const unsigned char *qual = seq + (l_seq + 1) / 2;
+        const unsigned char *qual = seq + ((uint64_t)l_seq + 1) / 2;
         const unsigned char *ax = qual + l_seq;
-        if (ax > rend || l_read_name == 0) return bail(DUET_DECODE_ERR_FORMAT);
+        if (ax > rend || ax < r || l_read_name == 0) { err = DUET_DECODE_ERR_FORMAT; return false; }
         aux.clear();
         for (const unsigned char *q = ax; q < rend;) {
             const size_t sz = aux_size(q, rend);
-            if (!sz) return bail(DUET_DECODE_ERR_FORMAT);
+            if (!sz) { err = DUET_DECODE_ERR_FORMAT; return false; }
             aux.push_back(q);
             q += sz;
         }
@@ -263,24 +241,9 @@ int duet_decode_bam(const unsigned char *data, int64_t len, uint64_t **key_out, 
             }
         };
         if (na >= 3 && is_int(aux[na - 1]) && is_int(aux[na - 2]) && is_int(aux[na - 3])) {
-            if (aux[na - 2][0] == 'P' && aux[na - 2][1] == 'C') {      // "PC:i:" can only sit at the start of "XX:i:<digits>"
-                const long long v0 = int_of(aux[na - 3]), v1 = int_of(aux[na - 2]), v2 = int_of(aux[na - 1]);
-                if (v0 < 0 || v0 > 255 || v1 < INT32_MIN || v1 > INT32_MAX || v2 < INT32_MIN || v2 > INT32_MAX)
-                    return bail(DUET_DECODE_ERR_RANGE);
-                const size_t nl = l_read_name - 1;
-                for (size_t i = 0; i < nl; ++i) if (name[i] >= 0x80) return bail(DUET_DECODE_ERR_ASCII);
-                const int64_t off[2] = {0, (int64_t)nl};
-                uint64_t lo, hi;
-                duet_hash_names(reinterpret_cast<const char *>(name), off, 1, &lo, &hi);
-                duet_read_tag t;
-                std::memset(&t, 0, sizeof(t));
-                t.hp = (uint8_t)v0; t.pc = (int32_t)v1; t.ps = (int32_t)v2; t.chk = (uint32_t)hi;
-                keys.push_back(lo);
-                tags.push_back(t);
-            }
-            ++rec;
-            p = rend;
-            continue;
+            if (aux[na - 2][0] == 'P' && aux[na - 2][1] == 'C')      // "PC:i:" can only sit at the start of "XX:i:<digits>"
+                return keep(name, l_read_name - 1, int_of(aux[na - 3]), int_of(aux[na - 2]), int_of(aux[na - 1]));
+            return true;
         }
         // general path: last three whitespace tokens of the text line, built from the end backwards
         tail.clear();
@@ -309,42 +272,195 @@ int duet_decode_bam(const unsigned char *data, int64_t len, uint64_t **key_out, 
             pieces.push_back(piece);
         }
         for (int i = (int)pieces.size() - 1; i >= 0; --i) { tail += pieces[i]; tail.push_back('\t'); }
-        for (char c : tail) if ((unsigned char)c >= 0x80) return bail(DUET_DECODE_ERR_ASCII);
+        for (char c : tail) if ((unsigned char)c >= 0x80) { err = DUET_DECODE_ERR_ASCII; return false; }
         tokenize(tail, toks);
         const size_t nt = toks.size();
-        if (nt < 3) return bail(DUET_DECODE_ERR_FORMAT);
+        if (nt < 3) { err = DUET_DECODE_ERR_FORMAT; return false; }
         const Tok t3 = toks[nt - 3], t2 = toks[nt - 2], t1 = toks[nt - 1];
-        if (tail.substr(t2.b, t2.e - t2.b).find("PC:i:") != std::string::npos) {
-            const Tok tk[3] = {t3, t2, t1};
-            long long v[3];
-            for (int k = 0; k < 3; ++k) {
-                bool ovf;
-                const size_t b = tk[k].b + 5 <= tk[k].e ? tk[k].b + 5 : tk[k].e;
-                if (!parse_int(tail.data() + b, tail.data() + tk[k].e, &v[k], &ovf)) return bail(DUET_DECODE_ERR_VALUE);
-                if (ovf) return bail(DUET_DECODE_ERR_RANGE);
-            }
-            if (v[0] < 0 || v[0] > 255 || v[1] < INT32_MIN || v[1] > INT32_MAX || v[2] < INT32_MIN || v[2] > INT32_MAX)
-                return bail(DUET_DECODE_ERR_RANGE);
-            size_t nl = l_read_name - 1;                          // QNAME is NUL terminated
-            for (size_t i = 0; i < nl; ++i) if (name[i] >= 0x80) return bail(DUET_DECODE_ERR_ASCII);
-            const int64_t off[2] = {0, (int64_t)nl};
-            uint64_t lo, hi;
-            duet_hash_names(reinterpret_cast<const char *>(name), off, 1, &lo, &hi);
-            duet_read_tag t;
-            std::memset(&t, 0, sizeof(t));
-            t.hp = (uint8_t)v[0]; t.pc = (int32_t)v[1]; t.ps = (int32_t)v[2]; t.chk = (uint32_t)hi;
-            keys.push_back(lo);
-            tags.push_back(t);
+        if (tail.substr(t2.b, t2.e - t2.b).find("PC:i:") == std::string::npos) return true;
+        const Tok tk[3] = {t3, t2, t1};
+        long long v[3];
+        for (int k = 0; k < 3; ++k) {
+            bool ovf;
+            const size_t b = tk[k].b + 5 <= tk[k].e ? tk[k].b + 5 : tk[k].e;
+            if (!parse_int(tail.data() + b, tail.data() + tk[k].e, &v[k], &ovf)) { err = DUET_DECODE_ERR_VALUE; return false; }
+            if (ovf) { err = DUET_DECODE_ERR_RANGE; return false; }
         }
-        ++rec;
-        p = rend;
+        return keep(name, l_read_name - 1, v[0], v[1], v[2]);
     }
-    const size_t n = keys.size();
+
+    // consume what is complete in [p, end); returns the first byte not consumed (nullptr on error: see err)
+    const unsigned char *feed(const unsigned char *p, const unsigned char *end) {
+        for (;;) {
+            switch (state) {
+                case MAGIC:
+                    if (end - p < 8) return p;
+                    if (std::memcmp(p, "BAM\1", 4) != 0) { err = DUET_DECODE_ERR_FORMAT; return nullptr; }
+                    skip = rd32(p + 4);
+                    p += 8;
+                    state = TEXT;
+                    break;
+                case TEXT: {
+                    const uint64_t n = std::min<uint64_t>(skip, (uint64_t)(end - p));
+                    p += n; skip -= n;
+                    if (skip) return p;
+                    state = NREF;
+                    break;
+                }
+                case NREF:
+                    if (end - p < 4) return p;
+                    refs_left = rd32(p);
+                    p += 4;
+                    state = REFS;
+                    break;
+                case REFS:
+                    while (refs_left) {
+                        if (end - p < 4) return p;
+                        const uint64_t l_name = rd32(p);
+                        if ((uint64_t)(end - p) < 4 + l_name + 4) {
+                            if (l_name > (1u << 20)) { err = DUET_DECODE_ERR_FORMAT; return nullptr; }   // no reference name is a megabyte long
+                            return p;
+                        }
+                        p += 4 + l_name + 4;
+                        --refs_left;
+                    }
+                    state = RECORDS;
+                    break;
+                case RECORDS:
+                    for (;;) {
+                        if (end - p < 4) return p;
+                        const uint32_t bs = rd32(p);
+                        if (bs < 32 || bs > (1u << 30)) { err = DUET_DECODE_ERR_FORMAT; return nullptr; }
+                        if ((uint64_t)(end - p) < 4ull + bs) return p;
+                        if (!record(p + 4, p + 4 + bs)) return nullptr;
+                        ++rec;
+                        p += 4 + bs;
+                    }
+            }
+        }
+    }
+};
+
+// the whole file, batch by batch: at most kBatchBytes of inflated data (plus one record carried over) at a time
+int walk_bam(const unsigned char *data, int64_t len, BamWalker &w) {
+    std::vector<unsigned char> buf;                            // [carry | this batch's inflated blocks]
+    std::vector<Block> batch;
+    std::vector<size_t> dst;
+    size_t carry = 0;
+    int64_t pos = 0;
+    while (pos < len) {
+        batch.clear();
+        dst.clear();
+        size_t bytes = 0;
+        while (pos < len && bytes < kBatchBytes) {
+            Block b;
+            const int rc = read_block_header(data, len, pos, &b);
+            if (rc != DUET_OK) return rc;
+            dst.push_back(bytes);
+            bytes += b.isize;
+            batch.push_back(b);
+            pos += b.bsize;
+        }
+        buf.resize(carry + bytes);
+        unsigned char *base = buf.data() + carry;
+        const int n_thr = (int)std::min<size_t>((size_t)std::max(1, g_inflate_threads.load()), batch.size() / 16 + 1);
+        if (n_thr > 1) {                                      // contiguous runs of blocks per worker
+            std::atomic<bool> ok{true};
+            std::vector<std::thread> pool;
+            for (int t = 0; t < n_thr; ++t)
+                pool.emplace_back([&, t] {
+                    const size_t b0 = batch.size() * (size_t)t / n_thr, b1 = batch.size() * (size_t)(t + 1) / n_thr;
+                    for (size_t i = b0; i < b1 && ok.load(std::memory_order_relaxed); ++i)
+                        if (!inflate_block(data, batch[i], base + dst[i])) ok = false;
+                });
+            for (auto &th : pool) th.join();
+            if (!ok) return DUET_DECODE_ERR_FORMAT;
+        } else {
+            for (size_t i = 0; i < batch.size(); ++i)
+                if (!inflate_block(data, batch[i], base + dst[i])) return DUET_DECODE_ERR_FORMAT;
+        }
+        const unsigned char *end = buf.data() + buf.size();
+        const unsigned char *stop = w.feed(buf.data(), end);
+        if (!stop) return w.err;
+        carry = (size_t)(end - stop);
+        if (carry) std::memmove(buf.data(), stop, carry);
+    }
+    if (carry || w.state != BamWalker::RECORDS) return DUET_DECODE_ERR_FORMAT;     // truncated record / header
+    return DUET_OK;
+}
+
+}  // namespace
+
+// The kept rows of one haplotagged file, held by the library until the caller has made room for them
+// (duet_rows_take copies them straight into the caller's -- page-locked -- column slices).
+struct duet_rows {
+    std::vector<uint64_t> keys;
+    std::vector<duet_read_tag> tags;
+};
+
+extern "C" {
+
+void duet_free(void *p) { std::free(p); }
+
+int duet_set_decode_threads(int n) {
+    return g_inflate_threads.exchange(n < 1 ? 1 : n);
+}
+
+int duet_decode_reads(const unsigned char *data, int64_t len, int kind, duet_rows **out, int64_t *n_rows,
+                      int64_t *n_records, int64_t *err_at) {
+    *out = nullptr; *n_rows = 0; *n_records = 0; *err_at = -1;
+    duet_rows *rows = new (std::nothrow) duet_rows();
+    if (!rows) return DUET_DECODE_ERR_CAPACITY;
+    int rc;
+    if (kind == DUET_READS_BAM) {
+        BamWalker w;
+        rc = walk_bam(data, len, w);
+        *n_records = w.rec;
+        if (rc != DUET_OK) *err_at = w.rec;
+        rows->keys.swap(w.keys);
+        rows->tags.swap(w.tags);
+    } else {
+        const int64_t cap = duet_count_lines(reinterpret_cast<const char *>(data), len);
+        rows->keys.resize((size_t)cap);
+        rows->tags.resize((size_t)cap);
+        int64_t kept = 0;
+        rc = duet_decode_sam_text(reinterpret_cast<const char *>(data), len, cap, rows->keys.data(), rows->tags.data(), &kept,
+                                  n_records, err_at);
+        rows->keys.resize((size_t)kept);
+        rows->tags.resize((size_t)kept);
+    }
+    if (rc != DUET_OK) { delete rows; return rc; }
+    *n_rows = (int64_t)rows->keys.size();
+    *out = rows;
+    return DUET_OK;
+}
+
+int duet_rows_take(duet_rows *rows, uint64_t *key_dst, duet_read_tag *tag_dst) {
+    if (!rows) return DUET_ERR_INVALID;
+    const size_t n = rows->keys.size();
+    if (n) {
+        std::memcpy(key_dst, rows->keys.data(), n * sizeof(uint64_t));
+        std::memcpy(tag_dst, rows->tags.data(), n * sizeof(duet_read_tag));
+    }
+    delete rows;
+    return DUET_OK;
+}
+
+void duet_rows_free(duet_rows *rows) { delete rows; }
+
+int duet_decode_bam(const unsigned char *data, int64_t len, uint64_t **key_out, duet_read_tag **tag_out,
+                    int64_t *n_rows, int64_t *n_records, int64_t *err_record) {
+    *key_out = nullptr; *tag_out = nullptr; *n_rows = 0; *n_records = 0; *err_record = -1;
+    BamWalker w;
+    const int rc = walk_bam(data, len, w);
+    *n_records = w.rec;
+    if (rc != DUET_OK) { *err_record = w.rec; return rc; }
+    const size_t n = w.keys.size();
     uint64_t *k = static_cast<uint64_t *>(std::malloc(n ? n * 8 : 8));
     duet_read_tag *t = static_cast<duet_read_tag *>(std::malloc(n ? n * sizeof(duet_read_tag) : 16));
     if (!k || !t) { std::free(k); std::free(t); return DUET_DECODE_ERR_CAPACITY; }
-    if (n) { std::memcpy(k, keys.data(), n * 8); std::memcpy(t, tags.data(), n * sizeof(duet_read_tag)); }
-    *key_out = k; *tag_out = t; *n_rows = (int64_t)n; *n_records = rec;
+    if (n) { std::memcpy(k, w.keys.data(), n * 8); std::memcpy(t, w.tags.data(), n * sizeof(duet_read_tag)); }
+    *key_out = k; *tag_out = t; *n_rows = (int64_t)n;
     return DUET_OK;
 }
 

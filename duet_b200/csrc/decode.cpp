@@ -9,7 +9,8 @@
 // file order (the device resolves duplicate QNAMEs to the last row).  Everything the reference
 // would raise on (a line with fewer fields than it indexes, a non-integer tag value, a
 // non-ASCII byte) is reported as an error code + line number so the Python layer can raise the
-// same exception type.
+// same exception type.  Header lines ('@...') of a SAM file read directly are passed over: the
+// reference only ever sees `samtools view` output, which does not contain them.
 #include <cstdint>
 #include <cstring>
 
@@ -135,6 +136,7 @@ int duet_decode_sam_text(const char *text, int64_t len, int64_t cap, uint64_t *k
     while (p < end) {
         const unsigned char *nl = static_cast<const unsigned char *>(std::memchr(p, '\n', (size_t)(end - p)));
         if (!nl) break;                                    // text after the last newline is dropped (:25 [:-1])
+        if (*p == '@') { p = nl + 1; continue; }           // a SAM header line: `samtools view` (:25) does not print those
         // field scan: remember the first field and the last three
         const unsigned char *f0b = nullptr, *f0e = nullptr;
         const unsigned char *fb[3] = {nullptr, nullptr, nullptr}, *fe[3] = {nullptr, nullptr, nullptr};

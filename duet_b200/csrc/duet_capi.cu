@@ -86,7 +86,7 @@ struct duet_handle {
     DevBuf in_sv_pos, in_sv_svlen, in_sv_svread, in_sv_refread, in_sv_flags, in_sv_group;
     DevBuf in_csr_off, in_csr_key, in_csr_chk;
     // descriptors (one page-locked staging buffer -> one device buffer, one copy), table, scratch, outputs
-    PinBuf h_desc;
+    PinBuf h_desc, h_back;          // h_back: status, per-shard emit counts and the raw order on their way out
     bool desc_in_flight = false;    // EV_DESC marks the end of the last descriptor copy
     DevBuf d_desc, d_c2, d_dbg;
     int build_grid = 0, build_per_thread = 1, build_occ[4] = {8, 8, 8, 8};      // k_table<U>, U = 1, 2, 4, 8
@@ -278,6 +278,7 @@ void duet_destroy(duet_handle *h) {
                       &h->d_feat, &h->d_order, &h->d_n_emit, &h->d_counts, &h->d_status};
     for (DevBuf *b : bufs) b->release();
     h->h_desc.release();
+    h->h_back.release();
     for (DevBuf &b : h->cl_in) b.release();
     for (DevBuf *b : {&h->cl_key[0], &h->cl_key[1], &h->cl_idx[0], &h->cl_idx[1], &h->cl_span, &h->cl_parent,
                       &h->cl_minidx, &h->cl_out, &h->cl_hist, &h->cl_misc}) b->release();
@@ -314,6 +315,12 @@ int duet_host_alloc(void **ptr, int64_t bytes) {
         return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? DUET_ERR_NO_DEVICE : DUET_ERR_CUDA;
     }
     return DUET_OK;
+}
+
+int duet_host_is_pinned(const void *ptr) {
+    cudaPointerAttributes pa;
+    if (!ptr || cudaPointerGetAttributes(&pa, ptr) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return pa.type == cudaMemoryTypeHost ? 1 : 0;
 }
 
 int duet_host_free(void *ptr) {
@@ -679,7 +686,14 @@ int duet_phase_download(duet_handle *h, duet_phase_output *out) {
     cudaStream_t st = h->stream;
     const PhaseArgs &a = h->a;
     const size_t S = (size_t)a.n_svs, J = (size_t)a.n_joins;
-    DevStatus status;
+    // what the host post-processes (status, emit counts, raw order) lands in page-locked staging: plain DMA
+    const size_t ns = (size_t)a.n_shards;
+    const size_t off_emit = 64, off_order = (off_emit + ns * 4 + 63) & ~(size_t)63;
+    CU(h, h->h_back.reserve(off_order + (out->order ? S * 4 : 0) + 64));
+    unsigned char *back = static_cast<unsigned char *>(h->h_back.p);
+    DevStatus &status = *reinterpret_cast<DevStatus *>(back);
+    int *n_emit = reinterpret_cast<int *>(back + off_emit);
+    int *order_raw = reinterpret_cast<int *>(back + off_order);
     CU(h, cudaEventRecord(h->ev[EV_D2H0], st));
     CU(h, cudaMemcpyAsync(&status, a.status, sizeof(status), cudaMemcpyDeviceToHost, st));
 #define PULL(dst, src, bytes)                                                                        \
@@ -695,13 +709,9 @@ int duet_phase_download(duet_handle *h, duet_phase_output *out) {
     PULL(out->totsc2, a.totsc2, S * 8)
     PULL(out->features, a.features, S * 8 * DUET_N_FEATURES)
     PULL(out->join_row, a.join_row, J * 4)
-    PULL(out->shard_counts, a.shard_counts, (size_t)a.n_shards * 8 * DUET_N_COUNTERS)
-    std::vector<int> n_emit(a.n_shards), order_raw;
-    CU(h, cudaMemcpyAsync(n_emit.data(), a.n_emit, sizeof(int) * a.n_shards, cudaMemcpyDeviceToHost, st));
-    if (out->order && S) {
-        order_raw.resize(S);
-        CU(h, cudaMemcpyAsync(order_raw.data(), a.order, S * 4, cudaMemcpyDeviceToHost, st));
-    }
+    PULL(out->shard_counts, a.shard_counts, ns * 8 * DUET_N_COUNTERS)
+    CU(h, cudaMemcpyAsync(n_emit, a.n_emit, sizeof(int) * ns, cudaMemcpyDeviceToHost, st));
+    if (out->order && S) CU(h, cudaMemcpyAsync(order_raw, a.order, S * 4, cudaMemcpyDeviceToHost, st));
 #undef PULL
     CU(h, cudaEventRecord(h->ev[EV_D2H1], st));
     CU(h, cudaStreamSynchronize(st));
@@ -721,7 +731,7 @@ int duet_phase_download(duet_handle *h, duet_phase_output *out) {
     long long total = 0;
     for (int s = 0; s < a.n_shards; ++s) {
         if (out->order && S)
-            std::memcpy(out->order + total, order_raw.data() + h->h_sv_off[s], sizeof(int) * (size_t)n_emit[s]);
+            std::memcpy(out->order + total, order_raw + h->h_sv_off[s], sizeof(int) * (size_t)n_emit[s]);
         total += n_emit[s];
     }
     out->n_emitted = total;

@@ -137,10 +137,17 @@ class PhaseEngine:
     def sync(self):
         self._check(self.lib.duet_sync(self.h))
 
-    def download(self, *, join: bool = True, buffers: dict | None = None) -> PhaseResult:
+    def download(self, *, join: bool = True, buffers: dict | None = None, only: tuple | None = None) -> PhaseResult:
+        """`only`: names of the outputs to copy back (the rest come back empty) -- the drop-in stage needs just
+        the genotype, the phase set, the emission order and the counters."""
         b = self._batch
         S, J, ns = b.n_svs, b.n_joins, b.n_shards
         mk = (lambda name, shape, dt: buffers[name]) if buffers else (lambda name, shape, dt: np.empty(shape, dt))
+        if only is not None:
+            keep = set(only)
+            mk0 = mk
+            mk = lambda name, shape, dt: mk0(name, shape, dt) if name in keep else None
+            join = join and "join_row" in keep
         arr = {
             "gt": mk("gt", S, np.uint8), "ps": mk("ps", S, np.int32), "cls": mk("cls", S, np.uint8),
             "hap1": mk("hap1", S, np.int32), "hap2": mk("hap2", S, np.int32), "hap0": mk("hap0", S, np.int32),
@@ -154,18 +161,20 @@ class PhaseEngine:
             setattr(out, k, _ptr(v))
         self._check(self.lib.duet_phase_download(self.h, C.byref(out)))
         n = int(out.n_emitted)
-        if arr["join_row"] is None:
-            arr["join_row"] = np.zeros(0, np.int32)
+        for k, v in list(arr.items()):
+            if v is None:
+                arr[k] = np.zeros((_lib.N_FEATURES, 0) if k == "features" else 0, np.int32)
         arr["order"] = arr["order"][:n]
         return PhaseResult(**arr)
 
     def run(self, batch: PhaseBatch, *, join: bool = True, buffers: dict | None = None,
-            tags_in_place: bool = False) -> PhaseResult:
+            tags_in_place: bool = False, only: tuple | None = None) -> PhaseResult:
         """upload + execute + download.  `buffers` (see `pinned_outputs`) lets the results land in
-        page-locked memory, so the device->host copies run as plain DMA; `tags_in_place`: see upload."""
+        page-locked memory, so the device->host copies run as plain DMA; `tags_in_place`: see upload;
+        `only`: see download."""
         self.upload(batch, tags_in_place=tags_in_place)
         self.execute()
-        return self.download(join=join, buffers=buffers)
+        return self.download(join=join, buffers=buffers, only=only)
 
     def timings(self) -> dict:
         t = _lib.Timings()
@@ -217,3 +226,28 @@ def pin_batch(batch: PhaseBatch) -> PhaseBatch:
         dst[...] = arr
         new[name] = dst
     return dataclasses.replace(batch, **new)
+
+
+class PinnedPool:
+    """Page-locked host buffers that outlive a call: page-locking costs far more than the copy it speeds up,
+    so the decoders of the drop-in stage write into buffers kept from call to call (grow-only, one per name).
+    `get` hands out a view; what it held before is overwritten."""
+
+    def __init__(self):
+        self._raw: dict[str, np.ndarray] = {}
+
+    def get(self, name: str, shape, dtype) -> np.ndarray:
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) if not isinstance(shape, int) else int(shape)
+        need = n * dtype.itemsize
+        raw = self._raw.get(name)
+        if raw is None or raw.nbytes < need:
+            raw = self._raw[name] = pinned_empty(max(need + need // 4, 64), np.uint8)
+        return raw[:need].view(dtype).reshape(shape)
+
+
+def is_pinned(arr: np.ndarray) -> bool:
+    """True when the array's memory is page-locked host memory known to CUDA."""
+    if arr is None or arr.nbytes == 0:
+        return True
+    return bool(_lib.load().duet_host_is_pinned(C.c_void_p(arr.ctypes.data)))

@@ -155,3 +155,54 @@ def parse_vcf(vcf_file, include_all_ctgs):
         for v in cs.svlen:
             _i32(abs(v), "svlen")
     return out
+
+
+@dataclass
+class SvColumns:
+    """What the native reader (csrc/vcf_decode.cpp) returns: the records of every listed contig as columns,
+    contig-major, VCF order inside a contig, support-read names already hashed."""
+    sv_off: np.ndarray        # int64 [n_contigs + 1]
+    pos: np.ndarray           # int32 [S]
+    svlen: np.ndarray         # int32 [S] signed, as parsed (:36)
+    svread: np.ndarray
+    refread: np.ndarray
+    flags: np.ndarray         # uint8 [S]
+    group: np.ndarray | None  # int32 [S] rank of the CHROM string inside its contig, None when all zero
+    csr_off: np.ndarray       # int64 [S + 1]
+    csr_key: np.ndarray       # uint64 [J]
+    csr_chk: np.ndarray       # uint32 [J]
+    text: object              # the VCF bytes the spans point into
+    str_span: np.ndarray      # int64 [S, 4, 2]: CHROM, REF, ALT, SVTYPE
+
+
+def decode_sv_vcf(vcf_file, include_all_ctgs, threads: int = 1, alloc=None):
+    """One multi-threaded native pass over the SV VCF -> SvColumns, or None when the file is outside what
+    the native reader reproduces exactly (then `parse_vcf`, the general reader, decides -- and raises what
+    the reference raises).  `alloc(shape, dtype)` supplies the arrays (page-locked ones, for the device)."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    alloc = alloc or (lambda shape, dt: np.empty(shape, dt))
+    chrom_list = init_chrom_list(include_all_ctgs, vcf_file[:len(vcf_file) - 24])
+    if any("\n" in c for c in chrom_list) or not chrom_list:
+        return None
+    with open(vcf_file, "rb") as fh:
+        text = fh.read()
+    contigs = "\n".join(chrom_list).encode("ascii", "replace")
+    job, n_svs, n_joins = C.c_void_p(), C.c_int64(), C.c_int64()
+    buf = C.c_char_p(text) if text else C.c_char_p(b"\0")
+    rc = lib.duet_decode_sv_vcf(buf, len(text), contigs, len(contigs), max(1, int(threads)), C.byref(job), C.byref(n_svs),
+                                C.byref(n_joins))
+    if rc != _lib.DUET_OK:
+        return None
+    S, J, nc = n_svs.value, n_joins.value, len(chrom_list)
+    cols = SvColumns(alloc(nc + 1, np.int64), alloc(S, np.int32), alloc(S, np.int32), alloc(S, np.int32), alloc(S, np.int32),
+                     alloc(S, np.uint8), alloc(S, np.int32), alloc(S + 1, np.int64), alloc(J, np.uint64), alloc(J, np.uint32),
+                     text, np.empty((S, 4, 2), np.int64))
+    has_groups = C.c_int32()
+    lib.duet_svs_take(job, cols.sv_off.ctypes.data, cols.pos.ctypes.data, cols.svlen.ctypes.data, cols.svread.ctypes.data,
+                      cols.refread.ctypes.data, cols.flags.ctypes.data, cols.group.ctypes.data, C.byref(has_groups),
+                      cols.csr_off.ctypes.data, cols.csr_key.ctypes.data, cols.csr_chk.ctypes.data, cols.str_span.ctypes.data)
+    if not has_groups.value:
+        cols.group = None
+    return cols

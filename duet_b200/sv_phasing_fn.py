@@ -13,6 +13,7 @@ There is no CPU compute path: without libduet_b200.so and a CUDA device these fu
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 import logging
 import os
 import shlex
@@ -310,32 +311,186 @@ def phase_batch(batch: PhaseBatch, svlen_thres, suppread_thres, engine: PhaseEng
         raise exc(e.msg) from e      # the exception the reference raises at :96 / :123
 
 
+# ---- the fast path of the stage: both decoders write straight into page-locked columns --------------------
+_POOL = None          # engine.PinnedPool of the process: page-locked column and result buffers, kept between calls
+last_batch = None     # the batch of the last generate_phased_callset call (tests look at where its columns live)
+
+
+def _pool():
+    global _POOL
+    if _POOL is None:
+        from .engine import PinnedPool
+        _POOL = PinnedPool()
+    return _POOL
+
+
+def _hap_paths(path, chrom_list):
+    out = []
+    for ctg in chrom_list:
+        if os.path.exists(path + "chr" + ctg + ".bam"):
+            out.append(path + "chr" + ctg + ".bam")
+        elif os.path.exists(path + ctg + ".bam"):
+            out.append(path + ctg + ".bam")
+        else:
+            out.append(None)
+    return out
+
+
+class _ReadJob:
+    """One haplotagged file scanned natively (csrc: duet_decode_reads): the kept rows stay inside the library
+    until `take` copies them into their slice of the page-locked columns.  BGZF files are mapped, not read:
+    the inflate runs in bounded batches, so memory does not grow with the file."""
+
+    def __init__(self, path: str):
+        import mmap
+        lib = _lib.load()
+        self.lib, self.path, self.job, self.n_rows, self.n_records = lib, path, C.c_void_p(), 0, 0
+        with open(path, "rb") as fh:
+            size = os.fstat(fh.fileno()).st_size
+            if size == 0:
+                return
+            mm = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+        try:
+            view = np.frombuffer(mm, np.uint8)
+            if bytes(view[:2]) == b"\x1f\x8b":
+                kind = _lib.READS_BAM
+            else:
+                kind = _lib.READS_SAM_TEXT
+            n_rows, n_rec, err = C.c_int64(), C.c_int64(), C.c_int64()
+            rc = lib.duet_decode_reads(C.c_void_p(view.ctypes.data), size, kind, C.byref(self.job), C.byref(n_rows),
+                                       C.byref(n_rec), C.byref(err))
+            if rc == _lib.DECODE_ERR_FORMAT and kind == _lib.READS_BAM:
+                raise _NotBam()                                   # gzip, but not BGZF/BAM: samtools' business
+            if rc != _lib.DUET_OK:
+                exc, msg = _DECODE_EXC.get(rc, (RuntimeError, f"decode error {rc}"))
+                what = "record" if kind == _lib.READS_BAM else "line"
+                if exc is UnicodeDecodeError:
+                    raise UnicodeDecodeError("ascii", b"\xff", 0, 1, f"ordinal not in range(128) ({what} {err.value})")
+                raise exc(f"{msg} (alignment {what} {err.value})")
+            self.n_rows, self.n_records = n_rows.value, n_rec.value
+        finally:
+            del view
+            mm.close()
+
+    def take(self, key: np.ndarray, tag: np.ndarray):
+        if self.job:
+            self.lib.duet_rows_take(self.job, C.c_void_p(key.ctypes.data), C.c_void_p(tag.ctypes.data))
+            self.job = C.c_void_p()
+
+    def drop(self):
+        if self.job:
+            self.lib.duet_rows_free(self.job)
+            self.job = C.c_void_p()
+
+
+class _NotBam(Exception):
+    pass
+
+
+def _fast_batch(vcf_path, sam_home, thread, include_all_ctgs):
+    """Both decodes natively and concurrently, rows and records landing in page-locked columns.  Returns None
+    when an input is outside what the native readers claim (then the general path below takes over)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from .columnar import TextColumn
+    from .read_file import decode_sv_vcf
+    chrom_list = init_chrom_list(include_all_ctgs, sam_home[:len(sam_home) - 13])
+    paths = _hap_paths(sam_home, chrom_list)
+    thread = max(1, int(thread))
+    pool = _pool()
+    n_files = max(1, sum(p is not None for p in paths))
+    workers = min(thread, n_files)
+    prev = _lib.load().duet_set_decode_threads(max(1, thread // workers))
+    jobs = []
+    try:
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            futs = [ex.submit(_ReadJob, p) if p else None for p in paths]
+            logging.info("extract SV signatures")
+            numbered = itertools.count()
+            svs = decode_sv_vcf(vcf_path, include_all_ctgs, thread,
+                                alloc=lambda shape, dt: pool.get(f"sv_col{next(numbered)}", shape, dt))
+            try:
+                jobs = [f.result() if f else None for f in futs]
+            except _NotBam:
+                svs = None
+        if svs is None:
+            return None
+        ns = len(chrom_list)
+        read_off = np.zeros(ns + 1, np.int64)
+        read_off[1:] = np.cumsum([j.n_rows if j else 0 for j in jobs])
+        R = int(read_off[-1])
+        read_key, read_tag = pool.get("read_key", R, np.uint64), pool.get("read_tag", R, TAG_DTYPE)
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            list(ex.map(lambda k: jobs[k].take(read_key[read_off[k]:read_off[k + 1]], read_tag[read_off[k]:read_off[k + 1]])
+                        if jobs[k] else None, range(ns)))
+        for ctg, j in zip(chrom_list, jobs):
+            if j:
+                logging.info(("  signatures extracted from " if j.n_records else "  no signature from ") + ctg)
+        svlen_abs = pool.get("svlen_abs", svs.svlen.shape[0], np.int32)
+        np.abs(svs.svlen, out=svlen_abs)
+        tc = lambda k, pre="", suf="": TextColumn(svs.text, svs.str_span[:, k, :], pre, suf)
+        batch = PhaseBatch(read_off, svs.sv_off, read_key, read_tag, svs.pos, svlen_abs, svs.svread, svs.refread, svs.flags,
+                           svs.group, svs.csr_off, svs.csr_key, svs.csr_chk, [0] * ns, list(chrom_list),
+                           tc(0), tc(3), tc(1), tc(2))
+        batch.validate()
+        return batch
+    finally:
+        for j in jobs:
+            if j:
+                j.drop()
+        _lib.load().duet_set_decode_threads(prev)
+
+
 def generate_phased_callset(vcf_path, sam_home, svlen_thres, suppread_thres, thread, include_all_ctgs):
     """Same signature and return value as the reference's (sv_phasing_fn.py:185-230)."""
+    global last_batch
     t0 = time.perf_counter()
-    # The two decodes are independent: the haplotagged BAMs are scanned by C++ threads (GIL released) while
-    # this thread parses the SV VCF.  Errors surface in the reference's order: it reads the BAMs first (:186).
-    from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max_workers=1) as background:
-        pending = background.submit(read_hap_bam, sam_home, thread, include_all_ctgs)
-        vcf_error = comp_call = None
-        try:
-            logging.info("extract SV signatures")
-            comp_call = parse_vcf(vcf_path, include_all_ctgs)
-        except Exception as e:                                   # noqa: BLE001 -- re-raised below, after the BAM errors
-            vcf_error = e
-        read_hap = pending.result()
-    if vcf_error is not None:
-        raise vcf_error
-    batch = generate_callinfo(vcf_path, read_hap, include_all_ctgs, comp_call)
+    logging.info("extract SNP signatures")
+    batch = None
+    if not os.environ.get("DUET_GENERAL_DECODE"):
+        batch = _fast_batch(vcf_path, sam_home, thread, include_all_ctgs)
+    fast = batch is not None
+    if batch is None:
+        # The general readers.  The two decodes are independent: the haplotagged BAMs are scanned by C++ threads
+        # (GIL released) while this thread parses the SV VCF.  Errors surface in the reference's order: it reads
+        # the BAMs first (:186).
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=1) as background:
+            pending = background.submit(read_hap_bam, sam_home, thread, include_all_ctgs)
+            vcf_error = comp_call = None
+            try:
+                logging.info("extract SV signatures")
+                comp_call = parse_vcf(vcf_path, include_all_ctgs)
+            except Exception as e:                               # noqa: BLE001 -- re-raised below, after the BAM errors
+                vcf_error = e
+            read_hap = pending.result()
+        if vcf_error is not None:
+            raise vcf_error
+        batch = generate_callinfo(vcf_path, read_hap, include_all_ctgs, comp_call)
+    last_batch = batch
     t1 = time.perf_counter()
     logging.info("integrate read weight information")
     logging.info("calculate read weight statistics")
     logging.info("predict SV haplotypes in the callset")
-    res = phase_batch(batch, svlen_thres, suppread_thres)
+    eng = get_engine()
+    eng.set_thresholds(int(svlen_thres), int(suppread_thres))
+    try:
+        if fast:
+            # page-locked columns: the tag records stay where they are (only the joined rows cross the bus), the
+            # results the rows need -- genotype, phase set, order, counters -- land in page-locked buffers too
+            pool, S, ns = _pool(), batch.n_svs, batch.n_shards
+            bufs = {"gt": pool.get("o_gt", S, np.uint8), "ps": pool.get("o_ps", S, np.int32), "order": pool.get("o_order", S, np.int32),
+                    "shard_counts": pool.get("o_counts", (ns, _lib.N_COUNTERS), np.int64)}
+            res = eng.run(batch, buffers=bufs, tags_in_place=True, only=("gt", "ps", "order", "shard_counts"))
+        else:
+            res = eng.run(batch)
+    except DuetError as e:
+        exc = _STATUS_EXC.get(e.code)
+        if exc is None:
+            raise
+        raise exc(e.msg) from e      # the exception the reference raises at :96 / :123
     t2 = time.perf_counter()
     rows = res.rows(batch)
     t3 = time.perf_counter()
     last_timings.clear()
-    last_timings.update(host_decode_s=t1 - t0, device_call_s=t2 - t1, rows_s=t3 - t2, **get_engine().timings())
+    last_timings.update(host_decode_s=t1 - t0, device_call_s=t2 - t1, rows_s=t3 - t2, native_decode=fast, **eng.timings())
     return rows

@@ -192,6 +192,7 @@ int duet_phase_run(duet_handle *h, const duet_phase_input *in, duet_phase_output
  * without a GPU. */
 int duet_host_alloc(void **ptr, int64_t bytes);
 int duet_host_free(void *ptr);
+int duet_host_is_pinned(const void *ptr);   /* 1 if ptr lies in page-locked host memory known to CUDA, else 0 */
 
 int duet_sync(duet_handle *h);
 
@@ -237,7 +238,9 @@ enum {
     DUET_DECODE_ERR_ASCII = 22,    /* byte >= 0x80 -> UnicodeDecodeError (.decode('ascii'), :25)        */
     DUET_DECODE_ERR_RANGE = 23,    /* HP outside 0..255 or PS/PC outside int32 (BAM aux ints are 32 bit) */
     DUET_DECODE_ERR_CAPACITY = 24, /* output arrays too small / out of memory                           */
-    DUET_DECODE_ERR_FORMAT = 25    /* not a BGZF-compressed BAM / truncated record                       */
+    DUET_DECODE_ERR_FORMAT = 25,   /* not a BGZF-compressed BAM / truncated record                       */
+    DUET_DECODE_FALLBACK = 26      /* duet_decode_sv_vcf: input outside what the native reader reproduces
+                                      exactly -- use the general reader (duet_b200/read_file.py)          */
 };
 
 /* 128-bit name hash (duet_b200/namehash.py): name i is buf[off[i] .. off[i+1]).  key = lo,
@@ -276,6 +279,37 @@ int duet_set_decode_threads(int n);
 int duet_decode_bam(const unsigned char *data, int64_t len, uint64_t **key_out, duet_read_tag **tag_out,
                     int64_t *n_rows, int64_t *n_records, int64_t *err_record);
 void duet_free(void *p);
+
+/* The same decoders as a two-step job, so that the rows can land directly in columns the caller sizes from
+ * the counts (page-locked, one slice per contig): duet_decode_reads scans one file's bytes -- kind
+ * DUET_READS_SAM_TEXT (`samtools view` text) or DUET_READS_BAM (BGZF; inflated and walked in bounded
+ * batches, so memory does not grow with the file) -- and holds the kept rows; duet_rows_take copies them to
+ * `key_dst` / `tag_dst` (room for *n_rows each) and releases the job; duet_rows_free drops it unread. */
+enum { DUET_READS_SAM_TEXT = 0, DUET_READS_BAM = 1 };
+typedef struct duet_rows duet_rows;
+int duet_decode_reads(const unsigned char *data, int64_t len, int kind, duet_rows **out, int64_t *n_rows,
+                      int64_t *n_records, int64_t *err_at);
+int duet_rows_take(duet_rows *rows, uint64_t *key_dst, duet_read_tag *tag_dst);
+void duet_rows_free(duet_rows *rows);
+
+/* The SV VCF (cuteSV / Sniffles2 / SVIM dialects) in one multi-threaded pass: what read_file.py::parse_vcf
+ * (reference: src/duet/read_file.py:25-76) returns, as columns, with the support-read names hashed in the
+ * same pass.  `contigs` = the contig list joined by '\n' (read_file.py:6-16); record i of contig c is row
+ * sv_off[c] + i.  Regular input only: anything the native reader does not reproduce exactly (irregular INFO
+ * items, integers that are not plain decimals, mixed dialects inside a contig, a CHROM string claimed by two
+ * contigs, blank lines, non-ASCII bytes ...) returns DUET_DECODE_FALLBACK -- the general reader then decides,
+ * raising what the reference raises.  duet_svs_take copies the columns out and releases the job:
+ *   sv_off[n_contigs+1]; pos, svlen (signed, as parsed), svread, refread [S]; flags [S] (DUET_SV_*);
+ *   group [S] (rank of the CHROM string inside its contig; *has_groups = 0 when all zero);
+ *   csr_off[S+1], csr_key[J], csr_chk[J]; str_span[S][4][2] = (offset, length) into `text` of CHROM, REF, ALT
+ *   and the SVTYPE value.  `text` must stay valid until duet_svs_take / duet_svs_free. */
+typedef struct duet_svs duet_svs;
+int duet_decode_sv_vcf(const char *text, int64_t len, const char *contigs, int64_t contigs_len, int threads,
+                       duet_svs **out, int64_t *n_svs, int64_t *n_joins);
+int duet_svs_take(duet_svs *h, int64_t *sv_off, int32_t *pos, int32_t *svlen, int32_t *svread, int32_t *refread,
+                  uint8_t *flags, int32_t *group, int32_t *has_groups, int64_t *csr_off, uint64_t *csr_key,
+                  uint32_t *csr_chk, int64_t *str_span);
+void duet_svs_free(duet_svs *h);
 int duet_get_timings(duet_handle *h, duet_timings *t);
 /* Number of kernels this library launched on the handle since creation (bench "gpu_launches"). */
 int64_t duet_launch_count(const duet_handle *h);

@@ -416,3 +416,91 @@ def test_c4_dense_full_size_parity(engine):
     batch = from_synth(synth.config_c4(0), with_text=False)
     assert batch.n_joins > 1_500_000 and np.diff(batch.csr_off).max() >= 1500
     _compare_with_columnar_oracle(engine, batch, 50, 2, repeats=6)
+
+
+def test_c5_share_full_size_parity(engine):
+    """BASELINE.json configs[4], one GPU's share at FULL size: 4 samples x WGS 30x = 96 (sample, contig)
+    shards, ~14.9 M haplotagged reads and 100 k SVs in ONE device call (the batch bench.py's c5 times), with
+    the per-sample id_base << 44 name spaces.  Every join row, class, genotype, PS, count, fp64 feature, the
+    emission order and the per-shard counters equal the columnar oracle's; the call is repeated (the
+    kernels of a call overlap on the device: a synchronisation slip shows as a run-to-run difference)."""
+    samples = [synth.config_c2(4 * 0 + k, id_base=(4 * 0 + k) << 44) for k in range(4)]
+    batch = from_synth(samples, with_text=False)
+    assert batch.n_shards == 96 and batch.n_svs == 4 * 25_001 and batch.n_reads > 14_000_000
+    res = _compare_with_columnar_oracle(engine, batch, 50, 2, repeats=3)
+    assert res.shard_counts[:, 2].sum() == res.order.shape[0] > 60_000
+    # size-independent: per shard the order is position sorted and covers exactly the SVs with a genotype
+    emitted = np.nonzero(res.gt)[0]
+    assert np.array_equal(np.sort(res.order), emitted)
+    shard = np.searchsorted(batch.sv_off, res.order, side="right") - 1
+    assert (np.diff(shard) >= 0).all()
+    assert (np.diff(batch.sv_pos[res.order])[np.diff(shard) == 0] >= 0).all()
+
+
+# ---- property-based differential testing (hypothesis) against the columnar oracle ---------------------------
+try:
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    _HAVE_HYPOTHESIS = True
+except Exception:                                            # pragma: no cover
+    _HAVE_HYPOTHESIS = False
+
+if _HAVE_HYPOTHESIS:
+    _ps = st.sampled_from([-5, 0, 7, 100, 2**31 - 1, -2**31 + 1, 4242, 99_999])
+    _pc = st.one_of(st.sampled_from([-3, 0, 1, 8099, 8100, 8101, 20000]), st.integers(0, 9000))
+
+    @st.composite
+    def _shards(draw):
+        n_shards = draw(st.integers(1, 6))
+        out = []
+        for s in range(n_shards):
+            n_reads = draw(st.sampled_from([0, 1, 3, 17, 90]))
+            pool = [f"s{s}r{k}" for k in range(max(n_reads, 1))]
+            reads = [(draw(st.sampled_from(pool)) if draw(st.integers(0, 9)) == 0 else pool[k],
+                      draw(st.integers(1, 2)), draw(_ps), draw(_pc)) for k in range(n_reads)]
+            svs = []
+            for v in range(draw(st.sampled_from([0, 1, 2, 9]))):
+                names = draw(st.lists(st.one_of(st.sampled_from(pool), st.just(f"ghost{s}_{v}")), min_size=1, max_size=40))
+                svs.append(dict(pos=draw(st.one_of(st.sampled_from([10, 500]), st.integers(-50, 10**6))),
+                                svread=draw(st.integers(1, 40)), refread=draw(st.integers(0, 40)), names=names,
+                                svlen=draw(st.sampled_from([10, 50, 3000])), gt_missing=draw(st.integers(0, 9)) == 0))
+            out.append((reads, svs))
+        return out
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow,
+                                                                     HealthCheck.data_too_large])
+    @given(shards=_shards(), svlen=st.sampled_from([0, 50]), supp=st.sampled_from([0, 2, 10]))
+    def test_hypothesis_batches_against_columnar_oracle(engine, shards, svlen, supp):
+        """Randomised (shrinking) differential test: arbitrary shards -- duplicate QNAMEs, names listed twice or
+        absent, PS / PC at the int32 and 8100 edges, empty shards, unsorted and equal positions -- must give the
+        oracle's join rows, classes, genotypes, PS, counts, features, order and counters."""
+        bb = BatchBuilder()
+        for s, (reads, svs) in enumerate(shards):
+            bb.shard(reads, svs, contig=str(s))
+        batch = bb.build()
+        if batch.n_svs == 0:
+            bb.shard([("a", 1, 5, 5)], [dict(pos=1, svread=3, refread=0, names=["a"])], contig="z")
+            batch = bb.build()
+        _compare_with_columnar_oracle(engine, batch, svlen, supp)
+
+
+def test_dropin_stage_decodes_into_page_locked_columns(golden_workdir, monkeypatch):
+    """The stage's own path: both native decoders write into page-locked columns, the device call reads the tag
+    records in place, only genotype / phase set / order / counters come back -- same rows as the general readers
+    (and as the reference)."""
+    from duet_b200 import sv_phasing_fn
+    from duet_b200.engine import is_pinned
+    case, home = golden_workdir("svim_shuffled")
+    args = (home + "/sv_calling/variants.vcf", home + "/snp_phasing/", case["svlen_thres"], case["suppread_thres"], 4, False)
+    rows = sv_phasing_fn.generate_phased_callset(*args)
+    assert rows == case["rows"]
+    assert sv_phasing_fn.last_timings["native_decode"] is True
+    b = sv_phasing_fn.last_batch
+    for name in _lib.INPUT_COLUMNS:
+        arr = getattr(b, name)
+        if name in ("read_off", "sv_off") or arr is None:      # host-side descriptors
+            continue
+        assert is_pinned(arr), name
+    assert not is_pinned(np.zeros(16))
+    monkeypatch.setenv("DUET_GENERAL_DECODE", "1")
+    assert sv_phasing_fn.generate_phased_callset(*args) == rows
+    assert sv_phasing_fn.last_timings["native_decode"] is False

@@ -8,7 +8,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import ROOT, golden_e2e_names
+from conftest import ROOT, golden_e2e_names, load_golden
 from duet_b200 import _lib, namehash, read_file, sv_phasing_fn, synth, write_file
 from duet_b200.columnar import from_synth
 from oracle import ref_port
@@ -300,3 +300,147 @@ def test_bam_reader_on_spec_laid_out_fixture():
             f.write(text)
         table = ref_port.haplotag_tables(home + "/snp_phasing/", 1, False)[0]
     assert table == {"r001": (2, 7, 10), "r003": (2, 100000, 300), "r005": (1, 42, -5)}
+
+
+# ---- the native SV-VCF reader (csrc/vcf_decode.cpp) against the general Python reader ---------------------
+def _vcf_columns_equal(native, general, vcf_path):
+    from duet_b200.columnar import TextColumn
+    assert native.sv_off.tolist() == np.concatenate([[0], np.cumsum([len(cs) for cs in general])]).tolist()
+    flat = lambda f: [v for cs in general for v in getattr(cs, f)]
+    assert native.pos.tolist() == flat("pos") and native.svlen.tolist() == flat("svlen")
+    assert native.svread.tolist() == flat("svread") and native.refread.tolist() == flat("refread")
+    assert [bool(x) for x in native.flags] == [g == "./." for g in flat("gt")]
+    for k, f in enumerate(("chrom", "ref", "alt", "svtype")):
+        assert list(TextColumn(native.text, native.str_span[:, k, :])) == flat(f)
+    lens, lo, hi = sv_phasing_fn.hash_name_csv(flat("names_csv"))
+    assert np.array_equal(np.diff(native.csr_off), lens) and np.array_equal(native.csr_key, lo)
+    assert np.array_equal(native.csr_chk, (hi & np.uint64(0xFFFFFFFF)).astype(np.uint32))
+    ranks = []
+    for cs in general:
+        order = {c: i for i, c in enumerate(sorted(set(cs.chrom)))}
+        ranks += [order[c] for c in cs.chrom]
+    assert (native.group.tolist() if native.group is not None else [0] * len(ranks)) == ranks
+
+
+@pytest.mark.parametrize("name", [n for n in golden_e2e_names() if n != "all_ctgs"])
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_native_vcf_reader_equals_general_reader(name, threads, golden_workdir):
+    """cuteSV / Sniffles2 / SVIM dialects, shuffled records, 'chr' and bare names in one contig, dense lists:
+    the one-pass native reader returns the columns the general reader's lists give, for any thread count."""
+    from duet_b200 import read_file
+    case, home = golden_workdir(name)
+    vcf = home + "/sv_calling/variants.vcf"
+    native = read_file.decode_sv_vcf(vcf, False, threads)
+    assert native is not None
+    _vcf_columns_equal(native, read_file.parse_vcf(vcf, False), vcf)
+
+
+def test_native_vcf_reader_declines_what_it_does_not_reproduce(golden_workdir, tmp_path):
+    """A CHROM string claimed by two contigs (`all_ctgs`: '7' and 'chr7' both listed), blank lines, integers
+    only Python's int() accepts, needles inside other keys, a dialect change inside a contig, a lone carriage
+    return: the native reader returns None and the general reader decides."""
+    from duet_b200 import read_file
+    case, home = golden_workdir("all_ctgs")
+    assert read_file.decode_sv_vcf(home + "/sv_calling/variants.vcf", True, 2) is None
+    case = load_golden("e2e_cutesv_3ctg.json.gz")
+    text = case["files"]["sv_calling/variants.vcf"]
+    lines = text.split("\n")
+    first = next(i for i, ln in enumerate(lines) if ln and not ln.startswith("#"))
+
+    def declined(mutated: str) -> bool:
+        d = tmp_path / f"case{declined.k}"
+        declined.k += 1
+        (d / "sv_calling").mkdir(parents=True)
+        (d / "sv_calling" / "variants.vcf").write_text(mutated)
+        return read_file.decode_sv_vcf(str(d) + "/sv_calling/variants.vcf", False, 2) is None
+    declined.k = 0
+    assert not declined(text)
+    assert declined("\n".join(lines[:first + 1] + [""] + lines[first + 1:]))                      # blank line
+    rec = lines[first]
+    assert declined(text.replace(rec, rec.replace("RE=", "XRE=", 1), 1))                            # needle not at an item start
+    assert declined(text.replace(rec, rec.replace("RNAMES=", "READS=", 1), 1) if "RNAMES=" in lines[first + 1] else text + "\n\n")
+    pos = rec.split("\t")[1]
+    assert declined(text.replace(rec, rec.replace("\t" + pos + "\t", "\t" + pos[0] + "_" + pos[1:] + "\t", 1), 1) if len(pos) > 1 else text + "\n\n")
+    assert declined(text.replace(rec, rec.replace("\t", "\r\t", 1), 1))                             # lone carriage return
+
+
+# ---- the two-step decode job (rows held by the library, copied into the caller's column slices) ---------------
+def _job(data: bytes, kind: int):
+    import ctypes as C
+    from duet_b200 import _lib
+    lib = _lib.load()
+    job, n_rows, n_rec, err = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int64()
+    rc = lib.duet_decode_reads(data, len(data), kind, C.byref(job), C.byref(n_rows), C.byref(n_rec), C.byref(err))
+    if rc != 0:
+        return rc, None, None, err.value
+    from duet_b200.columnar import TAG_DTYPE
+    key, tag = np.empty(n_rows.value, np.uint64), np.empty(n_rows.value, TAG_DTYPE)
+    assert lib.duet_rows_take(job, key.ctypes.data, tag.ctypes.data) == 0
+    return 0, key, tag, n_rec.value
+
+
+def test_decode_job_equals_direct_decoders_and_streams_large_bams(tmp_path):
+    """duet_decode_reads on SAM text and on a BAM whose inflated size exceeds one 16 MB batch several times
+    (records straddle BGZF blocks and batches): same rows as the whole-buffer decoders."""
+    from duet_b200 import _lib
+    from util_bam import write_bam
+    rng = np.random.default_rng(5)
+    rows = []
+    for k in range(120_000):
+        aux = [("NM", "C", int(rng.integers(0, 9)))]
+        if k % 3:
+            aux += [("HP", "C", int(rng.integers(1, 3))), ("PC", "S", int(rng.integers(0, 9000))), ("PS", "I", int(rng.integers(1, 10**8)))]
+        rows.append((f"read{k:07d}-{int(rng.integers(1 << 30)):x}", int(rng.integers(1, 10**8)), "ACGT" * 60, "*", aux))
+    recs, text = _bam_and_text(rows)
+    path = str(tmp_path / "big.bam")
+    write_bam(path, recs, block=50000)
+    with open(path, "rb") as f:
+        data = f.read()
+    assert sum(len(r) for r in recs) > 3 * (16 << 20)
+    rc, key, tag, n_rec = _job(data, _lib.READS_BAM)
+    assert rc == 0 and n_rec == len(rows)
+    ref = sv_phasing_fn.decode_sam_text(text)
+    assert np.array_equal(key, ref.key) and np.array_equal(tag, ref.tag)
+    rc, key2, tag2, n_lines = _job(text, _lib.READS_SAM_TEXT)
+    assert rc == 0 and np.array_equal(key2, ref.key) and np.array_equal(tag2, ref.tag) and n_lines == len(rows)
+    whole = sv_phasing_fn.decode_bam(data)
+    assert np.array_equal(whole.key, ref.key) and np.array_equal(whole.tag, ref.tag)
+
+
+def test_bam_reader_rejects_forged_and_truncated_blocks(tmp_path):
+    """ADVICE (round 1): a BGZF header whose XLEN points past the end of the input, an extra subfield that
+    overruns XLEN, a forged ISIZE above the 64 KiB a block can hold, a file cut inside a record: an error
+    code, never an out-of-bounds read or a giant allocation."""
+    from duet_b200 import _lib
+    from util_bam import write_bam
+    recs, _ = _bam_and_text([(f"r{k}", 10 + k, "ACGT", "*", [("HP", "C", 1), ("PC", "C", 5), ("PS", "C", 9)]) for k in range(50)])
+    path = str(tmp_path / "x.bam")
+    write_bam(path, recs, block=700)
+    good = open(path, "rb").read()
+    assert _job(good, _lib.READS_BAM)[0] == 0
+    forged_xlen = bytes.fromhex("1f8b08040000000000ffffff4243020011000300")[:18]
+    assert _job(forged_xlen, _lib.READS_BAM)[0] == _lib.DECODE_ERR_FORMAT
+    bad_sub = bytearray(good)
+    bad_sub[14:16] = (60000).to_bytes(2, "little")                   # subfield length overruns XLEN
+    assert _job(bytes(bad_sub), _lib.READS_BAM)[0] == _lib.DECODE_ERR_FORMAT
+    bsize = int.from_bytes(good[16:18], "little") + 1
+    forged_isize = bytearray(good)
+    forged_isize[bsize - 4:bsize] = (1 << 30).to_bytes(4, "little")
+    assert _job(bytes(forged_isize), _lib.READS_BAM)[0] == _lib.DECODE_ERR_FORMAT
+    eof = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    cut_blocks, pos = [], 0
+    while pos < len(good) - len(eof):
+        n = int.from_bytes(good[pos + 16:pos + 18], "little") + 1
+        cut_blocks.append(good[pos:pos + n])
+        pos += n
+    truncated = b"".join(cut_blocks[:-1]) + eof                      # the last data block is gone: a record is cut short
+    assert _job(truncated, _lib.READS_BAM)[0] == _lib.DECODE_ERR_FORMAT
+
+
+def test_sam_text_with_header_lines_is_read_like_samtools_view():
+    """A SAM file read directly may start with '@' header lines; `samtools view` (what the reference reads)
+    does not print them, so they are passed over instead of being indexed as alignments (ADVICE round 1:
+    b'@HD...\\n@CO\\n' used to raise IndexError)."""
+    text = b"@HD\tVN:1.6\tSO:coordinate\n@CO\nq1\t0\t1\t5\t60\t4M\t*\t0\t0\tACGT\t*\tHP:i:1\tPC:i:7\tPS:i:3\n"
+    cols = sv_phasing_fn.decode_sam_text(text)
+    assert len(cols) == 1 and (int(cols.hp[0]), int(cols.pc[0]), int(cols.ps[0])) == (1, 7, 3)

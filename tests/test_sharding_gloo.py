@@ -61,6 +61,11 @@ def _worker(rank, world, port, home, svlen, supp, out_q, on_gpu=False, inc=False
     try:
         counts = sharding.sv_phasing_sharded(home, svlen, supp, 1, inc,
                                              phase_fn=None if on_gpu else _oracle_phase_fn)
+        if on_gpu:
+            import torch
+            from duet_b200 import sv_phasing_fn
+            used = sorted(sv_phasing_fn._ENGINES)
+            assert used == [rank % torch.cuda.device_count()], used      # >= 2 GPUs visible: every rank on its own
         out_q.put((rank, counts))
     finally:
         dist.destroy_process_group()
