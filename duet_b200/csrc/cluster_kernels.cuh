@@ -2,9 +2,11 @@
 //
 // The reference does not contain this arithmetic: Duet passes `--cluster_max_distance` to the
 // external `svim` CLI (/root/reference/src/duet/sv_calling.py:14-15, default 0.9 utils.py:27-28).
-// svim 1.4.2 is not vendored and not installed here, so PARITY WITH SVIM IS UNPINNED.  What these
-// kernels implement -- and what oracle/cluster_oracle.py restates on the CPU -- is the spec frozen
-// in SURVEY.md §8(c), following the north_star's formulation (sort, windowed pairwise distances
+// svim 1.4.2 is not vendored and not installed here, so PARITY WITH SVIM IS UNPINNED -- and this is
+// a DIFFERENT algorithm from svim's (svim cuts partitions and runs average-linkage hierarchical
+// clustering on them; single linkage chains, so for the same threshold it gives fewer, larger clusters).
+// What these kernels implement -- and what oracle/cluster_oracle.py restates on the CPU -- is the spec
+// frozen in SURVEY.md §8(c), following the north_star's formulation (sort, windowed pairwise distances
 // in shared-memory tiles, union-find):
 //
 //   signature i = (contig, type, start, end);  c2_i = start+end (twice the centre), span_i = end-start
@@ -12,6 +14,16 @@
 //                   (|c2_i - c2_j| * 0.5) / normalizer + |span_i - span_j| / max(span_i, span_j)  <=  max_distance
 //                   (fp64, this operand order; the span term is 0 when both spans are 0)
 //   clusters = connected components;  cluster id = smallest ORIGINAL index in the component.
+//
+// Device path, no host round trip anywhere:
+//   k_cl_keys     64-bit keys contig | type | c2, payload (original index, span), the three maxima
+//   k_rs_*        stable LSD radix sort, 8-bit digits taken from the PACKED key (only as many bits as the
+//                 maxima need: 36 for a human genome -> five passes; passes beyond that return at once).  A
+//                 tile is ranked in one go: every warp ranks its own contiguous 256 keys with match_any, one
+//                 block-wide prefix over the warps' digit counts, then the scatter
+//   k_cl_edges    one block per tile of 256 sorted signatures (+ 256 halo): the windowed pairwise distances
+//                 out of shared memory, passing pairs united in a lock-free union-find (roots = minima)
+//   k_cl_label / k_cl_write   roots' smallest original index, cluster ids in input order
 #pragma once
 
 #include <cuda_runtime.h>
@@ -20,74 +32,112 @@
 namespace duet {
 
 constexpr int kClThreads = 256;
-constexpr int kRsItems = 16;                       // radix sort: items per thread per tile
-constexpr int kRsTile = kClThreads * kRsItems;
+constexpr int kRsItems = 8;                        // radix sort: keys per thread per tile
+constexpr int kRsTile = kClThreads * kRsItems;     // 2048
+constexpr int kRsBits = 8;
+constexpr int kRsBins = 1 << kRsBits;
+constexpr int kRsMaxPasses = 7;                    // 16 + 8 + 32 key bits
 constexpr int kClHalo = 256;
+
+struct ClMeta {                    // device-side facts about the call
+    unsigned max_contig, max_type, max_c2;
+    int bad;                       // invalid input seen
+    int n_clusters;
+    int pad[3];
+};
 
 struct ClusterArgs {
     int n;
     const int *contig, *type, *start, *end;
-    unsigned long long *key;       // current sorted keys: contig:16 | type:8 | 0:8 | c2:32
-    int *idx;                      // original index of each sorted position
-    int *span;                     // span of each sorted position
+    unsigned long long *key[2];    // ping-pong: contig:16 | type:8 | 0:8 | c2:32
+    unsigned long long *pay[2];    // span:32 | original index:32
     int *parent;                   // union-find over sorted positions; roots are component minima
     int *minidx;                   // smallest original index per root
     int *out;                      // [n] cluster id per ORIGINAL index
-    unsigned long long *vary;      // [2]: OR of (key ^ key[0]); error flag
-    int *n_clusters;
+    ClMeta *meta;
+    unsigned *block_hist;          // [kRsBins][n_tiles] bin-major, then [kRsBins] bin totals
+    int n_tiles;
     double max_distance, normalizer;
     unsigned window2;              // 2 * partition window
 };
+
+__device__ __forceinline__ int bits_for(unsigned v) { return 32 - __clz(v); }          // 0 for v == 0
+
+// how the sort sees a key: only the bits the call's maxima need, contig above type above c2
+struct Packing {
+    int b2, bt, total;
+    __device__ __forceinline__ unsigned long long pack(unsigned long long k) const {
+        const unsigned long long c2 = k & 0xFFFFFFFFull, t = (k >> 32) & 0xFFull, c = k >> 40;
+        return (c << (bt + b2)) | (t << b2) | c2;
+    }
+};
+__device__ __forceinline__ Packing packing_of(const ClMeta *m) {
+    Packing p;
+    p.b2 = bits_for(m->max_c2); p.bt = bits_for(m->max_type);
+    p.total = p.b2 + p.bt + bits_for(m->max_contig);
+    return p;
+}
+__device__ __forceinline__ int sorted_buffer(const Packing &p) { return ((p.total + kRsBits - 1) / kRsBits) & 1; }
 
 // ---- keys ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kClThreads)
 k_cl_keys(ClusterArgs a) {
     const int i = blockIdx.x * kClThreads + threadIdx.x;
-    unsigned long long diff = 0ull;
+    unsigned mc = 0, mt = 0, m2 = 0;
     if (i < a.n) {
         const long long st = a.start[i], en = a.end[i];
         const unsigned c = (unsigned)a.contig[i], t = (unsigned)a.type[i];
-        if (st < 0 || en < st || st + en > 0xFFFFFFFFll || c > 0xFFFFu || t > 0xFFu) a.vary[1] = 1ull;   // invalid input
-        const unsigned long long k = ((unsigned long long)(c & 0xFFFFu) << 48) | ((unsigned long long)(t & 0xFFu) << 40) |
-                                     (unsigned long long)(unsigned)(st + en);
-        a.key[i] = k;
-        a.idx[i] = i;
+        if (st < 0 || en < st || st + en > 0xFFFFFFFFll || c > 0xFFFFu || t > 0xFFu) a.meta->bad = 1;      // invalid input
+        mc = c & 0xFFFFu; mt = t & 0xFFu; m2 = (unsigned)(st + en);
+        a.key[0][i] = ((unsigned long long)mc << 40) | ((unsigned long long)mt << 32) | (unsigned long long)m2;
+        a.pay[0][i] = ((unsigned long long)(unsigned)(en - st) << 32) | (unsigned)i;
         a.parent[i] = i;
         a.minidx[i] = INT32_MAX;
-        const long long s0 = a.start[0], e0 = a.end[0];
-        const unsigned long long k0 = ((unsigned long long)((unsigned)a.contig[0] & 0xFFFFu) << 48) |
-                                      ((unsigned long long)((unsigned)a.type[0] & 0xFFu) << 40) |
-                                      (unsigned long long)(unsigned)(s0 + e0);
-        diff = k ^ k0;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) diff |= __shfl_xor_sync(0xffffffffu, diff, o);
-    if ((threadIdx.x & 31) == 0 && diff) atomicOr(a.vary, diff);
+    for (int o = 16; o > 0; o >>= 1) {
+        mc = max(mc, __shfl_xor_sync(0xffffffffu, mc, o));
+        mt = max(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+        m2 = max(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (mc > a.meta->max_contig) atomicMax(&a.meta->max_contig, mc);
+        if (mt > a.meta->max_type) atomicMax(&a.meta->max_type, mt);
+        if (m2 > a.meta->max_c2) atomicMax(&a.meta->max_c2, m2);
+    }
 }
 
-// ---- LSD radix sort, 8-bit digits: histogram / scan / stable scatter ---------------------------
+// ---- LSD radix sort, 8-bit digits of the packed key: histogram / scan / ranked scatter -----------------
 __global__ void __launch_bounds__(kClThreads)
-k_rs_hist(const unsigned long long *__restrict__ key, int n, int shift, unsigned *block_hist, int n_blocks) {
-    __shared__ unsigned s_h[256];
+k_rs_hist(ClusterArgs a, int pass) {
+    const Packing pk = packing_of(a.meta);
+    const int shift = pass * kRsBits;
+    if (shift >= pk.total) return;                       // this call's keys have no such digit
+    __shared__ unsigned s_h[kRsBins];
     s_h[threadIdx.x] = 0;
     __syncthreads();
+    const unsigned long long *key = a.key[pass & 1];
     const int base = blockIdx.x * kRsTile;
-#pragma unroll 4
+#pragma unroll
     for (int r = 0; r < kRsItems; ++r) {
         const int i = base + r * kClThreads + threadIdx.x;
-        if (i < n) atomicAdd(&s_h[(unsigned)(key[i] >> shift) & 255u], 1u);
+        if (i < a.n) atomicAdd(&s_h[(unsigned)(pk.pack(key[i]) >> shift) & (kRsBins - 1)], 1u);
     }
     __syncthreads();
-    block_hist[threadIdx.x * n_blocks + blockIdx.x] = s_h[threadIdx.x];      // bin-major
+    a.block_hist[threadIdx.x * a.n_tiles + blockIdx.x] = s_h[threadIdx.x];      // bin-major
 }
 
-// per-bin scan: block b turns row b of the bin-major histogram (n_blocks counters) into exclusive
+// per-bin scan: block b turns row b of the bin-major histogram (n_tiles counters) into exclusive
 // offsets inside the bin and records the bin total; k_rs_scatter adds the bins' bases itself
 __global__ void __launch_bounds__(kClThreads)
-k_rs_scan(unsigned *block_hist, int n_blocks, unsigned *bin_total) {
+k_rs_scan(ClusterArgs a, int pass) {
+    const Packing pk = packing_of(a.meta);
+    if (pass * kRsBits >= pk.total) return;
     __shared__ unsigned s_w[kClThreads / 32];
     __shared__ unsigned s_carry;
-    unsigned *row = block_hist + (size_t)blockIdx.x * n_blocks;
+    const int n_blocks = a.n_tiles;
+    unsigned *row = a.block_hist + (size_t)blockIdx.x * n_blocks;
+    unsigned *bin_total = a.block_hist + (size_t)kRsBins * n_blocks;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -113,15 +163,24 @@ k_rs_scan(unsigned *block_hist, int n_blocks, unsigned *bin_total) {
     if (threadIdx.x == 0) bin_total[blockIdx.x] = s_carry;
 }
 
+// One tile of 2048 keys: warp w owns the contiguous keys [256 w, 256 (w+1)) of the tile, in eight rounds of
+// 32.  A round ranks its keys inside the warp with match_any (lanes holding the same digit, in lane = key
+// order) on top of the warp's running count of that digit; ONE block-wide step then turns the warps' counts
+// into offsets (bin base + tile offset + the warps before), and the keys go out.  Stable: a key's place among
+// equal digits follows (tile, warp, round, lane) = input order.
 __global__ void __launch_bounds__(kClThreads)
-k_rs_scatter(const unsigned long long *__restrict__ key_in, const int *__restrict__ idx_in,
-             unsigned long long *__restrict__ key_out, int *__restrict__ idx_out, int n, int shift,
-             const unsigned *__restrict__ block_off, int n_blocks, const unsigned *__restrict__ bin_total) {
-    __shared__ unsigned s_base[256];
-    __shared__ unsigned s_cnt[kClThreads / 32][256];
+k_rs_scatter(ClusterArgs a, int pass) {
+    const Packing pk = packing_of(a.meta);
+    const int shift = pass * kRsBits;
+    if (shift >= pk.total) return;
+    __shared__ unsigned s_cnt[kClThreads / 32][kRsBins];
+    __shared__ unsigned s_base[kRsBins];
     __shared__ unsigned s_w[kClThreads / 32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    {   // base of bin t = totals of the bins before it (block-wide exclusive scan of 256 totals)
+    const unsigned long long *kin = a.key[pass & 1], *pin = a.pay[pass & 1];
+    unsigned long long *kout = a.key[(pass + 1) & 1], *pout = a.pay[(pass + 1) & 1];
+    const unsigned *bin_total = a.block_hist + (size_t)kRsBins * a.n_tiles;
+    {   // base of bin t = totals of the bins before it (block-wide exclusive scan of 256 totals) + this tile's offset
         const unsigned x = bin_total[threadIdx.x];
         unsigned inc = x;
 #pragma unroll
@@ -130,58 +189,58 @@ k_rs_scatter(const unsigned long long *__restrict__ key_in, const int *__restric
             if (lane >= o) inc += t;
         }
         if (lane == 31) s_w[w] = inc;
+#pragma unroll
+        for (int k = 0; k < kClThreads / 32; ++k) s_cnt[k][threadIdx.x] = 0;
         __syncthreads();
         unsigned before = 0;
         for (int k = 0; k < w; ++k) before += s_w[k];
-        s_base[threadIdx.x] = before + inc - x + block_off[threadIdx.x * n_blocks + blockIdx.x];
+        s_base[threadIdx.x] = before + inc - x + a.block_hist[threadIdx.x * a.n_tiles + blockIdx.x];
     }
-    const int base = blockIdx.x * kRsTile;
-    for (int r = 0; r < kRsItems; ++r) {                 // rounds keep the tile's order: the sort is stable
-        for (int k = 0; k < kClThreads / 32; ++k) s_cnt[k][threadIdx.x] = 0;
-        __syncthreads();
-        const int i = base + r * kClThreads + threadIdx.x;
-        const bool live = i < n;
-        unsigned long long key = 0ull;
-        int idx = 0;
-        if (live) { key = key_in[i]; idx = idx_in[i]; }
-        const unsigned d = live ? (unsigned)(key >> shift) & 255u : 256u + lane;      // dead lanes match nobody
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const unsigned rank = __popc(peers & ((1u << lane) - 1u));
-        if (live && rank == 0) s_cnt[w][d] = __popc(peers);
-        __syncthreads();
-        {
-            unsigned run = s_base[threadIdx.x];
-            for (int k = 0; k < kClThreads / 32; ++k) {
-                const unsigned c = s_cnt[k][threadIdx.x];
-                s_cnt[k][threadIdx.x] = run;
-                run += c;
-            }
-            s_base[threadIdx.x] = run;
-        }
-        __syncthreads();
-        if (live) {
-            const unsigned pos = s_cnt[w][d] + rank;
-            key_out[pos] = key;
-            idx_out[pos] = idx;
-        }
-        __syncthreads();
+    unsigned long long key[kRsItems], pay[kRsItems];
+    unsigned rank[kRsItems];
+    const int base = blockIdx.x * kRsTile + w * (32 * kRsItems);
+#pragma unroll
+    for (int r = 0; r < kRsItems; ++r) {
+        const int i = base + r * 32 + lane;
+        key[r] = i < a.n ? kin[i] : 0ull;
+        pay[r] = i < a.n ? pin[i] : 0ull;
     }
-}
-
-// ---- span gather ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kClThreads)
-k_cl_span(ClusterArgs a) {
-    const int i = blockIdx.x * kClThreads + threadIdx.x;
-    if (i < a.n) {
-        const int o = a.idx[i];
-        a.span[i] = a.end[o] - a.start[o];
+#pragma unroll
+    for (int r = 0; r < kRsItems; ++r) {
+        const bool live = base + r * 32 + lane < a.n;
+        const unsigned d = (unsigned)(pk.pack(key[r]) >> shift) & (kRsBins - 1);
+        const unsigned peers = __match_any_sync(0xffffffffu, live ? d : kRsBins + lane);      // dead lanes match nobody
+        const unsigned before = live ? s_cnt[w][d] : 0u;
+        __syncwarp();
+        rank[r] = before + __popc(peers & ((1u << lane) - 1u));
+        if (live && (peers & ((1u << lane) - 1u)) == 0) s_cnt[w][d] = before + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // digit t: the warps' counts -> where each warp's keys of that digit start
+        unsigned run = s_base[threadIdx.x];
+#pragma unroll
+        for (int k = 0; k < kClThreads / 32; ++k) {
+            const unsigned c = s_cnt[k][threadIdx.x];
+            s_cnt[k][threadIdx.x] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kRsItems; ++r) {
+        if (base + r * 32 + lane >= a.n) continue;
+        const unsigned d = (unsigned)(pk.pack(key[r]) >> shift) & (kRsBins - 1);
+        const unsigned pos = s_cnt[w][d] + rank[r];
+        kout[pos] = key[r];
+        pout[pos] = pay[r];
     }
 }
 
 // ---- union-find ----------------------------------------------------------------------------------
 // Path halving: every write re-points x to its CURRENT grandparent, an ancestor read just now.
 // Parents only ever move to smaller indices (roots hang under smaller roots), so concurrent
-// finds / unions can never create a cycle.
+// finds / unions can never create a cycle.  Works on global and on shared memory alike.
 __device__ __forceinline__ int uf_find(volatile int *p, int x) {
     for (;;) {
         const int px = p[x];
@@ -202,17 +261,24 @@ __device__ __forceinline__ void uf_unite(int *parent, int x, int y) {
     }
 }
 
-// windowed pairwise distances: each thread owns sorted position i and scans forward while the
-// neighbour is in the same (contig, type) segment and within the partition window
+// windowed pairwise distances: each thread owns sorted position i and scans forward, out of the tile in
+// shared memory, while the neighbour is in the same (contig, type) segment and within the partition window.
+// A pair that passes is united in the global forest unless a glance at the two parent words shows it
+// connected already (most pairs of a dense cluster are).  (A per-tile forest in shared memory, merged into
+// the global one afterwards, was measured: 0.74 ms against 0.40 ms -- the threads of a dense cluster all
+// start as their own roots there and fight over the same few words.)
 __global__ void __launch_bounds__(kClThreads)
 k_cl_edges(ClusterArgs a) {
     __shared__ unsigned long long s_key[kClThreads + kClHalo];
     __shared__ int s_span[kClThreads + kClHalo];
+    const Packing pk = packing_of(a.meta);
+    const int cur = sorted_buffer(pk);
+    const unsigned long long *key = a.key[cur], *pay = a.pay[cur];
     const int i0 = blockIdx.x * kClThreads;
     for (int t = threadIdx.x; t < kClThreads + kClHalo; t += kClThreads) {
         const int j = i0 + t;
-        s_key[t] = j < a.n ? a.key[j] : ~0ull;
-        s_span[t] = j < a.n ? a.span[j] : 0;
+        s_key[t] = j < a.n ? key[j] : ~0ull;
+        s_span[t] = j < a.n ? (int)(pay[j] >> 32) : 0;
     }
     __syncthreads();
     const int i = i0 + threadIdx.x;
@@ -223,11 +289,12 @@ k_cl_edges(ClusterArgs a) {
     const float nf = (float)a.normalizer, mdf = (float)a.max_distance;
     for (int j = i + 1; j < a.n; ++j) {
         const int t = j - i0;
-        const unsigned long long kj = t < kClThreads + kClHalo ? s_key[t] : a.key[j];
+        const bool in_smem = t < kClThreads + kClHalo;
+        const unsigned long long kj = in_smem ? s_key[t] : key[j];
         if ((unsigned)(kj >> 32) != seg) break;
         const unsigned d2 = (unsigned)kj - c2;              // keys are sorted: non-negative
         if (d2 > a.window2) break;
-        const int sj = t < kClThreads + kClHalo ? s_span[t] : a.span[j];
+        const int sj = in_smem ? s_span[t] : (int)(pay[j] >> 32);
         const int mx = max(si, sj);
         // single precision first: only pairs within 1e-4 of the threshold need the exact fp64 quotients
         const float approx = (float)d2 * 0.5f / nf + (mx > 0 ? (float)abs(si - sj) / (float)mx : 0.0f);
@@ -245,22 +312,26 @@ k_cl_edges(ClusterArgs a) {
 
 __global__ void __launch_bounds__(kClThreads)
 k_cl_label(ClusterArgs a) {
+    const Packing pk = packing_of(a.meta);
+    const unsigned long long *pay = a.pay[sorted_buffer(pk)];
     const int i = blockIdx.x * kClThreads + threadIdx.x;
     bool root = false;
     if (i < a.n) {
         const int r = uf_find(a.parent, i);
         a.parent[i] = r;
         root = r == i;
-        atomicMin(a.minidx + r, a.idx[i]);
+        atomicMin(a.minidx + r, (int)(unsigned)pay[i]);
     }
     const unsigned m = __ballot_sync(0xffffffffu, root);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(a.n_clusters, __popc(m));
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&a.meta->n_clusters, __popc(m));
 }
 
 __global__ void __launch_bounds__(kClThreads)
 k_cl_write(ClusterArgs a) {
+    const Packing pk = packing_of(a.meta);
+    const unsigned long long *pay = a.pay[sorted_buffer(pk)];
     const int i = blockIdx.x * kClThreads + threadIdx.x;
-    if (i < a.n) a.out[a.idx[i]] = a.minidx[a.parent[i]];
+    if (i < a.n) a.out[(int)(unsigned)pay[i]] = a.minidx[a.parent[i]];
 }
 
 }  // namespace duet

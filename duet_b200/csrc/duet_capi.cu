@@ -60,7 +60,7 @@ struct PinBuf {
     }
 };
 
-enum { EV_H2D0, EV_H2D1, EV_X0, EV_K0, EV_K1, EV_K2, EV_K3, EV_K4, EV_K5, EV_K6, EV_D2H0, EV_D2H1, EV_DESC, EV_COUNT };
+enum { EV_H2D0, EV_H2D1, EV_X0, EV_K0, EV_K1, EV_K2, EV_K3, EV_K4, EV_K5, EV_K6, EV_K7, EV_D2H0, EV_D2H1, EV_DESC, EV_COUNT };
 
 }  // namespace
 
@@ -107,7 +107,9 @@ struct duet_handle {
     DevBuf d_counts, d_status;
     // kernel set B (signature clustering)
     DevBuf cl_in[4], cl_key[2], cl_idx[2], cl_span, cl_parent, cl_minidx, cl_out, cl_hist, cl_misc;
-    cudaEvent_t cl_ev[2] = {};
+    cudaEvent_t cl_ev[6] = {};      // staging, keys, sort, edges, label + write
+    int cl_passes = 0;
+    bool cl_timed = false;
 };
 
 namespace {
@@ -587,36 +589,37 @@ static int launch_all(duet_handle *h, cudaStream_t st, bool marks) {
     const bool join = a.n_joins > 0;
     const bool probe = a.n_reads && a.n_joins;
     int n = 0;
+    if (join) { launch(k_init, h->n_sm * 4, kThreads, 0, st, false, false, a); ++n; }
+    mark(EV_K0);
     if (join) {
-        launch(k_init, h->n_sm * 4, kThreads, 0, st, false, false, a);
         switch (h->build_per_thread) {
             case 1: launch(k_table<1>, h->build_grid, kThreads, 0, st, pdl, false, a); break;
             case 2: launch(k_table<2>, h->build_grid, kThreads, 0, st, pdl, false, a); break;
             case 4: launch(k_table<4>, h->build_grid, kThreads, 0, st, pdl, false, a); break;
             default: launch(k_table<8>, h->build_grid, kThreads, 0, st, pdl, false, a); break;
         }
-        n += 2;
+        ++n;
     }
-    mark(EV_K0);
-    if (probe) { launch(k_probe, h->probe_grid, kProbeBlock, h->probe_smem, st, pdl, false, a); ++n; }
     mark(EV_K1);
+    if (probe) { launch(k_probe, h->probe_grid, kProbeBlock, h->probe_smem, st, pdl, false, a); ++n; }
+    mark(EV_K2);
     if (S) {
         const int per = kThreads / h->reduce_lanes;
         if (h->reduce_lanes == kReduceLanesDense) launch(k_reduce<kReduceLanesDense>, (S + per - 1) / per, kThreads, 0, st, pdl && join, false, a);
         else launch(k_reduce<kReduceLanesSparse>, (S + per - 1) / per, kThreads, 0, st, pdl && join, false, a);
         ++n;
     }
-    mark(EV_K2);
+    mark(EV_K3);
     if (S && h->tail_fused) {
         launch(k_tail, a.n_shards * kTailCluster, kThreads, tail_smem_bytes(h->tail_set, h->tail_vals), st, pdl, false, a,
                h->tail_set, h->tail_vals);
         ++n;
     }
-    mark(EV_K3);
-    if (S && !h->tail_fused) { launch(k_oneps, a.n_shards, kThreads, 0, st, pdl, false, a); ++n; }
     mark(EV_K4);
-    if (S && !h->tail_fused) { launch(k_predict, h->predict_grid, kThreads, 0, st, pdl, false, a); ++n; }
+    if (S && !h->tail_fused) { launch(k_oneps, a.n_shards, kThreads, 0, st, pdl, false, a); ++n; }
     mark(EV_K5);
+    if (S && !h->tail_fused) { launch(k_predict, h->predict_grid, kThreads, 0, st, pdl, false, a); ++n; }
+    mark(EV_K6);
     if (S && !h->tail_fused) { launch(k_order, a.n_shards, kThreads, 0, st, pdl, false, a); ++n; }
     return n;
 }
@@ -666,7 +669,7 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
             h->launches += launch_all(h, st, false);
         }
     }
-    CU(h, cudaEventRecord(h->ev[EV_K6], st));
+    CU(h, cudaEventRecord(h->ev[EV_K7], st));
     CU(h, cudaGetLastError());
     h->executed = true;
     return DUET_OK;
@@ -752,10 +755,10 @@ int duet_get_timings(duet_handle *h, duet_timings *t) {
     CU(h, cudaStreamSynchronize(h->stream));
     if (h->have_h2d) cudaEventElapsedTime(&t->h2d_ms, h->ev[EV_H2D0], h->ev[EV_H2D1]);
     if (h->executed) {
-        cudaEventElapsedTime(&t->device_ms, h->ev[EV_X0], h->ev[EV_K6]);
+        cudaEventElapsedTime(&t->device_ms, h->ev[EV_X0], h->ev[EV_K7]);
         if (h->per_kernel) {
-            const int seq[] = {EV_X0, EV_K0, EV_K1, EV_K2, EV_K3, EV_K4, EV_K5, EV_K6};
-            for (int i = 0; i < 7; ++i)
+            const int seq[] = {EV_X0, EV_K0, EV_K1, EV_K2, EV_K3, EV_K4, EV_K5, EV_K6, EV_K7};
+            for (int i = 0; i < 8; ++i)
                 if (cudaEventElapsedTime(&t->kernel_ms[i], h->ev[seq[i]], h->ev[seq[i + 1]]) != cudaSuccess) t->kernel_ms[i] = 0.f;
         }
     }
@@ -796,6 +799,7 @@ int duet_cluster_run(duet_handle *h, const duet_cluster_input *in, const duet_cl
     if (n < 0 || n >= (1ll << 31)) return fail(h, DUET_ERR_INVALID, "duet_cluster_run: n out of range");
     if (n_clusters) *n_clusters = 0;
     if (device_ms) *device_ms = 0.f;
+    h->cl_timed = false;
     if (n == 0) return DUET_OK;
     if (!in->contig || !in->type || !in->start || !in->end)
         return fail(h, DUET_ERR_INVALID, "duet_cluster_run: a column is NULL");
@@ -810,70 +814,72 @@ int duet_cluster_run(duet_handle *h, const duet_cluster_input *in, const duet_cl
     int rc;
     const int32_t *cols[4] = {in->contig, in->type, in->start, in->end};
     const int **dst[4] = {&a.contig, &a.type, &a.start, &a.end};
+    CU(h, cudaEventRecord(h->cl_ev[0], st));
     for (int c = 0; c < 4; ++c) {
         if ((rc = stage(h, h->cl_in[c], cols[c], sizeof(int32_t) * (size_t)n, in->mem, &dv))) return rc;
         *dst[c] = static_cast<const int *>(dv);
     }
     const size_t N = (size_t)n;
-    const int n_tiles = (int)((n + kRsTile - 1) / kRsTile);
+    a.n_tiles = (int)((n + kRsTile - 1) / kRsTile);
     for (int k = 0; k < 2; ++k) {
-        CU(h, h->cl_key[k].reserve(N * 8));
-        CU(h, h->cl_idx[k].reserve(N * 4));
+        CU(h, h->cl_key[k].reserve(N * 8));  a.key[k] = h->cl_key[k].as<unsigned long long>();
+        CU(h, h->cl_idx[k].reserve(N * 8));  a.pay[k] = h->cl_idx[k].as<unsigned long long>();
     }
-    CU(h, h->cl_span.reserve(N * 4));    a.span = h->cl_span.as<int>();
     CU(h, h->cl_parent.reserve(N * 4));  a.parent = h->cl_parent.as<int>();
     CU(h, h->cl_minidx.reserve(N * 4));  a.minidx = h->cl_minidx.as<int>();
-    CU(h, h->cl_hist.reserve(((size_t)n_tiles + 1) * 256 * 4));
-    CU(h, h->cl_misc.reserve(64));
-    a.vary = h->cl_misc.as<unsigned long long>();
-    a.n_clusters = reinterpret_cast<int *>(a.vary + 2);
+    CU(h, h->cl_hist.reserve(((size_t)a.n_tiles + 1) * kRsBins * 4));
+    a.block_hist = h->cl_hist.as<unsigned>();
+    CU(h, h->cl_misc.reserve(sizeof(ClMeta)));
+    a.meta = h->cl_misc.as<ClMeta>();
     if (in->mem == DUET_MEM_DEVICE) a.out = cluster_id;
     else { CU(h, h->cl_out.reserve(N * 4)); a.out = h->cl_out.as<int>(); }
     a.max_distance = params->max_distance;
     a.normalizer = params->position_normalizer;
     a.window2 = 2u * (unsigned)params->partition_window;
 
+    // one stream, no host round trip: how many key bits (sort passes) the call needs is decided on the device
     const int blocks = (int)((n + kClThreads - 1) / kClThreads);
-    CU(h, cudaEventRecord(h->cl_ev[0], st));
-    CU(h, cudaMemsetAsync(h->cl_misc.p, 0, 64, st));
-    a.key = h->cl_key[0].as<unsigned long long>();
-    a.idx = h->cl_idx[0].as<int>();
+    CU(h, cudaMemsetAsync(h->cl_misc.p, 0, sizeof(ClMeta), st));
+    CU(h, cudaEventRecord(h->cl_ev[1], st));
     k_cl_keys<<<blocks, kClThreads, 0, st>>>(a);
-    ++h->launches;
-    unsigned long long vary[2];
-    CU(h, cudaMemcpyAsync(vary, a.vary, 16, cudaMemcpyDeviceToHost, st));
-    CU(h, cudaStreamSynchronize(st));                   // which key bytes differ decides the sort passes
-    if (vary[1]) return fail(h, DUET_ERR_INVALID, "duet_cluster_run: need 0 <= start <= end, start+end < 2^32, contig < 65536, type < 256");
-    int cur = 0;
-    for (int shift = 0; shift < 64; shift += 8) {
-        if (!((vary[0] >> shift) & 0xFFull)) continue;
-        unsigned *hist = h->cl_hist.as<unsigned>();
-        k_rs_hist<<<n_tiles, kClThreads, 0, st>>>(h->cl_key[cur].as<unsigned long long>(), (int)n, shift, hist, n_tiles);
-        unsigned *bin_total = hist + (size_t)n_tiles * 256;
-        k_rs_scan<<<256, kClThreads, 0, st>>>(hist, n_tiles, bin_total);
-        k_rs_scatter<<<n_tiles, kClThreads, 0, st>>>(h->cl_key[cur].as<unsigned long long>(), h->cl_idx[cur].as<int>(),
-                                                      h->cl_key[cur ^ 1].as<unsigned long long>(),
-                                                      h->cl_idx[cur ^ 1].as<int>(), (int)n, shift, hist, n_tiles, bin_total);
-        h->launches += 3;
-        cur ^= 1;
+    CU(h, cudaEventRecord(h->cl_ev[2], st));
+    for (int pass = 0; pass < kRsMaxPasses; ++pass) {
+        k_rs_hist<<<a.n_tiles, kClThreads, 0, st>>>(a, pass);
+        k_rs_scan<<<kRsBins, kClThreads, 0, st>>>(a, pass);
+        k_rs_scatter<<<a.n_tiles, kClThreads, 0, st>>>(a, pass);
     }
-    a.key = h->cl_key[cur].as<unsigned long long>();
-    a.idx = h->cl_idx[cur].as<int>();
-    k_cl_span<<<blocks, kClThreads, 0, st>>>(a);
+    CU(h, cudaEventRecord(h->cl_ev[3], st));
     k_cl_edges<<<blocks, kClThreads, 0, st>>>(a);
+    CU(h, cudaEventRecord(h->cl_ev[4], st));
     k_cl_label<<<blocks, kClThreads, 0, st>>>(a);
     k_cl_write<<<blocks, kClThreads, 0, st>>>(a);
-    h->launches += 4;
-    CU(h, cudaEventRecord(h->cl_ev[1], st));
-    int nc = 0;
-    CU(h, cudaMemcpyAsync(&nc, a.n_clusters, 4, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaEventRecord(h->cl_ev[5], st));
+    ClMeta meta;
+    CU(h, cudaMemcpyAsync(&meta, a.meta, sizeof(meta), cudaMemcpyDeviceToHost, st));
     if (in->mem != DUET_MEM_DEVICE)
         CU(h, cudaMemcpyAsync(cluster_id, a.out, N * 4, cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
     CU(h, cudaGetLastError());
-    if (n_clusters) *n_clusters = nc;
-    if (device_ms) cudaEventElapsedTime(device_ms, h->cl_ev[0], h->cl_ev[1]);
+    if (meta.bad) return fail(h, DUET_ERR_INVALID, "duet_cluster_run: need 0 <= start <= end, start+end < 2^32, contig < 65536, type < 256");
+    const int key_bits = (meta.max_c2 ? 32 - __builtin_clz(meta.max_c2) : 0) + (meta.max_type ? 32 - __builtin_clz(meta.max_type) : 0) +
+                         (meta.max_contig ? 32 - __builtin_clz(meta.max_contig) : 0);
+    h->cl_passes = (key_bits + kRsBits - 1) / kRsBits;
+    h->launches += 1 + 3 * h->cl_passes + 3;            // the passes beyond the key's bits return at once: not counted
+    h->cl_timed = true;
+    if (n_clusters) *n_clusters = meta.n_clusters;
+    if (device_ms) cudaEventElapsedTime(device_ms, h->cl_ev[1], h->cl_ev[5]);
     return DUET_OK;
+}
+
+int duet_cluster_timings(duet_handle *h, const char **names, float *ms, int cap) {
+    static const char *const kNames[4] = {"k_cl_keys", "k_rs_hist + k_rs_scan + k_rs_scatter", "k_cl_edges", "k_cl_label + k_cl_write"};
+    if (!h || !names || !ms || cap < 4 || !h->cl_timed) return 0;
+    for (int k = 0; k < 4; ++k) {
+        names[k] = kNames[k];
+        if (cudaEventElapsedTime(&ms[k], h->cl_ev[1 + k], h->cl_ev[2 + k]) != cudaSuccess) ms[k] = 0.f;
+    }
+    cudaGetLastError();
+    return 4;
 }
 
 }  // extern "C"

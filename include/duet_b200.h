@@ -157,9 +157,9 @@ typedef struct duet_timings {
     float h2d_ms;          /* upload: host -> device copies                       */
     float device_ms;       /* all kernels of one execute                          */
     float d2h_ms;          /* download                                            */
-    float kernel_ms[8];    /* build (k_init + k_table), probe, reduce, tail (k_tail: the three per-contig steps
-                              in one cluster launch), oneps, predict, order (the same steps as separate kernels,
-                              only when a contig has more SVs than a cluster holds), unused */
+    float kernel_ms[8];    /* init (k_init), build (k_table), probe, reduce, tail (k_tail: the three per-contig
+                              steps in one cluster launch), oneps, predict, order (the same steps as separate
+                              kernels, only when a contig has more SVs than a cluster holds) */
 } duet_timings;
 
 typedef struct duet_handle duet_handle;
@@ -229,6 +229,9 @@ void duet_default_cluster_params(duet_cluster_params *p);
  * *device_ms (optional) = device time of the call. */
 int duet_cluster_run(duet_handle *h, const duet_cluster_input *in, const duet_cluster_params *params,
                      int32_t *cluster_id, int64_t *n_clusters, float *device_ms);
+/* Event-timed stages of the last duet_cluster_run (keys; sort passes; windowed distances + union-find;
+ * labels): fills names[k] / ms[k], returns how many (0 if nothing was run). */
+int duet_cluster_timings(duet_handle *h, const char **names, float *ms, int cap);
 
 /* ---- host-side decoders (no GPU needed) -------------------------------------------------- */
 

@@ -80,3 +80,57 @@ def test_gpu_rejects_bad_input():
     with pytest.raises(DuetError):
         cluster_signatures([0], [0], [10], [5])          # end < start
     assert cluster_signatures([], [], [], [])[1] == 0
+
+
+def _oracle_cluster_fn(contig, typ, start, end, cluster_max_distance=0.9, *, position_normalizer=900.0, partition_window=1000):
+    from oracle import cluster_oracle
+    ids, n = cluster_oracle.cluster(contig, typ, start, end, cluster_max_distance, position_normalizer, partition_window)
+    return ids, n, 0.0
+
+
+def _shard_worker(rank, world, port, out_q):
+    import os
+    import sys
+    import torch.distributed as dist
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from duet_b200 import synth
+        from duet_b200.sv_clustering import cluster_signatures_sharded
+        cols = synth.make_signatures(3, 60_000, contigs=["1", "2", "21", "X"])
+        index, ids, total = cluster_signatures_sharded(*cols, cluster_fn=_oracle_cluster_fn)
+        out_q.put((rank, index, ids, total))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_contig_sharded_clustering_equals_single_process():
+    """(contig, type) groups LPT-packed over 3 gloo ranks (the oracle stands in for the device): the union of
+    the ranks' slices is the single-process result, every signature is owned exactly once, the all-reduced
+    cluster count is the global one."""
+    import socket
+    import torch.multiprocessing as mp
+    from duet_b200 import synth
+    from oracle import cluster_oracle
+    cols = synth.make_signatures(3, 60_000, contigs=["1", "2", "21", "X"])
+    want, n_want = cluster_oracle.cluster(*cols)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    merged = np.full(want.shape[0], -1, np.int64)
+    for rank, index, ids, total in got:
+        assert total == n_want
+        assert (merged[index] == -1).all()
+        merged[index] = ids
+    assert np.array_equal(merged, want)
