@@ -251,6 +251,8 @@ class Ctx:
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         torch.cuda.set_device(self.local)
+        from duet_b200.sharding import bind_to_gpu_numa_node
+        self.numa = bind_to_gpu_numa_node(self.local)        # before any page-locked buffer is allocated
         if self.world > 1:
             os.environ.setdefault("NCCL_DEBUG", "WARN")       # a pre-set level (the driver's) is honoured
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
@@ -703,7 +705,7 @@ def main():
                               "note": "SURVEY.md 8(d): 33 B/tagged read + 24 B/join + 64 B/SV over the whole device path, per GPU"},
             "counters": dict(zip(("n_sv", "n_kept", "n_emitted", "n_1|0", "n_0|1", "n_1|1", "n_joins", "n_hits"),
                                  [int(x) for x in all_counts])),
-            "gather_ms": gather_ms, "synth_seconds": gen_s,
+            "gather_ms": gather_ms, "synth_seconds": gen_s, "numa": ctx.numa,
         }
         if strong is not None:
             line["strong"] = strong

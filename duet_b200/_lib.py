@@ -67,7 +67,7 @@ SYMBOLS = (
     "duet_phase_download", "duet_phase_run", "duet_host_alloc", "duet_host_free", "duet_sync",
     "duet_get_timings", "duet_launch_count", "duet_default_cluster_params", "duet_cluster_run", "duet_hash_names",
     "duet_pack_tags", "duet_hash_name_lists", "duet_debug_timers", "duet_decode_bam", "duet_set_decode_threads", "duet_free", "duet_decode_sam_text", "duet_count_lines",
-    "duet_host_is_pinned", "duet_cluster_timings", "duet_decode_reads", "duet_rows_take", "duet_rows_free", "duet_decode_sv_vcf", "duet_svs_take", "duet_svs_free",
+    "duet_host_is_pinned", "duet_phase_input_layout", "duet_phase_output_layout", "duet_cluster_timings", "duet_decode_reads", "duet_rows_take", "duet_rows_free", "duet_decode_sv_vcf", "duet_svs_take", "duet_svs_free",
 )
 DECODE_ERR_INDEX, DECODE_ERR_VALUE, DECODE_ERR_ASCII, DECODE_ERR_RANGE, DECODE_ERR_CAPACITY, DECODE_ERR_FORMAT = 20, 21, 22, 23, 24, 25
 DECODE_FALLBACK = 26
@@ -141,6 +141,10 @@ def load() -> C.CDLL:
     lib.duet_count_lines.argtypes = [C.c_void_p, C.c_int64]
     lib.duet_count_lines.restype = C.c_int64
     lib.duet_host_is_pinned.argtypes = [C.c_void_p]
+    lib.duet_phase_input_layout.argtypes = [C.c_int64, C.c_int64, C.c_void_p]
+    lib.duet_phase_input_layout.restype = C.c_int64
+    lib.duet_phase_output_layout.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
+    lib.duet_phase_output_layout.restype = C.c_int64
     lib.duet_cluster_timings.argtypes = [H, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     lib.duet_decode_reads.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_void_p)] + [C.POINTER(C.c_int64)] * 3
     lib.duet_rows_take.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]

@@ -83,8 +83,7 @@ struct duet_handle {
 
     // staged input copies (HOST mode)
     DevBuf in_read_key, in_read_tag;
-    DevBuf in_sv_pos, in_sv_svlen, in_sv_svread, in_sv_refread, in_sv_flags, in_sv_group;
-    DevBuf in_csr_off, in_csr_key, in_csr_chk;
+    DevBuf in_small;                // sv_* and csr_* columns, laid out by input_layout()
     // descriptors (one page-locked staging buffer -> one device buffer, one copy), table, scratch, outputs
     PinBuf h_desc, h_back;          // h_back: status, per-shard emit counts and the raw order on their way out
     bool desc_in_flight = false;    // EV_DESC marks the end of the last descriptor copy
@@ -102,9 +101,9 @@ struct duet_handle {
     DevBuf d_table;                 // Slot[n_slots], swept to all-ones by k_init at the start of every call
     DevBuf d_bitmap;                // Bloom filter words, zeroed by k_init
     DevBuf d_cand_list;
-    DevBuf d_next, d_join_row, d_n_hit, d_cand, d_oneps, d_oneps_n, d_sort;
-    DevBuf d_gt, d_cls, d_ps, d_hap1, d_hap2, d_hap0, d_allhap, d_t1, d_t2, d_feat, d_order, d_n_emit;
-    DevBuf d_counts, d_status;
+    DevBuf d_next, d_n_hit, d_cand, d_oneps, d_oneps_n, d_sort;
+    DevBuf d_out;                   // every result column (and the join rows), laid out by output_layout()
+    DevBuf d_order, d_n_emit, d_status;
     // kernel set B (signature clustering)
     DevBuf cl_in[4], cl_key[2], cl_idx[2], cl_span, cl_parent, cl_minidx, cl_out, cl_hist, cl_misc;
     cudaEvent_t cl_ev[6] = {};      // staging, keys, sort, edges, label + write
@@ -139,6 +138,28 @@ long long pow2_at_least(long long n) {
     long long p = 1;
     while (p < n) p <<= 1;
     return p;
+}
+
+// Arena layouts.  The small input columns and the results each live in ONE device buffer; a caller whose
+// host arrays follow the same layout inside one page-locked allocation (duet_phase_input_layout /
+// duet_phase_output_layout; engine.pin_batch, engine.pinned_outputs) gets ONE copy each way instead of a
+// dozen ~10 us ones.
+constexpr int kInCols = 9, kOutCols = 12;
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+void input_layout(long long S, long long J, size_t off[kInCols], size_t len[kInCols], size_t *total) {
+    const size_t S1 = (size_t)std::max<long long>(S, 0), J1 = (size_t)std::max<long long>(J, 0);
+    const size_t bytes[kInCols] = {S1 * 4, S1 * 4, S1 * 4, S1 * 4, S1, S1 * 4, (S1 + 1) * 8, J1 * 8, J1 * 4};   // pos svlen svread refread flags group csr_off csr_key csr_chk
+    size_t at = 0;
+    for (int k = 0; k < kInCols; ++k) { off[k] = at; len[k] = bytes[k]; at = align256(at + bytes[k]); }
+    *total = at;
+}
+void output_layout(long long S, long long J, int ns, size_t off[kOutCols], size_t len[kOutCols], size_t *total) {
+    const size_t S1 = (size_t)std::max<long long>(S, 0), J1 = (size_t)std::max<long long>(J, 0);
+    const size_t bytes[kOutCols] = {S1, S1 * 4, S1, S1 * 4, S1 * 4, S1 * 4, S1 * 4, S1 * 8, S1 * 8, S1 * 8 * DUET_N_FEATURES,
+                                    (size_t)ns * 8 * DUET_N_COUNTERS, J1 * 4};   // gt ps cls hap1 hap2 hap0 allhap totsc1 totsc2 features shard_counts join_row
+    size_t at = 0;
+    for (int k = 0; k < kOutCols; ++k) { off[k] = at; len[k] = bytes[k]; at = align256(at + bytes[k] + 16); }
+    *total = at;
 }
 
 // descriptor arena: sections of one host buffer, 256-byte aligned, copied to the device in one piece
@@ -271,13 +292,10 @@ void duet_destroy(duet_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->in_read_key, &h->in_read_tag,
-                      &h->in_sv_pos, &h->in_sv_svlen, &h->in_sv_svread, &h->in_sv_refread, &h->in_sv_flags,
-                      &h->in_sv_group, &h->in_csr_off, &h->in_csr_key, &h->in_csr_chk, &h->d_desc,
+    DevBuf *bufs[] = {&h->in_read_key, &h->in_read_tag, &h->in_small, &h->d_desc,
                       &h->d_c2, &h->d_dbg, &h->d_table, &h->d_bitmap, &h->d_cand_list, &h->d_next,
-                      &h->d_join_row, &h->d_n_hit, &h->d_cand, &h->d_oneps, &h->d_oneps_n, &h->d_sort, &h->d_gt,
-                      &h->d_cls, &h->d_ps, &h->d_hap1, &h->d_hap2, &h->d_hap0, &h->d_allhap, &h->d_t1, &h->d_t2,
-                      &h->d_feat, &h->d_order, &h->d_n_emit, &h->d_counts, &h->d_status};
+                      &h->d_n_hit, &h->d_cand, &h->d_oneps, &h->d_oneps_n, &h->d_sort, &h->d_out,
+                      &h->d_order, &h->d_n_emit, &h->d_status};
     for (DevBuf *b : bufs) b->release();
     h->h_desc.release();
     h->h_back.release();
@@ -328,6 +346,20 @@ int duet_host_is_pinned(const void *ptr) {
 int duet_host_free(void *ptr) {
     if (!ptr) return DUET_OK;
     return cudaFreeHost(ptr) == cudaSuccess ? DUET_OK : DUET_ERR_CUDA;
+}
+
+int64_t duet_phase_input_layout(int64_t n_svs, int64_t n_joins, int64_t *offsets) {
+    size_t off[kInCols], len[kInCols], total;
+    input_layout(n_svs, n_joins, off, len, &total);
+    if (offsets) for (int k = 0; k < kInCols; ++k) offsets[k] = (int64_t)off[k];
+    return (int64_t)total;
+}
+
+int64_t duet_phase_output_layout(int64_t n_svs, int64_t n_joins, int32_t n_shards, int64_t *offsets) {
+    size_t off[kOutCols], len[kOutCols], total;
+    output_layout(n_svs, n_joins, n_shards, off, len, &total);
+    if (offsets) for (int k = 0; k < kOutCols; ++k) offsets[k] = (int64_t)off[k];
+    return (int64_t)total;
 }
 
 int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
@@ -423,15 +455,37 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     } else {
         STAGE(in_read_tag, read_tag, duet_read_tag, R)
     }
-    STAGE(in_sv_pos, sv_pos, int32_t, S)
-    STAGE(in_sv_svlen, sv_svlen, int32_t, S)
-    STAGE(in_sv_svread, sv_svread, int32_t, S)
-    STAGE(in_sv_refread, sv_refread, int32_t, S)
-    STAGE(in_sv_flags, sv_flags, uint8_t, S)
-    STAGE(in_sv_group, sv_group, int32_t, S)
-    STAGE(in_csr_off, csr_off, int64_t, S + 1)
-    STAGE(in_csr_key, csr_key, uint64_t, J)
-    STAGE(in_csr_chk, csr_chk, uint32_t, J)
+    {
+        size_t off[kInCols], len[kInCols], total;
+        input_layout(S, J, off, len, &total);
+        const void *src[kInCols] = {in->sv_pos, in->sv_svlen, in->sv_svread, in->sv_refread, in->sv_flags, in->sv_group,
+                                    in->csr_off, in->csr_key, in->csr_chk};
+        const void **dst[kInCols] = {reinterpret_cast<const void **>(&a.sv_pos), reinterpret_cast<const void **>(&a.sv_svlen),
+                                     reinterpret_cast<const void **>(&a.sv_svread), reinterpret_cast<const void **>(&a.sv_refread),
+                                     reinterpret_cast<const void **>(&a.sv_flags), reinterpret_cast<const void **>(&a.sv_group),
+                                     reinterpret_cast<const void **>(&a.csr_off), reinterpret_cast<const void **>(&a.csr_key),
+                                     reinterpret_cast<const void **>(&a.csr_chk)};
+        if (mem == DUET_MEM_DEVICE) {
+            for (int k = 0; k < kInCols; ++k) *dst[k] = src[k];
+        } else {
+            CU(h, h->in_small.reserve(total + 256));
+            unsigned char *dev = h->in_small.as<unsigned char>();
+            // one copy when the host columns sit in one allocation at the layout's offsets (engine.pin_batch, the stage)
+            const unsigned char *base = src[0] ? static_cast<const unsigned char *>(src[0]) - off[0] : nullptr;
+            bool arena = base != nullptr;
+            for (int k = 0; k < kInCols && arena; ++k)
+                if (src[k] != nullptr && static_cast<const unsigned char *>(src[k]) != base + off[k]) arena = false;
+            if (arena && src[5] == nullptr) arena = false;              // a missing column: the arena would copy garbage over it
+            if (arena && src[8] == nullptr) arena = false;
+            if (arena) {
+                CU(h, cudaMemcpyAsync(dev, base, off[kInCols - 1] + len[kInCols - 1], cudaMemcpyHostToDevice, st));
+            } else {
+                for (int k = 0; k < kInCols; ++k)
+                    if (src[k] && len[k]) CU(h, cudaMemcpyAsync(dev + off[k], src[k], len[k], cudaMemcpyHostToDevice, st));
+            }
+            for (int k = 0; k < kInCols; ++k) *dst[k] = src[k] ? dev + off[k] : nullptr;
+        }
+    }
 #undef STAGE
 
     // ---- descriptors: shard offsets, table / filter ranges and the per-block tiles of every kernel (what a
@@ -542,7 +596,6 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     a.bitmap = h->d_bitmap.as<unsigned>();
     CU(h, h->d_cand_list.reserve((size_t)std::max<long long>(R, 1) * 16)); a.cand_list = h->d_cand_list.as<ulonglong2>();
     CU(h, h->d_next.reserve(J1 * 4));                    a.next = h->d_next.as<int>();
-    CU(h, h->d_join_row.reserve(J1 * 4 + 16));                a.join_row = h->d_join_row.as<int>();
     CU(h, h->d_n_hit.reserve(S1 * 4));                   a.n_hit = h->d_n_hit.as<int>();
     CU(h, h->d_cand.reserve(S1 * 8));                    a.cand = h->d_cand.as<long long>();
     CU(h, h->d_oneps.reserve(S1 * 4));                   a.oneps = h->d_oneps.as<int>();
@@ -550,24 +603,26 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     CU(h, h->d_sort.reserve(S1 * 32));                   a.sort_scratch = h->d_sort.as<long long>();
     CU(h, h->d_c2.reserve(S1 * sizeof(C2Rec)));          a.c2rec = h->d_c2.as<C2Rec>();
 
-    CU(h, h->d_gt.reserve(S1));                          a.gt = h->d_gt.as<uint8_t>();
-    CU(h, h->d_cls.reserve(S1));                         a.cls = h->d_cls.as<uint8_t>();
-    CU(h, h->d_ps.reserve(S1 * 4));                      a.ps = h->d_ps.as<int>();
-    CU(h, h->d_hap1.reserve(S1 * 4));                    a.hap1 = h->d_hap1.as<int>();
-    CU(h, h->d_hap2.reserve(S1 * 4));                    a.hap2 = h->d_hap2.as<int>();
-    CU(h, h->d_hap0.reserve(S1 * 4));                    a.hap0 = h->d_hap0.as<int>();
-    CU(h, h->d_allhap.reserve(S1 * 4));                  a.allhap = h->d_allhap.as<int>();
-    CU(h, h->d_t1.reserve(S1 * 8));                      a.totsc1 = h->d_t1.as<long long>();
-    CU(h, h->d_t2.reserve(S1 * 8));                      a.totsc2 = h->d_t2.as<long long>();
-    CU(h, h->d_feat.reserve(S1 * 8 * DUET_N_FEATURES));  a.features = h->d_feat.as<double>();
+    {
+        size_t off[kOutCols], len[kOutCols], total;
+        output_layout(S, J, ns, off, len, &total);
+        CU(h, h->d_out.reserve(total + 256));
+        unsigned char *o = h->d_out.as<unsigned char>();
+        a.gt = o + off[0]; a.ps = reinterpret_cast<int *>(o + off[1]); a.cls = o + off[2];
+        a.hap1 = reinterpret_cast<int *>(o + off[3]); a.hap2 = reinterpret_cast<int *>(o + off[4]);
+        a.hap0 = reinterpret_cast<int *>(o + off[5]); a.allhap = reinterpret_cast<int *>(o + off[6]);
+        a.totsc1 = reinterpret_cast<long long *>(o + off[7]); a.totsc2 = reinterpret_cast<long long *>(o + off[8]);
+        a.features = reinterpret_cast<double *>(o + off[9]);
+        a.shard_counts = reinterpret_cast<long long *>(o + off[10]);
+        a.join_row = reinterpret_cast<int *>(o + off[11]);
+    }
     CU(h, h->d_order.reserve(S1 * 4));                   a.order = h->d_order.as<int>();
     CU(h, h->d_n_emit.reserve((size_t)ns * 4));          a.n_emit = h->d_n_emit.as<int>();
-    CU(h, h->d_counts.reserve((size_t)ns * 8 * DUET_N_COUNTERS)); a.shard_counts = h->d_counts.as<long long>();
     CU(h, h->d_status.reserve(sizeof(DevStatus)));       a.status = h->d_status.as<DevStatus>();
     // state the kernels keep clean between calls: counters of shards without SVs stay zero, status zero
     CU(h, cudaMemsetAsync(h->d_oneps_n.p, 0, (size_t)ns * 4, st));
     CU(h, cudaMemsetAsync(h->d_n_emit.p, 0, (size_t)ns * 4, st));
-    CU(h, cudaMemsetAsync(h->d_counts.p, 0, (size_t)ns * 8 * DUET_N_COUNTERS, st));
+    CU(h, cudaMemsetAsync(a.shard_counts, 0, (size_t)ns * 8 * DUET_N_COUNTERS, st));
     CU(h, cudaMemsetAsync(h->d_status.p, 0, sizeof(DevStatus), st));
     if (h->dbg_on) {
         CU(h, h->d_dbg.reserve((size_t)4 * kDbgBlocks * kDbgMarks * 2 * 8));
@@ -699,23 +754,30 @@ int duet_phase_download(duet_handle *h, duet_phase_output *out) {
     int *order_raw = reinterpret_cast<int *>(back + off_order);
     CU(h, cudaEventRecord(h->ev[EV_D2H0], st));
     CU(h, cudaMemcpyAsync(&status, a.status, sizeof(status), cudaMemcpyDeviceToHost, st));
-#define PULL(dst, src, bytes)                                                                        \
-    if ((dst) != nullptr && (bytes) != 0) CU(h, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, st));
-    PULL(out->gt, a.gt, S)
-    PULL(out->ps, a.ps, S * 4)
-    PULL(out->cls, a.cls, S)
-    PULL(out->hap1, a.hap1, S * 4)
-    PULL(out->hap2, a.hap2, S * 4)
-    PULL(out->hap0, a.hap0, S * 4)
-    PULL(out->allhap, a.allhap, S * 4)
-    PULL(out->totsc1, a.totsc1, S * 8)
-    PULL(out->totsc2, a.totsc2, S * 8)
-    PULL(out->features, a.features, S * 8 * DUET_N_FEATURES)
-    PULL(out->join_row, a.join_row, J * 4)
-    PULL(out->shard_counts, a.shard_counts, ns * 8 * DUET_N_COUNTERS)
+    {
+        size_t off[kOutCols], len[kOutCols], total;
+        output_layout((long long)S, (long long)J, a.n_shards, off, len, &total);
+        void *dst[kOutCols] = {out->gt, out->ps, out->cls, out->hap1, out->hap2, out->hap0, out->allhap, out->totsc1, out->totsc2,
+                               out->features, out->shard_counts, out->join_row};
+        const unsigned char *dev = h->d_out.as<unsigned char>();
+        // one copy when the host arrays sit in one allocation at the layout's offsets (engine.pinned_outputs)
+        unsigned char *base = dst[0] ? static_cast<unsigned char *>(dst[0]) - off[0] : nullptr;
+        int last = -1;
+        bool arena = base != nullptr;
+        for (int k = 0; k < kOutCols && arena; ++k) {
+            if (dst[k] == nullptr) { for (int m = k + 1; m < kOutCols; ++m) if (dst[m]) arena = false; break; }   // only a tail may be missing
+            if (static_cast<unsigned char *>(dst[k]) != base + off[k]) arena = false;
+            last = k;
+        }
+        if (arena && last >= 0) {
+            CU(h, cudaMemcpyAsync(base, dev, off[last] + len[last], cudaMemcpyDeviceToHost, st));
+        } else {
+            for (int k = 0; k < kOutCols; ++k)
+                if (dst[k] && len[k]) CU(h, cudaMemcpyAsync(dst[k], dev + off[k], len[k], cudaMemcpyDeviceToHost, st));
+        }
+    }
     CU(h, cudaMemcpyAsync(n_emit, a.n_emit, sizeof(int) * ns, cudaMemcpyDeviceToHost, st));
     if (out->order && S) CU(h, cudaMemcpyAsync(order_raw, a.order, S * 4, cudaMemcpyDeviceToHost, st));
-#undef PULL
     CU(h, cudaEventRecord(h->ev[EV_D2H1], st));
     CU(h, cudaStreamSynchronize(st));
     h->have_d2h = true;

@@ -203,23 +203,63 @@ def pinned_empty(shape, dtype) -> np.ndarray:
 _COLUMNS = _lib.INPUT_COLUMNS
 
 
-def pinned_outputs(batch: PhaseBatch) -> dict:
-    """Page-locked result arrays for `PhaseEngine.run(batch, buffers=...)` / `download(buffers=...)`."""
+_IN_ARENA = (("sv_pos", np.int32, 0), ("sv_svlen", np.int32, 0), ("sv_svread", np.int32, 0), ("sv_refread", np.int32, 0),
+             ("sv_flags", np.uint8, 0), ("sv_group", np.int32, 0), ("csr_off", np.int64, 1), ("csr_key", np.uint64, 2),
+             ("csr_chk", np.uint32, 2))          # name, dtype, length kind: 0 = S, 1 = S + 1, 2 = J
+_OUT_ARENA = ("gt", "ps", "cls", "hap1", "hap2", "hap0", "allhap", "totsc1", "totsc2", "features", "shard_counts", "join_row")
+
+
+def input_arena(n_svs: int, n_joins: int, raw_alloc=None) -> dict:
+    """The small input columns as views into ONE page-locked allocation at the offsets the library keeps
+    them at on the device (duet_phase_input_layout): duet_phase_upload then moves them with one copy."""
+    lib = _lib.load()
+    off = (C.c_int64 * 9)()
+    total = int(lib.duet_phase_input_layout(n_svs, n_joins, off))
+    raw = (raw_alloc or (lambda n: pinned_empty(n, np.uint8)))(max(total, 64))
+    out = {}
+    for k, (name, dt, kind) in enumerate(_IN_ARENA):
+        n = (n_svs, n_svs + 1, n_joins)[kind]
+        out[name] = raw[off[k]:off[k] + n * np.dtype(dt).itemsize].view(dt)
+    return out
+
+
+def pinned_outputs(batch: PhaseBatch, raw_alloc=None) -> dict:
+    """Page-locked result arrays for `PhaseEngine.run(batch, buffers=...)` / `download(buffers=...)`: views into
+    ONE allocation at the library's own result layout (duet_phase_output_layout), so the download is one copy."""
+    lib = _lib.load()
     S, J, ns = batch.n_svs, batch.n_joins, batch.n_shards
+    off = (C.c_int64 * 12)()
+    total = int(lib.duet_phase_output_layout(S, J, ns, off))
+    alloc = raw_alloc or (lambda n: pinned_empty(n, np.uint8))
+    raw = alloc(max(total, 64))
     shapes = {"gt": (S, np.uint8), "ps": (S, np.int32), "cls": (S, np.uint8), "hap1": (S, np.int32),
               "hap2": (S, np.int32), "hap0": (S, np.int32), "allhap": (S, np.int32), "totsc1": (S, np.int64),
               "totsc2": (S, np.int64), "features": ((_lib.N_FEATURES, S), np.float64), "join_row": (J, np.int32),
-              "order": (S, np.int32), "shard_counts": ((ns, _lib.N_COUNTERS), np.int64)}
-    return {k: pinned_empty(shape, dt) for k, (shape, dt) in shapes.items()}
+              "shard_counts": ((ns, _lib.N_COUNTERS), np.int64)}
+    out = {}
+    for k, name in enumerate(_OUT_ARENA):
+        shape, dt = shapes[name]
+        n = int(np.prod(shape))
+        out[name] = raw[off[k]:off[k] + n * np.dtype(dt).itemsize].view(dt).reshape(shape)
+    out["order"] = alloc(max(S * 4, 64))[:S * 4].view(np.int32)
+    return out
 
 
 def pin_batch(batch: PhaseBatch) -> PhaseBatch:
-    """Copy every column into page-locked memory (what a decoder writing into duet_host_alloc'd
-    buffers produces directly)."""
+    """Copy every column into page-locked memory (what a decoder writing into duet_host_alloc'd buffers
+    produces directly); the small columns go into one arena (see input_arena)."""
     import dataclasses
     new = {}
+    small = input_arena(batch.n_svs, batch.n_joins)
     for name in _COLUMNS:
         arr = getattr(batch, name)
+        if name in small:
+            if arr is None and name == "csr_chk":
+                continue                            # absent check words mean "do not check": stays absent
+            dst = small[name]
+            dst[...] = 0 if arr is None else arr    # an absent sv_group column: all zero means the same
+            new[name] = dst
+            continue
         if arr is None:
             continue
         dst = pinned_empty(arr.shape, arr.dtype)

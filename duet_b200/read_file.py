@@ -167,22 +167,23 @@ class SvColumns:
     svread: np.ndarray
     refread: np.ndarray
     flags: np.ndarray         # uint8 [S]
-    group: np.ndarray | None  # int32 [S] rank of the CHROM string inside its contig, None when all zero
+    group: np.ndarray         # int32 [S] rank of the CHROM string inside its contig (all zero unless has_groups)
     csr_off: np.ndarray       # int64 [S + 1]
     csr_key: np.ndarray       # uint64 [J]
     csr_chk: np.ndarray       # uint32 [J]
     text: object              # the VCF bytes the spans point into
     str_span: np.ndarray      # int64 [S, 4, 2]: CHROM, REF, ALT, SVTYPE
+    has_groups: bool = False
 
 
-def decode_sv_vcf(vcf_file, include_all_ctgs, threads: int = 1, alloc=None):
+def decode_sv_vcf(vcf_file, include_all_ctgs, threads: int = 1, arena=None):
     """One multi-threaded native pass over the SV VCF -> SvColumns, or None when the file is outside what
     the native reader reproduces exactly (then `parse_vcf`, the general reader, decides -- and raises what
-    the reference raises).  `alloc(shape, dtype)` supplies the arrays (page-locked ones, for the device)."""
+    the reference raises).  `arena(n_svs, n_joins)` supplies the column arrays by name (engine.input_arena:
+    views into one page-locked allocation); default: plain numpy arrays."""
     import ctypes as C
     from . import _lib
     lib = _lib.load()
-    alloc = alloc or (lambda shape, dt: np.empty(shape, dt))
     chrom_list = init_chrom_list(include_all_ctgs, vcf_file[:len(vcf_file) - 24])
     if any("\n" in c for c in chrom_list) or not chrom_list:
         return None
@@ -196,13 +197,17 @@ def decode_sv_vcf(vcf_file, include_all_ctgs, threads: int = 1, alloc=None):
     if rc != _lib.DUET_OK:
         return None
     S, J, nc = n_svs.value, n_joins.value, len(chrom_list)
-    cols = SvColumns(alloc(nc + 1, np.int64), alloc(S, np.int32), alloc(S, np.int32), alloc(S, np.int32), alloc(S, np.int32),
-                     alloc(S, np.uint8), alloc(S, np.int32), alloc(S + 1, np.int64), alloc(J, np.uint64), alloc(J, np.uint32),
-                     text, np.empty((S, 4, 2), np.int64))
+    if arena is not None:
+        a = arena(S, J)
+    else:
+        a = {"sv_pos": np.empty(S, np.int32), "sv_svlen": np.empty(S, np.int32), "sv_svread": np.empty(S, np.int32),
+             "sv_refread": np.empty(S, np.int32), "sv_flags": np.empty(S, np.uint8), "sv_group": np.empty(S, np.int32),
+             "csr_off": np.empty(S + 1, np.int64), "csr_key": np.empty(J, np.uint64), "csr_chk": np.empty(J, np.uint32)}
+    cols = SvColumns(np.empty(nc + 1, np.int64), a["sv_pos"], a["sv_svlen"], a["sv_svread"], a["sv_refread"], a["sv_flags"],
+                     a["sv_group"], a["csr_off"], a["csr_key"], a["csr_chk"], text, np.empty((S, 4, 2), np.int64))
     has_groups = C.c_int32()
     lib.duet_svs_take(job, cols.sv_off.ctypes.data, cols.pos.ctypes.data, cols.svlen.ctypes.data, cols.svread.ctypes.data,
                       cols.refread.ctypes.data, cols.flags.ctypes.data, cols.group.ctypes.data, C.byref(has_groups),
                       cols.csr_off.ctypes.data, cols.csr_key.ctypes.data, cols.csr_chk.ctypes.data, cols.str_span.ctypes.data)
-    if not has_groups.value:
-        cols.group = None
+    cols.has_groups = bool(has_groups.value)
     return cols

@@ -17,6 +17,40 @@ import numpy as np
 from . import _lib
 
 
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (and so, by first touch, its page-locked
+    buffers to that node's memory).  With one process per GPU and nothing bound, eight ranks' uploads and in-place
+    tag gathers cross the socket interconnect and contend for the same root complexes (round 1: e2e efficiency
+    0.59 at 8 GPUs).  Best effort: returns what it did; never raises."""
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                     # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(bound=True, cpus=len(allowed))
+    except Exception as e:                                  # noqa: BLE001 -- a machine without sysfs / nvml: leave it
+        info["error"] = type(e).__name__
+    return info
+
+
 def lpt_assign(weights, n_bins: int) -> list[list[int]]:
     """Longest-processing-time-first bin packing; deterministic on every rank.  Items of equal load
     (in particular the zero-weight ones: contigs without a haplotagged BAM) go to the bin holding the

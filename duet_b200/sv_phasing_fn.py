@@ -13,7 +13,6 @@ There is no CPU compute path: without libduet_b200.so and a CUDA device these fu
 from __future__ import annotations
 
 import ctypes as C
-import itertools
 import logging
 import os
 import shlex
@@ -392,6 +391,7 @@ def _fast_batch(vcf_path, sam_home, thread, include_all_ctgs):
     when an input is outside what the native readers claim (then the general path below takes over)."""
     from concurrent.futures import ThreadPoolExecutor
     from .columnar import TextColumn
+    from .engine import input_arena
     from .read_file import decode_sv_vcf
     chrom_list = init_chrom_list(include_all_ctgs, sam_home[:len(sam_home) - 13])
     paths = _hap_paths(sam_home, chrom_list)
@@ -405,9 +405,8 @@ def _fast_batch(vcf_path, sam_home, thread, include_all_ctgs):
         with ThreadPoolExecutor(max_workers=workers) as ex:
             futs = [ex.submit(_ReadJob, p) if p else None for p in paths]
             logging.info("extract SV signatures")
-            numbered = itertools.count()
             svs = decode_sv_vcf(vcf_path, include_all_ctgs, thread,
-                                alloc=lambda shape, dt: pool.get(f"sv_col{next(numbered)}", shape, dt))
+                                arena=lambda S, J: input_arena(S, J, raw_alloc=lambda n: pool.get("sv_arena", n, np.uint8)))
             try:
                 jobs = [f.result() if f else None for f in futs]
             except _NotBam:
@@ -425,10 +424,9 @@ def _fast_batch(vcf_path, sam_home, thread, include_all_ctgs):
         for ctg, j in zip(chrom_list, jobs):
             if j:
                 logging.info(("  signatures extracted from " if j.n_records else "  no signature from ") + ctg)
-        svlen_abs = pool.get("svlen_abs", svs.svlen.shape[0], np.int32)
-        np.abs(svs.svlen, out=svlen_abs)
+        np.abs(svs.svlen, out=svs.svlen)                          # the device column is |SVLEN| (:62); rows take the sign from SVTYPE
         tc = lambda k, pre="", suf="": TextColumn(svs.text, svs.str_span[:, k, :], pre, suf)
-        batch = PhaseBatch(read_off, svs.sv_off, read_key, read_tag, svs.pos, svlen_abs, svs.svread, svs.refread, svs.flags,
+        batch = PhaseBatch(read_off, svs.sv_off, read_key, read_tag, svs.pos, svs.svlen, svs.svread, svs.refread, svs.flags,
                            svs.group, svs.csr_off, svs.csr_key, svs.csr_chk, [0] * ns, list(chrom_list),
                            tc(0), tc(3), tc(1), tc(2))
         batch.validate()

@@ -177,6 +177,16 @@ int duet_set_thresholds(duet_handle *h, const duet_thresholds *t);
  * handle; NULL = the handle's own non-blocking stream (default). */
 int duet_set_stream(duet_handle *h, void *cuda_stream);
 
+/* Arena layouts.  The library keeps the small input columns (sv_pos, sv_svlen, sv_svread, sv_refread, sv_flags,
+ * sv_group, csr_off, csr_key, csr_chk -- in this order) in one device buffer and the results (gt, ps, cls, hap1,
+ * hap2, hap0, allhap, totsc1, totsc2, features, shard_counts, join_row -- in this order) in another.  A caller
+ * whose host arrays sit at the same offsets inside ONE page-locked allocation gets one copy each way instead of
+ * one per column: `offsets` receives the 9 / 12 byte offsets, the return value is the arena size.  (Trailing
+ * results may be left NULL -- e.g. no join_row; `order` is separate in any case.)  Arrays placed any other way
+ * work too: they are copied one by one. */
+int64_t duet_phase_input_layout(int64_t n_svs, int64_t n_joins, int64_t *offsets);
+int64_t duet_phase_output_layout(int64_t n_svs, int64_t n_joins, int32_t n_shards, int64_t *offsets);
+
 /* Stage the columns on the device (copy for HOST, alias for DEVICE) and size the join table. */
 int duet_phase_upload(duet_handle *h, const duet_phase_input *in);
 /* Launch the whole path on the staged columns (asynchronous; may be called repeatedly).

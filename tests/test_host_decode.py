@@ -319,7 +319,7 @@ def _vcf_columns_equal(native, general, vcf_path):
     for cs in general:
         order = {c: i for i, c in enumerate(sorted(set(cs.chrom)))}
         ranks += [order[c] for c in cs.chrom]
-    assert (native.group.tolist() if native.group is not None else [0] * len(ranks)) == ranks
+    assert native.group.tolist() == ranks and native.has_groups == any(ranks)
 
 
 @pytest.mark.parametrize("name", [n for n in golden_e2e_names() if n != "all_ctgs"])
