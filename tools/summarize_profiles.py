@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turn what tools/collect_profiles.sh left in gpurun_out/ into the tracked summaries under profiles/.
-    python tools/summarize_profiles.py r1j
-Needs `ncu` (reads gpurun_out/prof_all.ncu-rep); runs in the build container, no GPU."""
+    python tools/summarize_profiles.py r2a
+Needs `ncu` (reads gpurun_out/prof/prof_all.ncu-rep) and cuobjdump; runs in the build container, no GPU."""
 import collections
 import csv
 import io
@@ -12,16 +12,18 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+G, P = os.path.join(ROOT, "gpurun_out", "prof"), os.path.join(ROOT, "profiles")
 tag = sys.argv[1] if len(sys.argv) > 1 else "rX"
-STAGES = ["init", "build", "probe", "reduce", "oneps", "predict", "order"]      # bench.py's names, in launch order
+STAGES = ["init", "build", "probe", "reduce", "tail"]      # bench.py's names, in launch order
 
-for w in ("c1", "c2", "c4", "c5", "ref"):
+for w in ("c2", "ref"):
     src = os.path.join(G, f"bench_{w}.json")
     if os.path.exists(src):
         shutil.copy(src, os.path.join(P, f"{tag}_bench_{w}.json"))
 shutil.copy(os.path.join(G, "launches.csv"), os.path.join(P, f"{tag}_launches_c2.csv"))
 shutil.copy(os.path.join(G, "timeline_c2.txt"), os.path.join(P, f"{tag}_timeline_c2.txt"))
+if os.path.exists(os.path.join(G, "timeline_c5.txt")):
+    shutil.copy(os.path.join(G, "timeline_c5.txt"), os.path.join(P, f"{tag}_timeline_c5.txt"))
 
 # ---- launch list: average per kernel, share of one call ----
 rows = list(csv.reader(open(os.path.join(G, "launches.csv"))))
@@ -67,19 +69,19 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 bench = json.loads(open(os.path.join(G, "bench_c2.json")).read().strip().splitlines()[-1])
 km = bench["kernel_ms"]
 tot = sum(km.values())
-L = [f"# {tag}: ncu --set full of the seven launches of one call, C2 (caches flushed by ncu before each kernel; kernels "
+L = [f"# {tag}: ncu --set full of the five launches of one call, C2 (caches flushed by ncu before each kernel; kernels "
      "serialised, so no programmatic-launch overlap)", "",
-     "`ncu --set full --clock-control none --import-source on -k regex:k_ -s 28 -c 7 python bench.py --steps 3 --warmup 3` "
-     "(tools/collect_profiles.sh; this file: tools/summarize_profiles.py)", "",
+     "`ncu --set full --clock-control none --import-source on -k regex:k_ -s 15 -c 5 python bench.py --steps 3 --warmup 3 "
+     "--no-configs --no-cpu-baseline --no-stage-wall` (tools/collect_profiles.sh; this file: tools/summarize_profiles.py)", "",
      "| metric | " + " | ".join(names) + " | unit |", "|---|" + "---|" * (len(names) + 1)]
 for w in want:
     if w in h:
         i = h.index(w)
         L.append("| " + w + " | " + " | ".join(r[i] for r in data) + " | " + units[i] + " |")
 L += ["",
-      "k_probe's SASS contains UBLKCP (cp.async.bulk, TMA) and SYNCS (mbarrier); every kernel contains PREEXIT / ACQBULK",
-      "(`griddepcontrol.launch_dependents` / `.wait`, programmatic dependent launch).",
-      "`dram__bytes` here are cold-cache figures: ncu flushes L2 before each kernel, so e.g. k_probe's filter copies and slot",
+      f"SASS evidence (UBLKCP = cp.async.bulk / TMA, SYNCS = mbarrier, PREEXIT / ACQBULK = programmatic dependent launch, UCGABAR = ",
+      f"cluster barrier): profiles/{tag}_sass_summary.txt.",
+      "`dram__bytes` here are cold-cache figures: ncu flushes L2 before each kernel, so e.g. k_probe's filter copy and slot",
       "lookups come from DRAM, while in a real call k_init / k_table wrote them microseconds earlier and they sit in L2.", "",
       f"{tag}_launches_c2.csv -- launch list of `python bench.py --steps 2 --warmup 1` (`--metrics gpu__time_duration.sum",
       "--clock-control none`; cold caches, serialised). Average per launch and share of one call:", ""]
@@ -88,7 +90,7 @@ L += [f"- ({k} with the tag records left in page-locked host memory, `e2e` mode:
       "launches -- the gather over PCIe)" for k, v in bus.items()]
 L += ["", f"Event-timed stages of the same kernels inside bench.py ({tag}_bench_c2.json, serial, L2 flushed between steps): "
       + ", ".join(f"{k} {km[k] * 1e3:.1f} us ({100 * km[k] / tot:.1f} %)" for k in STAGES)
-      + f" -- the shares agree. The graph replay that `value` measures takes {bench['ms_per_step'] * 1e3:.1f} us for the seven "
+      + f" -- the shares agree. The graph replay that `value` measures takes {bench['ms_per_step'] * 1e3:.1f} us for the five "
       "(programmatic dependent launch overlaps each kernel's set-up with its predecessor's tail).",
       f"{tag}_timeline_c2.txt -- per-block stamps in graph-replay mode: where inside each kernel the microseconds go."]
 open(os.path.join(P, f"{tag}_ncu_all_kernels_c2.md"), "w").write("\n".join(L) + "\n")
@@ -105,6 +107,48 @@ tj = json.load(open(path))
 tj["c2"] = tr
 tj["_note"] = (f"dram__bytes_read.sum + dram__bytes_write.sum per launch, bytes, from profiles/{tag}_ncu_all_kernels_c2.md "
                "(ncu --set full, cold caches); stages as bench.py times them: init = k_init, build = k_table, probe = k_probe "
-               "(stream + candidate resolution), reduce = k_reduce, predict = k_predict")
+               "(stream + candidate resolution), reduce = k_reduce, tail = k_tail")
+# ---- clustering capture ----
+c3 = os.path.join(G, "prof_c3.ncu-rep")
+if os.path.exists(c3):
+    raw = subprocess.run(["ncu", "-i", c3, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    t3 = list(csv.reader(io.StringIO(raw)))
+    h3, u3, d3 = t3[0], t3[1], t3[2:]
+    per = collections.OrderedDict()
+    for r in d3:
+        nm = r[h3.index("Kernel Name")].split("(")[0].replace("void ", "")
+        e = per.setdefault(nm, {"n": 0, "us": 0.0, "rd": 0.0, "wr": 0.0})
+        e["n"] += 1
+        e["us"] += float(r[h3.index("gpu__time_duration.sum")].replace(",", "")) * {"us": 1, "usecond": 1, "ns": 1e-3, "nsecond": 1e-3, "ms": 1e3, "msecond": 1e3}[u3[h3.index("gpu__time_duration.sum")]]
+        for key, col in (("rd", "dram__bytes_read.sum"), ("wr", "dram__bytes_write.sum")):
+            i = h3.index(col)
+            e[key] += float(r[i].replace(",", "")) * {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "Gbyte": 1e9}[u3[i]]
+    M = [f"# {tag}: ncu --set full of one clustering call (C3: 2 M signatures), per kernel, summed over its launches", "",
+         "| kernel | launches | time (us) | dram read (MB) | dram write (MB) |", "|---|---|---|---|---|"]
+    M += [f"| {k} | {v['n']} | {v['us']:.1f} | {v['rd'] / 1e6:.1f} | {v['wr'] / 1e6:.1f} |" for k, v in per.items()]
+    M += ["", "Sort passes beyond the key's 36 bits return at once (the launches with ~2 us).  Parity: bit-exact against",
+          "oracle/cluster_oracle.py, which restates THIS spec; SVIM parity unpinned (svim clusters by average linkage)."]
+    open(os.path.join(P, f"{tag}_ncu_cluster_c3.md"), "w").write("\n".join(M) + "\n")
+    tj["c3"] = {k: v["rd"] + v["wr"] for k, v in per.items()}
 json.dump(tj, open(path, "w"), indent=1)
+
+# ---- SASS evidence ----
+lib = os.path.join(ROOT, "duet_b200", "csrc", "libduet_b200.so")
+sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+cur, counts = None, collections.OrderedDict()
+for line in sass.splitlines():
+    if "Function :" in line:
+        cur = line.split("Function :")[1].strip()
+        counts[cur] = collections.Counter()
+    elif cur:
+        for mn in ("UBLKCP", "SYNCS", "PREEXIT", "ACQBULK", "UCGABAR", "ATOMG", "ATOMS", "RED.", "MATCH", "UTMALDG", "UTCMMA", "LDTM"):
+            if mn in line:
+                counts[cur][mn] += 1
+S = [f"# {tag}: `cuobjdump -sass duet_b200/csrc/libduet_b200.so | grep -c` per kernel (sm_100a)",
+     "# UBLKCP = cp.async.bulk (TMA bulk copy), SYNCS = mbarrier, PREEXIT / ACQBULK = griddepcontrol.launch_dependents / .wait,",
+     "# UCGABAR = barrier.cluster, MATCH = match.any, ATOMG / ATOMS / RED = global / shared atomics.  No UTMALDG / UTCMMA / LDTM:",
+     "# the path has no tensor (2-D) tile and no dense contraction, so tcgen05 / TMEM are not used (BASELINE.json north_star).", ""]
+for fn, c in counts.items():
+    S.append(f"{fn}: " + (", ".join(f"{k}x{v}" for k, v in c.items()) or "-"))
+open(os.path.join(P, f"{tag}_sass_summary.txt"), "w").write("\n".join(S) + "\n")
 print(open(os.path.join(P, f"{tag}_ncu_all_kernels_c2.md")).read())
