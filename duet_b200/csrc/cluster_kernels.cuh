@@ -21,9 +21,12 @@
 //                 maxima need: 36 for a human genome -> five passes; passes beyond that return at once).  A
 //                 tile is ranked in one go: every warp ranks its own contiguous 256 keys with match_any, one
 //                 block-wide prefix over the warps' digit counts, then the scatter
+//   k_cl_runs     maximal runs of sorted neighbours that pass the edge rule: the forest starts with every run
+//                 hanging under its first position (block-wide scan, no atomics)
 //   k_cl_edges    one block per tile of 256 sorted signatures (+ 256 halo): the windowed pairwise distances
-//                 out of shared memory, passing pairs united in a lock-free union-find (roots = minima)
-//   k_cl_label / k_cl_write   roots' smallest original index, cluster ids in input order
+//                 out of shared memory; only pairs of DIFFERENT runs are tested, passing pairs united in a
+//                 lock-free union-find (roots = minima)
+//   k_cl_label / k_cl_write   roots' smallest original index (one atomic per warp and root), ids in input order
 #pragma once
 
 #include <cuda_runtime.h>
@@ -59,7 +62,13 @@ struct ClusterArgs {
     int n_tiles;
     double max_distance, normalizer;
     unsigned window2;              // 2 * partition window
+    long long *dbg;                // optional per-block clock stamps of k_cl_edges (DUET_CL_DBG), NULL in production
 };
+
+constexpr int kClDbgMarks = 8;
+__device__ __forceinline__ void cl_mark(const ClusterArgs &a, int k) {
+    if (a.dbg && threadIdx.x == 0) a.dbg[(size_t)blockIdx.x * kClDbgMarks + k] = clock64();
+}
 
 __device__ __forceinline__ int bits_for(unsigned v) { return 32 - __clz(v); }          // 0 for v == 0
 
@@ -91,8 +100,6 @@ k_cl_keys(ClusterArgs a) {
         mc = c & 0xFFFFu; mt = t & 0xFFu; m2 = (unsigned)(st + en);
         a.key[0][i] = ((unsigned long long)mc << 40) | ((unsigned long long)mt << 32) | (unsigned long long)m2;
         a.pay[0][i] = ((unsigned long long)(unsigned)(en - st) << 32) | (unsigned)i;
-        a.parent[i] = i;
-        a.minidx[i] = INT32_MAX;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -261,77 +268,246 @@ __device__ __forceinline__ void uf_unite(int *parent, int x, int y) {
     }
 }
 
-// windowed pairwise distances: each thread owns sorted position i and scans forward, out of the tile in
-// shared memory, while the neighbour is in the same (contig, type) segment and within the partition window.
-// A pair that passes is united in the global forest unless a glance at the two parent words shows it
-// connected already (most pairs of a dense cluster are).  (A per-tile forest in shared memory, merged into
-// the global one afterwards, was measured: 0.74 ms against 0.40 ms -- the threads of a dense cluster all
-// start as their own roots there and fight over the same few words.)
+// the edge rule for two signatures of one (contig, type) segment, d2 = |c2_i - c2_j| <= window2 already checked.
+// A division-free single-precision version of the inequality, multiplied through by normalizer * max(span),
+// decides all pairs that are not within 1e-5 (relative) of the threshold; only those pay for the exact fp64
+// quotients in the spec's operand order.
+__device__ __forceinline__ bool cl_edge(unsigned d2, int si, int sj, float nf, float mdf, double normalizer, double max_distance) {
+    const int mx = max(si, sj);
+    const float fm = mx > 0 ? (float)mx : 1.0f;
+    const float lhs = (float)d2 * 0.5f * fm + (float)abs(si - sj) * nf;       // (dpos + dspan) * nf * mx
+    const float rhs = mdf * nf * fm;
+    if (lhs > rhs * 1.00001f) return false;
+    if (lhs < rhs * 0.99999f) return true;
+    const double dpos = ((double)d2 * 0.5) / normalizer;
+    const double dspan = mx > 0 ? (double)abs(si - sj) / (double)mx : 0.0;
+    return dpos + dspan <= max_distance;
+}
+
+// Runs: sorted neighbours i-1, i that pass the edge rule belong together, and in real signature sets that is
+// nearly every edge there is (the members of one event sit next to each other).  So the forest STARTS with
+// every maximal run of linked neighbours hanging under its first position -- a block-wide max-scan, no
+// atomics -- and k_cl_edges only has to unite the runs that some longer-range pair connects.  A run that
+// began in the previous tile hangs under that tile's last position (find follows it from there).
+// These kernels work on tiles of kClTile = 1024 sorted positions, four per thread: what bounds them is the
+// chain of dependent global round trips of a block (meta -> columns -> forest words), not bytes, so a block
+// requests four positions' worth at once and the grid is resident in two waves.
+constexpr int kClItems = 4;
+constexpr int kClTile = kClThreads * kClItems;      // 1024
+
+__device__ __forceinline__ bool cl_linked(unsigned long long kp, unsigned long long ki, int sp, int si, const ClusterArgs &a) {
+    const unsigned d2 = (unsigned)ki - (unsigned)kp;            // sorted: non-negative inside a segment
+    return (unsigned)(kp >> 32) == (unsigned)(ki >> 32) && d2 <= a.window2 &&
+           cl_edge(d2, sp, si, (float)a.normalizer, (float)a.max_distance, a.normalizer, a.max_distance);
+}
+
 __global__ void __launch_bounds__(kClThreads)
-k_cl_edges(ClusterArgs a) {
-    __shared__ unsigned long long s_key[kClThreads + kClHalo];
-    __shared__ int s_span[kClThreads + kClHalo];
+k_cl_runs(ClusterArgs a) {
+    __shared__ unsigned long long s_key[kClTile + 1];
+    __shared__ int s_span[kClTile + 1];
+    __shared__ int s_w[kClThreads / 32];
     const Packing pk = packing_of(a.meta);
     const int cur = sorted_buffer(pk);
     const unsigned long long *key = a.key[cur], *pay = a.pay[cur];
-    const int i0 = blockIdx.x * kClThreads;
-    for (int t = threadIdx.x; t < kClThreads + kClHalo; t += kClThreads) {
+    const int i0 = blockIdx.x * kClTile;
+    for (int t = threadIdx.x; t < kClTile + 1; t += kClThreads) {      // positions i0-1 .. i0+1023
+        const int j = i0 - 1 + t;
+        const bool ok = j >= 0 && j < a.n;
+        s_key[t] = ok ? key[j] : ~0ull;
+        s_span[t] = ok ? (int)(pay[j] >> 32) : 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int t0 = threadIdx.x * kClItems;                              // my four consecutive positions
+    int head[kClItems];
+    int run = -1;                                                       // where the current run starts inside the tile
+#pragma unroll
+    for (int u = 0; u < kClItems; ++u) {
+        const int t = t0 + u, i = i0 + t;
+        const bool link = i > 0 && i < a.n && cl_linked(s_key[t], s_key[t + 1], s_span[t], s_span[t + 1], a);
+        if (!link) run = t;
+        head[u] = run;                                                  // -1: continues from before my first position
+    }
+    int inc = run;                                                      // inclusive max-scan over the threads
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int x = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc = max(inc, x);
+    }
+    if (lane == 31) s_w[w] = inc;
+    int before = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) before = -1;
+    __syncthreads();
+    for (int k = 0; k < w; ++k) before = max(before, s_w[k]);
+    int par[kClItems];
+#pragma unroll
+    for (int u = 0; u < kClItems; ++u) {
+        const int hd = head[u] >= 0 ? head[u] : before;
+        par[u] = hd >= 0 ? i0 + hd : i0 - 1;
+    }
+    const int i = i0 + t0;
+    if (i + kClItems <= a.n) {                                          // allocations are 16-byte aligned, i is a multiple of 4
+        *reinterpret_cast<int4 *>(a.parent + i) = make_int4(par[0], par[1], par[2], par[3]);
+        *reinterpret_cast<int4 *>(a.minidx + i) = make_int4(INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX);
+    } else {
+#pragma unroll
+        for (int u = 0; u < kClItems; ++u)
+            if (i + u < a.n) { a.parent[i + u] = par[u]; a.minidx[i + u] = INT32_MAX; }
+    }
+}
+
+// Windowed pairwise distances, out of the tile (+ halo) in shared memory.  The members of a position's own
+// run are connected already and are SKIPPED AS A RANGE: a bit per position marks the run starts, and the
+// scan of position i begins at the first run start behind it.  From there on, a neighbour inside the segment
+// and the partition window that is not yet known to be connected to i is tested; pairs that pass are united
+// in a forest of the BLOCK (shared memory: interleaved events make every member a run of its own, and their
+// quadratically many unions would each be a chain of global round trips), and the rest of that neighbour's
+// run is skipped as well.  At the end every run start that found a smaller root hangs itself under it in
+// the global forest: one global union per merged run, not per pair.
+__global__ void __launch_bounds__(kClThreads)
+k_cl_edges(ClusterArgs a) {
+    constexpr int kSpan = kClTile + kClHalo;                            // 1280 positions in shared memory
+    __shared__ unsigned long long s_key[kSpan];
+    __shared__ int s_span[kSpan];
+    __shared__ int s_uf[kSpan];                                         // the block's forest over span positions
+    __shared__ unsigned s_brk[kSpan / 32 + 1];
+    cl_mark(a, 0);
+    const Packing pk = packing_of(a.meta);
+    const int cur = sorted_buffer(pk);
+    const unsigned long long *key = a.key[cur], *pay = a.pay[cur];
+    const int i0 = blockIdx.x * kClTile;
+    for (int t = threadIdx.x; t < kSpan; t += kClThreads) {
         const int j = i0 + t;
         s_key[t] = j < a.n ? key[j] : ~0ull;
         s_span[t] = j < a.n ? (int)(pay[j] >> 32) : 0;
     }
+    if (threadIdx.x == 0) s_brk[kSpan / 32] = 0xffffffffu;              // sentinel: the scan stops at the end of the span
     __syncthreads();
-    const int i = i0 + threadIdx.x;
-    if (i >= a.n) return;
-    const unsigned long long ki = s_key[threadIdx.x];
-    const unsigned seg = (unsigned)(ki >> 32), c2 = (unsigned)ki;
-    const int si = s_span[threadIdx.x];
-    const float nf = (float)a.normalizer, mdf = (float)a.max_distance;
-    for (int j = i + 1; j < a.n; ++j) {
-        const int t = j - i0;
-        const bool in_smem = t < kClThreads + kClHalo;
-        const unsigned long long kj = in_smem ? s_key[t] : key[j];
-        if ((unsigned)(kj >> 32) != seg) break;
-        const unsigned d2 = (unsigned)kj - c2;              // keys are sorted: non-negative
-        if (d2 > a.window2) break;
-        const int sj = in_smem ? s_span[t] : (int)(pay[j] >> 32);
-        const int mx = max(si, sj);
-        // single precision first: only pairs within 1e-4 of the threshold need the exact fp64 quotients
-        const float approx = (float)d2 * 0.5f / nf + (mx > 0 ? (float)abs(si - sj) / (float)mx : 0.0f);
-        bool edge;
-        if (approx > mdf + 1e-4f) edge = false;
-        else if (approx < mdf - 1e-4f) edge = true;
-        else {
-            const double dpos = ((double)d2 * 0.5) / a.normalizer;
-            const double dspan = mx > 0 ? (double)abs(si - sj) / (double)mx : 0.0;
-            edge = dpos + dspan <= a.max_distance;
-        }
-        if (edge && a.parent[i] != a.parent[j]) uf_unite(a.parent, i, j);
+    cl_mark(a, 1);
+    for (int t = threadIdx.x; t < kSpan; t += kClThreads) {             // kSpan is a multiple of 32: whole warps
+        const bool brk = t == 0 || !cl_linked(s_key[t - 1], s_key[t], s_span[t - 1], s_span[t], a);
+        const unsigned m = __ballot_sync(0xffffffffu, brk);
+        if ((threadIdx.x & 31) == 0) s_brk[t >> 5] = m;
+        // every position under the start of its run -- or, when that lies before this warp's 32 positions,
+        // under the position just before them (a smaller member of the same run: as good a parent)
+        const unsigned own = m & (0xffffffffu >> (31 - (t & 31)));
+        s_uf[t] = own ? (t & ~31) + 31 - __clz(own) : (t & ~31) - 1;
     }
+    __syncthreads();
+    cl_mark(a, 2);
+    auto next_start = [&](int t) {                                      // first run start behind span position t
+        int w = (t + 1) >> 5;
+        unsigned m = s_brk[w] & (0xffffffffu << ((t + 1) & 31));
+        while (!m) m = s_brk[++w];
+        return (w << 5) + __ffs(m) - 1;                                 // >= kSpan when there is none inside the span
+    };
+    const float nf = (float)a.normalizer, mdf = (float)a.max_distance;
+#pragma unroll 1
+    for (int u = 0; u < kClItems; ++u) {
+        const int ti = u * kClThreads + threadIdx.x, i = i0 + ti;
+        if (i >= a.n) break;
+        const unsigned long long ki = s_key[ti];
+        const unsigned seg = (unsigned)(ki >> 32), c2 = (unsigned)ki;
+        const int si = s_span[ti];
+        int t = next_start(ti);
+        for (;;) {
+            const int j = i0 + t;
+            if (j >= a.n) break;
+            const bool in_smem = t < kSpan;
+            const unsigned long long kj = in_smem ? s_key[t] : key[j];
+            if ((unsigned)(kj >> 32) != seg) break;
+            const unsigned d2 = (unsigned)kj - c2;                      // keys are sorted: non-negative
+            if (d2 > a.window2) break;
+            if (in_smem) {
+                if (uf_find(s_uf, t) != uf_find(s_uf, ti) && cl_edge(d2, si, s_span[t], nf, mdf, a.normalizer, a.max_distance)) {
+                    uf_unite(s_uf, ti, t);
+                    t = next_start(t);                                  // the rest of j's run came with it
+                    continue;
+                }
+            } else if (cl_edge(d2, si, (int)(pay[j] >> 32), nf, mdf, a.normalizer, a.max_distance)) {
+                uf_unite(a.parent, i, j);                               // a window wider than the halo: straight to the global forest
+            }
+            ++t;
+        }
+    }
+    cl_mark(a, 3);
+    __syncthreads();
+    cl_mark(a, 4);
+    for (int t = threadIdx.x; t < kSpan; t += kClThreads) {
+        if (i0 + t >= a.n || !(s_brk[t >> 5] >> (t & 31) & 1u)) continue;
+        const int r = uf_find(s_uf, t);
+        if (r != t) {
+            if (a.dbg) atomicAdd((unsigned long long *)&a.dbg[(size_t)blockIdx.x * kClDbgMarks + 6], 1ull);
+            uf_unite(a.parent, i0 + r, i0 + t);
+        }
+    }
+    cl_mark(a, 5);
 }
 
+// every position learns its root, and every root the smallest original index below it.  Nearly every
+// component lies inside one tile under a root of that tile: those are settled in shared memory (the parent
+// words of the tile, one shared-memory atomicMin per position) and cost the global forest one atomicMin per
+// root; only positions whose parent lies outside the tile walk the global forest.
 __global__ void __launch_bounds__(kClThreads)
 k_cl_label(ClusterArgs a) {
+    __shared__ int s_par[kClTile], s_min[kClTile];
     const Packing pk = packing_of(a.meta);
     const unsigned long long *pay = a.pay[sorted_buffer(pk)];
-    const int i = blockIdx.x * kClThreads + threadIdx.x;
-    bool root = false;
-    if (i < a.n) {
-        const int r = uf_find(a.parent, i);
-        a.parent[i] = r;
-        root = r == i;
-        atomicMin(a.minidx + r, (int)(unsigned)pay[i]);
+    const int i0 = blockIdx.x * kClTile;
+    int p0[kClItems], idx[kClItems];
+#pragma unroll
+    for (int u = 0; u < kClItems; ++u) {
+        const int t = u * kClThreads + threadIdx.x, i = i0 + t;
+        p0[u] = i < a.n ? a.parent[i] : -1;
+        idx[u] = i < a.n ? (int)(unsigned)pay[i] : INT32_MAX;
+        s_par[t] = p0[u];
+        s_min[t] = INT32_MAX;
     }
-    const unsigned m = __ballot_sync(0xffffffffu, root);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&a.meta->n_clusters, __popc(m));
+    __syncthreads();
+    int n_root = 0;
+#pragma unroll
+    for (int u = 0; u < kClItems; ++u) {
+        const int t = u * kClThreads + threadIdx.x, i = i0 + t;
+        if (i >= a.n) continue;
+        int p = p0[u];
+        // follow the parents while they stay inside the tile (shared memory); roots are fixed points
+        while (p >= i0 && p != s_par[p - i0]) p = s_par[p - i0];
+        if (p >= i0) {
+            atomicMin(&s_min[p - i0], idx[u]);
+        } else {
+            p = uf_find(a.parent, p);
+            atomicMin(a.minidx + p, idx[u]);
+        }
+        a.parent[i] = p;
+        n_root += p0[u] == i;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kClItems; ++u) {
+        const int t = u * kClThreads + threadIdx.x;
+        if (s_min[t] != INT32_MAX) atomicMin(a.minidx + i0 + t, s_min[t]);
+    }
+    n_root = __reduce_add_sync(0xffffffffu, n_root);
+    if ((threadIdx.x & 31) == 0 && n_root) atomicAdd(&a.meta->n_clusters, n_root);
 }
 
 __global__ void __launch_bounds__(kClThreads)
 k_cl_write(ClusterArgs a) {
     const Packing pk = packing_of(a.meta);
     const unsigned long long *pay = a.pay[sorted_buffer(pk)];
-    const int i = blockIdx.x * kClThreads + threadIdx.x;
-    if (i < a.n) a.out[(int)(unsigned)pay[i]] = a.minidx[a.parent[i]];
+    const int i0 = blockIdx.x * kClTile;
+    int r[kClItems], idx[kClItems];
+#pragma unroll
+    for (int u = 0; u < kClItems; ++u) {
+        const int i = i0 + u * kClThreads + threadIdx.x;
+        r[u] = i < a.n ? a.parent[i] : -1;
+        idx[u] = i < a.n ? (int)(unsigned)pay[i] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < kClItems; ++u) if (r[u] >= 0) r[u] = a.minidx[r[u]];
+#pragma unroll
+    for (int u = 0; u < kClItems; ++u)
+        if (i0 + u * kClThreads + threadIdx.x < a.n) a.out[idx[u]] = r[u];
 }
 
 }  // namespace duet

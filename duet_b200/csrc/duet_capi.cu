@@ -105,7 +105,7 @@ struct duet_handle {
     DevBuf d_out;                   // every result column (and the join rows), laid out by output_layout()
     DevBuf d_order, d_n_emit, d_status;
     // kernel set B (signature clustering)
-    DevBuf cl_in[4], cl_key[2], cl_idx[2], cl_span, cl_parent, cl_minidx, cl_out, cl_hist, cl_misc;
+    DevBuf cl_in[4], cl_key[2], cl_idx[2], cl_span, cl_parent, cl_minidx, cl_out, cl_hist, cl_misc, cl_dbg;
     cudaEvent_t cl_ev[6] = {};      // staging, keys, sort, edges, label + write
     int cl_passes = 0;
     bool cl_timed = false;
@@ -301,7 +301,7 @@ void duet_destroy(duet_handle *h) {
     h->h_back.release();
     for (DevBuf &b : h->cl_in) b.release();
     for (DevBuf *b : {&h->cl_key[0], &h->cl_key[1], &h->cl_idx[0], &h->cl_idx[1], &h->cl_span, &h->cl_parent,
-                      &h->cl_minidx, &h->cl_out, &h->cl_hist, &h->cl_misc}) b->release();
+                      &h->cl_minidx, &h->cl_out, &h->cl_hist, &h->cl_misc, &h->cl_dbg}) b->release();
     for (auto &ev : h->cl_ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
@@ -911,10 +911,18 @@ int duet_cluster_run(duet_handle *h, const duet_cluster_input *in, const duet_cl
         k_rs_scatter<<<a.n_tiles, kClThreads, 0, st>>>(a, pass);
     }
     CU(h, cudaEventRecord(h->cl_ev[3], st));
-    k_cl_edges<<<blocks, kClThreads, 0, st>>>(a);
+    const int tiles = (int)((n + kClTile - 1) / kClTile);
+    const bool cl_dbg = std::getenv("DUET_CL_DBG") != nullptr;         // developer aid: per-block clock stamps of k_cl_edges
+    if (cl_dbg) {
+        CU(h, h->cl_dbg.reserve((size_t)tiles * kClDbgMarks * 8));
+        CU(h, cudaMemsetAsync(h->cl_dbg.p, 0, (size_t)tiles * kClDbgMarks * 8, st));
+        a.dbg = h->cl_dbg.as<long long>();
+    }
+    k_cl_runs<<<tiles, kClThreads, 0, st>>>(a);
+    k_cl_edges<<<tiles, kClThreads, 0, st>>>(a);
     CU(h, cudaEventRecord(h->cl_ev[4], st));
-    k_cl_label<<<blocks, kClThreads, 0, st>>>(a);
-    k_cl_write<<<blocks, kClThreads, 0, st>>>(a);
+    k_cl_label<<<tiles, kClThreads, 0, st>>>(a);
+    k_cl_write<<<tiles, kClThreads, 0, st>>>(a);
     CU(h, cudaEventRecord(h->cl_ev[5], st));
     ClMeta meta;
     CU(h, cudaMemcpyAsync(&meta, a.meta, sizeof(meta), cudaMemcpyDeviceToHost, st));
@@ -922,11 +930,28 @@ int duet_cluster_run(duet_handle *h, const duet_cluster_input *in, const duet_cl
         CU(h, cudaMemcpyAsync(cluster_id, a.out, N * 4, cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
     CU(h, cudaGetLastError());
+    if (cl_dbg) {
+        std::vector<long long> d((size_t)tiles * kClDbgMarks);
+        CU(h, cudaMemcpy(d.data(), a.dbg, d.size() * 8, cudaMemcpyDeviceToHost));
+        {
+            long long ex = 0; int nb = 0;
+            for (int b = 0; b < tiles; ++b) { ex += d[(size_t)b * kClDbgMarks + 6]; nb += d[(size_t)b * kClDbgMarks + 6] > 0; }
+            std::fprintf(stderr, "k_cl_edges exports %lld in %d blocks of %d\n", ex, nb, tiles);
+        }
+        for (int k = 1; k <= 5; ++k) {
+            std::vector<long long> v(tiles);
+            for (int b = 0; b < tiles; ++b) v[b] = d[(size_t)b * kClDbgMarks + k] - d[(size_t)b * kClDbgMarks + k - 1];
+            const int arg = (int)(std::max_element(v.begin(), v.end()) - v.begin());
+            std::sort(v.begin(), v.end());
+            std::fprintf(stderr, "k_cl_edges phase %d cycles: p50 %lld  p90 %lld  p99 %lld  max %lld (block %d)\n", k, v[tiles / 2],
+                         v[(size_t)tiles * 9 / 10], v[(size_t)tiles * 99 / 100], v[tiles - 1], arg);
+        }
+    }
     if (meta.bad) return fail(h, DUET_ERR_INVALID, "duet_cluster_run: need 0 <= start <= end, start+end < 2^32, contig < 65536, type < 256");
     const int key_bits = (meta.max_c2 ? 32 - __builtin_clz(meta.max_c2) : 0) + (meta.max_type ? 32 - __builtin_clz(meta.max_type) : 0) +
                          (meta.max_contig ? 32 - __builtin_clz(meta.max_contig) : 0);
     h->cl_passes = (key_bits + kRsBits - 1) / kRsBits;
-    h->launches += 1 + 3 * h->cl_passes + 3;            // the passes beyond the key's bits return at once: not counted
+    h->launches += 1 + 3 * h->cl_passes + 4;            // the passes beyond the key's bits return at once: not counted
     h->cl_timed = true;
     if (n_clusters) *n_clusters = meta.n_clusters;
     if (device_ms) cudaEventElapsedTime(device_ms, h->cl_ev[1], h->cl_ev[5]);
@@ -934,7 +959,7 @@ int duet_cluster_run(duet_handle *h, const duet_cluster_input *in, const duet_cl
 }
 
 int duet_cluster_timings(duet_handle *h, const char **names, float *ms, int cap) {
-    static const char *const kNames[4] = {"k_cl_keys", "k_rs_hist + k_rs_scan + k_rs_scatter", "k_cl_edges", "k_cl_label + k_cl_write"};
+    static const char *const kNames[4] = {"k_cl_keys", "k_rs_hist + k_rs_scan + k_rs_scatter", "k_cl_runs + k_cl_edges", "k_cl_label + k_cl_write"};
     if (!h || !names || !ms || cap < 4 || !h->cl_timed) return 0;
     for (int k = 0; k < 4; ++k) {
         names[k] = kNames[k];
