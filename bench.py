@@ -512,7 +512,8 @@ def cluster_kernel_bytes(n: int) -> dict:
     """Algorithmic bytes per stage of kernel set B: keys 16 B in + 16 B out; a sort
     pass moves 16 B in + 16 B out per signature and reads the keys once more for the histogram (five passes for
     a human genome: 36 key bits); k_cl_runs reads 12 B and writes the 8 B of forest state, the edge kernel reads 12 B + the 4-byte forest; labels 12 B + 8 B."""
-    return {"k_cl_keys": 32 * n, "k_rs_hist + k_rs_scan + k_rs_scatter": 5 * 40 * n, "k_cl_runs + k_cl_edges": 20 * n + 16 * n,
+    return {"k_cl_max + k_cl_hist + k_cl_scatter": (16 + 12) * n + 8 * n + (12 + 16) * n, "k_cl_bucket": 16 * n + 4 * n, "k_cl_fix": 4 * n,
+            "k_cl_keys": 32 * n, "k_rs_hist + k_rs_scan + k_rs_scatter": 5 * 40 * n, "k_cl_runs + k_cl_edges": 20 * n + 16 * n,
             "k_cl_label + k_cl_write": 24 * n}
 
 

@@ -46,6 +46,11 @@ struct ClMeta {                    // device-side facts about the call
     unsigned max_contig, max_type, max_c2;
     int bad;                       // invalid input seen
     int n_clusters;
+    // the bucketed path (cluster_fast.cuh)
+    int oversize;                  // a bucket does not fit shared memory: the call takes the general path
+    int n_buckets;                 // non-empty buckets
+    int ticket;                    // next entry of the bucket list to hand out
+    int n_pending;                 // members of components that touch a bucket boundary
     int pad[3];
 };
 

@@ -10,6 +10,7 @@
 
 #include "phase_kernels.cuh"
 #include "cluster_kernels.cuh"
+#include "cluster_fast.cuh"
 
 using namespace duet;
 
@@ -106,8 +107,12 @@ struct duet_handle {
     DevBuf d_order, d_n_emit, d_status;
     // kernel set B (signature clustering)
     DevBuf cl_in[4], cl_key[2], cl_idx[2], cl_span, cl_parent, cl_minidx, cl_out, cl_hist, cl_misc, cl_dbg;
-    cudaEvent_t cl_ev[6] = {};      // staging, keys, sort, edges, label + write
+    DevBuf cl_rec, cl_zone, cl_ctr; // the bucketed path: records, zone lists, per-bucket counters
+    cudaEvent_t cl_ev[8] = {};      // staging, then one per stage boundary
+    const char *cl_stage[6] = {};   // names of the stages between cl_ev[1..]
+    int cl_stages = 0;
     int cl_passes = 0;
+    int cl_bucket_blocks = 0;       // resident blocks of k_cl_bucket (0: not asked yet, -1: it does not fit)
     bool cl_timed = false;
 };
 
@@ -301,7 +306,7 @@ void duet_destroy(duet_handle *h) {
     h->h_back.release();
     for (DevBuf &b : h->cl_in) b.release();
     for (DevBuf *b : {&h->cl_key[0], &h->cl_key[1], &h->cl_idx[0], &h->cl_idx[1], &h->cl_span, &h->cl_parent,
-                      &h->cl_minidx, &h->cl_out, &h->cl_hist, &h->cl_misc, &h->cl_dbg}) b->release();
+                      &h->cl_minidx, &h->cl_out, &h->cl_hist, &h->cl_misc, &h->cl_dbg, &h->cl_rec, &h->cl_zone, &h->cl_ctr}) b->release();
     for (auto &ev : h->cl_ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
@@ -854,6 +859,94 @@ void duet_default_cluster_params(duet_cluster_params *p) {
     p->partition_window = 1000;
 }
 
+// the bucketed path (cluster_fast.cuh): five launches chained with programmatic dependent launch.  Returns DUET_OK
+// with *done = false when the call has to take the general path (a bucket that does not fit shared memory).
+static int cluster_fast(duet_handle *h, const ClusterArgs &g, ClMeta *meta, bool *done) {
+    *done = false;
+    cudaStream_t st = h->stream;
+    const size_t N = (size_t)g.n, NB = (size_t)1 << kBkMaxBits;
+    const size_t bucket_smem = sizeof(BucketSmem);
+    if (h->cl_bucket_blocks == 0) {
+        int per_sm = 0;
+        if (cudaFuncSetAttribute(k_cl_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NB * sizeof(unsigned))) == cudaSuccess &&
+            cudaFuncSetAttribute(k_cl_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NB * sizeof(unsigned))) == cudaSuccess &&
+            cudaFuncSetAttribute(k_cl_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bucket_smem) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cl_bucket, kBkThreads, bucket_smem) == cudaSuccess && per_sm > 0)
+            h->cl_bucket_blocks = per_sm * h->n_sm;
+        else
+            h->cl_bucket_blocks = -1;
+        cudaGetLastError();
+    }
+    if (h->cl_bucket_blocks < 0) return DUET_OK;
+    FastArgs f;
+    std::memset(&f, 0, sizeof(f));
+    f.n = g.n; f.contig = g.contig; f.type = g.type; f.start = g.start; f.end = g.end;
+    CU(h, h->cl_key[0].reserve(N * 8));                  f.key = h->cl_key[0].as<unsigned long long>();
+    CU(h, h->cl_rec.reserve(N * 16));                    f.rec = h->cl_rec.as<ulonglong2>();
+    CU(h, h->cl_zone.reserve(NB * kZoneCap * 16));       f.zone = h->cl_zone.as<ulonglong2>();
+    CU(h, h->cl_ctr.reserve(NB * (4 * 4 + 16)));
+    f.bucket_list = h->cl_ctr.as<int4>();
+    f.hist = reinterpret_cast<unsigned *>(f.bucket_list + NB); f.cursor = f.hist + NB; f.zone_n = f.cursor + NB;
+    f.parent = g.parent; f.pending = g.minidx; f.out = g.out; f.meta = g.meta;
+    f.max_distance = g.max_distance; f.normalizer = g.normalizer; f.window2 = g.window2;
+    const char *ob = std::getenv("DUET_CL_BITS");       // developer aid: bucket bits
+    f.bucket_bits_override = ob ? std::atoi(ob) : -1;
+    const int stream_grid = (int)((g.n + kClThreads * kSpUnroll - 1) / (kClThreads * kSpUnroll));
+    const bool dbg = std::getenv("DUET_CL_DBG") != nullptr;          // developer aid: cycles per phase of k_cl_bucket
+    if (dbg) {
+        CU(h, h->cl_dbg.reserve((size_t)4096 * 12 * 8));
+        CU(h, cudaMemsetAsync(h->cl_dbg.p, 0, (size_t)4096 * 12 * 8, st));
+        f.dbg = h->cl_dbg.as<long long>();
+    }
+    const int bucket_grid = (int)std::max<long long>(1, std::min<long long>(h->cl_bucket_blocks, (g.n + 255) / 256));
+    cudaEvent_t de[5] = {};
+    if (dbg) for (auto &e : de) CU(h, cudaEventCreate(&e));
+    if (dbg) CU(h, cudaEventRecord(de[0], st));
+    CU(h, launch(k_cl_max, stream_grid, kClThreads, 0, st, false, false, f));
+    if (dbg) CU(h, cudaEventRecord(de[1], st));
+    const int ag_grid = (int)((g.n + kAgThreads * kAgItems - 1) / (kAgThreads * kAgItems));
+    const size_t ag_smem = NB * sizeof(unsigned);
+    CU(h, launch(k_cl_hist, ag_grid, kAgThreads, ag_smem, st, !dbg, false, f));
+    if (dbg) CU(h, cudaEventRecord(de[2], st));
+    if (dbg) CU(h, cudaEventRecord(de[3], st));
+    CU(h, launch(k_cl_scatter, ag_grid, kAgThreads, ag_smem, st, !dbg, false, f));
+    if (dbg) CU(h, cudaEventRecord(de[4], st));
+    CU(h, cudaEventRecord(h->cl_ev[2], st));
+    CU(h, launch(k_cl_bucket, bucket_grid, kBkThreads, bucket_smem, st, false, false, f));
+    CU(h, cudaEventRecord(h->cl_ev[3], st));
+    CU(h, launch(k_cl_fix, kFixBlocks, kClThreads, 0, st, false, false, f));
+    CU(h, cudaEventRecord(h->cl_ev[4], st));
+    CU(h, cudaMemcpyAsync(meta, g.meta, sizeof(*meta), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    CU(h, cudaGetLastError());
+    if (dbg) {
+        static const char *const kK[4] = {"k_cl_max", "k_cl_hist", "-", "k_cl_scatter"};
+        for (int k = 0; k < 4; ++k) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, de[k], de[k + 1]);
+            std::fprintf(stderr, "%-14s %7.1f us (serial, no programmatic overlap)\n", kK[k], ms * 1e3);
+        }
+        for (auto &e : de) cudaEventDestroy(e);
+        std::vector<long long> d((size_t)bucket_grid * 12);
+        CU(h, cudaMemcpy(d.data(), f.dbg, d.size() * 8, cudaMemcpyDeviceToHost));
+        static const char *const kPh[10] = {"wait for the block", "records loaded", "cells counted", "cell starts", "grouped by cell",
+                                            "ranked inside cells", "runs", "window scan", "minima", "output"};
+        for (int k = 0; k < 10; ++k) {
+            double sum = 0; long long mx = 0;
+            for (int b = 0; b < bucket_grid; ++b) { sum += (double)d[(size_t)b * 12 + k]; mx = std::max(mx, d[(size_t)b * 12 + k]); }
+            std::fprintf(stderr, "k_cl_bucket %-22s mean %9.0f cycles per block, max %9lld  (%d buckets, %d blocks)\n", kPh[k], sum / bucket_grid, mx,
+                         meta->n_buckets, bucket_grid);
+        }
+    }
+    if (meta->oversize && !meta->bad) return DUET_OK;
+    static const char *const kNames[3] = {"k_cl_max + k_cl_hist + k_cl_scatter", "k_cl_bucket", "k_cl_fix"};
+    for (int k = 0; k < 3; ++k) h->cl_stage[k] = kNames[k];
+    h->cl_stages = 3;
+    h->launches += 5;
+    *done = true;
+    return DUET_OK;
+}
+
 int duet_cluster_run(duet_handle *h, const duet_cluster_input *in, const duet_cluster_params *params,
                      int32_t *cluster_id, int64_t *n_clusters, float *device_ms) {
     if (!h || !in || !params || !cluster_id) return fail(h, DUET_ERR_INVALID, "duet_cluster_run: NULL argument");
@@ -882,15 +975,8 @@ int duet_cluster_run(duet_handle *h, const duet_cluster_input *in, const duet_cl
         *dst[c] = static_cast<const int *>(dv);
     }
     const size_t N = (size_t)n;
-    a.n_tiles = (int)((n + kRsTile - 1) / kRsTile);
-    for (int k = 0; k < 2; ++k) {
-        CU(h, h->cl_key[k].reserve(N * 8));  a.key[k] = h->cl_key[k].as<unsigned long long>();
-        CU(h, h->cl_idx[k].reserve(N * 8));  a.pay[k] = h->cl_idx[k].as<unsigned long long>();
-    }
     CU(h, h->cl_parent.reserve(N * 4));  a.parent = h->cl_parent.as<int>();
     CU(h, h->cl_minidx.reserve(N * 4));  a.minidx = h->cl_minidx.as<int>();
-    CU(h, h->cl_hist.reserve(((size_t)a.n_tiles + 1) * kRsBins * 4));
-    a.block_hist = h->cl_hist.as<unsigned>();
     CU(h, h->cl_misc.reserve(sizeof(ClMeta)));
     a.meta = h->cl_misc.as<ClMeta>();
     if (in->mem == DUET_MEM_DEVICE) a.out = cluster_id;
@@ -898,75 +984,94 @@ int duet_cluster_run(duet_handle *h, const duet_cluster_input *in, const duet_cl
     a.max_distance = params->max_distance;
     a.normalizer = params->position_normalizer;
     a.window2 = 2u * (unsigned)params->partition_window;
+    static const char kBadInput[] = "duet_cluster_run: need 0 <= start <= end, start+end < 2^32, contig < 65536, type < 256";
 
-    // one stream, no host round trip: how many key bits (sort passes) the call needs is decided on the device
-    const int blocks = (int)((n + kClThreads - 1) / kClThreads);
+    ClMeta meta;
     CU(h, cudaMemsetAsync(h->cl_misc.p, 0, sizeof(ClMeta), st));
     CU(h, cudaEventRecord(h->cl_ev[1], st));
-    k_cl_keys<<<blocks, kClThreads, 0, st>>>(a);
-    CU(h, cudaEventRecord(h->cl_ev[2], st));
-    for (int pass = 0; pass < kRsMaxPasses; ++pass) {
-        k_rs_hist<<<a.n_tiles, kClThreads, 0, st>>>(a, pass);
-        k_rs_scan<<<kRsBins, kClThreads, 0, st>>>(a, pass);
-        k_rs_scatter<<<a.n_tiles, kClThreads, 0, st>>>(a, pass);
+    bool done = false;
+    int last_ev = 4;
+    if (!std::getenv("DUET_CL_GENERAL")) {                             // developer / test switch: general path only
+        if ((rc = cluster_fast(h, a, &meta, &done))) return rc;
+        if (done && meta.bad) return fail(h, DUET_ERR_INVALID, kBadInput);
     }
-    CU(h, cudaEventRecord(h->cl_ev[3], st));
-    const int tiles = (int)((n + kClTile - 1) / kClTile);
-    const bool cl_dbg = std::getenv("DUET_CL_DBG") != nullptr;         // developer aid: per-block clock stamps of k_cl_edges
-    if (cl_dbg) {
-        CU(h, h->cl_dbg.reserve((size_t)tiles * kClDbgMarks * 8));
-        CU(h, cudaMemsetAsync(h->cl_dbg.p, 0, (size_t)tiles * kClDbgMarks * 8, st));
-        a.dbg = h->cl_dbg.as<long long>();
+    if (!done) {
+        // the general path: global radix sort by (contig, type, c2), then tile kernels over the sorted array.
+        // One stream, no host round trip: how many key bits (sort passes) the call needs is decided on the device
+        a.n_tiles = (int)((n + kRsTile - 1) / kRsTile);
+        for (int k = 0; k < 2; ++k) {
+            CU(h, h->cl_key[k].reserve(N * 8));  a.key[k] = h->cl_key[k].as<unsigned long long>();
+            CU(h, h->cl_idx[k].reserve(N * 8));  a.pay[k] = h->cl_idx[k].as<unsigned long long>();
+        }
+        CU(h, h->cl_hist.reserve(((size_t)a.n_tiles + 1) * kRsBins * 4));
+        a.block_hist = h->cl_hist.as<unsigned>();
+        const int blocks = (int)((n + kClThreads - 1) / kClThreads);
+        CU(h, cudaMemsetAsync(h->cl_misc.p, 0, sizeof(ClMeta), st));
+        CU(h, cudaEventRecord(h->cl_ev[1], st));
+        k_cl_keys<<<blocks, kClThreads, 0, st>>>(a);
+        CU(h, cudaEventRecord(h->cl_ev[2], st));
+        for (int pass = 0; pass < kRsMaxPasses; ++pass) {
+            k_rs_hist<<<a.n_tiles, kClThreads, 0, st>>>(a, pass);
+            k_rs_scan<<<kRsBins, kClThreads, 0, st>>>(a, pass);
+            k_rs_scatter<<<a.n_tiles, kClThreads, 0, st>>>(a, pass);
+        }
+        CU(h, cudaEventRecord(h->cl_ev[3], st));
+        const int tiles = (int)((n + kClTile - 1) / kClTile);
+        const bool cl_dbg = std::getenv("DUET_CL_DBG") != nullptr;         // developer aid: per-block clock stamps of k_cl_edges
+        if (cl_dbg) {
+            CU(h, h->cl_dbg.reserve((size_t)tiles * kClDbgMarks * 8));
+            CU(h, cudaMemsetAsync(h->cl_dbg.p, 0, (size_t)tiles * kClDbgMarks * 8, st));
+            a.dbg = h->cl_dbg.as<long long>();
+        }
+        k_cl_runs<<<tiles, kClThreads, 0, st>>>(a);
+        k_cl_edges<<<tiles, kClThreads, 0, st>>>(a);
+        CU(h, cudaEventRecord(h->cl_ev[4], st));
+        k_cl_label<<<tiles, kClThreads, 0, st>>>(a);
+        k_cl_write<<<tiles, kClThreads, 0, st>>>(a);
+        CU(h, cudaEventRecord(h->cl_ev[5], st));
+        last_ev = 5;
+        CU(h, cudaMemcpyAsync(&meta, a.meta, sizeof(meta), cudaMemcpyDeviceToHost, st));
+        CU(h, cudaStreamSynchronize(st));
+        CU(h, cudaGetLastError());
+        if (cl_dbg) {
+            std::vector<long long> d((size_t)tiles * kClDbgMarks);
+            CU(h, cudaMemcpy(d.data(), a.dbg, d.size() * 8, cudaMemcpyDeviceToHost));
+            for (int k = 1; k <= 5; ++k) {
+                std::vector<long long> v(tiles);
+                for (int b = 0; b < tiles; ++b) v[b] = d[(size_t)b * kClDbgMarks + k] - d[(size_t)b * kClDbgMarks + k - 1];
+                const int arg = (int)(std::max_element(v.begin(), v.end()) - v.begin());
+                std::sort(v.begin(), v.end());
+                std::fprintf(stderr, "k_cl_edges phase %d cycles: p50 %lld  p90 %lld  p99 %lld  max %lld (block %d)\n", k, v[tiles / 2],
+                             v[(size_t)tiles * 9 / 10], v[(size_t)tiles * 99 / 100], v[tiles - 1], arg);
+            }
+        }
+        if (meta.bad) return fail(h, DUET_ERR_INVALID, kBadInput);
+        const int key_bits = (meta.max_c2 ? 32 - __builtin_clz(meta.max_c2) : 0) + (meta.max_type ? 32 - __builtin_clz(meta.max_type) : 0) +
+                             (meta.max_contig ? 32 - __builtin_clz(meta.max_contig) : 0);
+        h->cl_passes = (key_bits + kRsBits - 1) / kRsBits;
+        h->launches += 1 + 3 * h->cl_passes + 4;            // the passes beyond the key's bits return at once: not counted
+        static const char *const kNames[4] = {"k_cl_keys", "k_rs_hist + k_rs_scan + k_rs_scatter", "k_cl_runs + k_cl_edges", "k_cl_label + k_cl_write"};
+        for (int k = 0; k < 4; ++k) h->cl_stage[k] = kNames[k];
+        h->cl_stages = 4;
     }
-    k_cl_runs<<<tiles, kClThreads, 0, st>>>(a);
-    k_cl_edges<<<tiles, kClThreads, 0, st>>>(a);
-    CU(h, cudaEventRecord(h->cl_ev[4], st));
-    k_cl_label<<<tiles, kClThreads, 0, st>>>(a);
-    k_cl_write<<<tiles, kClThreads, 0, st>>>(a);
-    CU(h, cudaEventRecord(h->cl_ev[5], st));
-    ClMeta meta;
-    CU(h, cudaMemcpyAsync(&meta, a.meta, sizeof(meta), cudaMemcpyDeviceToHost, st));
-    if (in->mem != DUET_MEM_DEVICE)
+    if (in->mem != DUET_MEM_DEVICE) {
         CU(h, cudaMemcpyAsync(cluster_id, a.out, N * 4, cudaMemcpyDeviceToHost, st));
-    CU(h, cudaStreamSynchronize(st));
-    CU(h, cudaGetLastError());
-    if (cl_dbg) {
-        std::vector<long long> d((size_t)tiles * kClDbgMarks);
-        CU(h, cudaMemcpy(d.data(), a.dbg, d.size() * 8, cudaMemcpyDeviceToHost));
-        {
-            long long ex = 0; int nb = 0;
-            for (int b = 0; b < tiles; ++b) { ex += d[(size_t)b * kClDbgMarks + 6]; nb += d[(size_t)b * kClDbgMarks + 6] > 0; }
-            std::fprintf(stderr, "k_cl_edges exports %lld in %d blocks of %d\n", ex, nb, tiles);
-        }
-        for (int k = 1; k <= 5; ++k) {
-            std::vector<long long> v(tiles);
-            for (int b = 0; b < tiles; ++b) v[b] = d[(size_t)b * kClDbgMarks + k] - d[(size_t)b * kClDbgMarks + k - 1];
-            const int arg = (int)(std::max_element(v.begin(), v.end()) - v.begin());
-            std::sort(v.begin(), v.end());
-            std::fprintf(stderr, "k_cl_edges phase %d cycles: p50 %lld  p90 %lld  p99 %lld  max %lld (block %d)\n", k, v[tiles / 2],
-                         v[(size_t)tiles * 9 / 10], v[(size_t)tiles * 99 / 100], v[tiles - 1], arg);
-        }
+        CU(h, cudaStreamSynchronize(st));
     }
-    if (meta.bad) return fail(h, DUET_ERR_INVALID, "duet_cluster_run: need 0 <= start <= end, start+end < 2^32, contig < 65536, type < 256");
-    const int key_bits = (meta.max_c2 ? 32 - __builtin_clz(meta.max_c2) : 0) + (meta.max_type ? 32 - __builtin_clz(meta.max_type) : 0) +
-                         (meta.max_contig ? 32 - __builtin_clz(meta.max_contig) : 0);
-    h->cl_passes = (key_bits + kRsBits - 1) / kRsBits;
-    h->launches += 1 + 3 * h->cl_passes + 4;            // the passes beyond the key's bits return at once: not counted
     h->cl_timed = true;
     if (n_clusters) *n_clusters = meta.n_clusters;
-    if (device_ms) cudaEventElapsedTime(device_ms, h->cl_ev[1], h->cl_ev[5]);
+    if (device_ms) cudaEventElapsedTime(device_ms, h->cl_ev[1], h->cl_ev[last_ev]);
     return DUET_OK;
 }
 
 int duet_cluster_timings(duet_handle *h, const char **names, float *ms, int cap) {
-    static const char *const kNames[4] = {"k_cl_keys", "k_rs_hist + k_rs_scan + k_rs_scatter", "k_cl_runs + k_cl_edges", "k_cl_label + k_cl_write"};
-    if (!h || !names || !ms || cap < 4 || !h->cl_timed) return 0;
-    for (int k = 0; k < 4; ++k) {
-        names[k] = kNames[k];
+    if (!h || !names || !ms || !h->cl_timed || cap < h->cl_stages) return 0;
+    for (int k = 0; k < h->cl_stages; ++k) {
+        names[k] = h->cl_stage[k];
         if (cudaEventElapsedTime(&ms[k], h->cl_ev[1 + k], h->cl_ev[2 + k]) != cudaSuccess) ms[k] = 0.f;
     }
     cudaGetLastError();
-    return 4;
+    return h->cl_stages;
 }
 
 }  // extern "C"

@@ -134,3 +134,45 @@ def test_contig_sharded_clustering_equals_single_process():
         assert (merged[index] == -1).all()
         merged[index] = ids
     assert np.array_equal(merged, want)
+
+
+@pytest.mark.gpu
+def test_gpu_general_path_and_oversize_fallback(monkeypatch):
+    """The call normally takes the bucketed path (cluster_fast.cuh).  DUET_CL_GENERAL forces the general path
+    (global radix sort + tile kernels); a hot spot that does not fit a bucket's shared memory makes the bucketed
+    path stand down and the host run the general one.  All three give the oracle's ids."""
+    from duet_b200.sv_clustering import cluster_signatures
+    cols = synth.make_signatures(7, n=150_000)
+    want, n_want = cluster_oracle.cluster(*cols)
+    got, n_got, _ = cluster_signatures(*cols)
+    assert n_got == n_want and np.array_equal(got, want)
+    monkeypatch.setenv("DUET_CL_GENERAL", "1")
+    got, n_got, _ = cluster_signatures(*cols)
+    assert n_got == n_want and np.array_equal(got, want)
+    monkeypatch.delenv("DUET_CL_GENERAL")
+    # 6000 signatures of one type inside 3 kb on top of a genome-wide background: one bucket overflows
+    rng = np.random.default_rng(11)
+    hot_start = rng.integers(5_000_000, 5_003_000, size=6000)
+    hot = (np.zeros(6000, np.int32), np.zeros(6000, np.int32), hot_start.astype(np.int32),
+           (hot_start + rng.integers(40, 4000, size=6000)).astype(np.int32))
+    mixed = [np.concatenate([a, b]) for a, b in zip(cols, hot)]
+    want, n_want = cluster_oracle.cluster(*mixed)
+    got, n_got, _ = cluster_signatures(*mixed)
+    assert n_got == n_want and np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_gpu_bucket_boundaries():
+    """Clusters that straddle bucket boundaries (the zone / pending / global-forest machinery): signatures laid
+    densely along one contig so that every boundary of the 2^B buckets is crossed by a chain."""
+    from duet_b200.sv_clustering import cluster_signatures
+    rng = np.random.default_rng(5)
+    n = 300_000
+    start = np.sort(rng.integers(0, 40_000_000, size=n)).astype(np.int32)       # ~130 bp apart: long chains everywhere
+    span = rng.integers(200, 260, size=n).astype(np.int32)
+    p = rng.permutation(n)
+    cols = (np.zeros(n, np.int32), rng.integers(0, 2, size=n).astype(np.int32)[p], start[p], (start + span)[p])
+    for win in (1000, 100):
+        want, n_want = cluster_oracle.cluster(*cols, window=win)
+        got, n_got, _ = cluster_signatures(*cols, partition_window=win)
+        assert n_got == n_want and np.array_equal(got, want)
