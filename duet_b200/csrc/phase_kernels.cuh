@@ -80,6 +80,7 @@ struct DevStatus {          // device -> host error report
 // developer switches (environment DUET_FLAGS, read once per handle); 0 in production
 enum {
     kFlagNoWarm = 2,          // k_init does not warm L2 with the input columns k_reduce / k_tail start from
+    kFlagNoStreamHint = 4,    // k_probe's key stream without the L2 evict-first hint
     kFlagFill2 = 16,          // host: load factor <= 1/2 always
     kFlagSplitTail = 32,      // host: k_oneps / k_predict / k_order instead of k_tail
 };
@@ -291,6 +292,20 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned b
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// the same, with an L2 eviction-priority hint: the read-key stream is touched exactly once, so its lines are marked
+// evict-first and leave the slot table, the join rows and the prefetched tag records alone (C2: 95.1 -> 93.7 us,
+// C5 share: 326 -> 323 us per call)
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_load_stream(void *dst, const void *src, unsigned bytes, unsigned long long *bar, unsigned long long policy) {
+    if (policy == 0ull) { bulk_load(dst, src, bytes, bar); return; }          // developer switch: no hint
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // k_init: start-of-call state in one sequential sweep: EMPTY slots (all ones), zero filter words, join
 // results -1.  Sequential 16-byte stores are the cheap way to get all three L2 resident for the scattered
@@ -402,6 +417,13 @@ k_table(PhaseArgs a) {
 // block's private stretch of the candidate list, one 16-byte record each, and their tag records start
 // moving into L2; when the stream is done the whole block resolves its candidates against the slot table,
 // kResolveUnroll per thread in flight together.
+// (Measured and dropped in round 2: four dedicated resolver warps following the list while twelve consumer warps
+// stream -- entries handed out / written counters, batches of 128 claimed below the complete prefix, the consumers
+// joining at the end.  Parity green, but C2 93.7 -> 98.4 us and the C5 share 323 -> 335 us: what resolves a
+// candidate quickly is the number of slot loads in flight, and the whole block after the stream has 2176 of them
+// where the resolver warps had 512 and slowed the stream they ran beside.  One thing learnt on the way: entries
+// written by other warps of the block must be read back with PLAIN loads after a block-scope fence -- ld.cg goes
+// to L2 past the L1 in which block-scope visibility lives, and lost joins at full size.)
 // ------------------------------------------------------------------------------------------
 constexpr int kProbeThreads = 512;                               // consumer threads
 constexpr int kProbeBlock = kProbeThreads + 32;                  // + one producer warp that only issues copies
@@ -431,6 +453,7 @@ k_probe(PhaseArgs a) {
     const long long q1 = (r1 + 1) >> 1;
     const long long q_full = min(q1, R >> 1);                    // pairs that lie completely inside the column
     const int n_tiles = (int)((q1 - q0 + kProbeBatch - 1) / kProbeBatch);
+    const unsigned long long stream_policy = (a.flags & kFlagNoStreamHint) ? 0ull : l2_evict_first_policy();
     auto tile_pairs = [&](int t) { return (unsigned)max(0ll, min(q_full, q0 + (long long)(t + 1) * kProbeBatch) - (q0 + (long long)t * kProbeBatch)); };
     if (threadIdx.x == 0) {
         for (int s = 0; s < kProbeStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kProbeThreads / 32); }
@@ -443,7 +466,7 @@ k_probe(PhaseArgs a) {
         for (int t = 0; t < min(n_tiles, kProbeStages); ++t) {
             const unsigned bytes = tile_pairs(t) * 16u;
             mbar_expect_tx(&s_full[t], bytes);
-            if (bytes) bulk_load(ring + (size_t)t * kProbeBatch, pairs + q0 + (long long)t * kProbeBatch, bytes, &s_full[t]);
+            if (bytes) bulk_load_stream(ring + (size_t)t * kProbeBatch, pairs + q0 + (long long)t * kProbeBatch, bytes, &s_full[t], stream_policy);
         }
     }
     pdl_trigger();
@@ -463,7 +486,7 @@ k_probe(PhaseArgs a) {
             if (lane == 0) {
                 const unsigned bytes = tile_pairs(t) * 16u;
                 mbar_expect_tx(&s_full[stage], bytes);
-                if (bytes) bulk_load(ring + (size_t)stage * kProbeBatch, pairs + q0 + (long long)t * kProbeBatch, bytes, &s_full[stage]);
+                if (bytes) bulk_load_stream(ring + (size_t)stage * kProbeBatch, pairs + q0 + (long long)t * kProbeBatch, bytes, &s_full[stage], stream_policy);
             }
             __syncwarp();
         }
