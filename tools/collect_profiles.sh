@@ -15,6 +15,8 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 # warm-up = 3 steps of 5 launches; the capture takes the 5 kernels of the first timed step
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_ -s 15 -c 5 -f -o $out/prof_all \
     python bench.py --steps 3 --warmup 3 --no-configs --no-cpu-baseline --no-stage-wall > $out/ncu_full.log 2>&1
-timeout 900 ncu --set full --clock-control none -k regex:"k_cl_|k_rs_" -s 25 -c 25 -f -o $out/prof_c3 \
+# clustering: five launches per call (k_cl_max, k_cl_hist, k_cl_scatter, k_cl_bucket, k_cl_fix); 3 warm-up calls
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_cl_|k_rs_" -s 15 -c 5 -f -o $out/prof_c3 \
     python bench.py --workload c3 --steps 3 --warmup 3 --no-cpu-baseline > $out/ncu_c3.log 2>&1
+timeout 600 python bench.py --workload c3 --steps 20 --warmup 5 > $out/bench_c3.json 2> $out/bench_c3.err
 ls -la $out | tail -15
