@@ -239,8 +239,9 @@ void duet_default_cluster_params(duet_cluster_params *p);
  * *device_ms (optional) = device time of the call. */
 int duet_cluster_run(duet_handle *h, const duet_cluster_input *in, const duet_cluster_params *params,
                      int32_t *cluster_id, int64_t *n_clusters, float *device_ms);
-/* Event-timed stages of the last duet_cluster_run (keys; sort passes; windowed distances + union-find;
- * labels): fills names[k] / ms[k], returns how many (0 if nothing was run). */
+/* Event-timed stages of the last duet_cluster_run -- bucketed path: split (maxima, histogram, scatter); buckets;
+ * boundary fix-up.  General path: keys; sort passes; runs + windowed distances; labels.  Fills names[k] / ms[k]
+ * (cap >= 6), returns how many (0 if nothing was run). */
 int duet_cluster_timings(duet_handle *h, const char **names, float *ms, int cap);
 
 /* ---- host-side decoders (no GPU needed) -------------------------------------------------- */
