@@ -186,6 +186,45 @@ class PhaseEngine:
         return int(self.lib.duet_launch_count(self.h))
 
 
+class PhasePipeline:
+    """Cohort mode: several samples (batches) through ONE GPU with two calls in flight.  Two engines, each
+    with its own stream and device buffers; sample k+1's upload and kernels are enqueued before sample k's
+    results are waited for, so its host->device copy runs under sample k's kernels and device->host copy
+    (the reference phases one sample per process run: sv_phasing.py:8-19; a cohort is a loop over samples).
+    Every call still moves its own inputs and results -- nothing is cached between samples."""
+
+    def __init__(self, device: int = 0, depth: int = 2):
+        self.engines = [PhaseEngine(device) for _ in range(max(1, int(depth)))]
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+
+    def set_thresholds(self, *a, **kw):
+        for e in self.engines:
+            e.set_thresholds(*a, **kw)
+
+    def run_many(self, batches, *, buffers=None, tags_in_place: bool = True, join: bool = True, only: tuple | None = None):
+        """Yields one PhaseResult per batch, in order.  `buffers`: one `pinned_outputs` dict per engine (results
+        land in page-locked memory); a result that lives in such a buffer is overwritten when its engine comes
+        round again, i.e. `depth` results later."""
+        n_e = len(self.engines)
+        pending = []                                           # (engine index) of the calls in flight, oldest first
+        for k, batch in enumerate(batches):
+            e = k % n_e
+            if len(pending) == n_e:                            # this engine still owes a result
+                j = pending.pop(0)
+                yield self.engines[j].download(join=join, buffers=buffers[j] if buffers else None, only=only)
+            self.engines[e].upload(batch, tags_in_place=tags_in_place)
+            self.engines[e].execute()
+            pending.append(e)
+        for j in pending:
+            yield self.engines[j].download(join=join, buffers=buffers[j] if buffers else None, only=only)
+
+    def launch_count(self) -> int:
+        return sum(e.launch_count() for e in self.engines)
+
+
 def pinned_empty(shape, dtype) -> np.ndarray:
     """numpy array over page-locked memory from duet_host_alloc; freed when the last view dies."""
     lib = _lib.load()

@@ -117,6 +117,40 @@ def test_tags_read_in_place_from_pinned_host_memory(engine):
     assert np.array_equal(a.gt, e.gt) and np.array_equal(a.order, e.order)
 
 
+def test_pipeline_two_calls_in_flight_equals_sequential(engine):
+    """PhasePipeline (cohort mode): five different samples through two engines with two calls in flight give, in
+    order, what the single engine gives one call at a time -- with pageable columns, with page-locked columns read
+    in place, and with results landing in per-engine page-locked buffers (copied before the engine comes round)."""
+    from duet_b200.engine import PhasePipeline, pinned_outputs
+    samples = [synth.make_sample(20 + k, contigs=["1", "2", "X"][: 1 + k % 3], n_reads=3000 + 900 * k, n_svs=200 + 60 * k,
+                                 bp_per_read=700, block_mean=1e5) for k in range(5)]
+    batches = [from_synth(s) for s in samples]
+    engine.set_thresholds(50, 2)
+    want = [engine.run(b) for b in batches]
+    keys = ("gt", "ps", "cls", "hap1", "hap2", "hap0", "allhap", "totsc1", "totsc2", "join_row", "order", "shard_counts", "features")
+    pipe = PhasePipeline(0, 2)
+    try:
+        pipe.set_thresholds(50, 2)
+        got = list(pipe.run_many(batches, tags_in_place=False))
+        assert len(got) == len(want)
+        for a, b in zip(want, got):
+            for k in keys:
+                assert np.array_equal(getattr(a, k), getattr(b, k)), k
+        pinned = [pin_batch(b) for b in batches]
+        i_big = max(range(len(batches)), key=lambda i: (batches[i].n_svs, batches[i].n_joins))
+        for k, r in enumerate(pipe.run_many(pinned, tags_in_place=True)):
+            for name in keys:
+                assert np.array_equal(getattr(want[k], name), getattr(r, name)), name
+        # same-shape batches may share per-engine result buffers; a result is valid until its engine's next download
+        bufs = [pinned_outputs(batches[i_big]), pinned_outputs(batches[i_big])]
+        same = [pinned[i_big]] * 4
+        for r in pipe.run_many(same, buffers=bufs, tags_in_place=True):
+            w = want[i_big]
+            assert np.array_equal(w.gt, r.gt) and np.array_equal(w.ps, r.ps) and np.array_equal(w.order, r.order)
+    finally:
+        pipe.close()
+
+
 def test_golden_kat_on_device(engine):
     """Every known-answer case recorded from the reference's get_phase_info / predict_hp whose
     class is reachable through the pipeline, run as one shard each in ONE device call."""
