@@ -176,3 +176,38 @@ def test_gpu_bucket_boundaries():
         want, n_want = cluster_oracle.cluster(*cols, window=win)
         got, n_got, _ = cluster_signatures(*cols, partition_window=win)
         assert n_got == n_want and np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_gpu_random_cases_against_oracle():
+    """Property-based differential test: random sizes, coordinate ranges (from everything-in-one-window to a whole
+    chromosome: that decides how many key bits and buckets a call gets), windows, thresholds and normalizers, zero
+    spans and exact duplicates -- device ids == oracle ids."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    from duet_b200.sv_clustering import cluster_signatures
+
+    @settings(max_examples=120, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(seed=st.integers(0, 2**31 - 1), n=st.integers(1, 3000), n_contig=st.integers(1, 4), n_type=st.integers(1, 3),
+           extent=st.sampled_from([50, 3_000, 200_000, 40_000_000, 240_000_000]),
+           max_span=st.sampled_from([0, 1, 300, 20_000]),
+           window=st.sampled_from([0, 3, 50, 1000, 60_000]),
+           md=st.sampled_from([0.0, 0.3, 0.9, 2.5]), norm=st.sampled_from([1.0, 900.0]),
+           dup=st.booleans())
+    def check(seed, n, n_contig, n_type, extent, max_span, window, md, norm, dup):
+        rng = np.random.default_rng(seed)
+        contig = rng.integers(0, n_contig, size=n).astype(np.int32) * 7          # sparse ids
+        typ = rng.integers(0, n_type, size=n).astype(np.int32)
+        start = rng.integers(0, extent + 1, size=n).astype(np.int32)
+        span = rng.integers(0, max_span + 1, size=n).astype(np.int32)
+        if dup and n > 4:                                                       # exact duplicates and near-ties
+            k = n // 3
+            src = rng.integers(0, n, size=k)
+            dst = rng.integers(0, n, size=k)
+            contig[dst], typ[dst], start[dst], span[dst] = contig[src], typ[src], start[src], span[src]
+        cols = (contig, typ, start, start + span)
+        want, n_want = cluster_oracle.cluster(*cols, max_distance=md, normalizer=norm, window=window)
+        got, n_got, _ = cluster_signatures(*cols, cluster_max_distance=md, position_normalizer=norm, partition_window=window)
+        assert n_got == n_want
+        assert np.array_equal(got, want)
+
+    check()
