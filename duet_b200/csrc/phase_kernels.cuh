@@ -66,7 +66,7 @@ struct PredictTile { int sv0, sv1, shard, b, n, pad[3]; };        // SVs [sv0, s
 struct BuildTile { int lo, hi, base, mask, bmo, bmw, pad[2]; };   // kThreads * U consecutive support reads: shards lo..hi
 struct ProbeTile { long long r0, r1; int shard, base, mask, bmo, bmw, pad; };   // rows [r0, r1) of ONE contig + its table / filter
 
-constexpr int kC2Max = 8;    // distinct PS per class-2 SV recorded by k_reduce (more -> warp fallback)
+constexpr int kC2Max = 16;   // distinct PS per class-2 SV recorded by k_reduce (more -> warp fallback)
 struct C2Ent { int ps, tot, n1, n2; long long s1, s2; int bad, pad; };
 struct C2Rec { int n_d, overflow, pad[2]; C2Ent d[kC2Max]; };
 
@@ -901,8 +901,8 @@ k_reduce(PhaseArgs a) {
         }
         C2Rec *rec = a.c2rec + sv;
         if (lane == 0) { rec->n_d = min(n_d, kC2Max); rec->overflow = n_d > kC2Max; }
-        if (lane < min(n_d, kC2Max))
-            rec->d[lane] = C2Ent{g.ps[lane], g.tot[lane], g.n1[lane], g.n2[lane], (long long)g.s1[lane], (long long)g.s2[lane], g.bad[lane], 0};
+        for (int t = lane; t < min(n_d, kC2Max); t += G)
+            rec->d[t] = C2Ent{g.ps[t], g.tot[t], g.n1[t], g.n2[t], (long long)g.s1[t], (long long)g.s2[t], g.bad[t], 0};
     }
 
     dbg_mark(a, 2, 2);

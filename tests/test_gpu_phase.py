@@ -244,7 +244,7 @@ def test_tie_order_and_filters(engine):
     assert res.order.tolist() == [4, 2, 1, 3, 0]
 
 
-@pytest.mark.parametrize("n_ps", [5, 8, 9, 12, 45])
+@pytest.mark.parametrize("n_ps", [5, 8, 9, 12, 16, 17, 33, 45])
 def test_many_phase_sets_in_one_sv(engine, n_ps):
     """k_reduce records up to 8 distinct PS per SV; 9..32 take the warp-cooperative fallback with its
     shared-memory list; beyond 32 the exact quadratic path runs.  All must agree with the oracle."""
