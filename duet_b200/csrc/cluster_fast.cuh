@@ -301,7 +301,7 @@ struct BucketSmem {
     unsigned brk[kBkCap / 32 + 1];
     unsigned char open[kBkCap];
     unsigned wscan[kBkThreads / 32];
-    int4 desc;                                   // the bucket to work on: {bucket, first record, signatures, zone copies of the next bucket}
+    int4 desc[2];                                // the bucket to work on / the next one: {bucket, first record, signatures, zone copies of the next bucket}
     int n_active;
 };
 
@@ -327,11 +327,13 @@ k_cl_bucket(FastArgs a) {
         const int tk = atomicAdd(&a.meta->ticket, 1);
         int4 d = make_int4(-1, 0, 0, 0);
         if (tk < n_list) { d = a.bucket_list[tk]; d.w = d.x + 1 < nb ? (int)a.zone_n[d.x + 1] : 0; }
-        S.desc = d;
+        S.desc[0] = d;
     }
-    for (;;) {
+#pragma unroll
+    for (int u = 0; u < (1 << kCellBits) / kBkThreads; ++u) S.cell[u * kBkThreads + tid] = 0;      // (re-zeroed at the end of every bucket)
+    for (int it_no = 0;; ++it_no) {
         __syncthreads();                                            // the descriptor is in; the previous bucket is done with shared memory
-        const int4 desc = S.desc;
+        const int4 desc = S.desc[it_no & 1];                        // (the other slot takes the next one: no second barrier)
         if (desc.x < 0) break;
         int next_tk = 0;
         if (tid == 0) next_tk = atomicAdd(&a.meta->ticket, 1);      // consumed at the end of this bucket
@@ -339,34 +341,29 @@ k_cl_bucket(FastArgs a) {
         const unsigned zn = (unsigned)desc.w;
         const int M = m + (int)min(zn, (unsigned)kZoneCap);
         const bool fits = zn <= (unsigned)kZoneCap && M <= kBkCap;
-        if (!fits && tid == 0) a.meta->oversize = 1;
-        __syncthreads();                                            // everyone has read the descriptor
         mark(0);
         if (!fits) {
-            if (tid == 0) S.desc = make_int4(-1, 0, 0, 0);          // the call takes the general path: stop
+            if (tid == 0) { a.meta->oversize = 1; S.desc[(it_no + 1) & 1] = make_int4(-1, 0, 0, 0); }      // the call takes the general path: stop
             continue;
         }
         int4 nd = make_int4(-1, 0, 0, 0);                           // thread 0: the next bucket's descriptor, fetched in steps below
         const unsigned long long base_key = (unsigned long long)b << sp.shift;
         const ulonglong2 *own = a.rec + desc.y, *halo = a.zone + (size_t)(b + 1) * kZoneCap;
-        // ---- load: own records, then the zone of the next bucket ----
-#pragma unroll
-        for (int u = 0; u < (1 << kCellBits) / kBkThreads; ++u) S.cell[u * kBkThreads + tid] = 0;
-#pragma unroll 4
-        for (int t = tid; t < M; t += kBkThreads) {
-            const ulonglong2 r = t < m ? __ldcs(own + t) : __ldcs(halo + t - m);
-            S.item[0][t] = ((r.x - base_key) << kBkSlotBits) | (unsigned long long)t;
-            S.span[t] = (int)(r.y >> 32);
-            S.idx[t] = (int)(unsigned)r.y;
-        }
-        __syncthreads();
-        mark(1);
-        // ---- ordering.  Cells first (one counting pass, arrival order inside a cell), then every item's exact
+        // ---- load: own records, then the zone of the next bucket; the members of every cell are counted on the way.
+        //      Ordering = cells first (one counting pass, arrival order inside a cell), then every item's exact
         //      place inside its cell by counting the smaller items there: a cell holds the signatures of about one
         //      window, so that is a few dozen comparisons per item instead of three radix passes ----
 #pragma unroll 4
-        for (int t = tid; t < M; t += kBkThreads) atomicAdd(&S.cell[(unsigned)(S.item[0][t] >> cshift)], 1u);
+        for (int t = tid; t < M; t += kBkThreads) {
+            const ulonglong2 r = t < m ? __ldcs(own + t) : __ldcs(halo + t - m);
+            const unsigned long long it = ((r.x - base_key) << kBkSlotBits) | (unsigned long long)t;
+            S.item[0][t] = it;
+            S.span[t] = (int)(r.y >> 32);
+            S.idx[t] = (int)(unsigned)r.y;
+            atomicAdd(&S.cell[(unsigned)(it >> cshift)], 1u);
+        }
         __syncthreads();
+        mark(1);
         mark(2);
         if (tid == 0 && next_tk < n_list) nd = a.bucket_list[next_tk];       // the ticket has long arrived
         {
@@ -480,6 +477,8 @@ k_cl_bucket(FastArgs a) {
         mark(7);
         // ---- smallest original index per component (a warp holds 32 consecutive sorted positions: equal roots
         //      sit next to each other, one shared-memory atomic per stretch); components that touch a zone are open ----
+#pragma unroll
+        for (int u = 0; u < (1 << kCellBits) / kBkThreads; ++u) S.cell[u * kBkThreads + tid] = 0;      // the list of active positions is dead: cells for the next bucket
         for (int k0 = 0; k0 < M; k0 += kBkThreads) {
             const int k = k0 + tid;
             const bool live = k < M;
@@ -522,7 +521,7 @@ k_cl_bucket(FastArgs a) {
             n_closed += live && rt == k && !is_open;
         }
         mark(9);
-        if (tid == 0) S.desc = nd;                                  // read behind the barrier at the top
+        if (tid == 0) S.desc[(it_no + 1) & 1] = nd;                 // read behind the barrier at the top
     }
     if (a.dbg && tid == 0) for (int k = 0; k < 10; ++k) a.dbg[(size_t)blockIdx.x * 12 + k] = ph[k];
     n_closed = __reduce_add_sync(0xffffffffu, n_closed);

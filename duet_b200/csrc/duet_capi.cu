@@ -929,7 +929,8 @@ static int cluster_fast(duet_handle *h, const ClusterArgs &g, ClMeta *meta, bool
         for (auto &e : de) cudaEventDestroy(e);
         std::vector<long long> d((size_t)bucket_grid * 12);
         CU(h, cudaMemcpy(d.data(), f.dbg, d.size() * 8, cudaMemcpyDeviceToHost));
-        static const char *const kPh[10] = {"wait for the block", "records loaded", "cells counted", "cell starts", "grouped by cell",
+        // (two stamps with nothing between them: what a stamp itself costs, to be subtracted from every phase)
+        static const char *const kPh[10] = {"wait for the block", "records + cell counts", "(a stamp's own cost)", "cell starts", "grouped by cell",
                                             "ranked inside cells", "runs", "window scan", "minima", "output"};
         for (int k = 0; k < 10; ++k) {
             double sum = 0; long long mx = 0;
