@@ -602,7 +602,7 @@ def strong_scaling(ctx: Ctx, eng, steps: int, warmup: int) -> dict:
             "n_emitted_unsharded": int(ref.shard_counts[:, 2].sum()),
             "collective": "dist.all_gather of 8 int64 counters per contig (NCCL), inside the timed call",
             "bounds": "speed-up is capped by the largest bin of the LPT plan (load_share_max; chr1 alone is 8 % of the genome) "
-                      "and by the launch floor of the four-kernel chain, which does not shrink with the shard"}
+                      "and by the launch floor of the chain, which does not shrink with the shard"}
 
 
 # ----------------------------------------------------------------------------------------------

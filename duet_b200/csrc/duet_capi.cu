@@ -100,8 +100,10 @@ struct duet_handle {
     bool dbg_on = false;
     size_t probe_smem = 0;
     DevBuf d_table;                 // Slot[n_slots], swept to all-ones by k_init at the start of every call
-    DevBuf d_bitmap;                // Bloom filter words, zeroed by k_init
-    DevBuf d_cand_list;
+    DevBuf d_bitmap;                // Bloom filter words: zeroed at upload, handed back zeroed by k_reduce
+    DevBuf d_cand_list, d_cand_count;
+    cudaStream_t side_stream = nullptr;   // two-branch mode: k_table's branch
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     DevBuf d_next, d_n_hit, d_cand, d_oneps, d_oneps_n, d_sort;
     DevBuf d_out;                   // every result column (and the join rows), laid out by output_layout()
     DevBuf d_order, d_n_emit, d_status;
@@ -185,14 +187,20 @@ struct Arena {
 // phase_kernels.cuh) before it touches anything the previous kernel writes.
 // `coop`: cooperative launch -- every block of the grid is resident at once (the runtime refuses the launch
 // otherwise); not used by the current chain (a cooperative single-kernel join was measured and lost).
+static thread_local int g_launch_priority = 0;
 template <typename... Params, typename... Args>
 static cudaError_t launch(void (*kernel)(Params...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, bool coop,
                           Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block);
     cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[3];
     int n = 0;
+    if (g_launch_priority != 0) {                                // set around a launch that should win the SMs (two-branch mode)
+        attr[n].id = cudaLaunchAttributePriority;
+        attr[n].val.priority = g_launch_priority;
+        ++n;
+    }
     if (pdl) {
         attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[n].val.programmaticStreamSerializationAllowed = 1;
@@ -263,6 +271,7 @@ int duet_create(int device_id, duet_handle **out) {
         cudaFuncAttributes fa;
         cudaFuncGetAttributes(&fa, k_probe);
         cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, kBloomMaxWords * 4 + kProbeRingBytes);
+        cudaFuncSetAttribute(k_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, kBloomMaxWords * 4 + kProbeRingBytes);
         cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)tail_smem_bytes((int)pow2_at_least(2 * kTailMaxSvs), kTailMaxSvs + 8));
         // one shared-memory carveout for all the kernels: switching it between launches drains the SMs
@@ -298,7 +307,7 @@ void duet_destroy(duet_handle *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     DevBuf *bufs[] = {&h->in_read_key, &h->in_read_tag, &h->in_small, &h->d_desc,
-                      &h->d_c2, &h->d_dbg, &h->d_table, &h->d_bitmap, &h->d_cand_list, &h->d_next,
+                      &h->d_c2, &h->d_dbg, &h->d_table, &h->d_bitmap, &h->d_cand_list, &h->d_cand_count, &h->d_next,
                       &h->d_n_hit, &h->d_cand, &h->d_oneps, &h->d_oneps_n, &h->d_sort, &h->d_out,
                       &h->d_order, &h->d_n_emit, &h->d_status};
     for (DevBuf *b : bufs) b->release();
@@ -312,6 +321,9 @@ void duet_destroy(duet_handle *h) {
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->graph) cudaGraphDestroy(h->graph);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
 }
 
@@ -443,6 +455,11 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     a.n_slots = slots;
     a.n_bm_words = bm_words;
     a.flags = h->flags;
+    // Big calls (dense callsets, cohort shares: >= 1 M support-read names) take the two-branch chain -- k_bloom ->
+    // k_stream beside k_init -> k_table, meeting at k_resolve: the read stream runs in the SM slots the table build
+    // leaves and under its tail (measured: C4 512 -> 481 us, C5 share 325 -> 302 us).  Small calls keep the serial
+    // chain: two more launches and the fork / join edges cost more than the overlap returns (C2 93 -> 95 us, C1 67 -> 69).
+    if (J >= (1ll << 20) && !(h->flags & kFlagSerialChain)) a.flags |= kFlagTwoBranch;
     const int mem = in->mem == DUET_MEM_HOST_MAPPED ? DUET_MEM_HOST : in->mem;      // only read_tag is special
     int rc;
 #define STAGE(buf, field, T, count)                                                                  \
@@ -599,7 +616,9 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     a.tab = h->d_table.as<Slot>();
     CU(h, h->d_bitmap.reserve((size_t)std::max<long long>(bm_words, 32) * 4));
     a.bitmap = h->d_bitmap.as<unsigned>();
+    CU(h, cudaMemsetAsync(a.bitmap, 0, (size_t)std::max<long long>(bm_words, 32) * 4, st));     // k_reduce keeps it clean from here on
     CU(h, h->d_cand_list.reserve((size_t)std::max<long long>(R, 1) * 16)); a.cand_list = h->d_cand_list.as<ulonglong2>();
+    CU(h, h->d_cand_count.reserve((size_t)std::max(h->probe_grid, 1) * 4)); a.cand_count = h->d_cand_count.as<int>();
     CU(h, h->d_next.reserve(J1 * 4));                    a.next = h->d_next.as<int>();
     CU(h, h->d_n_hit.reserve(S1 * 4));                   a.n_hit = h->d_n_hit.as<int>();
     CU(h, h->d_cand.reserve(S1 * 8));                    a.cand = h->d_cand.as<long long>();
@@ -644,13 +663,44 @@ static int launch_all(duet_handle *h, cudaStream_t st, bool marks) {
     auto mark = [&](int ev) { if (marks) cudaEventRecord(h->ev[ev], st); };
     static const bool no_pdl = std::getenv("DUET_NO_PDL") != nullptr;      // diagnostic switch
     const bool pdl = !marks && !no_pdl;
-    const PhaseArgs &a = h->a;
+    PhaseArgs a = h->a;
     const int S = a.n_svs;
     const bool join = a.n_joins > 0;
     const bool probe = a.n_reads && a.n_joins;
+    if (marks || !probe) a.flags &= ~kFlagTwoBranch;             // the serial (per-kernel timing) chain is the fused one
     int n = 0;
+    if (a.flags & kFlagTwoBranch) {
+        if (!h->side_stream) {
+            cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
+            cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+        }
+        cudaEventRecord(h->ev_fork, st);                         // the side branch starts with the call
+        cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0);
+    }
     if (join) { launch(k_init, h->n_sm * 4, kThreads, 0, st, false, false, a); ++n; }
     mark(EV_K0);
+    if (a.flags & kFlagTwoBranch) {
+        // developer variant: k_table stays behind k_init on this stream (programmatic launch, as in the serial
+        // chain: it is the critical path and gets the higher priority); k_bloom -> k_stream run beside it on a second
+        // stream; k_resolve waits for both (captured as a fork / join inside the graph)
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);              // hi = numerically smallest = greatest priority
+        g_launch_priority = hi;
+        switch (h->build_per_thread) {
+            case 1: launch(k_table<1>, h->build_grid, kThreads, 0, st, pdl, false, a); break;
+            case 2: launch(k_table<2>, h->build_grid, kThreads, 0, st, pdl, false, a); break;
+            case 4: launch(k_table<4>, h->build_grid, kThreads, 0, st, pdl, false, a); break;
+            default: launch(k_table<8>, h->build_grid, kThreads, 0, st, pdl, false, a); break;
+        }
+        g_launch_priority = 0;
+        launch(k_bloom, h->build_grid, kThreads, 0, h->side_stream, false, false, a, h->build_per_thread);
+        launch(k_stream, h->probe_grid, kProbeBlock, h->probe_smem, h->side_stream, pdl, false, a);
+        cudaEventRecord(h->ev_join, h->side_stream);
+        cudaStreamWaitEvent(st, h->ev_join, 0);
+        launch(k_resolve, h->probe_grid, kProbeBlock, 0, st, false, false, a);
+        n += 4;                                                  // k_table, k_bloom, k_stream, k_resolve
+    } else {
     if (join) {
         switch (h->build_per_thread) {
             case 1: launch(k_table<1>, h->build_grid, kThreads, 0, st, pdl, false, a); break;
@@ -662,6 +712,7 @@ static int launch_all(duet_handle *h, cudaStream_t st, bool marks) {
     }
     mark(EV_K1);
     if (probe) { launch(k_probe, h->probe_grid, kProbeBlock, h->probe_smem, st, pdl, false, a); ++n; }
+    }
     mark(EV_K2);
     if (S) {
         const int per = kThreads / h->reduce_lanes;
@@ -723,7 +774,8 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
         if (h->graph_exec) {
             CU(h, cudaGraphLaunch(h->graph_exec, st));
             const PhaseArgs &a = h->a;
-            n_graph = (a.n_joins ? 2 : 0) + (a.n_reads && a.n_joins ? 1 : 0) + (a.n_svs ? (h->tail_fused ? 2 : 4) : 0);
+            const bool probe = a.n_reads && a.n_joins;
+            n_graph = (a.n_joins ? 2 : 0) + (probe ? ((a.flags & kFlagTwoBranch) ? 3 : 1) : 0) + (a.n_svs ? (h->tail_fused ? 2 : 4) : 0);
             h->launches += n_graph;
         } else {
             h->launches += launch_all(h, st, false);

@@ -1,8 +1,8 @@
 // sm_100a kernels of the sv_phasing hot path.
 //
 // Reference behaviour restated per kernel (citations: /root/reference/src/duet/sv_phasing_fn.py):
-//   k_init     start-of-call state in one sequential sweep: EMPTY slot table, zero Bloom filter, join
-//              results -1 -- which also leaves all three L2 resident for the scattered traffic that follows
+//   k_init     start-of-call state in one sequential sweep: EMPTY slot table, join results -1 (the Bloom
+//              filter is handed back zeroed by k_reduce) -- which also leaves all three L2 resident for the scattered traffic that follows
 //   k_table    the dict-insert side of the JOIN (:26-29 keyed by QNAME) -- here the SMALL side is
 //              inserted: every support-read name of the SVs (:46-48) claims a slot (one CAS) and sets its
 //              two Bloom-filter bits (one RED)
@@ -83,6 +83,8 @@ enum {
     kFlagNoStreamHint = 4,    // k_probe's key stream without the L2 evict-first hint
     kFlagFill2 = 16,          // host: load factor <= 1/2 always
     kFlagSplitTail = 32,      // host: k_oneps / k_predict / k_order instead of k_tail
+    kFlagTwoBranch = 64,      // k_bloom -> k_stream beside k_init -> k_table, meeting at k_resolve: set by the host for big calls, or forced here
+    kFlagSerialChain = 128,   // host: never the two-branch chain
 };
 
 struct PhaseArgs {
@@ -99,6 +101,7 @@ struct PhaseArgs {
     const ProbeTile *probe_tiles;   // [n_probe_tiles] = k_probe grid
     int n_probe_tiles;
     ulonglong2 *cand_list;          // [R] rows that passed their contig's filter, (key, row): tile t appends at [r0(t), ...)
+    int *cand_count;                // [n_probe_tiles] candidates of each tile (k_stream -> k_resolve; unused by the fused k_probe)
     const unsigned long long *read_key;
     const ReadTag *read_tag;
     const int *sv_pos, *sv_svlen, *sv_svread, *sv_refread;
@@ -325,13 +328,12 @@ k_init(PhaseArgs a) {
     pdl_wait();                                                  // first kernel of a call: returns at once
     const long long stride = (long long)gridDim.x * kThreads;
     const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
-    const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0u, 0u, 0u, 0u);
+    const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
     uint4 *tab = reinterpret_cast<uint4 *>(a.tab);
     for (long long i = t; i < a.n_slots; i += stride) tab[i] = ones;
     uint4 *jr = reinterpret_cast<uint4 *>(a.join_row);           // allocation padded to 16 bytes
     for (long long i = t; i < ((long long)a.n_joins + 3) / 4; i += stride) jr[i] = ones;
-    uint4 *bm = reinterpret_cast<uint4 *>(a.bitmap);
-    for (long long i = t; i < a.n_bm_words / 4; i += stride) bm[i] = zero;
+    // (the Bloom filter is zero already: duet_phase_upload clears it once and k_reduce hands it back clean)
     if (!(a.flags & kFlagNoWarm)) {
         const size_t S = (size_t)a.n_svs, J = (size_t)a.n_joins;
         warm_l2(a.csr_off, (S + 1) * 8, t, stride);
@@ -385,9 +387,11 @@ k_table(PhaseArgs a) {
     pdl_trigger();
     pdl_wait();                                                  // the slots and the filter words are initialised
     dbg_mark(a, 0, 1);
+    if (!(a.flags & kFlagTwoBranch)) {                           // (two-branch mode: k_bloom has set them)
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-        if (pend >> u & 1u) atomicOr(a.bitmap + bmo[u] + (int)bloom_word(key[u], bmw[u]), bloom_bits(key[u]));    // fire and forget
+        for (int u = 0; u < U; ++u)
+            if (pend >> u & 1u) atomicOr(a.bitmap + bmo[u] + (int)bloom_word(key[u], bmw[u]), bloom_bits(key[u]));    // fire and forget
+    }
     while (pend) {
         unsigned long long prev[U];
 #pragma unroll
@@ -404,6 +408,23 @@ k_table(PhaseArgs a) {
         }
     }
     dbg_mark(a, 0, 2);
+}
+
+// two-branch mode: the filter bits alone, so that the read stream can start while k_table is still claiming slots
+__global__ void __launch_bounds__(kThreads)
+k_bloom(PhaseArgs a, int per_thread) {
+    const BuildTile t = a.build_tiles[blockIdx.x];
+    const long long j0 = (long long)blockIdx.x * (kThreads * per_thread) + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();                                                  // the filter words are zero
+    for (int u = 0; u < per_thread; ++u) {
+        const long long j = j0 + (long long)u * kThreads;
+        if (j >= a.n_joins) break;
+        const unsigned long long key = __ldcs(a.csr_key + j);
+        int base, bmo; unsigned mask, bmw;
+        build_where(a, t, j, base, mask, bmo, bmw);
+        atomicOr(a.bitmap + bmo + (int)bloom_word(key, bmw), bloom_bits(key));
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -435,8 +456,10 @@ constexpr int kProbeStages = 3;                                  // tiles in fli
 constexpr int kProbeRingBytes = kProbeStages * kProbeBatch * 16;
 constexpr int kResolveUnroll = 4;                                // candidates per thread in flight in the drain
 
-__global__ void __launch_bounds__(kProbeBlock, kProbeBlocksPerSm)
-k_probe(PhaseArgs a) {
+// MODE 0: the fused kernel (stream, then resolve).  MODE 1 = k_stream: the stream alone, the tile's candidate count
+// goes to cand_count.  MODE 2 = k_resolve: the resolve alone.
+template <int MODE>
+__device__ __forceinline__ void probe_body(const PhaseArgs &a) {
     extern __shared__ __align__(128) unsigned char s_raw[];      // [key ring | filter words]
     __shared__ __align__(8) unsigned long long s_full[kProbeStages], s_empty[kProbeStages], s_bm_full;
     __shared__ int s_count;
@@ -455,6 +478,11 @@ k_probe(PhaseArgs a) {
     const int n_tiles = (int)((q1 - q0 + kProbeBatch - 1) / kProbeBatch);
     const unsigned long long stream_policy = (a.flags & kFlagNoStreamHint) ? 0ull : l2_evict_first_policy();
     auto tile_pairs = [&](int t) { return (unsigned)max(0ll, min(q_full, q0 + (long long)(t + 1) * kProbeBatch) - (q0 + (long long)t * kProbeBatch)); };
+    if (MODE == 2) {                                             // k_resolve: everything before it has completed
+        pdl_trigger();
+        pdl_wait();
+        if (threadIdx.x == 0) s_count = a.cand_count[blockIdx.x];
+    } else {
     if (threadIdx.x == 0) {
         for (int s = 0; s < kProbeStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kProbeThreads / 32); }
         mbar_init(&s_bm_full, 1);
@@ -546,8 +574,13 @@ k_probe(PhaseArgs a) {
                 }
         }
     }
+    }                                                            // MODE != 2
     __syncthreads();
     dbg_mark(a, 1, 3);
+    if (MODE == 1) {                                             // k_stream: k_resolve takes it from here
+        if (threadIdx.x == 0) a.cand_count[blockIdx.x] = s_count;
+        return;
+    }
     // Resolve the block's candidates (all 17 warps): one 16-byte slot load decides; a hit pushes the row
     // index to every support-read entry of that name with atomicMax -- a later row overrides an earlier
     // one (sv_phasing_fn.py:29).
@@ -592,6 +625,14 @@ k_probe(PhaseArgs a) {
     }
     dbg_mark(a, 1, 4);
 }
+
+__global__ void __launch_bounds__(kProbeBlock, kProbeBlocksPerSm)
+k_probe(PhaseArgs a) { probe_body<0>(a); }
+// two-branch mode (kFlagTwoBranch): the stream beside k_table, the resolve behind both
+__global__ void __launch_bounds__(kProbeBlock, kProbeBlocksPerSm)
+k_stream(PhaseArgs a) { probe_body<1>(a); }
+__global__ void __launch_bounds__(kProbeBlock, kProbeBlocksPerSm)
+k_resolve(PhaseArgs a) { probe_body<2>(a); }
 
 // ------------------------------------------------------------------------------------------
 // one-PS list of a shard, as a block of its own (k_oneps: contigs too large for k_tail's cluster).
@@ -813,6 +854,12 @@ k_reduce(PhaseArgs a) {
     }
     pdl_trigger();
     pdl_wait();                                                  // the join rows are final
+    {   // every reader of the Bloom filter is done: hand it back zeroed, so that the next call's filter bits can be
+        // set from its first microsecond on (two-branch mode: k_bloom beside k_init)
+        uint4 *bm = reinterpret_cast<uint4 *>(a.bitmap);
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.n_bm_words / 4; i += (long long)gridDim.x * kThreads) bm[i] = zero;
+    }
     int hits = 0, ps_lo = INT32_MAX, ps_hi = INT32_MIN;
     int h1 = 0, h2 = 0, nq = 0;
     long long t1 = 0, t2 = 0;

@@ -151,6 +151,32 @@ def test_pipeline_two_calls_in_flight_equals_sequential(engine):
         pipe.close()
 
 
+def test_two_branch_chain_equals_serial_chain(engine, monkeypatch):
+    """Calls with >= 1 M support-read names take the two-branch chain (k_bloom -> k_stream beside k_init -> k_table,
+    meeting at k_resolve; the full-size C4 / C5 parity tests run it).  DUET_FLAGS=64 forces it for small calls too:
+    same results as the serial chain, call after call (the filter is handed back clean by k_reduce)."""
+    from duet_b200.engine import PhaseEngine
+    monkeypatch.setenv("DUET_FLAGS", "64")
+    forced = PhaseEngine(0)
+    monkeypatch.delenv("DUET_FLAGS")
+    try:
+        forced.set_thresholds(50, 2)
+        engine.set_thresholds(50, 2)
+        keys = ("gt", "ps", "cls", "hap1", "hap2", "hap0", "allhap", "totsc1", "totsc2", "join_row", "order", "shard_counts", "features")
+        for k in range(4):
+            s = synth.make_sample(40 + k, contigs=["1", "2", "X", "21"][: 1 + k], n_reads=5000 + 3000 * k, n_svs=300 + 150 * k,
+                                  bp_per_read=700, block_mean=1e5, dense=(k == 3))
+            batch = from_synth(s)
+            want = engine.run(batch)
+            for _ in range(3):
+                got = forced.run(batch)
+                for name in keys:
+                    assert np.array_equal(getattr(want, name), getattr(got, name)), name
+            assert forced.launch_count() % 7 == 0                # k_init, k_table, k_bloom, k_stream, k_resolve, k_reduce, k_tail
+    finally:
+        forced.close()
+
+
 def test_golden_kat_on_device(engine):
     """Every known-answer case recorded from the reference's get_phase_info / predict_hp whose
     class is reachable through the pipeline, run as one shard each in ONE device call."""
