@@ -12,7 +12,7 @@
 //                 array (unordered inside the bucket; one returning atomic per signature).  A signature within
 //                 the partition window of its bucket's lower boundary is also copied into that bucket's ZONE
 //                 list: it is the halo of the bucket before.
-//   k_cl_bucket   persistent blocks walk the list of non-empty buckets.  A bucket (+ the zone of the next one)
+//   k_cl_bucket   persistent 512-thread blocks take the non-empty buckets from a ticket counter.  A bucket (+ the zone of the next one)
 //                 lives in shared memory from here on: radix-sorted by the remaining key bits, runs of linked
 //                 sorted neighbours, the windowed scan over the other runs with a forest of the block, smallest
 //                 original index per component -- and the cluster ids of every component that does not touch a
@@ -25,8 +25,6 @@
 // zone) sets `oversize`; the host then runs the general path for the call.  Same spec, same result: cluster ids
 // do not depend on the order of equal keys, so neither path needs a stable sort order to agree with the other.
 #pragma once
-
-#include <cooperative_groups.h>
 
 #include "cluster_kernels.cuh"
 
