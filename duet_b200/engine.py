@@ -45,14 +45,18 @@ class PhaseResult:
         stably sorted by (chrom, pos).  The device order already is the reference's append order
         sorted per shard, so the final sort only has to interleave shards."""
         out = []
-        shard_of = np.searchsorted(batch.sv_off, self.order, side="right") - 1
-        for i, s in zip(self.order.tolist(), shard_of.tolist()):
+        order = self.order
+        shard_of = (np.searchsorted(batch.sv_off, order, side="right") - 1).tolist()
+        # plain Python lists of just the emitted rows: indexing numpy scalars one by one is what costs here
+        ps, gt = self.ps[order].tolist(), self.gt[order].tolist()
+        pos, svlen = batch.sv_pos[order].tolist(), batch.sv_svlen[order].tolist()
+        for k, (i, s) in enumerate(zip(order.tolist(), shard_of)):
             if sample is not None and batch.shard_sample[s] != sample:
                 continue
             svtype = batch.sv_type[i]
-            ln = int(batch.sv_svlen[i])
-            out.append({"ps": int(self.ps[i]), "hp": GT_TEXT[int(self.gt[i])], "chrom": batch.sv_chrom[i],
-                        "pos": int(batch.sv_pos[i]), "svlen": ln if svtype in ("INS", "DUP") else -ln,
+            ln = svlen[k]
+            out.append({"ps": ps[k], "hp": GT_TEXT[gt[k]], "chrom": batch.sv_chrom[i],
+                        "pos": pos[k], "svlen": ln if svtype in ("INS", "DUP") else -ln,
                         "svtype": svtype, "ref": batch.sv_ref[i], "alt": batch.sv_alt[i]})
         out.sort(key=lambda d: (d["chrom"], d["pos"]))
         return out

@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import logging
 
-from .read_file import init_chrom_list, read_file
+from .read_file import init_chrom_list
 
 _FIXED_HEADER = "".join([
     "##fileformat=VCFv4.2\n",
@@ -35,16 +35,32 @@ def print_sv(phased_callset, output_path):
         f.write(format_rows(phased_callset))
 
 
+def _contig_tokens(vcf_path) -> list:
+    """The first whitespace-separated token of every line whose first token contains '##contig=<ID=', in file
+    order -- all the reference's header loop (:31-40) ever matches -- without splitting the 20 MB of RNAMES lists
+    the way `read_file` does.  A blank line raises IndexError, as `l[0]` does there."""
+    out = []
+    with open(vcf_path, "r") as fh:
+        for ln in fh:
+            if "##contig=<ID=" in ln:
+                tok = ln.split(None, 1)[0]
+                if "##contig=<ID=" in tok:
+                    out.append(tok)
+            elif ln.isspace():
+                raise IndexError("list index out of range")
+    return out
+
+
 def header_text(vcf_path, include_all_ctgs) -> str:
-    vcf_rows = read_file(vcf_path)
+    tokens = _contig_tokens(vcf_path)
     chrom_list = init_chrom_list(include_all_ctgs, vcf_path[:len(vcf_path) - 24])
     out = [_FIXED_HEADER]
     if not include_all_ctgs:
         for ctg in chrom_list[:24]:                       # contig lines re-ordered to the chrom list (:33-37)
             a, b = "##contig=<ID=chr" + ctg + ",", "##contig=<ID=" + ctg + ","
-            out += [row[0] + "\n" for row in vcf_rows if a in row[0] or b in row[0]]
+            out += [t + "\n" for t in tokens if a in t or b in t]
     else:
-        out += [row[0] + "\n" for row in vcf_rows if "##contig=<ID=" in row[0]]
+        out += [t + "\n" for t in tokens]
     out.append(_COLUMNS)
     return "".join(out)
 

@@ -444,3 +444,25 @@ def test_sam_text_with_header_lines_is_read_like_samtools_view():
     text = b"@HD\tVN:1.6\tSO:coordinate\n@CO\nq1\t0\t1\t5\t60\t4M\t*\t0\t0\tACGT\t*\tHP:i:1\tPC:i:7\tPS:i:3\n"
     cols = sv_phasing_fn.decode_sam_text(text)
     assert len(cols) == 1 and (int(cols.hp[0]), int(cols.pc[0]), int(cols.ps[0])) == (1, 7, 3)
+
+
+def test_header_scan_matches_the_reference_loop(tmp_path):
+    """write_file.header_text no longer splits every record (read_file) to find the ##contig lines: same lines, same
+    order, same IndexError on a blank line as the reference's `l[0]` (write_file.py:31-40)."""
+    from duet_b200 import write_file
+    from oracle import ref_port
+    home = tmp_path / "h"
+    (home / "sv_calling").mkdir(parents=True)
+    vcf = home / "sv_calling" / "variants.vcf"
+    body = ("##fileformat=VCFv4.2\n##contig=<ID=2,length=5>\n##contig=<ID=chr1,length=9>  trailing tokens\n"
+            "##contig=<ID=GL000,length=1>\n##other\t##contig=<ID=3,length=2>\n  ##contig=<ID=X,length=7>\n"
+            "#CHROM\tPOS\n1\t5\t##contig=<ID=Y,length=3>\n")
+    vcf.write_text(body)
+    got = write_file.header_text(str(vcf), False)
+    assert got == ref_port.header_text(str(vcf), False)
+    assert "##contig=<ID=3," not in got and "##contig=<ID=Y," not in got and "##contig=<ID=X,length=7>\n" in got
+    vcf.write_text(body + "\n")                              # a blank line
+    with pytest.raises(IndexError):
+        write_file.header_text(str(vcf), False)
+    with pytest.raises(IndexError):
+        ref_port.header_text(str(vcf), False)
