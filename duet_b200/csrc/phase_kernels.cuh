@@ -85,6 +85,7 @@ enum {
     kFlagSplitTail = 32,      // host: k_oneps / k_predict / k_order instead of k_tail
     kFlagTwoBranch = 64,      // k_bloom -> k_stream beside k_init -> k_table, meeting at k_resolve: set by the host for big calls, or forced here
     kFlagSerialChain = 128,   // host: never the two-branch chain
+    kFlagNoTagPrefetch = 256, // k_probe does not prefetch the candidates' tag records into L2
 };
 
 struct PhaseArgs {
@@ -570,7 +571,7 @@ __device__ __forceinline__ void probe_body(const PhaseArgs &a) {
                     out[pos++] = make_ulonglong2(key[u], (unsigned long long)(unsigned)row);
                     // what k_reduce will want from HBM at random -- the row's tag record -- starts moving into
                     // L2 now, under the stream
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.read_tag + row));
+                    if (!(a.flags & kFlagNoTagPrefetch)) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.read_tag + row));
                 }
         }
     }
