@@ -88,25 +88,34 @@ def _oracle_cluster_fn(contig, typ, start, end, cluster_max_distance=0.9, *, pos
     return ids, n, 0.0
 
 
-def _shard_worker(rank, world, port, out_q):
+def _shard_worker(rank, world, port, out_q, on_gpu=False):
     import os
     import sys
     import torch.distributed as dist
     from conftest import ROOT
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if on_gpu:
+        import torch
+        os.environ["DUET_DEVICE"] = str(rank % torch.cuda.device_count())      # >= 2 GPUs visible: every rank its own
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from duet_b200 import synth
         from duet_b200.sv_clustering import cluster_signatures_sharded
         cols = synth.make_signatures(3, 60_000, contigs=["1", "2", "21", "X"])
-        index, ids, total = cluster_signatures_sharded(*cols, cluster_fn=_oracle_cluster_fn)
+        index, ids, total = cluster_signatures_sharded(*cols, cluster_fn=None if on_gpu else _oracle_cluster_fn)
         out_q.put((rank, index, ids, total))
     finally:
         dist.destroy_process_group()
 
 
-def test_contig_sharded_clustering_equals_single_process():
+@pytest.mark.gpu
+def test_contig_sharded_clustering_on_gpu():
+    """The same with the device path in every rank (each on its own GPU when the box has several)."""
+    test_contig_sharded_clustering_equals_single_process(on_gpu=True, world=2)
+
+
+def test_contig_sharded_clustering_equals_single_process(on_gpu=False, world=3):
     """(contig, type) groups LPT-packed over 3 gloo ranks (the oracle stands in for the device): the union of
     the ranks' slices is the single-process result, every signature is owned exactly once, the all-reduced
     cluster count is the global one."""
@@ -121,7 +130,7 @@ def test_contig_sharded_clustering_equals_single_process():
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_shard_worker, args=(r, 3, port, q)) for r in range(3)]
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port, q, on_gpu)) for r in range(world)]
     for p in procs:
         p.start()
     got = [q.get(timeout=120) for _ in procs]
