@@ -82,6 +82,7 @@ class ClockSampler:
     def __init__(self, index: int):
         self.samples, self.reasons = [], set()
         self.max_mhz = None
+        self.period_s = float(os.environ.get("BENCH_CLOCK_PERIOD_MS", "2")) * 1e-3
         self._stop = threading.Event()
         self._active = threading.Event()
         try:
@@ -106,7 +107,7 @@ class ClockSampler:
                             self.reasons.add(name)
                 except Exception:
                     pass
-            time.sleep(0.002)
+            time.sleep(self.period_s)
 
     def __enter__(self):
         self._active.set()
@@ -658,6 +659,16 @@ def main():
     m = measure_phase(ctx, eng, batch, args.steps, args.warmup)
     res = m["res"]
     total_ms, e2e_s, copied_s, pipe_s = ctx.max_over_ranks(m["total_ms"], m["e2e_s"], m["copied_s"], m["pipe_s"])
+    per_rank = None
+    if world > 1:                                  # where the e2e time of a multi-GPU run goes: every rank's own figures
+        tm_r = m["e2e_tm"]
+        torch = ctx.torch
+        mine = torch.tensor([m["e2e_s"] / args.steps * 1e3, tm_r["h2d_ms"], tm_r["device_ms"], tm_r["d2h_ms"]], dtype=torch.float64, device=ctx.dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        ctx.dist.all_gather(allr, mine)
+        per_rank = {"call_ms": [round(float(t[0]), 3) for t in allr], "h2d_ms_last_step": [round(float(t[1]), 3) for t in allr],
+                    "device_ms_last_step": [round(float(t[2]), 3) for t in allr], "d2h_ms_last_step": [round(float(t[3]), 3) for t in allr],
+                    "note": "wall clock per call of each rank's e2e loop, and the event-timed copies / kernels of its last step"}
     n_svs, n_joins, n_reads = ctx.sum_over_ranks(batch.n_svs, batch.n_joins, batch.n_reads)
 
     # counters gathered once (not on the weak-scaling data path: shards never exchange data)
@@ -713,6 +724,7 @@ def main():
                             "16-byte tag records, which k_reduce gathers over the bus (one 32-byte sector per joined "
                             "read, counted in h2d_bytes_per_step)",
                     "last_step": {k: tm[k] for k in ("h2d_ms", "device_ms", "d2h_ms")},
+                    "per_rank": per_rank,
                     "two_calls_in_flight": {"value": n_svs / (pipe_s / args.steps), "ms_per_step": pipe_s / args.steps * 1e3,
                                             "mode": "duet_b200.engine.PhasePipeline(depth=2): the same calls, sample k+1's upload and "
                                                     "kernels enqueued before sample k's results are waited for (cohort mode); every "
