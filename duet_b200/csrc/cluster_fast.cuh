@@ -113,25 +113,28 @@ k_cl_max(FastArgs a) {
     const int tid = threadIdx.x, lane = tid & 31;
     unsigned mc = 0, mt = 0, m2 = 0;
     bool bad = false;
-    const long long base = (long long)blockIdx.x * (kClThreads * kSpUnroll);
-    int c[kSpUnroll], t[kSpUnroll], st[kSpUnroll], en[kSpUnroll];
-#pragma unroll
-    for (int u = 0; u < kSpUnroll; ++u) {
-        const long long i = base + u * kClThreads + tid;
-        c[u] = t[u] = st[u] = en[u] = 0;
-        if (i < a.n) { c[u] = __ldcs(a.contig + i); t[u] = __ldcs(a.type + i); st[u] = a.start[i]; en[u] = __ldcs(a.end + i); }
-    }
     fast_pdl_wait();                                               // the previous call is done with key / parent / counters
+    // a resident grid (8 blocks per SM) strides over the tiles: 7809 one-tile blocks spent a third of the kernel
+    // being scheduled
+    for (long long base = (long long)blockIdx.x * (kClThreads * kSpUnroll); base < a.n; base += (long long)gridDim.x * (kClThreads * kSpUnroll)) {
+        int c[kSpUnroll], t[kSpUnroll], st[kSpUnroll], en[kSpUnroll];
 #pragma unroll
-    for (int u = 0; u < kSpUnroll; ++u) {
-        const long long i = base + u * kClThreads + tid;
-        const long long s2 = (long long)st[u] + en[u];
-        bad |= st[u] < 0 || en[u] < st[u] || s2 > 0xFFFFFFFFll || (unsigned)c[u] > 0xFFFFu || (unsigned)t[u] > 0xFFu;
-        const unsigned cc = (unsigned)c[u] & 0xFFFFu, tt = (unsigned)t[u] & 0xFFu;
-        mc = max(mc, cc); mt = max(mt, tt); m2 = max(m2, (unsigned)s2);
-        if (i < a.n) {
-            a.key[i] = ((unsigned long long)cc << 40) | ((unsigned long long)tt << 32) | (unsigned long long)(unsigned)s2;
-            a.parent[i] = -1;
+        for (int u = 0; u < kSpUnroll; ++u) {
+            const long long i = base + u * kClThreads + tid;
+            c[u] = t[u] = st[u] = en[u] = 0;
+            if (i < a.n) { c[u] = __ldcs(a.contig + i); t[u] = __ldcs(a.type + i); st[u] = a.start[i]; en[u] = __ldcs(a.end + i); }
+        }
+#pragma unroll
+        for (int u = 0; u < kSpUnroll; ++u) {
+            const long long i = base + u * kClThreads + tid;
+            const long long s2 = (long long)st[u] + en[u];
+            bad |= st[u] < 0 || en[u] < st[u] || s2 > 0xFFFFFFFFll || (unsigned)c[u] > 0xFFFFu || (unsigned)t[u] > 0xFFu;
+            const unsigned cc = (unsigned)c[u] & 0xFFFFu, tt = (unsigned)t[u] & 0xFFu;
+            mc = max(mc, cc); mt = max(mt, tt); m2 = max(m2, (unsigned)s2);
+            if (i < a.n) {
+                a.key[i] = ((unsigned long long)cc << 40) | ((unsigned long long)tt << 32) | (unsigned long long)(unsigned)s2;
+                a.parent[i] = -1;
+            }
         }
     }
     mc = __reduce_max_sync(0xffffffffu, mc); mt = __reduce_max_sync(0xffffffffu, mt); m2 = __reduce_max_sync(0xffffffffu, m2);

@@ -954,7 +954,7 @@ static int cluster_fast(duet_handle *h, const ClusterArgs &g, ClMeta *meta, bool
     cudaEvent_t de[5] = {};
     if (dbg) for (auto &e : de) CU(h, cudaEventCreate(&e));
     if (dbg) CU(h, cudaEventRecord(de[0], st));
-    CU(h, launch(k_cl_max, stream_grid, kClThreads, 0, st, false, false, f));
+    CU(h, launch(k_cl_max, std::min(stream_grid, h->n_sm * 8), kClThreads, 0, st, false, false, f));
     if (dbg) CU(h, cudaEventRecord(de[1], st));
     const int ag_grid = (int)((g.n + kAgThreads * kAgItems - 1) / (kAgThreads * kAgItems));
     const size_t ag_smem = NB * sizeof(unsigned);
