@@ -187,17 +187,11 @@ k_cl_hist(FastArgs a) {
 // Every signature into its bucket's stretch.  The block counts its own signatures per bucket in shared memory
 // (the count a signature sees is its place among the block's), reserves one range per non-empty counter with a
 // single returning atomic, and writes the records.
-__global__ void __launch_bounds__(kAgThreads)
+__global__ void __launch_bounds__(kAgThreads, 2)
 k_cl_scatter(FastArgs a) {
     extern __shared__ unsigned s_ag[];                             // [1 << B]
     fast_pdl_trigger();
     const long long base = (long long)blockIdx.x * (kAgThreads * kAgItems);
-    int st[kAgItems];
-#pragma unroll
-    for (int u = 0; u < kAgItems; ++u) {
-        const long long i = base + u * kAgThreads + threadIdx.x;
-        st[u] = i < a.n ? __ldcs(a.start + i) : 0;                 // an input column: no need to wait for it
-    }
     fast_pdl_wait();                                               // the histogram is final (and, transitively, the keys)
     const Split sp = split_of(a.meta, a.n, a.window2, a.bucket_bits_override);
     if (a.meta->bad || sp.shift + 1 + kBkSlotBits > 64) {          // invalid input / keys too wide for a bucket's sort items
@@ -205,19 +199,28 @@ k_cl_scatter(FastArgs a) {
         return;
     }
     const int nb = 1 << sp.B;
-    unsigned long long key[kAgItems];
-#pragma unroll
-    for (int u = 0; u < kAgItems; ++u) {
-        const long long i = base + u * kAgThreads + threadIdx.x;
-        key[u] = i < a.n ? __ldcs(a.key + i) : 0ull;
-    }
     for (int b = threadIdx.x; b < nb; b += kAgThreads) s_ag[b] = 0;
     __syncthreads();
-    unsigned rank[kAgItems];
+    // Two blocks of 1024 threads per SM (the whole grid resident at once) leave 32 registers per thread: the keys are
+    // not kept across the phases -- they are read again for the write (out of L2) -- and a signature's place among
+    // the block's (< 8192) is kept in 16 bits.
+    unsigned rank2[kAgItems / 2];
 #pragma unroll
-    for (int u = 0; u < kAgItems; ++u) {
-        rank[u] = 0;
-        if (base + u * kAgThreads + threadIdx.x < a.n) rank[u] = atomicAdd(&s_ag[(unsigned)(repack(sp, key[u]) >> sp.shift)], 1u);
+    for (int half = 0; half < 2; ++half) {
+        constexpr int kH = kAgItems / 2;
+        unsigned long long key[kH];
+#pragma unroll
+        for (int v = 0; v < kH; ++v) {
+            const long long i = base + (half * kH + v) * kAgThreads + threadIdx.x;
+            key[v] = i < a.n ? a.key[i] : 0ull;
+        }
+#pragma unroll
+        for (int v = 0; v < kH; ++v) {
+            const int u = half * kH + v;
+            unsigned r = 0;
+            if (base + u * kAgThreads + threadIdx.x < a.n) r = atomicAdd(&s_ag[(unsigned)(repack(sp, key[v]) >> sp.shift)], 1u);
+            if (u & 1) rank2[u >> 1] |= r << 16; else rank2[u >> 1] = r;
+        }
     }
     __syncthreads();
     {   // where the buckets start: every block scans the 2^B counters itself (64 KB out of L2) -- a kernel of one
@@ -227,16 +230,14 @@ k_cl_scatter(FastArgs a) {
         // warp w owns the `per` x 32 consecutive buckets from w * per * 32 on, lane l the buckets j * 32 + l of them:
         // coalesced loads, conflict-free shared memory (a thread owning 16 CONSECUTIVE counters cost 8 us in
         // 64-byte-strided accesses alone)
-        constexpr int kPer = (1 << kBkMaxBits) / kAgThreads;       // 16
-        const int per = max(nb / kAgThreads, 1);
+        const int per = max(nb / kAgThreads, 1);                   // <= 16
         const int wb = w * per * 32;
-        unsigned cnt[kPer];
         unsigned long long sum = 0;                                // signatures : 32 | non-empty buckets : 32
-#pragma unroll
-        for (int j = 0; j < kPer; ++j) {
+#pragma unroll 4
+        for (int j = 0; j < per; ++j) {
             const int b = wb + j * 32 + lane;
-            cnt[j] = (j < per && b < nb) ? __ldcg(a.hist + b) : 0u;
-            sum += ((unsigned long long)cnt[j] << 32) | (cnt[j] ? 1ull : 0ull);
+            const unsigned c = b < nb ? __ldcg(a.hist + b) : 0u;
+            sum += ((unsigned long long)c << 32) | (c ? 1ull : 0ull);
         }
         unsigned long long wsum = sum;                             // the warp's total
 #pragma unroll
@@ -246,10 +247,10 @@ k_cl_scatter(FastArgs a) {
         unsigned long long carry = 0;
         for (int k = 0; k < w; ++k) carry += s_scan[k];
         bool big = false;
-#pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-            if (j >= per) break;
-            const unsigned long long x = ((unsigned long long)cnt[j] << 32) | (cnt[j] ? 1ull : 0ull);
+        for (int j = 0; j < per; ++j) {                            // (the counters are read again: registers are what is scarce)
+            const int b = wb + j * 32 + lane;
+            const unsigned c = b < nb ? __ldcg(a.hist + b) : 0u;
+            const unsigned long long x = ((unsigned long long)c << 32) | (c ? 1ull : 0ull);
             unsigned long long inc = x;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -258,13 +259,12 @@ k_cl_scatter(FastArgs a) {
             }
             const unsigned long long before = carry + inc - x;
             carry += __shfl_sync(0xffffffffu, inc, 31);
-            const int b = wb + j * 32 + lane;
             if (b < nb) {
                 const unsigned at = (unsigned)(before >> 32);
                 const unsigned mine = s_ag[b];
                 if (mine) s_ag[b] = at + atomicAdd(&a.cursor[b], mine);          // the block's range inside the bucket
-                if (blockIdx.x == 0 && cnt[j]) a.bucket_list[(int)(unsigned)before] = make_int4(b, (int)at, (int)cnt[j], 0);
-                big |= cnt[j] > (unsigned)kBkCap;
+                if (blockIdx.x == 0 && c) a.bucket_list[(int)(unsigned)before] = make_int4(b, (int)at, (int)c, 0);
+                big |= c > (unsigned)kBkCap;
             }
         }
         if (blockIdx.x == 0 && tid == kAgThreads - 1) a.meta->n_buckets = (int)(unsigned)carry;
@@ -273,18 +273,32 @@ k_cl_scatter(FastArgs a) {
     __syncthreads();
     const unsigned long long low_mask = sp.shift >= 64 ? ~0ull : ((1ull << sp.shift) - 1ull);
 #pragma unroll
-    for (int u = 0; u < kAgItems; ++u) {
-        const long long i = base + u * kAgThreads + threadIdx.x;
-        if (i >= a.n) continue;
-        const unsigned long long pk = repack(sp, key[u]);
-        const unsigned b = (unsigned)(pk >> sp.shift);
-        const unsigned span = (unsigned)key[u] - 2u * (unsigned)st[u];          // c2 - 2 start = end - start
-        const ulonglong2 r = make_ulonglong2(pk, ((unsigned long long)span << 32) | (unsigned)i);
-        a.rec[s_ag[b] + rank[u]] = r;
-        if (b > 0 && (pk & low_mask) <= a.window2) {               // inside the window of the bucket's lower boundary
-            const unsigned z = atomicAdd(&a.zone_n[b], 1u);
-            if (z < (unsigned)kZoneCap) a.zone[(size_t)b * kZoneCap + z] = r;
-            else a.meta->oversize = 1;
+    for (int half = 0; half < 2; ++half) {
+        constexpr int kH = kAgItems / 2;
+        unsigned long long key[kH];
+        int st[kH];
+#pragma unroll
+        for (int v = 0; v < kH; ++v) {
+            const long long i = base + (half * kH + v) * kAgThreads + threadIdx.x;
+            key[v] = i < a.n ? __ldcs(a.key + i) : 0ull;
+            st[v] = i < a.n ? __ldcs(a.start + i) : 0;
+        }
+#pragma unroll
+        for (int v = 0; v < kH; ++v) {
+            const int u = half * kH + v;
+            const long long i = base + u * kAgThreads + threadIdx.x;
+            if (i >= a.n) continue;
+            const unsigned long long pk = repack(sp, key[v]);
+            const unsigned b = (unsigned)(pk >> sp.shift);
+            const unsigned rank = (rank2[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu;
+            const unsigned span = (unsigned)key[v] - 2u * (unsigned)st[v];      // c2 - 2 start = end - start
+            const ulonglong2 r = make_ulonglong2(pk, ((unsigned long long)span << 32) | (unsigned)i);
+            a.rec[s_ag[b] + rank] = r;
+            if (b > 0 && (pk & low_mask) <= a.window2) {           // inside the window of the bucket's lower boundary
+                const unsigned z = atomicAdd(&a.zone_n[b], 1u);
+                if (z < (unsigned)kZoneCap) a.zone[(size_t)b * kZoneCap + z] = r;
+                else a.meta->oversize = 1;
+            }
         }
     }
 }
