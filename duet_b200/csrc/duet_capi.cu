@@ -2,6 +2,7 @@
 // The library owns the stream, the join table and every scratch array; callers pass plain
 // column pointers.  No CPU fallback exists: every entry point needs a CUDA device.
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -625,7 +626,8 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     CU(h, h->d_oneps.reserve(S1 * 4));                   a.oneps = h->d_oneps.as<int>();
     CU(h, h->d_oneps_n.reserve((size_t)ns * 4));         a.oneps_n = h->d_oneps_n.as<int>();
     CU(h, h->d_sort.reserve(S1 * 32));                   a.sort_scratch = h->d_sort.as<long long>();
-    CU(h, h->d_c2.reserve(S1 * sizeof(C2Rec)));          a.c2rec = h->d_c2.as<C2Rec>();
+    a.c2_stride = (int)(offsetof(C2Rec, d) + (size_t)c2_cap(h->reduce_lanes) * sizeof(C2Ent));
+    CU(h, h->d_c2.reserve(S1 * (size_t)a.c2_stride + sizeof(C2Rec)));          a.c2rec = h->d_c2.as<C2Rec>();
 
     {
         size_t off[kOutCols], len[kOutCols], total;

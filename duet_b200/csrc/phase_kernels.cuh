@@ -66,7 +66,8 @@ struct PredictTile { int sv0, sv1, shard, b, n, pad[3]; };        // SVs [sv0, s
 struct BuildTile { int lo, hi, base, mask, bmo, bmw, pad[2]; };   // kThreads * U consecutive support reads: shards lo..hi
 struct ProbeTile { long long r0, r1; int shard, base, mask, bmo, bmw, pad; };   // rows [r0, r1) of ONE contig + its table / filter
 
-constexpr int kC2Max = 16;   // distinct PS per class-2 SV recorded by k_reduce (more -> warp fallback)
+constexpr int kC2Max = 32;   // distinct PS per class-2 SV a record can hold (k_reduce<G> fills up to c2_cap(G); more -> warp fallback)
+__host__ __device__ constexpr int c2_cap(int G) { return G == 32 ? 32 : 16; }     // dense batches (one warp per SV) keep 32, the others 16 (shared memory)
 struct C2Ent { int ps, tot, n1, n2; long long s1, s2; int bad, pad; };
 struct C2Rec { int n_d, overflow, pad[2]; C2Ent d[kC2Max]; };
 
@@ -127,7 +128,8 @@ struct PhaseArgs {
     long long *cand;             // [S] one-PS candidate or kNoCand
     int *oneps;                  // [S] shard s: sorted unique list at [sv_off[s], +oneps_n[s])
     int *oneps_n;                // [n_shards]
-    C2Rec *c2rec;                // [S] per-PS statistics of class-2 SVs (k_reduce -> k_predict)
+    C2Rec *c2rec;                // [S] per-PS statistics of class-2 SVs (k_reduce -> k_tail), c2_stride bytes apart:
+    int c2_stride;               //     a record holds the header and c2_cap(reduce lanes) entries, not all kC2Max
     long long *sort_scratch;     // [4*S] global tile for slow-path sorts of big shards
     uint8_t *gt, *cls;
     int *ps, *hap1, *hap2, *hap0, *allhap;
@@ -139,6 +141,10 @@ struct PhaseArgs {
     DevStatus *status;
     long long *dbg;              // optional per-block timestamps (duet_debug_timers), NULL in production
 };
+
+__device__ __forceinline__ C2Rec *c2_at(const PhaseArgs &a, int sv) {
+    return reinterpret_cast<C2Rec *>(reinterpret_cast<char *>(a.c2rec) + (size_t)sv * (size_t)a.c2_stride);
+}
 
 // ---- programmatic dependent launch: the kernels of one call are launched back to back with the
 // programmatic-serialization attribute, so a kernel's blocks are scheduled as soon as every block of its
@@ -799,16 +805,18 @@ __device__ __forceinline__ ReadTag load_tag(const PhaseArgs &a, int row) {
     return ReadTag{v.x, v.y, (unsigned)v.z, (unsigned)v.w};
 }
 
+template <int CAP>
 struct C2Group {                                   // shared-memory table of one lane group
-    int ps[kC2Max], tot[kC2Max], n1[kC2Max], n2[kC2Max], bad[kC2Max];
-    unsigned long long s1[kC2Max], s2[kC2Max];
+    int ps[CAP], tot[CAP], n1[CAP], n2[CAP], bad[CAP];
+    unsigned long long s1[CAP], s2[CAP];
 };
 
 // one step of the per-PS table: every lane of the group offers one read (q = qualifying)
-__device__ __forceinline__ void c2_update(C2Group &g, unsigned gmask, bool q, int ps, int pc, int hp, int &n_d) {
+template <int CAP>
+__device__ __forceinline__ void c2_update(C2Group<CAP> &g, unsigned gmask, bool q, int ps, int pc, int hp, int &n_d) {
     const int wl = threadIdx.x & 31;
     int id = -1;
-    const int known = min(n_d, kC2Max);
+    const int known = min(n_d, CAP);
     for (int k = 0; k < known; ++k)
         if (q && g.ps[k] == ps) id = k;
     const bool fresh = q && id < 0;
@@ -818,13 +826,13 @@ __device__ __forceinline__ void c2_update(C2Group &g, unsigned gmask, bool q, in
     const unsigned leaders = __ballot_sync(gmask, fresh && leader == wl) & gmask;
     if (fresh) {
         id = n_d + __popc(leaders & ((1u << leader) - 1u));
-        if (leader == wl && id < kC2Max) {
+        if (leader == wl && id < CAP) {
             g.ps[id] = ps; g.tot[id] = 0; g.n1[id] = 0; g.n2[id] = 0; g.bad[id] = 0; g.s1[id] = 0ull; g.s2[id] = 0ull;
         }
     }
     n_d += __popc(leaders);
     __syncwarp(gmask);
-    if (q && id < kC2Max) {
+    if (q && id < CAP) {
         atomicAdd(&g.tot[id], 1);
         if (hp == 1) { atomicAdd(&g.n1[id], 1); atomicAdd(&g.s1[id], (unsigned long long)(long long)pc); }
         else if (hp == 2) { atomicAdd(&g.n2[id], 1); atomicAdd(&g.s2[id], (unsigned long long)(long long)pc); }
@@ -838,7 +846,8 @@ __global__ void __launch_bounds__(kThreads, 6)
 k_reduce(PhaseArgs a) {
     constexpr int kReducePerBlock = kThreads / G;
     dbg_mark(a, 2, 0);
-    __shared__ C2Group s_c2[kReducePerBlock];
+    constexpr int kCap = c2_cap(G);
+    __shared__ C2Group<kCap> s_c2[kReducePerBlock];
     const int lane = threadIdx.x % G, grp = threadIdx.x / G;
     const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) / G * G));
     const int sv0 = blockIdx.x * kReducePerBlock;
@@ -924,7 +933,7 @@ k_reduce(PhaseArgs a) {
     if (live && lane < DUET_N_FEATURES) a.features[(size_t)lane * a.n_svs + sv] = 0.0;
 
     if (live && kept && cls == 2) {                  // group-uniform: per-PS statistics in read order
-        C2Group &g = s_c2[grp];
+        C2Group<kCap> &g = s_c2[grp];
         int n_d = 0;
         if (e - b <= G * kReduceUnroll) {            // the tags are still in registers
 #pragma unroll
@@ -947,9 +956,9 @@ k_reduce(PhaseArgs a) {
                     c2_update(g, gmask, row[u] >= 0 && pc[u] <= c_thr.pc_max, ps[u], pc[u], hp[u], n_d);
             }
         }
-        C2Rec *rec = a.c2rec + sv;
-        if (lane == 0) { rec->n_d = min(n_d, kC2Max); rec->overflow = n_d > kC2Max; }
-        for (int t = lane; t < min(n_d, kC2Max); t += G)
+        C2Rec *rec = c2_at(a, sv);
+        if (lane == 0) { rec->n_d = min(n_d, kCap); rec->overflow = n_d > kCap; }
+        for (int t = lane; t < min(n_d, kCap); t += G)
             rec->d[t] = C2Ent{g.ps[t], g.tot[t], g.n1[t], g.n2[t], (long long)g.s1[t], (long long)g.s2[t], g.bad[t], 0};
     }
 
@@ -1441,7 +1450,7 @@ k_predict(PhaseArgs a) {
             bool ready = true;
             if (cls == 0) st = Class2Stats{0, 0, 0, 0, 0, 0, 0};     // get_phase_info skips both loops
             if (cls == 2) {
-                const C2Rec *rec = a.c2rec + sv;
+                const C2Rec *rec = c2_at(a, sv);
                 const int allhap = st.allhap;
                 st = Class2Stats{0, 0, 0, allhap, 0, 0, 0};
                 if (rec->overflow) {
@@ -1652,7 +1661,7 @@ k_tail(PhaseArgs a, int n_set, int n_vals) {
         Class2Stats t = st[u];
         if (cls[u] == 0) t = Class2Stats{0, 0, 0, 0, 0, 0, 0};  // get_phase_info skips both loops
         if (cls[u] == 2) {
-            const C2Rec *rec = a.c2rec + sv;
+            const C2Rec *rec = c2_at(a, sv);
             const int allhap = t.allhap;
             t = Class2Stats{0, 0, 0, allhap, 0, 0, 0};
             if (rec->overflow) {                                 // > kC2Max phase sets: the warps take it together below

@@ -270,14 +270,16 @@ def test_tie_order_and_filters(engine):
     assert res.order.tolist() == [4, 2, 1, 3, 0]
 
 
-@pytest.mark.parametrize("n_ps", [5, 8, 9, 12, 16, 17, 33, 45])
-def test_many_phase_sets_in_one_sv(engine, n_ps):
-    """k_reduce records up to 8 distinct PS per SV; 9..32 take the warp-cooperative fallback with its
-    shared-memory list; beyond 32 the exact quadratic path runs.  All must agree with the oracle."""
+@pytest.mark.parametrize("n_ps,n_reads", [(5, 400), (8, 400), (9, 400), (12, 400), (16, 400), (17, 400), (33, 400), (45, 400),
+                                          (16, 4000), (17, 4000), (32, 4000), (33, 4000), (45, 4000)])
+def test_many_phase_sets_in_one_sv(engine, n_ps, n_reads):
+    """k_reduce records up to 16 distinct PS per SV (32 in dense batches, one warp per SV: the 4000-read cases);
+    more take the warp-cooperative fallback with its shared-memory list of 32; beyond that the exact quadratic
+    path runs.  All must agree with the oracle."""
     rng = np.random.default_rng(n_ps)
     pss = list(range(1000, 1000 + n_ps * 10, 10))
     reads, names = [], []
-    for k in range(400):
+    for k in range(n_reads):
         ps = int(rng.choice(pss)) if k >= n_ps else pss[k]
         reads.append((f"r{k}", int(rng.integers(1, 3)), ps, int(rng.integers(0, 9000))))
         names.append(f"r{k}")
