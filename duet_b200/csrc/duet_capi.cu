@@ -410,17 +410,21 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
 
     // CSR offsets at shard boundaries size the per-shard slot ranges
     std::vector<long long> join_off(ns + 1);
+    std::vector<long long> csr_host;
+    const long long *csr_view = nullptr;                          // csr_off as the host can read it
     if (in->mem == DUET_MEM_DEVICE) {
-        // the columns are resident: fetch just the ns+1 boundary values (one small strided copy)
-        std::vector<long long> csr_host((size_t)S + 1);
+        // the columns are resident: fetch the offsets (one small copy)
+        csr_host.resize((size_t)S + 1);
         CU(h, cudaMemcpyAsync(csr_host.data(), in->csr_off, (S + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
         CU(h, cudaStreamSynchronize(st));
         if (csr_host[0] != 0 || csr_host[S] != J) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: csr_off does not span csr_key");
         for (int s = 0; s <= ns; ++s) join_off[s] = csr_host[in->sv_off[s]];
+        csr_view = csr_host.data();
     } else {
         const long long *csr = reinterpret_cast<const long long *>(in->csr_off);
         if (csr[0] != 0 || csr[S] != J) return fail(h, DUET_ERR_INVALID, "duet_phase_upload: csr_off does not span csr_key");
         for (int s = 0; s <= ns; ++s) join_off[s] = csr[in->sv_off[s]];
+        csr_view = csr;
     }
     std::vector<int> tab_off(ns), tab_mask(ns), bm_off(ns), bm_wmask(ns);
     // slot table: 16-byte slots, load factor <= 1/4 while such a table (<= 8 slots of 16 B per name after
@@ -517,6 +521,12 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         return (int)(std::upper_bound(off.begin(), off.end(), x) - off.begin()) - 1;
     };
     h->reduce_lanes = (S > 0 && J / std::max<long long>(S, 1) > 32) ? kReduceLanesDense : kReduceLanesSparse;
+    // dense callsets have a heavy tail (support lists of a thousand reads beside a median of forty): those SVs get a
+    // block of their own in k_reduce_heavy instead of one warp of k_reduce
+    std::vector<int> heavy_sv;
+    if (h->reduce_lanes == kReduceLanesDense && csr_view)
+        for (long long i = 0; i < S; ++i)
+            if (csr_view[i + 1] - csr_view[i] > kHeavyReads) heavy_sv.push_back((int)i);
     // the per-contig steps: one cluster per contig (k_tail) when every contig fits one
     h->tail_fused = max_sv <= kTailMaxSvs && !(h->flags & kFlagSplitTail);
     h->tail_set = (int)pow2_at_least(std::max<long long>(2 * max_sv, kTailMinSet));
@@ -589,7 +599,7 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         Arena ar;
         const size_t o_read = ar.put(h->h_read_off), o_sv = ar.put(h->h_sv_off), o_join = ar.put(join_off);
         const size_t o_toff = ar.put(tab_off), o_tmask = ar.put(tab_mask), o_boff = ar.put(bm_off), o_bmask = ar.put(bm_wmask);
-        const size_t o_bt = ar.put(btiles), o_pt = ar.put(ptiles), o_qt = ar.put(qtiles);
+        const size_t o_bt = ar.put(btiles), o_pt = ar.put(ptiles), o_qt = ar.put(qtiles), o_hv = ar.put(heavy_sv);
         if (h->desc_in_flight) CU(h, cudaEventSynchronize(h->ev[EV_DESC]));      // the previous copy out of h_desc is over
         CU(h, h->h_desc.reserve(ar.bytes.size()));
         CU(h, h->d_desc.reserve(ar.bytes.size()));
@@ -608,6 +618,8 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
         a.predict_tiles = reinterpret_cast<const PredictTile *>(d + o_pt);
         a.build_tiles = reinterpret_cast<const BuildTile *>(d + o_bt);
         a.probe_tiles = reinterpret_cast<const ProbeTile *>(d + o_qt);
+        a.heavy_sv = heavy_sv.empty() ? nullptr : reinterpret_cast<const int *>(d + o_hv);
+        a.n_heavy = (int)heavy_sv.size();
     }
     CU(h, cudaEventRecord(h->ev[EV_H2D1], st));
     h->have_h2d = true;
@@ -721,6 +733,7 @@ static int launch_all(duet_handle *h, cudaStream_t st, bool marks) {
         if (h->reduce_lanes == kReduceLanesDense) launch(k_reduce<kReduceLanesDense>, (S + per - 1) / per, kThreads, 0, st, pdl && join, false, a);
         else launch(k_reduce<kReduceLanesSparse>, (S + per - 1) / per, kThreads, 0, st, pdl && join, false, a);
         ++n;
+        if (a.n_heavy > 0) { launch(k_reduce_heavy, a.n_heavy, kThreads, 0, st, pdl, false, a); ++n; }
     }
     mark(EV_K3);
     if (S && h->tail_fused) {
@@ -777,7 +790,8 @@ int duet_phase_execute(duet_handle *h, int per_kernel) {
             CU(h, cudaGraphLaunch(h->graph_exec, st));
             const PhaseArgs &a = h->a;
             const bool probe = a.n_reads && a.n_joins;
-            n_graph = (a.n_joins ? 2 : 0) + (probe ? ((a.flags & kFlagTwoBranch) ? 3 : 1) : 0) + (a.n_svs ? (h->tail_fused ? 2 : 4) : 0);
+            n_graph = (a.n_joins ? 2 : 0) + (probe ? ((a.flags & kFlagTwoBranch) ? 3 : 1) : 0) + (a.n_svs ? (h->tail_fused ? 2 : 4) : 0) +
+                      (a.n_svs && a.n_heavy > 0 ? 1 : 0);
             h->launches += n_graph;
         } else {
             h->launches += launch_all(h, st, false);

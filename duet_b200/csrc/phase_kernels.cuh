@@ -130,6 +130,8 @@ struct PhaseArgs {
     int *oneps_n;                // [n_shards]
     C2Rec *c2rec;                // [S] per-PS statistics of class-2 SVs (k_reduce -> k_tail), c2_stride bytes apart:
     int c2_stride;               //     a record holds the header and c2_cap(reduce lanes) entries, not all kC2Max
+    const int *heavy_sv;         // dense batches: the SVs with more than kHeavyReads support reads (k_reduce_heavy), or NULL
+    int n_heavy;
     long long *sort_scratch;     // [4*S] global tile for slow-path sorts of big shards
     uint8_t *gt, *cls;
     int *ps, *hap1, *hap2, *hap0, *allhap;
@@ -799,6 +801,7 @@ __device__ __forceinline__ void oneps_any(const PhaseArgs &a, int s, long long *
 // Dependent chain: csr_off -> join_row -> tags -> (shuffles) -> stores -> credit.
 // ------------------------------------------------------------------------------------------
 constexpr int kReduceUnroll = 4;
+constexpr int kHeavyReads = 512;                    // dense batches: longer support lists go to k_reduce_heavy
 
 __device__ __forceinline__ ReadTag load_tag(const PhaseArgs &a, int row) {
     const int4 v = __ldg(reinterpret_cast<const int4 *>(a.read_tag + row));
@@ -862,6 +865,9 @@ k_reduce(PhaseArgs a) {
                __ldg(a.sv_svread + sv) >= c_thr.suppread_thres &&
                !(__ldg(a.sv_flags + sv) & DUET_SV_GT_MISSING);
     }
+    // dense batches: a support list of a thousand reads would keep this one warp busy long after the rest of the grid
+    // is done -- such SVs are left to k_reduce_heavy, eight warps each
+    const bool skip = G == 32 && a.heavy_sv != nullptr && e - b > kHeavyReads;
     pdl_trigger();
     pdl_wait();                                                  // the join rows are final
     {   // every reader of the Bloom filter is done: hand it back zeroed, so that the next call's filter bits can be
@@ -870,6 +876,7 @@ k_reduce(PhaseArgs a) {
         const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
         for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.n_bm_words / 4; i += (long long)gridDim.x * kThreads) bm[i] = zero;
     }
+    if (skip) return;                                            // (G == 32: the whole warp)
     int hits = 0, ps_lo = INT32_MAX, ps_hi = INT32_MIN;
     int h1 = 0, h2 = 0, nq = 0;
     long long t1 = 0, t2 = 0;
@@ -963,6 +970,152 @@ k_reduce(PhaseArgs a) {
     }
 
     dbg_mark(a, 2, 2);
+}
+
+// k_reduce_heavy (dense batches): ONE BLOCK per SV with more than kHeavyReads support reads.  The list is cut into
+// eight contiguous stretches of whole 128-read batches, one per warp; every warp does what a k_reduce<32> warp does on
+// its stretch -- the order-free statistics first, then (class 2) its own per-PS table in first-seen order --, and
+// warp 0 puts the pieces together IN STRETCH ORDER, which is read order: the sums and extrema combine freely, the first
+// qualifying read is the smallest index, and a phase set's place in the merged table is where the first stretch that saw
+// it put it.  Same outputs as k_reduce, bit for bit.
+struct HeavyPart { int hits, ps_lo, ps_hi, h1, h2, nq, n_d, first_q_ps; long long t1, t2, first_q; };
+
+__global__ void __launch_bounds__(kThreads)
+k_reduce_heavy(PhaseArgs a) {
+    constexpr int G = 32, W = kThreads / 32, kCap = c2_cap(32);
+    __shared__ C2Group<kCap> s_c2[W];
+    __shared__ C2Group<kCap> s_m;                                // the merged table
+    __shared__ HeavyPart s_part[W];
+    const int sv = a.heavy_sv[blockIdx.x];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned gmask = 0xffffffffu;
+    const long long b = __ldg(a.csr_off + sv), e = __ldg(a.csr_off + sv + 1);
+    const bool kept = __ldg(a.sv_svlen + sv) >= c_thr.svlen_thres && __ldg(a.sv_svread + sv) >= c_thr.suppread_thres &&
+                      !(__ldg(a.sv_flags + sv) & DUET_SV_GT_MISSING);
+    constexpr int kBatch = G * kReduceUnroll;
+    const long long n_batches = (e - b + kBatch - 1) / kBatch, per = (n_batches + W - 1) / W;
+    const long long wb = min(e, b + (long long)w * per * kBatch), we = min(e, wb + per * kBatch);
+    pdl_trigger();
+    pdl_wait();                                                  // the join rows are final
+    int hits = 0, ps_lo = INT32_MAX, ps_hi = INT32_MIN, h1 = 0, h2 = 0, nq = 0, first_q_ps = 0;
+    long long t1 = 0, t2 = 0, first_q = INT64_MAX;
+    int row[kReduceUnroll], ps[kReduceUnroll], pc[kReduceUnroll], hp[kReduceUnroll];
+    for (long long base = wb; base < we; base += kBatch) {
+        unsigned want[kReduceUnroll];
+#pragma unroll
+        for (int u = 0; u < kReduceUnroll; ++u) {
+            const long long j = base + u * G + lane;
+            row[u] = j < we ? __ldcg(a.join_row + j) : -1;
+            want[u] = j < we && a.csr_chk ? __ldg(a.csr_chk + j) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kReduceUnroll; ++u) {
+            ps[u] = pc[u] = hp[u] = 0;
+            if (row[u] >= 0) {
+                const ReadTag t = load_tag(a, row[u]);
+                ps[u] = t.ps; pc[u] = t.pc; hp[u] = (int)(t.hp & 0xffu);
+                if (a.csr_chk && t.chk != want[u])
+                    report(a.status, DUET_ERR_HASH_COLLISION, sv, (long long)__ldg(a.csr_key + base + u * G + lane));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kReduceUnroll; ++u) {
+            if (row[u] < 0) continue;
+            ++hits;
+            ps_lo = min(ps_lo, ps[u]);
+            ps_hi = max(ps_hi, ps[u]);
+            if (pc[u] <= c_thr.pc_max) {
+                ++nq;
+                const long long j = base + u * G + lane;
+                if (j < first_q) { first_q = j; first_q_ps = ps[u]; }
+                if (hp[u] == 1) { ++h1; t1 += pc[u]; }
+                else if (hp[u] == 2) { ++h2; t2 += pc[u]; }
+            }
+        }
+    }
+    hits = group_sum(hits, gmask, G);
+    ps_lo = group_min(ps_lo, gmask, G);
+    ps_hi = group_max(ps_hi, gmask, G);
+    h1 = group_sum(h1, gmask, G); h2 = group_sum(h2, gmask, G); nq = group_sum(nq, gmask, G);
+    t1 = group_sum(t1, gmask, G); t2 = group_sum(t2, gmask, G);
+    {
+        const long long fq = group_min(first_q, gmask, G);
+        const unsigned owner = __ballot_sync(gmask, first_q == fq && fq != INT64_MAX);
+        const int fps = __shfl_sync(gmask, first_q_ps, owner ? __ffs(owner) - 1 : 0);
+        if (lane == 0) s_part[w] = HeavyPart{hits, ps_lo, ps_hi, h1, h2, nq, 0, fps, t1, t2, fq};
+    }
+    __syncthreads();
+    // every thread puts the eight pieces together (cheap, and the class is needed by all)
+    hits = 0; ps_lo = INT32_MAX; ps_hi = INT32_MIN; h1 = h2 = nq = 0; t1 = t2 = 0; first_q = INT64_MAX; first_q_ps = 0;
+    for (int k = 0; k < W; ++k) {
+        const HeavyPart p = s_part[k];
+        hits += p.hits; ps_lo = min(ps_lo, p.ps_lo); ps_hi = max(ps_hi, p.ps_hi);
+        h1 += p.h1; h2 += p.h2; nq += p.nq; t1 += p.t1; t2 += p.t2;
+        if (p.first_q < first_q) { first_q = p.first_q; first_q_ps = p.first_q_ps; }
+    }
+    const bool owner = first_q != INT64_MAX;
+    const int cls = hits == 0 ? 0 : (ps_lo == ps_hi ? 1 : 2);
+    if (threadIdx.x == 0) {
+        a.n_hit[sv] = hits;
+        a.cls[sv] = kept ? (uint8_t)cls : (uint8_t)DUET_CLS_FILTERED;
+        a.gt[sv] = 0;
+        a.cand[sv] = (kept && cls == 1 && owner) ? (long long)first_q_ps : kNoCand;
+        a.hap1[sv] = h1; a.hap2[sv] = h2; a.hap0[sv] = 0;
+        a.allhap[sv] = cls == 2 ? nq : h1 + h2;
+        a.totsc1[sv] = t1; a.totsc2[sv] = t2;
+        a.ps[sv] = owner ? ps_lo : 0;
+    }
+    if (threadIdx.x < DUET_N_FEATURES) a.features[(size_t)threadIdx.x * a.n_svs + sv] = 0.0;
+    if (!(kept && cls == 2)) return;                             // block-uniform
+
+    // per-PS statistics: every warp its own table over its stretch, in read order
+    C2Group<kCap> &g = s_c2[w];
+    int n_d = 0;
+    for (long long base = wb; base < we; base += kBatch) {
+#pragma unroll
+        for (int u = 0; u < kReduceUnroll; ++u) {
+            const long long j = base + u * G + lane;
+            row[u] = j < we ? __ldcg(a.join_row + j) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < kReduceUnroll; ++u) {
+            ps[u] = pc[u] = hp[u] = 0;
+            if (row[u] >= 0) { const ReadTag t = load_tag(a, row[u]); ps[u] = t.ps; pc[u] = t.pc; hp[u] = (int)(t.hp & 0xffu); }
+        }
+#pragma unroll
+        for (int u = 0; u < kReduceUnroll; ++u)                  // u-major == read order
+            c2_update(g, gmask, row[u] >= 0 && pc[u] <= c_thr.pc_max, ps[u], pc[u], hp[u], n_d);
+    }
+    if (lane == 0) s_part[w].n_d = n_d;
+    __syncthreads();
+    if (w != 0) return;
+    // warp 0: the tables one after the other; lane t looks after merged entry t
+    int m = 0;
+    bool over = false;
+    for (int k = 0; k < W; ++k) {
+        const int nk = s_part[k].n_d;
+        over |= nk > kCap;
+        for (int t = 0; t < min(nk, kCap); ++t) {
+            const int psv = s_c2[k].ps[t];
+            const unsigned hit = __ballot_sync(gmask, lane < m && s_m.ps[lane] == psv);
+            int id = hit ? __ffs(hit) - 1 : m;
+            if (!hit) {
+                if (m == kCap) { over = true; continue; }
+                if (lane == 0) { s_m.ps[m] = psv; s_m.tot[m] = 0; s_m.n1[m] = 0; s_m.n2[m] = 0; s_m.bad[m] = 0; s_m.s1[m] = 0ull; s_m.s2[m] = 0ull; }
+                ++m;
+            }
+            if (lane == 0) {
+                s_m.tot[id] += s_c2[k].tot[t]; s_m.n1[id] += s_c2[k].n1[t]; s_m.n2[id] += s_c2[k].n2[t];
+                s_m.s1[id] += s_c2[k].s1[t]; s_m.s2[id] += s_c2[k].s2[t];
+                if (!s_m.bad[id]) s_m.bad[id] = s_c2[k].bad[t];
+            }
+            __syncwarp();
+        }
+    }
+    C2Rec *rec = c2_at(a, sv);
+    if (lane == 0) { rec->n_d = m; rec->overflow = over; }
+    if (lane < m)
+        rec->d[lane] = C2Ent{s_m.ps[lane], s_m.tot[lane], s_m.n1[lane], s_m.n2[lane], (long long)s_m.s1[lane], (long long)s_m.s2[lane], s_m.bad[lane], 0};
 }
 
 // k_oneps: one block per shard -- the contig's sorted unique one-PS list (:107) from the candidates

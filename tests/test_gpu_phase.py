@@ -169,10 +169,13 @@ def test_two_branch_chain_equals_serial_chain(engine, monkeypatch):
             batch = from_synth(s)
             want = engine.run(batch)
             for _ in range(3):
+                before = forced.launch_count()
                 got = forced.run(batch)
                 for name in keys:
                     assert np.array_equal(getattr(want, name), getattr(got, name)), name
-            assert forced.launch_count() % 7 == 0                # k_init, k_table, k_bloom, k_stream, k_resolve, k_reduce, k_tail
+                # k_init, k_table, k_bloom, k_stream, k_resolve, k_reduce, k_tail (+ k_reduce_heavy when a dense batch
+                # has support lists of more than 512 reads)
+                assert forced.launch_count() - before in ((7, 8) if k == 3 else (7,))
     finally:
         forced.close()
 
