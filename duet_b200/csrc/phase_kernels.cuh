@@ -801,7 +801,7 @@ __device__ __forceinline__ void oneps_any(const PhaseArgs &a, int s, long long *
 // Dependent chain: csr_off -> join_row -> tags -> (shuffles) -> stores -> credit.
 // ------------------------------------------------------------------------------------------
 constexpr int kReduceUnroll = 4;
-constexpr int kHeavyReads = 512;                    // dense batches: longer support lists go to k_reduce_heavy
+constexpr int kHeavyReads = 256;                    // dense batches: longer support lists go to k_reduce_heavy
 
 __device__ __forceinline__ ReadTag load_tag(const PhaseArgs &a, int row) {
     const int4 v = __ldg(reinterpret_cast<const int4 *>(a.read_tag + row));

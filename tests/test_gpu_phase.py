@@ -174,7 +174,7 @@ def test_two_branch_chain_equals_serial_chain(engine, monkeypatch):
                 for name in keys:
                     assert np.array_equal(getattr(want, name), getattr(got, name)), name
                 # k_init, k_table, k_bloom, k_stream, k_resolve, k_reduce, k_tail (+ k_reduce_heavy when a dense batch
-                # has support lists of more than 512 reads)
+                # has support lists of more than 256 reads)
                 assert forced.launch_count() - before in ((7, 8) if k == 3 else (7,))
     finally:
         forced.close()
