@@ -978,7 +978,7 @@ k_reduce(PhaseArgs a) {
 // warp 0 puts the pieces together IN STRETCH ORDER, which is read order: the sums and extrema combine freely, the first
 // qualifying read is the smallest index, and a phase set's place in the merged table is where the first stretch that saw
 // it put it.  Same outputs as k_reduce, bit for bit.
-struct HeavyPart { int hits, ps_lo, ps_hi, h1, h2, nq, n_d, first_q_ps; long long t1, t2, first_q; };
+struct HeavyPart { int hits, ps_lo, ps_hi, h1, h2, nq, first_q_ps, pad; long long t1, t2, first_q; };
 
 __global__ void __launch_bounds__(kThreads)
 k_reduce_heavy(PhaseArgs a) {
@@ -986,6 +986,7 @@ k_reduce_heavy(PhaseArgs a) {
     __shared__ C2Group<kCap> s_c2[W];
     __shared__ C2Group<kCap> s_m;                                // the merged table
     __shared__ HeavyPart s_part[W];
+    __shared__ int s_nd[W];                                      // distinct phase sets each warp saw (its own word: the pieces above are still being read)
     const int sv = a.heavy_sv[blockIdx.x];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned gmask = 0xffffffffu;
@@ -1042,7 +1043,7 @@ k_reduce_heavy(PhaseArgs a) {
         const long long fq = group_min(first_q, gmask, G);
         const unsigned owner = __ballot_sync(gmask, first_q == fq && fq != INT64_MAX);
         const int fps = __shfl_sync(gmask, first_q_ps, owner ? __ffs(owner) - 1 : 0);
-        if (lane == 0) s_part[w] = HeavyPart{hits, ps_lo, ps_hi, h1, h2, nq, 0, fps, t1, t2, fq};
+        if (lane == 0) s_part[w] = HeavyPart{hits, ps_lo, ps_hi, h1, h2, nq, fps, 0, t1, t2, fq};
     }
     __syncthreads();
     // every thread puts the eight pieces together (cheap, and the class is needed by all)
@@ -1086,14 +1087,14 @@ k_reduce_heavy(PhaseArgs a) {
         for (int u = 0; u < kReduceUnroll; ++u)                  // u-major == read order
             c2_update(g, gmask, row[u] >= 0 && pc[u] <= c_thr.pc_max, ps[u], pc[u], hp[u], n_d);
     }
-    if (lane == 0) s_part[w].n_d = n_d;
+    if (lane == 0) s_nd[w] = n_d;
     __syncthreads();
     if (w != 0) return;
     // warp 0: the tables one after the other; lane t looks after merged entry t
     int m = 0;
     bool over = false;
     for (int k = 0; k < W; ++k) {
-        const int nk = s_part[k].n_d;
+        const int nk = s_nd[k];
         over |= nk > kCap;
         for (int t = 0; t < min(nk, kCap); ++t) {
             const int psv = s_c2[k].ps[t];
