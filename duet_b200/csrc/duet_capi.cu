@@ -3,6 +3,7 @@
 // column pointers.  No CPU fallback exists: every entry point needs a CUDA device.
 #include <algorithm>
 #include <cstddef>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1000,6 +1001,16 @@ static int cluster_fast(duet_handle *h, const ClusterArgs &g, ClMeta *meta, bool
         // (two stamps with nothing between them: what a stamp itself costs, to be subtracted from every phase)
         static const char *const kPh[10] = {"wait for the block", "records + cell counts", "(a stamp's own cost)", "cell starts", "grouped by cell",
                                             "ranked inside cells", "runs", "window scan", "minima", "output"};
+        {
+            long long s0 = INT64_MAX, s1 = 0, e0 = INT64_MAX, e1 = 0;
+            for (int b = 0; b < bucket_grid; ++b) {
+                const long long st0 = d[(size_t)b * 12 + 10], en0 = d[(size_t)b * 12 + 11];
+                if (!st0 || !en0) continue;
+                s0 = std::min(s0, st0); s1 = std::max(s1, st0); e0 = std::min(e0, en0); e1 = std::max(e1, en0);
+            }
+            std::fprintf(stderr, "k_cl_bucket blocks start within %.1f us, the first is done after %.1f us, the last after %.1f us\n",
+                         (s1 - s0) * 1e-3, (e0 - s0) * 1e-3, (e1 - s0) * 1e-3);
+        }
         for (int k = 0; k < 10; ++k) {
             double sum = 0; long long mx = 0;
             for (int b = 0; b < bucket_grid; ++b) { sum += (double)d[(size_t)b * 12 + k]; mx = std::max(mx, d[(size_t)b * 12 + k]); }
