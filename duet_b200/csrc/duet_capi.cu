@@ -528,6 +528,8 @@ int duet_phase_upload(duet_handle *h, const duet_phase_input *in) {
     if (h->reduce_lanes == kReduceLanesDense && csr_view)
         for (long long i = 0; i < S; ++i)
             if (csr_view[i + 1] - csr_view[i] > kHeavyReads) heavy_sv.push_back((int)i);
+    std::stable_sort(heavy_sv.begin(), heavy_sv.end(),            // longest first: the kernel should not end on its longest lists
+                     [&](int x, int y) { return csr_view[x + 1] - csr_view[x] > csr_view[y + 1] - csr_view[y]; });
     // the per-contig steps: one cluster per contig (k_tail) when every contig fits one
     h->tail_fused = max_sv <= kTailMaxSvs && !(h->flags & kFlagSplitTail);
     h->tail_set = (int)pow2_at_least(std::max<long long>(2 * max_sv, kTailMinSet));
